@@ -1,0 +1,132 @@
+// C-ABI entry points for the convolutions: choose a kernel family, pack weights, own the plan.
+#include <new>
+
+#include "common.cuh"
+
+namespace diqt {
+struct TcPlan;
+int simt_taps(int mode);
+int conv_simt_pack(const diqt_conv_desc* d, const float* w, void* packed, cudaStream_t st);
+int conv_simt_run(const diqt_conv_desc* d, const void* in, void* out, const void* packed, const float* bias, cudaStream_t st);
+int conv_bias_permute_up(const float* b, int c_out, float* out, cudaStream_t st);
+bool conv_tc_supported(const diqt_conv_desc* d);
+size_t conv_tc_packed_bytes(const diqt_conv_desc* d);
+int conv_tc_pack(const diqt_conv_desc* d, const float* w, void* packed, cudaStream_t st);
+int conv_tc_plan(const diqt_conv_desc* d, const void* in, void* out, const void* packed, const float* bias, TcPlan** plan);
+int conv_tc_run(const TcPlan* plan, cudaStream_t st);
+void conv_tc_destroy(TcPlan* plan);
+}  // namespace diqt
+
+using namespace diqt;
+
+struct diqt_conv_plan {
+  diqt_conv_desc d;
+  int impl;
+  const void* in;
+  void* out;
+  const void* packed;
+  const float* bias;
+  TcPlan* tc;
+};
+
+static int check_desc(const diqt_conv_desc* d) {
+  DIQT_REQUIRE(d, "conv: null descriptor");
+  DIQT_REQUIRE(d->mode >= DIQT_CONV_K3 && d->mode <= DIQT_CONV_UP, "conv: bad mode %d", d->mode);
+  DIQT_REQUIRE(d->dtype == DIQT_F32 || d->dtype == DIQT_BF16, "conv: bad dtype %d", d->dtype);
+  DIQT_REQUIRE(d->n > 0 && d->d0 > 0 && d->d1 > 0 && d->d2 > 0 && d->c_in > 0 && d->c_out > 0, "conv: non-positive dimension");
+  DIQT_REQUIRE(d->ld_in >= d->c_in, "conv: ld_in=%d < c_in=%d", d->ld_in, d->c_in);
+  if (d->mode == DIQT_CONV_UP) {
+    DIQT_REQUIRE(d->c_out % 8 == 0 && d->ld_out >= d->c_out / 8, "conv(up): c_out=%d ld_out=%d", d->c_out, d->ld_out);
+  } else {
+    DIQT_REQUIRE(d->ld_out >= d->c_out, "conv: ld_out=%d < c_out=%d", d->ld_out, d->c_out);
+  }
+  return DIQT_OK;
+}
+
+static int resolve_impl(const diqt_conv_desc* d, int* impl) {
+  int want = d->impl;
+  if (want == DIQT_IMPL_AUTO) want = conv_tc_supported(d) ? DIQT_IMPL_TC : DIQT_IMPL_SIMT;
+  if (want == DIQT_IMPL_TC && !conv_tc_supported(d)) {
+    set_error("conv: tcgen05 kernel does not take dtype=%d c_in=%d c_out=%d ld_in=%d ld_out=%d", d->dtype, d->c_in, d->c_out,
+              d->ld_in, d->ld_out);
+    return DIQT_EUNSUPPORTED;
+  }
+  if (want != DIQT_IMPL_TC && want != DIQT_IMPL_SIMT) {
+    set_error("conv: bad impl %d", d->impl);
+    return DIQT_EINVAL;
+  }
+  *impl = want;
+  return DIQT_OK;
+}
+
+extern "C" int diqt_conv_resolved_impl(const diqt_conv_desc* d, int* impl) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  return resolve_impl(d, impl);
+}
+
+extern "C" int diqt_conv_packed_bytes(const diqt_conv_desc* d, size_t* bytes) {
+  int rc = check_desc(d), impl = 0;
+  if (rc) return rc;
+  if ((rc = resolve_impl(d, &impl))) return rc;
+  DIQT_REQUIRE(bytes, "conv_packed_bytes: null output");
+  *bytes = impl == DIQT_IMPL_TC ? conv_tc_packed_bytes(d) : (size_t)simt_taps(d->mode) * d->c_in * d->c_out * sizeof(float);
+  return DIQT_OK;
+}
+
+extern "C" int diqt_conv_pack(const diqt_conv_desc* d, const float* w, const float* bias, void* packed_w, float* packed_bias,
+                              void* stream) {
+  int rc = check_desc(d), impl = 0;
+  if (rc) return rc;
+  if ((rc = resolve_impl(d, &impl))) return rc;
+  DIQT_REQUIRE(w && packed_w && packed_bias, "conv_pack: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = impl == DIQT_IMPL_TC ? conv_tc_pack(d, w, packed_w, st) : conv_simt_pack(d, w, packed_w, st);
+  if (rc) return rc;
+  if (!bias) {
+    DIQT_CUDA(cudaMemsetAsync(packed_bias, 0, sizeof(float) * d->c_out, st));
+    return DIQT_OK;
+  }
+  if (d->mode == DIQT_CONV_UP) return conv_bias_permute_up(bias, d->c_out, packed_bias, st);
+  DIQT_CUDA(cudaMemcpyAsync(packed_bias, bias, sizeof(float) * d->c_out, cudaMemcpyDeviceToDevice, st));
+  return DIQT_OK;
+}
+
+extern "C" int diqt_conv_plan_create(const diqt_conv_desc* d, const void* in, void* out, const void* packed_w,
+                                     const float* packed_bias, diqt_conv_plan** plan) {
+  int rc = check_desc(d), impl = 0;
+  if (rc) return rc;
+  if ((rc = resolve_impl(d, &impl))) return rc;
+  DIQT_REQUIRE(in && out && packed_w && packed_bias && plan, "conv_plan_create: null pointer");
+  diqt_conv_plan* pl = new (std::nothrow) diqt_conv_plan();
+  DIQT_REQUIRE(pl, "conv_plan_create: out of host memory");
+  pl->d = *d;
+  pl->impl = impl;
+  pl->in = in;
+  pl->out = out;
+  pl->packed = packed_w;
+  pl->bias = packed_bias;
+  pl->tc = nullptr;
+  if (impl == DIQT_IMPL_TC) {
+    rc = conv_tc_plan(d, in, out, packed_w, packed_bias, &pl->tc);
+    if (rc) {
+      delete pl;
+      return rc;
+    }
+  }
+  *plan = pl;
+  return DIQT_OK;
+}
+
+extern "C" void diqt_conv_plan_destroy(diqt_conv_plan* plan) {
+  if (!plan) return;
+  if (plan->tc) conv_tc_destroy(plan->tc);
+  delete plan;
+}
+
+extern "C" int diqt_conv_run(const diqt_conv_plan* plan, void* stream) {
+  DIQT_REQUIRE(plan, "conv_run: null plan");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (plan->impl == DIQT_IMPL_TC) return conv_tc_run(plan->tc, st);
+  return conv_simt_run(&plan->d, plan->in, plan->out, plan->packed, plan->bias, st);
+}

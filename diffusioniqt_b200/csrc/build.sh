@@ -1,0 +1,22 @@
+#!/bin/bash
+# Build libdiqt_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/../libdiqt_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -Wall --expt-relaxed-constexpr)
+[ -n "${DIQT_PTXAS_V:-}" ] && FLAGS+=(-Xptxas -v)
+mkdir -p "$HERE/../../build"
+OBJS=()
+PIDS=()
+for f in elementwise ends conv_simt conv_tc api; do
+  o="$HERE/../../build/$f.o"
+  if [ ! -f "$o" ] || [ "$HERE/$f.cu" -nt "$o" ] || [ "$HERE/common.cuh" -nt "$o" ] || [ "$HERE/../../include/diqt.h" -nt "$o" ] || [ -n "${DIQT_PTXAS_V:-}" ]; then
+    "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$o" &
+    PIDS+=($!)
+  fi
+  OBJS+=("$o")
+done
+for p in "${PIDS[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+"$NVCC" -shared -o "$OUT" "${OBJS[@]}" -lcudart
+echo "built $OUT"

@@ -1,0 +1,528 @@
+// tcgen05 implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulation in TMEM).
+//
+// Replaces nn.Conv3d at imagen_pytorch3D.py:551-553 (3x3x3), :597 / :1388 (1x1x1), :495
+// (pixel-unshuffle + 1x1x1) and :467 (+ Mish + PixelShuffle3D, :416-439) when channel counts are
+// multiples of 64.
+//
+// GEMM view.  M tile = 128 output voxels forming a box (bx,by,bz,bn) of the channels-last volume,
+// N tile = block_n <= 256 output channels, K = taps x c_in walked in K-blocks of 64 channels of
+// one tap.  For every K-block
+//   A [128 voxels x 64 ch] is ONE 5-D TMA box load of the input volume at the tap-shifted
+//     coordinate; out-of-volume voxels are zero-filled by TMA, which IS the conv's zero padding;
+//     the box lands in shared memory as 128 rows of 128 bytes in the 128B-swizzle K-major layout
+//     tcgen05.mma wants;
+//   B [block_n x 64] is one bulk copy of weights pre-swizzled at pack time.
+// One elected thread issues 4 tcgen05.mma (K=16 each) per K-block into a TMEM accumulator;
+// accumulators are double buffered so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Epilogue warps read TMEM (tcgen05.ld), add bias, (UP: Mish), round to bf16, stage the tile in
+// swizzled shared memory and write it with TMA stores - for UP through per-sub-position tensor
+// maps so that PixelShuffle3D is folded into the store coordinates; for DOWN the pixel-unshuffle
+// is folded into per-tap load tensor maps.
+//
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 epilogue.
+#include <cuda.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace diqt {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzle shared-memory matrix descriptor (rows of 128 B, 8-row atoms 1024 B apart).
+// Field layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor (InstrDescriptor in mma_sm100_desc.hpp): D=f32, A=B=bf16, both K-major.
+__host__ __device__ inline uint32_t make_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+constexpr int kTileM = 128;
+constexpr int kABytes = kTileM * 128;  // one A stage: 128 rows x 64 bf16
+constexpr int kMaxMaps = 8;
+constexpr int kThreads = 192;
+
+struct TcParams {
+  CUtensorMap in_map[kMaxMaps];
+  CUtensorMap out_map[kMaxMaps];
+  const uint8_t* w;   // [n_tile][kblock][block_n][128 B], pre-swizzled
+  const float* bias;  // GEMM column order, n_tiles * block_n entries
+  int mode, taps, kchunks;
+  int block_n, n_tiles;
+  int up_c;  // UP: channels stored per sub-position
+  int bx, by, bz, bn;
+  int tiles_x, tiles_y, tiles_z, tiles_n, m_tiles;
+  int stages;
+  uint32_t idesc;
+  uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve-up: [stages x (A | B)] [out staging block_n/64 x 16 KB] [bias] [barriers] [tmem ptr]
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int b_bytes = p.block_n * 128;
+  const int stage_bytes = kABytes + b_bytes;
+  uint8_t* stage_base = smem;
+  uint8_t* out_stage = stage_base + (size_t)p.stages * stage_bytes;
+  float* s_bias = reinterpret_cast<float*>(out_stage + (size_t)(p.block_n / 64) * kABytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + p.n_tiles * p.block_n);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + p.stages;
+  uint64_t* tfull_bar = bars + 2 * p.stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = p.taps * p.kchunks;
+  const int total_work = p.m_tiles * p.n_tiles;
+
+  for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += blockDim.x) s_bias[i] = p.bias[i];
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&tfull_bar[a]), 1);
+      mbar_init(smem_u32(&tempty_bar[a]), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode_tile = [&](int work, int& n_tile, int& x0, int& y0, int& z0, int& b0) {
+    n_tile = work % p.n_tiles;
+    int m = work / p.n_tiles;
+    const int tx = m % p.tiles_x; m /= p.tiles_x;
+    const int ty = m % p.tiles_y; m /= p.tiles_y;
+    const int tz = m % p.tiles_z; m /= p.tiles_z;
+    x0 = tx * p.bx; y0 = ty * p.by; z0 = tz * p.bz; b0 = m * p.bn;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        int n_tile, x0, y0, z0, b0;
+        decode_tile(work, n_tile, x0, y0, z0, b0);
+        const uint8_t* wsrc = p.w + (size_t)n_tile * kblocks * b_bytes;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int t = kb / p.kchunks, q = kb - t * p.kchunks;
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t bar = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(bar, (uint32_t)stage_bytes);
+          uint8_t* a_dst = stage_base + (size_t)stage * stage_bytes;
+          int dx = 0, dy = 0, dz = 0, mi = 0;
+          if (p.mode == DIQT_CONV_K3) { dz = t / 9 - 1; dy = (t / 3) % 3 - 1; dx = t % 3 - 1; }
+          else if (p.mode == DIQT_CONV_DOWN) { mi = t; }
+          tma_load_5d(smem_u32(a_dst), &p.in_map[mi], bar, q * 64, x0 + dx, y0 + dy, z0 + dz, b0);
+          bulk_load(smem_u32(a_dst + kABytes), wsrc + (size_t)kb * b_bytes, (uint32_t)b_bytes, bar);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(stage_base + (size_t)stage * stage_bytes);
+          const uint64_t adesc = make_sw128_desc(a_addr);
+          const uint64_t bdesc = make_sw128_desc(a_addr + kABytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // +32 B (16 bf16) along K inside the swizzle atom = +2 in the address field
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (kb | k) != 0);
+          umma_commit(smem_u32(&empty_bar[stage]));
+          if (kb == kblocks - 1) umma_commit(smem_u32(&tfull_bar[acc]));
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;    // tile row = voxel index inside the box
+    const int et = threadIdx.x - 64;        // 0..127
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const int ngroups = p.block_n / 64;
+    for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+      int n_tile, x0, y0, z0, b0;
+      decode_tile(work, n_tile, x0, y0, z0, b0);
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      if (et == 0) bulk_wait_read0();  // previous tile's TMA stores have finished reading the staging tile
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float* bias = s_bias + n_tile * p.block_n;
+      for (int c32 = 0; c32 < p.block_n / 32; ++c32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.block_n + c32 * 32), r);
+        tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v0 = __uint_as_float(r[2 * j]) + bias[c32 * 32 + 2 * j];
+          float v1 = __uint_as_float(r[2 * j + 1]) + bias[c32 * 32 + 2 * j + 1];
+          if (p.mode == DIQT_CONV_UP) { v0 = mish<true>(v0); v1 = mish<true>(v1); }
+          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+          packed[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        // 64 B of this row -> four 16 B chunks of a 128 B swizzled staging row
+        uint8_t* rowp = out_stage + (size_t)(c32 >> 1) * kABytes + (size_t)row * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int chunk = ((c32 & 1) * 4 + j) ^ (row & 7);
+          *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      fence_proxy_async();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        for (int g = 0; g < ngroups; ++g) {
+          const int col = n_tile * p.block_n + g * 64;
+          if (p.mode == DIQT_CONV_UP) {
+            const int sub = col / p.up_c, c0 = col - sub * p.up_c;
+            tma_store_5d(&p.out_map[sub], smem_u32(out_stage + (size_t)g * kABytes), c0, x0, y0, z0, b0);
+          } else {
+            tma_store_5d(&p.out_map[0], smem_u32(out_stage + (size_t)g * kABytes), col, x0, y0, z0, b0);
+          }
+        }
+        bulk_commit();
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (et == 0) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: (c_out, c_in*, k,k,k) fp32 -> [n_tile][kblock = tap*kchunks + q][block_n][64] bf16, 16-byte chunks
+// XOR-swizzled by (row & 7) (what TMA SWIZZLE_128B would have produced).
+// ------------------------------------------------------------------------------------------------
+__global__ void conv_pack_tc_kernel(const float* __restrict__ w, int mode, int c_in, int c_out, int taps, int block_n,
+                                    __nv_bfloat16* __restrict__ packed) {
+  const int kchunks = c_in / 64, kblocks = taps * kchunks, n_tiles = c_out / block_n;
+  const int64_t total = (int64_t)n_tiles * kblocks * block_n * 64;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i % 64);
+    const int r = (int)((i / 64) % block_n);
+    const int kb = (int)((i / (64 * (int64_t)block_n)) % kblocks);
+    const int nt = (int)(i / (64 * (int64_t)block_n * kblocks));
+    const int t = kb / kchunks, q = kb - t * kchunks;
+    const int ci = q * 64 + e;
+    const int nn = nt * block_n + r;  // GEMM column
+    float v;
+    if (mode == DIQT_CONV_K3) v = w[((int64_t)nn * c_in + ci) * 27 + t];
+    else if (mode == DIQT_CONV_K1) v = w[(int64_t)nn * c_in + ci];
+    else if (mode == DIQT_CONV_DOWN) v = w[(int64_t)nn * (c_in * 8) + ci * 8 + t];
+    else {
+      const int C = c_out / 8, sub = nn / C, c = nn - sub * C;
+      v = w[(int64_t)(c * 8 + sub) * c_in + ci];
+    }
+    const int chunk = (e >> 3) ^ (r & 7);
+    const int64_t dst = (((int64_t)nt * kblocks + kb) * block_n + r) * 64 + chunk * 8 + (e & 7);
+    packed[dst] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)ptr;
+  return fn;
+}
+
+static int pow2floor(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+// channels-last bf16 volume view: dims (c, x, y, z, n) with element strides (1, sx, sy, sz, sn); box (64, bx, by, bz, bn)
+static int encode_volume_map(CUtensorMap* map, const void* base, int c, int x, int y, int z, int n, int64_t sx, int64_t sy,
+                             int64_t sz, int64_t sn, int bx, int by, int bz, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available (is a CUDA driver loaded?)");
+    return DIQT_ECUDA;
+  }
+  cuuint64_t dims[5] = {(cuuint64_t)c, (cuuint64_t)x, (cuuint64_t)y, (cuuint64_t)z, (cuuint64_t)n};
+  cuuint64_t strides[4] = {(cuuint64_t)sx * 2, (cuuint64_t)sy * 2, (cuuint64_t)sz * 2, (cuuint64_t)sn * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz, (cuuint32_t)bn};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): dims c=%d x=%d y=%d z=%d n=%d box %d,%d,%d,%d", (int)r, c, x, y, z, n, bx, by,
+              bz, bn);
+    return DIQT_ECUDA;
+  }
+  return DIQT_OK;
+}
+
+struct TcPlan {
+  TcParams p;
+  int grid;
+  size_t smem;
+};
+
+int tc_taps(int mode) { return mode == DIQT_CONV_K3 ? 27 : mode == DIQT_CONV_DOWN ? 8 : 1; }
+
+int tc_block_n(const diqt_conv_desc* d) {
+  if (d->c_out % 256 == 0) return 256;
+  if (d->c_out % 128 == 0) return 128;
+  return 64;
+}
+
+bool conv_tc_supported(const diqt_conv_desc* d) {
+  if (d->dtype != DIQT_BF16) return false;
+  if (d->c_in % 64 != 0 || d->c_out % 64 != 0) return false;
+  if (d->ld_in % 8 != 0 || d->ld_out % 8 != 0) return false;
+  if (d->mode == DIQT_CONV_UP && (d->c_out / 8) % 64 != 0) return false;
+  if (d->mode == DIQT_CONV_DOWN && (d->d0 % 2 || d->d1 % 2 || d->d2 % 2)) return false;
+  return true;
+}
+
+size_t conv_tc_packed_bytes(const diqt_conv_desc* d) { return (size_t)tc_taps(d->mode) * d->c_in * d->c_out * 2; }
+
+int conv_tc_pack(const diqt_conv_desc* d, const float* w, void* packed, cudaStream_t st) {
+  conv_pack_tc_kernel<<<512, 256, 0, st>>>(w, d->mode, d->c_in, d->c_out, tc_taps(d->mode), tc_block_n(d), (__nv_bfloat16*)packed);
+  return check_launch("conv_pack_tc");
+}
+
+int conv_tc_plan(const diqt_conv_desc* d, const void* in, void* out, const void* packed, const float* bias, TcPlan** out_plan) {
+  DIQT_REQUIRE(conv_tc_supported(d), "conv(tc): unsupported shape c_in=%d c_out=%d ld_in=%d ld_out=%d mode=%d", d->c_in, d->c_out,
+               d->ld_in, d->ld_out, d->mode);
+  TcPlan* plan = new TcPlan();
+  TcParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  p.mode = d->mode;
+  p.taps = tc_taps(d->mode);
+  p.kchunks = d->c_in / 64;
+  p.block_n = tc_block_n(d);
+  p.n_tiles = d->c_out / p.block_n;
+  p.up_c = d->c_out / 8;
+  p.w = (const uint8_t*)packed;
+  p.bias = bias;
+  // GEMM output voxel grid
+  int od0 = d->d0, od1 = d->d1, od2 = d->d2;
+  if (d->mode == DIQT_CONV_DOWN) { od0 /= 2; od1 /= 2; od2 /= 2; }
+  int rem = kTileM;
+  p.bx = std::min(8, pow2floor(od2)); rem /= p.bx;
+  p.by = std::min(std::min(4, rem), pow2floor(od1)); rem /= p.by;
+  p.bz = std::min(rem, pow2floor(od0)); rem /= p.bz;
+  p.bn = rem;
+  p.tiles_x = (od2 + p.bx - 1) / p.bx;
+  p.tiles_y = (od1 + p.by - 1) / p.by;
+  p.tiles_z = (od0 + p.bz - 1) / p.bz;
+  p.tiles_n = (d->n + p.bn - 1) / p.bn;
+  p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_z * p.tiles_n;
+  p.idesc = make_idesc_bf16(kTileM, p.block_n);
+  p.tmem_cols = 2 * p.block_n < 32 ? 32 : 2 * p.block_n;  // 128 / 256 / 512: powers of two
+
+  const __nv_bfloat16* inb = (const __nv_bfloat16*)in;
+  __nv_bfloat16* outb = (__nv_bfloat16*)out;
+  const int64_t ld = d->ld_in;
+  int rc = DIQT_OK;
+  if (d->mode == DIQT_CONV_DOWN) {
+    // tap (s1,s2,s3): input voxel (2z+s1, 2y+s2, 2x+s3)  -> a view with doubled strides and an offset base
+    for (int t = 0; t < 8 && rc == DIQT_OK; ++t) {
+      const int s1 = (t >> 2) & 1, s2 = (t >> 1) & 1, s3 = t & 1;
+      const __nv_bfloat16* base = inb + (((int64_t)s1 * d->d1 + s2) * d->d2 + s3) * ld;
+      rc = encode_volume_map(&p.in_map[t], base, d->c_in, od2, od1, od0, d->n, 2 * ld, 2 * (int64_t)d->d2 * ld,
+                             2 * (int64_t)d->d1 * d->d2 * ld, (int64_t)d->d0 * d->d1 * d->d2 * ld, p.bx, p.by, p.bz, p.bn);
+    }
+  } else {
+    rc = encode_volume_map(&p.in_map[0], inb, d->c_in, d->d2, d->d1, d->d0, d->n, ld, (int64_t)d->d2 * ld,
+                           (int64_t)d->d1 * d->d2 * ld, (int64_t)d->d0 * d->d1 * d->d2 * ld, p.bx, p.by, p.bz, p.bn);
+  }
+  const int64_t lo = d->ld_out;
+  if (rc == DIQT_OK) {
+    if (d->mode == DIQT_CONV_UP) {
+      const int D0 = 2 * d->d0, D1 = 2 * d->d1, D2 = 2 * d->d2;
+      for (int s = 0; s < 8 && rc == DIQT_OK; ++s) {
+        const int i = (s >> 2) & 1, j = (s >> 1) & 1, k = s & 1;
+        __nv_bfloat16* base = outb + (((int64_t)i * D1 + j) * D2 + k) * lo;
+        rc = encode_volume_map(&p.out_map[s], base, p.up_c, d->d2, d->d1, d->d0, d->n, 2 * lo, 2 * (int64_t)D2 * lo,
+                               2 * (int64_t)D1 * D2 * lo, (int64_t)D0 * D1 * D2 * lo, p.bx, p.by, p.bz, p.bn);
+      }
+    } else {
+      rc = encode_volume_map(&p.out_map[0], outb, d->c_out, od2, od1, od0, d->n, lo, (int64_t)od2 * lo, (int64_t)od1 * od2 * lo,
+                             (int64_t)od0 * od1 * od2 * lo, p.bx, p.by, p.bz, p.bn);
+    }
+  }
+  if (rc != DIQT_OK) {
+    delete plan;
+    return rc;
+  }
+  // shared memory budget
+  const int stage_bytes = kABytes + p.block_n * 128;
+  const size_t fixed = (size_t)(p.block_n / 64) * kABytes + (size_t)p.n_tiles * p.block_n * 4 + 256 + 1024;
+  int stages = (int)((220 * 1024 - fixed) / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages < 2) {
+    set_error("conv(tc): not enough shared memory for block_n=%d", p.block_n);
+    delete plan;
+    return DIQT_EINVAL;
+  }
+  p.stages = stages;
+  plan->smem = fixed + (size_t)stages * stage_bytes;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int total = p.m_tiles * p.n_tiles;
+  plan->grid = total < sms ? total : sms;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DIQT_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  *out_plan = plan;
+  return DIQT_OK;
+}
+
+int conv_tc_run(const TcPlan* plan, cudaStream_t st) {
+  conv_tc_kernel<<<plan->grid, kThreads, plan->smem, st>>>(plan->p);
+  return check_launch("conv_tc");
+}
+
+void conv_tc_destroy(TcPlan* plan) { delete plan; }
+
+}  // namespace diqt

@@ -1,0 +1,379 @@
+// Bandwidth-bound kernels of the ResnetBlock: channel statistics, GroupNorm(+FiLM)+Mish,
+// squeeze-excitation gate, gated residual add.  All operate on channels-last activations
+// [n][voxels][c] with row pitch ld, 16-byte vector accesses, fp32 math.
+//
+// Reference call sites replaced: nn.GroupNorm (imagen_pytorch3D.py:546, 557), FiLM (:559-561),
+// nn.Mish (:547, 563), SE3D (:617-632), residual add (:612).
+#include "common.cuh"
+
+namespace diqt {
+
+// thread mapping shared by every kernel in this file:
+//   nvec = c / VEC vectors per voxel row; thread -> (col = tid % nvec, lane = tid / nvec);
+//   a block owns voxels [blk*vpb, (blk+1)*vpb) of volume blockIdx.y and strides them by `lanes`.
+struct RowMap {
+  int nvec, lanes, threads;
+};
+
+static inline RowMap make_rowmap(int c, int vec, int max_threads = 256) {
+  RowMap m;
+  m.nvec = c / vec;
+  m.lanes = max_threads / m.nvec;
+  if (m.lanes < 1) m.lanes = 1;
+  m.threads = m.nvec * m.lanes;
+  return m;
+}
+
+// ---- per-block reduction of per-thread channel sums -> partial[n][blk][c][2] ------------------
+template <int VEC>
+__device__ __forceinline__ void block_channel_reduce(const float (&s)[VEC], const float (&q)[VEC], int col, int lane,
+                                                     int lanes, int c, float* __restrict__ partial_out,
+                                                     float* smem /* 2 * lanes * c floats */) {
+  float* ss = smem;
+  float* sq = smem + (size_t)lanes * c;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    ss[lane * c + col * VEC + i] = s[i];
+    sq[lane * c + col * VEC + i] = q[i];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < lanes; ++l) {  // fixed order: deterministic
+      a += ss[l * c + ch];
+      b += sq[l * c + ch];
+    }
+    partial_out[2 * ch] = a;
+    partial_out[2 * ch + 1] = b;
+  }
+}
+
+template <typename T>
+__global__ void channel_stats_kernel(const T* __restrict__ x, int64_t voxels, int c, int ld, int nvec, int lanes,
+                                     int64_t vpb, float* __restrict__ partial) {
+  constexpr int VEC = Vec<T>::N;
+  extern __shared__ float smem[];
+  const int col = threadIdx.x % nvec, lane = threadIdx.x / nvec;
+  const int blk = blockIdx.x, n = blockIdx.y, nblk = gridDim.x;
+  const int64_t v0 = (int64_t)blk * vpb;
+  const int64_t v1 = min(voxels, v0 + vpb);
+  const T* base = x + ((int64_t)n * voxels) * ld + col * VEC;
+  float s[VEC], q[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s[i] = q[i] = 0.f;
+  int64_t v = v0 + lane;
+  for (; v + 3 * (int64_t)lanes < v1; v += 4 * (int64_t)lanes) {
+    Vec<T> r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u].load(base + (v + (int64_t)u * lanes) * ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        s[i] += r[u].v[i];
+        q[i] = fmaf(r[u].v[i], r[u].v[i], q[i]);
+      }
+  }
+  for (; v < v1; v += lanes) {
+    Vec<T> r;
+    r.load(base + v * ld);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      s[i] += r.v[i];
+      q[i] = fmaf(r.v[i], r.v[i], q[i]);
+    }
+  }
+  block_channel_reduce<VEC>(s, q, col, lane, lanes, c, partial + ((int64_t)n * nblk + blk) * c * 2, smem);
+}
+
+// ---- GroupNorm finalize: partial sums -> per-(n,c) affine (a, b), with FiLM folded in -----------
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblk, int64_t voxels, int c, int groups,
+                                   float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   const float* __restrict__ film, int film_ld, const int32_t* __restrict__ film_row,
+                                   int film_row_stride_n, float* __restrict__ a_out, float* __restrict__ b_out) {
+  extern __shared__ double sm[];  // acc[parts][c][2], tot[c][2], gstat[groups][2]
+  const int n = blockIdx.x;
+  const int parts = max(1, (int)blockDim.x / c);
+  double* acc = sm;
+  double* tot = sm + (size_t)parts * c * 2;
+  double* gstat = tot + (size_t)c * 2;
+  const float* p = partial + (int64_t)n * nblk * c * 2;
+  for (int idx = threadIdx.x; idx < parts * c; idx += blockDim.x) {
+    const int ch = idx % c, part = idx / c;
+    double s = 0.0, q = 0.0;
+    for (int b = part; b < nblk; b += parts) {
+      s += (double)p[((int64_t)b * c + ch) * 2];
+      q += (double)p[((int64_t)b * c + ch) * 2 + 1];
+    }
+    acc[(part * c + ch) * 2] = s;
+    acc[(part * c + ch) * 2 + 1] = q;
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int part = 0; part < parts; ++part) {
+      s += acc[(part * c + ch) * 2];
+      q += acc[(part * c + ch) * 2 + 1];
+    }
+    tot[ch * 2] = s;
+    tot[ch * 2 + 1] = q;
+  }
+  __syncthreads();
+  const int cpg = c / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < cpg; ++i) {
+      s += tot[(g * cpg + i) * 2];
+      q += tot[(g * cpg + i) * 2 + 1];
+    }
+    const double cnt = (double)voxels * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    gstat[g * 2] = mean;
+    gstat[g * 2 + 1] = 1.0 / sqrt(var + (double)eps);
+  }
+  __syncthreads();
+  const float* fr = nullptr;
+  if (film) {
+    const int row = (film_row ? *film_row : 0) + n * film_row_stride_n;
+    fr = film + (int64_t)row * film_ld;
+  }
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    const int g = ch / cpg;
+    const float mean = (float)gstat[g * 2], rstd = (float)gstat[g * 2 + 1];
+    float a = rstd * gamma[ch];
+    float b = beta[ch] - mean * a;
+    if (fr) {  // x * (scale + 1) + shift   (imagen_pytorch3D.py:559-561)
+      const float sc = fr[ch] + 1.f, sh = fr[c + ch];
+      a *= sc;
+      b = fmaf(b, sc, sh);
+    }
+    a_out[(int64_t)n * c + ch] = a;
+    b_out[(int64_t)n * c + ch] = b;
+  }
+}
+
+// ---- y = mish(a * x + b) -----------------------------------------------------------------------
+template <typename T, bool kFast>
+__global__ void affine_mish_kernel(const T* __restrict__ x, int ld_x, T* __restrict__ y, int ld_y, int64_t voxels,
+                                   int c, int nvec, int lanes, int64_t vpb, const float* __restrict__ a,
+                                   const float* __restrict__ b) {
+  constexpr int VEC = Vec<T>::N;
+  const int col = threadIdx.x % nvec, lane = threadIdx.x / nvec;
+  const int n = blockIdx.y;
+  const int64_t v0 = (int64_t)blockIdx.x * vpb;
+  const int64_t v1 = min(voxels, v0 + vpb);
+  float av[VEC], bv[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    av[i] = a[(int64_t)n * c + col * VEC + i];
+    bv[i] = b[(int64_t)n * c + col * VEC + i];
+  }
+  const T* xb = x + ((int64_t)n * voxels) * ld_x + col * VEC;
+  T* yb = y + ((int64_t)n * voxels) * ld_y + col * VEC;
+  int64_t v = v0 + lane;
+  for (; v + 3 * (int64_t)lanes < v1; v += 4 * (int64_t)lanes) {
+    Vec<T> r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u].load(xb + (v + (int64_t)u * lanes) * ld_x);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) r[u].v[i] = mish<kFast>(fmaf(av[i], r[u].v[i], bv[i]));
+      r[u].store(yb + (v + (int64_t)u * lanes) * ld_y);
+    }
+  }
+  for (; v < v1; v += lanes) {
+    Vec<T> r;
+    r.load(xb + v * ld_x);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r.v[i] = mish<kFast>(fmaf(av[i], r.v[i], bv[i]));
+    r.store(yb + v * ld_y);
+  }
+}
+
+// ---- SE gate from channel partial sums -----------------------------------------------------------
+__global__ void se_gate_kernel(const float* __restrict__ partial, int nblk, int64_t voxels, int c, int hidden,
+                               const float* __restrict__ w1, const float* __restrict__ w2, float* __restrict__ gate) {
+  extern __shared__ float sf[];  // mean[c], hid[hidden]
+  float* mean = sf;
+  float* hid = sf + c;
+  const int n = blockIdx.x;
+  const float* p = partial + (int64_t)n * nblk * c * 2;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += (double)p[((int64_t)b * c + ch) * 2];
+    mean[ch] = (float)(s / (double)voxels);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarps = blockDim.x / 32;
+  for (int j = warp; j < hidden; j += nwarps) {
+    float acc = 0.f;
+    for (int k = lane; k < c; k += 32) acc = fmaf(w1[(int64_t)j * c + k], mean[k], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) hid[j] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < hidden; ++j) acc = fmaf(w2[(int64_t)ch * hidden + j], hid[j], acc);
+    gate[(int64_t)n * c + ch] = 1.f / (1.f + expf(-acc));
+  }
+}
+
+// ---- out = h * gate + res, plus channel stats of out ---------------------------------------------
+template <typename T>
+__global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T* __restrict__ res, int ld_res,
+                                      T* __restrict__ out, int ld_out, int64_t voxels, int c, int nvec, int lanes,
+                                      int64_t vpb, const float* __restrict__ gate, float* __restrict__ partial) {
+  constexpr int VEC = Vec<T>::N;
+  extern __shared__ float smem[];
+  const int col = threadIdx.x % nvec, lane = threadIdx.x / nvec;
+  const int blk = blockIdx.x, n = blockIdx.y, nblk = gridDim.x;
+  const int64_t v0 = (int64_t)blk * vpb;
+  const int64_t v1 = min(voxels, v0 + vpb);
+  float g[VEC], s[VEC], q[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    g[i] = gate ? gate[(int64_t)n * c + col * VEC + i] : 1.f;
+    s[i] = q[i] = 0.f;
+  }
+  const T* hb = h + ((int64_t)n * voxels) * ld_h + col * VEC;
+  const T* rb = res + ((int64_t)n * voxels) * ld_res + col * VEC;
+  T* ob = out + ((int64_t)n * voxels) * ld_out + col * VEC;
+  int64_t v = v0 + lane;
+  for (; v + (int64_t)lanes < v1; v += 2 * (int64_t)lanes) {
+    Vec<T> a[2], r[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      a[u].load(hb + (v + (int64_t)u * lanes) * ld_h);
+      r[u].load(rb + (v + (int64_t)u * lanes) * ld_res);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      Vec<T> o;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) o.v[i] = fmaf(a[u].v[i], g[i], r[u].v[i]);
+      o.store(ob + (v + (int64_t)u * lanes) * ld_out);
+      if (partial) {
+        // statistics of what the next GroupNorm will actually read (the stored, rounded value)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const float w = to_float(from_float<T>(o.v[i]));
+          s[i] += w;
+          q[i] = fmaf(w, w, q[i]);
+        }
+      }
+    }
+  }
+  for (; v < v1; v += lanes) {
+    Vec<T> a, r, o;
+    a.load(hb + v * ld_h);
+    r.load(rb + v * ld_res);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) o.v[i] = fmaf(a.v[i], g[i], r.v[i]);
+    o.store(ob + v * ld_out);
+    if (partial) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float w = to_float(from_float<T>(o.v[i]));
+        s[i] += w;
+        q[i] = fmaf(w, w, q[i]);
+      }
+    }
+  }
+  if (partial)
+    block_channel_reduce<VEC>(s, q, col, lane, lanes, c, partial + ((int64_t)n * nblk + blk) * c * 2, smem);
+}
+
+static inline int64_t vox_per_block(int64_t voxels, int nblk) { return (voxels + nblk - 1) / nblk; }
+
+}  // namespace diqt
+
+using namespace diqt;
+
+extern "C" int diqt_channel_stats(const void* x, int dtype, int n, int64_t voxels, int c, int ld, int nblk,
+                                  float* partial, void* stream) {
+  const int vec = dtype == DIQT_BF16 ? 8 : 4;
+  DIQT_REQUIRE(x && partial && n > 0 && voxels > 0 && nblk > 0, "channel_stats: bad arguments");
+  DIQT_REQUIRE(c % vec == 0 && ld % vec == 0 && c / vec <= 256, "channel_stats: c=%d ld=%d not a multiple of %d", c, ld, vec);
+  RowMap m = make_rowmap(c, vec);
+  dim3 grid(nblk, n);
+  size_t sh = (size_t)2 * m.lanes * c * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DIQT_BF16)
+    channel_stats_kernel<__nv_bfloat16><<<grid, m.threads, sh, st>>>((const __nv_bfloat16*)x, voxels, c, ld, m.nvec, m.lanes,
+                                                                    vox_per_block(voxels, nblk), partial);
+  else
+    channel_stats_kernel<float><<<grid, m.threads, sh, st>>>((const float*)x, voxels, c, ld, m.nvec, m.lanes,
+                                                            vox_per_block(voxels, nblk), partial);
+  return check_launch("channel_stats");
+}
+
+extern "C" int diqt_gn_finalize(const float* partial, int n, int nblk, int64_t voxels, int c, int groups, float eps,
+                                const float* gamma, const float* beta, const float* film, int film_ld,
+                                const int32_t* film_row, int film_row_stride_n, float* a, float* b, void* stream) {
+  DIQT_REQUIRE(partial && gamma && beta && a && b, "gn_finalize: null pointer");
+  DIQT_REQUIRE(groups > 0 && c % groups == 0 && c <= 4096, "gn_finalize: c=%d groups=%d", c, groups);
+  const int threads = 1024;
+  const int parts = threads / c > 0 ? threads / c : 1;
+  size_t sh = ((size_t)parts * c * 2 + (size_t)c * 2 + (size_t)groups * 2) * sizeof(double);
+  static bool attr_set = false;
+  if (sh > 48 * 1024 && !attr_set) {
+    DIQT_CUDA(cudaFuncSetAttribute(gn_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  gn_finalize_kernel<<<n, threads, sh, (cudaStream_t)stream>>>(partial, nblk, voxels, c, groups, eps, gamma, beta, film,
+                                                               film_ld, film_row, film_row_stride_n, a, b);
+  return check_launch("gn_finalize");
+}
+
+extern "C" int diqt_affine_mish(const void* x, int ld_x, void* y, int ld_y, int dtype, int n, int64_t voxels, int c,
+                                const float* a, const float* b, int nblk, void* stream) {
+  const int vec = dtype == DIQT_BF16 ? 8 : 4;
+  DIQT_REQUIRE(x && y && a && b && nblk > 0, "affine_mish: bad arguments");
+  DIQT_REQUIRE(c % vec == 0 && ld_x % vec == 0 && ld_y % vec == 0 && c / vec <= 256, "affine_mish: c=%d not a multiple of %d", c, vec);
+  RowMap m = make_rowmap(c, vec);
+  dim3 grid(nblk, n);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DIQT_BF16)
+    affine_mish_kernel<__nv_bfloat16, true><<<grid, m.threads, 0, st>>>((const __nv_bfloat16*)x, ld_x, (__nv_bfloat16*)y, ld_y,
+                                                                       voxels, c, m.nvec, m.lanes,
+                                                                       vox_per_block(voxels, nblk), a, b);
+  else
+    affine_mish_kernel<float, false><<<grid, m.threads, 0, st>>>((const float*)x, ld_x, (float*)y, ld_y, voxels, c, m.nvec,
+                                                                m.lanes, vox_per_block(voxels, nblk), a, b);
+  return check_launch("affine_mish");
+}
+
+extern "C" int diqt_se_gate(const float* partial, int n, int nblk, int64_t voxels, int c, int hidden, const float* w1,
+                            const float* w2, float* gate, void* stream) {
+  DIQT_REQUIRE(partial && w1 && w2 && gate && hidden > 0, "se_gate: bad arguments (hidden=%d)", hidden);
+  size_t sh = (size_t)(c + hidden) * sizeof(float);
+  se_gate_kernel<<<n, 256, sh, (cudaStream_t)stream>>>(partial, nblk, voxels, c, hidden, w1, w2, gate);
+  return check_launch("se_gate");
+}
+
+extern "C" int diqt_scale_residual(const void* h, int ld_h, const void* res, int ld_res, void* out, int ld_out, int dtype,
+                                   int n, int64_t voxels, int c, const float* gate, int nblk, float* partial,
+                                   void* stream) {
+  const int vec = dtype == DIQT_BF16 ? 8 : 4;
+  DIQT_REQUIRE(h && res && out && nblk > 0, "scale_residual: bad arguments");
+  DIQT_REQUIRE(c % vec == 0 && ld_h % vec == 0 && ld_res % vec == 0 && ld_out % vec == 0 && c / vec <= 256,
+               "scale_residual: c=%d not a multiple of %d", c, vec);
+  RowMap m = make_rowmap(c, vec);
+  dim3 grid(nblk, n);
+  size_t sh = partial ? (size_t)2 * m.lanes * c * sizeof(float) : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DIQT_BF16)
+    scale_residual_kernel<__nv_bfloat16><<<grid, m.threads, sh, st>>>(
+        (const __nv_bfloat16*)h, ld_h, (const __nv_bfloat16*)res, ld_res, (__nv_bfloat16*)out, ld_out, voxels, c, m.nvec,
+        m.lanes, vox_per_block(voxels, nblk), gate, partial);
+  else
+    scale_residual_kernel<float><<<grid, m.threads, sh, st>>>((const float*)h, ld_h, (const float*)res, ld_res, (float*)out,
+                                                             ld_out, voxels, c, m.nvec, m.lanes,
+                                                             vox_per_block(voxels, nblk), gate, partial);
+  return check_launch("scale_residual");
+}

@@ -1,0 +1,331 @@
+// Network ends and sampler glue: init_conv over fp32 planes, final 1x1x1 conv fused with the
+// DDPM posterior update, the time-conditioning dense layers, and the step counter.
+//
+// Reference call sites replaced: init_conv (imagen_pytorch3D.py:1291, 1576-1589), final_conv
+// (:1477, 1682), p_mean_variance / p_sample / q_posterior (:1976-2056, :290-309),
+// LearnedSinusoidalPosEmb + to_time_hiddens + to_time_cond + ResnetBlock.time_mlp
+// (:518-533, :1305-1316, :586-589, :603-605).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace diqt {
+
+static thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---- init conv: up to 8 single-channel fp32 planes -> channels-last activations -----------------
+constexpr int kInitMaxCin = 8;
+struct InitPlanes {
+  const float* p[kInitMaxCin];
+  long long stride[kInitMaxCin];
+};
+
+// one thread = one output voxel; CO_T output channels at a time are held in registers
+template <typename T, int CO_T>
+__global__ void __launch_bounds__(128)
+init_conv_kernel(InitPlanes planes, int c_in, const float* __restrict__ w /*[27][c_in][c_out]*/,
+                 const float* __restrict__ bias, T* __restrict__ out, int ld_out, int n, int d0, int d1, int d2,
+                 int c_out) {
+  extern __shared__ float sw[];  // weights [27*c_in][c_out] + bias[c_out]
+  const int wcount = 27 * c_in * c_out;
+  for (int i = threadIdx.x; i < wcount; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < c_out; i += blockDim.x) sw[wcount + i] = bias[i];
+  __syncthreads();
+  const int64_t vol = (int64_t)d0 * d1 * d2;
+  const int64_t total = (int64_t)n * vol;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int b = (int)(idx / vol);
+  int64_t r = idx - (int64_t)b * vol;
+  const int z = (int)(r / ((int64_t)d1 * d2));
+  r -= (int64_t)z * d1 * d2;
+  const int y = (int)(r / d2);
+  const int x = (int)(r - (int64_t)y * d2);
+  T* orow = out + idx * ld_out;
+  for (int co0 = 0; co0 < c_out; co0 += CO_T) {
+    float acc[CO_T];
+#pragma unroll
+    for (int j = 0; j < CO_T; ++j) acc[j] = sw[wcount + co0 + j];
+#pragma unroll 1
+    for (int t = 0; t < 27; ++t) {
+      const int zz = z + t / 9 - 1, yy = y + (t / 3) % 3 - 1, xx = x + t % 3 - 1;
+      if (zz < 0 || zz >= d0 || yy < 0 || yy >= d1 || xx < 0 || xx >= d2) continue;  // zero padding
+      const int64_t off = ((int64_t)zz * d1 + yy) * d2 + xx;
+      for (int ci = 0; ci < c_in; ++ci) {
+        const float v = __ldg(planes.p[ci] + (int64_t)b * planes.stride[ci] + off);
+        const float* wr = sw + (t * c_in + ci) * c_out + co0;
+#pragma unroll
+        for (int j = 0; j < CO_T; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
+      }
+    }
+    constexpr int VN = Vec<T>::N;
+#pragma unroll
+    for (int j = 0; j < CO_T; j += VN) {
+      Vec<T> o;
+#pragma unroll
+      for (int i = 0; i < VN; ++i) o.v[i] = acc[j + i];
+      o.store(orow + co0 + j);
+    }
+  }
+}
+
+__global__ void init_conv_pack_kernel(const float* __restrict__ w, int c_out, int c_in, float* __restrict__ packed) {
+  // (c_out, c_in, 3,3,3) -> [tap][c_in][c_out]
+  const int total = 27 * c_in * c_out;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % c_out, ci = (i / c_out) % c_in, t = i / (c_out * c_in);
+    packed[i] = w[((int64_t)co * c_in + ci) * 27 + t];
+  }
+}
+
+// ---- final 1x1x1 conv (+ fused DDPM update) -------------------------------------------------------
+// sched row: (alpha, sigma, c, alpha_next, noise_scale, lo, hi, objective)
+struct StepConsts {
+  float alpha, sigma, c, alpha_next, noise_scale, lo, hi;
+  int objective;  // 0 x_start, 1 noise, 2 v
+};
+
+__device__ __forceinline__ StepConsts load_step(const float* __restrict__ sched, const int32_t* __restrict__ step) {
+  const float* r = sched + (int64_t)(step ? *step : 0) * 8;
+  StepConsts s;
+  s.alpha = r[0]; s.sigma = r[1]; s.c = r[2]; s.alpha_next = r[3]; s.noise_scale = r[4]; s.lo = r[5]; s.hi = r[6];
+  s.objective = (int)r[7];
+  return s;
+}
+
+// x_start from the network output (imagen_pytorch3D.py:1996-2004), static clamp (:2022-2026), posterior mean
+// (:301-302) and the sampling line (:2055), in the reference's operation order.
+__device__ __forceinline__ void ddpm_point(const StepConsts& s, float pred, float xt, float eps, float& x_next, float& x0) {
+  float xs = pred;
+  if (s.objective == 1) xs = (xt - s.sigma * pred) / fmaxf(s.alpha, 1e-8f);
+  else if (s.objective == 2) xs = s.alpha * xt - s.sigma * pred;
+  xs = fminf(fmaxf(xs, s.lo), s.hi);
+  const float mean = s.alpha_next * (xt * (1.f - s.c) / s.alpha + s.c * xs);
+  x_next = mean + s.noise_scale * eps;
+  x0 = xs;
+}
+
+template <typename T, int MAXCO>
+__global__ void final_conv_kernel(const T* __restrict__ x, int ld, int64_t voxels, int c, int c_out, int nvec,
+                                  const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ pred,
+                                  int step_mode, const float* __restrict__ sched, const int32_t* __restrict__ step,
+                                  const float* __restrict__ x_t, const float* __restrict__ noise,
+                                  float* __restrict__ x_next, float* __restrict__ x0, int64_t total_rows) {
+  constexpr int VEC = Vec<T>::N;
+  // nvec (power of two <= 32) consecutive threads share one voxel row
+  const int col = threadIdx.x % nvec;
+  const int64_t rows_per_block = blockDim.x / nvec;
+  float wv[MAXCO][VEC];
+#pragma unroll
+  for (int co = 0; co < MAXCO; ++co)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) wv[co][i] = co < c_out ? w[co * c + col * VEC + i] : 0.f;
+  StepConsts sc;
+  if (step_mode) sc = load_step(sched, step);
+  // block-uniform trip count so the full-mask shuffles below are always converged
+  for (int64_t base = (int64_t)blockIdx.x * rows_per_block; base < total_rows; base += (int64_t)gridDim.x * rows_per_block) {
+    const int64_t row = base + threadIdx.x / nvec;
+    const bool valid = row < total_rows;
+    Vec<T> r;
+    if (valid) r.load(x + row * ld + col * VEC);
+    else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) r.v[i] = 0.f;
+    }
+    float acc[MAXCO];
+#pragma unroll
+    for (int co = 0; co < MAXCO; ++co) {
+      acc[co] = 0.f;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) acc[co] = fmaf(r.v[i], wv[co][i], acc[co]);
+      for (int o = nvec >> 1; o > 0; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+    }
+    if (valid && col == 0) {
+      const int64_t b = row / voxels, v = row - b * voxels;
+      for (int co = 0; co < c_out; ++co) {
+        const float p = acc[co] + bias[co];
+        const int64_t o = (b * c_out + co) * voxels + v;  // NCDHW fp32
+        if (!step_mode) {
+          pred[o] = p;
+        } else {
+          float xn, xs;
+          ddpm_point(sc, p, x_t[o], noise[o], xn, xs);
+          x_next[o] = xn;
+          x0[o] = xs;
+        }
+      }
+    }
+  }
+}
+
+__global__ void ddpm_update_kernel(const float* __restrict__ pred, const float* __restrict__ sched,
+                                   const int32_t* __restrict__ step, const float* __restrict__ x_t,
+                                   const float* __restrict__ noise, float* __restrict__ x_next, float* __restrict__ x0,
+                                   int64_t count) {
+  StepConsts sc = load_step(sched, step);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    float xn, xs;
+    ddpm_point(sc, pred[i], x_t[i], noise[i], xn, xs);
+    x_next[i] = xn;
+    if (x0) x0[i] = xs;
+  }
+}
+
+// ---- time conditioning ------------------------------------------------------------------------------
+__global__ void fourier_kernel(const float* __restrict__ t, int rows, const float* __restrict__ w, int half,
+                               float* __restrict__ out) {
+  const int r = blockIdx.x;
+  const int width = 1 + 2 * half;
+  const float tv = t[r];
+  for (int j = threadIdx.x; j < width; j += blockDim.x) {
+    float v;
+    if (j == 0) v = tv;
+    else {
+      const int k = (j - 1) % half;
+      const float f = tv * w[k] * 2.f * 3.14159265358979323846f;  // x * weights * 2 * pi  (:530)
+      v = (j - 1) < half ? sinf(f) : cosf(f);
+    }
+    out[(int64_t)r * width + j] = v;
+  }
+}
+
+__global__ void linear_kernel(const float* __restrict__ x, int ldx, int k, const float* __restrict__ w,
+                              const float* __restrict__ b, int out_features, float* __restrict__ y, int ldy, int act_in,
+                              int act_out) {
+  extern __shared__ float xs[];
+  const int r = blockIdx.x;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    float v = x[(int64_t)r * ldx + i];
+    xs[i] = act_in ? mish<false>(v) : v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarps = blockDim.x / 32;
+  for (int o = blockIdx.y * nwarps + warp; o < out_features; o += gridDim.y * nwarps) {
+    float acc = 0.f;
+    for (int i = lane; i < k; i += 32) acc = fmaf(xs[i], w[(int64_t)o * k + i], acc);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) {
+      acc += b ? b[o] : 0.f;
+      y[(int64_t)r * ldy + o] = act_out ? mish<false>(acc) : acc;
+    }
+  }
+}
+
+__global__ void advance_step_kernel(int32_t* step) { *step += 1; }
+
+}  // namespace diqt
+
+using namespace diqt;
+
+extern "C" int diqt_abi_version(void) { return DIQT_ABI_VERSION; }
+extern "C" const char* diqt_last_error(void) { return g_err; }
+extern "C" uint64_t diqt_launch_count(void) { return g_launches.load(); }
+
+extern "C" int diqt_init_conv_pack(const float* w, int c_out, int c_in, float* packed, void* stream) {
+  DIQT_REQUIRE(w && packed && c_in > 0 && c_in <= kInitMaxCin, "init_conv_pack: c_in=%d (max %d)", c_in, kInitMaxCin);
+  init_conv_pack_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(w, c_out, c_in, packed);
+  return check_launch("init_conv_pack");
+}
+
+extern "C" int diqt_init_conv(const float* const* planes, const int64_t* plane_stride, int c_in, const float* w_packed,
+                              const float* bias, void* out, int ld_out, int dtype, int n, int d0, int d1, int d2, int c_out,
+                              void* stream) {
+  DIQT_REQUIRE(planes && plane_stride && w_packed && bias && out, "init_conv: null pointer");
+  DIQT_REQUIRE(c_in > 0 && c_in <= kInitMaxCin, "init_conv: c_in=%d (max %d)", c_in, kInitMaxCin);
+  DIQT_REQUIRE(c_out % 16 == 0, "init_conv: c_out=%d must be a multiple of 16", c_out);
+  InitPlanes ip;
+  for (int i = 0; i < kInitMaxCin; ++i) {
+    ip.p[i] = i < c_in ? planes[i] : nullptr;
+    ip.stride[i] = i < c_in ? plane_stride[i] : 0;
+  }
+  const int64_t total = (int64_t)n * d0 * d1 * d2;
+  const int threads = 128;
+  const size_t sh = ((size_t)27 * c_in * c_out + c_out) * sizeof(float);
+  DIQT_REQUIRE(sh <= 200 * 1024, "init_conv: weights do not fit shared memory");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+#define DIQT_INIT_LAUNCH(T, COT)                                                                                  \
+  do {                                                                                                            \
+    auto k = init_conv_kernel<T, COT>;                                                                            \
+    if (sh > 48 * 1024) DIQT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh)); \
+    k<<<blocks, threads, sh, st>>>(ip, c_in, w_packed, bias, (T*)out, ld_out, n, d0, d1, d2, c_out);              \
+  } while (0)
+  if (dtype == DIQT_BF16) {
+    if (c_out % 64 == 0) DIQT_INIT_LAUNCH(__nv_bfloat16, 64);
+    else if (c_out % 32 == 0) DIQT_INIT_LAUNCH(__nv_bfloat16, 32);
+    else DIQT_INIT_LAUNCH(__nv_bfloat16, 16);
+  } else {
+    if (c_out % 64 == 0) DIQT_INIT_LAUNCH(float, 64);
+    else if (c_out % 32 == 0) DIQT_INIT_LAUNCH(float, 32);
+    else DIQT_INIT_LAUNCH(float, 16);
+  }
+#undef DIQT_INIT_LAUNCH
+  return check_launch("init_conv");
+}
+
+extern "C" int diqt_final_conv(const void* x, int ld, int dtype, int n, int64_t voxels, int c, int c_out, const float* w,
+                               const float* bias, float* pred, int step_mode, const float* sched, const int32_t* step,
+                               const float* x_t, const float* noise, float* x_next, float* x0, void* stream) {
+  const int vec = dtype == DIQT_BF16 ? 8 : 4;
+  DIQT_REQUIRE(x && w && bias, "final_conv: null pointer");
+  DIQT_REQUIRE(c_out >= 1 && c_out <= 4, "final_conv: c_out=%d (1..4 supported)", c_out);
+  DIQT_REQUIRE(c % vec == 0 && ld % vec == 0, "final_conv: c=%d not a multiple of %d", c, vec);
+  const int nvec = c / vec;
+  DIQT_REQUIRE(nvec <= 32 && (nvec & (nvec - 1)) == 0, "final_conv: c/%d=%d must be a power of two <= 32", vec, nvec);
+  if (step_mode) DIQT_REQUIRE(sched && x_t && noise && x_next && x0, "final_conv: fused step needs sched/x_t/noise/x_next/x0");
+  else DIQT_REQUIRE(pred, "final_conv: pred is null");
+  const int64_t rows = (int64_t)n * voxels;
+  const int threads = 256;
+  const int64_t rpb = threads / nvec;
+  int64_t blocks = (rows + rpb - 1) / rpb;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DIQT_BF16)
+    final_conv_kernel<__nv_bfloat16, 4><<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)x, ld, voxels, c, c_out, nvec, w,
+                                                                            bias, pred, step_mode, sched, step, x_t, noise,
+                                                                            x_next, x0, rows);
+  else
+    final_conv_kernel<float, 4><<<(unsigned)blocks, threads, 0, st>>>((const float*)x, ld, voxels, c, c_out, nvec, w, bias, pred,
+                                                                    step_mode, sched, step, x_t, noise, x_next, x0, rows);
+  return check_launch("final_conv");
+}
+
+extern "C" int diqt_ddpm_update(const float* pred, const float* sched, const int32_t* step, const float* x_t,
+                                const float* noise, float* x_next, float* x0, int64_t count, void* stream) {
+  DIQT_REQUIRE(pred && sched && x_t && noise && x_next, "ddpm_update: null pointer");
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ddpm_update_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pred, sched, step, x_t, noise, x_next, x0, count);
+  return check_launch("ddpm_update");
+}
+
+extern "C" int diqt_fourier_features(const float* t, int rows, const float* w, int half, float* out, void* stream) {
+  DIQT_REQUIRE(t && w && out && rows > 0 && half > 0, "fourier_features: bad arguments");
+  fourier_kernel<<<rows, 64, 0, (cudaStream_t)stream>>>(t, rows, w, half, out);
+  return check_launch("fourier_features");
+}
+
+extern "C" int diqt_linear(const float* x, int ldx, int rows, int k, const float* w, const float* b, int out_features,
+                           float* y, int ldy, int act_in, int act_out, void* stream) {
+  DIQT_REQUIRE(x && w && y && rows > 0 && k > 0 && out_features > 0, "linear: bad arguments");
+  DIQT_REQUIRE((size_t)k * sizeof(float) <= 48 * 1024, "linear: k=%d too large", k);
+  dim3 grid(rows, (out_features + 63) / 64);
+  linear_kernel<<<grid, 256, (size_t)k * sizeof(float), (cudaStream_t)stream>>>(x, ldx, k, w, b, out_features, y, ldy, act_in,
+                                                                               act_out);
+  return check_launch("linear");
+}
+
+extern "C" int diqt_advance_step(int32_t* step, void* stream) {
+  DIQT_REQUIRE(step, "advance_step: null pointer");
+  advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+  return check_launch("advance_step");
+}

@@ -1,0 +1,168 @@
+/*
+ * diqt.h -- C ABI of libdiqt_b200.so, the sm_100a kernel library under the DiffusionIQT
+ * sampling hot path (Imagen.sample -> p_sample_loop -> p_sample -> Unet.forward).
+ *
+ * The reference has no FFI layer of its own: every arithmetic op on the path is a PyTorch
+ * library call inside /root/reference/imagen_pytorch3D.py.  Each entry point below names the
+ * reference call site(s) it replaces.  The Python shells in diffusioniqt_b200/ (same class
+ * names, constructor / forward / sample signatures and state_dict keys as the reference) bind
+ * these with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only: raw device pointers, ints, floats, a cudaStream_t passed as void*.
+ *   - every call is asynchronous on `stream`, never allocates, never synchronises, and is legal
+ *     inside CUDA-graph stream capture (diqt_conv_plan_create is the exception: call it once,
+ *     outside capture).
+ *   - return 0 on success, negative DIQT_E* on failure; diqt_last_error() gives the text
+ *     (thread-local).
+ *   - activations are channels-last volumes  [n][d0][d1][d2][c]  with a row pitch `ld`
+ *     (elements between consecutive voxels, >= c) so that the skip concat
+ *     (imagen_pytorch3D.py:1653) is a view, not a copy.  (d0,d1,d2) are the reference's
+ *     tensor dims (2,3,4).
+ *   - dtype: DIQT_F32 (exact mode, CUDA-core fp32) or DIQT_BF16 (tcgen05 tensor cores, fp32
+ *     accumulation in TMEM; statistics, gates, sampler state stay fp32).
+ */
+#ifndef DIQT_H_
+#define DIQT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIQT_ABI_VERSION 1
+
+enum { DIQT_F32 = 0, DIQT_BF16 = 1 };
+
+enum {
+  DIQT_OK = 0,
+  DIQT_EINVAL = -1,      /* bad argument / unsupported shape            */
+  DIQT_ECUDA = -2,       /* a CUDA runtime / driver call failed         */
+  DIQT_EUNSUPPORTED = -3 /* valid request this build has no kernel for  */
+};
+
+/* conv modes */
+enum {
+  DIQT_CONV_K3 = 0,   /* 3x3x3, stride 1, zero padding 1:  Block.project, imagen_pytorch3D.py:550-553 */
+  DIQT_CONV_K1 = 1,   /* 1x1x1: ResnetBlock.res_conv :597, last-level post_downsample :1388            */
+  DIQT_CONV_DOWN = 2, /* pixel-unshuffle(2) + 1x1x1: Downsample :489-496 (a 2x2x2 stride-2 conv)      */
+  DIQT_CONV_UP = 3    /* 1x1x1 + Mish + PixelShuffle3D(2): PixelShuffleUpsample :459-487, :416-439    */
+};
+
+/* conv kernel families */
+enum {
+  DIQT_IMPL_AUTO = 0,
+  DIQT_IMPL_SIMT = 1, /* CUDA-core implicit GEMM, fp32 accumulate; any channel count; both dtypes */
+  DIQT_IMPL_TC = 2    /* tcgen05 + TMA implicit GEMM, bf16 only, C_in % 64 == 0, C_out % 64 == 0   */
+};
+
+int diqt_abi_version(void);
+const char* diqt_last_error(void);
+/* number of kernels this library has launched from the calling process (for bench.py's gpu_launches) */
+uint64_t diqt_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolutions (implicit GEMM).  Replaces nn.Conv3d at imagen_pytorch3D.py:467, 495, 551-553,
+ * 597, 1388 and the einops / PixelShuffle3D data movement around them (:416-439, :493).
+ *
+ * Weights are repacked once by diqt_conv_pack_weights from the reference's
+ * (C_out, C_in, k, k, k) fp32 tensor into the layout the chosen kernel family wants.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct diqt_conv_desc {
+  int32_t mode;          /* DIQT_CONV_*                                                     */
+  int32_t dtype;         /* DIQT_F32 / DIQT_BF16 (activations in and out)                   */
+  int32_t impl;          /* DIQT_IMPL_*                                                     */
+  int32_t n;             /* volumes                                                         */
+  int32_t d0, d1, d2;    /* INPUT spatial dims                                              */
+  int32_t c_in, ld_in;   /* input channels / row pitch                                      */
+  int32_t c_out, ld_out; /* GEMM N (for DIQT_CONV_UP: 8x the channels stored) / out pitch   */
+  int32_t flags;         /* reserved, 0                                                     */
+} diqt_conv_desc;
+
+/* which kernel family DIQT_IMPL_AUTO resolves to for this shape (DIQT_IMPL_SIMT or DIQT_IMPL_TC) */
+int diqt_conv_resolved_impl(const diqt_conv_desc* d, int* impl);
+/* bytes needed for the packed weight buffer of this conv */
+int diqt_conv_packed_bytes(const diqt_conv_desc* d, size_t* bytes);
+/* w: device fp32 (C_out, C_in, k,k,k) exactly as in the reference state_dict; bias: device fp32 (C_out) or
+ * NULL.  packed_w: device buffer of diqt_conv_packed_bytes; packed_bias: device fp32 [c_out] in GEMM column
+ * order (DIQT_CONV_UP re-orders output channels to [sub-position][channel]). */
+int diqt_conv_pack(const diqt_conv_desc* d, const float* w, const float* bias, void* packed_w, float* packed_bias,
+                   void* stream);
+
+/* A plan owns the TMA descriptors of one conv call site (input / output pointers are baked in). */
+typedef struct diqt_conv_plan diqt_conv_plan;
+int diqt_conv_plan_create(const diqt_conv_desc* d, const void* in, void* out, const void* packed_w,
+                          const float* packed_bias, diqt_conv_plan** plan);
+void diqt_conv_plan_destroy(diqt_conv_plan* plan);
+int diqt_conv_run(const diqt_conv_plan* plan, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Channel statistics, GroupNorm + FiLM + Mish, SE gate, residual.
+ * Replaces nn.GroupNorm :546, the FiLM line :559-561, nn.Mish :547, SE3D :617-632 and the
+ * residual add :612 of Block / ResnetBlock.
+ * ------------------------------------------------------------------------------------------ */
+/* per-block partial channel sums: partial[n][nblk][c][2] (sum, sum of squares), fp32; block b of volume i
+ * covers voxels [b*ceil(voxels/nblk), ...).  Reduced in a fixed order -> bitwise reproducible. */
+int diqt_channel_stats(const void* x, int dtype, int n, int64_t voxels, int c, int ld, int nblk,
+                       float* partial, void* stream);
+/* Fold GroupNorm(groups, c, eps) (+ optional FiLM) into a per-(n,c) affine  y = a*x + b.
+ * film: NULL or fp32 rows [..][film_ld] holding (scale[c], shift[c]) at film[row][0..2c);
+ * row = (film_row ? *film_row : 0) + i * film_row_stride_n   (film_row is a DEVICE pointer so a
+ * captured graph can follow the sampler step). */
+int diqt_gn_finalize(const float* partial, int n, int nblk, int64_t voxels, int c, int groups, float eps,
+                     const float* gamma, const float* beta, const float* film, int film_ld,
+                     const int32_t* film_row, int film_row_stride_n, float* a, float* b, void* stream);
+/* y = mish(a[n][c] * x + b[n][c]) */
+int diqt_affine_mish(const void* x, int ld_x, void* y, int ld_y, int dtype, int n, int64_t voxels, int c,
+                     const float* a, const float* b, int nblk, void* stream);
+/* gate[n][c] = sigmoid(W2 . relu(W1 . mean[n][:])), mean from the channel partial sums;
+ * W1: (hidden, c)  W2: (c, hidden), bias-free */
+int diqt_se_gate(const float* partial, int n, int nblk, int64_t voxels, int c, int hidden, const float* w1,
+                 const float* w2, float* gate, void* stream);
+/* out = h * gate[n][c] + res  (gate may be NULL -> 1); if partial != NULL also writes per-block channel
+ * stats of out (the input of the next GroupNorm) */
+int diqt_scale_residual(const void* h, int ld_h, const void* res, int ld_res, void* out, int ld_out, int dtype,
+                        int n, int64_t voxels, int c, const float* gate, int nblk, float* partial, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Network ends.
+ * ------------------------------------------------------------------------------------------ */
+/* init_conv (:1291, :1576): 3x3x3 conv over up to 8 single-channel fp32 planes (the channel
+ * concat of x_t, low-res patch, ...) -> channels-last activations.  planes[i] points at a
+ * (n, d0, d1, d2) fp32 volume with batch stride plane_stride[i] elements.
+ * w: fp32 packed [27][c_in][c_out]; */
+int diqt_init_conv(const float* const* planes, const int64_t* plane_stride, int c_in, const float* w_packed,
+                   const float* bias, void* out, int ld_out, int dtype, int n, int d0, int d1, int d2, int c_out,
+                   void* stream);
+int diqt_init_conv_pack(const float* w, int c_out, int c_in, float* packed, void* stream);
+
+/* final_conv (:1477, 1x1x1, c -> c_out<=4) producing the fp32 NCDHW prediction, optionally fused
+ * with the DDPM update of Imagen.p_mean_variance / p_sample / q_posterior (:1976-2056, :290-309):
+ *   x0 = clamp(pred);  mean = an*(x_t*(1-c)/al + c*x0);  x_next = mean + ns*noise
+ * sched: DEVICE fp32 table [steps][8] = (alpha, sigma, c, alpha_next, noise_scale, lo, hi, objective)
+ * read at row *step.  step_mode 0: only write pred.  1: fused update (x_t, noise, x_next, x0). */
+int diqt_final_conv(const void* x, int ld, int dtype, int n, int64_t voxels, int c, int c_out, const float* w,
+                    const float* bias, float* pred, int step_mode, const float* sched, const int32_t* step,
+                    const float* x_t, const float* noise, float* x_next, float* x0, void* stream);
+/* the same elementwise update on an existing prediction (used with dynamic thresholding) */
+int diqt_ddpm_update(const float* pred, const float* sched, const int32_t* step, const float* x_t,
+                     const float* noise, float* x_next, float* x0, int64_t count, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Time conditioning (:518-533, :1305-1316, :586-589): tiny dense layers, run once per
+ * sampler for all steps.
+ * ------------------------------------------------------------------------------------------ */
+/* out[r][0] = t[r]; out[r][1+j] = sin(2 pi t w_j); out[r][1+half+j] = cos(2 pi t w_j) */
+int diqt_fourier_features(const float* t, int rows, const float* w, int half, float* out, void* stream);
+/* y[r][o] = act_out( sum_k act_in(x[r][k]) * W[o][k] + b[o] );  act: 0 none, 1 mish */
+int diqt_linear(const float* x, int ldx, int rows, int k, const float* w, const float* b, int out_features,
+                float* y, int ldy, int act_in, int act_out, void* stream);
+/* increments a device step counter (last node of the captured step graph) */
+int diqt_advance_step(int32_t* step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIQT_H_ */

@@ -1,0 +1,84 @@
+"""Case table shared by make_golden.py (reference side) and the tests (oracle / CUDA side)."""
+from __future__ import annotations
+
+import torch
+
+from diffusioniqt_b200.synth import synthetic_field
+
+MIN_BOUND = (0.0 - 271.64814106698583) / 377.117173547721      # train.py:72 with config.yaml:12-13
+
+
+def _unet(dim, **kw):
+    base = dict(dim=dim, init_dim=dim, dim_mults=(1, 2, 4), num_resnet_blocks=(2, 2, 2), channels=1,
+                lowres_cond=True, init_cross_embed=False, attend_at_middle=False,
+                attend_at_enc=(False, False, False), use_se_attn=True, pixel_shuffle_upsample=True,
+                memory_efficient=False, deep_feature=False, boundary=False, batch_sample=False)
+    base.update(kw)
+    return base
+
+
+# U-Net forward cases: {name: {unet kwargs, batch, size, seeds, log-SNR values, hooked submodules}}
+FORWARD_CASES = {
+    # driver architecture (train.py:83-116) at a CPU-sized patch
+    "driver_dim64_s16": dict(unet=_unet(64), batch=1, size=16, weight_seed=11, input_seed=21,
+                             log_snr=[2.5], taps=("init_conv", "downs.0.1", "downs.0.4", "downs.2.4", "ups.0.0", "ups.0.1", "final_res_block")),
+    # BASELINE config 1 architecture (dim 32), two different noise levels in one batch
+    "cfg1_dim32_s16_b2": dict(unet=_unet(32), batch=2, size=16, weight_seed=12, input_seed=22,
+                              log_snr=[-4.0, 6.0], taps=("downs.1.3.1", "ups.1.2.1")),
+    # deep_feature=True executes the mid block (imagen_pytorch3D.py:1633-1651)
+    "deep_dim32_s8": dict(unet=_unet(32, deep_feature=True), batch=1, size=8, weight_seed=13, input_seed=23,
+                          log_snr=[0.3], taps=("mid_block",)),
+    # eval_config.yaml geometry: 27 sub-volumes with boundary exchange (imagen_pytorch3D.py:37-46)
+    "boundary_dim32_s8": dict(unet=_unet(32, boundary=True, batch_sample=True), batch=27, size=8, weight_seed=14,
+                              input_seed=24, log_snr=[1.0] * 27, taps=("downs.0.1",)),
+    # different depth / width pattern and skip scaling
+    "alt_dim32_s16": dict(unet=_unet(32, dim_mults=(1, 2), num_resnet_blocks=(1, 2), scale_skip_connection=True, init_dim=64),
+                          batch=1, size=16, weight_seed=15, input_seed=25, log_snr=[-1.0], taps=()),
+}
+
+# Full-sampler cases (Imagen.sample with injected noise)
+SAMPLE_CASES = {
+    "cfg1_dim32_s16_t12": dict(unet=_unet(32), batch=1, size=16, timesteps=12, weight_seed=31, input_seed=41,
+                               noise_seed=51, min_bound=MIN_BOUND, norm="z-score"),
+    "driver_dim64_s8_t6_b2": dict(unet=_unet(64), batch=2, size=8, timesteps=6, weight_seed=32, input_seed=42,
+                                  noise_seed=52, min_bound=MIN_BOUND, norm="z-score"),
+    "minmax_dim32_s8_t8": dict(unet=_unet(32), batch=1, size=8, timesteps=8, weight_seed=33, input_seed=43,
+                               noise_seed=53, min_bound=MIN_BOUND, norm="min-max"),
+    "noise_obj_dim32_s8_t8": dict(unet=_unet(32), batch=1, size=8, timesteps=8, weight_seed=34, input_seed=44,
+                                  noise_seed=54, min_bound=MIN_BOUND, norm="min-max", pred_objective="noise"),
+    "boundary_dim32_s8_t4": dict(unet=_unet(32, boundary=True, batch_sample=True), batch=27, size=8, timesteps=4,
+                                 weight_seed=35, input_seed=45, noise_seed=55, min_bound=MIN_BOUND, norm="z-score",
+                                 boundary=True),
+    "skip_dim32_s8_t20_skip4": dict(unet=_unet(32), batch=1, size=8, timesteps=20, skip_steps=4, weight_seed=36,
+                                    input_seed=46, noise_seed=56, min_bound=MIN_BOUND, norm="z-score"),
+}
+
+
+def unet_kwargs_for_reference(case):
+    kw = dict(case["unet"])
+    kw.setdefault("img_size", case["size"])
+    return kw
+
+
+def make_configs(case):
+    """The nested dict the reference reads inside the sampler (imagen_pytorch3D.py:2016, 2023, 2154)."""
+    return {"Data": {"norm": case.get("norm", "z-score")}, "Train": {"batch_sample": case["unet"].get("batch_sample", False)}}
+
+
+def build_inputs(case):
+    B, S = case["batch"], case["size"]
+    x = synthetic_field((B, 1, S, S, S), case["input_seed"])
+    lr = synthetic_field((B, 1, S, S, S), case["input_seed"] + 1000)
+    time = torch.tensor(case.get("log_snr", [0.0] * B), dtype=torch.float32)
+    return x, lr, time
+
+
+def sample_noise_count(case):
+    T = case["timesteps"]
+    skip = case.get("skip_steps")
+    return (len(range(0, T, skip)) + 1 if skip and skip > 1 else T) + 1
+
+
+def tap_digest(v):
+    """Strided sub-sample of an activation (B, C, D, H, W): every 8th channel, every 2nd voxel."""
+    return v[:1, ::8, ::2, ::2, ::2].contiguous()
