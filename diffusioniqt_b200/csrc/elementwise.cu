@@ -288,6 +288,22 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
     block_channel_reduce<VEC>(s, q, col, lane, lanes, c, partial + ((int64_t)n * nblk + blk) * c * 2, smem);
 }
 
+// ---- dst = src * scale  (row-pitched copy; the scaled skip connection, imagen_pytorch3D.py:1346, 1653) ----------
+template <typename T>
+__global__ void scale_copy_kernel(const T* __restrict__ src, int ld_src, T* __restrict__ dst, int ld_dst, int64_t rows,
+                                  int nvec, float scale) {
+  const int64_t total = rows * nvec;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / nvec;
+    const int col = (int)(i - r * nvec);
+    Vec<T> v;
+    v.load(src + r * ld_src + col * Vec<T>::N);
+#pragma unroll
+    for (int k = 0; k < Vec<T>::N; ++k) v.v[k] *= scale;
+    v.store(dst + r * ld_dst + col * Vec<T>::N);
+  }
+}
+
 static inline int64_t vox_per_block(int64_t voxels, int nblk) { return (voxels + nblk - 1) / nblk; }
 
 }  // namespace diqt
@@ -376,4 +392,21 @@ extern "C" int diqt_scale_residual(const void* h, int ld_h, const void* res, int
                                                              ld_out, voxels, c, m.nvec, m.lanes,
                                                              vox_per_block(voxels, nblk), gate, partial);
   return check_launch("scale_residual");
+}
+
+extern "C" int diqt_scale_copy(const void* src, int ld_src, void* dst, int ld_dst, int dtype, int64_t rows, int c, float scale,
+                               void* stream) {
+  const int vec = dtype == DIQT_BF16 ? 8 : 4;
+  DIQT_REQUIRE(src && dst && rows > 0, "scale_copy: bad arguments");
+  DIQT_REQUIRE(c % vec == 0 && ld_src % vec == 0 && ld_dst % vec == 0, "scale_copy: c=%d not a multiple of %d", c, vec);
+  const int nvec = c / vec;
+  int64_t blocks = (rows * nvec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DIQT_BF16)
+    scale_copy_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)src, ld_src, (__nv_bfloat16*)dst, ld_dst,
+                                                                     rows, nvec, scale);
+  else
+    scale_copy_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)src, ld_src, (float*)dst, ld_dst, rows, nvec, scale);
+  return check_launch("scale_copy");
 }

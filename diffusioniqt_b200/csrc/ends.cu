@@ -150,7 +150,9 @@ __global__ void final_conv_kernel(const T* __restrict__ x, int ld, int64_t voxel
     }
     if (valid && col == 0) {
       const int64_t b = row / voxels, v = row - b * voxels;
-      for (int co = 0; co < c_out; ++co) {
+#pragma unroll
+      for (int co = 0; co < MAXCO; ++co) {
+        if (co >= c_out) break;
         const float p = acc[co] + bias[co];
         const int64_t o = (b * c_out + co) * voxels + v;  // NCDHW fp32
         if (!step_mode) {
@@ -221,6 +223,11 @@ __global__ void linear_kernel(const float* __restrict__ x, int ldx, int k, const
 }
 
 __global__ void advance_step_kernel(int32_t* step) { *step += 1; }
+
+__global__ void clamp_kernel(float* __restrict__ x, int64_t count, float lo, float hi) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = fminf(fmaxf(x[i], lo), hi);
+}
 
 }  // namespace diqt
 
@@ -328,4 +335,12 @@ extern "C" int diqt_advance_step(int32_t* step, void* stream) {
   DIQT_REQUIRE(step, "advance_step: null pointer");
   advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
   return check_launch("advance_step");
+}
+
+extern "C" int diqt_clamp(float* x, int64_t count, float lo, float hi, void* stream) {
+  DIQT_REQUIRE(x && count > 0, "clamp: bad arguments");
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  clamp_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, count, lo, hi);
+  return check_launch("clamp");
 }

@@ -1,0 +1,415 @@
+"""UnetEngine: one compiled instance of the 3-D U-Net forward for a fixed (batch, volume, dtype).
+
+It owns the device buffers (channels-last activations, packed weights, statistics scratch), the
+conv plans (TMA descriptors) and an ordered list of kernel launches that reproduces
+`Unet.forward` (/root/reference/imagen_pytorch3D.py:1554-1684).  PyTorch is used for device
+memory and streams only; every arithmetic op is a call into libdiqt_b200.so.
+
+Fusions relative to the reference's op list:
+  * GroupNorm + FiLM + Mish  -> channel-stats pass, tiny finalize, one affine+Mish pass
+  * SE pool / gate / scale + residual add -> stats pass, tiny gate kernel, one fused pass that also
+    emits the statistics the next block's GroupNorm needs
+  * skip concat (:1653)      -> producers write straight into a row-pitched concat buffer
+  * pixel-unshuffle / pixel-shuffle (+Mish) -> folded into the 1x1x1 conv's loads / stores
+  * time MLPs of all blocks  -> one dense layer, evaluated once per sampler for all steps
+  * final 1x1x1 conv + clamp + posterior + noise (:1976-2056) -> one kernel
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional
+
+import torch
+
+from . import lib as L
+
+
+class Act:
+    """A channels-last activation view: n volumes x voxels rows of `c` channels, row pitch `ld`."""
+
+    __slots__ = ("buf", "ptr", "c", "ld", "stats")
+
+    def __init__(self, buf: torch.Tensor, c: int, ld: int, offset: int = 0):
+        self.buf = buf
+        self.ptr = buf.data_ptr() + offset * buf.element_size()
+        self.c, self.ld = c, ld
+        self.stats = None  # (partial tensor, nblk) when a producer already reduced this tensor
+
+
+def _nblk(n: int, voxels: int) -> int:
+    return max(1, min(voxels // 128, max(1, 592 // n)))
+
+
+class UnetEngine:
+    def __init__(self, unet, batch: int, dims, dtype: str = "bf16", device=None, conv_impl: str = "auto"):
+        self.lib = L.load()
+        if not torch.cuda.is_available():
+            raise L.DiqtError("UnetEngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda")
+        self.unet = unet
+        self.n = int(batch)
+        self.dims0 = tuple(int(d) for d in dims)
+        assert len(self.dims0) == 3
+        self.dtype = dtype
+        self.tdtype = torch.bfloat16 if dtype == "bf16" else torch.float32
+        self.ddtype = L.BF16 if dtype == "bf16" else L.F32
+        self.impl = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tc": L.IMPL_TC}[conv_impl]
+        if dtype == "fp32":
+            self.impl = L.IMPL_SIMT
+        if unet.boundary:
+            raise NotImplementedError("boundary=True (sub-volume halo exchange, imagen_pytorch3D.py:37-46) is not built yet")
+        nl = len(unet.in_out)
+        for d in self.dims0:
+            if d % (1 << (nl - 1)) != 0:
+                raise ValueError(f"volume side {d} is not divisible by 2^{nl - 1}")
+        self.nl = nl
+        self.level_dims = [tuple(d >> l for d in self.dims0) for l in range(nl)]
+        self.level_vox = [a * b * c for (a, b, c) in self.level_dims]
+        self._plans: List[int] = []
+        self._keep: List[torch.Tensor] = []   # packed weights etc.
+        self._ops = []                        # callables(stream)
+        self._film_rows = 0
+        self.film_row_ptr = 0                 # device int32* (sampler step) or NULL
+        self.film_stride_n = 1
+        self.conv_impls = {}                  # site name -> resolved impl (for tests / reporting)
+        self._build()
+
+    # ------------------------------------------------------------------ helpers
+    def _empty(self, *shape, dtype=None):
+        return torch.empty(*shape, dtype=dtype or self.tdtype, device=self.device)
+
+    def _f32(self, t: torch.Tensor) -> torch.Tensor:
+        t = t.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        self._keep.append(t)
+        return t
+
+    def _conv_site(self, name, mode, level_in, c_in, ld_in, c_out, ld_out, weight, bias, src_ptr, dst_ptr):
+        d0, d1, d2 = self.level_dims[level_in]
+        desc = L.ConvDesc(mode=mode, dtype=self.ddtype, impl=self.impl, n=self.n, d0=d0, d1=d1, d2=d2,
+                          c_in=c_in, ld_in=ld_in, c_out=c_out, ld_out=ld_out, flags=0)
+        impl = C.c_int(0)
+        L.check(self.lib.diqt_conv_resolved_impl(C.byref(desc), C.byref(impl)), f"conv {name}")
+        self.conv_impls[name] = impl.value
+        nbytes = C.c_size_t(0)
+        L.check(self.lib.diqt_conv_packed_bytes(C.byref(desc), C.byref(nbytes)), f"conv {name}")
+        packed = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        pbias = torch.empty(c_out, dtype=torch.float32, device=self.device)
+        w = weight.detach().to(device=self.device, dtype=torch.float32)
+        if self.dtype == "bf16":
+            w = w.to(torch.bfloat16).to(torch.float32)  # both kernel families see the same bf16-rounded weights
+        w = w.contiguous()
+        b = bias.detach().to(device=self.device, dtype=torch.float32).contiguous() if bias is not None else None
+        st = L.current_stream()
+        L.check(self.lib.diqt_conv_pack(C.byref(desc), w.data_ptr(), L.ptr(b), packed.data_ptr(), pbias.data_ptr(), st), f"pack {name}")
+        torch.cuda.current_stream().synchronize()  # w / b temporaries may be freed after this
+        self._keep += [packed, pbias]
+        plan = C.c_void_p(0)
+        L.check(self.lib.diqt_conv_plan_create(C.byref(desc), src_ptr, dst_ptr, packed.data_ptr(), pbias.data_ptr(), C.byref(plan)),
+                f"plan {name}")
+        self._plans.append(plan.value)
+        run, pv = self.lib.diqt_conv_run, plan.value
+        return lambda st: L.check(run(pv, st), name)
+
+    # ------------------------------------------------------------------ build
+    def _build(self):
+        u, lib, n = self.unet, self.lib, self.n
+        nl, dims = self.nl, u.dims
+        nblocks = u.num_resnet_blocks
+        ops = self._ops
+        dd = self.ddtype
+
+        # ---- inputs (static, so that a captured graph can be replayed)
+        ch = u.channels
+        sp = self.dims0
+        self.x_in = self._empty(n, ch, *sp, dtype=torch.float32)
+        self.lowres = self._empty(n, ch, *sp, dtype=torch.float32) if u.lowres_cond else None
+        self.cond_images = self._empty(n, u.cond_images_channels, *sp, dtype=torch.float32) if u.has_cond_image else None
+        vox0 = self.level_vox[0]
+        planes, strides = [], []
+        # channel order of the reference's concats (:1569-1584): [cond_images, x, lowres]
+        for t in (self.cond_images, self.x_in, self.lowres):
+            if t is None:
+                continue
+            for c in range(t.shape[1]):
+                planes.append(t.data_ptr() + c * vox0 * 4)
+                strides.append(t.shape[1] * vox0)
+        assert len(planes) == u.init_channels, (len(planes), u.init_channels)
+        if len(planes) > 8:
+            raise NotImplementedError("init_conv with more than 8 input channels")
+        self._planes = (C.c_void_p * len(planes))(*planes)
+        self._pstrides = (C.c_int64 * len(planes))(*strides)
+
+        # ---- widest channel count at each resolution level (sizes the shared scratch buffers)
+        need = [0] * nl
+        for l in range(nl):
+            need[l] = max(need[l], dims[l], dims[l + 1] if l == nl - 1 else 0)
+        for l in range(nl - 1):
+            need[l] = max(need[l], dims[l + 1] + dims[l])
+        need[0] = max(need[0], u._locals["dim"], dims[0])
+        cmax = max(need)
+
+        # ---- scratch for statistics / affine parameters
+        self.nblk = [_nblk(n, v) for v in self.level_vox]
+        pmax = max(self.nblk) * n * cmax * 2
+        self.part = [torch.zeros(pmax, dtype=torch.float32, device=self.device) for _ in range(3)]
+        self.aff_a = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
+        self.aff_b = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
+        self.gate = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
+        self._pp = 0  # ping-pong index of block-output partial buffers (part[0], part[1]); part[2] is intra-block scratch
+
+        # ---- time conditioning weights
+        th = u.to_time_hiddens
+        self.w_four = self._f32(th[0].weights)
+        self.w_t1, self.b_t1 = self._f32(th[1].weight), self._f32(th[1].bias)
+        self.w_t2, self.b_t2 = self._f32(u.to_time_cond[0].weight), self._f32(u.to_time_cond[0].bias)
+        self.tdim = u.time_cond_dim
+        self._film_w, self._film_b, self._film_cols = [], [], 0
+
+        def film_slot(block):
+            off = self._film_cols
+            self._film_w.append(block.time_mlp[1].weight.detach())
+            self._film_b.append(block.time_mlp[1].bias.detach())
+            self._film_cols += 2 * block.dim_out
+            return off
+
+        # ---- activation buffers per resolution level
+        def act_buf(level, c):
+            return Act(self._empty(n * self.level_vox[level], c), c, c)
+
+        # concat buffers for the up path: Cat[l] lives at resolution level l and holds [up output (dims[l+1]) | skip (dims[l])]
+        self.cat = {l: self._empty(n * self.level_vox[l], dims[l + 1] + dims[l]) for l in range(nl - 1)}
+
+        # A (normalised input), H (conv output), R (res_conv output): shared by all blocks of a level
+        scratch = {l: dict(c=need[l], A=self._empty(n * self.level_vox[l], need[l]), H=self._empty(n * self.level_vox[l], need[l]),
+                           R=self._empty(n * self.level_vox[l], need[l])) for l in range(nl)}
+
+        def level_scratch(level, c_need):
+            assert scratch[level]["c"] >= c_need, (level, c_need, scratch[level]["c"])
+            return scratch[level]
+
+        pingpong = {}
+
+        def next_out(level, c):
+            key = (level, c)
+            if key not in pingpong:
+                pingpong[key] = [act_buf(level, c), act_buf(level, c), 0]
+                self._keep += [pingpong[key][0].buf, pingpong[key][1].buf]
+            pp = pingpong[key]
+            pp[2] ^= 1
+            return pp[pp[2]]
+
+        gnf, aff, stats_fn, seg, sres = lib.diqt_gn_finalize, lib.diqt_affine_mish, lib.diqt_channel_stats, lib.diqt_se_gate, lib.diqt_scale_residual
+        eng = self
+
+        def add_stats(x: Act, level, part):
+            nb, vox = self.nblk[level], self.level_vox[level]
+            xp, xc, xl, pp = x.ptr, x.c, x.ld, part.data_ptr()
+            ops.append(lambda st: L.check(stats_fn(xp, dd, n, vox, xc, xl, nb, pp, st), "channel_stats"))
+            return (part, nb)
+
+        def add_norm_act(x: Act, level, gn, film_off, dst_buf, name):
+            """GroupNorm(+FiLM)+Mish of x into dst_buf[:, :x.c]; returns the Act."""
+            part, nb = x.stats
+            vox = self.level_vox[level]
+            gamma, beta = self._f32(gn.weight), self._f32(gn.bias)
+            groups, eps = gn.num_groups, float(gn.eps)
+            pa, pb, pp = self.aff_a.data_ptr(), self.aff_b.data_ptr(), part.data_ptr()
+            gp, bp, c = gamma.data_ptr(), beta.data_ptr(), x.c
+            if film_off is None:
+                ops.append(lambda st: L.check(gnf(pp, n, nb, vox, c, groups, eps, gp, bp, 0, 0, 0, 0, pa, pb, st), name + ".gn"))
+            else:
+                def op(st, film_off=film_off):
+                    fptr = eng.film.data_ptr() + film_off * 4
+                    L.check(gnf(pp, n, nb, vox, c, groups, eps, gp, bp, fptr, eng._film_cols, eng.film_row_ptr, eng.film_stride_n, pa, pb, st), name + ".gn")
+                ops.append(op)
+            dst = Act(dst_buf, x.c, x.c)
+            xp, xl, dp, dl, nbk = x.ptr, x.ld, dst.ptr, dst.ld, self.nblk[level]
+            ops.append(lambda st: L.check(aff(xp, xl, dp, dl, dd, n, vox, c, pa, pb, nbk, st), name + ".mish"))
+            return dst
+
+        def add_resblock(blk, x: Act, level, out: Act, name):
+            cin, cout = blk.dim, blk.dim_out
+            assert x.c == cin and out.c == cout, (name, x.c, cin, out.c, cout)
+            sc = level_scratch(level, max(cin, cout))
+            vox = self.level_vox[level]
+            tmp = self.part[2]
+            if x.stats is None:
+                x.stats = add_stats(x, level, self.part[self._pp])
+                self._pp ^= 1
+            film_off = film_slot(blk)
+            a1 = add_norm_act(x, level, blk.block1.groupnorm, None, sc["A"], name + ".block1")
+            h = Act(sc["H"], cout, cout)
+            ops.append(self._conv_site(name + ".block1.project", L.CONV_K3, level, cin, a1.ld, cout, h.ld, blk.block1.project.weight,
+                                       blk.block1.project.bias, a1.ptr, h.ptr))
+            h.stats = add_stats(h, level, tmp)
+            a2 = add_norm_act(h, level, blk.block2.groupnorm, film_off, sc["A"], name + ".block2")
+            ops.append(self._conv_site(name + ".block2.project", L.CONV_K3, level, cout, a2.ld, cout, h.ld, blk.block2.project.weight,
+                                       blk.block2.project.bias, a2.ptr, h.ptr))
+            gate_ptr = 0
+            if blk.has_se:
+                part, nb = add_stats(h, level, tmp)
+                w1, w2 = self._f32(blk.se.fc[0].weight), self._f32(blk.se.fc[2].weight)
+                hidden = w1.shape[0]
+                if hidden < 1:
+                    raise ValueError(f"{name}: SE3D with {cout} channels has an empty bottleneck (reduction 16)")
+                gate_ptr = self.gate.data_ptr()
+                pp, w1p, w2p = part.data_ptr(), w1.data_ptr(), w2.data_ptr()
+                ops.append(lambda st: L.check(seg(pp, n, nb, vox, cout, hidden, w1p, w2p, gate_ptr, st), name + ".se"))
+            if blk.has_res_conv:
+                r = Act(sc["R"], cout, cout)
+                ops.append(self._conv_site(name + ".res_conv", L.CONV_K1, level, cin, x.ld, cout, r.ld, blk.res_conv.weight, blk.res_conv.bias,
+                                           x.ptr, r.ptr))
+            else:
+                r = x
+            opart = self.part[self._pp]
+            self._pp ^= 1
+            nbk = self.nblk[level]
+            hp, hl, rp, rl, op_, ol, opp = h.ptr, h.ld, r.ptr, r.ld, out.ptr, out.ld, opart.data_ptr()
+            ops.append(lambda st: L.check(sres(hp, hl, rp, rl, op_, ol, dd, n, vox, cout, gate_ptr, nbk, opp, st), name + ".residual"))
+            out.stats = (opart, nbk)
+            return out
+
+        # ---- init conv
+        x = next_out(0, dims[0])
+        self.w_init = torch.empty(27 * u.init_channels * dims[0], dtype=torch.float32, device=self.device)
+        wi = self._f32(u.init_conv.weight)
+        self.b_init = self._f32(u.init_conv.bias)
+        L.check(lib.diqt_init_conv_pack(wi.data_ptr(), dims[0], u.init_channels, self.w_init.data_ptr(), L.current_stream()), "init_conv_pack")
+        d0, d1, d2 = self.dims0
+        xp, xl, c0, nin = x.ptr, x.ld, dims[0], u.init_channels
+        wip, bip = self.w_init.data_ptr(), self.b_init.data_ptr()
+        planes_ref, strides_ref = self._planes, self._pstrides
+        ops.append(lambda st: L.check(lib.diqt_init_conv(planes_ref, strides_ref, nin, wip, bip, xp, xl, dd, n, d0, d1, d2, c0, st), "init_conv"))
+
+        # ---- down path
+        skip_scale = u.skip_connect_scale
+        for l in range(nl):
+            c = dims[l]
+            level_blocks = [(u.downs[l][1], f"downs.{l}.1")] + [(b, f"downs.{l}.3.{i}") for i, b in enumerate(u.downs[l][3])]
+            for j, (blk, name) in enumerate(level_blocks):
+                last_of_level = j == len(level_blocks) - 1
+                if last_of_level and l != nl - 1 and skip_scale == 1.0:
+                    out = Act(self.cat[l], c, dims[l + 1] + c, offset=dims[l + 1])  # write the skip straight into the concat buffer
+                else:
+                    out = next_out(l, c)
+                x = add_resblock(blk, x, l, out, name)
+            if l != nl - 1:
+                if skip_scale != 1.0:
+                    dst = Act(self.cat[l], c, dims[l + 1] + c, offset=dims[l + 1])
+                    rows = n * self.level_vox[l]
+                    sp_, sl, dp_, dl = x.ptr, x.ld, dst.ptr, dst.ld
+                    ops.append(lambda st, sp_=sp_, sl=sl, dp_=dp_, dl=dl, rows=rows, c=c: L.check(
+                        lib.diqt_scale_copy(sp_, sl, dp_, dl, dd, rows, c, skip_scale, st), "skip_scale"))
+                nxt = next_out(l + 1, dims[l + 1])
+                conv = u.downs[l][4][1]
+                ops.append(self._conv_site(f"downs.{l}.4.1", L.CONV_DOWN, l, c, x.ld, dims[l + 1], nxt.ld, conv.weight, conv.bias, x.ptr, nxt.ptr))
+                x = nxt
+            else:
+                conv = u.downs[l][4]
+                nxt = next_out(l, dims[l + 1])
+                ops.append(self._conv_site(f"downs.{l}.4", L.CONV_K1, l, c, x.ld, dims[l + 1], nxt.ld, conv.weight, conv.bias, x.ptr, nxt.ptr))
+                x = nxt
+
+        level = nl - 1
+        if u.deep_feature:
+            x = add_resblock(u.mid_block, x, level, next_out(level, dims[-1]), "mid_block")
+
+        # ---- up path
+        for ui in range(nl):
+            upsample, init_block, blocks = u.ups[ui]
+            last = ui == nl - 1
+            if not last:
+                lo = nl - 2 - ui                      # resolution level of the output
+                c_up = dims[lo + 1]
+                ctot = c_up + dims[lo]
+                conv = upsample.net[0]
+                cat = Act(self.cat[lo], ctot, ctot)
+                # GEMM N = 8*c_up; stored channels c_up at pitch ctot (channel offset 0 of the concat buffer)
+                ops.append(self._conv_site(f"ups.{ui}.0.net.0", L.CONV_UP, lo + 1, x.c, x.ld, 8 * c_up, ctot, conv.weight, conv.bias, x.ptr, cat.ptr))
+                x, level = cat, lo
+            x = add_resblock(init_block, x, level, next_out(level, init_block.dim_out), f"ups.{ui}.1")
+            for i, blk in enumerate(blocks):
+                x = add_resblock(blk, x, level, next_out(level, blk.dim_out), f"ups.{ui}.2.{i}")
+
+        if u.final_res_block is not None:
+            x = add_resblock(u.final_res_block, x, 0, next_out(0, u.final_res_block.dim_out), "final_res_block")
+        self.last_act = x
+        self._scratch = scratch
+
+        # ---- final conv
+        self.w_final = self._f32(u.final_conv.weight.reshape(u.channels_out, -1))
+        self.b_final = self._f32(u.final_conv.bias)
+        self.pred = self._empty(n, u.channels_out, *sp, dtype=torch.float32)
+        self.film_w = self._f32(torch.cat([w.to(self.device) for w in self._film_w], dim=0))
+        self.film_b = self._f32(torch.cat([b.to(self.device) for b in self._film_b], dim=0))
+        self.film = None
+        torch.cuda.current_stream().synchronize()
+
+    # ------------------------------------------------------------------ conditioning
+    def set_condition(self, log_snr: torch.Tensor, stream=None):
+        """Evaluate the time MLPs for `log_snr` (R,) -> FiLM table [R][sum 2C] (one row per batch element for
+        a plain forward, one row per sampler step in the sampler)."""
+        lib = self.lib
+        st = stream if stream is not None else L.current_stream()
+        rows = int(log_snr.shape[0])
+        t = log_snr.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        half = self.w_four.shape[0]
+        if self.film is None or self._film_rows < rows:
+            self._film_rows = rows
+            self.four = torch.empty(rows, 1 + 2 * half, dtype=torch.float32, device=self.device)
+            self.thid = torch.empty(rows, self.tdim, dtype=torch.float32, device=self.device)
+            self.tcond = torch.empty(rows, self.tdim, dtype=torch.float32, device=self.device)
+            self.film = torch.empty(rows, self._film_cols, dtype=torch.float32, device=self.device)
+        self._t_keep = t
+        L.check(lib.diqt_fourier_features(t.data_ptr(), rows, self.w_four.data_ptr(), half, self.four.data_ptr(), st), "fourier")
+        L.check(lib.diqt_linear(self.four.data_ptr(), 1 + 2 * half, rows, 1 + 2 * half, self.w_t1.data_ptr(), self.b_t1.data_ptr(), self.tdim,
+                                self.thid.data_ptr(), self.tdim, 0, 1, st), "to_time_hiddens")
+        L.check(lib.diqt_linear(self.thid.data_ptr(), self.tdim, rows, self.tdim, self.w_t2.data_ptr(), self.b_t2.data_ptr(), self.tdim,
+                                self.tcond.data_ptr(), self.tdim, 0, 0, st), "to_time_cond")
+        L.check(lib.diqt_linear(self.tcond.data_ptr(), self.tdim, rows, self.tdim, self.film_w.data_ptr(), self.film_b.data_ptr(), self._film_cols,
+                                self.film.data_ptr(), self._film_cols, 1, 0, st), "time_mlps")
+
+    # ------------------------------------------------------------------ execution
+    def run_body(self, stream=None):
+        st = stream if stream is not None else L.current_stream()
+        for op in self._ops:
+            op(st)
+
+    def run_final(self, stream=None, *, fused=False, sched=0, step=0, noise=0, x0=0):
+        """final 1x1x1 conv; fused=True also applies the DDPM update in place on x_in."""
+        st = stream if stream is not None else L.current_stream()
+        x, u = self.last_act, self.unet
+        L.check(self.lib.diqt_final_conv(x.ptr, x.ld, self.ddtype, self.n, self.level_vox[0], x.c, u.channels_out, self.w_final.data_ptr(),
+                                         self.b_final.data_ptr(), self.pred.data_ptr(), 1 if fused else 0, sched, step,
+                                         self.x_in.data_ptr(), noise, self.x_in.data_ptr(), x0, st), "final_conv")
+
+    def load_inputs(self, x=None, lowres_cond_img=None, cond_images=None):
+        if x is not None:
+            self.x_in.copy_(x, non_blocking=True)
+        if self.lowres is not None and lowres_cond_img is not None:
+            self.lowres.copy_(lowres_cond_img, non_blocking=True)
+        if self.cond_images is not None and cond_images is not None:
+            self.cond_images.copy_(cond_images, non_blocking=True)
+
+    def forward(self, x, time, *, lowres_cond_img=None, cond_images=None, self_cond=None):
+        assert tuple(x.shape) == tuple(self.x_in.shape), (x.shape, self.x_in.shape)
+        assert time.shape[0] == self.n
+        self.load_inputs(x, lowres_cond_img, cond_images)
+        self.set_condition(time)
+        self.film_row_ptr, self.film_stride_n = 0, 1
+        self.run_body()
+        self.run_final()
+        return self.pred.clone()
+
+    def close(self):
+        for p in self._plans:
+            self.lib.diqt_conv_plan_destroy(p)
+        self._plans = []
+        self._ops = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

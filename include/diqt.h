@@ -126,6 +126,11 @@ int diqt_se_gate(const float* partial, int n, int nblk, int64_t voxels, int c, i
 int diqt_scale_residual(const void* h, int ld_h, const void* res, int ld_res, void* out, int ld_out, int dtype,
                         int n, int64_t voxels, int c, const float* gate, int nblk, float* partial, void* stream);
 
+/* dst[r][0..c) = src[r][0..c) * scale over `rows` pitched rows: the scaled skip connection
+ * (scale_skip_connection, :1346, :1653) when it cannot be a pure view */
+int diqt_scale_copy(const void* src, int ld_src, void* dst, int ld_dst, int dtype, int64_t rows, int c, float scale,
+                    void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Network ends.
  * ------------------------------------------------------------------------------------------ */
@@ -149,6 +154,9 @@ int diqt_final_conv(const void* x, int ld, int dtype, int n, int64_t voxels, int
 /* the same elementwise update on an existing prediction (used with dynamic thresholding) */
 int diqt_ddpm_update(const float* pred, const float* sched, const int32_t* step, const float* x_t,
                      const float* noise, float* x_next, float* x0, int64_t count, void* stream);
+
+/* x = min(max(x, lo), hi): the clamp after the loop (:2154-2157) */
+int diqt_clamp(float* x, int64_t count, float lo, float hi, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Time conditioning (:518-533, :1305-1316, :586-589): tiny dense layers, run once per

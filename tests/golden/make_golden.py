@@ -64,8 +64,11 @@ def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     ref = ref_shim.load_reference()
 
+    import json
+    contract = {}
     for name, case in FORWARD_CASES.items():
         unet = build_reference_unet(ref, case)
+        contract[name] = [[k, list(v.shape)] for k, v in unet.state_dict().items()]
         x, lr, time = build_inputs(case)
         acts = {}
         hooks = []
@@ -81,6 +84,9 @@ def main():
             out["tap:" + k] = tap_digest(v).numpy()
         np.savez_compressed(os.path.join(HERE, f"fwd_{name}.npz"), **out)
         print(f"fwd_{name}: out {tuple(y.shape)} std {y.std():.4f}")
+
+    with open(os.path.join(HERE, "state_dict_contract.json"), "w") as f:
+        json.dump(contract, f)
 
     for name, case in SAMPLE_CASES.items():
         unet = build_reference_unet(ref, case)
