@@ -1,0 +1,122 @@
+"""Tensor-level wrappers over the C ABI (one call = one or a few kernels).
+
+Used by the per-kernel parity tests and handy for experiments; the engine binds the same entry
+points with pre-resolved pointers.  Activations are channels-last: `(n, d0, d1, d2, c)` tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as L
+
+_MODES = {"k3": L.CONV_K3, "k1": L.CONV_K1, "down": L.CONV_DOWN, "up": L.CONV_UP}
+_IMPLS = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tc": L.IMPL_TC}
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.bfloat16:
+        return L.BF16
+    if t.dtype == torch.float32:
+        return L.F32
+    raise TypeError(f"unsupported activation dtype {t.dtype}")
+
+
+def to_channels_last(x: torch.Tensor, dtype=None) -> torch.Tensor:
+    """(n, c, d0, d1, d2) -> contiguous (n, d0, d1, d2, c)."""
+    y = x.permute(0, 2, 3, 4, 1).contiguous()
+    return y.to(dtype) if dtype is not None else y
+
+
+def from_channels_last(x: torch.Tensor) -> torch.Tensor:
+    return x.permute(0, 4, 1, 2, 3).contiguous().float()
+
+
+def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], mode: str = "k3", impl: str = "auto") -> torch.Tensor:
+    """x: (n, d0, d1, d2, c_in) bf16/fp32 on CUDA; weight/bias exactly as in the reference state_dict (fp32)."""
+    lib = L.load()
+    n, d0, d1, d2, c_in = x.shape
+    x = x.contiguous()
+    c_out = weight.shape[0]
+    if mode == "down":
+        assert weight.shape[1] == 8 * c_in
+        out = torch.empty(n, d0 // 2, d1 // 2, d2 // 2, c_out, dtype=x.dtype, device=x.device)
+        ld_out = c_out
+    elif mode == "up":
+        out = torch.empty(n, 2 * d0, 2 * d1, 2 * d2, c_out // 8, dtype=x.dtype, device=x.device)
+        ld_out = c_out // 8
+    else:
+        out = torch.empty(n, d0, d1, d2, c_out, dtype=x.dtype, device=x.device)
+        ld_out = c_out
+    desc = L.ConvDesc(mode=_MODES[mode], dtype=_dt(x), impl=_IMPLS[impl], n=n, d0=d0, d1=d1, d2=d2, c_in=c_in, ld_in=c_in,
+                      c_out=c_out, ld_out=ld_out, flags=0)
+    nbytes = C.c_size_t(0)
+    L.check(lib.diqt_conv_packed_bytes(C.byref(desc), C.byref(nbytes)), "conv_packed_bytes")
+    packed = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
+    pbias = torch.empty(c_out, dtype=torch.float32, device=x.device)
+    w = weight.detach().to(device=x.device, dtype=torch.float32)
+    if x.dtype == torch.bfloat16:
+        w = w.to(torch.bfloat16).float()
+    w = w.contiguous()
+    b = bias.detach().to(device=x.device, dtype=torch.float32).contiguous() if bias is not None else None
+    st = L.current_stream()
+    L.check(lib.diqt_conv_pack(C.byref(desc), w.data_ptr(), L.ptr(b), packed.data_ptr(), pbias.data_ptr(), st), "conv_pack")
+    plan = C.c_void_p(0)
+    L.check(lib.diqt_conv_plan_create(C.byref(desc), x.data_ptr(), out.data_ptr(), packed.data_ptr(), pbias.data_ptr(), C.byref(plan)), "conv_plan")
+    try:
+        L.check(lib.diqt_conv_run(plan.value, st), "conv_run")
+        torch.cuda.current_stream().synchronize()
+    finally:
+        lib.diqt_conv_plan_destroy(plan.value)
+    return out
+
+
+def channel_stats(x: torch.Tensor, nblk: int = 8) -> torch.Tensor:
+    """-> partial sums (n, nblk, c, 2)."""
+    lib = L.load()
+    n, c = x.shape[0], x.shape[-1]
+    vox = x.numel() // (n * c)
+    part = torch.empty(n, nblk, c, 2, dtype=torch.float32, device=x.device)
+    L.check(lib.diqt_channel_stats(x.data_ptr(), _dt(x), n, vox, c, c, nblk, part.data_ptr(), L.current_stream()), "channel_stats")
+    return part
+
+
+def group_norm_film_mish(x: torch.Tensor, groups: int, gamma, beta, scale_shift: Optional[torch.Tensor] = None, eps: float = 1e-5, nblk: int = 8):
+    """GroupNorm(groups) -> [x*(scale+1)+shift] -> Mish.  scale_shift: (n, 2c) fp32 rows (scale | shift) or None."""
+    lib = L.load()
+    n, c = x.shape[0], x.shape[-1]
+    vox = x.numel() // (n * c)
+    part = channel_stats(x, nblk)
+    a = torch.empty(n, c, dtype=torch.float32, device=x.device)
+    b = torch.empty_like(a)
+    g = gamma.detach().float().contiguous().to(x.device)
+    be = beta.detach().float().contiguous().to(x.device)
+    film = scale_shift.detach().float().contiguous().to(x.device) if scale_shift is not None else None
+    st = L.current_stream()
+    L.check(lib.diqt_gn_finalize(part.data_ptr(), n, nblk, vox, c, groups, eps, g.data_ptr(), be.data_ptr(), L.ptr(film), 2 * c, 0, 1,
+                                 a.data_ptr(), b.data_ptr(), st), "gn_finalize")
+    y = torch.empty_like(x)
+    L.check(lib.diqt_affine_mish(x.data_ptr(), c, y.data_ptr(), c, _dt(x), n, vox, c, a.data_ptr(), b.data_ptr(), nblk, st), "affine_mish")
+    torch.cuda.current_stream().synchronize()
+    return y
+
+
+def se_scale_residual(h: torch.Tensor, res: torch.Tensor, w1, w2, nblk: int = 8):
+    """SE3D gate on h, then h*gate + res.  Returns (out, gate, partial stats of out)."""
+    lib = L.load()
+    n, c = h.shape[0], h.shape[-1]
+    vox = h.numel() // (n * c)
+    st = L.current_stream()
+    part = channel_stats(h, nblk)
+    gate = torch.empty(n, c, dtype=torch.float32, device=h.device)
+    w1 = w1.detach().float().contiguous().to(h.device)
+    w2 = w2.detach().float().contiguous().to(h.device)
+    L.check(lib.diqt_se_gate(part.data_ptr(), n, nblk, vox, c, w1.shape[0], w1.data_ptr(), w2.data_ptr(), gate.data_ptr(), st), "se_gate")
+    out = torch.empty_like(h)
+    opart = torch.empty(n, nblk, c, 2, dtype=torch.float32, device=h.device)
+    L.check(lib.diqt_scale_residual(h.data_ptr(), c, res.data_ptr(), c, out.data_ptr(), c, _dt(h), n, vox, c, gate.data_ptr(), nblk,
+                                    opart.data_ptr(), st), "scale_residual")
+    torch.cuda.current_stream().synchronize()
+    return out, gate, opart

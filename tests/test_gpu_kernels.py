@@ -1,0 +1,158 @@
+"""Per-kernel parity of the CUDA library against plain fp32 PyTorch on the CPU (the library the reference calls).
+
+Tolerances (BASELINE.json north_star): 1e-5 relative in fp32 mode, 1e-2 relative in bf16 mode, where
+"relative" = max |a-b| / max |b| for one kernel's output.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import max_rel
+from oracle.unet_oracle import pixel_shuffle3d, pixel_unshuffle3d
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+BF16_TOL = 1e-2
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def _conv_reference(x, w, b, mode):
+    if mode == "k3":
+        return F.conv3d(x, w, b, padding=1)
+    if mode == "k1":
+        return F.conv3d(x, w, b)
+    if mode == "down":
+        return F.conv3d(pixel_unshuffle3d(x), w, b)
+    return pixel_shuffle3d(F.mish(F.conv3d(x, w, b)))
+
+
+def _conv_weight(mode, c_in, c_out, seed):
+    k = 3 if mode == "k3" else 1
+    cin_w = c_in * 8 if mode == "down" else c_in
+    fan = cin_w * k ** 3
+    return _rand(c_out, cin_w, k, k, k, seed=seed, scale=fan ** -0.5), _rand(c_out, seed=seed + 1, scale=0.1)
+
+
+CONV_SHAPES = [
+    # mode, n, (d0,d1,d2), c_in, c_out
+    ("k3", 1, (8, 8, 8), 16, 16),
+    ("k3", 2, (4, 6, 10), 32, 48),
+    ("k3", 1, (16, 16, 16), 64, 64),
+    ("k3", 1, (8, 8, 8), 192, 128),
+    ("k1", 2, (4, 4, 4), 128, 64),
+    ("k1", 1, (8, 8, 8), 192, 128),
+    ("down", 1, (8, 8, 8), 64, 128),
+    ("down", 2, (4, 8, 16), 16, 32),
+    ("up", 1, (4, 4, 4), 128, 512),
+    ("up", 2, (2, 4, 8), 32, 128),
+]
+
+
+@pytest.mark.parametrize("mode,n,dims,c_in,c_out", CONV_SHAPES)
+def test_conv_simt_fp32(mode, n, dims, c_in, c_out):
+    from diffusioniqt_b200 import ops
+    x = _rand(n, c_in, *dims, seed=1)
+    w, b = _conv_weight(mode, c_in, c_out, 2)
+    want = _conv_reference(x, w, b, mode)
+    got = ops.conv3d(ops.to_channels_last(x.cuda()), w, b, mode=mode, impl="simt")
+    assert max_rel(ops.from_channels_last(got).cpu(), want) < FP32_TOL
+
+
+@pytest.mark.parametrize("mode,n,dims,c_in,c_out", CONV_SHAPES)
+def test_conv_simt_bf16(mode, n, dims, c_in, c_out):
+    from diffusioniqt_b200 import ops
+    x = _rand(n, c_in, *dims, seed=3).bfloat16().float()
+    w, b = _conv_weight(mode, c_in, c_out, 4)
+    want = _conv_reference(x, w.bfloat16().float(), b, mode)
+    got = ops.conv3d(ops.to_channels_last(x.cuda(), torch.bfloat16), w, b, mode=mode, impl="simt")
+    assert max_rel(ops.from_channels_last(got).cpu(), want) < BF16_TOL
+
+
+TC_SHAPES = [
+    ("k3", 1, (16, 16, 16), 64, 64),
+    ("k3", 1, (8, 8, 8), 128, 128),
+    ("k3", 1, (8, 8, 8), 192, 128),
+    ("k3", 2, (4, 4, 4), 128, 128),      # volume smaller than the 8x4x4 box: batch folded into the tile
+    ("k3", 1, (12, 12, 12), 64, 64),     # edge tiles (12 is not a multiple of the box)
+    ("k3", 1, (32, 32, 32), 64, 64),
+    ("k3", 3, (2, 2, 2), 128, 128),
+    ("k1", 1, (8, 8, 8), 192, 128),
+    ("k1", 1, (16, 16, 16), 128, 64),
+    ("k1", 2, (4, 4, 4), 128, 256),
+    ("down", 1, (16, 16, 16), 64, 64),
+    ("down", 1, (8, 8, 8), 64, 128),
+    ("up", 1, (4, 4, 4), 256, 1024),
+    ("up", 1, (8, 8, 8), 128, 512),
+]
+
+
+@pytest.mark.parametrize("mode,n,dims,c_in,c_out", TC_SHAPES)
+def test_conv_tcgen05_bf16(mode, n, dims, c_in, c_out):
+    from diffusioniqt_b200 import ops
+    x = _rand(n, c_in, *dims, seed=5).bfloat16().float()
+    w, b = _conv_weight(mode, c_in, c_out, 6)
+    want = _conv_reference(x, w.bfloat16().float(), b, mode)
+    got = ops.conv3d(ops.to_channels_last(x.cuda(), torch.bfloat16), w, b, mode=mode, impl="tc")
+    assert max_rel(ops.from_channels_last(got).cpu(), want) < BF16_TOL
+
+
+def test_conv_tcgen05_matches_simt_closely():
+    """Same bf16 operands, fp32 accumulation in both: the two kernel families agree to bf16 output rounding."""
+    from diffusioniqt_b200 import ops
+    x = ops.to_channels_last(_rand(1, 64, 16, 16, 16, seed=7).cuda(), torch.bfloat16)
+    w, b = _conv_weight("k3", 64, 64, 8)
+    a = ops.conv3d(x, w, b, mode="k3", impl="tc").float()
+    c = ops.conv3d(x, w, b, mode="k3", impl="simt").float()
+    assert max_rel(a, c) < 2 ** -7
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+@pytest.mark.parametrize("n,dims,c,groups,film", [(1, (8, 8, 8), 64, 8, True), (2, (4, 6, 10), 96, 8, False), (3, (2, 2, 2), 128, 8, True),
+                                                   (1, (16, 16, 16), 192, 8, True)])
+def test_group_norm_film_mish(dtype, tol, n, dims, c, groups, film):
+    from diffusioniqt_b200 import ops
+    x = (_rand(n, c, *dims, seed=9) * 1.7 + 0.4)
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    gamma, beta = 1 + 0.2 * _rand(c, seed=10), 0.1 * _rand(c, seed=11)
+    ss = 0.5 * _rand(n, 2 * c, seed=12) if film else None
+    want = F.group_norm(x, groups, gamma, beta, eps=1e-5)
+    if film:
+        sc, sh = ss[:, :c, None, None, None], ss[:, c:, None, None, None]
+        want = want * (sc + 1) + sh
+    want = F.mish(want)
+    got = ops.group_norm_film_mish(ops.to_channels_last(x.cuda(), dtype), groups, gamma, beta, ss.cuda() if film else None, nblk=5)
+    assert max_rel(ops.from_channels_last(got).cpu(), want) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+def test_se_scale_residual(dtype, tol):
+    from diffusioniqt_b200 import ops
+    n, c, dims = 2, 64, (6, 4, 8)
+    h, r = _rand(n, c, *dims, seed=13), _rand(n, c, *dims, seed=14)
+    if dtype == torch.bfloat16:
+        h, r = h.bfloat16().float(), r.bfloat16().float()
+    w1, w2 = _rand(c // 16, c, seed=15, scale=0.3), _rand(c, c // 16, seed=16, scale=0.8)
+    y = torch.sigmoid(F.linear(torch.relu(F.linear(h.mean(dim=(2, 3, 4)), w1)), w2))
+    want = h * y[:, :, None, None, None] + r
+    out, gate, part = ops.se_scale_residual(ops.to_channels_last(h.cuda(), dtype), ops.to_channels_last(r.cuda(), dtype), w1, w2, nblk=7)
+    assert max_rel(gate.cpu(), y) < 1e-5
+    assert max_rel(ops.from_channels_last(out).cpu(), want) < tol
+    # the fused statistics describe the stored output
+    stored = ops.from_channels_last(out).cpu()
+    s = part.sum(dim=1).cpu()
+    assert max_rel(s[..., 0], stored.sum(dim=(2, 3, 4))) < 1e-4
+    assert max_rel(s[..., 1], (stored ** 2).sum(dim=(2, 3, 4))) < 1e-4
+
+
+def test_channel_stats_is_deterministic():
+    from diffusioniqt_b200 import ops
+    x = ops.to_channels_last(_rand(2, 64, 8, 8, 8, seed=17).cuda(), torch.bfloat16)
+    a, b = ops.channel_stats(x, 13), ops.channel_stats(x, 13)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
