@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the DiffusionIQT sampling hot path (BASELINE.json metric: 3-D patches/sec through the
+full denoise loop).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one full pass of the sampler (T denoising iterations of the driver-config U-Net) over one
+batch of synthetic low-field patches.  Workload at N=1 is BASELINE config 2: a single 64^3 patch, the U-Net of
+train.py:83-116 + config/config.yaml, T = 1000, bf16.  For N > 1 (torchrun, one rank per GPU) every rank
+denoises its own patch(es) (weak scaling) and the denoised patches are all-gathered for stitching.
+
+Prints ONE JSON line on rank 0 (see the task contract): value = device-resident throughput, e2e = the same
+through Imagen.sample() with host buffers, roofline = the dominant kernel (3x3x3 conv 64->64 at 64^3) timed
+live with CUDA events, cpu_baseline = the CPU oracle port timed on this box's host cores.
+`--impl reference` times the reference's CPU algorithm (oracle port; the Python reference itself cannot
+travel to the GPU box) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+DRIVER_UNET = dict(dim=64, init_dim=64, dim_mults=(1, 2, 4), num_resnet_blocks=(2, 2, 2), channels=1, lowres_cond=True,
+                   init_cross_embed=False, attend_at_middle=False, attend_at_enc=(False, False, False), use_se_attn=True,
+                   memory_efficient=False, pixel_shuffle_upsample=True, deep_feature=False, boundary=False, batch_sample=False)
+MIN_BOUND = (0.0 - 271.64814106698583) / 377.117173547721
+FLOPS_PER_FWD_64 = 1488.442865152e9       # BASELINE.md section 3 (B=1, 64^3, driver config)
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(burst=p.get("bf16_tflops", 1590.0), sustained=p.get("bf16_tflops_sustained", 1400.0), hbm=p.get("hbm_gbs", 6650.0), source="measured")
+    return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                    power_w_max=max(power) if power else None)
+
+
+def build_model(timesteps, device, dtype):
+    from diffusioniqt_b200 import Imagen, NullUnet, SRUnet256
+    from diffusioniqt_b200.synth import synthetic_state_dict
+    unet = SRUnet256(**DRIVER_UNET, img_size=64)
+    unet.load_state_dict(synthetic_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, seed=0))
+    configs = {"Data": {"norm": "z-score"}, "Train": {"batch_sample": False}}
+    imagen = Imagen(unets=(NullUnet(), unet), configs=configs, image_sizes=(64, 64), channels=1, min_bound=MIN_BOUND, timesteps=timesteps,
+                    pred_objectives="x_start", dynamic_thresholding=False, p2_loss_weight_gamma=0.0, auto_normalize_img=False,
+                    cond_drop_prob=0.0).to(device)
+    imagen.unets[1].set_compute_dtype(dtype)
+    return imagen
+
+
+def time_dominant_kernel(size, batch, reps=20):
+    """The 3x3x3 conv 64->64 at full resolution (82 % of all FLOPs), alone, CUDA events."""
+    import ctypes as C
+    from diffusioniqt_b200 import lib as L
+    lib = L.load()
+    dev = torch.device("cuda")
+    n, c = batch, 64
+    # two input/output pairs, alternated, so consecutive launches do not hit the same lines in L2 (each tensor 32 MiB at 64^3)
+    bufs = [(torch.randn(n, size, size, size, c, device=dev).bfloat16(), torch.empty(n, size, size, size, c, device=dev, dtype=torch.bfloat16)) for _ in range(4)]
+    w = torch.randn(c, c, 3, 3, 3, device=dev) * 0.02
+    b = torch.zeros(c, device=dev)
+    desc = L.ConvDesc(mode=L.CONV_K3, dtype=L.BF16, impl=L.IMPL_TC, n=n, d0=size, d1=size, d2=size, c_in=c, ld_in=c, c_out=c, ld_out=c, flags=0)
+    nbytes = C.c_size_t(0)
+    L.check(lib.diqt_conv_packed_bytes(C.byref(desc), C.byref(nbytes)))
+    packed = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    pb = torch.empty(c, dtype=torch.float32, device=dev)
+    st = L.current_stream()
+    L.check(lib.diqt_conv_pack(C.byref(desc), w.data_ptr(), b.data_ptr(), packed.data_ptr(), pb.data_ptr(), st))
+    plans = []
+    for xi, yo in bufs:
+        p = C.c_void_p(0)
+        L.check(lib.diqt_conv_plan_create(C.byref(desc), xi.data_ptr(), yo.data_ptr(), packed.data_ptr(), pb.data_ptr(), C.byref(p)))
+        plans.append(p.value)
+    for p in plans:
+        L.check(lib.diqt_conv_run(p, st))
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    ev[0].record()
+    for i in range(reps):
+        L.check(lib.diqt_conv_run(plans[i % len(plans)], st))
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    times = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
+    for p in plans:
+        lib.diqt_conv_plan_destroy(p)
+    flops = 2.0 * c * c * 27 * n * size ** 3
+    ms = sum(times) / len(times)
+    return dict(ms=ms, ms_min=min(times), flops=flops, tflops=flops / (ms * 1e-3) / 1e12)
+
+
+def cpu_baseline(size, timesteps, batch, denoise_steps, threads=None):
+    """The CPU oracle port (same algorithm as the reference's CPU sampler) on a bounded sample: `denoise_steps`
+    iterations of the sampler at the benchmark shape; patches/s is extrapolated to `timesteps` iterations."""
+    from diffusioniqt_b200 import SRUnet256
+    from diffusioniqt_b200.synth import synthetic_field, synthetic_state_dict
+    from oracle.ddpm_oracle import alpha_cosine_log_snr, q_posterior
+    from oracle.unet_oracle import UnetSpec, unet_forward
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    shapes = {k: tuple(v.shape) for k, v in SRUnet256(**DRIVER_UNET, img_size=size).state_dict().items()}
+    sd = synthetic_state_dict(shapes, seed=0)
+    spec = UnetSpec(dim=64, init_dim=64, dim_mults=(1, 2, 4), num_resnet_blocks=(2, 2, 2), channels=1, lowres_cond=True, deep_feature=False)
+    lr = synthetic_field((batch, 1, size, size, size), 1)
+    x = torch.randn(batch, 1, size, size, size)
+    times = torch.linspace(1.0, 0.0, timesteps + 1)
+
+    def one(i):
+        nonlocal x
+        t, tn = times[i].expand(batch), times[i + 1].expand(batch)
+        with torch.no_grad():
+            x0 = unet_forward(sd, spec, x, alpha_cosine_log_snr(t), lowres_cond_img=lr).clamp(min=MIN_BOUND)
+            mean, _, log_var = q_posterior(x0, x, t, tn)
+            x = mean + (0.5 * log_var).exp() * torch.randn_like(x)
+
+    one(0)  # warm-up (oneDNN primitive creation)
+    t0 = time.perf_counter()
+    for i in range(denoise_steps):
+        one(1 + i)
+    dt = (time.perf_counter() - t0) / denoise_steps
+    return dict(value=batch / (dt * timesteps), unit="patches/s", cores=threads, kind="port", ms_per_denoise_step=dt * 1e3,
+                sample=f"{denoise_steps} of {timesteps} denoising iterations of one {size}^3 patch (batch {batch}), oracle/ CPU port of the reference "
+                       f"sampler, torch {torch.__version__} fp32, extrapolated linearly to {timesteps} iterations")
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    per_step = max(1, args.ref_denoise_steps)
+    vals, ms = [], []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = cpu_baseline(args.size, args.timesteps, args.batch, per_step)
+        if i >= args.warmup:
+            vals.append(r["value"])
+            ms.append((time.perf_counter() - t0) * 1e3)
+    v = statistics.median(vals)
+    r["value"] = v
+    line = dict(impl="reference", metric="3D patches/sec (full denoise loop)", value=v, unit="patches/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=1e3 / v * args.batch, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", config=workload_config(args), cpu_baseline=r,
+                e2e=dict(value=v, unit="patches/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0,
+                note="reference CPU algorithm (oracle port) on host cores; one bench step = a bounded sample, value extrapolated to the full sampler")
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return dict(workload=f"BASELINE config 2: single {args.size}^3 patch, SRUnet256 driver config (dim 64, mults 1-2-4, 2 resnet blocks/level, SE, "
+                         f"deep_feature off), {args.timesteps}-step DDPM sampler, batch {args.batch} per GPU",
+                patch=args.size, batch_per_gpu=args.batch, timesteps=args.timesteps, parallelism=f"patch-parallel x{args.gpus}",
+                l2="per-step working set ~0.4 GB of activations > 126 MB L2; no explicit flush")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--timesteps", type=int, default=1000)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-denoise-steps", type=int, default=3, help="bounded CPU-baseline sample (denoising iterations)")
+    ap.add_argument("--ref-denoise-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    from diffusioniqt_b200 import lib as L
+    from diffusioniqt_b200.synth import synthetic_field
+    L.load()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    imagen = build_model(args.timesteps, dev, args.dtype)
+    unet, sched = imagen.unets[1], imagen.noise_schedulers[1]
+    B, S = args.batch, args.size
+    shape = (B, 1, S, S, S)
+    lr_host = synthetic_field(shape, 100 + rank).pin_memory()
+    lr_dev = lr_host.to(dev)
+    gathered = torch.empty((world,) + shape, dtype=torch.float32, device=dev) if dist is not None else None
+
+    def device_step():
+        imagen.return_host_lists = False
+        img, _, _ = imagen.p_sample_loop(unet, shape, noise_scheduler=sched, lowres_cond_img=lr_dev, pred_objective="x_start",
+                                         dynamic_threshold=False, use_tqdm=False)
+        if dist is not None:
+            dist.all_gather_into_tensor(gathered, img)       # the only collective on the path: denoised patches for stitching
+        return img
+
+    def e2e_step():
+        imagen.return_host_lists = True
+        img, _, lst = imagen.sample(batch_size=B, start_image_or_video=lr_host, start_at_unet_number=2, use_tqdm=False)
+        if dist is not None:
+            dist.all_gather_into_tensor(gathered, img)
+        return img.cpu()
+
+    torch.manual_seed(1234 + rank)
+    for _ in range(args.warmup):
+        device_step()
+    launches0 = L.launch_count()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = device_step()
+    e1.record()
+    barrier()
+    clk = clocks.stop()
+    elapsed_ms = e0.elapsed_time(e1)
+    eager_launches = L.launch_count() - launches0
+    graph_launches = imagen.last_graph_launches * args.timesteps * args.steps
+    assert torch.isfinite(out).all(), "non-finite sampler output"
+
+    # ---- end to end through the public API with host buffers
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+
+    if dist is not None:
+        t = torch.tensor([elapsed_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        peaks = read_peaks()
+        patches = world * B * args.steps
+        value = patches / (elapsed_ms * 1e-3)
+        ms_per_step = elapsed_ms / args.steps
+        flops_per_patch = FLOPS_PER_FWD_64 * (S / 64.0) ** 3 * args.timesteps
+        step_tflops = value / world * flops_per_patch / 1e12
+        dom = time_dominant_kernel(S, B)
+        roofline = dict(bound="tensor", kernel="conv_tc_kernel 3x3x3 64->64 @%d^3 (batch %d)" % (S, B), achieved=dom["tflops"], peak=peaks["burst"],
+                        unit="TFLOP/s", frac=dom["tflops"] / peaks["burst"], traffic=None, ms_per_launch=dom["ms"], flops_per_launch=dom["flops"],
+                        peak_source=peaks["source"] + " (burst: kernel timed alone)",
+                        whole_step=dict(achieved=step_tflops, peak=peaks["sustained"], frac=step_tflops / peaks["sustained"], unit="TFLOP/s",
+                                        note="all FLOPs of the U-Net / wall time of the sampler, per GPU, vs sustained bf16 peak"))
+        line = dict(metric="3D patches/sec (full denoise loop)", value=value, unit="patches/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
+                    config=workload_config(args), clocks=clk,
+                    e2e=dict(value=patches / (e2e_ms * 1e-3), unit="patches/s", h2d_bytes_per_step=B * S ** 3 * 4, d2h_bytes_per_step=3 * B * S ** 3 * 4),
+                    gpu_launches=int(graph_launches + eager_launches), ms_per_denoise_iteration=ms_per_step / args.timesteps,
+                    roofline=roofline)
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(S, args.timesteps, B, args.cpu_denoise_steps)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
