@@ -15,6 +15,7 @@ int conv_tc_pack(const diqt_conv_desc* d, const float* w, void* packed, cudaStre
 int conv_tc_plan(const diqt_conv_desc* d, const void* in, void* out, const void* packed, const float* bias, TcPlan** plan);
 int conv_tc_run(const TcPlan* plan, cudaStream_t st);
 void conv_tc_destroy(TcPlan* plan);
+int conv_tc_set_stats(TcPlan* plan, float* partial);
 }  // namespace diqt
 
 using namespace diqt;
@@ -129,4 +130,10 @@ extern "C" int diqt_conv_run(const diqt_conv_plan* plan, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (plan->impl == DIQT_IMPL_TC) return conv_tc_run(plan->tc, st);
   return conv_simt_run(&plan->d, plan->in, plan->out, plan->packed, plan->bias, st);
+}
+
+extern "C" int diqt_conv_plan_set_stats(diqt_conv_plan* plan, float* partial, int* nblk) {
+  DIQT_REQUIRE(plan && partial && nblk, "conv_plan_set_stats: null pointer");
+  *nblk = plan->impl == DIQT_IMPL_TC ? conv_tc_set_stats(plan->tc, partial) : 0;
+  return DIQT_OK;
 }

@@ -147,6 +147,11 @@ struct TcParams {
   int stages;
   uint32_t idesc;
   uint32_t tmem_cols;
+  // fused channel statistics of the stored output (for the next GroupNorm / the SE pool); NULL = off
+  float* stats;          // [n][gridDim.x][c_out][2]
+  int n_batch;           // volumes
+  int ox, oy, oz;        // output voxel grid (to mask rows of edge tiles)
+  int edge_tiles;        // 1 if some tile sticks out of the volume
 };
 
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
@@ -158,7 +163,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   uint8_t* stage_base = smem;
   uint8_t* out_stage = stage_base + (size_t)p.stages * stage_bytes;
   float* s_bias = reinterpret_cast<float*>(out_stage + (size_t)(p.block_n / 64) * kABytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + p.n_tiles * p.block_n);
+  float* s_red = s_bias + p.n_tiles * p.block_n;  // [4][block_n][2] statistics scratch
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 4 * p.block_n * 2);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* tfull_bar = bars + 2 * p.stages;
@@ -260,9 +266,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     const int ngroups = p.block_n / 64;
+    // fused statistics: thread -> (column pair cp of a 64-column group, row quarter rq); sums live in registers
+    const int cp = et & 31, rq = et >> 5;
+    float st_s[4][2], st_q[4][2];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) st_s[g][0] = st_s[g][1] = st_q[g][0] = st_q[g][1] = 0.f;
+    int st_n = -1, st_first = -1;
+    auto flush_stats = [&](int nvol) {
+      // combine the four row quarters in a fixed order -> one partial per (volume, CTA): deterministic
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (g < ngroups) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            s_red[(rq * p.block_n + g * 64 + cp * 2 + h) * 2] = st_s[g][h];
+            s_red[(rq * p.block_n + g * 64 + cp * 2 + h) * 2 + 1] = st_q[g][h];
+            st_s[g][h] = st_q[g][h] = 0.f;
+          }
+        }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* dst = p.stats + ((size_t)nvol * gridDim.x + blockIdx.x) * p.block_n * 2;
+      for (int col = et; col < p.block_n; col += 128) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+          a += s_red[(r4 * p.block_n + col) * 2];
+          b += s_red[(r4 * p.block_n + col) * 2 + 1];
+        }
+        dst[col * 2] = a;
+        dst[col * 2 + 1] = b;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
       int n_tile, x0, y0, z0, b0;
       decode_tile(work, n_tile, x0, y0, z0, b0);
+      if (p.stats) {
+        if (st_n >= 0 && b0 != st_n) flush_stats(st_n);
+        if (st_first < 0) st_first = b0;
+        st_n = b0;
+      }
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       tc_fence_after();
       if (et == 0) bulk_wait_read0();  // previous tile's TMA stores have finished reading the staging tile
@@ -306,7 +349,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         bulk_commit();
       }
+      if (p.stats) {
+        // column sums of the staged (bf16-rounded) tile: a warp reads one 128 B row per step -> conflict free
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          if (g < ngroups) {
+            const uint8_t* gb = out_stage + (size_t)g * kABytes;
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+              const int rr = rq * 32 + r;
+              if (p.edge_tiles) {
+                const int lx = rr % p.bx, ly = (rr / p.bx) % p.by, lz = rr / (p.bx * p.by);
+                if (x0 + lx >= p.ox || y0 + ly >= p.oy || z0 + lz >= p.oz) continue;
+              }
+              const uint32_t v = *reinterpret_cast<const uint32_t*>(gb + (size_t)rr * 128 + (((cp >> 2) ^ (rr & 7)) << 4) + ((cp & 3) << 2));
+              const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
+              st_s[g][0] += lo; st_q[g][0] = fmaf(lo, lo, st_q[g][0]);
+              st_s[g][1] += hi; st_q[g][1] = fmaf(hi, hi, st_q[g][1]);
+            }
+          }
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.stats) {
+      if (st_n >= 0) flush_stats(st_n);
+      // volumes this CTA never touched still need a (zero) partial
+      for (int nv = 0; nv < p.n_batch; ++nv) {
+        if (st_first >= 0 && nv >= st_first && nv <= st_n) continue;
+        float* dst = p.stats + ((size_t)nv * gridDim.x + blockIdx.x) * p.block_n * 2;
+        for (int col = et; col < p.block_n * 2; col += 128) dst[col] = 0.f;
+      }
     }
     if (et == 0) bulk_wait0();
   }
@@ -455,6 +527,10 @@ int conv_tc_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
   p.tiles_n = (d->n + p.bn - 1) / p.bn;
   p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_z * p.tiles_n;
   p.idesc = make_idesc_bf16(kTileM, p.block_n);
+  p.stats = nullptr;
+  p.n_batch = d->n;
+  p.ox = od2; p.oy = od1; p.oz = od0;
+  p.edge_tiles = (od2 % p.bx || od1 % p.by || od0 % p.bz) ? 1 : 0;
   p.tmem_cols = 2 * p.block_n < 32 ? 32 : 2 * p.block_n;  // 128 / 256 / 512: powers of two
 
   const __nv_bfloat16* inb = (const __nv_bfloat16*)in;
@@ -494,7 +570,7 @@ int conv_tc_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
   }
   // shared memory budget
   const int stage_bytes = kABytes + p.block_n * 128;
-  const size_t fixed = (size_t)(p.block_n / 64) * kABytes + (size_t)p.n_tiles * p.block_n * 4 + 256 + 1024;
+  const size_t fixed = (size_t)(p.block_n / 64) * kABytes + (size_t)p.n_tiles * p.block_n * 4 + (size_t)p.block_n * 32 + 256 + 1024;
   int stages = (int)((220 * 1024 - fixed) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) {
@@ -524,5 +600,13 @@ int conv_tc_run(const TcPlan* plan, cudaStream_t st) {
 }
 
 void conv_tc_destroy(TcPlan* plan) { delete plan; }
+
+// Fused output statistics are available when one CTA tile never mixes volumes and N fits one tile.
+int conv_tc_set_stats(TcPlan* plan, float* partial) {
+  TcParams& p = plan->p;
+  if (p.n_tiles != 1 || p.bn != 1 || p.mode == DIQT_CONV_UP) return 0;
+  p.stats = partial;
+  return plan->grid;
+}
 
 }  // namespace diqt

@@ -15,7 +15,7 @@ struct RowMap {
   int nvec, lanes, threads;
 };
 
-static inline RowMap make_rowmap(int c, int vec, int max_threads = 256) {
+static inline RowMap make_rowmap(int c, int vec, int max_threads) {
   RowMap m;
   m.nvec = c / vec;
   m.lanes = max_threads / m.nvec;
@@ -196,30 +196,39 @@ __global__ void affine_mish_kernel(const T* __restrict__ x, int ld_x, T* __restr
 // ---- SE gate from channel partial sums -----------------------------------------------------------
 __global__ void se_gate_kernel(const float* __restrict__ partial, int nblk, int64_t voxels, int c, int hidden,
                                const float* __restrict__ w1, const float* __restrict__ w2, float* __restrict__ gate) {
-  extern __shared__ float sf[];  // mean[c], hid[hidden]
-  float* mean = sf;
-  float* hid = sf + c;
+  extern __shared__ double sd[];  // acc[parts][c] doubles, then mean[c] + hid[hidden] floats
   const int n = blockIdx.x;
+  const int parts = max(1, (int)blockDim.x / c);
+  double* acc = sd;
+  float* mean = reinterpret_cast<float*>(sd + (size_t)parts * c);
+  float* hid = mean + c;
   const float* p = partial + (int64_t)n * nblk * c * 2;
+  for (int idx = threadIdx.x; idx < parts * c; idx += blockDim.x) {
+    const int ch = idx % c, part = idx / c;
+    double s = 0.0;
+    for (int b = part; b < nblk; b += parts) s += (double)p[((int64_t)b * c + ch) * 2];
+    acc[part * c + ch] = s;
+  }
+  __syncthreads();
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     double s = 0.0;
-    for (int b = 0; b < nblk; ++b) s += (double)p[((int64_t)b * c + ch) * 2];
+    for (int part = 0; part < parts; ++part) s += acc[part * c + ch];
     mean[ch] = (float)(s / (double)voxels);
   }
   __syncthreads();
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32, nwarps = blockDim.x / 32;
   for (int j = warp; j < hidden; j += nwarps) {
-    float acc = 0.f;
-    for (int k = lane; k < c; k += 32) acc = fmaf(w1[(int64_t)j * c + k], mean[k], acc);
+    float a = 0.f;
+    for (int k = lane; k < c; k += 32) a = fmaf(w1[(int64_t)j * c + k], mean[k], a);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) hid[j] = fmaxf(acc, 0.f);
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) hid[j] = fmaxf(a, 0.f);
   }
   __syncthreads();
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    float acc = 0.f;
-    for (int j = 0; j < hidden; ++j) acc = fmaf(w2[(int64_t)ch * hidden + j], hid[j], acc);
-    gate[(int64_t)n * c + ch] = 1.f / (1.f + expf(-acc));
+    float a = 0.f;
+    for (int j = 0; j < hidden; ++j) a = fmaf(w2[(int64_t)ch * hidden + j], hid[j], a);
+    gate[(int64_t)n * c + ch] = 1.f / (1.f + expf(-a));
   }
 }
 
@@ -315,7 +324,7 @@ extern "C" int diqt_channel_stats(const void* x, int dtype, int n, int64_t voxel
   const int vec = dtype == DIQT_BF16 ? 8 : 4;
   DIQT_REQUIRE(x && partial && n > 0 && voxels > 0 && nblk > 0, "channel_stats: bad arguments");
   DIQT_REQUIRE(c % vec == 0 && ld % vec == 0 && c / vec <= 256, "channel_stats: c=%d ld=%d not a multiple of %d", c, ld, vec);
-  RowMap m = make_rowmap(c, vec);
+  RowMap m = make_rowmap(c, vec, 512);
   dim3 grid(nblk, n);
   size_t sh = (size_t)2 * m.lanes * c * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
@@ -351,7 +360,7 @@ extern "C" int diqt_affine_mish(const void* x, int ld_x, void* y, int ld_y, int 
   const int vec = dtype == DIQT_BF16 ? 8 : 4;
   DIQT_REQUIRE(x && y && a && b && nblk > 0, "affine_mish: bad arguments");
   DIQT_REQUIRE(c % vec == 0 && ld_x % vec == 0 && ld_y % vec == 0 && c / vec <= 256, "affine_mish: c=%d not a multiple of %d", c, vec);
-  RowMap m = make_rowmap(c, vec);
+  RowMap m = make_rowmap(c, vec, 256);
   dim3 grid(nblk, n);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)
@@ -367,8 +376,11 @@ extern "C" int diqt_affine_mish(const void* x, int ld_x, void* y, int ld_y, int 
 extern "C" int diqt_se_gate(const float* partial, int n, int nblk, int64_t voxels, int c, int hidden, const float* w1,
                             const float* w2, float* gate, void* stream) {
   DIQT_REQUIRE(partial && w1 && w2 && gate && hidden > 0, "se_gate: bad arguments (hidden=%d)", hidden);
-  size_t sh = (size_t)(c + hidden) * sizeof(float);
-  se_gate_kernel<<<n, 256, sh, (cudaStream_t)stream>>>(partial, nblk, voxels, c, hidden, w1, w2, gate);
+  DIQT_REQUIRE(c <= 2048, "se_gate: c=%d too large", c);
+  const int threads = 1024;
+  const int parts = threads / c > 0 ? threads / c : 1;
+  size_t sh = (size_t)parts * c * sizeof(double) + (size_t)(c + hidden) * sizeof(float);
+  se_gate_kernel<<<n, threads, sh, (cudaStream_t)stream>>>(partial, nblk, voxels, c, hidden, w1, w2, gate);
   return check_launch("se_gate");
 }
 
@@ -379,7 +391,7 @@ extern "C" int diqt_scale_residual(const void* h, int ld_h, const void* res, int
   DIQT_REQUIRE(h && res && out && nblk > 0, "scale_residual: bad arguments");
   DIQT_REQUIRE(c % vec == 0 && ld_h % vec == 0 && ld_res % vec == 0 && ld_out % vec == 0 && c / vec <= 256,
                "scale_residual: c=%d not a multiple of %d", c, vec);
-  RowMap m = make_rowmap(c, vec);
+  RowMap m = make_rowmap(c, vec, 512);
   dim3 grid(nblk, n);
   size_t sh = partial ? (size_t)2 * m.lanes * c * sizeof(float) : 0;
   cudaStream_t st = (cudaStream_t)stream;

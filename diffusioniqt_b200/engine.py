@@ -37,8 +37,10 @@ class Act:
         self.stats = None  # (partial tensor, nblk) when a producer already reduced this tensor
 
 
-def _nblk(n: int, voxels: int) -> int:
-    return max(1, min(voxels // 128, max(1, 592 // n)))
+def _nblk(n: int, voxels: int, per_device: int = 148) -> int:
+    """Blocks per volume: reductions use ~one 512-thread block per SM (few partial sums to finalize),
+    pure streaming kernels ~four 256-thread blocks per SM."""
+    return max(1, min(voxels // 128, max(1, per_device // n)))
 
 
 class UnetEngine:
@@ -84,7 +86,9 @@ class UnetEngine:
         self._keep.append(t)
         return t
 
-    def _conv_site(self, name, mode, level_in, c_in, ld_in, c_out, ld_out, weight, bias, src_ptr, dst_ptr):
+    def _conv_site(self, name, mode, level_in, c_in, ld_in, c_out, ld_out, weight, bias, src_ptr, dst_ptr, stats=None):
+        """Pack weights, create the plan, return the launch closure.  With `stats` (an Act + partial buffer) the conv is
+        asked to emit the channel statistics of its output; if it cannot, a separate stats pass is appended by the caller."""
         d0, d1, d2 = self.level_dims[level_in]
         desc = L.ConvDesc(mode=mode, dtype=self.ddtype, impl=self.impl, n=self.n, d0=d0, d1=d1, d2=d2,
                           c_in=c_in, ld_in=ld_in, c_out=c_out, ld_out=ld_out, flags=0)
@@ -109,6 +113,11 @@ class UnetEngine:
                 f"plan {name}")
         self._plans.append(plan.value)
         run, pv = self.lib.diqt_conv_run, plan.value
+        self._last_conv_stats_nblk = 0
+        if stats is not None:
+            nb = C.c_int(0)
+            L.check(self.lib.diqt_conv_plan_set_stats(pv, stats.data_ptr(), C.byref(nb)), f"set_stats {name}")
+            self._last_conv_stats_nblk = nb.value
         return lambda st: L.check(run(pv, st), name)
 
     # ------------------------------------------------------------------ build
@@ -151,7 +160,8 @@ class UnetEngine:
 
         # ---- scratch for statistics / affine parameters
         self.nblk = [_nblk(n, v) for v in self.level_vox]
-        pmax = max(self.nblk) * n * cmax * 2
+        self.nblk_stream = [_nblk(n, v, 592) for v in self.level_vox]
+        pmax = 160 * n * cmax * 2     # up to one partial per SM and volume
         self.part = [torch.zeros(pmax, dtype=torch.float32, device=self.device) for _ in range(3)]
         self.aff_a = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
         self.aff_b = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
@@ -224,7 +234,7 @@ class UnetEngine:
                     L.check(gnf(pp, n, nb, vox, c, groups, eps, gp, bp, fptr, eng._film_cols, eng.film_row_ptr, eng.film_stride_n, pa, pb, st), name + ".gn")
                 ops.append(op)
             dst = Act(dst_buf, x.c, x.c)
-            xp, xl, dp, dl, nbk = x.ptr, x.ld, dst.ptr, dst.ld, self.nblk[level]
+            xp, xl, dp, dl, nbk = x.ptr, x.ld, dst.ptr, dst.ld, self.nblk_stream[level]
             ops.append(lambda st: L.check(aff(xp, xl, dp, dl, dd, n, vox, c, pa, pb, nbk, st), name + ".mish"))
             return dst
 
@@ -241,14 +251,14 @@ class UnetEngine:
             a1 = add_norm_act(x, level, blk.block1.groupnorm, None, sc["A"], name + ".block1")
             h = Act(sc["H"], cout, cout)
             ops.append(self._conv_site(name + ".block1.project", L.CONV_K3, level, cin, a1.ld, cout, h.ld, blk.block1.project.weight,
-                                       blk.block1.project.bias, a1.ptr, h.ptr))
-            h.stats = add_stats(h, level, tmp)
+                                       blk.block1.project.bias, a1.ptr, h.ptr, stats=tmp))
+            h.stats = (tmp, self._last_conv_stats_nblk) if self._last_conv_stats_nblk else add_stats(h, level, tmp)
             a2 = add_norm_act(h, level, blk.block2.groupnorm, film_off, sc["A"], name + ".block2")
             ops.append(self._conv_site(name + ".block2.project", L.CONV_K3, level, cout, a2.ld, cout, h.ld, blk.block2.project.weight,
-                                       blk.block2.project.bias, a2.ptr, h.ptr))
+                                       blk.block2.project.bias, a2.ptr, h.ptr, stats=tmp if blk.has_se else None))
             gate_ptr = 0
             if blk.has_se:
-                part, nb = add_stats(h, level, tmp)
+                part, nb = (tmp, self._last_conv_stats_nblk) if self._last_conv_stats_nblk else add_stats(h, level, tmp)
                 w1, w2 = self._f32(blk.se.fc[0].weight), self._f32(blk.se.fc[2].weight)
                 hidden = w1.shape[0]
                 if hidden < 1:
@@ -303,12 +313,22 @@ class UnetEngine:
                         lib.diqt_scale_copy(sp_, sl, dp_, dl, dd, rows, c, skip_scale, st), "skip_scale"))
                 nxt = next_out(l + 1, dims[l + 1])
                 conv = u.downs[l][4][1]
-                ops.append(self._conv_site(f"downs.{l}.4.1", L.CONV_DOWN, l, c, x.ld, dims[l + 1], nxt.ld, conv.weight, conv.bias, x.ptr, nxt.ptr))
+                opart = self.part[self._pp]
+                ops.append(self._conv_site(f"downs.{l}.4.1", L.CONV_DOWN, l, c, x.ld, dims[l + 1], nxt.ld, conv.weight, conv.bias, x.ptr, nxt.ptr,
+                                           stats=opart))
+                if self._last_conv_stats_nblk:
+                    nxt.stats = (opart, self._last_conv_stats_nblk)
+                    self._pp ^= 1
                 x = nxt
             else:
                 conv = u.downs[l][4]
                 nxt = next_out(l, dims[l + 1])
-                ops.append(self._conv_site(f"downs.{l}.4", L.CONV_K1, l, c, x.ld, dims[l + 1], nxt.ld, conv.weight, conv.bias, x.ptr, nxt.ptr))
+                opart = self.part[self._pp]
+                ops.append(self._conv_site(f"downs.{l}.4", L.CONV_K1, l, c, x.ld, dims[l + 1], nxt.ld, conv.weight, conv.bias, x.ptr, nxt.ptr,
+                                           stats=opart))
+                if self._last_conv_stats_nblk:
+                    nxt.stats = (opart, self._last_conv_stats_nblk)
+                    self._pp ^= 1
                 x = nxt
 
         level = nl - 1

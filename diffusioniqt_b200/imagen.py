@@ -14,6 +14,7 @@ conditioning and inpainting are out of scope and raise.
 from __future__ import annotations
 
 import math
+import os
 from contextlib import contextmanager, nullcontext
 from typing import Optional
 
@@ -201,7 +202,7 @@ class Imagen(nn.Module):
 
         # ---- execution options of this implementation (not in the reference)
         self.keep_trajectory = False   # True: append img / x_start to host lists every step like :2147-2153
-        self.use_cuda_graph = True
+        self.use_cuda_graph = os.environ.get("DIQT_DISABLE_CUDA_GRAPH", "0") != "1"   # profiling runs set the variable
         self.return_host_lists = True  # False: skip the two final host copies too (device-resident benchmarking)
         self.noise_override = None     # tests: an iterable of tensors consumed instead of torch.randn (draw order of the reference)
         self._samplers = {}

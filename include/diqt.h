@@ -95,6 +95,10 @@ int diqt_conv_pack(const diqt_conv_desc* d, const float* w, const float* bias, v
 typedef struct diqt_conv_plan diqt_conv_plan;
 int diqt_conv_plan_create(const diqt_conv_desc* d, const void* in, void* out, const void* packed_w,
                           const float* packed_bias, diqt_conv_plan** plan);
+/* Ask the conv to also emit per-block channel (sum, sumsq) of the output it STORES (bf16-rounded), in the
+ * layout of diqt_channel_stats: partial[n][*nblk][c_out][2].  *nblk = 0 means this plan cannot fuse them
+ * (SIMT family, DIQT_CONV_UP, tiny volumes): run diqt_channel_stats on the output instead. */
+int diqt_conv_plan_set_stats(diqt_conv_plan* plan, float* partial, int* nblk);
 void diqt_conv_plan_destroy(diqt_conv_plan* plan);
 int diqt_conv_run(const diqt_conv_plan* plan, void* stream);
 
