@@ -16,6 +16,15 @@ int conv_tc_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
 int conv_tc_run(const TcPlan* plan, cudaStream_t st);
 void conv_tc_destroy(TcPlan* plan);
 int conv_tc_set_stats(TcPlan* plan, float* partial);
+struct ZmPlan;
+bool conv_zm_supported(const diqt_conv_desc* d);
+bool conv_zm_profitable(const diqt_conv_desc* d);
+size_t conv_zm_packed_bytes();
+int conv_zm_pack(const float* w, void* packed, cudaStream_t st);
+int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void* packed, const float* bias, ZmPlan** plan);
+int conv_zm_run(const ZmPlan* plan, cudaStream_t st);
+int conv_zm_set_stats(ZmPlan* plan, float* partial);
+void conv_zm_destroy(ZmPlan* plan);
 }  // namespace diqt
 
 using namespace diqt;
@@ -28,6 +37,7 @@ struct diqt_conv_plan {
   const void* packed;
   const float* bias;
   TcPlan* tc;
+  ZmPlan* zm;
 };
 
 static int check_desc(const diqt_conv_desc* d) {
@@ -46,13 +56,19 @@ static int check_desc(const diqt_conv_desc* d) {
 
 static int resolve_impl(const diqt_conv_desc* d, int* impl) {
   int want = d->impl;
-  if (want == DIQT_IMPL_AUTO) want = conv_tc_supported(d) ? DIQT_IMPL_TC : DIQT_IMPL_SIMT;
+  if (want == DIQT_IMPL_AUTO)
+    want = (conv_zm_supported(d) && conv_zm_profitable(d)) ? DIQT_IMPL_ZM : conv_tc_supported(d) ? DIQT_IMPL_TC : DIQT_IMPL_SIMT;
+  if (want == DIQT_IMPL_ZM && !conv_zm_supported(d)) {
+    set_error("conv: z-march kernel needs 3x3x3 bf16 64->64 with d2 %% 8 == 0, d1 %% 16 == 0 (got c_in=%d c_out=%d dims %d,%d,%d)", d->c_in,
+              d->c_out, d->d0, d->d1, d->d2);
+    return DIQT_EUNSUPPORTED;
+  }
   if (want == DIQT_IMPL_TC && !conv_tc_supported(d)) {
     set_error("conv: tcgen05 kernel does not take dtype=%d c_in=%d c_out=%d ld_in=%d ld_out=%d", d->dtype, d->c_in, d->c_out,
               d->ld_in, d->ld_out);
     return DIQT_EUNSUPPORTED;
   }
-  if (want != DIQT_IMPL_TC && want != DIQT_IMPL_SIMT) {
+  if (want != DIQT_IMPL_TC && want != DIQT_IMPL_SIMT && want != DIQT_IMPL_ZM) {
     set_error("conv: bad impl %d", d->impl);
     return DIQT_EINVAL;
   }
@@ -71,7 +87,9 @@ extern "C" int diqt_conv_packed_bytes(const diqt_conv_desc* d, size_t* bytes) {
   if (rc) return rc;
   if ((rc = resolve_impl(d, &impl))) return rc;
   DIQT_REQUIRE(bytes, "conv_packed_bytes: null output");
-  *bytes = impl == DIQT_IMPL_TC ? conv_tc_packed_bytes(d) : (size_t)simt_taps(d->mode) * d->c_in * d->c_out * sizeof(float);
+  *bytes = impl == DIQT_IMPL_ZM   ? conv_zm_packed_bytes()
+           : impl == DIQT_IMPL_TC ? conv_tc_packed_bytes(d)
+                                  : (size_t)simt_taps(d->mode) * d->c_in * d->c_out * sizeof(float);
   return DIQT_OK;
 }
 
@@ -82,7 +100,7 @@ extern "C" int diqt_conv_pack(const diqt_conv_desc* d, const float* w, const flo
   if ((rc = resolve_impl(d, &impl))) return rc;
   DIQT_REQUIRE(w && packed_w && packed_bias, "conv_pack: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  rc = impl == DIQT_IMPL_TC ? conv_tc_pack(d, w, packed_w, st) : conv_simt_pack(d, w, packed_w, st);
+  rc = impl == DIQT_IMPL_ZM ? conv_zm_pack(w, packed_w, st) : impl == DIQT_IMPL_TC ? conv_tc_pack(d, w, packed_w, st) : conv_simt_pack(d, w, packed_w, st);
   if (rc) return rc;
   if (!bias) {
     DIQT_CUDA(cudaMemsetAsync(packed_bias, 0, sizeof(float) * d->c_out, st));
@@ -108,12 +126,12 @@ extern "C" int diqt_conv_plan_create(const diqt_conv_desc* d, const void* in, vo
   pl->packed = packed_w;
   pl->bias = packed_bias;
   pl->tc = nullptr;
-  if (impl == DIQT_IMPL_TC) {
-    rc = conv_tc_plan(d, in, out, packed_w, packed_bias, &pl->tc);
-    if (rc) {
-      delete pl;
-      return rc;
-    }
+  pl->zm = nullptr;
+  if (impl == DIQT_IMPL_TC) rc = conv_tc_plan(d, in, out, packed_w, packed_bias, &pl->tc);
+  if (impl == DIQT_IMPL_ZM) rc = conv_zm_plan(d, in, out, packed_w, packed_bias, &pl->zm);
+  if (rc) {
+    delete pl;
+    return rc;
   }
   *plan = pl;
   return DIQT_OK;
@@ -122,18 +140,20 @@ extern "C" int diqt_conv_plan_create(const diqt_conv_desc* d, const void* in, vo
 extern "C" void diqt_conv_plan_destroy(diqt_conv_plan* plan) {
   if (!plan) return;
   if (plan->tc) conv_tc_destroy(plan->tc);
+  if (plan->zm) conv_zm_destroy(plan->zm);
   delete plan;
 }
 
 extern "C" int diqt_conv_run(const diqt_conv_plan* plan, void* stream) {
   DIQT_REQUIRE(plan, "conv_run: null plan");
   cudaStream_t st = (cudaStream_t)stream;
+  if (plan->impl == DIQT_IMPL_ZM) return conv_zm_run(plan->zm, st);
   if (plan->impl == DIQT_IMPL_TC) return conv_tc_run(plan->tc, st);
   return conv_simt_run(&plan->d, plan->in, plan->out, plan->packed, plan->bias, st);
 }
 
 extern "C" int diqt_conv_plan_set_stats(diqt_conv_plan* plan, float* partial, int* nblk) {
   DIQT_REQUIRE(plan && partial && nblk, "conv_plan_set_stats: null pointer");
-  *nblk = plan->impl == DIQT_IMPL_TC ? conv_tc_set_stats(plan->tc, partial) : 0;
+  *nblk = plan->impl == DIQT_IMPL_ZM ? conv_zm_set_stats(plan->zm, partial) : plan->impl == DIQT_IMPL_TC ? conv_tc_set_stats(plan->tc, partial) : 0;
   return DIQT_OK;
 }

@@ -1,0 +1,471 @@
+// "z-march" tcgen05 convolution: 3x3x3, 64 -> 64 channels, bf16, the shape that carries 77 % of the U-Net's FLOPs
+// (Block.project at full resolution, imagen_pytorch3D.py:550-553).
+//
+// Two measurements on B200 shape this kernel (tools/umma_probe.cu, profiles/umma_probe_r1.log):
+//   1. tcgen05.mma M=128 takes 64 cycles per K=16 step for N=64 AND for N=128: an N=64 GEMM can only reach half of
+//      the tensor peak.  So the three dz taps that read the SAME input voxels are stacked along N: one MMA with
+//      N = 192 multiplies an input z-plane by [W(dz=+1) | W(dz=0) | W(dz=-1)] and accumulates into the three output
+//      planes p-1, p, p+1 at once (full rate).
+//   2. The 128B-swizzle XOR is taken from absolute shared-memory address bits, so a K-major descriptor may start at
+//      any 128-byte row of a TMA-written tile (base_offset = 0).  So the nine (dy,dx) taps are nine row-shifted views
+//      (start = (kh*10+kw) rows, 8-row groups 10 rows apart) of ONE haloed input plane of 18 x 10 voxels.
+//
+// A CTA marches along z through a column of 16(y) x 8(x) voxels: every input plane is loaded once (1.4x halo
+// redundancy instead of 27x) and contributes 9 MMAs of N=192.  Output plane z lives in TMEM block (z - z0) mod 4 of
+// the slot's 256 columns; it is complete after input plane z+1, is drained / stored / re-zeroed by the epilogue warps
+// while the tensor core already works on the next planes.  Two such columns ("slots") are processed in lockstep so
+// that each 24 KB weight stage streamed from L2 is used twice.
+//
+// Warp roles (224 threads): 0 plane TMA producer, 1 weight producer, 2 TMEM owner + MMA issuer, 3-6 epilogue.
+#include <string.h>
+
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace diqt {
+
+constexpr int ZM_TX = 8, ZM_TY = 16;                    // output tile of one plane: 16 (y) x 8 (x) = 128 GEMM rows
+constexpr int ZM_PLANE_BYTES = (ZM_TY + 2) * (ZM_TX + 2) * 128;  // 180 haloed rows x 64 bf16 = 23040
+constexpr int ZM_PLANE_STRIDE = 23552;                  // next multiple of 1024
+constexpr int ZM_RING = 2;                              // plane buffers per slot
+constexpr int ZM_WBLOCK = 64 * 128;                     // one (dz,dy,dx) weight block: 64 c_out rows x 64 c_in
+constexpr int ZM_WSTAGE = 3 * ZM_WBLOCK;
+constexpr int ZM_WSTAGES = 4;
+constexpr int ZM_THREADS = 224;
+constexpr int ZM_OUT_BYTES = 128 * 128;
+
+struct ZmParams {
+  CUtensorMap in_map, out_map;
+  const uint8_t* w;   // [kb = kh*3+kw][j: 0 -> kd=2 (dz=+1), 1 -> kd=1, 2 -> kd=0 (dz=-1)][64 c_out][64 c_in], pre-swizzled
+  const float* bias;
+  float* stats;       // NULL or [n][2*gridDim.x][64][2]
+  int n, D, H, W;
+  int tiles_x, tiles_y, nseg, L, items, pairs;
+  uint32_t idesc[3];  // N = 64, 128, 192
+};
+
+struct ZmItem {
+  int valid, b, x0, y0, z0, z1, p_lo, niter;
+};
+
+__device__ __forceinline__ ZmItem zm_item(const ZmParams& p, int item) {
+  ZmItem it;
+  it.valid = item < p.items;
+  if (!it.valid) { it.b = it.x0 = it.y0 = it.z0 = it.z1 = it.p_lo = 0; it.niter = 0; return it; }
+  const int seg = item % p.nseg;
+  int t = item / p.nseg;
+  const int tx = t % p.tiles_x; t /= p.tiles_x;
+  const int ty = t % p.tiles_y;
+  it.b = t / p.tiles_y;
+  it.x0 = tx * ZM_TX; it.y0 = ty * ZM_TY;
+  it.z0 = seg * p.L; it.z1 = min(p.D, it.z0 + p.L);
+  it.p_lo = max(it.z0 - 1, 0);
+  it.niter = min(it.z1, p.D - 1) - it.p_lo + 1;
+  return it;
+}
+
+// weight sub-blocks j (output plane p-1+j) needed when input plane pl feeds outputs [z0, z1)
+__device__ __forceinline__ void zm_jrange(int pl, int z0, int z1, int& jlo, int& jhi) {
+  jlo = max(0, z0 - (pl - 1));
+  jhi = min(2, (z1 - 1) - (pl - 1));
+}
+
+__global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_constant__ ZmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* planes = smem;                                               // [2 slots][ZM_RING][ZM_PLANE_STRIDE]
+  uint8_t* wst = planes + 2 * ZM_RING * ZM_PLANE_STRIDE;                // [ZM_WSTAGES][ZM_WSTAGE]
+  uint8_t* out_stage = wst + ZM_WSTAGES * ZM_WSTAGE;                    // 16 KB
+  float* s_bias = reinterpret_cast<float*>(out_stage + ZM_OUT_BYTES);   // 64
+  float* s_red = s_bias + 64;                                           // [4][64][2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 4 * 64 * 2);
+  uint64_t* pl_full = bars;                       // [2][ZM_RING]
+  uint64_t* pl_empty = pl_full + 2 * ZM_RING;     // [2][ZM_RING]
+  uint64_t* w_full = pl_empty + 2 * ZM_RING;      // [ZM_WSTAGES]
+  uint64_t* w_empty = w_full + ZM_WSTAGES;        // [ZM_WSTAGES]
+  uint64_t* acc_full = w_empty + ZM_WSTAGES;      // [2][2]
+  uint64_t* acc_free = acc_full + 4;              // [2][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 2 * ZM_RING; ++i) { mbar_init(smem_u32(&pl_full[i]), 1); mbar_init(smem_u32(&pl_empty[i]), 1); }
+    for (int i = 0; i < ZM_WSTAGES; ++i) { mbar_init(smem_u32(&w_full[i]), 1); mbar_init(smem_u32(&w_empty[i]), 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_free[i]), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp >= 3) {  // all accumulator blocks start at zero: every MMA accumulates
+    const uint32_t q = (uint32_t)(warp & 3) * 32;
+    for (int c = 0; c < 16; ++c) tmem_st32_zero(tmem_base + (q << 16) + (uint32_t)c * 32);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ===================== input plane producer =====================
+    if (lane == 0) {
+      int ring[2] = {0, 0};
+      uint32_t phase[2] = {0, 0};
+      for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
+        const ZmItem it0 = zm_item(p, 2 * pair), it1 = zm_item(p, 2 * pair + 1);
+        const int niter = max(it0.niter, it1.niter);
+        for (int i = 0; i < niter; ++i) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const ZmItem& it = s ? it1 : it0;
+            if (i >= it.niter) continue;
+            const int b = s * ZM_RING + ring[s];
+            mbar_wait(smem_u32(&pl_empty[b]), phase[s] ^ 1);
+            const uint32_t bar = smem_u32(&pl_full[b]);
+            mbar_expect_tx(bar, ZM_PLANE_BYTES);
+            tma_load_5d(smem_u32(planes + (size_t)b * ZM_PLANE_STRIDE), &p.in_map, bar, 0, it.x0 - 1, it.y0 - 1, it.p_lo + i, it.b);
+            if (++ring[s] == ZM_RING) { ring[s] = 0; phase[s] ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
+        const ZmItem it0 = zm_item(p, 2 * pair), it1 = zm_item(p, 2 * pair + 1);
+        const int niter = max(it0.niter, it1.niter);
+        for (int i = 0; i < niter; ++i) {
+          int jlo = 2, jhi = 0;
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const ZmItem& it = s ? it1 : it0;
+            if (i >= it.niter) continue;
+            int a, b;
+            zm_jrange(it.p_lo + i, it.z0, it.z1, a, b);
+            jlo = min(jlo, a); jhi = max(jhi, b);
+          }
+          const uint32_t bytes = (uint32_t)(jhi - jlo + 1) * ZM_WBLOCK;
+          for (int kb = 0; kb < 9; ++kb) {
+            mbar_wait(smem_u32(&w_empty[stage]), phase ^ 1);
+            const uint32_t bar = smem_u32(&w_full[stage]);
+            mbar_expect_tx(bar, bytes);
+            bulk_load(smem_u32(wst + (size_t)stage * ZM_WSTAGE + (size_t)jlo * ZM_WBLOCK), p.w + ((size_t)kb * 3 + jlo) * ZM_WBLOCK, bytes, bar);
+            if (++stage == ZM_WSTAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== MMA issuer =====================
+    int stage = 0;
+    uint32_t wphase = 0;
+    int ring[2] = {0, 0};
+    uint32_t rphase[2] = {0, 0};
+    int kcount[2] = {0, 0};  // plane iterations issued so far per slot (pairs up with the epilogue's counter)
+    for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
+      const ZmItem it0 = zm_item(p, 2 * pair), it1 = zm_item(p, 2 * pair + 1);
+      const int niter = max(it0.niter, it1.niter);
+      for (int i = 0; i < niter; ++i) {
+        uint32_t a_base[2] = {0, 0};
+        int jlo[2], jhi[2], blk0[2];
+        bool act[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const ZmItem& it = s ? it1 : it0;
+          act[s] = i < it.niter;
+          jlo[s] = 0; jhi[s] = -1; blk0[s] = 0;
+          if (!act[s]) continue;
+          const int pl = it.p_lo + i;
+          zm_jrange(pl, it.z0, it.z1, jlo[s], jhi[s]);
+          blk0[s] = (pl - 1 + jlo[s] - it.z0) & 3;  // TMEM block of the first needed output plane
+          const int k = kcount[s];
+          // the block written for the first time in this iteration was drained two iterations ago; a new item needs
+          // every block of the slot drained
+          if (k >= 2) mbar_wait(smem_u32(&acc_free[s * 2 + (k & 1)]), (uint32_t)(((k - 2) >> 1) & 1));
+          if (i == 0 && k >= 1) mbar_wait(smem_u32(&acc_free[s * 2 + ((k - 1) & 1)]), (uint32_t)(((k - 1) >> 1) & 1));
+          mbar_wait(smem_u32(&pl_full[s * ZM_RING + ring[s]]), rphase[s]);
+          a_base[s] = smem_u32(planes + (size_t)(s * ZM_RING + ring[s]) * ZM_PLANE_STRIDE);
+        }
+        tc_fence_after();
+        for (int kb = 0; kb < 9; ++kb) {
+          mbar_wait(smem_u32(&w_full[stage]), wphase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t w_addr = smem_u32(wst + (size_t)stage * ZM_WSTAGE);
+            const uint32_t a_off = (uint32_t)((kb / 3) * (ZM_TX + 2) + (kb % 3)) * 128;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              if (!act[s]) continue;
+              const uint64_t adesc = make_sw128_desc_sbo(a_base[s] + a_off, (ZM_TX + 2) * 128);
+              // split the needed blocks into runs that do not wrap around the 4-block ring of TMEM columns
+              int j = jlo[s], blk = blk0[s];
+              while (j <= jhi[s]) {
+                const int len = min(jhi[s] - j + 1, 4 - blk);
+                const uint64_t bdesc = make_sw128_desc(w_addr + (uint32_t)j * ZM_WBLOCK);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256 + blk * 64);
+                const uint32_t idesc = p.idesc[len - 1];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
+                j += len;
+                blk = (blk + len) & 3;
+              }
+            }
+            umma_commit(smem_u32(&w_empty[stage]));
+          }
+          __syncwarp();
+          if (++stage == ZM_WSTAGES) { stage = 0; wphase ^= 1; }
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (!act[s]) continue;
+          if (lane == 0) {
+            umma_commit(smem_u32(&pl_empty[s * ZM_RING + ring[s]]));
+            umma_commit(smem_u32(&acc_full[s * 2 + (kcount[s] & 1)]));
+          }
+          __syncwarp();
+          if (++ring[s] == ZM_RING) { ring[s] = 0; rphase[s] ^= 1; }
+          ++kcount[s];
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 3..6) =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;  // GEMM row = y * 8 + x inside the tile
+    const int et = threadIdx.x - 96;      // 0..127
+    const int cp = et & 31, rq = et >> 5;
+    int kcount[2] = {0, 0};
+    float st_s[2][2], st_q[2][2];
+    int st_n[2] = {-1, -1}, st_first[2] = {-1, -1};
+    st_s[0][0] = st_s[0][1] = st_s[1][0] = st_s[1][1] = 0.f;
+    st_q[0][0] = st_q[0][1] = st_q[1][0] = st_q[1][1] = 0.f;
+    auto flush_stats = [&](int s, int nvol) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        s_red[(rq * 64 + cp * 2 + h) * 2] = st_s[s][h];
+        s_red[(rq * 64 + cp * 2 + h) * 2 + 1] = st_q[s][h];
+        st_s[s][h] = st_q[s][h] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      float* dst = p.stats + ((size_t)nvol * (2 * gridDim.x) + blockIdx.x * 2 + s) * 64 * 2;
+      if (et < 64) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) { a += s_red[(r4 * 64 + et) * 2]; b += s_red[(r4 * 64 + et) * 2 + 1]; }
+        dst[et * 2] = a;
+        dst[et * 2 + 1] = b;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+
+    for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
+      const ZmItem it0 = zm_item(p, 2 * pair), it1 = zm_item(p, 2 * pair + 1);
+      const int niter = max(it0.niter, it1.niter);
+      if (p.stats) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const ZmItem& it = s ? it1 : it0;
+          if (!it.valid) continue;
+          if (st_n[s] >= 0 && it.b != st_n[s]) flush_stats(s, st_n[s]);
+          if (st_first[s] < 0) st_first[s] = it.b;
+          st_n[s] = it.b;
+        }
+      }
+      for (int i = 0; i < niter; ++i) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const ZmItem& it = s ? it1 : it0;
+          if (i >= it.niter) continue;
+          const int pl = it.p_lo + i;
+          const int k = kcount[s];
+          mbar_wait(smem_u32(&acc_full[s * 2 + (k & 1)]), (uint32_t)((k >> 1) & 1));
+          tc_fence_after();
+          // outputs whose last contributing input plane is pl:  z = pl-1, and z = pl at the top face of the volume
+          for (int which = 0; which < 2; ++which) {
+            const int z = which == 0 ? pl - 1 : pl;
+            if (which == 0 && z < it.z0) continue;
+            if (which == 1 && !(pl == p.D - 1 && pl < it.z1)) continue;
+            const uint32_t tcol = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 256 + ((z - it.z0) & 3) * 64);
+            if (et == 0) bulk_wait_read0();  // staging tile free again
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int c32 = 0; c32 < 2; ++c32) {
+              uint32_t r[32];
+              tmem_ld32(tcol + c32 * 32, r);
+              tmem_ld_wait();
+              tmem_st32_zero(tcol + c32 * 32);  // the block is reused for output plane z+4
+              uint32_t packed[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * j]) + s_bias[c32 * 32 + 2 * j],
+                                                          __uint_as_float(r[2 * j + 1]) + s_bias[c32 * 32 + 2 * j + 1]);
+                packed[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              uint8_t* rowp = out_stage + (size_t)row * 128;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int chunk = (c32 * 4 + j) ^ (row & 7);
+                *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+              }
+            }
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) {
+              tma_store_5d(&p.out_map, smem_u32(out_stage), 0, it.x0, it.y0, z, it.b);
+              bulk_commit();
+            }
+            if (p.stats) {
+#pragma unroll 4
+              for (int r = 0; r < 32; ++r) {
+                const int rr = rq * 32 + r;
+                const uint32_t v = *reinterpret_cast<const uint32_t*>(out_stage + (size_t)rr * 128 + (((cp >> 2) ^ (rr & 7)) << 4) + ((cp & 3) << 2));
+                const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
+                st_s[s][0] += lo; st_q[s][0] = fmaf(lo, lo, st_q[s][0]);
+                st_s[s][1] += hi; st_q[s][1] = fmaf(hi, hi, st_q[s][1]);
+              }
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&acc_free[s * 2 + (k & 1)]));
+          ++kcount[s];
+        }
+      }
+    }
+    if (p.stats) {
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        if (st_n[s] >= 0) flush_stats(s, st_n[s]);
+        for (int nv = 0; nv < p.n; ++nv) {
+          if (st_first[s] >= 0 && nv >= st_first[s] && nv <= st_n[s]) continue;
+          float* dst = p.stats + ((size_t)nv * (2 * gridDim.x) + blockIdx.x * 2 + s) * 64 * 2;
+          if (et < 128) dst[et] = 0.f;
+        }
+      }
+    }
+    if (et == 0) bulk_wait0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// (64, 64, 3,3,3) fp32 -> [kb = kh*3+kw][j][c_out][c_in] bf16 with 16-byte chunks XOR-swizzled by (row & 7)
+__global__ void conv_pack_zm_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed) {
+  const int total = 9 * 3 * 64 * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int e = i % 64, r = (i / 64) % 64, j = (i / 4096) % 3, kb = i / (4096 * 3);
+    const int kd = 2 - j, kh = kb / 3, kw = kb % 3;
+    const float v = w[((int64_t)r * 64 + e) * 27 + kd * 9 + kh * 3 + kw];
+    const int chunk = (e >> 3) ^ (r & 7);
+    packed[((int64_t)(kb * 3 + j) * 64 + r) * 64 + chunk * 8 + (e & 7)] = __float2bfloat16_rn(v);
+  }
+}
+
+struct ZmPlan {
+  ZmParams p;
+  int grid;
+  size_t smem;
+};
+
+bool conv_zm_supported(const diqt_conv_desc* d) {
+  if (d->mode != DIQT_CONV_K3 || d->dtype != DIQT_BF16) return false;
+  if (d->c_in != 64 || d->c_out != 64) return false;
+  if (d->ld_in % 8 != 0 || d->ld_out % 8 != 0) return false;
+  if (d->d2 % ZM_TX != 0 || d->d1 % ZM_TY != 0 || d->d0 < 2) return false;
+  return true;
+}
+
+// enough plane-tiles to keep ~every SM busy with two z-columns; below that the per-tap kernel wins
+bool conv_zm_profitable(const diqt_conv_desc* d) {
+  const int64_t plane_tiles = (int64_t)d->n * (d->d2 / ZM_TX) * (d->d1 / ZM_TY) * d->d0;
+  return plane_tiles >= 1024;
+}
+
+size_t conv_zm_packed_bytes() { return (size_t)27 * 64 * 64 * 2; }
+
+int conv_zm_pack(const float* w, void* packed, cudaStream_t st) {
+  conv_pack_zm_kernel<<<108, 256, 0, st>>>(w, (__nv_bfloat16*)packed);
+  return check_launch("conv_pack_zm");
+}
+
+int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void* packed, const float* bias, ZmPlan** out_plan) {
+  DIQT_REQUIRE(conv_zm_supported(d), "conv(zm): needs 3x3x3 bf16 64->64 with d2 %% 8 == 0 and d1 %% 16 == 0");
+  ZmPlan* plan = new ZmPlan();
+  ZmParams& p = plan->p;
+  memset(&p, 0, sizeof(p));
+  p.w = (const uint8_t*)packed;
+  p.bias = bias;
+  p.stats = nullptr;
+  p.n = d->n; p.D = d->d0; p.H = d->d1; p.W = d->d2;
+  p.tiles_x = d->d2 / ZM_TX;
+  p.tiles_y = d->d1 / ZM_TY;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // pick the z-segment length: minimise  rounds * (L + boundary cost)  over the CTAs' lockstep slot pairs
+  const int64_t cols = (int64_t)d->n * p.tiles_x * p.tiles_y;
+  double best = 1e30;
+  int bestL = d->d0;
+  for (int L = 2; L <= d->d0; ++L) {
+    const int nseg = (d->d0 + L - 1) / L;
+    const int64_t pairs = (cols * nseg + 1) / 2;
+    const int64_t rounds = (pairs + sms - 1) / sms;
+    const double cost = (double)rounds * (L + 1.34);
+    if (cost < best - 1e-9) { best = cost; bestL = L; }
+  }
+  p.L = bestL;
+  p.nseg = (d->d0 + p.L - 1) / p.L;
+  p.items = (int)(cols * p.nseg);
+  p.pairs = (p.items + 1) / 2;
+  for (int i = 0; i < 3; ++i) p.idesc[i] = make_idesc_bf16(128, 64 * (i + 1));
+  const int64_t ld = d->ld_in, lo = d->ld_out;
+  int rc = encode_volume_map(&p.in_map, in, 64, d->d2, d->d1, d->d0, d->n, ld, (int64_t)d->d2 * ld, (int64_t)d->d1 * d->d2 * ld,
+                             (int64_t)d->d0 * d->d1 * d->d2 * ld, ZM_TX + 2, ZM_TY + 2, 1, 1);
+  if (rc == DIQT_OK)
+    rc = encode_volume_map(&p.out_map, out, 64, d->d2, d->d1, d->d0, d->n, lo, (int64_t)d->d2 * lo, (int64_t)d->d1 * d->d2 * lo,
+                           (int64_t)d->d0 * d->d1 * d->d2 * lo, ZM_TX, ZM_TY, 1, 1);
+  if (rc != DIQT_OK) {
+    delete plan;
+    return rc;
+  }
+  plan->grid = p.pairs < sms ? p.pairs : sms;
+  plan->smem = (size_t)2 * ZM_RING * ZM_PLANE_STRIDE + (size_t)ZM_WSTAGES * ZM_WSTAGE + ZM_OUT_BYTES + 64 * 4 + 4 * 64 * 2 * 4 + 512 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DIQT_CUDA(cudaFuncSetAttribute(conv_zm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  *out_plan = plan;
+  return DIQT_OK;
+}
+
+int conv_zm_run(const ZmPlan* plan, cudaStream_t st) {
+  conv_zm_kernel<<<plan->grid, ZM_THREADS, plan->smem, st>>>(plan->p);
+  return check_launch("conv_zm");
+}
+
+int conv_zm_set_stats(ZmPlan* plan, float* partial) {
+  plan->p.stats = partial;
+  return 2 * plan->grid;
+}
+
+void conv_zm_destroy(ZmPlan* plan) { delete plan; }
+
+}  // namespace diqt

@@ -56,7 +56,7 @@ class UnetEngine:
         self.dtype = dtype
         self.tdtype = torch.bfloat16 if dtype == "bf16" else torch.float32
         self.ddtype = L.BF16 if dtype == "bf16" else L.F32
-        self.impl = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tc": L.IMPL_TC}[conv_impl]
+        self.impl = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tc": L.IMPL_TC, "zm": L.IMPL_ZM}[conv_impl]
         if dtype == "fp32":
             self.impl = L.IMPL_SIMT
         if unet.boundary:

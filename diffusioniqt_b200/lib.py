@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libdiqt_b200.so")
 
 F32, BF16 = 0, 1
 CONV_K3, CONV_K1, CONV_DOWN, CONV_UP = 0, 1, 2, 3
-IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_ZM = 0, 1, 2, 3
 ABI_VERSION = 1
 
 

@@ -13,7 +13,7 @@ import torch
 from . import lib as L
 
 _MODES = {"k3": L.CONV_K3, "k1": L.CONV_K1, "down": L.CONV_DOWN, "up": L.CONV_UP}
-_IMPLS = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tc": L.IMPL_TC}
+_IMPLS = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tc": L.IMPL_TC, "zm": L.IMPL_ZM}
 
 
 def _dt(t: torch.Tensor) -> int:
@@ -34,8 +34,9 @@ def from_channels_last(x: torch.Tensor) -> torch.Tensor:
     return x.permute(0, 4, 1, 2, 3).contiguous().float()
 
 
-def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], mode: str = "k3", impl: str = "auto") -> torch.Tensor:
-    """x: (n, d0, d1, d2, c_in) bf16/fp32 on CUDA; weight/bias exactly as in the reference state_dict (fp32)."""
+def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], mode: str = "k3", impl: str = "auto", with_stats: bool = False):
+    """x: (n, d0, d1, d2, c_in) bf16/fp32 on CUDA; weight/bias exactly as in the reference state_dict (fp32).
+    with_stats=True also returns the fused per-block channel statistics (n, nblk, c_out, 2) or None if the kernel cannot fuse them."""
     lib = L.load()
     n, d0, d1, d2, c_in = x.shape
     x = x.contiguous()
@@ -65,12 +66,19 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
     L.check(lib.diqt_conv_pack(C.byref(desc), w.data_ptr(), L.ptr(b), packed.data_ptr(), pbias.data_ptr(), st), "conv_pack")
     plan = C.c_void_p(0)
     L.check(lib.diqt_conv_plan_create(C.byref(desc), x.data_ptr(), out.data_ptr(), packed.data_ptr(), pbias.data_ptr(), C.byref(plan)), "conv_plan")
+    stats = None
     try:
+        if with_stats:
+            buf = torch.full((n * 320 * c_out * 2,), float("nan"), dtype=torch.float32, device=x.device)
+            nb = C.c_int(0)
+            L.check(lib.diqt_conv_plan_set_stats(plan.value, buf.data_ptr(), C.byref(nb)), "conv_set_stats")
+            if nb.value > 0:
+                stats = buf[: n * nb.value * c_out * 2].view(n, nb.value, c_out, 2)
         L.check(lib.diqt_conv_run(plan.value, st), "conv_run")
         torch.cuda.current_stream().synchronize()
     finally:
         lib.diqt_conv_plan_destroy(plan.value)
-    return out
+    return (out, stats) if with_stats else out
 
 
 def channel_stats(x: torch.Tensor, nblk: int = 8) -> torch.Tensor:

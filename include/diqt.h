@@ -55,7 +55,8 @@ enum {
 enum {
   DIQT_IMPL_AUTO = 0,
   DIQT_IMPL_SIMT = 1, /* CUDA-core implicit GEMM, fp32 accumulate; any channel count; both dtypes */
-  DIQT_IMPL_TC = 2    /* tcgen05 + TMA implicit GEMM, bf16 only, C_in % 64 == 0, C_out % 64 == 0   */
+  DIQT_IMPL_TC = 2,   /* tcgen05 + TMA implicit GEMM, bf16 only, C_in % 64 == 0, C_out % 64 == 0   */
+  DIQT_IMPL_ZM = 3    /* tcgen05 "z-march" 3x3x3 64->64 bf16: haloed planes reused by 9 taps, dz taps stacked to N=192 */
 };
 
 int diqt_abi_version(void);

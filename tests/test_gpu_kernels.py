@@ -101,6 +101,57 @@ def test_conv_tcgen05_bf16(mode, n, dims, c_in, c_out):
     assert max_rel(ops.from_channels_last(got).cpu(), want) < BF16_TOL
 
 
+ZM_SHAPES = [
+    # n, (d0, d1, d2): z-march kernel needs d1 % 16 == 0, d2 % 8 == 0
+    (1, (16, 16, 16)),
+    (1, (2, 16, 8)),
+    (1, (5, 16, 8)),       # odd depth: last z-segment shorter
+    (2, (8, 32, 16)),
+    (3, (4, 16, 24)),      # more items than one slot pair per column, batch > 1
+    (1, (32, 32, 32)),
+    (1, (64, 64, 64)),     # BASELINE config 2 shape
+]
+
+
+@pytest.mark.parametrize("n,dims", ZM_SHAPES)
+def test_conv_zmarch_bf16(n, dims):
+    from diffusioniqt_b200 import ops
+    x = _rand(n, 64, *dims, seed=21).bfloat16().float()
+    w, b = _conv_weight("k3", 64, 64, 22)
+    want = _conv_reference(x, w.bfloat16().float(), b, "k3")
+    got, stats = ops.conv3d(ops.to_channels_last(x.cuda(), torch.bfloat16), w, b, mode="k3", impl="zm", with_stats=True)
+    stored = ops.from_channels_last(got).cpu()
+    assert max_rel(stored, want) < BF16_TOL
+    # fused statistics describe the stored (bf16-rounded) output exactly up to fp32 summation order
+    s = stats.sum(dim=1).cpu()
+    assert max_rel(s[..., 0], stored.sum(dim=(2, 3, 4))) < 2e-4
+    assert max_rel(s[..., 1], (stored ** 2).sum(dim=(2, 3, 4))) < 2e-4
+
+
+@pytest.mark.parametrize("mode,n,dims,c_in,c_out", [("k3", 1, (16, 16, 16), 64, 64), ("k3", 2, (8, 8, 8), 128, 128), ("down", 1, (16, 16, 16), 64, 128),
+                                                     ("k1", 2, (8, 8, 8), 128, 256), ("k3", 1, (12, 12, 12), 64, 64)])
+def test_conv_tcgen05_fused_stats(mode, n, dims, c_in, c_out):
+    from diffusioniqt_b200 import ops
+    x = _rand(n, c_in, *dims, seed=23).bfloat16().float()
+    w, b = _conv_weight(mode, c_in, c_out, 24)
+    got, stats = ops.conv3d(ops.to_channels_last(x.cuda(), torch.bfloat16), w, b, mode=mode, impl="tc", with_stats=True)
+    assert stats is not None
+    stored = ops.from_channels_last(got).cpu()
+    s = stats.sum(dim=1).cpu()
+    assert max_rel(s[..., 0], stored.sum(dim=(2, 3, 4))) < 2e-4
+    assert max_rel(s[..., 1], (stored ** 2).sum(dim=(2, 3, 4))) < 2e-4
+
+
+def test_conv_zmarch_equals_per_tap_kernel():
+    """Same operands, same fp32 accumulation, different summation order only."""
+    from diffusioniqt_b200 import ops
+    x = ops.to_channels_last(_rand(1, 64, 16, 32, 16, seed=25).cuda(), torch.bfloat16)
+    w, b = _conv_weight("k3", 64, 64, 26)
+    a = ops.conv3d(x, w, b, mode="k3", impl="zm").float()
+    c = ops.conv3d(x, w, b, mode="k3", impl="tc").float()
+    assert max_rel(a, c) < 2 ** -7
+
+
 def test_conv_tcgen05_matches_simt_closely():
     """Same bf16 operands, fp32 accumulation in both: the two kernel families agree to bf16 output rounding."""
     from diffusioniqt_b200 import ops
