@@ -121,7 +121,9 @@ def time_dominant_kernel(size, batch, reps=20):
     bufs = [(torch.randn(n, size, size, size, c, device=dev).bfloat16(), torch.empty(n, size, size, size, c, device=dev, dtype=torch.bfloat16)) for _ in range(4)]
     w = torch.randn(c, c, 3, 3, 3, device=dev) * 0.02
     b = torch.zeros(c, device=dev)
-    desc = L.ConvDesc(mode=L.CONV_K3, dtype=L.BF16, impl=L.IMPL_TC, n=n, d0=size, d1=size, d2=size, c_in=c, ld_in=c, c_out=c, ld_out=c, flags=0)
+    desc = L.ConvDesc(mode=L.CONV_K3, dtype=L.BF16, impl=L.IMPL_AUTO, n=n, d0=size, d1=size, d2=size, c_in=c, ld_in=c, c_out=c, ld_out=c, flags=0)
+    impl = C.c_int(0)
+    L.check(lib.diqt_conv_resolved_impl(C.byref(desc), C.byref(impl)))
     nbytes = C.c_size_t(0)
     L.check(lib.diqt_conv_packed_bytes(C.byref(desc), C.byref(nbytes)))
     packed = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
@@ -147,7 +149,8 @@ def time_dominant_kernel(size, batch, reps=20):
         lib.diqt_conv_plan_destroy(p)
     flops = 2.0 * c * c * 27 * n * size ** 3
     ms = sum(times) / len(times)
-    return dict(ms=ms, ms_min=min(times), flops=flops, tflops=flops / (ms * 1e-3) / 1e12)
+    kernel = {L.IMPL_SIMT: "conv_simt_kernel", L.IMPL_TC: "conv_tc_kernel", L.IMPL_ZM: "conv_zm_kernel"}[impl.value]
+    return dict(ms=ms, ms_min=min(times), flops=flops, tflops=flops / (ms * 1e-3) / 1e12, kernel=kernel)
 
 
 def cpu_baseline(size, timesteps, batch, denoise_steps, threads=None):
@@ -316,7 +319,7 @@ def main():
         flops_per_patch = FLOPS_PER_FWD_64 * (S / 64.0) ** 3 * args.timesteps
         step_tflops = value / world * flops_per_patch / 1e12
         dom = time_dominant_kernel(S, B)
-        roofline = dict(bound="tensor", kernel="conv_tc_kernel 3x3x3 64->64 @%d^3 (batch %d)" % (S, B), achieved=dom["tflops"], peak=peaks["burst"],
+        roofline = dict(bound="tensor", kernel="%s 3x3x3 64->64 @%d^3 (batch %d)" % (dom["kernel"], S, B), achieved=dom["tflops"], peak=peaks["burst"],
                         unit="TFLOP/s", frac=dom["tflops"] / peaks["burst"], traffic=None, ms_per_launch=dom["ms"], flops_per_launch=dom["flops"],
                         peak_source=peaks["source"] + " (burst: kernel timed alone)",
                         whole_step=dict(achieved=step_tflops, peak=peaks["sustained"], frac=step_tflops / peaks["sustained"], unit="TFLOP/s",

@@ -101,9 +101,20 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblk, 
   for (int idx = threadIdx.x; idx < parts * c; idx += blockDim.x) {
     const int ch = idx % c, part = idx / c;
     double s = 0.0, q = 0.0;
-    for (int b = part; b < nblk; b += parts) {
-      s += (double)p[((int64_t)b * c + ch) * 2];
-      q += (double)p[((int64_t)b * c + ch) * 2 + 1];
+    int b = part;
+    for (; b + 3 * parts < nblk; b += 4 * parts) {  // four independent loads in flight; summation order stays fixed
+      const float2 v0 = *reinterpret_cast<const float2*>(p + ((int64_t)b * c + ch) * 2);
+      const float2 v1 = *reinterpret_cast<const float2*>(p + ((int64_t)(b + parts) * c + ch) * 2);
+      const float2 v2 = *reinterpret_cast<const float2*>(p + ((int64_t)(b + 2 * parts) * c + ch) * 2);
+      const float2 v3 = *reinterpret_cast<const float2*>(p + ((int64_t)(b + 3 * parts) * c + ch) * 2);
+      s += (double)v0.x; q += (double)v0.y;
+      s += (double)v1.x; q += (double)v1.y;
+      s += (double)v2.x; q += (double)v2.y;
+      s += (double)v3.x; q += (double)v3.y;
+    }
+    for (; b < nblk; b += parts) {
+      const float2 v = *reinterpret_cast<const float2*>(p + ((int64_t)b * c + ch) * 2);
+      s += (double)v.x; q += (double)v.y;
     }
     acc[(part * c + ch) * 2] = s;
     acc[(part * c + ch) * 2 + 1] = q;
@@ -206,7 +217,13 @@ __global__ void se_gate_kernel(const float* __restrict__ partial, int nblk, int6
   for (int idx = threadIdx.x; idx < parts * c; idx += blockDim.x) {
     const int ch = idx % c, part = idx / c;
     double s = 0.0;
-    for (int b = part; b < nblk; b += parts) s += (double)p[((int64_t)b * c + ch) * 2];
+    int b = part;
+    for (; b + 3 * parts < nblk; b += 4 * parts) {
+      const float v0 = p[((int64_t)b * c + ch) * 2], v1 = p[((int64_t)(b + parts) * c + ch) * 2];
+      const float v2 = p[((int64_t)(b + 2 * parts) * c + ch) * 2], v3 = p[((int64_t)(b + 3 * parts) * c + ch) * 2];
+      s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
+    }
+    for (; b < nblk; b += parts) s += (double)p[((int64_t)b * c + ch) * 2];
     acc[part * c + ch] = s;
   }
   __syncthreads();

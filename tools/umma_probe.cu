@@ -223,7 +223,8 @@ int main(int argc, char** argv) {
     long long* cyc; CK(cudaMalloc(&cyc, 148 * sizeof(long long)));
     CK(cudaFuncSetAttribute(probe_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
     const int iters = 27 * 64;
-    struct { int n, shift, sbo; } runs[] = {{64, 0, 1024}, {128, 0, 1024}, {256, 0, 1024}, {64, 1, 1280}, {64, 11, 1280}};
+    struct { int n, shift, sbo; } runs[] = {{64, 0, 1024}, {128, 0, 1024}, {256, 0, 1024}, {64, 1, 1280}, {64, 11, 1280},
+                                            {192, 0, 1024}, {192, 1, 1280}, {192, 11, 1280}, {128, 11, 1280}, {192, 8, 2048}, {192, 0, 1280}};
     for (auto r : runs) {
       for (int rep = 0; rep < 2; ++rep) {
         probe_rate<<<148, 128, 110 * 1024>>>(r.n, iters, r.shift, r.sbo, cyc);
