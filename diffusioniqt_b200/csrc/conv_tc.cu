@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
-        if (lane == 0) {
+        {  // warp-uniform issue code; the issuing lane is elected inside umma_bf16 / umma_commit
           const uint32_t a_addr = smem_u32(stage_base + (size_t)stage * stage_bytes);
           const uint64_t adesc = make_sw128_desc(a_addr);
           const uint64_t bdesc = make_sw128_desc(a_addr + kABytes);
@@ -153,7 +153,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           umma_commit(smem_u32(&empty_bar[stage]));
           if (kb == kblocks - 1) umma_commit(smem_u32(&tfull_bar[acc]));
         }
-        __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }

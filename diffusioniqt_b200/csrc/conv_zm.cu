@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
         for (int kb = 0; kb < 9; ++kb) {
           mbar_wait(smem_u32(&w_full[stage]), wphase);
           tc_fence_after();
-          if (lane == 0) {
+          {  // warp-uniform issue code; the single issuing lane is elected inside umma_bf16 / umma_commit
             const uint32_t w_addr = smem_u32(wst + (size_t)stage * ZM_WSTAGE);
             const uint32_t a_off = (uint32_t)((kb / 3) * (ZM_TX + 2) + (kb % 3)) * 128;
 #pragma unroll
@@ -223,17 +223,13 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
             }
             umma_commit(smem_u32(&w_empty[stage]));
           }
-          __syncwarp();
           if (++stage == ZM_WSTAGES) { stage = 0; wphase ^= 1; }
         }
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           if (!act[s]) continue;
-          if (lane == 0) {
-            umma_commit(smem_u32(&pl_empty[s * ZM_RING + ring[s]]));
-            umma_commit(smem_u32(&acc_full[s * 2 + (kcount[s] & 1)]));
-          }
-          __syncwarp();
+          umma_commit(smem_u32(&pl_empty[s * ZM_RING + ring[s]]));
+          umma_commit(smem_u32(&acc_full[s * 2 + (kcount[s] & 1)]));
           if (++ring[s] == ZM_RING) { ring[s] = 0; rphase[s] ^= 1; }
           ++kcount[s];
         }
