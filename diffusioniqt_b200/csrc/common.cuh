@@ -94,12 +94,20 @@ template <>
 __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
 
 // Mish(x) = x * tanh(softplus(x)) = x * n / (n + 2),  n = e^x (e^x + 2)       (nn.Mish)
+// Branch-free: the exponent is clamped at 20 (the softplus threshold of the reference op), where n/(n+2) == 1 in fp32.
+// kFast uses the approximate SFU ops with flush-to-zero (2 MUFU + 7 FP32 ops per element, no range fix-up code).
 template <bool kFast>
 __device__ __forceinline__ float mish(float x) {
-  if (x > 20.f) return x;  // softplus threshold of the reference op; also avoids overflow of e^2x
-  float u = kFast ? __expf(x) : expf(x);
-  float n = u * (u + 2.f);
-  return kFast ? x * __fdividef(n, n + 2.f) : x * (n / (n + 2.f));
+  if (kFast) {
+    float t = fminf(x * 1.4426950408889634f, 28.853900817779268f), u, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(t));
+    const float n = u * (u + 2.f);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n + 2.f));
+    return x * (n * r);
+  }
+  const float u = expf(fminf(x, 20.f));
+  const float n = u * (u + 2.f);
+  return x * (n / (n + 2.f));
 }
 
 }  // namespace diqt

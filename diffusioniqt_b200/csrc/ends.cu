@@ -77,6 +77,76 @@ init_conv_kernel(InitPlanes planes, int c_in, const float* __restrict__ w /*[27]
   }
 }
 
+// four consecutive voxels along d2 per thread, CO_T output channels per pass: every weight vector read from shared memory
+// feeds 4 x as many FMAs as in the one-voxel kernel (which was bound by broadcast LDS traffic)
+template <typename T, int CO_T>
+__global__ void __launch_bounds__(128)
+init_conv_x4_kernel(InitPlanes planes, int c_in, const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
+                    int ld_out, int n, int d0, int d1, int d2, int c_out) {
+  extern __shared__ float sw[];
+  const int wcount = 27 * c_in * c_out;
+  for (int i = threadIdx.x; i < wcount; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < c_out; i += blockDim.x) sw[wcount + i] = bias[i];
+  __syncthreads();
+  const int xq = d2 / 4;
+  const int64_t total = (int64_t)n * d0 * d1 * xq;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int64_t r = idx;
+  const int x = (int)(r % xq) * 4; r /= xq;
+  const int y = (int)(r % d1); r /= d1;
+  const int z = (int)(r % d0);
+  const int b = (int)(r / d0);
+  const int64_t vox = (((int64_t)b * d0 + z) * d1 + y) * d2 + x;
+  for (int co0 = 0; co0 < c_out; co0 += CO_T) {
+    float acc[4][CO_T];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int j = 0; j < CO_T; ++j) acc[v][j] = sw[wcount + co0 + j];
+#pragma unroll 1
+    for (int t9 = 0; t9 < 9; ++t9) {
+      const int zz = z + t9 / 3 - 1, yy = y + t9 % 3 - 1;
+      if (zz < 0 || zz >= d0 || yy < 0 || yy >= d1) continue;
+      const int64_t rowoff = ((int64_t)zz * d1 + yy) * d2;
+      for (int ci = 0; ci < c_in; ++ci) {
+        const float* src = planes.p[ci] + (int64_t)b * planes.stride[ci] + rowoff;
+        float in[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int xx = x - 1 + k;
+          in[k] = (xx >= 0 && xx < d2) ? __ldg(src + xx) : 0.f;
+        }
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float* wr = sw + ((t9 * 3 + dx) * c_in + ci) * c_out + co0;
+#pragma unroll
+          for (int j = 0; j < CO_T; j += 4) {
+            const float4 wv = *reinterpret_cast<const float4*>(wr + j);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              acc[v][j] = fmaf(in[v + dx], wv.x, acc[v][j]);
+              acc[v][j + 1] = fmaf(in[v + dx], wv.y, acc[v][j + 1]);
+              acc[v][j + 2] = fmaf(in[v + dx], wv.z, acc[v][j + 2]);
+              acc[v][j + 3] = fmaf(in[v + dx], wv.w, acc[v][j + 3]);
+            }
+          }
+        }
+      }
+    }
+    constexpr int VN = Vec<T>::N;
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int j = 0; j < CO_T; j += VN) {
+        Vec<T> o;
+#pragma unroll
+        for (int i = 0; i < VN; ++i) o.v[i] = acc[v][j + i];
+        o.store(out + (vox + v) * ld_out + co0 + j);
+      }
+  }
+}
+
 __global__ void init_conv_pack_kernel(const float* __restrict__ w, int c_out, int c_in, float* __restrict__ packed) {
   // (c_out, c_in, 3,3,3) -> [tap][c_in][c_out]
   const int total = 27 * c_in * c_out;
@@ -130,38 +200,49 @@ __global__ void final_conv_kernel(const T* __restrict__ x, int ld, int64_t voxel
     for (int i = 0; i < VEC; ++i) wv[co][i] = co < c_out ? w[co * c + col * VEC + i] : 0.f;
   StepConsts sc;
   if (step_mode) sc = load_step(sched, step);
-  // block-uniform trip count so the full-mask shuffles below are always converged
-  for (int64_t base = (int64_t)blockIdx.x * rows_per_block; base < total_rows; base += (int64_t)gridDim.x * rows_per_block) {
-    const int64_t row = base + threadIdx.x / nvec;
-    const bool valid = row < total_rows;
-    Vec<T> r;
-    if (valid) r.load(x + row * ld + col * VEC);
-    else {
+  // block-uniform trip count so the full-mask shuffles below are always converged; UNR rows in flight per thread group
+  constexpr int UNR = 4;
+  for (int64_t base = (int64_t)blockIdx.x * rows_per_block * UNR; base < total_rows; base += (int64_t)gridDim.x * rows_per_block * UNR) {
+    Vec<T> r[UNR];
+    bool valid[UNR];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) r.v[i] = 0.f;
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t row = base + (int64_t)u * rows_per_block + threadIdx.x / nvec;
+      valid[u] = row < total_rows;
+      if (valid[u]) r[u].load(x + row * ld + col * VEC);
+      else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) r[u].v[i] = 0.f;
+      }
     }
-    float acc[MAXCO];
 #pragma unroll
-    for (int co = 0; co < MAXCO; ++co) {
-      acc[co] = 0.f;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[co] = fmaf(r.v[i], wv[co][i], acc[co]);
-      for (int o = nvec >> 1; o > 0; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
-    }
-    if (valid && col == 0) {
-      const int64_t b = row / voxels, v = row - b * voxels;
+    for (int u = 0; u < UNR; ++u) {
+      const int64_t row = base + (int64_t)u * rows_per_block + threadIdx.x / nvec;
+      float acc[MAXCO];
 #pragma unroll
       for (int co = 0; co < MAXCO; ++co) {
-        if (co >= c_out) break;
-        const float p = acc[co] + bias[co];
-        const int64_t o = (b * c_out + co) * voxels + v;  // NCDHW fp32
-        if (!step_mode) {
-          pred[o] = p;
-        } else {
-          float xn, xs;
-          ddpm_point(sc, p, x_t[o], noise[o], xn, xs);
-          x_next[o] = xn;
-          x0[o] = xs;
+        acc[co] = 0.f;
+        if (co < c_out) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[co] = fmaf(r[u].v[i], wv[co][i], acc[co]);
+          for (int o = nvec >> 1; o > 0; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+        }
+      }
+      if (valid[u] && col == 0) {
+        const int64_t b = row / voxels, v = row - b * voxels;
+#pragma unroll
+        for (int co = 0; co < MAXCO; ++co) {
+          if (co >= c_out) break;
+          const float p = acc[co] + bias[co];
+          const int64_t o = (b * c_out + co) * voxels + v;  // NCDHW fp32
+          if (!step_mode) {
+            pred[o] = p;
+          } else {
+            float xn, xs;
+            ddpm_point(sc, p, x_t[o], noise[o], xn, xs);
+            x_next[o] = xn;
+            x0[o] = xs;
+          }
         }
       }
     }
@@ -260,6 +341,20 @@ extern "C" int diqt_init_conv(const float* const* planes, const int64_t* plane_s
   DIQT_REQUIRE(sh <= 200 * 1024, "init_conv: weights do not fit shared memory");
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  if (d2 % 4 == 0 && c_out % 32 == 0) {
+    const int64_t total4 = total / 4;
+    const unsigned blocks4 = (unsigned)((total4 + threads - 1) / threads);
+    if (dtype == DIQT_BF16) {
+      auto k = init_conv_x4_kernel<__nv_bfloat16, 32>;
+      if (sh > 48 * 1024) DIQT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+      k<<<blocks4, threads, sh, st>>>(ip, c_in, w_packed, bias, (__nv_bfloat16*)out, ld_out, n, d0, d1, d2, c_out);
+    } else {
+      auto k = init_conv_x4_kernel<float, 32>;
+      if (sh > 48 * 1024) DIQT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+      k<<<blocks4, threads, sh, st>>>(ip, c_in, w_packed, bias, (float*)out, ld_out, n, d0, d1, d2, c_out);
+    }
+    return check_launch("init_conv_x4");
+  }
 #define DIQT_INIT_LAUNCH(T, COT)                                                                                  \
   do {                                                                                                            \
     auto k = init_conv_kernel<T, COT>;                                                                            \
@@ -293,8 +388,8 @@ extern "C" int diqt_final_conv(const void* x, int ld, int dtype, int n, int64_t 
   const int64_t rows = (int64_t)n * voxels;
   const int threads = 256;
   const int64_t rpb = threads / nvec;
-  int64_t blocks = (rows + rpb - 1) / rpb;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  int64_t blocks = (rows + rpb * 4 - 1) / (rpb * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)
     final_conv_kernel<__nv_bfloat16, 4><<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)x, ld, voxels, c, c_out, nvec, w,
