@@ -1,0 +1,44 @@
+"""CPU oracle for the acceptance metrics  --  TEST INFRASTRUCTURE, NOT PRODUCT.
+
+Restates /root/reference/metrics.py:17-30 as used by test_all.py:47-85: PSNR after min-max normalisation of both
+volumes (data_range 1), and SSIM with a 3-D gaussian window (torchmetrics 0.9.0 `StructuralSimilarityIndexMeasure`
+defaults: kernel 11, sigma 1.5, k1 0.01, k2 0.03).  torchmetrics is a third-party dependency that is absent here
+(requirements.txt:201 pins 0.9.0), so its published formula is restated and the SAME restatement is applied to both
+sides of every comparison; absolute values are not claimed to match torchmetrics bit for bit (parity unpinned).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+def _minmax(x):
+    return (x - x.min()) / (x.max() - x.min())
+
+
+def psnr(pred: torch.Tensor, target: torch.Tensor) -> float:
+    p, t = _minmax(pred.double()), _minmax(target.double())
+    mse = torch.mean((p - t) ** 2)
+    return float(10.0 * torch.log10(1.0 / mse))
+
+
+def ssim3d(pred: torch.Tensor, target: torch.Tensor, kernel_size: int = 11, sigma: float = 1.5, normalise: bool = True) -> float:
+    p, t = pred.double(), target.double()
+    if normalise:
+        p, t = _minmax(p), _minmax(t)
+    p, t = p[None, None], t[None, None]
+    g = torch.arange(kernel_size, dtype=torch.float64) - (kernel_size - 1) / 2
+    g = torch.exp(-(g ** 2) / (2 * sigma ** 2))
+    g = g / g.sum()
+    k3 = (g[:, None, None] * g[None, :, None] * g[None, None, :])[None, None]
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+
+    def blur(x):
+        return F.conv3d(x, k3)
+
+    mu_p, mu_t = blur(p), blur(t)
+    s_pp = blur(p * p) - mu_p ** 2
+    s_tt = blur(t * t) - mu_t ** 2
+    s_pt = blur(p * t) - mu_p * mu_t
+    ssim = ((2 * mu_p * mu_t + c1) * (2 * s_pt + c2)) / ((mu_p ** 2 + mu_t ** 2 + c1) * (s_pp + s_tt + c2))
+    return float(ssim.mean())

@@ -1,0 +1,67 @@
+"""Whole-volume path on the GPU: patches -> Imagen.sample (CUDA kernels) -> stitch, against the CPU oracle pipeline,
+judged with the north star's acceptance metrics (PSNR within 0.05 dB, SSIM within 1e-3 of the reference pipeline)."""
+import numpy as np
+import pytest
+import torch
+
+from cases import MIN_BOUND
+from diffusioniqt_b200 import volume as V
+from diffusioniqt_b200.synth import synthetic_field, synthetic_noise, synthetic_state_dict
+from helpers import spec_from_kwargs
+from oracle import metrics_oracle as mo
+from oracle import stitch_oracle as so
+from oracle.ddpm_oracle import ddpm_sample
+from oracle.unet_oracle import unet_forward
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(dim=32, init_dim=32, dim_mults=(1, 2, 4), num_resnet_blocks=(2, 2, 2), channels=1, lowres_cond=True, init_cross_embed=False,
+          attend_at_middle=False, attend_at_enc=(False, False, False), use_se_attn=True, memory_efficient=False, deep_feature=False,
+          boundary=False, batch_sample=False)
+
+
+@pytest.mark.parametrize("dtype,psnr_tol,ssim_tol", [("fp32", 0.05, 1e-3), ("bf16", 0.05, 1e-3)])
+def test_stitched_volume_psnr_ssim(dtype, psnr_tol, ssim_tol):
+    from diffusioniqt_b200 import Imagen, NullUnet, Unet
+    P, stride, T, N = 16, 8, 6, 32
+    unet = Unet(**KW, img_size=P)
+    sd = synthetic_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, seed=61)
+    unet.load_state_dict(sd)
+    imagen = Imagen(unets=(NullUnet(), unet), configs={"Data": {"norm": "z-score"}, "Train": {"batch_sample": False}}, image_sizes=(P, P),
+                    channels=1, min_bound=MIN_BOUND, timesteps=T, pred_objectives="x_start", dynamic_thresholding=False,
+                    cond_drop_prob=0.0).cuda()
+    imagen.unets[1].set_compute_dtype(dtype)
+    lowres = synthetic_field((N, N, N), 62)[...]
+    lowres[:6, :10] = lowres.min()                       # a background corner
+    truth = synthetic_field((N, N, N), 63)
+    grid = V.patch_grid(lowres.shape, P, stride)
+    noise = {g: synthetic_noise((1, 1, P, P, P), T + 1, 64 + n) for n, g in enumerate(grid)}
+    order = iter(grid)
+
+    def gpu_sampler(lr):
+        imagen.noise_override = noise[next(order)]
+        return imagen.sample(batch_size=1, start_image_or_video=lr, start_at_unet_number=2, use_tqdm=False)[0]
+
+    res = V.infer_volume(gpu_sampler, lowres.cuda(), patch=P, overlap=stride, raw_lowres=(lowres - lowres.min()).cuda(), batch_size=1,
+                         fill_value=MIN_BOUND)
+    got = res.volume.cpu()
+
+    spec = spec_from_kwargs(KW)
+    outs, kept = [], []
+    raw = (lowres - lowres.min()).numpy()
+    for g in grid:
+        if so.is_skipped(raw, list(g), P):
+            continue
+        lr = lowres[g[0]:g[0] + P, g[1]:g[1] + P, g[2]:g[2] + P][None, None]
+        with torch.no_grad():
+            img, _, _ = ddpm_sample(lambda x, ls: unet_forward(sd, spec, x, ls, lowres_cond_img=lr), (1, 1, P, P, P), noise[g], timesteps=T,
+                                    min_bound=MIN_BOUND)
+        outs.append(img[0, 0].numpy())
+        kept.append(list(g))
+    want = np.full((N, N, N), MIN_BOUND, np.float32)
+    so.stitch(want, outs, kept, P, stride, False)
+    want = torch.from_numpy(so.background_mask(want, lowres.numpy()))
+    assert res.n_patches == len(kept)
+    assert abs(mo.psnr(got, truth) - mo.psnr(want, truth)) < psnr_tol
+    assert abs(mo.ssim3d(got, truth) - mo.ssim3d(want, truth)) < ssim_tol
+    assert mo.psnr(got, want) > (60.0 if dtype == "fp32" else 30.0)

@@ -1,0 +1,101 @@
+"""Patch grid / sharding / stitching host logic, single process and world_size = 2 over gloo (CPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from diffusioniqt_b200 import volume as V
+from oracle import stitch_oracle as so
+
+
+def _volume(shape, seed=0, hole=True):
+    rs = np.random.RandomState(seed)
+    raw = rs.uniform(0, 900, shape).astype(np.float32)
+    if hole:
+        raw[: shape[0] // 3, : shape[1] // 2] = 0.0          # empty corner: exercises the 5 % skip rule and the background mask
+    return raw
+
+
+@pytest.mark.parametrize("shape,patch,stride", [((96, 96, 96), 32, 16), ((64, 64, 64), 32, 32), ((80, 96, 112), 32, 24)])
+def test_grid_and_skip_rule_match_oracle(shape, patch, stride):
+    raw = _volume(shape)
+    grid = V.patch_grid(shape, patch, stride)
+    assert [list(g) for g in grid] == so.patch_index_list(shape, patch, stride)
+    for g in grid:
+        assert V.keep_patch(torch.from_numpy(raw), g, patch) == (not so.is_skipped(raw, list(g), patch))
+
+
+@pytest.mark.parametrize("batch_sample", [False, True])
+@pytest.mark.parametrize("shape,patch,stride", [((96, 96, 96), 32, 16), ((64, 64, 64), 32, 32), ((128, 128, 128), 64, 32), ((96, 96, 96), 32, 48)])
+def test_stitch_matches_oracle(shape, patch, stride, batch_sample):
+    rs = np.random.RandomState(1)
+    grid = V.patch_grid(shape, patch, stride)
+    outs = [rs.standard_normal((patch,) * 3).astype(np.float32) for _ in grid]
+    want = so.stitch(np.full(shape, -0.72, np.float32), outs, [list(g) for g in grid], patch, stride, batch_sample)
+    got = torch.full(shape, -0.72)
+    for o, g in zip(outs, grid):
+        V.stitch_patch_(got, torch.from_numpy(o), g, patch, stride, batch_sample)
+    assert np.array_equal(got.numpy(), want)
+
+
+def test_shard_ranges_cover_everything():
+    for n in (0, 1, 7, 343, 344):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                a, b, per = V.shard_range(n, r, world)
+                assert b - a <= per
+                seen += list(range(a, b))
+            assert seen == list(range(n))
+
+
+def _fake_sampler(lr):
+    return lr * 0.5 + 1.0 + lr.flip(-1) * 0.25        # deterministic, patch-local
+
+
+def _reference_volume(raw, mean, std, patch, stride):
+    lr = (raw - mean) / std
+    grid = so.patch_index_list(raw.shape, patch, stride)
+    kept = [g for g in grid if not so.is_skipped(raw, g, patch)]
+    outs = [_fake_sampler(torch.from_numpy(lr[g[0]:g[0] + patch, g[1]:g[1] + patch, g[2]:g[2] + patch].copy())[None, None])[0, 0].numpy() for g in kept]
+    pred = np.full(raw.shape, (0 - mean) / std, np.float32)
+    so.stitch(pred, outs, kept, patch, stride, False)
+    return so.background_mask(pred, lr), len(kept)
+
+
+def test_infer_volume_single_rank_matches_oracle():
+    raw = _volume((96, 96, 96), seed=3)
+    mean, std = 271.648, 377.117
+    want, nkept = _reference_volume(raw, mean, std, 32, 16)
+    res = V.infer_volume(_fake_sampler, torch.from_numpy((raw - mean) / std), patch=32, overlap=16, raw_lowres=torch.from_numpy(raw),
+                         batch_size=5, fill_value=(0 - mean) / std)
+    assert res.n_patches == nkept and res.n_skipped > 0
+    assert np.allclose(res.volume.numpy(), want, atol=1e-6)
+
+
+def _worker(rank, world, port, raw, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mean, std = 271.648, 377.117
+    res = V.infer_volume(_fake_sampler, torch.from_numpy((raw - mean) / std), patch=32, overlap=16, raw_lowres=torch.from_numpy(raw),
+                         batch_size=4, fill_value=(0 - mean) / std, rank=rank, world=world)
+    ret[rank] = (res.volume.numpy(), res.n_patches, res.patches_per_rank)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_infer_volume_two_ranks_gloo():
+    raw = _volume((96, 96, 96), seed=4)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, raw, ret), nprocs=2, join=True)
+    want, nkept = _reference_volume(raw, 271.648, 377.117, 32, 16)
+    for r in (0, 1):
+        vol, n, per = ret[r]
+        assert n == nkept and per == (nkept + 1) // 2
+        assert np.allclose(vol, want, atol=1e-6)
