@@ -93,6 +93,21 @@ __device__ __forceinline__ float from_float<float>(float x) { return x; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
 
+// Row addressing of per-volume kernels.  f <= 1: volume i owns rows [i*voxels, (i+1)*voxels).  f > 1 ("boundary" mode,
+// imagen_pytorch3D.py:37-46): the f^3 sub-volumes of side h live merged in ONE volume of side f*h so that convolutions see
+// their neighbours; sub-volume b = zb + f*yb + f*f*xb is block (zb, yb, xb) along (d0, d1, d2) (utils_mine.py:25-67) and its
+// local voxel l = (zl*h + yl)*h + xl sits at merged row ((zb*h+zl)*f*h + yb*h+yl)*f*h + xb*h+xl.
+struct SubGeom {
+  int f, h;
+};
+__device__ __forceinline__ int64_t sub_row(const SubGeom g, int64_t voxels, int b, int64_t l) {
+  if (g.f <= 1) return (int64_t)b * voxels + l;
+  const int h = g.h, fh = g.f * g.h;
+  const int xl = (int)(l % h), yl = (int)((l / h) % h), zl = (int)(l / ((int64_t)h * h));
+  const int zb = b % g.f, yb = (b / g.f) % g.f, xb = b / (g.f * g.f);
+  return ((int64_t)(zb * h + zl) * fh + (yb * h + yl)) * fh + xb * h + xl;
+}
+
 // Mish(x) = x * tanh(softplus(x)) = x * n / (n + 2),  n = e^x (e^x + 2)       (nn.Mish)
 // Branch-free: the exponent is clamped at 20 (the softplus threshold of the reference op), where n/(n+2) == 1 in fp32.
 // kFast uses the approximate SFU ops with flush-to-zero (2 MUFU + 7 FP32 ops per element, no range fix-up code).

@@ -50,14 +50,14 @@ __device__ __forceinline__ void block_channel_reduce(const float (&s)[VEC], cons
 
 template <typename T>
 __global__ void channel_stats_kernel(const T* __restrict__ x, int64_t voxels, int c, int ld, int nvec, int lanes,
-                                     int64_t vpb, float* __restrict__ partial) {
+                                     int64_t vpb, float* __restrict__ partial, SubGeom sg) {
   constexpr int VEC = Vec<T>::N;
   extern __shared__ float smem[];
   const int col = threadIdx.x % nvec, lane = threadIdx.x / nvec;
   const int blk = blockIdx.x, n = blockIdx.y, nblk = gridDim.x;
   const int64_t v0 = (int64_t)blk * vpb;
   const int64_t v1 = min(voxels, v0 + vpb);
-  const T* base = x + ((int64_t)n * voxels) * ld + col * VEC;
+  const T* base = x + col * VEC;
   float s[VEC], q[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) s[i] = q[i] = 0.f;
@@ -65,7 +65,7 @@ __global__ void channel_stats_kernel(const T* __restrict__ x, int64_t voxels, in
   for (; v + 3 * (int64_t)lanes < v1; v += 4 * (int64_t)lanes) {
     Vec<T> r[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) r[u].load(base + (v + (int64_t)u * lanes) * ld);
+    for (int u = 0; u < 4; ++u) r[u].load(base + sub_row(sg, voxels, n, v + (int64_t)u * lanes) * ld);
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -76,7 +76,7 @@ __global__ void channel_stats_kernel(const T* __restrict__ x, int64_t voxels, in
   }
   for (; v < v1; v += lanes) {
     Vec<T> r;
-    r.load(base + v * ld);
+    r.load(base + sub_row(sg, voxels, n, v) * ld);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       s[i] += r.v[i];
@@ -169,7 +169,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblk, 
 template <typename T, bool kFast>
 __global__ void affine_mish_kernel(const T* __restrict__ x, int ld_x, T* __restrict__ y, int ld_y, int64_t voxels,
                                    int c, int nvec, int lanes, int64_t vpb, const float* __restrict__ a,
-                                   const float* __restrict__ b) {
+                                   const float* __restrict__ b, SubGeom sg) {
   constexpr int VEC = Vec<T>::N;
   const int col = threadIdx.x % nvec, lane = threadIdx.x / nvec;
   const int n = blockIdx.y;
@@ -181,26 +181,26 @@ __global__ void affine_mish_kernel(const T* __restrict__ x, int ld_x, T* __restr
     av[i] = a[(int64_t)n * c + col * VEC + i];
     bv[i] = b[(int64_t)n * c + col * VEC + i];
   }
-  const T* xb = x + ((int64_t)n * voxels) * ld_x + col * VEC;
-  T* yb = y + ((int64_t)n * voxels) * ld_y + col * VEC;
+  const T* xb = x + col * VEC;
+  T* yb = y + col * VEC;
   int64_t v = v0 + lane;
   for (; v + 3 * (int64_t)lanes < v1; v += 4 * (int64_t)lanes) {
     Vec<T> r[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) r[u].load(xb + (v + (int64_t)u * lanes) * ld_x);
+    for (int u = 0; u < 4; ++u) r[u].load(xb + sub_row(sg, voxels, n, v + (int64_t)u * lanes) * ld_x);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
 #pragma unroll
       for (int i = 0; i < VEC; ++i) r[u].v[i] = mish<kFast>(fmaf(av[i], r[u].v[i], bv[i]));
-      r[u].store(yb + (v + (int64_t)u * lanes) * ld_y);
+      r[u].store(yb + sub_row(sg, voxels, n, v + (int64_t)u * lanes) * ld_y);
     }
   }
   for (; v < v1; v += lanes) {
     Vec<T> r;
-    r.load(xb + v * ld_x);
+    r.load(xb + sub_row(sg, voxels, n, v) * ld_x);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) r.v[i] = mish<kFast>(fmaf(av[i], r.v[i], bv[i]));
-    r.store(yb + v * ld_y);
+    r.store(yb + sub_row(sg, voxels, n, v) * ld_y);
   }
 }
 
@@ -253,7 +253,7 @@ __global__ void se_gate_kernel(const float* __restrict__ partial, int nblk, int6
 template <typename T>
 __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T* __restrict__ res, int ld_res,
                                       T* __restrict__ out, int ld_out, int64_t voxels, int c, int nvec, int lanes,
-                                      int64_t vpb, const float* __restrict__ gate, float* __restrict__ partial) {
+                                      int64_t vpb, const float* __restrict__ gate, float* __restrict__ partial, SubGeom sg) {
   constexpr int VEC = Vec<T>::N;
   extern __shared__ float smem[];
   const int col = threadIdx.x % nvec, lane = threadIdx.x / nvec;
@@ -266,23 +266,24 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
     g[i] = gate ? gate[(int64_t)n * c + col * VEC + i] : 1.f;
     s[i] = q[i] = 0.f;
   }
-  const T* hb = h + ((int64_t)n * voxels) * ld_h + col * VEC;
-  const T* rb = res + ((int64_t)n * voxels) * ld_res + col * VEC;
-  T* ob = out + ((int64_t)n * voxels) * ld_out + col * VEC;
+  const T* hb = h + col * VEC;
+  const T* rb = res + col * VEC;
+  T* ob = out + col * VEC;
   int64_t v = v0 + lane;
   for (; v + (int64_t)lanes < v1; v += 2 * (int64_t)lanes) {
     Vec<T> a[2], r[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      a[u].load(hb + (v + (int64_t)u * lanes) * ld_h);
-      r[u].load(rb + (v + (int64_t)u * lanes) * ld_res);
+      const int64_t row = sub_row(sg, voxels, n, v + (int64_t)u * lanes);
+      a[u].load(hb + row * ld_h);
+      r[u].load(rb + row * ld_res);
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       Vec<T> o;
 #pragma unroll
       for (int i = 0; i < VEC; ++i) o.v[i] = fmaf(a[u].v[i], g[i], r[u].v[i]);
-      o.store(ob + (v + (int64_t)u * lanes) * ld_out);
+      o.store(ob + sub_row(sg, voxels, n, v + (int64_t)u * lanes) * ld_out);
       if (partial) {
         // statistics of what the next GroupNorm will actually read (the stored, rounded value)
 #pragma unroll
@@ -296,11 +297,12 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
   }
   for (; v < v1; v += lanes) {
     Vec<T> a, r, o;
-    a.load(hb + v * ld_h);
-    r.load(rb + v * ld_res);
+    const int64_t row = sub_row(sg, voxels, n, v);
+    a.load(hb + row * ld_h);
+    r.load(rb + row * ld_res);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) o.v[i] = fmaf(a.v[i], g[i], r.v[i]);
-    o.store(ob + v * ld_out);
+    o.store(ob + row * ld_out);
     if (partial) {
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
@@ -337,7 +339,9 @@ static inline int64_t vox_per_block(int64_t voxels, int nblk) { return (voxels +
 using namespace diqt;
 
 extern "C" int diqt_channel_stats(const void* x, int dtype, int n, int64_t voxels, int c, int ld, int nblk,
-                                  float* partial, void* stream) {
+                                  float* partial, int sub_f, int sub_h, void* stream) {
+  const SubGeom sg{sub_f, sub_h};
+  if (sub_f > 1) DIQT_REQUIRE(n == sub_f * sub_f * sub_f && voxels == (int64_t)sub_h * sub_h * sub_h, "channel_stats: sub-volume geometry mismatch");
   const int vec = dtype == DIQT_BF16 ? 8 : 4;
   DIQT_REQUIRE(x && partial && n > 0 && voxels > 0 && nblk > 0, "channel_stats: bad arguments");
   DIQT_REQUIRE(c % vec == 0 && ld % vec == 0 && c / vec <= 256, "channel_stats: c=%d ld=%d not a multiple of %d", c, ld, vec);
@@ -347,10 +351,10 @@ extern "C" int diqt_channel_stats(const void* x, int dtype, int n, int64_t voxel
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)
     channel_stats_kernel<__nv_bfloat16><<<grid, m.threads, sh, st>>>((const __nv_bfloat16*)x, voxels, c, ld, m.nvec, m.lanes,
-                                                                    vox_per_block(voxels, nblk), partial);
+                                                                    vox_per_block(voxels, nblk), partial, sg);
   else
     channel_stats_kernel<float><<<grid, m.threads, sh, st>>>((const float*)x, voxels, c, ld, m.nvec, m.lanes,
-                                                            vox_per_block(voxels, nblk), partial);
+                                                            vox_per_block(voxels, nblk), partial, sg);
   return check_launch("channel_stats");
 }
 
@@ -373,7 +377,9 @@ extern "C" int diqt_gn_finalize(const float* partial, int n, int nblk, int64_t v
 }
 
 extern "C" int diqt_affine_mish(const void* x, int ld_x, void* y, int ld_y, int dtype, int n, int64_t voxels, int c,
-                                const float* a, const float* b, int nblk, void* stream) {
+                                const float* a, const float* b, int nblk, int sub_f, int sub_h, void* stream) {
+  const SubGeom sg{sub_f, sub_h};
+  if (sub_f > 1) DIQT_REQUIRE(n == sub_f * sub_f * sub_f && voxels == (int64_t)sub_h * sub_h * sub_h, "affine_mish: sub-volume geometry mismatch");
   const int vec = dtype == DIQT_BF16 ? 8 : 4;
   DIQT_REQUIRE(x && y && a && b && nblk > 0, "affine_mish: bad arguments");
   DIQT_REQUIRE(c % vec == 0 && ld_x % vec == 0 && ld_y % vec == 0 && c / vec <= 256, "affine_mish: c=%d not a multiple of %d", c, vec);
@@ -383,10 +389,10 @@ extern "C" int diqt_affine_mish(const void* x, int ld_x, void* y, int ld_y, int 
   if (dtype == DIQT_BF16)
     affine_mish_kernel<__nv_bfloat16, true><<<grid, m.threads, 0, st>>>((const __nv_bfloat16*)x, ld_x, (__nv_bfloat16*)y, ld_y,
                                                                        voxels, c, m.nvec, m.lanes,
-                                                                       vox_per_block(voxels, nblk), a, b);
+                                                                       vox_per_block(voxels, nblk), a, b, sg);
   else
     affine_mish_kernel<float, false><<<grid, m.threads, 0, st>>>((const float*)x, ld_x, (float*)y, ld_y, voxels, c, m.nvec,
-                                                                m.lanes, vox_per_block(voxels, nblk), a, b);
+                                                                m.lanes, vox_per_block(voxels, nblk), a, b, sg);
   return check_launch("affine_mish");
 }
 
@@ -403,7 +409,9 @@ extern "C" int diqt_se_gate(const float* partial, int n, int nblk, int64_t voxel
 
 extern "C" int diqt_scale_residual(const void* h, int ld_h, const void* res, int ld_res, void* out, int ld_out, int dtype,
                                    int n, int64_t voxels, int c, const float* gate, int nblk, float* partial,
-                                   void* stream) {
+                                   int sub_f, int sub_h, void* stream) {
+  const SubGeom sg{sub_f, sub_h};
+  if (sub_f > 1) DIQT_REQUIRE(n == sub_f * sub_f * sub_f && voxels == (int64_t)sub_h * sub_h * sub_h, "scale_residual: sub-volume geometry mismatch");
   const int vec = dtype == DIQT_BF16 ? 8 : 4;
   DIQT_REQUIRE(h && res && out && nblk > 0, "scale_residual: bad arguments");
   DIQT_REQUIRE(c % vec == 0 && ld_h % vec == 0 && ld_res % vec == 0 && ld_out % vec == 0 && c / vec <= 256,
@@ -415,11 +423,11 @@ extern "C" int diqt_scale_residual(const void* h, int ld_h, const void* res, int
   if (dtype == DIQT_BF16)
     scale_residual_kernel<__nv_bfloat16><<<grid, m.threads, sh, st>>>(
         (const __nv_bfloat16*)h, ld_h, (const __nv_bfloat16*)res, ld_res, (__nv_bfloat16*)out, ld_out, voxels, c, m.nvec,
-        m.lanes, vox_per_block(voxels, nblk), gate, partial);
+        m.lanes, vox_per_block(voxels, nblk), gate, partial, sg);
   else
     scale_residual_kernel<float><<<grid, m.threads, sh, st>>>((const float*)h, ld_h, (const float*)res, ld_res, (float*)out,
                                                              ld_out, voxels, c, m.nvec, m.lanes,
-                                                             vox_per_block(voxels, nblk), gate, partial);
+                                                             vox_per_block(voxels, nblk), gate, partial, sg);
   return check_launch("scale_residual");
 }
 

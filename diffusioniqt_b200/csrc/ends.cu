@@ -28,12 +28,21 @@ struct InitPlanes {
   long long stride[kInitMaxCin];
 };
 
+// element offset of merged-volume voxel (b, zz, yy, xx) inside a (n, d0, d1, d2) fp32 plane; in boundary mode (sg.f > 1) the
+// planes hold f^3 separate sub-volumes of side h while the conv runs over the merged volume
+__device__ __forceinline__ int64_t plane_offset(const SubGeom sg, int b, int zz, int yy, int xx, int d1, int d2, long long stride) {
+  if (sg.f <= 1) return (int64_t)b * stride + ((int64_t)zz * d1 + yy) * d2 + xx;
+  const int h = sg.h;
+  const int sb = zz / h + sg.f * (yy / h) + sg.f * sg.f * (xx / h);
+  return (int64_t)sb * stride + ((int64_t)(zz % h) * h + yy % h) * h + xx % h;
+}
+
 // one thread = one output voxel; CO_T output channels at a time are held in registers
 template <typename T, int CO_T>
 __global__ void __launch_bounds__(128)
 init_conv_kernel(InitPlanes planes, int c_in, const float* __restrict__ w /*[27][c_in][c_out]*/,
                  const float* __restrict__ bias, T* __restrict__ out, int ld_out, int n, int d0, int d1, int d2,
-                 int c_out) {
+                 int c_out, SubGeom sg) {
   extern __shared__ float sw[];  // weights [27*c_in][c_out] + bias[c_out]
   const int wcount = 27 * c_in * c_out;
   for (int i = threadIdx.x; i < wcount; i += blockDim.x) sw[i] = w[i];
@@ -58,9 +67,8 @@ init_conv_kernel(InitPlanes planes, int c_in, const float* __restrict__ w /*[27]
     for (int t = 0; t < 27; ++t) {
       const int zz = z + t / 9 - 1, yy = y + (t / 3) % 3 - 1, xx = x + t % 3 - 1;
       if (zz < 0 || zz >= d0 || yy < 0 || yy >= d1 || xx < 0 || xx >= d2) continue;  // zero padding
-      const int64_t off = ((int64_t)zz * d1 + yy) * d2 + xx;
       for (int ci = 0; ci < c_in; ++ci) {
-        const float v = __ldg(planes.p[ci] + (int64_t)b * planes.stride[ci] + off);
+        const float v = __ldg(planes.p[ci] + plane_offset(sg, b, zz, yy, xx, d1, d2, planes.stride[ci]));
         const float* wr = sw + (t * c_in + ci) * c_out + co0;
 #pragma unroll
         for (int j = 0; j < CO_T; ++j) acc[j] = fmaf(v, wr[j], acc[j]);
@@ -82,7 +90,7 @@ init_conv_kernel(InitPlanes planes, int c_in, const float* __restrict__ w /*[27]
 template <typename T, int CO_T>
 __global__ void __launch_bounds__(128)
 init_conv_x4_kernel(InitPlanes planes, int c_in, const float* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
-                    int ld_out, int n, int d0, int d1, int d2, int c_out) {
+                    int ld_out, int n, int d0, int d1, int d2, int c_out, SubGeom sg) {
   extern __shared__ float sw[];
   const int wcount = 27 * c_in * c_out;
   for (int i = threadIdx.x; i < wcount; i += blockDim.x) sw[i] = w[i];
@@ -108,14 +116,12 @@ init_conv_x4_kernel(InitPlanes planes, int c_in, const float* __restrict__ w, co
     for (int t9 = 0; t9 < 9; ++t9) {
       const int zz = z + t9 / 3 - 1, yy = y + t9 % 3 - 1;
       if (zz < 0 || zz >= d0 || yy < 0 || yy >= d1) continue;
-      const int64_t rowoff = ((int64_t)zz * d1 + yy) * d2;
       for (int ci = 0; ci < c_in; ++ci) {
-        const float* src = planes.p[ci] + (int64_t)b * planes.stride[ci] + rowoff;
         float in[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
           const int xx = x - 1 + k;
-          in[k] = (xx >= 0 && xx < d2) ? __ldg(src + xx) : 0.f;
+          in[k] = (xx >= 0 && xx < d2) ? __ldg(planes.p[ci] + plane_offset(sg, b, zz, yy, xx, d1, d2, planes.stride[ci])) : 0.f;
         }
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
@@ -188,7 +194,7 @@ __global__ void final_conv_kernel(const T* __restrict__ x, int ld, int64_t voxel
                                   const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ pred,
                                   int step_mode, const float* __restrict__ sched, const int32_t* __restrict__ step,
                                   const float* __restrict__ x_t, const float* __restrict__ noise,
-                                  float* __restrict__ x_next, float* __restrict__ x0, int64_t total_rows) {
+                                  float* __restrict__ x_next, float* __restrict__ x0, int64_t total_rows, SubGeom sg) {
   constexpr int VEC = Vec<T>::N;
   // nvec (power of two <= 32) consecutive threads share one voxel row
   const int col = threadIdx.x % nvec;
@@ -229,12 +235,19 @@ __global__ void final_conv_kernel(const T* __restrict__ x, int ld, int64_t voxel
         }
       }
       if (valid[u] && col == 0) {
-        const int64_t b = row / voxels, v = row - b * voxels;
+        int64_t b = row / voxels, v = row - b * voxels, ovox = voxels;
+        if (sg.f > 1) {  // merged row -> (sub-volume, local voxel); the fp32 state tensors stay in sub-volume layout
+          const int h = sg.h, fh = sg.f * sg.h;
+          const int xx = (int)(row % fh), yy = (int)((row / fh) % fh), zz = (int)(row / ((int64_t)fh * fh));
+          b = zz / h + sg.f * (yy / h) + sg.f * sg.f * (xx / h);
+          v = ((int64_t)(zz % h) * h + yy % h) * h + xx % h;
+          ovox = (int64_t)h * h * h;
+        }
 #pragma unroll
         for (int co = 0; co < MAXCO; ++co) {
           if (co >= c_out) break;
           const float p = acc[co] + bias[co];
-          const int64_t o = (b * c_out + co) * voxels + v;  // NCDHW fp32
+          const int64_t o = (b * c_out + co) * ovox + v;  // NCDHW fp32
           if (!step_mode) {
             pred[o] = p;
           } else {
@@ -326,7 +339,9 @@ extern "C" int diqt_init_conv_pack(const float* w, int c_out, int c_in, float* p
 
 extern "C" int diqt_init_conv(const float* const* planes, const int64_t* plane_stride, int c_in, const float* w_packed,
                               const float* bias, void* out, int ld_out, int dtype, int n, int d0, int d1, int d2, int c_out,
-                              void* stream) {
+                              int sub_f, int sub_h, void* stream) {
+  const SubGeom sg{sub_f, sub_h};
+  if (sub_f > 1) DIQT_REQUIRE(n == 1 && d0 == sub_f * sub_h && d1 == d0 && d2 == d0, "init_conv: boundary mode runs over ONE merged volume of side f*h");
   DIQT_REQUIRE(planes && plane_stride && w_packed && bias && out, "init_conv: null pointer");
   DIQT_REQUIRE(c_in > 0 && c_in <= kInitMaxCin, "init_conv: c_in=%d (max %d)", c_in, kInitMaxCin);
   DIQT_REQUIRE(c_out % 16 == 0, "init_conv: c_out=%d must be a multiple of 16", c_out);
@@ -347,11 +362,11 @@ extern "C" int diqt_init_conv(const float* const* planes, const int64_t* plane_s
     if (dtype == DIQT_BF16) {
       auto k = init_conv_x4_kernel<__nv_bfloat16, 32>;
       if (sh > 48 * 1024) DIQT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-      k<<<blocks4, threads, sh, st>>>(ip, c_in, w_packed, bias, (__nv_bfloat16*)out, ld_out, n, d0, d1, d2, c_out);
+      k<<<blocks4, threads, sh, st>>>(ip, c_in, w_packed, bias, (__nv_bfloat16*)out, ld_out, n, d0, d1, d2, c_out, sg);
     } else {
       auto k = init_conv_x4_kernel<float, 32>;
       if (sh > 48 * 1024) DIQT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-      k<<<blocks4, threads, sh, st>>>(ip, c_in, w_packed, bias, (float*)out, ld_out, n, d0, d1, d2, c_out);
+      k<<<blocks4, threads, sh, st>>>(ip, c_in, w_packed, bias, (float*)out, ld_out, n, d0, d1, d2, c_out, sg);
     }
     return check_launch("init_conv_x4");
   }
@@ -359,7 +374,7 @@ extern "C" int diqt_init_conv(const float* const* planes, const int64_t* plane_s
   do {                                                                                                            \
     auto k = init_conv_kernel<T, COT>;                                                                            \
     if (sh > 48 * 1024) DIQT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh)); \
-    k<<<blocks, threads, sh, st>>>(ip, c_in, w_packed, bias, (T*)out, ld_out, n, d0, d1, d2, c_out);              \
+    k<<<blocks, threads, sh, st>>>(ip, c_in, w_packed, bias, (T*)out, ld_out, n, d0, d1, d2, c_out, sg);          \
   } while (0)
   if (dtype == DIQT_BF16) {
     if (c_out % 64 == 0) DIQT_INIT_LAUNCH(__nv_bfloat16, 64);
@@ -376,7 +391,9 @@ extern "C" int diqt_init_conv(const float* const* planes, const int64_t* plane_s
 
 extern "C" int diqt_final_conv(const void* x, int ld, int dtype, int n, int64_t voxels, int c, int c_out, const float* w,
                                const float* bias, float* pred, int step_mode, const float* sched, const int32_t* step,
-                               const float* x_t, const float* noise, float* x_next, float* x0, void* stream) {
+                               const float* x_t, const float* noise, float* x_next, float* x0, int sub_f, int sub_h, void* stream) {
+  const SubGeom sg{sub_f, sub_h};
+  if (sub_f > 1) DIQT_REQUIRE(n == 1 && voxels == (int64_t)sub_f * sub_f * sub_f * sub_h * sub_h * sub_h, "final_conv: boundary mode runs over ONE merged volume");
   const int vec = dtype == DIQT_BF16 ? 8 : 4;
   DIQT_REQUIRE(x && w && bias, "final_conv: null pointer");
   DIQT_REQUIRE(c_out >= 1 && c_out <= 4, "final_conv: c_out=%d (1..4 supported)", c_out);
@@ -394,10 +411,10 @@ extern "C" int diqt_final_conv(const void* x, int ld, int dtype, int n, int64_t 
   if (dtype == DIQT_BF16)
     final_conv_kernel<__nv_bfloat16, 4><<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)x, ld, voxels, c, c_out, nvec, w,
                                                                             bias, pred, step_mode, sched, step, x_t, noise,
-                                                                            x_next, x0, rows);
+                                                                            x_next, x0, rows, sg);
   else
     final_conv_kernel<float, 4><<<(unsigned)blocks, threads, 0, st>>>((const float*)x, ld, voxels, c, c_out, nvec, w, bias, pred,
-                                                                    step_mode, sched, step, x_t, noise, x_next, x0, rows);
+                                                                    step_mode, sched, step, x_t, noise, x_next, x0, rows, sg);
   return check_launch("final_conv");
 }
 

@@ -59,15 +59,25 @@ class UnetEngine:
         self.impl = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tc": L.IMPL_TC, "zm": L.IMPL_ZM}[conv_impl]
         if dtype == "fp32":
             self.impl = L.IMPL_SIMT
-        if unet.boundary:
-            raise NotImplementedError("boundary=True (sub-volume halo exchange, imagen_pytorch3D.py:37-46) is not built yet")
+        # boundary mode (imagen_pytorch3D.py:37-46): the f^3 sub-volumes are stored merged as one (f*h)^3 volume, so every conv is a
+        # plain zero-padded conv over the merged volume (== boundary_pad + unpadded conv) while statistics stay per sub-volume
+        self.sub_f = int(unet.batch_sample_factor) if unet.boundary else 0
+        if self.sub_f > 1:
+            if self.n != self.sub_f ** 3 or len(set(self.dims0)) != 1:
+                raise ValueError(f"boundary mode needs batch == batch_sample_factor^3 = {self.sub_f ** 3} cubic sub-volumes, got batch {self.n}, dims {self.dims0}")
         nl = len(unet.in_out)
         for d in self.dims0:
             if d % (1 << (nl - 1)) != 0:
                 raise ValueError(f"volume side {d} is not divisible by 2^{nl - 1}")
         self.nl = nl
         self.level_dims = [tuple(d >> l for d in self.dims0) for l in range(nl)]
-        self.level_vox = [a * b * c for (a, b, c) in self.level_dims]
+        self.level_vox = [a * b * c for (a, b, c) in self.level_dims]          # rows per statistics volume
+        if self.sub_f > 1:
+            self.conv_n = 1
+            self.conv_dims = [tuple(self.sub_f * d for d in ld) for ld in self.level_dims]
+        else:
+            self.conv_n, self.conv_dims = self.n, self.level_dims
+        self.level_sub = [(self.sub_f, ld[0]) if self.sub_f > 1 else (0, 0) for ld in self.level_dims]
         self._plans: List[int] = []
         self._keep: List[torch.Tensor] = []   # packed weights etc.
         self._ops = []                        # callables(stream)
@@ -89,8 +99,10 @@ class UnetEngine:
     def _conv_site(self, name, mode, level_in, c_in, ld_in, c_out, ld_out, weight, bias, src_ptr, dst_ptr, stats=None):
         """Pack weights, create the plan, return the launch closure.  With `stats` (an Act + partial buffer) the conv is
         asked to emit the channel statistics of its output; if it cannot, a separate stats pass is appended by the caller."""
-        d0, d1, d2 = self.level_dims[level_in]
-        desc = L.ConvDesc(mode=mode, dtype=self.ddtype, impl=self.impl, n=self.n, d0=d0, d1=d1, d2=d2,
+        d0, d1, d2 = self.conv_dims[level_in]
+        if self.sub_f > 1:
+            stats = None   # fused conv statistics are per conv volume; boundary mode needs them per sub-volume
+        desc = L.ConvDesc(mode=mode, dtype=self.ddtype, impl=self.impl, n=self.conv_n, d0=d0, d1=d1, d2=d2,
                           c_in=c_in, ld_in=ld_in, c_out=c_out, ld_out=ld_out, flags=0)
         impl = C.c_int(0)
         L.check(self.lib.diqt_conv_resolved_impl(C.byref(desc), C.byref(impl)), f"conv {name}")
@@ -215,7 +227,8 @@ class UnetEngine:
         def add_stats(x: Act, level, part):
             nb, vox = self.nblk[level], self.level_vox[level]
             xp, xc, xl, pp = x.ptr, x.c, x.ld, part.data_ptr()
-            ops.append(lambda st: L.check(stats_fn(xp, dd, n, vox, xc, xl, nb, pp, st), "channel_stats"))
+            sf, sh = self.level_sub[level]
+            ops.append(lambda st: L.check(stats_fn(xp, dd, n, vox, xc, xl, nb, pp, sf, sh, st), "channel_stats"))
             return (part, nb)
 
         def add_norm_act(x: Act, level, gn, film_off, dst_buf, name):
@@ -235,7 +248,8 @@ class UnetEngine:
                 ops.append(op)
             dst = Act(dst_buf, x.c, x.c)
             xp, xl, dp, dl, nbk = x.ptr, x.ld, dst.ptr, dst.ld, self.nblk_stream[level]
-            ops.append(lambda st: L.check(aff(xp, xl, dp, dl, dd, n, vox, c, pa, pb, nbk, st), name + ".mish"))
+            sf, sh = self.level_sub[level]
+            ops.append(lambda st: L.check(aff(xp, xl, dp, dl, dd, n, vox, c, pa, pb, nbk, sf, sh, st), name + ".mish"))
             return dst
 
         def add_resblock(blk, x: Act, level, out: Act, name):
@@ -276,7 +290,8 @@ class UnetEngine:
             self._pp ^= 1
             nbk = self.nblk[level]
             hp, hl, rp, rl, op_, ol, opp = h.ptr, h.ld, r.ptr, r.ld, out.ptr, out.ld, opart.data_ptr()
-            ops.append(lambda st: L.check(sres(hp, hl, rp, rl, op_, ol, dd, n, vox, cout, gate_ptr, nbk, opp, st), name + ".residual"))
+            sf, sh = self.level_sub[level]
+            ops.append(lambda st: L.check(sres(hp, hl, rp, rl, op_, ol, dd, n, vox, cout, gate_ptr, nbk, opp, sf, sh, st), name + ".residual"))
             out.stats = (opart, nbk)
             return out
 
@@ -286,11 +301,12 @@ class UnetEngine:
         wi = self._f32(u.init_conv.weight)
         self.b_init = self._f32(u.init_conv.bias)
         L.check(lib.diqt_init_conv_pack(wi.data_ptr(), dims[0], u.init_channels, self.w_init.data_ptr(), L.current_stream()), "init_conv_pack")
-        d0, d1, d2 = self.dims0
-        xp, xl, c0, nin = x.ptr, x.ld, dims[0], u.init_channels
+        d0, d1, d2 = self.conv_dims[0]
+        xp, xl, c0, nin, cn = x.ptr, x.ld, dims[0], u.init_channels, self.conv_n
         wip, bip = self.w_init.data_ptr(), self.b_init.data_ptr()
         planes_ref, strides_ref = self._planes, self._pstrides
-        ops.append(lambda st: L.check(lib.diqt_init_conv(planes_ref, strides_ref, nin, wip, bip, xp, xl, dd, n, d0, d1, d2, c0, st), "init_conv"))
+        sf0, sh0 = self.level_sub[0]
+        ops.append(lambda st: L.check(lib.diqt_init_conv(planes_ref, strides_ref, nin, wip, bip, xp, xl, dd, cn, d0, d1, d2, c0, sf0, sh0, st), "init_conv"))
 
         # ---- down path
         skip_scale = u.skip_connect_scale
@@ -307,7 +323,7 @@ class UnetEngine:
             if l != nl - 1:
                 if skip_scale != 1.0:
                     dst = Act(self.cat[l], c, dims[l + 1] + c, offset=dims[l + 1])
-                    rows = n * self.level_vox[l]
+                    rows = n * self.level_vox[l]   # pitched row copy: layout (merged or not) does not matter
                     sp_, sl, dp_, dl = x.ptr, x.ld, dst.ptr, dst.ld
                     ops.append(lambda st, sp_=sp_, sl=sl, dp_=dp_, dl=dl, rows=rows, c=c: L.check(
                         lib.diqt_scale_copy(sp_, sl, dp_, dl, dd, rows, c, skip_scale, st), "skip_scale"))
@@ -400,9 +416,10 @@ class UnetEngine:
         """final 1x1x1 conv; fused=True also applies the DDPM update in place on x_in."""
         st = stream if stream is not None else L.current_stream()
         x, u = self.last_act, self.unet
-        L.check(self.lib.diqt_final_conv(x.ptr, x.ld, self.ddtype, self.n, self.level_vox[0], x.c, u.channels_out, self.w_final.data_ptr(),
-                                         self.b_final.data_ptr(), self.pred.data_ptr(), 1 if fused else 0, sched, step,
-                                         self.x_in.data_ptr(), noise, self.x_in.data_ptr(), x0, st), "final_conv")
+        sf, sh = self.level_sub[0]
+        L.check(self.lib.diqt_final_conv(x.ptr, x.ld, self.ddtype, self.conv_n, self.level_vox[0] * (self.n // self.conv_n), x.c, u.channels_out,
+                                         self.w_final.data_ptr(), self.b_final.data_ptr(), self.pred.data_ptr(), 1 if fused else 0, sched, step,
+                                         self.x_in.data_ptr(), noise, self.x_in.data_ptr(), x0, sf, sh, st), "final_conv")
 
     def load_inputs(self, x=None, lowres_cond_img=None, cond_images=None):
         if x is not None:

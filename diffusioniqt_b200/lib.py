@@ -41,15 +41,15 @@ _SIGNATURES = {
     "diqt_conv_plan_set_stats": [_vp, _vp, C.POINTER(C.c_int)],
     "diqt_conv_plan_destroy": [_vp],
     "diqt_conv_run": [_vp, _vp],
-    "diqt_channel_stats": [_vp, _i, _i, _i64, _i, _i, _i, _vp, _vp],
+    "diqt_channel_stats": [_vp, _i, _i, _i64, _i, _i, _i, _vp, _i, _i, _vp],
     "diqt_gn_finalize": [_vp, _i, _i, _i64, _i, _i, _f, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp],
-    "diqt_affine_mish": [_vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _vp, _i, _vp],
+    "diqt_affine_mish": [_vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _vp, _i, _i, _i, _vp],
     "diqt_se_gate": [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp],
-    "diqt_scale_residual": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _i, _vp, _vp],
+    "diqt_scale_residual": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _i, _vp, _i, _i, _vp],
     "diqt_scale_copy": [_vp, _i, _vp, _i, _i, _i64, _i, _f, _vp],
     "diqt_init_conv_pack": [_vp, _i, _i, _vp, _vp],
-    "diqt_init_conv": [C.POINTER(_vp), C.POINTER(_i64), _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp],
-    "diqt_final_conv": [_vp, _i, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "diqt_init_conv": [C.POINTER(_vp), C.POINTER(_i64), _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "diqt_final_conv": [_vp, _i, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "diqt_ddpm_update": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "diqt_clamp": [_vp, _i64, _f, _f, _vp],
     "diqt_fourier_features": [_vp, _i, _vp, _i, _vp, _vp],

@@ -87,7 +87,7 @@ def channel_stats(x: torch.Tensor, nblk: int = 8) -> torch.Tensor:
     n, c = x.shape[0], x.shape[-1]
     vox = x.numel() // (n * c)
     part = torch.empty(n, nblk, c, 2, dtype=torch.float32, device=x.device)
-    L.check(lib.diqt_channel_stats(x.data_ptr(), _dt(x), n, vox, c, c, nblk, part.data_ptr(), L.current_stream()), "channel_stats")
+    L.check(lib.diqt_channel_stats(x.data_ptr(), _dt(x), n, vox, c, c, nblk, part.data_ptr(), 0, 0, L.current_stream()), "channel_stats")
     return part
 
 
@@ -106,7 +106,7 @@ def group_norm_film_mish(x: torch.Tensor, groups: int, gamma, beta, scale_shift:
     L.check(lib.diqt_gn_finalize(part.data_ptr(), n, nblk, vox, c, groups, eps, g.data_ptr(), be.data_ptr(), L.ptr(film), 2 * c, 0, 1,
                                  a.data_ptr(), b.data_ptr(), st), "gn_finalize")
     y = torch.empty_like(x)
-    L.check(lib.diqt_affine_mish(x.data_ptr(), c, y.data_ptr(), c, _dt(x), n, vox, c, a.data_ptr(), b.data_ptr(), nblk, st), "affine_mish")
+    L.check(lib.diqt_affine_mish(x.data_ptr(), c, y.data_ptr(), c, _dt(x), n, vox, c, a.data_ptr(), b.data_ptr(), nblk, 0, 0, st), "affine_mish")
     torch.cuda.current_stream().synchronize()
     return y
 
@@ -125,6 +125,6 @@ def se_scale_residual(h: torch.Tensor, res: torch.Tensor, w1, w2, nblk: int = 8)
     out = torch.empty_like(h)
     opart = torch.empty(n, nblk, c, 2, dtype=torch.float32, device=h.device)
     L.check(lib.diqt_scale_residual(h.data_ptr(), c, res.data_ptr(), c, out.data_ptr(), c, _dt(h), n, vox, c, gate.data_ptr(), nblk,
-                                    opart.data_ptr(), st), "scale_residual")
+                                    opart.data_ptr(), 0, 0, st), "scale_residual")
     torch.cuda.current_stream().synchronize()
     return out, gate, opart

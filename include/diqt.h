@@ -108,10 +108,15 @@ int diqt_conv_run(const diqt_conv_plan* plan, void* stream);
  * Replaces nn.GroupNorm :546, the FiLM line :559-561, nn.Mish :547, SE3D :617-632 and the
  * residual add :612 of Block / ResnetBlock.
  * ------------------------------------------------------------------------------------------ */
+/* Sub-volume ("boundary") geometry, taken by the per-volume kernels as (sub_f, sub_h): sub_f <= 1 means n independent volumes of
+ * `voxels` rows each.  sub_f = f > 1 is the reference's boundary mode (boundary_pad, imagen_pytorch3D.py:37-46, eval_config.yaml:26):
+ * the n = f^3 sub-volumes of side sub_h are stored MERGED as one volume of side f*sub_h (so convolutions see their neighbours for
+ * free), sub-volume b = zb + f*yb + f*f*xb being block (zb, yb, xb) along (d0, d1, d2) (utils_mine.py:25-67); statistics, FiLM and
+ * gates stay per sub-volume. */
 /* per-block partial channel sums: partial[n][nblk][c][2] (sum, sum of squares), fp32; block b of volume i
  * covers voxels [b*ceil(voxels/nblk), ...).  Reduced in a fixed order -> bitwise reproducible. */
 int diqt_channel_stats(const void* x, int dtype, int n, int64_t voxels, int c, int ld, int nblk,
-                       float* partial, void* stream);
+                       float* partial, int sub_f, int sub_h, void* stream);
 /* Fold GroupNorm(groups, c, eps) (+ optional FiLM) into a per-(n,c) affine  y = a*x + b.
  * film: NULL or fp32 rows [..][film_ld] holding (scale[c], shift[c]) at film[row][0..2c);
  * row = (film_row ? *film_row : 0) + i * film_row_stride_n   (film_row is a DEVICE pointer so a
@@ -121,7 +126,7 @@ int diqt_gn_finalize(const float* partial, int n, int nblk, int64_t voxels, int 
                      const int32_t* film_row, int film_row_stride_n, float* a, float* b, void* stream);
 /* y = mish(a[n][c] * x + b[n][c]) */
 int diqt_affine_mish(const void* x, int ld_x, void* y, int ld_y, int dtype, int n, int64_t voxels, int c,
-                     const float* a, const float* b, int nblk, void* stream);
+                     const float* a, const float* b, int nblk, int sub_f, int sub_h, void* stream);
 /* gate[n][c] = sigmoid(W2 . relu(W1 . mean[n][:])), mean from the channel partial sums;
  * W1: (hidden, c)  W2: (c, hidden), bias-free */
 int diqt_se_gate(const float* partial, int n, int nblk, int64_t voxels, int c, int hidden, const float* w1,
@@ -129,7 +134,8 @@ int diqt_se_gate(const float* partial, int n, int nblk, int64_t voxels, int c, i
 /* out = h * gate[n][c] + res  (gate may be NULL -> 1); if partial != NULL also writes per-block channel
  * stats of out (the input of the next GroupNorm) */
 int diqt_scale_residual(const void* h, int ld_h, const void* res, int ld_res, void* out, int ld_out, int dtype,
-                        int n, int64_t voxels, int c, const float* gate, int nblk, float* partial, void* stream);
+                        int n, int64_t voxels, int c, const float* gate, int nblk, float* partial, int sub_f, int sub_h,
+                        void* stream);
 
 /* dst[r][0..c) = src[r][0..c) * scale over `rows` pitched rows: the scaled skip connection
  * (scale_skip_connection, :1346, :1653) when it cannot be a pure view */
@@ -145,7 +151,7 @@ int diqt_scale_copy(const void* src, int ld_src, void* dst, int ld_dst, int dtyp
  * w: fp32 packed [27][c_in][c_out]; */
 int diqt_init_conv(const float* const* planes, const int64_t* plane_stride, int c_in, const float* w_packed,
                    const float* bias, void* out, int ld_out, int dtype, int n, int d0, int d1, int d2, int c_out,
-                   void* stream);
+                   int sub_f, int sub_h, void* stream);
 int diqt_init_conv_pack(const float* w, int c_out, int c_in, float* packed, void* stream);
 
 /* final_conv (:1477, 1x1x1, c -> c_out<=4) producing the fp32 NCDHW prediction, optionally fused
@@ -155,7 +161,7 @@ int diqt_init_conv_pack(const float* w, int c_out, int c_in, float* packed, void
  * read at row *step.  step_mode 0: only write pred.  1: fused update (x_t, noise, x_next, x0). */
 int diqt_final_conv(const void* x, int ld, int dtype, int n, int64_t voxels, int c, int c_out, const float* w,
                     const float* bias, float* pred, int step_mode, const float* sched, const int32_t* step,
-                    const float* x_t, const float* noise, float* x_next, float* x0, void* stream);
+                    const float* x_t, const float* noise, float* x_next, float* x0, int sub_f, int sub_h, void* stream);
 /* the same elementwise update on an existing prediction (used with dynamic thresholding) */
 int diqt_ddpm_update(const float* pred, const float* sched, const int32_t* step, const float* x_t,
                      const float* noise, float* x_next, float* x0, int64_t count, void* stream);

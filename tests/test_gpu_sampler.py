@@ -9,7 +9,7 @@ from helpers import load_golden, max_rel, oracle_sample, rel_err, weights_for
 
 pytestmark = pytest.mark.gpu
 
-CASES = [n for n in SAMPLE_CASES if not SAMPLE_CASES[n]["unet"].get("boundary")]
+CASES = list(SAMPLE_CASES)
 
 
 def _imagen(case, dtype):

@@ -7,7 +7,7 @@ from helpers import load_golden, max_rel, oracle_forward, rel_err, weights_for
 
 pytestmark = pytest.mark.gpu
 
-CASES = [n for n in FORWARD_CASES if not FORWARD_CASES[n]["unet"].get("boundary")]
+CASES = list(FORWARD_CASES)
 
 
 def _gpu_unet(case, dtype):
