@@ -62,10 +62,10 @@ def test_stitched_volume_psnr_ssim(dtype, psnr_tol, ssim_tol):
     want = torch.from_numpy(so.background_mask(want, lowres.numpy()))
     assert res.n_patches == len(kept)
     # No trained checkpoint ships, so the "ground truth" is synthetic: the reference pipeline's own output plus an independent
-    # field sized so that the reference scores ~25 dB, the regime of a real IQT model.  (Against an unrelated random truth, ~13 dB,
-    # the statistic mostly measures chance correlations of rounding noise.)
+    # field sized so that the reference scores ~26 dB after the metric's min-max normalisation (CPU-checked: 25.93 dB), the regime
+    # of a real IQT model.  (Against an unrelated random truth, ~13 dB, the statistic mostly measures chance correlations of rounding noise.)
     span = float(want.max() - want.min())
-    truth = want + synthetic_field((N, N, N), 63) * (span * 10 ** (-25 / 20))
+    truth = want + synthetic_field((N, N, N), 63) * (span * 10 ** (-35 / 20))
     assert 23.0 < mo.psnr(want, truth) < 27.0
     assert abs(mo.psnr(got, truth) - mo.psnr(want, truth)) < psnr_tol
     assert abs(mo.ssim3d(got, truth) - mo.ssim3d(want, truth)) < ssim_tol
