@@ -19,8 +19,8 @@ int conv_tc_set_stats(TcPlan* plan, float* partial);
 struct ZmPlan;
 bool conv_zm_supported(const diqt_conv_desc* d);
 bool conv_zm_profitable(const diqt_conv_desc* d);
-size_t conv_zm_packed_bytes();
-int conv_zm_pack(const float* w, void* packed, cudaStream_t st);
+size_t conv_zm_packed_bytes(const diqt_conv_desc* d);
+int conv_zm_pack(const diqt_conv_desc* d, const float* w, void* packed, cudaStream_t st);
 int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void* packed, const float* bias, ZmPlan** plan);
 int conv_zm_run(const ZmPlan* plan, cudaStream_t st);
 int conv_zm_set_stats(ZmPlan* plan, float* partial);
@@ -59,7 +59,7 @@ static int resolve_impl(const diqt_conv_desc* d, int* impl) {
   if (want == DIQT_IMPL_AUTO)
     want = (conv_zm_supported(d) && conv_zm_profitable(d)) ? DIQT_IMPL_ZM : conv_tc_supported(d) ? DIQT_IMPL_TC : DIQT_IMPL_SIMT;
   if (want == DIQT_IMPL_ZM && !conv_zm_supported(d)) {
-    set_error("conv: z-march kernel needs 3x3x3 bf16 64->64 with d2 %% 8 == 0, d1 %% 16 == 0 (got c_in=%d c_out=%d dims %d,%d,%d)", d->c_in,
+    set_error("conv: z-march kernel needs 3x3x3 bf16, c_in %% 64 == 0, c_out %% 64 == 0 (<= 256), d2 %% 8 == 0, d1 %% 16 == 0 (got c_in=%d c_out=%d dims %d,%d,%d)", d->c_in,
               d->c_out, d->d0, d->d1, d->d2);
     return DIQT_EUNSUPPORTED;
   }
@@ -87,7 +87,7 @@ extern "C" int diqt_conv_packed_bytes(const diqt_conv_desc* d, size_t* bytes) {
   if (rc) return rc;
   if ((rc = resolve_impl(d, &impl))) return rc;
   DIQT_REQUIRE(bytes, "conv_packed_bytes: null output");
-  *bytes = impl == DIQT_IMPL_ZM   ? conv_zm_packed_bytes()
+  *bytes = impl == DIQT_IMPL_ZM   ? conv_zm_packed_bytes(d)
            : impl == DIQT_IMPL_TC ? conv_tc_packed_bytes(d)
                                   : (size_t)simt_taps(d->mode) * d->c_in * d->c_out * sizeof(float);
   return DIQT_OK;
@@ -100,7 +100,7 @@ extern "C" int diqt_conv_pack(const diqt_conv_desc* d, const float* w, const flo
   if ((rc = resolve_impl(d, &impl))) return rc;
   DIQT_REQUIRE(w && packed_w && packed_bias, "conv_pack: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  rc = impl == DIQT_IMPL_ZM ? conv_zm_pack(w, packed_w, st) : impl == DIQT_IMPL_TC ? conv_tc_pack(d, w, packed_w, st) : conv_simt_pack(d, w, packed_w, st);
+  rc = impl == DIQT_IMPL_ZM ? conv_zm_pack(d, w, packed_w, st) : impl == DIQT_IMPL_TC ? conv_tc_pack(d, w, packed_w, st) : conv_simt_pack(d, w, packed_w, st);
   if (rc) return rc;
   if (!bias) {
     DIQT_CUDA(cudaMemsetAsync(packed_bias, 0, sizeof(float) * d->c_out, st));

@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <utility>
 
 #include "../../include/diqt.h"
 
@@ -24,6 +25,33 @@ inline int check_launch(const char* what) {
     return DIQT_ECUDA;
   }
   return DIQT_OK;
+}
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// One sampler iteration is a chain of ~175 dependent kernels, many of them a few microseconds long.  Every hot-path
+// kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may become resident while its
+// predecessor is still running, does its private prologue (barrier init, TMEM allocation, weight / bias loads) and then
+// blocks in pdl_wait() until the predecessor grid has completed and flushed.  Because EVERY such kernel executes
+// pdl_wait(), completion is transitive: after pdl_wait() all earlier kernels of the stream are complete.  Kernels that
+// do not call pdl_wait() must be launched with plain <<<>>>.  Works under stream capture (programmatic graph edges).
+bool pdl_enabled();  // DIQT_DISABLE_PDL=1 switches the attribute off (A/B measurements)
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);  // errors surface in check_launch()
 }
 
 #define DIQT_REQUIRE(cond, ...)          \

@@ -1,5 +1,5 @@
-// "z-march" tcgen05 convolution: 3x3x3, 64 -> 64 channels, bf16, the shape that carries 77 % of the U-Net's FLOPs
-// (Block.project at full resolution, imagen_pytorch3D.py:550-553).
+// "z-march" tcgen05 convolution: 3x3x3, C_in = 64*KC -> C_out = 64*NH channels, bf16: every Block.project of the U-Net
+// (imagen_pytorch3D.py:550-553; 64->64 at full resolution alone carries 77 % of the FLOPs).
 //
 // Two measurements on B200 shape this kernel (tools/umma_probe.cu, profiles/umma_probe_r1.log):
 //   1. tcgen05.mma M=128 takes 64 cycles per K=16 step for N=64 AND for N=128: an N=64 GEMM can only reach half of
@@ -16,7 +16,15 @@
 // while the tensor core already works on the next planes.  Two such columns ("slots") are processed in lockstep so
 // that each 24 KB weight stage streamed from L2 is used twice.
 //
-// Warp roles (224 threads): 0 plane TMA producer, 1 weight producer, 2 TMEM owner + MMA issuer, 3-6 epilogue.
+// Wider layers: the input plane is walked in KC chunks of 64 channels (one TMA box per chunk, 9 weight stages each, all
+// accumulating into the same TMEM blocks) and the output channels in NH groups of 64 that are separate work items (the
+// per-tap kernel this replaces re-read every input voxel 27 times and was L2->SM bandwidth bound, profiles/r1f_*).
+//
+// ncu (profiles/r1f_ncu_conv_summary.md) showed ONE issuing warp could not keep the tensor pipe fed (~104 cycles of
+// descriptor arithmetic per UTCHMMA against 64-96 cycles of pipe time), so each slot has its own issuing warp.
+//
+// Warp roles (256 threads): 0 plane TMA producer, 1 weight producer, 2-3 MMA issuers (slot 0 / 1; warp 2 owns TMEM),
+// 4-7 epilogue.
 #include <string.h>
 
 #include <algorithm>
@@ -32,29 +40,35 @@ constexpr int ZM_RING = 2;                              // plane buffers per slo
 constexpr int ZM_WBLOCK = 64 * 128;                     // one (dz,dy,dx) weight block: 64 c_out rows x 64 c_in
 constexpr int ZM_WSTAGE = 3 * ZM_WBLOCK;
 constexpr int ZM_WSTAGES = 4;
-constexpr int ZM_THREADS = 224;
+constexpr int ZM_THREADS = 256;
 constexpr int ZM_OUT_BYTES = 128 * 128;
+constexpr int ZM_MAX_COUT = 256;
 
 struct ZmParams {
   CUtensorMap in_map, out_map;
-  const uint8_t* w;   // [kb = kh*3+kw][j: 0 -> kd=2 (dz=+1), 1 -> kd=1, 2 -> kd=0 (dz=-1)][64 c_out][64 c_in], pre-swizzled
-  const float* bias;
-  float* stats;       // NULL or [n][2*gridDim.x][64][2]
+  const uint8_t* w;   // [nh][kc][kb = kh*3+kw][j: 0 -> kd=2 (dz=+1), 1 -> kd=1, 2 -> kd=0 (dz=-1)][64 c_out][64 c_in], pre-swizzled
+  const float* bias;  // [c_out]
+  float* stats;       // NULL or [n][2*gridDim.x][c_out][2]
   int n, D, H, W;
-  int tiles_x, tiles_y, nseg, L, items, pairs;
+  int KC, NH, c_out;  // c_in / 64, c_out / 64
+  int tiles_x, tiles_y, nseg, L;
+  int ipn, ipn_pad;   // work items per output-channel group (padded to even so that a slot pair shares its weights)
+  int items, pairs;
   uint32_t idesc[3];  // N = 64, 128, 192
 };
 
 struct ZmItem {
-  int valid, b, x0, y0, z0, z1, p_lo, niter;
+  int valid, b, nh, x0, y0, z0, z1, p_lo, niter;
 };
 
 __device__ __forceinline__ ZmItem zm_item(const ZmParams& p, int item) {
   ZmItem it;
-  it.valid = item < p.items;
+  it.nh = item / p.ipn_pad;
+  const int r = item - it.nh * p.ipn_pad;
+  it.valid = item < p.items && r < p.ipn;
   if (!it.valid) { it.b = it.x0 = it.y0 = it.z0 = it.z1 = it.p_lo = 0; it.niter = 0; return it; }
-  const int seg = item % p.nseg;
-  int t = item / p.nseg;
+  const int seg = r % p.nseg;
+  int t = r / p.nseg;
   const int tx = t % p.tiles_x; t /= p.tiles_x;
   const int ty = t % p.tiles_y;
   it.b = t / p.tiles_y;
@@ -77,23 +91,23 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
   uint8_t* planes = smem;                                               // [2 slots][ZM_RING][ZM_PLANE_STRIDE]
   uint8_t* wst = planes + 2 * ZM_RING * ZM_PLANE_STRIDE;                // [ZM_WSTAGES][ZM_WSTAGE]
   uint8_t* out_stage = wst + ZM_WSTAGES * ZM_WSTAGE;                    // 16 KB
-  float* s_bias = reinterpret_cast<float*>(out_stage + ZM_OUT_BYTES);   // 64
-  float* s_red = s_bias + 64;                                           // [4][64][2]
+  float* s_bias = reinterpret_cast<float*>(out_stage + ZM_OUT_BYTES);   // [ZM_MAX_COUT]
+  float* s_red = s_bias + ZM_MAX_COUT;                                  // [4][64][2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_red + 4 * 64 * 2);
   uint64_t* pl_full = bars;                       // [2][ZM_RING]
   uint64_t* pl_empty = pl_full + 2 * ZM_RING;     // [2][ZM_RING]
   uint64_t* w_full = pl_empty + 2 * ZM_RING;      // [ZM_WSTAGES]
-  uint64_t* w_empty = w_full + ZM_WSTAGES;        // [ZM_WSTAGES]
+  uint64_t* w_empty = w_full + ZM_WSTAGES;        // [ZM_WSTAGES]  (one arrival per issuing warp)
   uint64_t* acc_full = w_empty + ZM_WSTAGES;      // [2][2]
   uint64_t* acc_free = acc_full + 4;              // [2][2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (threadIdx.x < 64) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  for (int i = threadIdx.x; i < p.c_out; i += ZM_THREADS) s_bias[i] = p.bias[i];
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2 * ZM_RING; ++i) { mbar_init(smem_u32(&pl_full[i]), 1); mbar_init(smem_u32(&pl_empty[i]), 1); }
-    for (int i = 0; i < ZM_WSTAGES; ++i) { mbar_init(smem_u32(&w_full[i]), 1); mbar_init(smem_u32(&w_empty[i]), 1); }
+    for (int i = 0; i < ZM_WSTAGES; ++i) { mbar_init(smem_u32(&w_full[i]), 1); mbar_init(smem_u32(&w_empty[i]), 2); }
     for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_free[i]), 4); }
     fence_barrier_init();
   }
@@ -105,7 +119,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 3) {  // all accumulator blocks start at zero: every MMA accumulates
+  if (warp >= 4) {  // all accumulator blocks start at zero: every MMA accumulates
     const uint32_t q = (uint32_t)(warp & 3) * 32;
     for (int c = 0; c < 16; ++c) tmem_st32_zero(tmem_base + (q << 16) + (uint32_t)c * 32);
     tmem_st_wait();
@@ -113,6 +127,8 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();  // everything above is private to this CTA; activations of the previous kernel are touched only below
 
   if (warp == 0) {
     // ===================== input plane producer =====================
@@ -123,16 +139,20 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
         const ZmItem it0 = zm_item(p, 2 * pair), it1 = zm_item(p, 2 * pair + 1);
         const int niter = max(it0.niter, it1.niter);
         for (int i = 0; i < niter; ++i) {
+          // chunk-major, slot-minor: both issuers consume the weight stages of chunk kc in lockstep, so the producer must never
+          // block on one slot's ring while the other slot still lacks an earlier chunk (KC > ZM_RING would deadlock)
+          for (int kc = 0; kc < p.KC; ++kc) {
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const ZmItem& it = s ? it1 : it0;
-            if (i >= it.niter) continue;
-            const int b = s * ZM_RING + ring[s];
-            mbar_wait(smem_u32(&pl_empty[b]), phase[s] ^ 1);
-            const uint32_t bar = smem_u32(&pl_full[b]);
-            mbar_expect_tx(bar, ZM_PLANE_BYTES);
-            tma_load_5d(smem_u32(planes + (size_t)b * ZM_PLANE_STRIDE), &p.in_map, bar, 0, it.x0 - 1, it.y0 - 1, it.p_lo + i, it.b);
-            if (++ring[s] == ZM_RING) { ring[s] = 0; phase[s] ^= 1; }
+            for (int s = 0; s < 2; ++s) {
+              const ZmItem& it = s ? it1 : it0;
+              if (i >= it.niter) continue;
+              const int b = s * ZM_RING + ring[s];
+              mbar_wait(smem_u32(&pl_empty[b]), phase[s] ^ 1);
+              const uint32_t bar = smem_u32(&pl_full[b]);
+              mbar_expect_tx(bar, ZM_PLANE_BYTES);
+              tma_load_5d(smem_u32(planes + (size_t)b * ZM_PLANE_STRIDE), &p.in_map, bar, kc * 64, it.x0 - 1, it.y0 - 1, it.p_lo + i, it.b);
+              if (++ring[s] == ZM_RING) { ring[s] = 0; phase[s] ^= 1; }
+            }
           }
         }
       }
@@ -145,6 +165,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
       for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
         const ZmItem it0 = zm_item(p, 2 * pair), it1 = zm_item(p, 2 * pair + 1);
         const int niter = max(it0.niter, it1.niter);
+        const uint8_t* wnh = p.w + (size_t)it0.nh * p.KC * 27 * ZM_WBLOCK;
         for (int i = 0; i < niter; ++i) {
           int jlo = 2, jhi = 0;
 #pragma unroll
@@ -156,97 +177,116 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
             jlo = min(jlo, a); jhi = max(jhi, b);
           }
           const uint32_t bytes = (uint32_t)(jhi - jlo + 1) * ZM_WBLOCK;
-          for (int kb = 0; kb < 9; ++kb) {
+          for (int kk = 0; kk < 9 * p.KC; ++kk) {  // kk = kc * 9 + kb
             mbar_wait(smem_u32(&w_empty[stage]), phase ^ 1);
             const uint32_t bar = smem_u32(&w_full[stage]);
             mbar_expect_tx(bar, bytes);
-            bulk_load(smem_u32(wst + (size_t)stage * ZM_WSTAGE + (size_t)jlo * ZM_WBLOCK), p.w + ((size_t)kb * 3 + jlo) * ZM_WBLOCK, bytes, bar);
+            bulk_load(smem_u32(wst + (size_t)stage * ZM_WSTAGE + (size_t)jlo * ZM_WBLOCK), wnh + ((size_t)kk * 3 + jlo) * ZM_WBLOCK, bytes, bar);
             if (++stage == ZM_WSTAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
-  } else if (warp == 2) {
-    // ===================== MMA issuer =====================
+  } else if (warp < 4) {
+    // ===================== MMA issuer of slot s =====================
+    const int s = warp - 2;
     int stage = 0;
     uint32_t wphase = 0;
-    int ring[2] = {0, 0};
-    uint32_t rphase[2] = {0, 0};
-    int kcount[2] = {0, 0};  // plane iterations issued so far per slot (pairs up with the epilogue's counter)
+    int ring = 0;
+    uint32_t rphase = 0;
+    int kcount = 0;  // plane iterations issued so far for this slot (pairs up with the epilogue's counter)
     for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
-      const ZmItem it0 = zm_item(p, 2 * pair), it1 = zm_item(p, 2 * pair + 1);
-      const int niter = max(it0.niter, it1.niter);
+      const ZmItem it = zm_item(p, 2 * pair + s), ot = zm_item(p, 2 * pair + 1 - s);
+      const int niter = max(it.niter, ot.niter);
       for (int i = 0; i < niter; ++i) {
-        uint32_t a_base[2] = {0, 0};
-        int jlo[2], jhi[2], blk0[2];
-        bool act[2];
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const ZmItem& it = s ? it1 : it0;
-          act[s] = i < it.niter;
-          jlo[s] = 0; jhi[s] = -1; blk0[s] = 0;
-          if (!act[s]) continue;
+        const bool act = i < it.niter;
+        // the needed accumulator blocks, split into (at most two) runs that do not wrap around the 4-block ring of TMEM columns
+        uint32_t b_off0 = 0, b_off1 = 0, d0 = 0, d1 = 0, idesc0 = 0, idesc1 = 0;
+        bool run1 = false;
+        if (act) {
           const int pl = it.p_lo + i;
-          zm_jrange(pl, it.z0, it.z1, jlo[s], jhi[s]);
-          blk0[s] = (pl - 1 + jlo[s] - it.z0) & 3;  // TMEM block of the first needed output plane
-          const int k = kcount[s];
+          int jlo, jhi;
+          zm_jrange(pl, it.z0, it.z1, jlo, jhi);
+          const int nb = jhi - jlo + 1, blk = (pl - 1 + jlo - it.z0) & 3;  // TMEM block of the first needed output plane
+          const int len0 = min(nb, 4 - blk);
+          b_off0 = (uint32_t)jlo * ZM_WBLOCK;
+          d0 = tmem_base + (uint32_t)(s * 256 + blk * 64);
+          idesc0 = p.idesc[len0 - 1];
+          run1 = len0 < nb;  // the rest of the window starts again at block 0
+          b_off1 = (uint32_t)(jlo + len0) * ZM_WBLOCK;
+          d1 = tmem_base + (uint32_t)(s * 256);
+          idesc1 = p.idesc[run1 ? nb - len0 - 1 : 0];
+          const int k = kcount;
           // the block written for the first time in this iteration was drained two iterations ago; a new item needs
           // every block of the slot drained
           if (k >= 2) mbar_wait(smem_u32(&acc_free[s * 2 + (k & 1)]), (uint32_t)(((k - 2) >> 1) & 1));
           if (i == 0 && k >= 1) mbar_wait(smem_u32(&acc_free[s * 2 + ((k - 1) & 1)]), (uint32_t)(((k - 1) >> 1) & 1));
-          mbar_wait(smem_u32(&pl_full[s * ZM_RING + ring[s]]), rphase[s]);
-          a_base[s] = smem_u32(planes + (size_t)(s * ZM_RING + ring[s]) * ZM_PLANE_STRIDE);
         }
-        tc_fence_after();
-        for (int kb = 0; kb < 9; ++kb) {
-          mbar_wait(smem_u32(&w_full[stage]), wphase);
-          tc_fence_after();
-          {  // warp-uniform issue code; the single issuing lane is elected inside umma_bf16 / umma_commit
-            const uint32_t w_addr = smem_u32(wst + (size_t)stage * ZM_WSTAGE);
-            const uint32_t a_off = (uint32_t)((kb / 3) * (ZM_TX + 2) + (kb % 3)) * 128;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-              if (!act[s]) continue;
-              const uint64_t adesc = make_sw128_desc_sbo(a_base[s] + a_off, (ZM_TX + 2) * 128);
-              // split the needed blocks into runs that do not wrap around the 4-block ring of TMEM columns
-              int j = jlo[s], blk = blk0[s];
-              while (j <= jhi[s]) {
-                const int len = min(jhi[s] - j + 1, 4 - blk);
-                const uint64_t bdesc = make_sw128_desc(w_addr + (uint32_t)j * ZM_WBLOCK);
-                const uint32_t d_tmem = tmem_base + (uint32_t)(s * 256 + blk * 64);
-                const uint32_t idesc = p.idesc[len - 1];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);
-                j += len;
-                blk = (blk + len) & 3;
-              }
-            }
-            umma_commit(smem_u32(&w_empty[stage]));
+        for (int kc = 0; kc < p.KC; ++kc) {
+          uint32_t a_base = 0;
+          if (act) {
+            mbar_wait(smem_u32(&pl_full[s * ZM_RING + ring]), rphase);
+            a_base = smem_u32(planes + (size_t)(s * ZM_RING + ring) * ZM_PLANE_STRIDE);
           }
-          if (++stage == ZM_WSTAGES) { stage = 0; wphase ^= 1; }
-        }
+          tc_fence_after();
+          for (int kb = 0; kb < 9; ++kb) {
+            mbar_wait(smem_u32(&w_full[stage]), wphase);
+            tc_fence_after();
+            if (act) {  // warp-uniform issue code; the single issuing lane is elected inside umma_bf16 / umma_commit
+              const uint32_t w_addr = smem_u32(wst + (size_t)stage * ZM_WSTAGE);
+              const uint64_t adesc = make_sw128_desc_sbo(a_base + (uint32_t)((kb / 3) * (ZM_TX + 2) + (kb % 3)) * 128, (ZM_TX + 2) * 128);
+              {
+                const uint64_t bdesc = make_sw128_desc(w_addr + b_off0);
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (!act[s]) continue;
-          umma_commit(smem_u32(&pl_empty[s * ZM_RING + ring[s]]));
-          umma_commit(smem_u32(&acc_full[s * 2 + (kcount[s] & 1)]));
-          if (++ring[s] == ZM_RING) { ring[s] = 0; rphase[s] ^= 1; }
-          ++kcount[s];
+                for (int k = 0; k < 4; ++k) umma_bf16(d0, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc0, 1u);
+              }
+              if (run1) {
+                const uint64_t bdesc = make_sw128_desc(w_addr + b_off1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(d1, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, 1u);
+              }
+              umma_commit(smem_u32(&w_empty[stage]));
+            } else {
+              // idle slot (odd item count / shorter z-segment): stay in lockstep with the weight ring
+              if (lane == 0) mbar_arrive(smem_u32(&w_empty[stage]));
+              __syncwarp();
+            }
+            if (++stage == ZM_WSTAGES) { stage = 0; wphase ^= 1; }
+          }
+          if (act) {
+            umma_commit(smem_u32(&pl_empty[s * ZM_RING + ring]));
+            if (++ring == ZM_RING) { ring = 0; rphase ^= 1; }
+          }
+        }
+        if (act) {
+          umma_commit(smem_u32(&acc_full[s * 2 + (kcount & 1)]));
+          ++kcount;
         }
       }
     }
   } else {
-    // ===================== epilogue (warps 3..6) =====================
+    // ===================== epilogue (warps 4..7) =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;  // GEMM row = y * 8 + x inside the tile
-    const int et = threadIdx.x - 96;      // 0..127
+    const int et = threadIdx.x - 128;     // 0..127
     const int cp = et & 31, rq = et >> 5;
+    const int nblk = 2 * (int)gridDim.x;
     int kcount[2] = {0, 0};
     float st_s[2][2], st_q[2][2];
-    int st_n[2] = {-1, -1}, st_first[2] = {-1, -1};
+    int st_key[2] = {-1, -1};  // (volume, output-channel group) the running sums of a slot belong to
     st_s[0][0] = st_s[0][1] = st_s[1][0] = st_s[1][1] = 0.f;
     st_q[0][0] = st_q[0][1] = st_q[1][0] = st_q[1][1] = 0.f;
-    auto flush_stats = [&](int s, int nvol) {
+    if (p.stats) {
+      // every (volume, channel) entry of this CTA's two partial rows must be defined: zero them, then overwrite what we produce
+      for (int nv = 0; nv < p.n; ++nv)
+        for (int s = 0; s < 2; ++s) {
+          float* dst = p.stats + ((size_t)nv * nblk + blockIdx.x * 2 + s) * p.c_out * 2;
+          for (int idx = et; idx < p.c_out * 2; idx += 128) dst[idx] = 0.f;
+        }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    auto flush_stats = [&](int s, int key) {
+      const int nvol = key / p.NH, nh = key - nvol * p.NH;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         s_red[(rq * 64 + cp * 2 + h) * 2] = st_s[s][h];
@@ -254,7 +294,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
         st_s[s][h] = st_q[s][h] = 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      float* dst = p.stats + ((size_t)nvol * (2 * gridDim.x) + blockIdx.x * 2 + s) * 64 * 2;
+      float* dst = p.stats + (((size_t)nvol * nblk + blockIdx.x * 2 + s) * p.c_out + nh * 64) * 2;
       if (et < 64) {
         float a = 0.f, b = 0.f;
 #pragma unroll
@@ -273,9 +313,9 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
         for (int s = 0; s < 2; ++s) {
           const ZmItem& it = s ? it1 : it0;
           if (!it.valid) continue;
-          if (st_n[s] >= 0 && it.b != st_n[s]) flush_stats(s, st_n[s]);
-          if (st_first[s] < 0) st_first[s] = it.b;
-          st_n[s] = it.b;
+          const int key = it.b * p.NH + it.nh;
+          if (st_key[s] >= 0 && key != st_key[s]) flush_stats(s, st_key[s]);
+          st_key[s] = key;
         }
       }
       for (int i = 0; i < niter; ++i) {
@@ -285,6 +325,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
           if (i >= it.niter) continue;
           const int pl = it.p_lo + i;
           const int k = kcount[s];
+          const float* bias = s_bias + it.nh * 64;
           mbar_wait(smem_u32(&acc_full[s * 2 + (k & 1)]), (uint32_t)((k >> 1) & 1));
           tc_fence_after();
           // outputs whose last contributing input plane is pl:  z = pl-1, and z = pl at the top face of the volume
@@ -304,8 +345,8 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
               uint32_t packed[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * j]) + s_bias[c32 * 32 + 2 * j],
-                                                          __uint_as_float(r[2 * j + 1]) + s_bias[c32 * 32 + 2 * j + 1]);
+                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * j]) + bias[c32 * 32 + 2 * j],
+                                                          __uint_as_float(r[2 * j + 1]) + bias[c32 * 32 + 2 * j + 1]);
                 packed[j] = *reinterpret_cast<uint32_t*>(&h);
               }
               uint8_t* rowp = out_stage + (size_t)row * 128;
@@ -318,7 +359,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
             fence_proxy_async();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (et == 0) {
-              tma_store_5d(&p.out_map, smem_u32(out_stage), 0, it.x0, it.y0, z, it.b);
+              tma_store_5d(&p.out_map, smem_u32(out_stage), it.nh * 64, it.x0, it.y0, z, it.b);
               bulk_commit();
             }
             if (p.stats) {
@@ -342,14 +383,8 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
     }
     if (p.stats) {
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        if (st_n[s] >= 0) flush_stats(s, st_n[s]);
-        for (int nv = 0; nv < p.n; ++nv) {
-          if (st_first[s] >= 0 && nv >= st_first[s] && nv <= st_n[s]) continue;
-          float* dst = p.stats + ((size_t)nv * (2 * gridDim.x) + blockIdx.x * 2 + s) * 64 * 2;
-          if (et < 128) dst[et] = 0.f;
-        }
-      }
+      for (int s = 0; s < 2; ++s)
+        if (st_key[s] >= 0) flush_stats(s, st_key[s]);
     }
     if (et == 0) bulk_wait0();
   }
@@ -362,15 +397,17 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
   }
 }
 
-// (64, 64, 3,3,3) fp32 -> [kb = kh*3+kw][j][c_out][c_in] bf16 with 16-byte chunks XOR-swizzled by (row & 7)
-__global__ void conv_pack_zm_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ packed) {
-  const int total = 9 * 3 * 64 * 64;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int e = i % 64, r = (i / 64) % 64, j = (i / 4096) % 3, kb = i / (4096 * 3);
+// (c_out, c_in, 3,3,3) fp32 -> [nh][kc][kb = kh*3+kw][j][64 c_out][64 c_in] bf16 with 16-byte chunks XOR-swizzled by (row & 7)
+__global__ void conv_pack_zm_kernel(const float* __restrict__ w, int c_in, int c_out, __nv_bfloat16* __restrict__ packed) {
+  const int KC = c_in / 64;
+  const int64_t total = (int64_t)27 * c_in * c_out;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(i % 64), r = (int)((i / 64) % 64), j = (int)((i / 4096) % 3), kb = (int)((i / 12288) % 9);
+    const int kc = (int)((i / (12288 * 9)) % KC), nh = (int)(i / ((int64_t)12288 * 9 * KC));
     const int kd = 2 - j, kh = kb / 3, kw = kb % 3;
-    const float v = w[((int64_t)r * 64 + e) * 27 + kd * 9 + kh * 3 + kw];
+    const float v = w[((int64_t)(nh * 64 + r) * c_in + kc * 64 + e) * 27 + kd * 9 + kh * 3 + kw];
     const int chunk = (e >> 3) ^ (r & 7);
-    packed[((int64_t)(kb * 3 + j) * 64 + r) * 64 + chunk * 8 + (e & 7)] = __float2bfloat16_rn(v);
+    packed[(i / 64) * 64 + chunk * 8 + (e & 7)] = __float2bfloat16_rn(v);
   }
 }
 
@@ -382,27 +419,38 @@ struct ZmPlan {
 
 bool conv_zm_supported(const diqt_conv_desc* d) {
   if (d->mode != DIQT_CONV_K3 || d->dtype != DIQT_BF16) return false;
-  if (d->c_in != 64 || d->c_out != 64) return false;
+  if (d->c_in % 64 != 0 || d->c_out % 64 != 0 || d->c_out > ZM_MAX_COUT) return false;
   if (d->ld_in % 8 != 0 || d->ld_out % 8 != 0) return false;
   if (d->d2 % ZM_TX != 0 || d->d1 % ZM_TY != 0 || d->d0 < 2) return false;
   return true;
 }
 
-// enough plane-tiles to keep ~every SM busy with two z-columns; below that the per-tap kernel wins
-bool conv_zm_profitable(const diqt_conv_desc* d) {
-  const int64_t plane_tiles = (int64_t)d->n * (d->d2 / ZM_TX) * (d->d1 / ZM_TY) * d->d0;
-  return plane_tiles >= 1024;
-}
+// The per-tap kernel re-reads the input 27 times from L2; the z-march kernel wins whenever its tile shape fits.
+bool conv_zm_profitable(const diqt_conv_desc* d) { return conv_zm_supported(d); }
 
-size_t conv_zm_packed_bytes() { return (size_t)27 * 64 * 64 * 2; }
+size_t conv_zm_packed_bytes(const diqt_conv_desc* d) { return (size_t)27 * d->c_in * d->c_out * 2; }
 
-int conv_zm_pack(const float* w, void* packed, cudaStream_t st) {
-  conv_pack_zm_kernel<<<108, 256, 0, st>>>(w, (__nv_bfloat16*)packed);
+int conv_zm_pack(const diqt_conv_desc* d, const float* w, void* packed, cudaStream_t st) {
+  conv_pack_zm_kernel<<<256, 256, 0, st>>>(w, d->c_in, d->c_out, (__nv_bfloat16*)packed);
   return check_launch("conv_pack_zm");
 }
 
+// tensor-pipe cycles (per K=16 step) one z-segment [z0, z1) of a column costs: N=64 and N=128 take 64 cycles, N=192 takes 96,
+// and a three-block window that wraps around the 4-block TMEM ring is issued as N=128 + N=64 (profiles/umma_probe_r1.log)
+static int zm_segment_cycles(int z0, int z1, int D) {
+  const int p_lo = std::max(z0 - 1, 0), niter = std::min(z1, D - 1) - p_lo + 1;
+  int cyc = 0;
+  for (int i = 0; i < niter; ++i) {
+    const int pl = p_lo + i;
+    const int jlo = std::max(0, z0 - (pl - 1)), jhi = std::min(2, (z1 - 1) - (pl - 1));
+    const int nb = jhi - jlo + 1, blk = (pl - 1 + jlo - z0) & 3;
+    cyc += nb <= 2 ? (blk + nb > 4 ? 128 : 64) : (blk + nb > 4 ? 128 : 96);
+  }
+  return cyc;
+}
+
 int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void* packed, const float* bias, ZmPlan** out_plan) {
-  DIQT_REQUIRE(conv_zm_supported(d), "conv(zm): needs 3x3x3 bf16 64->64 with d2 %% 8 == 0 and d1 %% 16 == 0");
+  DIQT_REQUIRE(conv_zm_supported(d), "conv(zm): needs 3x3x3 bf16, c_in %% 64 == 0, c_out %% 64 == 0 (<= %d), d2 %% 8 == 0 and d1 %% 16 == 0", ZM_MAX_COUT);
   ZmPlan* plan = new ZmPlan();
   ZmParams& p = plan->p;
   memset(&p, 0, sizeof(p));
@@ -410,39 +458,46 @@ int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
   p.bias = bias;
   p.stats = nullptr;
   p.n = d->n; p.D = d->d0; p.H = d->d1; p.W = d->d2;
+  p.KC = d->c_in / 64; p.NH = d->c_out / 64; p.c_out = d->c_out;
   p.tiles_x = d->d2 / ZM_TX;
   p.tiles_y = d->d1 / ZM_TY;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // pick the z-segment length: minimise  rounds * (L + boundary cost)  over the CTAs' lockstep slot pairs
+  // pick the z-segment length: minimise  rounds x (tensor cycles of the slot pair + fixed per-CTA cost); ties go to the longer
+  // segment (fewer halo planes streamed from L2)
   const int64_t cols = (int64_t)d->n * p.tiles_x * p.tiles_y;
   double best = 1e30;
   int bestL = d->d0;
-  for (int L = 2; L <= d->d0; ++L) {
+  for (int L = d->d0; L >= 1; --L) {
     const int nseg = (d->d0 + L - 1) / L;
-    const int64_t pairs = (cols * nseg + 1) / 2;
+    const int64_t ipn = cols * nseg, ipn_pad = ipn + (ipn & 1);
+    const int64_t pairs = (int64_t)p.NH * ipn_pad / 2;
     const int64_t rounds = (pairs + sms - 1) / sms;
-    const double cost = (double)rounds * (L + 1.34);
-    if (cost < best - 1e-9) { best = cost; bestL = L; }
+    int worst = 0;
+    for (int sgi = 0; sgi < nseg; ++sgi) worst = std::max(worst, zm_segment_cycles(sgi * L, std::min(d->d0, sgi * L + L), d->d0));
+    const double cost = (double)rounds * (2.0 * worst * 36.0 * p.KC + 6000.0);
+    if (cost < best * 0.99) { best = cost; bestL = L; }
   }
   p.L = bestL;
   p.nseg = (d->d0 + p.L - 1) / p.L;
-  p.items = (int)(cols * p.nseg);
-  p.pairs = (p.items + 1) / 2;
+  p.ipn = (int)(cols * p.nseg);
+  p.ipn_pad = p.ipn + (p.ipn & 1);
+  p.items = p.NH * p.ipn_pad;
+  p.pairs = p.items / 2;
   for (int i = 0; i < 3; ++i) p.idesc[i] = make_idesc_bf16(128, 64 * (i + 1));
   const int64_t ld = d->ld_in, lo = d->ld_out;
-  int rc = encode_volume_map(&p.in_map, in, 64, d->d2, d->d1, d->d0, d->n, ld, (int64_t)d->d2 * ld, (int64_t)d->d1 * d->d2 * ld,
+  int rc = encode_volume_map(&p.in_map, in, d->c_in, d->d2, d->d1, d->d0, d->n, ld, (int64_t)d->d2 * ld, (int64_t)d->d1 * d->d2 * ld,
                              (int64_t)d->d0 * d->d1 * d->d2 * ld, ZM_TX + 2, ZM_TY + 2, 1, 1);
   if (rc == DIQT_OK)
-    rc = encode_volume_map(&p.out_map, out, 64, d->d2, d->d1, d->d0, d->n, lo, (int64_t)d->d2 * lo, (int64_t)d->d1 * d->d2 * lo,
+    rc = encode_volume_map(&p.out_map, out, d->c_out, d->d2, d->d1, d->d0, d->n, lo, (int64_t)d->d2 * lo, (int64_t)d->d1 * d->d2 * lo,
                            (int64_t)d->d0 * d->d1 * d->d2 * lo, ZM_TX, ZM_TY, 1, 1);
   if (rc != DIQT_OK) {
     delete plan;
     return rc;
   }
   plan->grid = p.pairs < sms ? p.pairs : sms;
-  plan->smem = (size_t)2 * ZM_RING * ZM_PLANE_STRIDE + (size_t)ZM_WSTAGES * ZM_WSTAGE + ZM_OUT_BYTES + 64 * 4 + 4 * 64 * 2 * 4 + 512 + 1024;
+  plan->smem = (size_t)2 * ZM_RING * ZM_PLANE_STRIDE + (size_t)ZM_WSTAGES * ZM_WSTAGE + ZM_OUT_BYTES + ZM_MAX_COUT * 4 + 4 * 64 * 2 * 4 + 512 + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     DIQT_CUDA(cudaFuncSetAttribute(conv_zm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -453,7 +508,7 @@ int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
 }
 
 int conv_zm_run(const ZmPlan* plan, cudaStream_t st) {
-  conv_zm_kernel<<<plan->grid, ZM_THREADS, plan->smem, st>>>(plan->p);
+  launch_pdl(conv_zm_kernel, plan->grid, ZM_THREADS, plan->smem, st, plan->p);
   return check_launch("conv_zm");
 }
 

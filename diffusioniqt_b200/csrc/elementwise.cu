@@ -57,6 +57,8 @@ __global__ void channel_stats_kernel(const T* __restrict__ x, int64_t voxels, in
   const int blk = blockIdx.x, n = blockIdx.y, nblk = gridDim.x;
   const int64_t v0 = (int64_t)blk * vpb;
   const int64_t v1 = min(voxels, v0 + vpb);
+  pdl_launch_dependents();
+  pdl_wait();
   const T* base = x + col * VEC;
   float s[VEC], q[VEC];
 #pragma unroll
@@ -92,6 +94,8 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblk, 
                                    const float* __restrict__ film, int film_ld, const int32_t* __restrict__ film_row,
                                    int film_row_stride_n, float* __restrict__ a_out, float* __restrict__ b_out) {
   extern __shared__ double sm[];  // acc[parts][c][2], tot[c][2], gstat[groups][2]
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.x;
   const int parts = max(1, (int)blockDim.x / c);
   double* acc = sm;
@@ -175,6 +179,8 @@ __global__ void affine_mish_kernel(const T* __restrict__ x, int ld_x, T* __restr
   const int n = blockIdx.y;
   const int64_t v0 = (int64_t)blockIdx.x * vpb;
   const int64_t v1 = min(voxels, v0 + vpb);
+  pdl_launch_dependents();
+  pdl_wait();
   float av[VEC], bv[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
@@ -208,6 +214,8 @@ __global__ void affine_mish_kernel(const T* __restrict__ x, int ld_x, T* __restr
 __global__ void se_gate_kernel(const float* __restrict__ partial, int nblk, int64_t voxels, int c, int hidden,
                                const float* __restrict__ w1, const float* __restrict__ w2, float* __restrict__ gate) {
   extern __shared__ double sd[];  // acc[parts][c] doubles, then mean[c] + hid[hidden] floats
+  pdl_launch_dependents();
+  pdl_wait();
   const int n = blockIdx.x;
   const int parts = max(1, (int)blockDim.x / c);
   double* acc = sd;
@@ -260,6 +268,8 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
   const int blk = blockIdx.x, n = blockIdx.y, nblk = gridDim.x;
   const int64_t v0 = (int64_t)blk * vpb;
   const int64_t v1 = min(voxels, v0 + vpb);
+  pdl_launch_dependents();
+  pdl_wait();
   float g[VEC], s[VEC], q[VEC];
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
@@ -321,6 +331,8 @@ template <typename T>
 __global__ void scale_copy_kernel(const T* __restrict__ src, int ld_src, T* __restrict__ dst, int ld_dst, int64_t rows,
                                   int nvec, float scale) {
   const int64_t total = rows * nvec;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / nvec;
     const int col = (int)(i - r * nvec);
@@ -350,10 +362,10 @@ extern "C" int diqt_channel_stats(const void* x, int dtype, int n, int64_t voxel
   size_t sh = (size_t)2 * m.lanes * c * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)
-    channel_stats_kernel<__nv_bfloat16><<<grid, m.threads, sh, st>>>((const __nv_bfloat16*)x, voxels, c, ld, m.nvec, m.lanes,
+    launch_pdl(channel_stats_kernel<__nv_bfloat16>, grid, m.threads, sh, st, (const __nv_bfloat16*)x, voxels, c, ld, m.nvec, m.lanes,
                                                                     vox_per_block(voxels, nblk), partial, sg);
   else
-    channel_stats_kernel<float><<<grid, m.threads, sh, st>>>((const float*)x, voxels, c, ld, m.nvec, m.lanes,
+    launch_pdl(channel_stats_kernel<float>, grid, m.threads, sh, st, (const float*)x, voxels, c, ld, m.nvec, m.lanes,
                                                             vox_per_block(voxels, nblk), partial, sg);
   return check_launch("channel_stats");
 }
@@ -371,7 +383,7 @@ extern "C" int diqt_gn_finalize(const float* partial, int n, int nblk, int64_t v
     DIQT_CUDA(cudaFuncSetAttribute(gn_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set = true;
   }
-  gn_finalize_kernel<<<n, threads, sh, (cudaStream_t)stream>>>(partial, nblk, voxels, c, groups, eps, gamma, beta, film,
+  launch_pdl(gn_finalize_kernel, n, threads, sh, (cudaStream_t)stream, partial, nblk, voxels, c, groups, eps, gamma, beta, film,
                                                                film_ld, film_row, film_row_stride_n, a, b);
   return check_launch("gn_finalize");
 }
@@ -387,11 +399,11 @@ extern "C" int diqt_affine_mish(const void* x, int ld_x, void* y, int ld_y, int 
   dim3 grid(nblk, n);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)
-    affine_mish_kernel<__nv_bfloat16, true><<<grid, m.threads, 0, st>>>((const __nv_bfloat16*)x, ld_x, (__nv_bfloat16*)y, ld_y,
+    launch_pdl(affine_mish_kernel<__nv_bfloat16, true>, grid, m.threads, 0, st, (const __nv_bfloat16*)x, ld_x, (__nv_bfloat16*)y, ld_y,
                                                                        voxels, c, m.nvec, m.lanes,
                                                                        vox_per_block(voxels, nblk), a, b, sg);
   else
-    affine_mish_kernel<float, false><<<grid, m.threads, 0, st>>>((const float*)x, ld_x, (float*)y, ld_y, voxels, c, m.nvec,
+    launch_pdl(affine_mish_kernel<float, false>, grid, m.threads, 0, st, (const float*)x, ld_x, (float*)y, ld_y, voxels, c, m.nvec,
                                                                 m.lanes, vox_per_block(voxels, nblk), a, b, sg);
   return check_launch("affine_mish");
 }
@@ -403,7 +415,7 @@ extern "C" int diqt_se_gate(const float* partial, int n, int nblk, int64_t voxel
   const int threads = 1024;
   const int parts = threads / c > 0 ? threads / c : 1;
   size_t sh = (size_t)parts * c * sizeof(double) + (size_t)(c + hidden) * sizeof(float);
-  se_gate_kernel<<<n, threads, sh, (cudaStream_t)stream>>>(partial, nblk, voxels, c, hidden, w1, w2, gate);
+  launch_pdl(se_gate_kernel, n, threads, sh, (cudaStream_t)stream, partial, nblk, voxels, c, hidden, w1, w2, gate);
   return check_launch("se_gate");
 }
 
@@ -421,11 +433,11 @@ extern "C" int diqt_scale_residual(const void* h, int ld_h, const void* res, int
   size_t sh = partial ? (size_t)2 * m.lanes * c * sizeof(float) : 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)
-    scale_residual_kernel<__nv_bfloat16><<<grid, m.threads, sh, st>>>(
+    launch_pdl(scale_residual_kernel<__nv_bfloat16>, grid, m.threads, sh, st, 
         (const __nv_bfloat16*)h, ld_h, (const __nv_bfloat16*)res, ld_res, (__nv_bfloat16*)out, ld_out, voxels, c, m.nvec,
         m.lanes, vox_per_block(voxels, nblk), gate, partial, sg);
   else
-    scale_residual_kernel<float><<<grid, m.threads, sh, st>>>((const float*)h, ld_h, (const float*)res, ld_res, (float*)out,
+    launch_pdl(scale_residual_kernel<float>, grid, m.threads, sh, st, (const float*)h, ld_h, (const float*)res, ld_res, (float*)out,
                                                              ld_out, voxels, c, m.nvec, m.lanes,
                                                              vox_per_block(voxels, nblk), gate, partial, sg);
   return check_launch("scale_residual");
@@ -441,9 +453,9 @@ extern "C" int diqt_scale_copy(const void* src, int ld_src, void* dst, int ld_ds
   if (blocks > 148 * 16) blocks = 148 * 16;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)
-    scale_copy_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)src, ld_src, (__nv_bfloat16*)dst, ld_dst,
+    launch_pdl(scale_copy_kernel<__nv_bfloat16>, (unsigned)blocks, 256, 0, st, (const __nv_bfloat16*)src, ld_src, (__nv_bfloat16*)dst, ld_dst,
                                                                      rows, nvec, scale);
   else
-    scale_copy_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)src, ld_src, (float*)dst, ld_dst, rows, nvec, scale);
+    launch_pdl(scale_copy_kernel<float>, (unsigned)blocks, 256, 0, st, (const float*)src, ld_src, (float*)dst, ld_dst, rows, nvec, scale);
   return check_launch("scale_copy");
 }

@@ -6,6 +6,7 @@
 // LearnedSinusoidalPosEmb + to_time_hiddens + to_time_cond + ResnetBlock.time_mlp
 // (:518-533, :1305-1316, :586-589, :603-605).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -13,6 +14,14 @@ namespace diqt {
 
 static thread_local char g_err[512] = "";
 std::atomic<uint64_t> g_launches{0};
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("DIQT_DISABLE_PDL");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -93,9 +102,11 @@ init_conv_x4_kernel(InitPlanes planes, int c_in, const float* __restrict__ w, co
                     int ld_out, int n, int d0, int d1, int d2, int c_out, SubGeom sg) {
   extern __shared__ float sw[];
   const int wcount = 27 * c_in * c_out;
+  pdl_launch_dependents();
   for (int i = threadIdx.x; i < wcount; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < c_out; i += blockDim.x) sw[wcount + i] = bias[i];
   __syncthreads();
+  pdl_wait();
   const int xq = d2 / 4;
   const int64_t total = (int64_t)n * d0 * d1 * xq;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,12 +200,59 @@ __device__ __forceinline__ void ddpm_point(const StepConsts& s, float pred, floa
   x0 = xs;
 }
 
+// ---- Elucidated (Karras et al.) sampler step, elucidated_imagen.py:329-358 (preconditioned network) and :468-519 -----
+// table row per U-Net forward (16 floats): 0 S_noise, 1 sqrt(sigma_hat^2 - sigma^2), 2 c_in(sigma of this forward), 3 c_skip,
+// 4 c_out, 5 divisor sigma (sigma_hat for the Euler pass, sigma_next for the Heun pass), 6 (sigma_next - sigma_hat),
+// 7 0.5 * (sigma_next - sigma_hat), 8 c_in(sigma_next), 9 clamp lo, 10 clamp hi
+constexpr int kEdmRow = 16;
+struct EdmConsts {
+  float s_noise, noise_k, c_in, c_skip, c_out, sigma, dt, half_dt, c_in_next, lo, hi;
+};
+__device__ __forceinline__ EdmConsts load_edm(const float* __restrict__ table, const int32_t* __restrict__ step) {
+  const float* r = table + (int64_t)(step ? *step : 0) * kEdmRow;
+  EdmConsts e;
+  e.s_noise = r[0]; e.noise_k = r[1]; e.c_in = r[2]; e.c_skip = r[3]; e.c_out = r[4]; e.sigma = r[5]; e.dt = r[6];
+  e.half_dt = r[7]; e.c_in_next = r[8]; e.lo = r[9]; e.hi = r[10];
+  return e;
+}
+// model_output = clamp(c_skip * x + c_out * net)   (:352-358; products and sum rounded separately like the reference's tensor ops)
+__device__ __forceinline__ float edm_denoised(const EdmConsts& e, float x, float net) {
+  const float out = __fadd_rn(__fmul_rn(e.c_skip, x), __fmul_rn(e.c_out, net));
+  return fminf(fmaxf(out, e.lo), e.hi);
+}
+// Euler pass (:488-498): x_hat -> (d = (x_hat - D(x_hat)) / sigma_hat, x_euler = x_hat + (sigma_next - sigma_hat) d)
+__device__ __forceinline__ void edm_euler_point(const EdmConsts& e, float net, float x_hat, float& d, float& x_euler, float& x0) {
+  x0 = edm_denoised(e, x_hat, net);
+  d = __fdiv_rn(__fsub_rn(x_hat, x0), e.sigma);
+  x_euler = __fadd_rn(x_hat, __fmul_rn(e.dt, d));
+}
+// Heun pass (:502-516): x = x_hat + 0.5 (sigma_next - sigma_hat) (d + d'),  d' = (x_euler - D(x_euler)) / sigma_next
+__device__ __forceinline__ void edm_heun_point(const EdmConsts& e, float net, float x_hat, float x_euler, float d, float& x_new, float& x0) {
+  x0 = edm_denoised(e, x_euler, net);
+  const float dp = __fdiv_rn(__fsub_rn(x_euler, x0), e.sigma);
+  x_new = __fadd_rn(x_hat, __fmul_rn(e.half_dt, __fadd_rn(d, dp)));
+}
+
+// x_hat = x + sqrt(sigma_hat^2 - sigma^2) * (S_noise * eps);  x_in = c_in(sigma_hat) * x_hat     (:476-481, :349)
+__global__ void edm_prepare_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ table,
+                                   const int32_t* __restrict__ step, float* __restrict__ x_hat, float* __restrict__ x_in, int64_t count) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const EdmConsts e = load_edm(table, step);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const float xh = __fadd_rn(x[i], __fmul_rn(e.noise_k, __fmul_rn(e.s_noise, eps[i])));
+    x_hat[i] = xh;
+    x_in[i] = __fmul_rn(e.c_in, xh);
+  }
+}
+
 template <typename T, int MAXCO>
 __global__ void final_conv_kernel(const T* __restrict__ x, int ld, int64_t voxels, int c, int c_out, int nvec,
                                   const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ pred,
                                   int step_mode, const float* __restrict__ sched, const int32_t* __restrict__ step,
                                   const float* __restrict__ x_t, const float* __restrict__ noise,
-                                  float* __restrict__ x_next, float* __restrict__ x0, int64_t total_rows, SubGeom sg) {
+                                  float* __restrict__ x_next, float* __restrict__ x0, float* __restrict__ aux_out,
+                                  int64_t total_rows, SubGeom sg) {
   constexpr int VEC = Vec<T>::N;
   // nvec (power of two <= 32) consecutive threads share one voxel row
   const int col = threadIdx.x % nvec;
@@ -204,8 +262,14 @@ __global__ void final_conv_kernel(const T* __restrict__ x, int ld, int64_t voxel
   for (int co = 0; co < MAXCO; ++co)
 #pragma unroll
     for (int i = 0; i < VEC; ++i) wv[co][i] = co < c_out ? w[co * c + col * VEC + i] : 0.f;
+  pdl_launch_dependents();
+  pdl_wait();
+  // step_mode: 0 store the prediction, 1 DDPM update, 2 Elucidated Euler pass, 3 Elucidated Heun pass.  In the Elucidated modes
+  // `noise` carries x_hat and `pred` the slope buffer d (written by 2, read by 3); aux_out receives the next network input.
   StepConsts sc;
-  if (step_mode) sc = load_step(sched, step);
+  EdmConsts ec;
+  if (step_mode == 1) sc = load_step(sched, step);
+  if (step_mode >= 2) ec = load_edm(sched, step);
   // block-uniform trip count so the full-mask shuffles below are always converged; UNR rows in flight per thread group
   constexpr int UNR = 4;
   for (int64_t base = (int64_t)blockIdx.x * rows_per_block * UNR; base < total_rows; base += (int64_t)gridDim.x * rows_per_block * UNR) {
@@ -250,9 +314,21 @@ __global__ void final_conv_kernel(const T* __restrict__ x, int ld, int64_t voxel
           const int64_t o = (b * c_out + co) * ovox + v;  // NCDHW fp32
           if (!step_mode) {
             pred[o] = p;
-          } else {
+          } else if (step_mode == 1) {
             float xn, xs;
             ddpm_point(sc, p, x_t[o], noise[o], xn, xs);
+            x_next[o] = xn;
+            x0[o] = xs;
+          } else if (step_mode == 2) {
+            float d, xe, xs;
+            edm_euler_point(ec, p, noise[o], d, xe, xs);
+            pred[o] = d;
+            x_next[o] = xe;
+            aux_out[o] = __fmul_rn(ec.c_in_next, xe);
+            x0[o] = xs;
+          } else {
+            float xn, xs;
+            edm_heun_point(ec, p, noise[o], x_t[o], pred[o], xn, xs);
             x_next[o] = xn;
             x0[o] = xs;
           }
@@ -266,6 +342,8 @@ __global__ void ddpm_update_kernel(const float* __restrict__ pred, const float* 
                                    const int32_t* __restrict__ step, const float* __restrict__ x_t,
                                    const float* __restrict__ noise, float* __restrict__ x_next, float* __restrict__ x0,
                                    int64_t count) {
+  pdl_launch_dependents();
+  pdl_wait();
   StepConsts sc = load_step(sched, step);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
     float xn, xs;
@@ -316,7 +394,11 @@ __global__ void linear_kernel(const float* __restrict__ x, int ldx, int k, const
   }
 }
 
-__global__ void advance_step_kernel(int32_t* step) { *step += 1; }
+__global__ void advance_step_kernel(int32_t* step) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *step += 1;
+}
 
 __global__ void clamp_kernel(float* __restrict__ x, int64_t count, float lo, float hi) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
@@ -362,11 +444,11 @@ extern "C" int diqt_init_conv(const float* const* planes, const int64_t* plane_s
     if (dtype == DIQT_BF16) {
       auto k = init_conv_x4_kernel<__nv_bfloat16, 32>;
       if (sh > 48 * 1024) DIQT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-      k<<<blocks4, threads, sh, st>>>(ip, c_in, w_packed, bias, (__nv_bfloat16*)out, ld_out, n, d0, d1, d2, c_out, sg);
+      launch_pdl(k, blocks4, threads, sh, st, ip, c_in, w_packed, bias, (__nv_bfloat16*)out, ld_out, n, d0, d1, d2, c_out, sg);
     } else {
       auto k = init_conv_x4_kernel<float, 32>;
       if (sh > 48 * 1024) DIQT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-      k<<<blocks4, threads, sh, st>>>(ip, c_in, w_packed, bias, (float*)out, ld_out, n, d0, d1, d2, c_out, sg);
+      launch_pdl(k, blocks4, threads, sh, st, ip, c_in, w_packed, bias, (float*)out, ld_out, n, d0, d1, d2, c_out, sg);
     }
     return check_launch("init_conv_x4");
   }
@@ -389,9 +471,9 @@ extern "C" int diqt_init_conv(const float* const* planes, const int64_t* plane_s
   return check_launch("init_conv");
 }
 
-extern "C" int diqt_final_conv(const void* x, int ld, int dtype, int n, int64_t voxels, int c, int c_out, const float* w,
-                               const float* bias, float* pred, int step_mode, const float* sched, const int32_t* step,
-                               const float* x_t, const float* noise, float* x_next, float* x0, int sub_f, int sub_h, void* stream) {
+static int final_conv_impl(const void* x, int ld, int dtype, int n, int64_t voxels, int c, int c_out, const float* w,
+                           const float* bias, float* pred, int step_mode, const float* sched, const int32_t* step,
+                           const float* x_t, const float* noise, float* x_next, float* x0, float* aux_out, int sub_f, int sub_h, void* stream) {
   const SubGeom sg{sub_f, sub_h};
   if (sub_f > 1) DIQT_REQUIRE(n == 1 && voxels == (int64_t)sub_f * sub_f * sub_f * sub_h * sub_h * sub_h, "final_conv: boundary mode runs over ONE merged volume");
   const int vec = dtype == DIQT_BF16 ? 8 : 4;
@@ -400,8 +482,10 @@ extern "C" int diqt_final_conv(const void* x, int ld, int dtype, int n, int64_t 
   DIQT_REQUIRE(c % vec == 0 && ld % vec == 0, "final_conv: c=%d not a multiple of %d", c, vec);
   const int nvec = c / vec;
   DIQT_REQUIRE(nvec <= 32 && (nvec & (nvec - 1)) == 0, "final_conv: c/%d=%d must be a power of two <= 32", vec, nvec);
+  DIQT_REQUIRE(step_mode >= 0 && step_mode <= 3, "final_conv: bad step_mode %d", step_mode);
   if (step_mode) DIQT_REQUIRE(sched && x_t && noise && x_next && x0, "final_conv: fused step needs sched/x_t/noise/x_next/x0");
-  else DIQT_REQUIRE(pred, "final_conv: pred is null");
+  if (step_mode != 1) DIQT_REQUIRE(pred, "final_conv: pred is null");
+  if (step_mode == 2) DIQT_REQUIRE(aux_out, "final_conv: the Euler pass needs the next-input buffer");
   const int64_t rows = (int64_t)n * voxels;
   const int threads = 256;
   const int64_t rpb = threads / nvec;
@@ -409,13 +493,69 @@ extern "C" int diqt_final_conv(const void* x, int ld, int dtype, int n, int64_t 
   if (blocks > 148 * 8) blocks = 148 * 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)
-    final_conv_kernel<__nv_bfloat16, 4><<<(unsigned)blocks, threads, 0, st>>>((const __nv_bfloat16*)x, ld, voxels, c, c_out, nvec, w,
-                                                                            bias, pred, step_mode, sched, step, x_t, noise,
-                                                                            x_next, x0, rows, sg);
+    launch_pdl(final_conv_kernel<__nv_bfloat16, 4>, (unsigned)blocks, threads, 0, st, (const __nv_bfloat16*)x, ld, voxels, c, c_out, nvec, w,
+               bias, pred, step_mode, sched, step, x_t, noise, x_next, x0, aux_out, rows, sg);
   else
-    final_conv_kernel<float, 4><<<(unsigned)blocks, threads, 0, st>>>((const float*)x, ld, voxels, c, c_out, nvec, w, bias, pred,
-                                                                    step_mode, sched, step, x_t, noise, x_next, x0, rows, sg);
+    launch_pdl(final_conv_kernel<float, 4>, (unsigned)blocks, threads, 0, st, (const float*)x, ld, voxels, c, c_out, nvec, w, bias, pred,
+               step_mode, sched, step, x_t, noise, x_next, x0, aux_out, rows, sg);
   return check_launch("final_conv");
+}
+
+extern "C" int diqt_final_conv(const void* x, int ld, int dtype, int n, int64_t voxels, int c, int c_out, const float* w,
+                               const float* bias, float* pred, int step_mode, const float* sched, const int32_t* step,
+                               const float* x_t, const float* noise, float* x_next, float* x0, int sub_f, int sub_h, void* stream) {
+  DIQT_REQUIRE(step_mode == 0 || step_mode == 1, "final_conv: step_mode %d (0 or 1; the Elucidated passes go through diqt_final_conv_edm)", step_mode);
+  return final_conv_impl(x, ld, dtype, n, voxels, c, c_out, w, bias, pred, step_mode, sched, step, x_t, noise, x_next, x0, nullptr, sub_f, sub_h, stream);
+}
+
+extern "C" int diqt_final_conv_edm(const void* x, int ld, int dtype, int n, int64_t voxels, int c, int c_out, const float* w,
+                                   const float* bias, int pass, const float* table, const int32_t* step, const float* x_hat,
+                                   float* slope, float* state, float* x0, float* next_input, int sub_f, int sub_h, void* stream) {
+  DIQT_REQUIRE(pass == 0 || pass == 1, "final_conv_edm: pass %d (0 Euler, 1 Heun)", pass);
+  return final_conv_impl(x, ld, dtype, n, voxels, c, c_out, w, bias, slope, 2 + pass, table, step, state, x_hat, state, x0, next_input, sub_f,
+                         sub_h, stream);
+}
+
+extern "C" int diqt_edm_prepare(const float* x, const float* eps, const float* table, const int32_t* step, float* x_hat, float* x_in,
+                                int64_t count, void* stream) {
+  DIQT_REQUIRE(x && eps && table && x_hat && x_in && count > 0, "edm_prepare: bad arguments");
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  launch_pdl(edm_prepare_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, x, eps, table, step, x_hat, x_in, count);
+  return check_launch("edm_prepare");
+}
+
+// the same two updates on an existing network output (dynamic thresholding runs its quantile in torch between them)
+__global__ void edm_update_kernel(const float* __restrict__ denoised, int pass, const float* __restrict__ table, const int32_t* __restrict__ step,
+                                  const float* __restrict__ x_hat, float* __restrict__ slope, float* __restrict__ state,
+                                  float* __restrict__ next_input, int64_t count) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const EdmConsts e = load_edm(table, step);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x0 = denoised[i];
+    if (pass == 0) {
+      const float d = __fdiv_rn(__fsub_rn(x_hat[i], x0), e.sigma);
+      const float xe = __fadd_rn(x_hat[i], __fmul_rn(e.dt, d));
+      slope[i] = d;
+      state[i] = xe;
+      next_input[i] = __fmul_rn(e.c_in_next, xe);
+    } else {
+      const float xe = state[i];
+      const float dp = __fdiv_rn(__fsub_rn(xe, x0), e.sigma);
+      state[i] = __fadd_rn(x_hat[i], __fmul_rn(e.half_dt, __fadd_rn(slope[i], dp)));
+    }
+  }
+}
+
+extern "C" int diqt_edm_update(const float* denoised, int pass, const float* table, const int32_t* step, const float* x_hat, float* slope,
+                               float* state, float* next_input, int64_t count, void* stream) {
+  DIQT_REQUIRE(denoised && table && x_hat && slope && state && count > 0 && (pass == 0 || pass == 1), "edm_update: bad arguments");
+  if (pass == 0) DIQT_REQUIRE(next_input, "edm_update: the Euler pass needs the next-input buffer");
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  launch_pdl(edm_update_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, denoised, pass, table, step, x_hat, slope, state, next_input, count);
+  return check_launch("edm_update");
 }
 
 extern "C" int diqt_ddpm_update(const float* pred, const float* sched, const int32_t* step, const float* x_t,
@@ -423,7 +563,7 @@ extern "C" int diqt_ddpm_update(const float* pred, const float* sched, const int
   DIQT_REQUIRE(pred && sched && x_t && noise && x_next, "ddpm_update: null pointer");
   int64_t blocks = (count + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  ddpm_update_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(pred, sched, step, x_t, noise, x_next, x0, count);
+  launch_pdl(ddpm_update_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, pred, sched, step, x_t, noise, x_next, x0, count);
   return check_launch("ddpm_update");
 }
 
@@ -445,7 +585,7 @@ extern "C" int diqt_linear(const float* x, int ldx, int rows, int k, const float
 
 extern "C" int diqt_advance_step(int32_t* step, void* stream) {
   DIQT_REQUIRE(step, "advance_step: null pointer");
-  advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+  launch_pdl(advance_step_kernel, 1, 1, 0, (cudaStream_t)stream, step);
   return check_launch("advance_step");
 }
 

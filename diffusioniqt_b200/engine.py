@@ -173,7 +173,7 @@ class UnetEngine:
         # ---- scratch for statistics / affine parameters
         self.nblk = [_nblk(n, v) for v in self.level_vox]
         self.nblk_stream = [_nblk(n, v, 592) for v in self.level_vox]
-        pmax = 160 * n * cmax * 2     # up to one partial per SM and volume
+        pmax = 304 * n * cmax * 2     # up to two partials (z-march slots) per SM and volume
         self.part = [torch.zeros(pmax, dtype=torch.float32, device=self.device) for _ in range(3)]
         self.aff_a = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
         self.aff_b = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)

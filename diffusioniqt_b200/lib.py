@@ -51,6 +51,9 @@ _SIGNATURES = {
     "diqt_init_conv": [C.POINTER(_vp), C.POINTER(_i64), _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "diqt_final_conv": [_vp, _i, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "diqt_ddpm_update": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "diqt_edm_prepare": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
+    "diqt_final_conv_edm": [_vp, _i, _i, _i, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "diqt_edm_update": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],
     "diqt_clamp": [_vp, _i64, _f, _f, _vp],
     "diqt_fourier_features": [_vp, _i, _vp, _i, _vp, _vp],
     "diqt_linear": [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp],

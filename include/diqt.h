@@ -166,6 +166,29 @@ int diqt_final_conv(const void* x, int ld, int dtype, int n, int64_t voxels, int
 int diqt_ddpm_update(const float* pred, const float* sched, const int32_t* step, const float* x_t,
                      const float* noise, float* x_next, float* x0, int64_t count, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Elucidated (Karras / Heun) sampler step: ElucidatedImagen.one_unet_sample and
+ * preconditioned_network_forward, elucidated_imagen.py:329-358, :468-519.
+ * table: DEVICE fp32 [forwards][16], one row per U-Net forward, read at row *step:
+ *   0 S_noise, 1 sqrt(sigma_hat^2 - sigma^2), 2 c_in(sigma of this forward), 3 c_skip, 4 c_out,
+ *   5 divisor sigma (sigma_hat in the Euler pass, sigma_next in the Heun pass),
+ *   6 (sigma_next - sigma_hat), 7 0.5*(sigma_next - sigma_hat), 8 c_in(sigma_next), 9 clamp lo, 10 clamp hi
+ * ------------------------------------------------------------------------------------------ */
+/* x_hat = x + table[1] * (table[0] * eps);  x_in = table[2] * x_hat     (:476-481 and the c_in scaling of :349) */
+int diqt_edm_prepare(const float* x, const float* eps, const float* table, const int32_t* step, float* x_hat, float* x_in,
+                     int64_t count, void* stream);
+/* final_conv (:1477) fused with one pass of the Heun step.  D(x) = clamp(c_skip*x + c_out*net, lo, hi).
+ *   pass 0 (Euler, :488-498): slope = (x_hat - D(x_hat)) / sigma_hat;  state = x_hat + (sigma_next - sigma_hat) * slope;
+ *                             next_input = c_in(sigma_next) * state;  x0 = D(x_hat)
+ *   pass 1 (Heun,  :502-516): d' = (state - D(state)) / sigma_next;   state = x_hat + 0.5 (sigma_next - sigma_hat) (slope + d');
+ *                             x0 = D(state_before) */
+int diqt_final_conv_edm(const void* x, int ld, int dtype, int n, int64_t voxels, int c, int c_out, const float* w,
+                        const float* bias, int pass, const float* table, const int32_t* step, const float* x_hat,
+                        float* slope, float* state, float* x0, float* next_input, int sub_f, int sub_h, void* stream);
+/* the same update given an already denoised tensor (dynamic thresholding takes its quantile in torch in between) */
+int diqt_edm_update(const float* denoised, int pass, const float* table, const int32_t* step, const float* x_hat, float* slope,
+                    float* state, float* next_input, int64_t count, void* stream);
+
 /* x = min(max(x, lo), hi): the clamp after the loop (:2154-2157) */
 int diqt_clamp(float* x, int64_t count, float lo, float hi, void* stream);
 

@@ -82,3 +82,29 @@ def sample_noise_count(case):
 def tap_digest(v):
     """Strided sub-sample of an activation (B, C, D, H, W): every 8th channel, every 2nd voxel."""
     return v[:1, ::8, ::2, ::2, ::2].contiguous()
+
+
+# Elucidated (Karras / Heun) sampler cases: reference `ElucidatedImagen.one_unet_sample` around the 3-D U-Net (adapter of
+# SURVEY.md Appendix C).  Fewer steps / milder sigma range than the defaults keep the CPU fixtures small; `hp` overrides
+# elucidated_imagen.py:96-106.
+ELUCIDATED_CASES = {
+    "edm_dim32_s8_n6": dict(unet=_unet(32), batch=1, size=8, weight_seed=71, input_seed=81, noise_seed=91,
+                            hp=dict(num_sample_steps=6), dynamic_threshold=False),
+    "edm_driver_dim64_s8_n4_b2": dict(unet=_unet(64), batch=2, size=8, weight_seed=72, input_seed=82, noise_seed=92,
+                                      hp=dict(num_sample_steps=4, sigma_max=20.0, S_churn=40.0), dynamic_threshold=False),
+    "edm_dynthr_dim32_s8_n5": dict(unet=_unet(32), batch=1, size=8, weight_seed=73, input_seed=83, noise_seed=93,
+                                   hp=dict(num_sample_steps=5), dynamic_threshold=True),
+    "edm_skip_dim32_s8_n8_skip3": dict(unet=_unet(32), batch=1, size=8, weight_seed=74, input_seed=84, noise_seed=94,
+                                       hp=dict(num_sample_steps=8), dynamic_threshold=False, skip_steps=3),
+}
+
+
+def elucidated_hparams(case):
+    hp = dict(num_sample_steps=32, sigma_min=0.002, sigma_max=80.0, sigma_data=0.5, rho=7.0, P_mean=-1.2, P_std=1.2, S_churn=80.0,
+              S_tmin=0.05, S_tmax=50.0, S_noise=1.003)
+    hp.update(case.get("hp", {}))
+    return hp
+
+
+def elucidated_noise_count(case):
+    return elucidated_hparams(case)["num_sample_steps"] - (case.get("skip_steps") or 0) + 1

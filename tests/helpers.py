@@ -69,3 +69,18 @@ def max_rel(a, b):
     a = torch.as_tensor(a, dtype=torch.float64)
     b = torch.as_tensor(b, dtype=torch.float64)
     return ((a - b).abs().max() / b.abs().max().clamp(min=1e-30)).item()
+
+
+def oracle_elucidated(case, sd=None):
+    """Elucidated sampler oracle on a case of cases.ELUCIDATED_CASES -> (img, [x_start per step])."""
+    from cases import elucidated_hparams, elucidated_noise_count
+    from oracle.elucidated_oracle import elucidated_sample
+    sd = sd if sd is not None else weights_for(case)
+    spec = spec_from_kwargs(case["unet"])
+    _, lr, _ = build_inputs(case)
+    B, S = case["batch"], case["size"]
+    hp = {k: v for k, v in elucidated_hparams(case).items() if k not in ("P_mean", "P_std")}
+    noise = synthetic_noise((B, 1, S, S, S), elucidated_noise_count(case), case["noise_seed"])
+    with torch.no_grad():
+        return elucidated_sample(lambda x, t: unet_forward(sd, spec, x, t, lowres_cond_img=lr), (B, 1, S, S, S), noise,
+                                 dynamic_threshold=case["dynamic_threshold"], skip_steps=case.get("skip_steps"), **hp)

@@ -102,27 +102,34 @@ def test_conv_tcgen05_bf16(mode, n, dims, c_in, c_out):
 
 
 ZM_SHAPES = [
-    # n, (d0, d1, d2): z-march kernel needs d1 % 16 == 0, d2 % 8 == 0
-    (1, (16, 16, 16)),
-    (1, (2, 16, 8)),
-    (1, (5, 16, 8)),       # odd depth: last z-segment shorter
-    (2, (8, 32, 16)),
-    (3, (4, 16, 24)),      # more items than one slot pair per column, batch > 1
-    (1, (32, 32, 32)),
-    (1, (64, 64, 64)),     # BASELINE config 2 shape
+    # n, (d0, d1, d2), c_in, c_out: z-march kernel needs d1 % 16 == 0, d2 % 8 == 0, channels in multiples of 64
+    (1, (16, 16, 16), 64, 64),
+    (1, (2, 16, 8), 64, 64),
+    (1, (5, 16, 8), 64, 64),        # odd depth: last z-segment shorter
+    (2, (8, 32, 16), 64, 64),
+    (3, (4, 16, 24), 64, 64),       # more items than one slot pair per column, batch > 1
+    (1, (32, 32, 32), 64, 64),
+    (1, (64, 64, 64), 64, 64),      # BASELINE config 2 shape
+    (1, (16, 16, 16), 128, 128),    # two K chunks, two output-channel groups (level 2 of the driver U-Net)
+    (1, (32, 32, 32), 192, 128),    # ups.0.1.block1: concat input, three K chunks
+    (1, (16, 32, 16), 128, 64),     # ups.1.1.block1 at a test-sized volume
+    (2, (3, 16, 8), 64, 192),       # odd item count per channel group: one slot of the last pair idles
+    (1, (8, 16, 16), 256, 256),     # mid_block width (deep_feature)
+    (5, (2, 16, 8), 64, 128),       # several volumes per CTA slot: per-(volume, group) statistics flushes
 ]
 
 
-@pytest.mark.parametrize("n,dims", ZM_SHAPES)
-def test_conv_zmarch_bf16(n, dims):
+@pytest.mark.parametrize("n,dims,c_in,c_out", ZM_SHAPES)
+def test_conv_zmarch_bf16(n, dims, c_in, c_out):
     from diffusioniqt_b200 import ops
-    x = _rand(n, 64, *dims, seed=21).bfloat16().float()
-    w, b = _conv_weight("k3", 64, 64, 22)
+    x = _rand(n, c_in, *dims, seed=21).bfloat16().float()
+    w, b = _conv_weight("k3", c_in, c_out, 22)
     want = _conv_reference(x, w.bfloat16().float(), b, "k3")
     got, stats = ops.conv3d(ops.to_channels_last(x.cuda(), torch.bfloat16), w, b, mode="k3", impl="zm", with_stats=True)
     stored = ops.from_channels_last(got).cpu()
     assert max_rel(stored, want) < BF16_TOL
     # fused statistics describe the stored (bf16-rounded) output exactly up to fp32 summation order
+    assert not torch.isnan(stats).any()
     s = stats.sum(dim=1).cpu()
     assert max_rel(s[..., 0], stored.sum(dim=(2, 3, 4))) < 2e-4
     assert max_rel(s[..., 1], (stored ** 2).sum(dim=(2, 3, 4))) < 2e-4

@@ -3,8 +3,8 @@ import numpy as np
 import pytest
 import torch
 
-from cases import FORWARD_CASES, SAMPLE_CASES, tap_digest
-from helpers import load_golden, max_rel, oracle_forward, oracle_sample
+from cases import ELUCIDATED_CASES, FORWARD_CASES, SAMPLE_CASES, tap_digest
+from helpers import load_golden, max_rel, oracle_elucidated, oracle_forward, oracle_sample
 
 # fixtures were generated on another CPU; oneDNN may pick other kernels -> tiny fp32 differences
 TOL = 2e-5
@@ -36,3 +36,14 @@ def test_sampler_matches_reference_fixture(name):
         assert max_rel(x_t, g[f"x_t:{int(k)}"]) < 20 * TOL
         assert max_rel(traj_x0[int(k)], g[f"x0:{int(k)}"]) < 20 * TOL
     assert float(img.min()) >= lo - 1e-6
+
+
+@pytest.mark.parametrize("name", list(ELUCIDATED_CASES))
+def test_elucidated_sampler_matches_reference_fixture(name):
+    """Fixture = the reference's own one_unet_sample loop around the reference Unet (tests/golden/make_golden_elucidated.py)."""
+    case = ELUCIDATED_CASES[name]
+    g = load_golden(name)
+    img, x_starts = oracle_elucidated(case)
+    assert max_rel(img, g["img"]) < 20 * TOL
+    assert float(img.min()) >= -1.0 and float(img.max()) <= 1.0
+    assert len(x_starts) == case["hp"]["num_sample_steps"] - (case.get("skip_steps") or 0)

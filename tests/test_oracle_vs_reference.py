@@ -5,7 +5,7 @@ import torch
 import ref_shim
 from cases import FORWARD_CASES, SAMPLE_CASES, build_inputs, make_configs, sample_noise_count, unet_kwargs_for_reference
 from diffusioniqt_b200.synth import fill_module_, synthetic_noise
-from helpers import oracle_forward, oracle_sample, spec_from_kwargs
+from helpers import oracle_elucidated, oracle_forward, oracle_sample, spec_from_kwargs
 from oracle import unet_oracle as uo
 
 pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference checkout not present")
@@ -55,6 +55,17 @@ def test_sampler_matches(ref):
     got, _, traj_o = oracle_sample(case, sd=unet.state_dict())
     assert torch.allclose(got, want, atol=1e-6, rtol=0)
     assert len(traj) == len(traj_o) == T + 1
+
+
+def test_elucidated_sampler_matches_reference_loop(ref):
+    """The reference's own one_unet_sample / preconditioned_network_forward (elucidated_imagen.py:329-532), run on an
+    instance assembled without its broken constructor, against the oracle restatement: bit-identical on the same CPU."""
+    import make_golden_elucidated as mg
+    from cases import ELUCIDATED_CASES
+    case = ELUCIDATED_CASES["edm_dim32_s8_n6"]
+    want = mg.run_reference(case)
+    got, _ = oracle_elucidated(case)
+    assert torch.equal(got, want)
 
 
 def test_flop_count_matches_survey():
