@@ -15,7 +15,7 @@ int conv_tc_pack(const diqt_conv_desc* d, const float* w, void* packed, cudaStre
 int conv_tc_plan(const diqt_conv_desc* d, const void* in, void* out, const void* packed, const float* bias, TcPlan** plan);
 int conv_tc_run(const TcPlan* plan, cudaStream_t st);
 void conv_tc_destroy(TcPlan* plan);
-int conv_tc_set_stats(TcPlan* plan, float* partial);
+int conv_tc_set_stats(TcPlan* plan, float* partial, float* group, unsigned int* tickets, int* ngroups);
 struct ZmPlan;
 bool conv_zm_supported(const diqt_conv_desc* d);
 bool conv_zm_profitable(const diqt_conv_desc* d);
@@ -23,7 +23,7 @@ size_t conv_zm_packed_bytes(const diqt_conv_desc* d);
 int conv_zm_pack(const diqt_conv_desc* d, const float* w, void* packed, cudaStream_t st);
 int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void* packed, const float* bias, ZmPlan** plan);
 int conv_zm_run(const ZmPlan* plan, cudaStream_t st);
-int conv_zm_set_stats(ZmPlan* plan, float* partial);
+int conv_zm_set_stats(ZmPlan* plan, float* partial, float* group, unsigned int* tickets, int* ngroups);
 void conv_zm_destroy(ZmPlan* plan);
 }  // namespace diqt
 
@@ -154,6 +154,17 @@ extern "C" int diqt_conv_run(const diqt_conv_plan* plan, void* stream) {
 
 extern "C" int diqt_conv_plan_set_stats(diqt_conv_plan* plan, float* partial, int* nblk) {
   DIQT_REQUIRE(plan && partial && nblk, "conv_plan_set_stats: null pointer");
-  *nblk = plan->impl == DIQT_IMPL_ZM ? conv_zm_set_stats(plan->zm, partial) : plan->impl == DIQT_IMPL_TC ? conv_tc_set_stats(plan->tc, partial) : 0;
+  *nblk = plan->impl == DIQT_IMPL_ZM   ? conv_zm_set_stats(plan->zm, partial, nullptr, nullptr, nullptr)
+          : plan->impl == DIQT_IMPL_TC ? conv_tc_set_stats(plan->tc, partial, nullptr, nullptr, nullptr)
+                                       : 0;
+  return DIQT_OK;
+}
+
+extern "C" int diqt_conv_plan_set_stats_g(diqt_conv_plan* plan, float* partial, float* group, uint32_t* tickets, int* nblk, int* ngroups) {
+  DIQT_REQUIRE(plan && partial && group && tickets && nblk && ngroups, "conv_plan_set_stats_g: null pointer");
+  *nblk = plan->impl == DIQT_IMPL_ZM   ? conv_zm_set_stats(plan->zm, partial, group, tickets, ngroups)
+          : plan->impl == DIQT_IMPL_TC ? conv_tc_set_stats(plan->tc, partial, group, tickets, ngroups)
+                                       : 0;
+  if (*nblk == 0) *ngroups = 0;
   return DIQT_OK;
 }

@@ -39,7 +39,9 @@ bool pdl_enabled();  // DIQT_DISABLE_PDL=1 switches the attribute off (A/B measu
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-template <typename... KArgs, typename... Args>
+// `allow` = false launches the same kernel without the attribute (full stream serialisation): used for the first and last
+// kernels of a sampler step, which sit next to launches this library does not control (graph boundaries, torch kernels).
+template <bool kAllow = true, typename... KArgs, typename... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -50,7 +52,7 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (kAllow && pdl_enabled()) ? 1 : 0;
   (void)cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);  // errors surface in check_launch()
 }
 
@@ -134,6 +136,107 @@ __device__ __forceinline__ int64_t sub_row(const SubGeom g, int64_t voxels, int 
   const int xl = (int)(l % h), yl = (int)((l / h) % h), zl = (int)(l / ((int64_t)h * h));
   const int zb = b % g.f, yb = (b / g.f) % g.f, xb = b / (g.f * g.f);
   return ((int64_t)(zb * h + zl) * fh + (yb * h + yl)) * fh + xb * h + xl;
+}
+
+// ---- grouped channel statistics -----------------------------------------------------------------------
+// Producers (convs, scale_residual, channel_stats) write one partial row [c][2] (sum, sum of squares) per CTA slot:
+// partial[n][nblk][c][2].  With a StatsGroups sink the LAST CTA of every group of `gsize` consecutive rows to finish
+// (atomic ticket) also sums its group's rows in index order into group[n][ngroups][c][2], ngroups <= 16.  Consumers then
+// fold the GroupNorm / SE finalisation into their own prologue (ngroups short rows) instead of a separate single-CTA kernel
+// over hundreds of rows.  Summation order is fixed at both levels, so results stay bitwise reproducible.
+struct StatsGroups {
+  float* group;           // NULL = off
+  unsigned int* tickets;  // [ngroups], zero before first use; the last CTA of a group resets its ticket
+  int gsize, ngroups;
+};
+
+__host__ __device__ inline int stats_group_size(int nblk, int rows_per_cta) {
+  int g = (nblk + 15) / 16;
+  g = (g + rows_per_cta - 1) / rows_per_cta * rows_per_cta;
+  return g < rows_per_cta ? rows_per_cta : g;
+}
+
+// Called by `nthreads` threads (tid 0..nthreads-1) of a CTA that owns rows [row0, row0 + nrows) of `partial`, after those rows
+// have been stored; `sync` is a barrier over exactly these threads, s_flag a shared int.
+template <typename Sync>
+__device__ __forceinline__ void stats_group_tail(const StatsGroups& g, const float* partial, int n, int nblk, int c, int row0,
+                                                 int nrows, int tid, int nthreads, int* s_flag, Sync sync) {
+  if (!g.group) return;
+  __threadfence();  // this thread's partial stores are visible device-wide before the ticket is taken
+  sync();
+  const int grp = row0 / g.gsize;
+  const int r0 = grp * g.gsize, r1 = min(nblk, r0 + g.gsize);
+  if (tid == 0) {
+    const unsigned members = (unsigned)((r1 - r0) / nrows);
+    const unsigned t = atomicAdd(&g.tickets[grp], 1u);
+    *s_flag = (t == members - 1u);
+    if (t == members - 1u) g.tickets[grp] = 0u;
+  }
+  sync();
+  if (!*s_flag) return;
+  __threadfence();
+  const int width = c * 2;
+  for (int idx = tid; idx < n * width; idx += nthreads) {
+    const int nv = idx / width, j = idx - nv * width;
+    const float* src = partial + ((size_t)nv * nblk + r0) * width + j;
+    float acc = 0.f;
+    for (int r = r0; r < r1; ++r) {  // fixed order
+      acc += __ldcg(src);
+      src += width;
+    }
+    g.group[((size_t)nv * g.ngroups + grp) * width + j] = acc;
+  }
+}
+
+// Consumer side: total (sum, sumsq) of channel ch of volume nv over the group rows, in double.
+__device__ __forceinline__ void stats_group_total(const float* __restrict__ group, int ngroups, int c, int nv, int ch, double& s, double& q) {
+  const float* p = group + ((size_t)nv * ngroups) * c * 2 + ch * 2;
+  s = 0.0; q = 0.0;
+  for (int g = 0; g < ngroups; ++g) {
+    const float2 v = __ldcg(reinterpret_cast<const float2*>(p + (size_t)g * c * 2));
+    s += (double)v.x;
+    q += (double)v.y;
+  }
+}
+
+// GroupNorm(+FiLM) folded into y = a*x + b for every channel of volume nv, from grouped statistics, into shared a_s[c], b_s[c].
+// All `nthreads` threads of the CTA call this; scratch: 2*c doubles + 2*groups doubles.   (imagen_pytorch3D.py:546, :559-561)
+struct GnParams {
+  const float* group; int ngroups; long long voxels; int c, groups; float eps;
+  const float* gamma; const float* beta; const float* film; int film_ld; const int* film_row; int film_row_stride_n;
+};
+__device__ __forceinline__ void gn_affine_from_groups(const GnParams& gp, int nv, int tid, int nthreads, double* scratch, float* a_s, float* b_s) {
+  double* tot = scratch;
+  double* gstat = scratch + 2 * gp.c;
+  for (int ch = tid; ch < gp.c; ch += nthreads) stats_group_total(gp.group, gp.ngroups, gp.c, nv, ch, tot[2 * ch], tot[2 * ch + 1]);
+  __syncthreads();
+  const int cpg = gp.c / gp.groups;
+  for (int g = tid; g < gp.groups; g += nthreads) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < cpg; ++i) { s += tot[(g * cpg + i) * 2]; q += tot[(g * cpg + i) * 2 + 1]; }
+    const double cnt = (double)gp.voxels * cpg, mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    gstat[2 * g] = mean;
+    gstat[2 * g + 1] = 1.0 / sqrt(var + (double)gp.eps);
+  }
+  __syncthreads();
+  const float* fr = nullptr;
+  if (gp.film) fr = gp.film + (long long)((gp.film_row ? *gp.film_row : 0) + nv * gp.film_row_stride_n) * gp.film_ld;
+  for (int ch = tid; ch < gp.c; ch += nthreads) {
+    const int g = ch / cpg;
+    const float mean = (float)gstat[2 * g], rstd = (float)gstat[2 * g + 1];
+    float a = rstd * gp.gamma[ch];
+    float b = gp.beta[ch] - mean * a;
+    if (fr) {  // x * (scale + 1) + shift
+      const float sc = fr[ch] + 1.f, sh = fr[gp.c + ch];
+      a *= sc;
+      b = fmaf(b, sc, sh);
+    }
+    a_s[ch] = a;
+    b_s[ch] = b;
+  }
+  __syncthreads();
 }
 
 // Mish(x) = x * tanh(softplus(x)) = x * n / (n + 2),  n = e^x (e^x + 2)       (nn.Mish)

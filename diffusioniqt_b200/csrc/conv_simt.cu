@@ -37,6 +37,8 @@ __device__ __forceinline__ void tap_offset(int mode, int t, int& dz, int& dy, in
 
 template <typename T>
 __global__ void __launch_bounds__(256) conv_simt_kernel(SimtConvParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float As[2][BK][AS_LD];
   __shared__ float Bs[2][BK][BN];
   const int tid = threadIdx.x;
@@ -220,8 +222,8 @@ int conv_simt_run(const diqt_conv_desc* d, const void* in, void* out, const void
   p.taps = simt_taps(d->mode); p.mode = d->mode;
   p.m_total = (int64_t)d->n * p.od0 * p.od1 * p.od2;
   dim3 grid((unsigned)((p.m_total + BM - 1) / BM), (unsigned)((d->c_out + BN - 1) / BN));
-  if (d->dtype == DIQT_BF16) conv_simt_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p);
-  else conv_simt_kernel<float><<<grid, 256, 0, st>>>(p);
+  if (d->dtype == DIQT_BF16) launch_pdl(conv_simt_kernel<__nv_bfloat16>, grid, 256, 0, st, p);
+  else launch_pdl(conv_simt_kernel<float>, grid, 256, 0, st, p);
   return check_launch("conv_simt");
 }
 

@@ -49,6 +49,7 @@ struct TcParams {
   uint32_t tmem_cols;
   // fused channel statistics of the stored output (for the next GroupNorm / the SE pool); NULL = off
   float* stats;          // [n][gridDim.x][c_out][2]
+  StatsGroups sink;      // optional grouped reduction of the statistics rows (common.cuh)
   int n_batch;           // volumes
   int ox, oy, oz;        // output voxel grid (to mask rows of edge tiles)
   int edge_tiles;        // 1 if some tile sticks out of the volume
@@ -280,6 +281,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         float* dst = p.stats + ((size_t)nv * gridDim.x + blockIdx.x) * p.block_n * 2;
         for (int col = et; col < p.block_n * 2; col += 128) dst[col] = 0.f;
       }
+      stats_group_tail(p.sink, p.stats, p.n_batch, (int)gridDim.x, p.block_n, (int)blockIdx.x, 1, et, 128, reinterpret_cast<int*>(s_red),
+                       [] { asm volatile("bar.sync 1, 128;" ::: "memory"); });
     }
     if (et == 0) bulk_wait0();
   }
@@ -498,10 +501,17 @@ int conv_tc_run(const TcPlan* plan, cudaStream_t st) {
 void conv_tc_destroy(TcPlan* plan) { delete plan; }
 
 // Fused output statistics are available when one CTA tile never mixes volumes and N fits one tile.
-int conv_tc_set_stats(TcPlan* plan, float* partial) {
+int conv_tc_set_stats(TcPlan* plan, float* partial, float* group, unsigned int* tickets, int* ngroups) {
   TcParams& p = plan->p;
+  if (ngroups) *ngroups = 0;
   if (p.n_tiles != 1 || p.bn != 1 || p.mode == DIQT_CONV_UP) return 0;
   p.stats = partial;
+  StatsGroups& g = p.sink;
+  g.group = group;
+  g.tickets = tickets;
+  g.gsize = stats_group_size(plan->grid, 1);
+  g.ngroups = (plan->grid + g.gsize - 1) / g.gsize;
+  if (ngroups) *ngroups = group ? g.ngroups : 0;
   return plan->grid;
 }
 

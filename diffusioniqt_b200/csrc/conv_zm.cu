@@ -49,6 +49,7 @@ struct ZmParams {
   const uint8_t* w;   // [nh][kc][kb = kh*3+kw][j: 0 -> kd=2 (dz=+1), 1 -> kd=1, 2 -> kd=0 (dz=-1)][64 c_out][64 c_in], pre-swizzled
   const float* bias;  // [c_out]
   float* stats;       // NULL or [n][2*gridDim.x][c_out][2]
+  StatsGroups sink;   // optional grouped reduction of the statistics rows (common.cuh)
   int n, D, H, W;
   int KC, NH, c_out;  // c_in / 64, c_out / 64
   int tiles_x, tiles_y, nseg, L;
@@ -128,11 +129,15 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   pdl_launch_dependents();
-  pdl_wait();  // everything above is private to this CTA; activations of the previous kernel are touched only below
+  // Everything above is private to this CTA.  Only the roles that touch activations / statistics of earlier kernels block in
+  // pdl_wait(): the plane producer (reads the input) and the epilogue (writes the output and the statistics rows).  The weight
+  // producer streams constant weights and runs ahead, so the first weight stages are already in flight when the predecessor
+  // kernel drains; the issuers only wait on mbarriers fed by those two.
 
   if (warp == 0) {
     // ===================== input plane producer =====================
     if (lane == 0) {
+      pdl_wait();
       int ring[2] = {0, 0};
       uint32_t phase[2] = {0, 0};
       for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
@@ -271,6 +276,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
     const int et = threadIdx.x - 128;     // 0..127
     const int cp = et & 31, rq = et >> 5;
     const int nblk = 2 * (int)gridDim.x;
+    pdl_wait();
     int kcount[2] = {0, 0};
     float st_s[2][2], st_q[2][2];
     int st_key[2] = {-1, -1};  // (volume, output-channel group) the running sums of a slot belong to
@@ -385,6 +391,8 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
 #pragma unroll
       for (int s = 0; s < 2; ++s)
         if (st_key[s] >= 0) flush_stats(s, st_key[s]);
+      stats_group_tail(p.sink, p.stats, p.n, nblk, p.c_out, (int)blockIdx.x * 2, 2, et, 128, reinterpret_cast<int*>(s_red),
+                       [] { asm volatile("bar.sync 1, 128;" ::: "memory"); });
     }
     if (et == 0) bulk_wait0();
   }
@@ -512,9 +520,16 @@ int conv_zm_run(const ZmPlan* plan, cudaStream_t st) {
   return check_launch("conv_zm");
 }
 
-int conv_zm_set_stats(ZmPlan* plan, float* partial) {
+int conv_zm_set_stats(ZmPlan* plan, float* partial, float* group, unsigned int* tickets, int* ngroups) {
   plan->p.stats = partial;
-  return 2 * plan->grid;
+  const int nblk = 2 * plan->grid;
+  StatsGroups& g = plan->p.sink;
+  g.group = group;
+  g.tickets = tickets;
+  g.gsize = stats_group_size(nblk, 2);
+  g.ngroups = (nblk + g.gsize - 1) / g.gsize;
+  if (ngroups) *ngroups = group ? g.ngroups : 0;
+  return nblk;
 }
 
 void conv_zm_destroy(ZmPlan* plan) { delete plan; }

@@ -4,9 +4,19 @@
 //
 // Reference call sites replaced: nn.GroupNorm (imagen_pytorch3D.py:546, 557), FiLM (:559-561),
 // nn.Mish (:547, 563), SE3D (:617-632), residual add (:612).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace diqt {
+
+// squeeze-excitation gate computed in the consumer's prologue from grouped statistics (group == NULL: read `gate` instead)
+struct SeParams {
+  const float* group;
+  int ngroups, hidden;
+  const float* w1;
+  const float* w2;
+};
 
 // thread mapping shared by every kernel in this file:
 //   nvec = c / VEC vectors per voxel row; thread -> (col = tid % nvec, lane = tid / nvec);
@@ -50,7 +60,7 @@ __device__ __forceinline__ void block_channel_reduce(const float (&s)[VEC], cons
 
 template <typename T>
 __global__ void channel_stats_kernel(const T* __restrict__ x, int64_t voxels, int c, int ld, int nvec, int lanes,
-                                     int64_t vpb, float* __restrict__ partial, SubGeom sg) {
+                                     int64_t vpb, float* __restrict__ partial, SubGeom sg, StatsGroups og) {
   constexpr int VEC = Vec<T>::N;
   extern __shared__ float smem[];
   const int col = threadIdx.x % nvec, lane = threadIdx.x / nvec;
@@ -86,6 +96,11 @@ __global__ void channel_stats_kernel(const T* __restrict__ x, int64_t voxels, in
     }
   }
   block_channel_reduce<VEC>(s, q, col, lane, lanes, c, partial + ((int64_t)n * nblk + blk) * c * 2, smem);
+  // grouped sink (single-volume launches only: the group row of volume n is built from this volume's partial rows)
+  StatsGroups ov = og;  // this volume's slice of the sink (tickets[n][ngroups], group[n][ngroups][c][2])
+  if (ov.group) { ov.group += (int64_t)n * og.ngroups * c * 2; ov.tickets += n * og.ngroups; }
+  stats_group_tail(ov, partial + (int64_t)n * nblk * c * 2, 1, nblk, c, blk, 1, threadIdx.x, blockDim.x, reinterpret_cast<int*>(smem),
+                   [] { __syncthreads(); });
 }
 
 // ---- GroupNorm finalize: partial sums -> per-(n,c) affine (a, b), with FiLM folded in -----------
@@ -173,8 +188,9 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblk, 
 template <typename T, bool kFast>
 __global__ void affine_mish_kernel(const T* __restrict__ x, int ld_x, T* __restrict__ y, int ld_y, int64_t voxels,
                                    int c, int nvec, int lanes, int64_t vpb, const float* __restrict__ a,
-                                   const float* __restrict__ b, SubGeom sg) {
+                                   const float* __restrict__ b, SubGeom sg, GnParams gp) {
   constexpr int VEC = Vec<T>::N;
+  extern __shared__ double gn_scratch[];  // grouped mode: 2c + 2 groups doubles, then a_s[c], b_s[c] floats
   const int col = threadIdx.x % nvec, lane = threadIdx.x / nvec;
   const int n = blockIdx.y;
   const int64_t v0 = (int64_t)blockIdx.x * vpb;
@@ -182,10 +198,21 @@ __global__ void affine_mish_kernel(const T* __restrict__ x, int ld_x, T* __restr
   pdl_launch_dependents();
   pdl_wait();
   float av[VEC], bv[VEC];
+  if (gp.group) {  // GroupNorm (+FiLM) finalised here from the producer's grouped statistics: no separate finalize kernel
+    float* a_s = reinterpret_cast<float*>(gn_scratch + 2 * c + 2 * gp.groups);
+    float* b_s = a_s + c;
+    gn_affine_from_groups(gp, n, threadIdx.x, blockDim.x, gn_scratch, a_s, b_s);
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    av[i] = a[(int64_t)n * c + col * VEC + i];
-    bv[i] = b[(int64_t)n * c + col * VEC + i];
+    for (int i = 0; i < VEC; ++i) {
+      av[i] = a_s[col * VEC + i];
+      bv[i] = b_s[col * VEC + i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      av[i] = a[(int64_t)n * c + col * VEC + i];
+      bv[i] = b[(int64_t)n * c + col * VEC + i];
+    }
   }
   const T* xb = x + col * VEC;
   T* yb = y + col * VEC;
@@ -261,7 +288,8 @@ __global__ void se_gate_kernel(const float* __restrict__ partial, int nblk, int6
 template <typename T>
 __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T* __restrict__ res, int ld_res,
                                       T* __restrict__ out, int ld_out, int64_t voxels, int c, int nvec, int lanes,
-                                      int64_t vpb, const float* __restrict__ gate, float* __restrict__ partial, SubGeom sg) {
+                                      int64_t vpb, const float* __restrict__ gate, float* __restrict__ partial, SubGeom sg,
+                                      SeParams se, StatsGroups og) {
   constexpr int VEC = Vec<T>::N;
   extern __shared__ float smem[];
   const int col = threadIdx.x % nvec, lane = threadIdx.x / nvec;
@@ -271,11 +299,41 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
   pdl_launch_dependents();
   pdl_wait();
   float g[VEC], s[VEC], q[VEC];
+  if (se.group) {
+    // squeeze-excitation gate (imagen_pytorch3D.py:617-632) from the grouped statistics of conv2's output, recomputed by every CTA
+    float* mean = smem;          // [c]
+    float* hid = smem + c;       // [hidden]
+    float* gs = hid + se.hidden; // [c]
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      double sm, sq;
+      stats_group_total(se.group, se.ngroups, c, n, ch, sm, sq);
+      mean[ch] = (float)(sm / (double)voxels);
+    }
+    __syncthreads();
+    const int warp = threadIdx.x / 32, wl = threadIdx.x % 32, nwarps = blockDim.x / 32;
+    for (int j = warp; j < se.hidden; j += nwarps) {
+      float acc = 0.f;
+      for (int k = wl; k < c; k += 32) acc = fmaf(se.w1[(int64_t)j * c + k], mean[k], acc);
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) {
-    g[i] = gate ? gate[(int64_t)n * c + col * VEC + i] : 1.f;
-    s[i] = q[i] = 0.f;
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (wl == 0) hid[j] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      float acc = 0.f;
+      for (int j = 0; j < se.hidden; ++j) acc = fmaf(se.w2[(int64_t)ch * se.hidden + j], hid[j], acc);
+      gs[ch] = 1.f / (1.f + expf(-acc));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) g[i] = gs[col * VEC + i];
+    __syncthreads();  // smem is reused by the block reduction below
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) g[i] = gate ? gate[(int64_t)n * c + col * VEC + i] : 1.f;
   }
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) s[i] = q[i] = 0.f;
   const T* hb = h + col * VEC;
   const T* rb = res + col * VEC;
   T* ob = out + col * VEC;
@@ -322,8 +380,13 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
       }
     }
   }
-  if (partial)
+  if (partial) {
     block_channel_reduce<VEC>(s, q, col, lane, lanes, c, partial + ((int64_t)n * nblk + blk) * c * 2, smem);
+    StatsGroups ov = og;
+    if (ov.group) { ov.group += (int64_t)n * og.ngroups * c * 2; ov.tickets += n * og.ngroups; }
+    stats_group_tail(ov, partial + (int64_t)n * nblk * c * 2, 1, nblk, c, blk, 1, threadIdx.x, blockDim.x, reinterpret_cast<int*>(smem),
+                     [] { __syncthreads(); });
+  }
 }
 
 // ---- dst = src * scale  (row-pitched copy; the scaled skip connection, imagen_pytorch3D.py:1346, 1653) ----------
@@ -350,9 +413,27 @@ static inline int64_t vox_per_block(int64_t voxels, int nblk) { return (voxels +
 
 using namespace diqt;
 
-extern "C" int diqt_channel_stats(const void* x, int dtype, int n, int64_t voxels, int c, int ld, int nblk,
-                                  float* partial, int sub_f, int sub_h, void* stream) {
+static StatsGroups make_sink(float* group, uint32_t* tickets, int nblk, int rows_per_cta) {
+  StatsGroups g;
+  g.group = group;
+  g.tickets = tickets;
+  g.gsize = stats_group_size(nblk, rows_per_cta);
+  g.ngroups = (nblk + g.gsize - 1) / g.gsize;
+  return g;
+}
+
+extern "C" int diqt_stats_groups(int nblk, int rows_per_cta, int* ngroups) {
+  DIQT_REQUIRE(nblk > 0 && rows_per_cta > 0 && ngroups, "stats_groups: bad arguments");
+  const int gs = stats_group_size(nblk, rows_per_cta);
+  *ngroups = (nblk + gs - 1) / gs;
+  return DIQT_OK;
+}
+
+static int channel_stats_impl(const void* x, int dtype, int n, int64_t voxels, int c, int ld, int nblk,
+                              float* partial, float* group, uint32_t* tickets, int sub_f, int sub_h, void* stream) {
   const SubGeom sg{sub_f, sub_h};
+  const StatsGroups og = make_sink(group, tickets, nblk, 1);
+  if (group) DIQT_REQUIRE(tickets && sub_f <= 1, "channel_stats: grouped sink needs tickets and plain volumes");
   if (sub_f > 1) DIQT_REQUIRE(n == sub_f * sub_f * sub_f && voxels == (int64_t)sub_h * sub_h * sub_h, "channel_stats: sub-volume geometry mismatch");
   const int vec = dtype == DIQT_BF16 ? 8 : 4;
   DIQT_REQUIRE(x && partial && n > 0 && voxels > 0 && nblk > 0, "channel_stats: bad arguments");
@@ -363,11 +444,22 @@ extern "C" int diqt_channel_stats(const void* x, int dtype, int n, int64_t voxel
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)
     launch_pdl(channel_stats_kernel<__nv_bfloat16>, grid, m.threads, sh, st, (const __nv_bfloat16*)x, voxels, c, ld, m.nvec, m.lanes,
-                                                                    vox_per_block(voxels, nblk), partial, sg);
+               vox_per_block(voxels, nblk), partial, sg, og);
   else
     launch_pdl(channel_stats_kernel<float>, grid, m.threads, sh, st, (const float*)x, voxels, c, ld, m.nvec, m.lanes,
-                                                            vox_per_block(voxels, nblk), partial, sg);
+               vox_per_block(voxels, nblk), partial, sg, og);
   return check_launch("channel_stats");
+}
+
+extern "C" int diqt_channel_stats(const void* x, int dtype, int n, int64_t voxels, int c, int ld, int nblk,
+                                  float* partial, int sub_f, int sub_h, void* stream) {
+  return channel_stats_impl(x, dtype, n, voxels, c, ld, nblk, partial, nullptr, nullptr, sub_f, sub_h, stream);
+}
+
+extern "C" int diqt_channel_stats_g(const void* x, int dtype, int n, int64_t voxels, int c, int ld, int nblk, float* partial,
+                                    float* group, uint32_t* tickets, void* stream) {
+  DIQT_REQUIRE(group && tickets, "channel_stats_g: null sink");
+  return channel_stats_impl(x, dtype, n, voxels, c, ld, nblk, partial, group, tickets, 0, 0, stream);
 }
 
 extern "C" int diqt_gn_finalize(const float* partial, int n, int nblk, int64_t voxels, int c, int groups, float eps,
@@ -388,24 +480,39 @@ extern "C" int diqt_gn_finalize(const float* partial, int n, int nblk, int64_t v
   return check_launch("gn_finalize");
 }
 
-extern "C" int diqt_affine_mish(const void* x, int ld_x, void* y, int ld_y, int dtype, int n, int64_t voxels, int c,
-                                const float* a, const float* b, int nblk, int sub_f, int sub_h, void* stream) {
+static int affine_mish_impl(const void* x, int ld_x, void* y, int ld_y, int dtype, int n, int64_t voxels, int c,
+                            const float* a, const float* b, int nblk, int sub_f, int sub_h, const GnParams& gp, void* stream) {
   const SubGeom sg{sub_f, sub_h};
   if (sub_f > 1) DIQT_REQUIRE(n == sub_f * sub_f * sub_f && voxels == (int64_t)sub_h * sub_h * sub_h, "affine_mish: sub-volume geometry mismatch");
   const int vec = dtype == DIQT_BF16 ? 8 : 4;
-  DIQT_REQUIRE(x && y && a && b && nblk > 0, "affine_mish: bad arguments");
+  DIQT_REQUIRE(x && y && ((a && b) || gp.group) && nblk > 0, "affine_mish: bad arguments");
+  const size_t gsh = gp.group ? (size_t)(2 * c + 2 * gp.groups) * sizeof(double) + (size_t)2 * c * sizeof(float) : 0;
   DIQT_REQUIRE(c % vec == 0 && ld_x % vec == 0 && ld_y % vec == 0 && c / vec <= 256, "affine_mish: c=%d not a multiple of %d", c, vec);
   RowMap m = make_rowmap(c, vec, 256);
   dim3 grid(nblk, n);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)
-    launch_pdl(affine_mish_kernel<__nv_bfloat16, true>, grid, m.threads, 0, st, (const __nv_bfloat16*)x, ld_x, (__nv_bfloat16*)y, ld_y,
-                                                                       voxels, c, m.nvec, m.lanes,
-                                                                       vox_per_block(voxels, nblk), a, b, sg);
+    launch_pdl(affine_mish_kernel<__nv_bfloat16, true>, grid, m.threads, gsh, st, (const __nv_bfloat16*)x, ld_x, (__nv_bfloat16*)y, ld_y,
+               voxels, c, m.nvec, m.lanes, vox_per_block(voxels, nblk), a, b, sg, gp);
   else
-    launch_pdl(affine_mish_kernel<float, false>, grid, m.threads, 0, st, (const float*)x, ld_x, (float*)y, ld_y, voxels, c, m.nvec,
-                                                                m.lanes, vox_per_block(voxels, nblk), a, b, sg);
+    launch_pdl(affine_mish_kernel<float, false>, grid, m.threads, gsh, st, (const float*)x, ld_x, (float*)y, ld_y, voxels, c, m.nvec,
+               m.lanes, vox_per_block(voxels, nblk), a, b, sg, gp);
   return check_launch("affine_mish");
+}
+
+extern "C" int diqt_affine_mish(const void* x, int ld_x, void* y, int ld_y, int dtype, int n, int64_t voxels, int c,
+                                const float* a, const float* b, int nblk, int sub_f, int sub_h, void* stream) {
+  GnParams gp = {};
+  return affine_mish_impl(x, ld_x, y, ld_y, dtype, n, voxels, c, a, b, nblk, sub_f, sub_h, gp, stream);
+}
+
+extern "C" int diqt_gn_mish_g(const void* x, int ld_x, void* y, int ld_y, int dtype, int n, int64_t voxels, int c, const float* group,
+                              int ngroups, int groups, float eps, const float* gamma, const float* beta, const float* film, int film_ld,
+                              const int32_t* film_row, int film_row_stride_n, int nblk, void* stream) {
+  DIQT_REQUIRE(group && ngroups > 0 && gamma && beta, "gn_mish_g: null pointer");
+  DIQT_REQUIRE(groups > 0 && c % groups == 0 && c <= 2048, "gn_mish_g: c=%d groups=%d", c, groups);
+  GnParams gp = {group, ngroups, (long long)voxels, c, groups, eps, gamma, beta, film, film_ld, film_row, film_row_stride_n};
+  return affine_mish_impl(x, ld_x, y, ld_y, dtype, n, voxels, c, nullptr, nullptr, nblk, 0, 0, gp, stream);
 }
 
 extern "C" int diqt_se_gate(const float* partial, int n, int nblk, int64_t voxels, int c, int hidden, const float* w1,
@@ -419,10 +526,12 @@ extern "C" int diqt_se_gate(const float* partial, int n, int nblk, int64_t voxel
   return check_launch("se_gate");
 }
 
-extern "C" int diqt_scale_residual(const void* h, int ld_h, const void* res, int ld_res, void* out, int ld_out, int dtype,
-                                   int n, int64_t voxels, int c, const float* gate, int nblk, float* partial,
-                                   int sub_f, int sub_h, void* stream) {
+static int scale_residual_impl(const void* h, int ld_h, const void* res, int ld_res, void* out, int ld_out, int dtype,
+                               int n, int64_t voxels, int c, const float* gate, int nblk, float* partial,
+                               int sub_f, int sub_h, const SeParams& se, float* group_out, uint32_t* tickets, void* stream) {
   const SubGeom sg{sub_f, sub_h};
+  const StatsGroups og = make_sink(group_out, tickets, nblk, 1);
+  if (group_out) DIQT_REQUIRE(partial && tickets && sub_f <= 1, "scale_residual: grouped sink needs partial rows, tickets and plain volumes");
   if (sub_f > 1) DIQT_REQUIRE(n == sub_f * sub_f * sub_f && voxels == (int64_t)sub_h * sub_h * sub_h, "scale_residual: sub-volume geometry mismatch");
   const int vec = dtype == DIQT_BF16 ? 8 : 4;
   DIQT_REQUIRE(h && res && out && nblk > 0, "scale_residual: bad arguments");
@@ -431,16 +540,33 @@ extern "C" int diqt_scale_residual(const void* h, int ld_h, const void* res, int
   RowMap m = make_rowmap(c, vec, 512);
   dim3 grid(nblk, n);
   size_t sh = partial ? (size_t)2 * m.lanes * c * sizeof(float) : 0;
+  if (se.group) sh = std::max(sh, (size_t)(2 * c + se.hidden) * sizeof(float));
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)
     launch_pdl(scale_residual_kernel<__nv_bfloat16>, grid, m.threads, sh, st, 
         (const __nv_bfloat16*)h, ld_h, (const __nv_bfloat16*)res, ld_res, (__nv_bfloat16*)out, ld_out, voxels, c, m.nvec,
-        m.lanes, vox_per_block(voxels, nblk), gate, partial, sg);
+        m.lanes, vox_per_block(voxels, nblk), gate, partial, sg, se, og);
   else
     launch_pdl(scale_residual_kernel<float>, grid, m.threads, sh, st, (const float*)h, ld_h, (const float*)res, ld_res, (float*)out,
-                                                             ld_out, voxels, c, m.nvec, m.lanes,
-                                                             vox_per_block(voxels, nblk), gate, partial, sg);
+               ld_out, voxels, c, m.nvec, m.lanes, vox_per_block(voxels, nblk), gate, partial, sg, se, og);
   return check_launch("scale_residual");
+}
+
+extern "C" int diqt_scale_residual(const void* h, int ld_h, const void* res, int ld_res, void* out, int ld_out, int dtype,
+                                   int n, int64_t voxels, int c, const float* gate, int nblk, float* partial,
+                                   int sub_f, int sub_h, void* stream) {
+  SeParams se = {};
+  return scale_residual_impl(h, ld_h, res, ld_res, out, ld_out, dtype, n, voxels, c, gate, nblk, partial, sub_f, sub_h, se, nullptr, nullptr,
+                             stream);
+}
+
+extern "C" int diqt_scale_residual_g(const void* h, int ld_h, const void* res, int ld_res, void* out, int ld_out, int dtype, int n,
+                                     int64_t voxels, int c, const float* se_group, int se_ngroups, int hidden, const float* w1,
+                                     const float* w2, int nblk, float* partial, float* group_out, uint32_t* tickets, void* stream) {
+  SeParams se = {se_group, se_ngroups, hidden, w1, w2};
+  if (se_group) DIQT_REQUIRE(se_ngroups > 0 && hidden > 0 && w1 && w2, "scale_residual_g: incomplete SE description");
+  return scale_residual_impl(h, ld_h, res, ld_res, out, ld_out, dtype, n, voxels, c, nullptr, nblk, partial, 0, 0, se, group_out, tickets,
+                             stream);
 }
 
 extern "C" int diqt_scale_copy(const void* src, int ld_src, void* dst, int ld_dst, int dtype, int64_t rows, int c, float scale,

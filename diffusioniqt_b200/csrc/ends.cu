@@ -444,11 +444,11 @@ extern "C" int diqt_init_conv(const float* const* planes, const int64_t* plane_s
     if (dtype == DIQT_BF16) {
       auto k = init_conv_x4_kernel<__nv_bfloat16, 32>;
       if (sh > 48 * 1024) DIQT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-      launch_pdl(k, blocks4, threads, sh, st, ip, c_in, w_packed, bias, (__nv_bfloat16*)out, ld_out, n, d0, d1, d2, c_out, sg);
+      launch_pdl<false>(k, blocks4, threads, sh, st, ip, c_in, w_packed, bias, (__nv_bfloat16*)out, ld_out, n, d0, d1, d2, c_out, sg);
     } else {
       auto k = init_conv_x4_kernel<float, 32>;
       if (sh > 48 * 1024) DIQT_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
-      launch_pdl(k, blocks4, threads, sh, st, ip, c_in, w_packed, bias, (float*)out, ld_out, n, d0, d1, d2, c_out, sg);
+      launch_pdl<false>(k, blocks4, threads, sh, st, ip, c_in, w_packed, bias, (float*)out, ld_out, n, d0, d1, d2, c_out, sg);
     }
     return check_launch("init_conv_x4");
   }
@@ -493,10 +493,10 @@ static int final_conv_impl(const void* x, int ld, int dtype, int n, int64_t voxe
   if (blocks > 148 * 8) blocks = 148 * 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)
-    launch_pdl(final_conv_kernel<__nv_bfloat16, 4>, (unsigned)blocks, threads, 0, st, (const __nv_bfloat16*)x, ld, voxels, c, c_out, nvec, w,
+    launch_pdl<false>(final_conv_kernel<__nv_bfloat16, 4>, (unsigned)blocks, threads, 0, st, (const __nv_bfloat16*)x, ld, voxels, c, c_out, nvec, w,
                bias, pred, step_mode, sched, step, x_t, noise, x_next, x0, aux_out, rows, sg);
   else
-    launch_pdl(final_conv_kernel<float, 4>, (unsigned)blocks, threads, 0, st, (const float*)x, ld, voxels, c, c_out, nvec, w, bias, pred,
+    launch_pdl<false>(final_conv_kernel<float, 4>, (unsigned)blocks, threads, 0, st, (const float*)x, ld, voxels, c, c_out, nvec, w, bias, pred,
                step_mode, sched, step, x_t, noise, x_next, x0, aux_out, rows, sg);
   return check_launch("final_conv");
 }
@@ -521,7 +521,7 @@ extern "C" int diqt_edm_prepare(const float* x, const float* eps, const float* t
   DIQT_REQUIRE(x && eps && table && x_hat && x_in && count > 0, "edm_prepare: bad arguments");
   int64_t blocks = (count + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_pdl(edm_prepare_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, x, eps, table, step, x_hat, x_in, count);
+  launch_pdl<false>(edm_prepare_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, x, eps, table, step, x_hat, x_in, count);
   return check_launch("edm_prepare");
 }
 
@@ -554,7 +554,7 @@ extern "C" int diqt_edm_update(const float* denoised, int pass, const float* tab
   if (pass == 0) DIQT_REQUIRE(next_input, "edm_update: the Euler pass needs the next-input buffer");
   int64_t blocks = (count + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_pdl(edm_update_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, denoised, pass, table, step, x_hat, slope, state, next_input, count);
+  launch_pdl<false>(edm_update_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, denoised, pass, table, step, x_hat, slope, state, next_input, count);
   return check_launch("edm_update");
 }
 
@@ -563,7 +563,7 @@ extern "C" int diqt_ddpm_update(const float* pred, const float* sched, const int
   DIQT_REQUIRE(pred && sched && x_t && noise && x_next, "ddpm_update: null pointer");
   int64_t blocks = (count + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_pdl(ddpm_update_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, pred, sched, step, x_t, noise, x_next, x0, count);
+  launch_pdl<false>(ddpm_update_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, pred, sched, step, x_t, noise, x_next, x0, count);
   return check_launch("ddpm_update");
 }
 
@@ -585,7 +585,7 @@ extern "C" int diqt_linear(const float* x, int ldx, int rows, int k, const float
 
 extern "C" int diqt_advance_step(int32_t* step, void* stream) {
   DIQT_REQUIRE(step, "advance_step: null pointer");
-  launch_pdl(advance_step_kernel, 1, 1, 0, (cudaStream_t)stream, step);
+  launch_pdl<false>(advance_step_kernel, 1, 1, 0, (cudaStream_t)stream, step);
   return check_launch("advance_step");
 }
 

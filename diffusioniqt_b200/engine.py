@@ -97,8 +97,8 @@ class UnetEngine:
         return t
 
     def _conv_site(self, name, mode, level_in, c_in, ld_in, c_out, ld_out, weight, bias, src_ptr, dst_ptr, stats=None):
-        """Pack weights, create the plan, return the launch closure.  With `stats` (an Act + partial buffer) the conv is
-        asked to emit the channel statistics of its output; if it cannot, a separate stats pass is appended by the caller."""
+        """Pack weights, create the plan, return the launch closure.  With `stats` (index of a statistics scratch set) the conv
+        is asked to emit the channel statistics of its output; if it cannot, a separate stats pass is appended by the caller."""
         d0, d1, d2 = self.conv_dims[level_in]
         if self.sub_f > 1:
             stats = None   # fused conv statistics are per conv volume; boundary mode needs them per sub-volume
@@ -125,11 +125,17 @@ class UnetEngine:
                 f"plan {name}")
         self._plans.append(plan.value)
         run, pv = self.lib.diqt_conv_run, plan.value
-        self._last_conv_stats_nblk = 0
+        self._last_conv_stats = None          # (partial, nblk, group, ngroups) when the conv emits the statistics of its output
         if stats is not None:
-            nb = C.c_int(0)
-            L.check(self.lib.diqt_conv_plan_set_stats(pv, stats.data_ptr(), C.byref(nb)), f"set_stats {name}")
-            self._last_conv_stats_nblk = nb.value
+            nb, ng = C.c_int(0), C.c_int(0)
+            part = self.part[stats]
+            if self.grouped:
+                L.check(self.lib.diqt_conv_plan_set_stats_g(pv, part.data_ptr(), self.grp[stats].data_ptr(), self.tick[stats].data_ptr(),
+                                                            C.byref(nb), C.byref(ng)), f"set_stats_g {name}")
+            else:
+                L.check(self.lib.diqt_conv_plan_set_stats(pv, part.data_ptr(), C.byref(nb)), f"set_stats {name}")
+            if nb.value:
+                self._last_conv_stats = (part, nb.value, self.grp[stats] if ng.value else None, ng.value)
         return lambda st: L.check(run(pv, st), name)
 
     # ------------------------------------------------------------------ build
@@ -175,6 +181,11 @@ class UnetEngine:
         self.nblk_stream = [_nblk(n, v, 592) for v in self.level_vox]
         pmax = 304 * n * cmax * 2     # up to two partials (z-march slots) per SM and volume
         self.part = [torch.zeros(pmax, dtype=torch.float32, device=self.device) for _ in range(3)]
+        # grouped statistics (include/diqt.h): producers also reduce their partial rows in <= 16 groups and the consumers finalise
+        # GroupNorm / SE in their own prologue, which removes ~57 single-CTA finalize launches per forward.  Plain small batches only.
+        self.grouped = self.sub_f <= 1 and n <= 2
+        self.grp = [torch.zeros(16 * n * cmax * 2, dtype=torch.float32, device=self.device) for _ in range(3)]
+        self.tick = [torch.zeros(16 * n, dtype=torch.int32, device=self.device) for _ in range(3)]
         self.aff_a = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
         self.aff_b = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
         self.gate = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
@@ -224,21 +235,43 @@ class UnetEngine:
         gnf, aff, stats_fn, seg, sres = lib.diqt_gn_finalize, lib.diqt_affine_mish, lib.diqt_channel_stats, lib.diqt_se_gate, lib.diqt_scale_residual
         eng = self
 
-        def add_stats(x: Act, level, part):
+        stats_g = lib.diqt_channel_stats_g
+
+        def add_stats(x: Act, level, si):
+            """A separate statistics pass over x into scratch set `si`; returns the stats record (partial, nblk, group, ngroups)."""
             nb, vox = self.nblk[level], self.level_vox[level]
+            part = self.part[si]
             xp, xc, xl, pp = x.ptr, x.c, x.ld, part.data_ptr()
             sf, sh = self.level_sub[level]
+            if self.grouped:
+                ng = C.c_int(0)
+                L.check(lib.diqt_stats_groups(nb, 1, C.byref(ng)), "stats_groups")
+                gp_, tp_ = self.grp[si].data_ptr(), self.tick[si].data_ptr()
+                ops.append(lambda st: L.check(stats_g(xp, dd, n, vox, xc, xl, nb, pp, gp_, tp_, st), "channel_stats_g"))
+                return (part, nb, self.grp[si], ng.value)
             ops.append(lambda st: L.check(stats_fn(xp, dd, n, vox, xc, xl, nb, pp, sf, sh, st), "channel_stats"))
-            return (part, nb)
+            return (part, nb, None, 0)
 
         def add_norm_act(x: Act, level, gn, film_off, dst_buf, name):
             """GroupNorm(+FiLM)+Mish of x into dst_buf[:, :x.c]; returns the Act."""
-            part, nb = x.stats
+            part, nb, grp, ng = x.stats
             vox = self.level_vox[level]
             gamma, beta = self._f32(gn.weight), self._f32(gn.bias)
             groups, eps = gn.num_groups, float(gn.eps)
-            pa, pb, pp = self.aff_a.data_ptr(), self.aff_b.data_ptr(), part.data_ptr()
             gp, bp, c = gamma.data_ptr(), beta.data_ptr(), x.c
+            dst = Act(dst_buf, x.c, x.c)
+            xp, xl, dp, dl, nbk = x.ptr, x.ld, dst.ptr, dst.ld, self.nblk_stream[level]
+            if grp is not None:
+                # one kernel: GroupNorm finalisation in the prologue, then the affine + Mish pass
+                gptr = grp.data_ptr()
+
+                def op(st, film_off=film_off):
+                    fptr = eng.film.data_ptr() + film_off * 4 if film_off is not None else 0
+                    L.check(lib.diqt_gn_mish_g(xp, xl, dp, dl, dd, n, vox, c, gptr, ng, groups, eps, gp, bp, fptr, eng._film_cols if film_off is not None else 0,
+                                               eng.film_row_ptr if film_off is not None else 0, eng.film_stride_n, nbk, st), name + ".gn_mish")
+                ops.append(op)
+                return dst
+            pa, pb, pp = self.aff_a.data_ptr(), self.aff_b.data_ptr(), part.data_ptr()
             if film_off is None:
                 ops.append(lambda st: L.check(gnf(pp, n, nb, vox, c, groups, eps, gp, bp, 0, 0, 0, 0, pa, pb, st), name + ".gn"))
             else:
@@ -246,8 +279,6 @@ class UnetEngine:
                     fptr = eng.film.data_ptr() + film_off * 4
                     L.check(gnf(pp, n, nb, vox, c, groups, eps, gp, bp, fptr, eng._film_cols, eng.film_row_ptr, eng.film_stride_n, pa, pb, st), name + ".gn")
                 ops.append(op)
-            dst = Act(dst_buf, x.c, x.c)
-            xp, xl, dp, dl, nbk = x.ptr, x.ld, dst.ptr, dst.ld, self.nblk_stream[level]
             sf, sh = self.level_sub[level]
             ops.append(lambda st: L.check(aff(xp, xl, dp, dl, dd, n, vox, c, pa, pb, nbk, sf, sh, st), name + ".mish"))
             return dst
@@ -257,42 +288,57 @@ class UnetEngine:
             assert x.c == cin and out.c == cout, (name, x.c, cin, out.c, cout)
             sc = level_scratch(level, max(cin, cout))
             vox = self.level_vox[level]
-            tmp = self.part[2]
             if x.stats is None:
-                x.stats = add_stats(x, level, self.part[self._pp])
+                x.stats = add_stats(x, level, self._pp)
                 self._pp ^= 1
             film_off = film_slot(blk)
             a1 = add_norm_act(x, level, blk.block1.groupnorm, None, sc["A"], name + ".block1")
             h = Act(sc["H"], cout, cout)
             ops.append(self._conv_site(name + ".block1.project", L.CONV_K3, level, cin, a1.ld, cout, h.ld, blk.block1.project.weight,
-                                       blk.block1.project.bias, a1.ptr, h.ptr, stats=tmp))
-            h.stats = (tmp, self._last_conv_stats_nblk) if self._last_conv_stats_nblk else add_stats(h, level, tmp)
+                                       blk.block1.project.bias, a1.ptr, h.ptr, stats=2))
+            h.stats = self._last_conv_stats or add_stats(h, level, 2)
             a2 = add_norm_act(h, level, blk.block2.groupnorm, film_off, sc["A"], name + ".block2")
             ops.append(self._conv_site(name + ".block2.project", L.CONV_K3, level, cout, a2.ld, cout, h.ld, blk.block2.project.weight,
-                                       blk.block2.project.bias, a2.ptr, h.ptr, stats=tmp if blk.has_se else None))
-            gate_ptr = 0
+                                       blk.block2.project.bias, a2.ptr, h.ptr, stats=2 if blk.has_se else None))
+            gate_ptr, se = 0, None
             if blk.has_se:
-                part, nb = (tmp, self._last_conv_stats_nblk) if self._last_conv_stats_nblk else add_stats(h, level, tmp)
+                part, nb, grp, ng = self._last_conv_stats or add_stats(h, level, 2)
                 w1, w2 = self._f32(blk.se.fc[0].weight), self._f32(blk.se.fc[2].weight)
                 hidden = w1.shape[0]
                 if hidden < 1:
                     raise ValueError(f"{name}: SE3D with {cout} channels has an empty bottleneck (reduction 16)")
-                gate_ptr = self.gate.data_ptr()
-                pp, w1p, w2p = part.data_ptr(), w1.data_ptr(), w2.data_ptr()
-                ops.append(lambda st: L.check(seg(pp, n, nb, vox, cout, hidden, w1p, w2p, gate_ptr, st), name + ".se"))
+                w1p, w2p = w1.data_ptr(), w2.data_ptr()
+                if grp is not None:
+                    se = (grp.data_ptr(), ng, hidden, w1p, w2p)       # gate computed in the residual kernel's prologue
+                else:
+                    gate_ptr = self.gate.data_ptr()
+                    pp = part.data_ptr()
+                    ops.append(lambda st: L.check(seg(pp, n, nb, vox, cout, hidden, w1p, w2p, gate_ptr, st), name + ".se"))
             if blk.has_res_conv:
                 r = Act(sc["R"], cout, cout)
                 ops.append(self._conv_site(name + ".res_conv", L.CONV_K1, level, cin, x.ld, cout, r.ld, blk.res_conv.weight, blk.res_conv.bias,
                                            x.ptr, r.ptr))
             else:
                 r = x
-            opart = self.part[self._pp]
+            si = self._pp
             self._pp ^= 1
+            opart = self.part[si]
             nbk = self.nblk[level]
             hp, hl, rp, rl, op_, ol, opp = h.ptr, h.ld, r.ptr, r.ld, out.ptr, out.ld, opart.data_ptr()
             sf, sh = self.level_sub[level]
-            ops.append(lambda st: L.check(sres(hp, hl, rp, rl, op_, ol, dd, n, vox, cout, gate_ptr, nbk, opp, sf, sh, st), name + ".residual"))
-            out.stats = (opart, nbk)
+            if self.grouped:
+                ng_out = C.c_int(0)
+                L.check(lib.diqt_stats_groups(nbk, 1, C.byref(ng_out)), "stats_groups")
+                seg_, sng, shid, sw1, sw2 = se if se is not None else (0, 0, 0, 0, 0)
+                if se is None and gate_ptr:
+                    raise RuntimeError(f"{name}: grouped statistics expect the SE gate to come from grouped conv statistics")
+                gop, tkp = self.grp[si].data_ptr(), self.tick[si].data_ptr()
+                ops.append(lambda st: L.check(lib.diqt_scale_residual_g(hp, hl, rp, rl, op_, ol, dd, n, vox, cout, seg_, sng, shid, sw1, sw2, nbk, opp,
+                                                                        gop, tkp, st), name + ".residual"))
+                out.stats = (opart, nbk, self.grp[si], ng_out.value)
+            else:
+                ops.append(lambda st: L.check(sres(hp, hl, rp, rl, op_, ol, dd, n, vox, cout, gate_ptr, nbk, opp, sf, sh, st), name + ".residual"))
+                out.stats = (opart, nbk, None, 0)
             return out
 
         # ---- init conv
@@ -329,21 +375,19 @@ class UnetEngine:
                         lib.diqt_scale_copy(sp_, sl, dp_, dl, dd, rows, c, skip_scale, st), "skip_scale"))
                 nxt = next_out(l + 1, dims[l + 1])
                 conv = u.downs[l][4][1]
-                opart = self.part[self._pp]
                 ops.append(self._conv_site(f"downs.{l}.4.1", L.CONV_DOWN, l, c, x.ld, dims[l + 1], nxt.ld, conv.weight, conv.bias, x.ptr, nxt.ptr,
-                                           stats=opart))
-                if self._last_conv_stats_nblk:
-                    nxt.stats = (opart, self._last_conv_stats_nblk)
+                                           stats=self._pp))
+                if self._last_conv_stats:
+                    nxt.stats = self._last_conv_stats
                     self._pp ^= 1
                 x = nxt
             else:
                 conv = u.downs[l][4]
                 nxt = next_out(l, dims[l + 1])
-                opart = self.part[self._pp]
                 ops.append(self._conv_site(f"downs.{l}.4", L.CONV_K1, l, c, x.ld, dims[l + 1], nxt.ld, conv.weight, conv.bias, x.ptr, nxt.ptr,
-                                           stats=opart))
-                if self._last_conv_stats_nblk:
-                    nxt.stats = (opart, self._last_conv_stats_nblk)
+                                           stats=self._pp))
+                if self._last_conv_stats:
+                    nxt.stats = self._last_conv_stats
                     self._pp ^= 1
                 x = nxt
 

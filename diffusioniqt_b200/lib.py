@@ -46,6 +46,11 @@ _SIGNATURES = {
     "diqt_affine_mish": [_vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _vp, _i, _i, _i, _vp],
     "diqt_se_gate": [_vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp],
     "diqt_scale_residual": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _i, _vp, _i, _i, _vp],
+    "diqt_stats_groups": [_i, _i, C.POINTER(C.c_int)],
+    "diqt_conv_plan_set_stats_g": [_vp, _vp, _vp, _vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "diqt_channel_stats_g": [_vp, _i, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "diqt_gn_mish_g": [_vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _i, _i, _f, _vp, _vp, _vp, _i, _vp, _i, _i, _vp],
+    "diqt_scale_residual_g": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp],
     "diqt_scale_copy": [_vp, _i, _vp, _i, _i, _i64, _i, _f, _vp],
     "diqt_init_conv_pack": [_vp, _i, _i, _vp, _vp],
     "diqt_init_conv": [C.POINTER(_vp), C.POINTER(_i64), _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],

@@ -34,9 +34,11 @@ def from_channels_last(x: torch.Tensor) -> torch.Tensor:
     return x.permute(0, 4, 1, 2, 3).contiguous().float()
 
 
-def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], mode: str = "k3", impl: str = "auto", with_stats: bool = False):
+def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], mode: str = "k3", impl: str = "auto", with_stats: bool = False,
+           grouped: bool = False):
     """x: (n, d0, d1, d2, c_in) bf16/fp32 on CUDA; weight/bias exactly as in the reference state_dict (fp32).
-    with_stats=True also returns the fused per-block channel statistics (n, nblk, c_out, 2) or None if the kernel cannot fuse them."""
+    with_stats=True also returns the fused per-block channel statistics (n, nblk, c_out, 2) or None if the kernel cannot fuse them;
+    with grouped=True the statistics are (partial rows, group sums (n, ngroups, c_out, 2)) through the grouped sink."""
     lib = L.load()
     n, d0, d1, d2, c_in = x.shape
     x = x.contiguous()
@@ -71,9 +73,17 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         if with_stats:
             buf = torch.full((n * 320 * c_out * 2,), float("nan"), dtype=torch.float32, device=x.device)
             nb = C.c_int(0)
-            L.check(lib.diqt_conv_plan_set_stats(plan.value, buf.data_ptr(), C.byref(nb)), "conv_set_stats")
-            if nb.value > 0:
-                stats = buf[: n * nb.value * c_out * 2].view(n, nb.value, c_out, 2)
+            if grouped:
+                gbuf = torch.full((n * 16 * c_out * 2,), float("nan"), dtype=torch.float32, device=x.device)
+                tick = torch.zeros(16, dtype=torch.int32, device=x.device)
+                ng = C.c_int(0)
+                L.check(lib.diqt_conv_plan_set_stats_g(plan.value, buf.data_ptr(), gbuf.data_ptr(), tick.data_ptr(), C.byref(nb), C.byref(ng)), "conv_set_stats_g")
+                if nb.value > 0:
+                    stats = (buf[: n * nb.value * c_out * 2].view(n, nb.value, c_out, 2), gbuf[: n * ng.value * c_out * 2].view(n, ng.value, c_out, 2))
+            else:
+                L.check(lib.diqt_conv_plan_set_stats(plan.value, buf.data_ptr(), C.byref(nb)), "conv_set_stats")
+                if nb.value > 0:
+                    stats = buf[: n * nb.value * c_out * 2].view(n, nb.value, c_out, 2)
         L.check(lib.diqt_conv_run(plan.value, st), "conv_run")
         torch.cuda.current_stream().synchronize()
     finally:
@@ -91,11 +101,40 @@ def channel_stats(x: torch.Tensor, nblk: int = 8) -> torch.Tensor:
     return part
 
 
-def group_norm_film_mish(x: torch.Tensor, groups: int, gamma, beta, scale_shift: Optional[torch.Tensor] = None, eps: float = 1e-5, nblk: int = 8):
-    """GroupNorm(groups) -> [x*(scale+1)+shift] -> Mish.  scale_shift: (n, 2c) fp32 rows (scale | shift) or None."""
+def channel_stats_grouped(x: torch.Tensor, nblk: int = 8):
+    """-> (partial (n, nblk, c, 2), group sums (n, ngroups, c, 2)) through the grouped sink of include/diqt.h."""
     lib = L.load()
     n, c = x.shape[0], x.shape[-1]
     vox = x.numel() // (n * c)
+    ng = C.c_int(0)
+    L.check(lib.diqt_stats_groups(nblk, 1, C.byref(ng)), "stats_groups")
+    part = torch.empty(n, nblk, c, 2, dtype=torch.float32, device=x.device)
+    grp = torch.full((n, ng.value, c, 2), float("nan"), dtype=torch.float32, device=x.device)
+    tick = torch.zeros(n * ng.value, dtype=torch.int32, device=x.device)
+    L.check(lib.diqt_channel_stats_g(x.data_ptr(), _dt(x), n, vox, c, c, nblk, part.data_ptr(), grp.data_ptr(), tick.data_ptr(),
+                                     L.current_stream()), "channel_stats_g")
+    torch.cuda.current_stream().synchronize()
+    assert int(tick.abs().sum()) == 0, "tickets must reset themselves"
+    return part, grp
+
+
+def group_norm_film_mish(x: torch.Tensor, groups: int, gamma, beta, scale_shift: Optional[torch.Tensor] = None, eps: float = 1e-5, nblk: int = 8,
+                         grouped: bool = False):
+    """GroupNorm(groups) -> [x*(scale+1)+shift] -> Mish.  scale_shift: (n, 2c) fp32 rows (scale | shift) or None.
+    grouped=True: statistics through the grouped sink and ONE kernel (finalisation in the prologue) instead of finalize + apply."""
+    lib = L.load()
+    n, c = x.shape[0], x.shape[-1]
+    vox = x.numel() // (n * c)
+    if grouped:
+        _, grp = channel_stats_grouped(x, nblk)
+        g = gamma.detach().float().contiguous().to(x.device)
+        be = beta.detach().float().contiguous().to(x.device)
+        film = scale_shift.detach().float().contiguous().to(x.device) if scale_shift is not None else None
+        y = torch.empty_like(x)
+        L.check(lib.diqt_gn_mish_g(x.data_ptr(), c, y.data_ptr(), c, _dt(x), n, vox, c, grp.data_ptr(), grp.shape[1], groups, eps, g.data_ptr(),
+                                   be.data_ptr(), L.ptr(film), 2 * c, 0, 1, nblk, L.current_stream()), "gn_mish_g")
+        torch.cuda.current_stream().synchronize()
+        return y
     part = channel_stats(x, nblk)
     a = torch.empty(n, c, dtype=torch.float32, device=x.device)
     b = torch.empty_like(a)
@@ -111,12 +150,26 @@ def group_norm_film_mish(x: torch.Tensor, groups: int, gamma, beta, scale_shift:
     return y
 
 
-def se_scale_residual(h: torch.Tensor, res: torch.Tensor, w1, w2, nblk: int = 8):
-    """SE3D gate on h, then h*gate + res.  Returns (out, gate, partial stats of out)."""
+def se_scale_residual(h: torch.Tensor, res: torch.Tensor, w1, w2, nblk: int = 8, grouped: bool = False):
+    """SE3D gate on h, then h*gate + res.  Returns (out, gate, partial stats of out); grouped=True computes the gate in the
+    residual kernel's prologue from grouped statistics and returns (out, None, group sums of out)."""
     lib = L.load()
     n, c = h.shape[0], h.shape[-1]
     vox = h.numel() // (n * c)
     st = L.current_stream()
+    if grouped:
+        _, grp = channel_stats_grouped(h, nblk)
+        w1 = w1.detach().float().contiguous().to(h.device)
+        w2 = w2.detach().float().contiguous().to(h.device)
+        out = torch.empty_like(h)
+        opart = torch.empty(n, nblk, c, 2, dtype=torch.float32, device=h.device)
+        ogrp = torch.full((n, grp.shape[1], c, 2), float("nan"), dtype=torch.float32, device=h.device)
+        tick = torch.zeros(n * grp.shape[1], dtype=torch.int32, device=h.device)
+        L.check(lib.diqt_scale_residual_g(h.data_ptr(), c, res.data_ptr(), c, out.data_ptr(), c, _dt(h), n, vox, c, grp.data_ptr(), grp.shape[1],
+                                          w1.shape[0], w1.data_ptr(), w2.data_ptr(), nblk, opart.data_ptr(), ogrp.data_ptr(), tick.data_ptr(), st),
+                "scale_residual_g")
+        torch.cuda.current_stream().synchronize()
+        return out, None, ogrp
     part = channel_stats(h, nblk)
     gate = torch.empty(n, c, dtype=torch.float32, device=h.device)
     w1 = w1.detach().float().contiguous().to(h.device)

@@ -137,6 +137,31 @@ int diqt_scale_residual(const void* h, int ld_h, const void* res, int ld_res, vo
                         int n, int64_t voxels, int c, const float* gate, int nblk, float* partial, int sub_f, int sub_h,
                         void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Grouped statistics: the same GroupNorm / FiLM / Mish / SE / residual arithmetic without the two
+ * single-CTA finalisation kernels (diqt_gn_finalize, diqt_se_gate).  A producer given a "sink" also reduces its partial rows in
+ * groups of consecutive rows (the last CTA of a group to finish sums that group, fixed order) into
+ * group[n][ngroups][c][2], ngroups <= 16; the consumer folds the finalisation into its own prologue.
+ * tickets: DEVICE uint32 [n * ngroups] (convs: [ngroups]), zero before first use, self-resetting.
+ * Single-launch semantics are identical to the un-grouped calls; plain volumes only (no sub-volume geometry).
+ * ------------------------------------------------------------------------------------------ */
+/* ngroups a producer with `nblk` partial rows and `rows_per_cta` rows per CTA (conv z-march: 2, everything else: 1) will write */
+int diqt_stats_groups(int nblk, int rows_per_cta, int* ngroups);
+/* like diqt_conv_plan_set_stats, plus the grouped sink; *ngroups = 0 (and *nblk = 0) if the plan cannot fuse statistics */
+int diqt_conv_plan_set_stats_g(diqt_conv_plan* plan, float* partial, float* group, uint32_t* tickets, int* nblk, int* ngroups);
+int diqt_channel_stats_g(const void* x, int dtype, int n, int64_t voxels, int c, int ld, int nblk, float* partial,
+                         float* group, uint32_t* tickets, void* stream);
+/* y = mish(GroupNorm(groups, eps, gamma, beta)(x) [* (scale + 1) + shift]) with the statistics of x taken from `group`
+ * (nn.GroupNorm :546, FiLM :559-561, nn.Mish :547); film arguments as in diqt_gn_finalize */
+int diqt_gn_mish_g(const void* x, int ld_x, void* y, int ld_y, int dtype, int n, int64_t voxels, int c, const float* group,
+                   int ngroups, int groups, float eps, const float* gamma, const float* beta, const float* film, int film_ld,
+                   const int32_t* film_row, int film_row_stride_n, int nblk, void* stream);
+/* out = h * SE(h) + res (SE3D :617-632 from the grouped statistics of h; se_group NULL = no gate), plus the statistics of out:
+ * partial rows [n][nblk][c][2] and, if group_out != NULL, their grouped reduction */
+int diqt_scale_residual_g(const void* h, int ld_h, const void* res, int ld_res, void* out, int ld_out, int dtype, int n,
+                          int64_t voxels, int c, const float* se_group, int se_ngroups, int hidden, const float* w1,
+                          const float* w2, int nblk, float* partial, float* group_out, uint32_t* tickets, void* stream);
+
 /* dst[r][0..c) = src[r][0..c) * scale over `rows` pitched rows: the scaled skip connection
  * (scale_skip_connection, :1346, :1653) when it cannot be a pure view */
 int diqt_scale_copy(const void* src, int ld_src, void* dst, int ld_dst, int dtype, int64_t rows, int c, float scale,

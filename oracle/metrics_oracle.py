@@ -12,20 +12,23 @@ import torch
 import torch.nn.functional as F
 
 
-def _minmax(x):
-    return (x - x.min()) / (x.max() - x.min())
+def _minmax(x, rng=None):
+    lo, hi = (x.min(), x.max()) if rng is None else rng
+    return (x - lo) / (hi - lo)
 
 
-def psnr(pred: torch.Tensor, target: torch.Tensor) -> float:
-    p, t = _minmax(pred.double()), _minmax(target.double())
+def psnr(pred: torch.Tensor, target: torch.Tensor, rng=None) -> float:
+    """metrics.py:17-21.  rng=None: each volume is scaled by its OWN min / max, as the reference does.  rng=(lo, hi): both
+    volumes are scaled by the same fixed range (used by tests that must not hinge on one extreme voxel)."""
+    p, t = _minmax(pred.double(), rng), _minmax(target.double(), rng)
     mse = torch.mean((p - t) ** 2)
     return float(10.0 * torch.log10(1.0 / mse))
 
 
-def ssim3d(pred: torch.Tensor, target: torch.Tensor, kernel_size: int = 11, sigma: float = 1.5, normalise: bool = True) -> float:
+def ssim3d(pred: torch.Tensor, target: torch.Tensor, kernel_size: int = 11, sigma: float = 1.5, normalise: bool = True, rng=None) -> float:
     p, t = pred.double(), target.double()
     if normalise:
-        p, t = _minmax(p), _minmax(t)
+        p, t = _minmax(p, rng), _minmax(t, rng)
     p, t = p[None, None], t[None, None]
     g = torch.arange(kernel_size, dtype=torch.float64) - (kernel_size - 1) / 2
     g = torch.exp(-(g ** 2) / (2 * sigma ** 2))

@@ -172,7 +172,8 @@ def test_conv_tcgen05_matches_simt_closely():
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
 @pytest.mark.parametrize("n,dims,c,groups,film", [(1, (8, 8, 8), 64, 8, True), (2, (4, 6, 10), 96, 8, False), (3, (2, 2, 2), 128, 8, True),
                                                    (1, (16, 16, 16), 192, 8, True)])
-def test_group_norm_film_mish(dtype, tol, n, dims, c, groups, film):
+@pytest.mark.parametrize("grouped", [False, True])
+def test_group_norm_film_mish(dtype, tol, n, dims, c, groups, film, grouped):
     from diffusioniqt_b200 import ops
     x = (_rand(n, c, *dims, seed=9) * 1.7 + 0.4)
     if dtype == torch.bfloat16:
@@ -184,12 +185,13 @@ def test_group_norm_film_mish(dtype, tol, n, dims, c, groups, film):
         sc, sh = ss[:, :c, None, None, None], ss[:, c:, None, None, None]
         want = want * (sc + 1) + sh
     want = F.mish(want)
-    got = ops.group_norm_film_mish(ops.to_channels_last(x.cuda(), dtype), groups, gamma, beta, ss.cuda() if film else None, nblk=5)
+    got = ops.group_norm_film_mish(ops.to_channels_last(x.cuda(), dtype), groups, gamma, beta, ss.cuda() if film else None, nblk=5, grouped=grouped)
     assert max_rel(ops.from_channels_last(got).cpu(), want) < tol
 
 
+@pytest.mark.parametrize("grouped", [False, True])
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
-def test_se_scale_residual(dtype, tol):
+def test_se_scale_residual(dtype, tol, grouped):
     from diffusioniqt_b200 import ops
     n, c, dims = 2, 64, (6, 4, 8)
     h, r = _rand(n, c, *dims, seed=13), _rand(n, c, *dims, seed=14)
@@ -198,14 +200,43 @@ def test_se_scale_residual(dtype, tol):
     w1, w2 = _rand(c // 16, c, seed=15, scale=0.3), _rand(c, c // 16, seed=16, scale=0.8)
     y = torch.sigmoid(F.linear(torch.relu(F.linear(h.mean(dim=(2, 3, 4)), w1)), w2))
     want = h * y[:, :, None, None, None] + r
-    out, gate, part = ops.se_scale_residual(ops.to_channels_last(h.cuda(), dtype), ops.to_channels_last(r.cuda(), dtype), w1, w2, nblk=7)
-    assert max_rel(gate.cpu(), y) < 1e-5
+    out, gate, part = ops.se_scale_residual(ops.to_channels_last(h.cuda(), dtype), ops.to_channels_last(r.cuda(), dtype), w1, w2, nblk=37 if grouped else 7,
+                                            grouped=grouped)
+    if not grouped:
+        assert max_rel(gate.cpu(), y) < 1e-5
     assert max_rel(ops.from_channels_last(out).cpu(), want) < tol
     # the fused statistics describe the stored output
     stored = ops.from_channels_last(out).cpu()
     s = part.sum(dim=1).cpu()
     assert max_rel(s[..., 0], stored.sum(dim=(2, 3, 4))) < 1e-4
     assert max_rel(s[..., 1], (stored ** 2).sum(dim=(2, 3, 4))) < 1e-4
+
+
+def test_grouped_statistics_sum_to_the_partial_rows():
+    """Group rows are sums of consecutive partial rows (fixed order); several group sizes incl. a ragged last group; tickets reset."""
+    from diffusioniqt_b200 import ops
+    x = ops.to_channels_last(_rand(2, 64, 8, 8, 8, seed=18).cuda(), torch.bfloat16)
+    for nblk in (1, 7, 16, 37, 148):
+        part, grp = ops.channel_stats_grouped(x, nblk)
+        assert not torch.isnan(grp).any() and grp.shape[1] <= 16
+        assert max_rel(grp.sum(dim=1).cpu(), part.sum(dim=1).cpu()) < 1e-6
+        part2, grp2 = ops.channel_stats_grouped(x, nblk)
+        assert torch.equal(grp, grp2)
+
+
+def test_conv_grouped_statistics():
+    """conv epilogue statistics through the grouped sink (z-march: two rows per CTA; per-tap kernel: one)."""
+    import ctypes as C
+    from diffusioniqt_b200 import lib as L, ops
+    for impl, dims, cin, cout in (("zm", (16, 16, 16), 64, 128), ("zm", (64, 64, 64), 64, 64), ("tc", (8, 8, 8), 128, 128)):
+        x = ops.to_channels_last(_rand(1, cin, *dims, seed=27).cuda(), torch.bfloat16)
+        w, b = _conv_weight("k3", cin, cout, 28)
+        got, stats = ops.conv3d(x, w, b, mode="k3", impl=impl, with_stats=True, grouped=True)
+        part, grp = stats
+        assert grp.shape[1] <= 16 and not torch.isnan(grp).any()
+        assert max_rel(grp.sum(dim=1).cpu(), part.sum(dim=1).cpu()) < 1e-6
+        stored = ops.from_channels_last(got).cpu()
+        assert max_rel(grp.sum(dim=1)[..., 0].cpu(), stored.sum(dim=(2, 3, 4))) < 2e-4
 
 
 def test_channel_stats_is_deterministic():

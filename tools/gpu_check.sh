@@ -10,11 +10,13 @@ tail -5 $OUT/pytest_$TAG.log
 timeout 150 python __graft_entry__.py --smoke > $OUT/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -3 $OUT/smoke_$TAG.log
 timeout 240 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "bench rc=$?"; cat $OUT/bench_$TAG.json
 if [ -z "${SKIP_NCU:-}" ]; then
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/launches_$TAG.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 1200 --csv --log-file $OUT/launches_$TAG.csv \
   python bench.py --timesteps 3 --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_launch_$TAG.log 2>&1; echo "ncu launches rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_zm_kernel -s 3 -c 2 -f -o $OUT/prof_zm_$TAG \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_zm_kernel -s 39 -c 39 -f -o $OUT/prof_zm_$TAG \
   python bench.py --timesteps 2 --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_zm_$TAG.log 2>&1; echo "ncu zm rc=$?"
+if [ -n "${NCU_TC:-}" ]; then
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 28 -c 28 -f -o $OUT/prof_tc_$TAG \
   python bench.py --timesteps 2 --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_tc_$TAG.log 2>&1; echo "ncu tc rc=$?"
+fi
 fi
 ls -la $OUT
