@@ -96,13 +96,14 @@ class UnetEngine:
         self._keep.append(t)
         return t
 
-    def _conv_site(self, name, mode, level_in, c_in, ld_in, c_out, ld_out, weight, bias, src_ptr, dst_ptr, stats=None):
+    def _conv_site(self, name, mode, level_in, c_in, ld_in, c_out, ld_out, weight, bias, src_ptr, dst_ptr, stats=None, vol=None, impl=None):
         """Pack weights, create the plan, return the launch closure.  With `stats` (index of a statistics scratch set) the conv
-        is asked to emit the channel statistics of its output; if it cannot, a separate stats pass is appended by the caller."""
-        d0, d1, d2 = self.conv_dims[level_in]
+        is asked to emit the channel statistics of its output; if it cannot, a separate stats pass is appended by the caller.
+        `vol` = (n, d0, d1, d2) overrides the level geometry (token volumes of the attention blocks)."""
+        cn, (d0, d1, d2) = (self.conv_n, self.conv_dims[level_in]) if vol is None else (vol[0], vol[1:])
         if self.sub_f > 1:
             stats = None   # fused conv statistics are per conv volume; boundary mode needs them per sub-volume
-        desc = L.ConvDesc(mode=mode, dtype=self.ddtype, impl=self.impl, n=self.conv_n, d0=d0, d1=d1, d2=d2,
+        desc = L.ConvDesc(mode=mode, dtype=self.ddtype, impl=self.impl if impl is None else impl, n=cn, d0=d0, d1=d1, d2=d2,
                           c_in=c_in, ld_in=ld_in, c_out=c_out, ld_out=ld_out, flags=0)
         impl = C.c_int(0)
         L.check(self.lib.diqt_conv_resolved_impl(C.byref(desc), C.byref(impl)), f"conv {name}")
@@ -361,11 +362,17 @@ class UnetEngine:
             level_blocks = [(u.downs[l][1], f"downs.{l}.1")] + [(b, f"downs.{l}.3.{i}") for i, b in enumerate(u.downs[l][3])]
             for j, (blk, name) in enumerate(level_blocks):
                 last_of_level = j == len(level_blocks) - 1
-                if last_of_level and l != nl - 1 and skip_scale == 1.0:
-                    out = Act(self.cat[l], c, dims[l + 1] + c, offset=dims[l + 1])  # write the skip straight into the concat buffer
+
+                def level_out():
+                    if last_of_level and l != nl - 1 and skip_scale == 1.0:
+                        return Act(self.cat[l], c, dims[l + 1] + c, offset=dims[l + 1])  # write the skip straight into the concat buffer
+                    return next_out(l, c)
+
+                if j == 0 and u.downs[l][2] is not None:      # :1610-1622: x = attn(merge(x)) split again, x += res
+                    x = add_resblock(blk, x, l, next_out(l, c), name)
+                    x = self._add_attention(u.downs[l][2], x, l, level_out(), f"downs.{l}.2", outer_residual=True)
                 else:
-                    out = next_out(l, c)
-                x = add_resblock(blk, x, l, out, name)
+                    x = add_resblock(blk, x, l, level_out(), name)
             if l != nl - 1:
                 if skip_scale != 1.0:
                     dst = Act(self.cat[l], c, dims[l + 1] + c, offset=dims[l + 1])
@@ -393,6 +400,8 @@ class UnetEngine:
 
         level = nl - 1
         if u.deep_feature:
+            if u.mid_attn is not None:                        # :1635-1646: no residual around mid_attn
+                x = self._add_attention(u.mid_attn, x, level, next_out(level, dims[-1]), "mid_attn", outer_residual=False)
             x = add_resblock(u.mid_block, x, level, next_out(level, dims[-1]), "mid_block")
 
         # ---- up path
@@ -425,6 +434,188 @@ class UnetEngine:
         self.film_b = self._f32(torch.cat([b.to(self.device) for b in self._film_b], dim=0))
         self.film = None
         torch.cuda.current_stream().synchronize()
+
+    # ------------------------------------------------------------------ attention blocks
+    def _add_attention(self, mod, x: Act, level: int, out: Act, name: str, outer_residual: bool) -> Act:
+        """Append the launches of one attention block (imagen_pytorch3D.py:1610-1622 / 1635-1646) reading `x`, writing `out`.
+
+        The reference merges the f^3 sub-volumes (utils_mine.py:44-67), runs the block on the merged volume and splits again.
+        Here only the two kernels at the edges translate rows (`xmap`); in boundary mode the activations already live merged.
+        1x1x1 convolutions run through the conv families (tcgen05 when the channel counts are multiples of 64), everything
+        else through csrc/attn.cu."""
+        lib, ops, dd, n, u = self.lib, self._ops, self.ddtype, self.n, self.unet
+        f = int(u.batch_sample_factor)
+        h = self.level_dims[level][0]
+        if n != f ** 3 or len(set(self.level_dims[level])) != 1:
+            # utils_mine.py:57-59 "The batch size must be the product of split dimensions"
+            raise ValueError(f"{name}: attention needs batch == batch_sample_factor^3 = {f ** 3} cubic sub-volumes, got batch {n}, dims {self.level_dims[level]}")
+        G, p, cdim = f * h, int(mod.patch_size), int(mod.dim)
+        if h % p != 0:
+            raise ValueError(f"{name}: sub-volume side {h} is not a multiple of the attention patch size {p}")
+        g = G // p
+        N = g ** 3
+        rows = n * self.level_vox[level]
+        assert x.c == cdim and out.c == cdim, (name, x.c, out.c, cdim)
+        xmap = (0, 0) if self.sub_f > 1 or f == 1 else (f, h)
+        heads, dh = int(mod.heads), int(mod.dim_head)
+        inner = heads * dh
+        impl = L.IMPL_SIMT if self.dtype == "fp32" else L.IMPL_AUTO
+        tok_vol = (1, g, g, g)
+
+        def buf(r, c):
+            t = self._empty(r, c)
+            self._keep.append(t)
+            return Act(t, c, c)
+
+        def dw_weight(conv):
+            w = conv.weight.detach().to(device=self.device, dtype=torch.float32)
+            return self._f32(w.reshape(w.shape[0], -1).t().contiguous())
+
+        def opt_f32(t):
+            return self._f32(t) if t is not None else None
+
+        def ln(src: Act, dst: Act, r, gain, beta=None, eps=1e-5, pre_act=0, res1=None, res2=None, merged_src=False, what="ln"):
+            gp, bp = self._f32(gain.reshape(-1)).data_ptr(), L.ptr(opt_f32(beta))
+            sp, sl, dp, dl, c = src.ptr, src.ld, dst.ptr, dst.ld, src.c
+            r1p, r1l = (res1.ptr, res1.ld) if res1 is not None else (0, 0)
+            r2p, r2l = (res2.ptr, res2.ld) if res2 is not None else (0, 0)
+            sf, sh = xmap if merged_src else (0, 0)
+            ops.append(lambda st: L.check(lib.diqt_chan_layernorm(sp, sl, dp, dl, dd, r, c, gp, bp, eps, pre_act, r1p, r1l, r2p, r2l, sf, sh, st),
+                                          f"{name}.{what}"))
+
+        def combine(a: Act, dst: Act, r, act=0, b=None, c2=None, what="add"):
+            ap, al, dp, dl, c = a.ptr, a.ld, dst.ptr, dst.ld, a.c
+            bp, bl = (b.ptr, b.ld) if b is not None else (0, 0)
+            cp, cl = (c2.ptr, c2.ld) if c2 is not None else (0, 0)
+            ops.append(lambda st: L.check(lib.diqt_rows_combine(ap, al, act, bp, bl, cp, cl, dp, dl, dd, r, c, st), f"{name}.{what}"))
+
+        def conv1(src: Act, dst: Act, weight, bias, what, vol=None, c_out=None):
+            co = c_out if c_out is not None else dst.c
+            w = weight.detach().reshape(co, src.c, 1, 1, 1)
+            ops.append(self._conv_site(f"{name}.{what}", L.CONV_K1, level, src.c, src.ld, co, dst.ld, w, bias, src.ptr, dst.ptr, vol=vol, impl=impl))
+
+        def dwconv3(src: Act, dst: Act, conv, side, what):
+            wp, bp = dw_weight(conv).data_ptr(), L.ptr(opt_f32(conv.bias))
+            sp, sl, dp, dl, c = src.ptr, src.ld, dst.ptr, dst.ld, src.c
+            ops.append(lambda st: L.check(lib.diqt_dw_conv3(sp, sl, dp, dl, dd, side, side, side, c, wp, bp, st), f"{name}.{what}"))
+
+        def patchify(src: Act, dst: Act, conv, what):
+            wp, bp = dw_weight(conv).data_ptr(), L.ptr(opt_f32(conv.bias))
+            sp, sl, dp, dl = src.ptr, src.ld, dst.ptr, dst.ld
+            ops.append(lambda st: L.check(lib.diqt_dw_patchify(sp, sl, dp, dl, dd, g, p, cdim, wp, bp, xmap[0], xmap[1], st), f"{name}.{what}"))
+
+        def upsample(src: Act, dst: Act, what):
+            sp, sl, dp, dl = src.ptr, src.ld, dst.ptr, dst.ld
+            ops.append(lambda st: L.check(lib.diqt_upsample_trilinear(sp, sl, dp, dl, dd, g, p, cdim, st), f"{name}.{what}"))
+
+        esz = 2 if self.dtype == "bf16" else 4
+        F0, F1, F2 = buf(rows, cdim), buf(rows, cdim), buf(rows, cdim)
+        T0, T1, T2, T3 = buf(N, cdim), buf(N, cdim), buf(N, cdim), buf(N, cdim)
+        QKV0, QKV, O = buf(N, 3 * inner), buf(N, 3 * inner), buf(N, inner)
+        q_ptr, k_ptr, v_ptr, ldq = QKV.ptr, QKV.ptr + inner * esz, QKV.ptr + 2 * inner * esz, 3 * inner
+        scale = float(dh) ** -0.5
+
+        if mod.kind == "vit":
+            # ---- ViT3D.forward :905-910
+            pe = mod.patch_embedding
+            patchify(x, T0, pe.projection[0].depthwise, "patch_embedding.depthwise")
+            conv1(T0, T1, pe.projection[0].pointwise.weight, pe.projection[0].pointwise.bias, "patch_embedding.pointwise", vol=tok_vol)
+            if tuple(pe.positions.shape) != (N, cdim):
+                raise ValueError(f"{name}: position table {tuple(pe.positions.shape)} does not match {N} tokens x {cdim} (img_size / patch_size of the constructor)")
+            pos_t = pe.positions.detach().to(device=self.device, dtype=self.tdtype).contiguous()
+            self._keep.append(pos_t)
+            tok = buf(N, cdim)
+            combine(T1, tok, N, b=Act(pos_t, cdim, cdim), what="positions")
+            hid = cdim * int(mod.expansion)
+            U0, U1 = buf(N, hid), buf(N, hid)
+            for i, layer in enumerate(mod.transformer_encoder.layers):
+                ln_a, mha = layer.block[0].fn[0], layer.block[0].fn[1]
+                ln(tok, T2, N, ln_a.weight, ln_a.bias, eps=float(ln_a.eps), what=f"layers.{i}.ln1")
+                # 'b n (h d qkv) -> qkv b h n d' (:824): permute the rows of the projection so that q | k | v come out as blocks
+                wq = mha.qkv.weight.detach().reshape(heads, dh, 3, cdim).permute(2, 0, 1, 3).reshape(3 * inner, cdim)
+                bq = mha.qkv.bias.detach().reshape(heads, dh, 3).permute(2, 0, 1).reshape(3 * inner)
+                conv1(T2, QKV, wq, bq, f"layers.{i}.qkv", vol=tok_vol, c_out=3 * inner)
+                op_, ol = O.ptr, O.ld
+                ops.append(lambda st, op_=op_, ol=ol, i=i: L.check(lib.diqt_softmax_attention(q_ptr, k_ptr, v_ptr, ldq, ldq, ldq, op_, ol, dd, N, heads, dh, scale, 0, st),
+                                                                   f"{name}.layers.{i}.mha"))
+                conv1(O, T3, mha.projection.weight, mha.projection.bias, f"layers.{i}.projection", vol=tok_vol)
+                tok2 = buf(N, cdim)
+                combine(T3, tok2, N, b=tok, what=f"layers.{i}.res1")
+                ln_f, ffb = layer.block[1].fn[0], layer.block[1].fn[1]
+                ln(tok2, T2, N, ln_f.weight, ln_f.bias, eps=float(ln_f.eps), what=f"layers.{i}.ln2")
+                if ffb.local:
+                    conv1(T2, U0, ffb.up_proj[1].weight, ffb.up_proj[1].bias, f"layers.{i}.up_proj", vol=tok_vol)
+                    combine(U0, U1, N, act=1, what=f"layers.{i}.up_mish")
+                    dwconv3(U1, U0, ffb.depth_conv[0].depthwise, g, f"layers.{i}.depth_conv.depthwise")
+                    conv1(U0, U1, ffb.depth_conv[0].pointwise.weight, ffb.depth_conv[0].pointwise.bias, f"layers.{i}.depth_conv.pointwise", vol=tok_vol)
+                    combine(U1, U0, N, act=1, what=f"layers.{i}.depth_mish")
+                    conv1(U0, T3, ffb.down_proj[0].weight, ffb.down_proj[0].bias, f"layers.{i}.down_proj", vol=tok_vol)
+                else:
+                    conv1(T2, U0, ffb.net[0].weight, ffb.net[0].bias, f"layers.{i}.ff0", vol=tok_vol)
+                    combine(U0, U1, N, act=1, what=f"layers.{i}.ff_mish")
+                    conv1(U1, T3, ffb.net[3].weight, ffb.net[3].bias, f"layers.{i}.ff1", vol=tok_vol)
+                tok = buf(N, cdim)
+                combine(T3, tok, N, b=tok2, what=f"layers.{i}.res2")
+            rec = mod.reconstruction
+            ln(tok, T2, N, rec[0].weight, rec[0].bias, eps=float(rec[0].eps), what="reconstruction.ln")
+            upsample(T2, F1, "reconstruction.upsample")
+            dwconv3(F1, F0, rec[3].depthwise, G, "reconstruction.depthwise")
+            conv1(F0, F1, rec[3].pointwise.weight, rec[3].pointwise.bias, "reconstruction.pointwise")
+            ln(F1, out, rows, rec[4].g, res1=x if outer_residual else None, merged_src=True, what="reconstruction.norm")
+            out.stats = None
+            return out
+
+        # ---- {Linear,SoftMax}AttentionTransformerBlock.forward :1146-1150 / :1181-1186
+        if mod.kind == "linear":
+            nch = C.c_int(0)
+            L.check(lib.diqt_linear_attention_chunks(N, C.byref(nch)), "linear_attention_chunks")
+            col_stat = torch.zeros(inner * 2, dtype=torch.float32, device=self.device)
+            ctx_part = torch.zeros(nch.value * heads * dh * dh, dtype=torch.float32, device=self.device)
+            self._keep += [col_stat, ctx_part]
+        depth = len(mod.layers)
+        hidden = mod.layers[0][1][1].weight.shape[0]
+        H0, H1 = buf(rows, hidden), buf(rows, hidden)
+        mid = buf(rows, cdim) if depth > 1 else None
+        xin = x
+        for i, (attn, ff) in enumerate(mod.layers):
+            last = i == depth - 1
+            lname = f"layers.{i}"
+            # Patchify :926-929 -> norm -> q, k, v (1x1x1 then depthwise 3x3x3, no biases) :961-977
+            ln(xin, F0, rows, attn.patch_embed.norm.g, what=f"{lname}.patch_embed.norm")
+            patchify(F0, T0, attn.patch_embed.projection.depthwise, f"{lname}.patch_embed.depthwise")
+            conv1(T0, T1, attn.patch_embed.projection.pointwise.weight, attn.patch_embed.projection.pointwise.bias, f"{lname}.patch_embed.pointwise", vol=tok_vol)
+            ln(T1, T2, N, attn.norm.g, what=f"{lname}.norm")
+            wqkv = torch.cat([attn.to_q[1].weight.detach(), attn.to_k[1].weight.detach(), attn.to_v[1].weight.detach()], dim=0)
+            conv1(T2, QKV0, wqkv, None, f"{lname}.to_qkv.1", vol=tok_vol, c_out=3 * inner)
+            wdw = torch.cat([attn.to_q[2].weight.detach(), attn.to_k[2].weight.detach(), attn.to_v[2].weight.detach()], dim=0)
+            wdw = self._f32(wdw.to(self.device, torch.float32).reshape(3 * inner, 27).t().contiguous())
+            wp, s0, s0l, d0p, d0l = wdw.data_ptr(), QKV0.ptr, QKV0.ld, QKV.ptr, QKV.ld
+            ops.append(lambda st, wp=wp, lname=lname: L.check(lib.diqt_dw_conv3(s0, s0l, d0p, d0l, dd, g, g, g, 3 * inner, wp, 0, st), f"{name}.{lname}.to_qkv.2"))
+            op_, ol = O.ptr, O.ld
+            if mod.kind == "linear":
+                csp, cpp = col_stat.data_ptr(), ctx_part.data_ptr()
+                ops.append(lambda st, lname=lname: L.check(lib.diqt_linear_attention(q_ptr, k_ptr, v_ptr, ldq, op_, ol, dd, N, heads, dh, scale, 1, csp, cpp, st),
+                                              f"{name}.{lname}.linear_attention"))
+            else:
+                ops.append(lambda st, lname=lname: L.check(lib.diqt_softmax_attention(q_ptr, k_ptr, v_ptr, ldq, ldq, ldq, op_, ol, dd, N, heads, dh, scale, 1, st),
+                                              f"{name}.{lname}.softmax_attention"))
+            conv1(O, T3, attn.to_out[0].weight, None, f"{lname}.to_out.0", vol=tok_vol)
+            ln(T3, T0, N, attn.to_out[1].g, what=f"{lname}.to_out.1")
+            # reconstruct :952-959, then "+ x" :1148
+            upsample(T0, F1, f"{lname}.reconstruct.upsample")
+            dwconv3(F1, F0, attn.reconstruct[1].depthwise, G, f"{lname}.reconstruct.depthwise")
+            conv1(F0, F1, attn.reconstruct[1].pointwise.weight, attn.reconstruct[1].pointwise.bias, f"{lname}.reconstruct.pointwise")
+            ln(F1, F2, rows, attn.reconstruct[2].g, res1=xin, merged_src=True, what=f"{lname}.reconstruct.norm")
+            # ChanFeedForward :1108-1116, then "+ x" :1149 (and the U-Net's own "x += res" :1622 after the last layer)
+            ln(F2, F0, rows, ff[0].g, what=f"{lname}.ff.0")
+            conv1(F0, H0, ff[1].weight, None, f"{lname}.ff.1")
+            ln(H0, H1, rows, ff[3].g, pre_act=2, what=f"{lname}.ff.3")
+            conv1(H1, F0, ff[4].weight, None, f"{lname}.ff.4")
+            dst = out if last else mid
+            combine(F0, dst, rows, b=F2, c2=x if (last and outer_residual) else None, what=f"{lname}.residual")
+            xin = dst
+        out.stats = None
+        return out
 
     # ------------------------------------------------------------------ conditioning
     def set_condition(self, log_snr: torch.Tensor, stream=None):

@@ -52,6 +52,14 @@ _SIGNATURES = {
     "diqt_gn_mish_g": [_vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _i, _i, _f, _vp, _vp, _vp, _i, _vp, _i, _i, _vp],
     "diqt_scale_residual_g": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp],
     "diqt_scale_copy": [_vp, _i, _vp, _i, _i, _i64, _i, _f, _vp],
+    "diqt_chan_layernorm": [_vp, _i, _vp, _i, _i, _i64, _i, _vp, _vp, _f, _i, _vp, _i, _vp, _i, _i, _i, _vp],
+    "diqt_rows_combine": [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i64, _i, _vp],
+    "diqt_dw_patchify": [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp],
+    "diqt_dw_conv3": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],
+    "diqt_upsample_trilinear": [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp],
+    "diqt_linear_attention_chunks": [_i, C.POINTER(C.c_int)],
+    "diqt_linear_attention": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp],
+    "diqt_softmax_attention": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _i, _vp],
     "diqt_init_conv_pack": [_vp, _i, _i, _vp, _vp],
     "diqt_init_conv": [C.POINTER(_vp), C.POINTER(_i64), _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "diqt_final_conv": [_vp, _i, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],

@@ -16,6 +16,8 @@ from typing import Optional
 import torch
 from torch import nn
 
+from .attention import make_attention
+
 
 def _cast_tuple(val, length=None):
     if isinstance(val, list):
@@ -185,8 +187,9 @@ class Unet(nn.Module):
             unsupported.append("pixel_shuffle_upsample=False (ConvTranspose3d upsampling)")
         if init_conv_to_final_conv_residual:
             unsupported.append("init_conv_to_final_conv_residual=True (channel mismatch in the reference itself)")
-        if any(attend_at_enc) or (deep_feature and attend_at_middle):
-            unsupported.append("attention blocks (attend_at_enc / attend_at_middle; off in both shipped configs)")
+        has_attn = any(attend_at_enc) or (deep_feature and attend_at_middle)
+        if has_attn and attn_dim_head not in (16, 32, 64):
+            unsupported.append(f"attention with attn_dim_head={attn_dim_head} (kernels take 16, 32 or 64)")
         if self_cond:
             unsupported.append("self_cond=True (the reference never widens init_conv for it, imagen_pytorch3D.py:1273-1286, so it cannot run there either)")
         if init_conv_kernel_size != 3:
@@ -197,6 +200,9 @@ class Unet(nn.Module):
             raise NotImplementedError("diffusioniqt_b200.Unet does not implement: " + "; ".join(unsupported))
 
         self.att_type = att_type
+        self.dim_head = attn_dim_head
+        self.att_localvit = att_localvit
+        self.att_forward_expansion = att_forward_expansion
         self.batch_sample = batch_sample
         self.img_size = img_size
         self.batch_sample_factor = batch_sample_factor
@@ -238,22 +244,35 @@ class Unet(nn.Module):
         self.downs = nn.ModuleList([])
         self.ups = nn.ModuleList([])
         skip_dims = []
+        # attention geometry (:1361, 1376-1379, 1412-1414): patch size 8 at the first level, halved per level (not after the last);
+        # img_size halves per level and only sizes the ViT position table
+        att_depth = _cast_tuple(attend_at_enc_depth, num_layers)
+        att_heads = _cast_tuple(attend_at_enc_heads, num_layers)
+        att_kw = dict(dim_head=attn_dim_head, ff_mult=att_forward_expansion, local=att_localvit)
+        patch_size, level_img = 8, img_size
         for ind, ((dim_in, dim_out), nblk, grp) in enumerate(zip(in_out, num_resnet_blocks, resnet_groups)):
             is_last = ind >= num_layers - 1
             if not is_last:
                 skip_dims.append(dim_in)
             post = Downsample(dim_in, dim_out) if not is_last else nn.Conv3d(dim_in, dim_out, 1)
+            attn = make_attention(att_type, dim_in, patch_size=patch_size, heads=att_heads[ind], img_size=level_img, depth=att_depth[ind],
+                                  **att_kw) if attend_at_enc[ind] else None
+            last_img = level_img
+            level_img //= 2
+            if not is_last:
+                patch_size //= 2
             self.downs.append(nn.ModuleList([
                 None,
                 ResnetBlock(dim_in, dim_in, groups=grp, use_se=use_se_attn, **rb),
-                None,
+                attn,
                 nn.ModuleList([ResnetBlock(dim_in, dim_in, groups=grp, use_se=use_se_attn, **rb) for _ in range(nblk)]),
                 post,
             ]))
 
         mid_dim = dims[-1]
         if deep_feature:
-            self.mid_attn = None
+            self.mid_attn = make_attention(att_type, mid_dim, patch_size=patch_size, heads=attend_at_middle_heads, img_size=last_img,
+                                           depth=attend_at_middle_depth, **att_kw) if attend_at_middle else None
         self.mid_block = ResnetBlock(mid_dim, mid_dim, groups=resnet_groups[-1], **rb)  # no SE (:1432-1434)
 
         for ind, ((dim_out, dim_in), nblk, grp) in enumerate(zip(reversed(in_out), reversed(num_resnet_blocks), reversed(resnet_groups))):

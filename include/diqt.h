@@ -168,6 +168,43 @@ int diqt_scale_copy(const void* src, int ld_src, void* dst, int ld_dst, int dtyp
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Attention blocks (attend_at_enc / attend_at_middle, imagen_pytorch3D.py:1392-1403, 1418-1430, 1610-1622, 1635-1646):
+ * LinearAttention :926-1016, SoftMaxAttention :1018-1106, ChanFeedForward :1108-1116, ViT3D :871-910.  The 1x1x1 convolutions
+ * inside them go through diqt_conv_* (DIQT_CONV_K1); these are the ops in between.  All take channels-last rows [row][ld].
+ * The reference runs attention on the f^3 sub-volumes merged into one volume (utils_mine.py:44-67): (x_sub_f, x_sub_h) with
+ * x_sub_f > 1 says "this operand is laid out as f^3 separate sub-volumes of side h" (or, for diqt_chan_layernorm, "x is merged
+ * while out / res are separate") and the kernel translates rows; 0 = no translation.
+ * act codes: 0 none, 1 Mish, 2 GELU (erf).
+ * ------------------------------------------------------------------------------------------ */
+/* out[r] = LayerNorm_c(act(x[r'])) * g (+ beta) (+ res1[r]) (+ res2[r]); biased variance, eps inside the sqrt (LayerNorm :361-382 with
+ * dim=-4, nn.LayerNorm :725, :731, :898).  x_sub_f > 1: x is in merged order, out / res1 / res2 in sub-volume order. */
+int diqt_chan_layernorm(const void* x, int ld_x, void* out, int ld_out, int dtype, int64_t rows, int c, const float* g,
+                        const float* beta, float eps, int pre_act, const void* res1, int ld_res1, const void* res2, int ld_res2,
+                        int x_sub_f, int x_sub_h, void* stream);
+/* out = act(a) (+ b) (+ c2), row-wise with pitches: residual adds :1148-1149, :1622, :756-757 and stand-alone activations */
+int diqt_rows_combine(const void* a, int ld_a, int act, const void* b, int ld_b, const void* c2, int ld_c, void* out, int ld_out,
+                      int dtype, int64_t rows, int c, void* stream);
+/* depthwise patch^3 / stride patch conv (Patchify :919, PatchEmbedding :847): tokens[(tz*g+ty)*g+tx][ch] over the merged volume of
+ * side g*patch.  w: fp32 [patch^3][c] (tap = (dz*patch+dy)*patch+dx), bias fp32 [c] or NULL.  x_sub_f > 1: x is in sub-volume order. */
+int diqt_dw_patchify(const void* x, int ld_x, void* tokens, int ld_t, int dtype, int grid_dim, int patch, int c, const float* w,
+                     const float* bias, int x_sub_f, int x_sub_h, void* stream);
+/* depthwise 3x3x3, padding 1, one volume (d0,d1,d2) (to_q/k/v.2 :963-975, reconstruct :955, depth_conv :787).  w: fp32 [27][c] */
+int diqt_dw_conv3(const void* x, int ld_x, void* out, int ld_out, int dtype, int d0, int d1, int d2, int c, const float* w,
+                  const float* bias, void* stream);
+/* nn.Upsample(scale_factor=factor, mode='trilinear', align_corners=True) (:900, :954) of a token volume g^3 -> (g*factor)^3 */
+int diqt_upsample_trilinear(const void* tokens, int ld_t, void* out, int ld_out, int dtype, int grid_dim, int factor, int c,
+                            void* stream);
+/* LinearAttention core (:1001-1011): out = act( (softmax_d(q) * scale) (softmax_n(k)^T v) ) per head; q, k, v: [tokens][ld_qkv] with
+ * channel = head*dim_head + d.  col_stat: fp32 scratch [heads*dim_head][2]; partial: fp32 scratch
+ * [chunks][heads][dim_head][dim_head] with chunks from diqt_linear_attention_chunks.  dim_head in {16, 32, 64}. */
+int diqt_linear_attention_chunks(int tokens, int* chunks);
+int diqt_linear_attention(const void* q, const void* k, const void* v, int ld_qkv, void* out, int ld_out, int dtype, int tokens,
+                          int heads, int dim_head, float scale, int act, float* col_stat, float* partial, void* stream);
+/* SoftMaxAttention / MultiHeadAttention core (:1087-1100, :826-836): out = act( softmax_k(q k^T * scale) v ) per head, online softmax */
+int diqt_softmax_attention(const void* q, const void* k, const void* v, int ld_q, int ld_k, int ld_v, void* out, int ld_out,
+                           int dtype, int tokens, int heads, int dim_head, float scale, int act, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Network ends.
  * ------------------------------------------------------------------------------------------ */
 /* init_conv (:1291, :1576): 3x3x3 conv over up to 8 single-channel fp32 planes (the channel

@@ -53,6 +53,25 @@ class UnetSpec:
     boundary: bool = False
     batch_sample_factor: int = 3
     init_conv_kernel_size: int = 3
+    # attention (imagen_pytorch3D.py:1392-1403, 1418-1430); off in both shipped configs
+    att_type: str = "vit"
+    attend_at_enc: Sequence[bool] | bool = False
+    attend_at_enc_depth: Sequence[int] | int = 1
+    attend_at_enc_heads: Sequence[int] | int = 8
+    attend_at_middle: bool = False
+    attend_at_middle_depth: int = 1
+    attend_at_middle_heads: int = 8
+    attn_dim_head: int = 64
+    att_localvit: bool = True
+
+    def patch_sizes(self):
+        """Patch size of the attention block at each encoder level and of the mid block (:1361, 1413-1414)."""
+        nl, ps, out = self.layers(), 8, []
+        for l in range(nl):
+            out.append(ps)
+            if l != nl - 1:
+                ps //= 2
+        return out, ps
 
     def layers(self) -> int:
         return len(tuple(self.dim_mults))
@@ -170,6 +189,19 @@ def pixel_shuffle3d(x: Tensor) -> Tensor:
     return x.reshape(B, C, D * 2, H * 2, W * 2)
 
 
+def attention_block(sd: Dict[str, Tensor], p: str, x: Tensor, spec: UnetSpec, *, depth: int, heads: int, patch_size: int) -> Tensor:
+    """merge the f^3 sub-volumes, run the attention block on the merged volume, split again (:1613-1617, 1638-1642)."""
+    from . import attn_oracle as A
+    f = spec.batch_sample_factor
+    v = merge_sub_volumes(x, f)
+    if spec.att_type == "vit":
+        v = A.vit3d(sd, p, v, depth=depth, heads=heads, dim_head=spec.attn_dim_head, patch_size=patch_size, local=spec.att_localvit)
+    else:
+        v = A.attention_transformer_block(sd, p, v, depth=depth, heads=heads, dim_head=spec.attn_dim_head, patch_size=patch_size,
+                                          kind="linear" if spec.att_type == "linear" else "softmax")
+    return split_sub_volumes(v, f)
+
+
 def time_embedding(sd: Dict[str, Tensor], time: Tensor) -> Tensor:
     """to_time_hiddens + to_time_cond (imagen_pytorch3D.py:518-533, 1305-1316, 1597-1599)."""
     w = sd["to_time_hiddens.0.weights"]
@@ -217,10 +249,20 @@ def unet_forward(sd: Dict[str, Tensor], spec: UnetSpec, x: Tensor, time: Tensor,
     t = time_embedding(sd, time)
     tap("time_cond", t)
 
+    # the reference indexes attend_at_enc[ind] (:1392): longer sequences than the level count are legal
+    att_enc = tuple(spec.attend_at_enc)[:nl] if isinstance(spec.attend_at_enc, (list, tuple)) else (spec.attend_at_enc,) * nl
+    att_depth = spec.per_layer(spec.attend_at_enc_depth)
+    att_heads = spec.per_layer(spec.attend_at_enc_heads)
+    enc_ps, mid_ps = spec.patch_sizes()
+
     hiddens = []
     for l in range(nl):                                                      # :1604-1631
         x = resnet_block(sd, f"downs.{l}.1.", x, t, groups[l], spec)
         tap(f"downs.{l}.1", x)
+        if att_enc[l]:                                                       # :1610-1622 (x += res)
+            a = attention_block(sd, f"downs.{l}.2.", x, spec, depth=att_depth[l], heads=att_heads[l], patch_size=enc_ps[l])
+            tap(f"downs.{l}.2", merge_sub_volumes(a, spec.batch_sample_factor))   # what a forward hook on the module sees
+            x = a + x
         for i in range(nblocks[l]):
             x = resnet_block(sd, f"downs.{l}.3.{i}.", x, t, groups[l], spec)
             tap(f"downs.{l}.3.{i}", x)
@@ -232,6 +274,10 @@ def unet_forward(sd: Dict[str, Tensor], spec: UnetSpec, x: Tensor, time: Tensor,
         tap(f"downs.{l}.4", x)
 
     if spec.deep_feature:                                                    # :1633-1651
+        if spec.attend_at_middle:                                            # :1635-1646 (no residual around mid_attn)
+            x = attention_block(sd, "mid_attn.", x, spec, depth=spec.attend_at_middle_depth, heads=spec.attend_at_middle_heads,
+                                patch_size=mid_ps)
+            tap("mid_attn", merge_sub_volumes(x, spec.batch_sample_factor))
         x = resnet_block(sd, "mid_block.", x, t, groups[-1], spec)
         tap("mid_block", x)
 

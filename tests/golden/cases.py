@@ -17,6 +17,15 @@ def _unet(dim, **kw):
     return base
 
 
+def _attn(att_type, **kw):
+    base = dict(att_type=att_type, attend_at_enc=(True, True, True), attend_at_enc_depth=(1, 2, 1), attend_at_enc_heads=(2, 4, 2),
+                attend_at_middle=True, attend_at_middle_depth=1, attend_at_middle_heads=2, attn_dim_head=16, att_forward_expansion=2,
+                att_drop=0.0, att_forward_drop=0.0, att_localvit=False, deep_feature=True, batch_sample=True, num_resnet_blocks=(1, 1, 1),
+                img_size=24)
+    base.update(kw)
+    return base
+
+
 # U-Net forward cases: {name: {unet kwargs, batch, size, seeds, log-SNR values, hooked submodules}}
 FORWARD_CASES = {
     # driver architecture (train.py:83-116) at a CPU-sized patch
@@ -34,6 +43,20 @@ FORWARD_CASES = {
     # different depth / width pattern and skip scaling
     "alt_dim32_s16": dict(unet=_unet(32, dim_mults=(1, 2), num_resnet_blocks=(1, 2), scale_skip_connection=True, init_dim=64),
                           batch=1, size=16, weight_seed=15, input_seed=25, log_snr=[-1.0], taps=()),
+    # ---- attention blocks (off in the shipped configs).  27 sub-volumes of 8^3 = one merged 24^3 volume; patch sizes
+    # 8 / 4 / 2 / 2 give 27 tokens at every level.  `img_size` is the merged side (it only sizes the ViT position table).
+    "attn_linear_dim32_s8": dict(unet=_unet(32, **_attn("linear")), batch=27, size=8, weight_seed=16, input_seed=26,
+                                 log_snr=[0.7] * 27, taps=("downs.0.2", "downs.1.2", "mid_attn")),
+    "attn_softmax_boundary_dim32_s8": dict(unet=_unet(32, **_attn("softmax", boundary=True)), batch=27, size=8, weight_seed=17, input_seed=27,
+                                           log_snr=[-0.5] * 27, taps=("downs.0.2", "mid_attn")),
+    "attn_vit_dim32_s8": dict(unet=_unet(32, **_attn("vit", att_localvit=False)), batch=27, size=8, weight_seed=18, input_seed=28,
+                              log_snr=[1.5] * 27, taps=("downs.0.2", "mid_attn")),
+    "attn_vitlocal_dim32_s8": dict(unet=_unet(32, **_attn("vit", att_localvit=True, attend_at_enc=(True, False, True))), batch=27, size=8,
+                                   weight_seed=19, input_seed=29, log_snr=[0.0] * 27, taps=("downs.2.2",)),
+    # channel counts that are multiples of 64 (tcgen05 1x1x1 convs in bf16), 2^3 sub-volumes of 32^3 -> 512 tokens, head dim 64
+    "attn_linear_dim64_f2_s32": dict(unet=_unet(64, **_attn("linear", batch_sample_factor=2, img_size=64, attn_dim_head=64, attend_at_enc_depth=(1, 1, 1),
+                                                            attend_at_enc_heads=(2, 2, 4), attend_at_enc=(True, False, True))),
+                                     batch=8, size=32, weight_seed=20, input_seed=30, log_snr=[0.9] * 8, taps=("downs.0.2",)),
 }
 
 # Full-sampler cases (Imagen.sample with injected noise)

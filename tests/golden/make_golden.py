@@ -65,10 +65,13 @@ def main():
     ref = ref_shim.load_reference()
 
     import json
+    only = set(sys.argv[1:])          # optional: regenerate just the named cases (the state_dict contract is always rewritten)
     contract = {}
     for name, case in FORWARD_CASES.items():
         unet = build_reference_unet(ref, case)
         contract[name] = [[k, list(v.shape)] for k, v in unet.state_dict().items()]
+        if only and name not in only:
+            continue
         x, lr, time = build_inputs(case)
         acts = {}
         hooks = []
@@ -89,6 +92,8 @@ def main():
         json.dump(contract, f)
 
     for name, case in SAMPLE_CASES.items():
+        if only and name not in only:
+            continue
         unet = build_reference_unet(ref, case)
         configs = make_configs(case)
         S, B, T = case["size"], case["batch"], case["timesteps"]

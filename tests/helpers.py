@@ -16,7 +16,8 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 _SPEC_KEYS = ("dim", "init_dim", "dim_mults", "num_resnet_blocks", "resnet_groups", "channels", "channels_out",
               "lowres_cond", "cond_images_channels", "self_cond", "learned_sinu_pos_emb_dim", "use_se_attn",
               "scale_skip_connection", "final_resnet_block", "deep_feature", "boundary", "batch_sample_factor",
-              "init_conv_kernel_size")
+              "init_conv_kernel_size", "att_type", "attend_at_enc", "attend_at_enc_depth", "attend_at_enc_heads", "attend_at_middle",
+              "attend_at_middle_depth", "attend_at_middle_heads", "attn_dim_head", "att_localvit")
 
 
 def spec_from_kwargs(kw) -> UnetSpec:

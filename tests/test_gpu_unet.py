@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from cases import FORWARD_CASES, build_inputs
+from cases import FORWARD_CASES, build_inputs, unet_kwargs_for_reference
 from helpers import load_golden, max_rel, oracle_forward, rel_err, weights_for
 
 pytestmark = pytest.mark.gpu
@@ -12,7 +12,7 @@ CASES = list(FORWARD_CASES)
 
 def _gpu_unet(case, dtype):
     from diffusioniqt_b200 import Unet
-    unet = Unet(**dict(case["unet"], img_size=case["size"]))
+    unet = Unet(**unet_kwargs_for_reference(case))
     unet.load_state_dict(weights_for(case))
     return unet.cuda().set_compute_dtype(dtype)
 

@@ -5,7 +5,7 @@ import os
 import pytest
 import torch
 
-from cases import FORWARD_CASES, MIN_BOUND
+from cases import FORWARD_CASES, MIN_BOUND, unet_kwargs_for_reference
 from helpers import GOLDEN_DIR
 from oracle import ddpm_oracle as do
 
@@ -14,7 +14,7 @@ from oracle import ddpm_oracle as do
 def test_state_dict_contract(name):
     from diffusioniqt_b200 import Unet
     contract = json.load(open(os.path.join(GOLDEN_DIR, "state_dict_contract.json")))[name]
-    kw = dict(FORWARD_CASES[name]["unet"], img_size=FORWARD_CASES[name]["size"])
+    kw = unet_kwargs_for_reference(FORWARD_CASES[name])
     got = [[k, list(v.shape)] for k, v in Unet(**kw).state_dict().items()]
     assert got == contract
 
@@ -35,7 +35,7 @@ def test_unsupported_options_raise():
     from diffusioniqt_b200 import Unet
     base = dict(dim=32, init_dim=32, dim_mults=(1, 2), channels=1, lowres_cond=True, init_cross_embed=False, attend_at_middle=False,
                 attend_at_enc=(False, False), deep_feature=False)
-    for bad in (dict(init_cross_embed=True), dict(memory_efficient=True), dict(pixel_shuffle_upsample=False), dict(attend_at_enc=(True, False)),
+    for bad in (dict(init_cross_embed=True), dict(memory_efficient=True), dict(pixel_shuffle_upsample=False), dict(attend_at_enc=(True, False), attn_dim_head=48),
                 dict(self_cond=True), dict(cross_embed_downsample=True)):
         with pytest.raises(NotImplementedError):
             Unet(**{**base, **bad})
