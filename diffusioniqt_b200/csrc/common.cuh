@@ -74,6 +74,11 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
   } while (0)
 
 // ---- 16-byte vector access over fp32 (4 lanes) or bf16 (8 lanes) ----------------------------
+// Loads go through ld.global.cg (L2 only), never the non-coherent path: a kernel launched with programmatic dependent launch is
+// resident (and its SM's L1 / read-only cache alive) while its predecessors are still writing the buffers it will read after
+// pdl_wait(); `const __restrict__` + plain dereference compiles to LDG.CONSTANT, whose lines are only guaranteed fresh for data that
+// is read-only over the whole lifetime of the grid -- which, with PDL, starts before the producer has finished.  Streaming data has
+// no L1 reuse anyway, so this costs nothing.
 template <typename T>
 struct Vec;
 
@@ -82,7 +87,7 @@ struct Vec<float> {
   static constexpr int N = 4;
   float v[4];
   __device__ __forceinline__ void load(const float* p) {
-    float4 t = *reinterpret_cast<const float4*>(p);
+    float4 t = __ldcg(reinterpret_cast<const float4*>(p));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
   __device__ __forceinline__ void store(float* p) const {
@@ -95,7 +100,7 @@ struct Vec<__nv_bfloat16> {
   static constexpr int N = 8;
   float v[8];
   __device__ __forceinline__ void load(const __nv_bfloat16* p) {
-    uint4 t = *reinterpret_cast<const uint4*>(p);
+    uint4 t = __ldcg(reinterpret_cast<const uint4*>(p));
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -222,7 +227,7 @@ __device__ __forceinline__ void gn_affine_from_groups(const GnParams& gp, int nv
   }
   __syncthreads();
   const float* fr = nullptr;
-  if (gp.film) fr = gp.film + (long long)((gp.film_row ? *gp.film_row : 0) + nv * gp.film_row_stride_n) * gp.film_ld;
+  if (gp.film) fr = gp.film + (long long)((gp.film_row ? __ldcg(gp.film_row) : 0) + nv * gp.film_row_stride_n) * gp.film_ld;
   for (int ch = tid; ch < gp.c; ch += nthreads) {
     const int g = ch / cpg;
     const float mean = (float)gstat[2 * g], rstd = (float)gstat[2 * g + 1];

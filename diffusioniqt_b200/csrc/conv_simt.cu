@@ -73,10 +73,10 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(SimtConvParams p) {
     if (ok) {
       const T* src = in + ((((int64_t)vb * p.id0 + iz) * p.id1 + iy) * p.id2 + ix) * p.ld_in + c0 + lq * 4;
       if constexpr (sizeof(T) == 4) {
-        const float4 v = *reinterpret_cast<const float4*>(src);
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(src));  // L2 only: see Vec<T>::load
         a_reg[0] = v.x; a_reg[1] = v.y; a_reg[2] = v.z; a_reg[3] = v.w;
       } else {
-        const uint2 v = *reinterpret_cast<const uint2*>(src);
+        const uint2 v = __ldcg(reinterpret_cast<const uint2*>(src));
         a_reg[0] = __uint_as_float(v.x << 16); a_reg[1] = __uint_as_float(v.x & 0xffff0000u);
         a_reg[2] = __uint_as_float(v.y << 16); a_reg[3] = __uint_as_float(v.y & 0xffff0000u);
       }

@@ -122,17 +122,17 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblk, 
     double s = 0.0, q = 0.0;
     int b = part;
     for (; b + 3 * parts < nblk; b += 4 * parts) {  // four independent loads in flight; summation order stays fixed
-      const float2 v0 = *reinterpret_cast<const float2*>(p + ((int64_t)b * c + ch) * 2);
-      const float2 v1 = *reinterpret_cast<const float2*>(p + ((int64_t)(b + parts) * c + ch) * 2);
-      const float2 v2 = *reinterpret_cast<const float2*>(p + ((int64_t)(b + 2 * parts) * c + ch) * 2);
-      const float2 v3 = *reinterpret_cast<const float2*>(p + ((int64_t)(b + 3 * parts) * c + ch) * 2);
+      const float2 v0 = __ldcg(reinterpret_cast<const float2*>(p + ((int64_t)b * c + ch) * 2));
+      const float2 v1 = __ldcg(reinterpret_cast<const float2*>(p + ((int64_t)(b + parts) * c + ch) * 2));
+      const float2 v2 = __ldcg(reinterpret_cast<const float2*>(p + ((int64_t)(b + 2 * parts) * c + ch) * 2));
+      const float2 v3 = __ldcg(reinterpret_cast<const float2*>(p + ((int64_t)(b + 3 * parts) * c + ch) * 2));
       s += (double)v0.x; q += (double)v0.y;
       s += (double)v1.x; q += (double)v1.y;
       s += (double)v2.x; q += (double)v2.y;
       s += (double)v3.x; q += (double)v3.y;
     }
     for (; b < nblk; b += parts) {
-      const float2 v = *reinterpret_cast<const float2*>(p + ((int64_t)b * c + ch) * 2);
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(p + ((int64_t)b * c + ch) * 2));
       s += (double)v.x; q += (double)v.y;
     }
     acc[(part * c + ch) * 2] = s;
@@ -166,7 +166,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblk, 
   __syncthreads();
   const float* fr = nullptr;
   if (film) {
-    const int row = (film_row ? *film_row : 0) + n * film_row_stride_n;
+    const int row = (film_row ? __ldcg(film_row) : 0) + n * film_row_stride_n;
     fr = film + (int64_t)row * film_ld;
   }
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
@@ -210,8 +210,8 @@ __global__ void affine_mish_kernel(const T* __restrict__ x, int ld_x, T* __restr
   } else {
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      av[i] = a[(int64_t)n * c + col * VEC + i];
-      bv[i] = b[(int64_t)n * c + col * VEC + i];
+      av[i] = __ldcg(a + (int64_t)n * c + col * VEC + i);  // written by the previous kernel (gn_finalize): L2 only, see Vec<T>::load
+      bv[i] = __ldcg(b + (int64_t)n * c + col * VEC + i);
     }
   }
   const T* xb = x + col * VEC;
@@ -254,11 +254,11 @@ __global__ void se_gate_kernel(const float* __restrict__ partial, int nblk, int6
     double s = 0.0;
     int b = part;
     for (; b + 3 * parts < nblk; b += 4 * parts) {
-      const float v0 = p[((int64_t)b * c + ch) * 2], v1 = p[((int64_t)(b + parts) * c + ch) * 2];
-      const float v2 = p[((int64_t)(b + 2 * parts) * c + ch) * 2], v3 = p[((int64_t)(b + 3 * parts) * c + ch) * 2];
+      const float v0 = __ldcg(p + ((int64_t)b * c + ch) * 2), v1 = __ldcg(p + ((int64_t)(b + parts) * c + ch) * 2);
+      const float v2 = __ldcg(p + ((int64_t)(b + 2 * parts) * c + ch) * 2), v3 = __ldcg(p + ((int64_t)(b + 3 * parts) * c + ch) * 2);
       s += (double)v0; s += (double)v1; s += (double)v2; s += (double)v3;
     }
-    for (; b < nblk; b += parts) s += (double)p[((int64_t)b * c + ch) * 2];
+    for (; b < nblk; b += parts) s += (double)__ldcg(p + ((int64_t)b * c + ch) * 2);
     acc[part * c + ch] = s;
   }
   __syncthreads();
@@ -330,7 +330,7 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
     __syncthreads();  // smem is reused by the block reduction below
   } else {
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) g[i] = gate ? gate[(int64_t)n * c + col * VEC + i] : 1.f;
+    for (int i = 0; i < VEC; ++i) g[i] = gate ? __ldcg(gate + (int64_t)n * c + col * VEC + i) : 1.f;
   }
 #pragma unroll
   for (int i = 0; i < VEC; ++i) s[i] = q[i] = 0.f;

@@ -181,7 +181,7 @@ struct StepConsts {
 };
 
 __device__ __forceinline__ StepConsts load_step(const float* __restrict__ sched, const int32_t* __restrict__ step) {
-  const float* r = sched + (int64_t)(step ? *step : 0) * 8;
+  const float* r = sched + (int64_t)(step ? __ldcg(step) : 0) * 8;
   StepConsts s;
   s.alpha = r[0]; s.sigma = r[1]; s.c = r[2]; s.alpha_next = r[3]; s.noise_scale = r[4]; s.lo = r[5]; s.hi = r[6];
   s.objective = (int)r[7];
@@ -209,7 +209,7 @@ struct EdmConsts {
   float s_noise, noise_k, c_in, c_skip, c_out, sigma, dt, half_dt, c_in_next, lo, hi;
 };
 __device__ __forceinline__ EdmConsts load_edm(const float* __restrict__ table, const int32_t* __restrict__ step) {
-  const float* r = table + (int64_t)(step ? *step : 0) * kEdmRow;
+  const float* r = table + (int64_t)(step ? __ldcg(step) : 0) * kEdmRow;
   EdmConsts e;
   e.s_noise = r[0]; e.noise_k = r[1]; e.c_in = r[2]; e.c_skip = r[3]; e.c_out = r[4]; e.sigma = r[5]; e.dt = r[6];
   e.half_dt = r[7]; e.c_in_next = r[8]; e.lo = r[9]; e.hi = r[10];

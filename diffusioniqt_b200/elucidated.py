@@ -235,15 +235,15 @@ class ElucidatedImagen(nn.Module):
         if eng.sub_f > 1:
             raise NotImplementedError("boundary mode with the Elucidated sampler")
 
-        key = (id(eng), tuple(hp), float(sigma_min), float(sigma_max), skip_steps or 0, bool(clamp), bool(dynamic_threshold), self.clamp_range)
-        st = self._samplers.get(key)
+        key = (tuple(hp), float(sigma_min), float(sigma_max), skip_steps or 0, bool(clamp), bool(dynamic_threshold), self.clamp_range)
+        st = eng.sampler_cache.get(key)
         if st is None:
             st = _EdmState()
             st.table, st.c_noise, st.sched, st.init_sigma = self._build_table(hp, sigma_min, sigma_max, skip_steps, clamp, dynamic_threshold)
             st.fwd = torch.zeros(1, dtype=torch.int32, device=device)
             for name in ("x", "x_hat", "slope", "x0", "eps"):
                 setattr(st, name, torch.empty(shape, dtype=torch.float32, device=device))
-            self._samplers[key] = st
+            eng.sampler_cache[key] = st
         inj = iter(self.noise_override) if self.noise_override is not None else None
 
         def draw(dst):

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Optional
 
 import torch
@@ -85,6 +86,8 @@ class UnetEngine:
         self.film_row_ptr = 0                 # device int32* (sampler step) or NULL
         self.film_stride_n = 1
         self.conv_impls = {}                  # site name -> resolved impl (for tests / reporting)
+        # sampler states (schedule tables, captured step graphs) that bake this engine's buffer addresses live and die with it
+        self.sampler_cache = {}
         self._build()
 
     # ------------------------------------------------------------------ helpers
@@ -184,7 +187,7 @@ class UnetEngine:
         self.part = [torch.zeros(pmax, dtype=torch.float32, device=self.device) for _ in range(3)]
         # grouped statistics (include/diqt.h): producers also reduce their partial rows in <= 16 groups and the consumers finalise
         # GroupNorm / SE in their own prologue, which removes ~57 single-CTA finalize launches per forward.  Plain small batches only.
-        self.grouped = self.sub_f <= 1 and n <= 2
+        self.grouped = self.sub_f <= 1 and n <= 2 and os.environ.get("DIQT_DISABLE_GROUPED", "0") != "1"   # variable: A/B and diagnostics
         self.grp = [torch.zeros(16 * n * cmax * 2, dtype=torch.float32, device=self.device) for _ in range(3)]
         self.tick = [torch.zeros(16 * n, dtype=torch.int32, device=self.device) for _ in range(3)]
         self.aff_a = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
@@ -679,6 +682,7 @@ class UnetEngine:
             self.lib.diqt_conv_plan_destroy(p)
         self._plans = []
         self._ops = []
+        self.sampler_cache = {}
 
     def __del__(self):
         try:

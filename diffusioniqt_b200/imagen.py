@@ -103,6 +103,9 @@ class GaussianDiffusionContinuousTimes(nn.Module):
 _OBJECTIVES = {"x_start": 0, "noise": 1, "v": 2}
 
 
+_DEBUG_SYNC = os.environ.get("DIQT_DEBUG_SYNC_REPLAY", "")   # diagnostics only: host sync before / after every graph replay
+
+
 class _SamplerState:
     """Device tables + captured graph of one (engine, schedule) pair."""
 
@@ -327,9 +330,10 @@ class Imagen(nn.Module):
         batch = shape[0]
         eng = unet.engine_for(batch, shape[2:], device)
 
-        key = (id(eng), id(noise_scheduler), noise_scheduler.num_timesteps, skip_steps or 0, pred_objective, bool(dynamic_threshold),
+        # cached on the engine (never keyed by id(): a rebuilt engine can reuse the address of a dead one while its buffers moved)
+        key = (noise_scheduler.log_snr.__name__, noise_scheduler.num_timesteps, skip_steps or 0, pred_objective, bool(dynamic_threshold),
                self._clamp_bounds())
-        st = self._samplers.get(key)
+        st = eng.sampler_cache.get(key)
         if st is None:
             st = _SamplerState()
             st.table, st.log_snr = self._build_schedule(noise_scheduler, skip_steps, pred_objective, device)
@@ -340,7 +344,7 @@ class Imagen(nn.Module):
             st.step = torch.zeros(1, dtype=torch.int32, device=device)
             st.noise = torch.empty(shape, dtype=torch.float32, device=device)
             st.x0 = torch.empty(shape, dtype=torch.float32, device=device)
-            self._samplers[key] = st
+            eng.sampler_cache[key] = st
         nsteps = st.steps
 
         inj = iter(self.noise_override) if self.noise_override is not None else None
@@ -399,7 +403,11 @@ class Imagen(nn.Module):
         for i in range(nsteps):
             draw(st.noise)                                                       # == torch.randn_like(x) of :2051, every step
             if use_graph:
+                if _DEBUG_SYNC in ("before", "both"):
+                    torch.cuda.synchronize(device)
                 st.graph.replay()
+                if _DEBUG_SYNC in ("after", "both"):
+                    torch.cuda.synchronize(device)
             else:
                 one_step(i)
             if self.keep_trajectory:

@@ -181,3 +181,92 @@ def se_scale_residual(h: torch.Tensor, res: torch.Tensor, w1, w2, nblk: int = 8,
                                     opart.data_ptr(), 0, 0, st), "scale_residual")
     torch.cuda.current_stream().synchronize()
     return out, gate, opart
+
+
+# ------------------------------------------------------------------ attention-block ops (csrc/attn.cu); rows = (rows, c) tensors
+
+def chan_layernorm(x, g, beta=None, eps=1e-5, pre_act=0, res1=None, res2=None, x_sub=(0, 0)):
+    """LayerNorm over the last dim of (rows, c) (imagen_pytorch3D.py:361-382); x_sub=(f, h): x rows are in merged order."""
+    lib = L.load()
+    rows, c = x.shape
+    out = torch.empty_like(x)
+    gf = g.detach().to(device=x.device, dtype=torch.float32).reshape(-1).contiguous()
+    bf = beta.detach().to(device=x.device, dtype=torch.float32).contiguous() if beta is not None else None
+    L.check(lib.diqt_chan_layernorm(x.data_ptr(), c, out.data_ptr(), c, _dt(x), rows, c, gf.data_ptr(), L.ptr(bf), float(eps), pre_act,
+                                    L.ptr(res1), c, L.ptr(res2), c, x_sub[0], x_sub[1], L.current_stream()), "chan_layernorm")
+    return out
+
+
+def rows_combine(a, act=0, b=None, c2=None):
+    lib = L.load()
+    rows, c = a.shape
+    out = torch.empty_like(a)
+    L.check(lib.diqt_rows_combine(a.data_ptr(), c, act, L.ptr(b), c, L.ptr(c2), c, out.data_ptr(), c, _dt(a), rows, c, L.current_stream()), "rows_combine")
+    return out
+
+
+def _dw_weight(w, device):
+    w = w.detach().to(device=device, dtype=torch.float32)
+    return w.reshape(w.shape[0], -1).t().contiguous()
+
+
+def dw_patchify(x, weight, bias, grid_dim, patch, x_sub=(0, 0)):
+    """x: (rows, c) voxels of the (grid_dim*patch)^3 volume (sub-volume order if x_sub=(f, h)); weight (c, 1, p, p, p)."""
+    lib = L.load()
+    c = x.shape[1]
+    out = torch.empty(grid_dim ** 3, c, dtype=x.dtype, device=x.device)
+    w = _dw_weight(weight, x.device)
+    b = bias.detach().to(device=x.device, dtype=torch.float32).contiguous() if bias is not None else None
+    L.check(lib.diqt_dw_patchify(x.data_ptr(), c, out.data_ptr(), c, _dt(x), grid_dim, patch, c, w.data_ptr(), L.ptr(b), x_sub[0], x_sub[1],
+                                 L.current_stream()), "dw_patchify")
+    return out
+
+
+def dw_conv3(x, weight, bias=None):
+    """x: (d0, d1, d2, c); weight (c, 1, 3, 3, 3): depthwise 3x3x3, zero padding 1."""
+    lib = L.load()
+    d0, d1, d2, c = x.shape
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    w = _dw_weight(weight, x.device)
+    b = bias.detach().to(device=x.device, dtype=torch.float32).contiguous() if bias is not None else None
+    L.check(lib.diqt_dw_conv3(x.data_ptr(), c, out.data_ptr(), c, _dt(x), d0, d1, d2, c, w.data_ptr(), L.ptr(b), L.current_stream()), "dw_conv3")
+    return out
+
+
+def upsample_trilinear(tokens, grid_dim, factor):
+    """tokens: (grid_dim^3, c) -> ((grid_dim*factor)^3, c), align_corners=True."""
+    lib = L.load()
+    c = tokens.shape[1]
+    G = grid_dim * factor
+    out = torch.empty(G ** 3, c, dtype=tokens.dtype, device=tokens.device)
+    L.check(lib.diqt_upsample_trilinear(tokens.data_ptr(), c, out.data_ptr(), c, _dt(tokens), grid_dim, factor, c, L.current_stream()), "upsample_trilinear")
+    return out
+
+
+def linear_attention(qkv, heads, dim_head, act=1):
+    """qkv: (tokens, 3*heads*dim_head) holding q | k | v blocks -> (tokens, heads*dim_head)   (imagen_pytorch3D.py:1001-1011)."""
+    lib = L.load()
+    n, inner = qkv.shape[0], heads * dim_head
+    esz = qkv.element_size()
+    out = torch.empty(n, inner, dtype=qkv.dtype, device=qkv.device)
+    chunks = C.c_int(0)
+    L.check(lib.diqt_linear_attention_chunks(n, C.byref(chunks)), "linear_attention_chunks")
+    stat = torch.empty(inner * 2, dtype=torch.float32, device=qkv.device)
+    part = torch.empty(chunks.value * heads * dim_head * dim_head, dtype=torch.float32, device=qkv.device)
+    p = qkv.data_ptr()
+    L.check(lib.diqt_linear_attention(p, p + inner * esz, p + 2 * inner * esz, 3 * inner, out.data_ptr(), inner, _dt(qkv), n, heads, dim_head,
+                                      float(dim_head) ** -0.5, act, stat.data_ptr(), part.data_ptr(), L.current_stream()), "linear_attention")
+    return out
+
+
+def softmax_attention(qkv, heads, dim_head, act=1):
+    """qkv: (tokens, 3*heads*dim_head) holding q | k | v blocks -> (tokens, heads*dim_head)   (imagen_pytorch3D.py:1087-1100)."""
+    lib = L.load()
+    n, inner = qkv.shape[0], heads * dim_head
+    esz = qkv.element_size()
+    out = torch.empty(n, inner, dtype=qkv.dtype, device=qkv.device)
+    p = qkv.data_ptr()
+    L.check(lib.diqt_softmax_attention(p, p + inner * esz, p + 2 * inner * esz, 3 * inner, 3 * inner, 3 * inner, out.data_ptr(), inner, _dt(qkv), n, heads,
+                                       dim_head, float(dim_head) ** -0.5, act, L.current_stream()), "softmax_attention")
+    return out

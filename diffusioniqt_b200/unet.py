@@ -348,9 +348,18 @@ class Unet(nn.Module):
         self.invalidate_engines()  # packed weight copies would be stale
         return super().load_state_dict(*args, **kwargs)
 
+    def _param_signature(self):
+        return tuple((p.data_ptr(), p.device, p.dtype, p._version) for p in self.parameters())
+
     def _apply(self, fn, *args, **kwargs):
-        self.invalidate_engines()
-        return super()._apply(fn, *args, **kwargs)
+        # `.to()` / `.cuda()` / `.float()` land here.  Engines hold packed copies of the weights, so they are dropped when a parameter
+        # really moved or changed -- and ONLY then: Imagen.sample calls `.to(device)` on every call (imagen_pytorch3D.py:1941-1962),
+        # which must not throw away the compiled engine and its captured CUDA graphs.
+        before = self._param_signature()
+        out = super()._apply(fn, *args, **kwargs)
+        if self._param_signature() != before:
+            self.invalidate_engines()
+        return out
 
     def engine_for(self, batch, dims, device):
         from .engine import UnetEngine

@@ -78,3 +78,51 @@ def test_stitched_volume_psnr_ssim(dtype, psnr_tol, ssim_tol):
     assert abs(mo.psnr(got, truth) - mo.psnr(want, truth)) < literal[0]
     assert abs(mo.ssim3d(got, truth) - mo.ssim3d(want, truth)) < literal[1]
     assert mo.psnr(got, want) > (60.0 if dtype == "fp32" else 30.0)
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_back_to_back_samples_are_reproducible(dtype):
+    """Samples queued back to back without host synchronisation (CUDA-graph replay, programmatic dependent launch inside the graph)
+    must not interfere with each other.  Every reduction has a fixed order, so repeats must be bit-identical."""
+    from diffusioniqt_b200 import Imagen, NullUnet, Unet
+    P, T = 16, 6
+    unet = Unet(**KW, img_size=P)
+    unet.load_state_dict(synthetic_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, seed=61))
+    imagen = Imagen(unets=(NullUnet(), unet), configs={"Data": {"norm": "z-score"}, "Train": {"batch_sample": False}}, image_sizes=(P, P),
+                    channels=1, min_bound=MIN_BOUND, timesteps=T, pred_objectives="x_start", dynamic_thresholding=False,
+                    cond_drop_prob=0.0).cuda()
+    imagen.unets[1].set_compute_dtype(dtype)
+    lrs = [synthetic_field((1, 1, P, P, P), 70 + i).cuda() for i in range(3)]
+    noises = [[t.cuda() for t in synthetic_noise((1, 1, P, P, P), T + 1, 80 + i)] for i in range(3)]
+    outs = []
+    for rep in range(8):                                   # 24 samples queued back to back, no host sync in between
+        for lr, nz in zip(lrs, noises):
+            imagen.noise_override = nz
+            outs.append(imagen.sample(batch_size=1, start_image_or_video=lr, start_at_unet_number=2, use_tqdm=False)[0])
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        assert torch.isfinite(o).all(), i
+        assert torch.equal(o, outs[i % 3]), f"sample {i} differs from its first run"
+
+
+def test_engine_and_graph_survive_repeated_sample_calls():
+    """One engine build + one graph capture serve every sample() call of a volume (regression: `.to(device)` inside sample() used to
+    drop the engine each call while the sampler cache, keyed by id(engine), could pair a dead engine's graph with the new buffers)."""
+    from diffusioniqt_b200 import Imagen, NullUnet, Unet
+    P, T = 16, 3
+    unet = Unet(**KW, img_size=P)
+    unet.load_state_dict(synthetic_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, seed=61))
+    imagen = Imagen(unets=(NullUnet(), unet), configs={"Data": {"norm": "z-score"}, "Train": {"batch_sample": False}}, image_sizes=(P, P),
+                    channels=1, min_bound=MIN_BOUND, timesteps=T, pred_objectives="x_start", dynamic_thresholding=False,
+                    cond_drop_prob=0.0).cuda()
+    lr = synthetic_field((1, 1, P, P, P), 70).cuda()
+    imagen.sample(batch_size=1, start_image_or_video=lr, start_at_unet_number=2, use_tqdm=False)
+    eng = next(iter(imagen.unets[1]._engines.values()))
+    st = next(iter(eng.sampler_cache.values()))
+    graph = st.graph
+    junk = [torch.empty(1 << 20, device="cuda") for _ in range(8)]        # perturb the allocator between calls
+    for _ in range(3):
+        imagen.sample(batch_size=1, start_image_or_video=lr, start_at_unet_number=2, use_tqdm=False)
+        junk.pop()
+    assert list(imagen.unets[1]._engines.values()) == [eng]
+    assert next(iter(eng.sampler_cache.values())) is st and st.graph is graph

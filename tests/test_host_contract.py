@@ -71,3 +71,29 @@ def test_schedule_table_matches_oracle(T, skip):
         assert abs(log_snr[i].item() - do.alpha_cosine_log_snr(tt).item()) < 1e-5
         assert lo == pytest.approx(MIN_BOUND) and hi == float("inf") and obj == 0
     assert table[-1, 4].item() == 0.0      # no noise on the last step (:2053-2054)
+
+
+def test_noop_moves_keep_engines_real_changes_drop_them():
+    """Imagen.sample calls `.to(device)` on every call (imagen_pytorch3D.py:1941-1962): a no-op move must not drop the compiled
+    engines (and the CUDA graphs cached on them); a real change of the parameters must."""
+    from diffusioniqt_b200 import Unet
+
+    class _Eng:
+        closed = False
+
+        def close(self):
+            self.closed = True
+
+    u = Unet(dim=32, init_dim=32, dim_mults=(1, 2), channels=1, lowres_cond=True, init_cross_embed=False, attend_at_middle=False,
+             attend_at_enc=(False, False), deep_feature=False)
+    e = _Eng()
+    u._engines["k"] = e
+    torch.nn.ModuleList([u]).to("cpu")
+    u.float()
+    assert u._engines == {"k": e} and not e.closed
+    u.double()
+    assert u._engines == {} and e.closed
+    e2 = _Eng()
+    u._engines["k"] = e2
+    u.load_state_dict(u.state_dict())
+    assert e2.closed and u._engines == {}
