@@ -8,5 +8,6 @@ is a drop-in for the reference's sampling path.  The arithmetic lives in libdiqt
 from .unet import Unet, Unet3D, SRUnet256, SRUnet1024, BaseUnet64, NullUnet  # noqa: F401
 from .imagen import Imagen, GaussianDiffusionContinuousTimes  # noqa: F401
 from .elucidated import ElucidatedImagen, Hparams  # noqa: F401
+from .trainer import ImagenTrainer  # noqa: F401
 
 __version__ = "0.1.0"

@@ -1,0 +1,239 @@
+"""Sampling-side mirror of the reference's `ImagenTrainer` (/root/reference/trainer.py:236-...): the caller
+that `test_all.py:166-172, 234` actually drives.  It accepts the reference's constructor keywords, restores the reference's
+checkpoint dictionary (`{'model', 'ema', 'steps', 'version', optim..}`, trainer.py:831-860) by name, samples with the EMA weights by
+default (`use_ema_unets`, trainer.py:982-1005), casts numpy / CPU arguments to the device (`cast_torch_tensor`, :123-147) and chunks
+a batch by `max_batch_size` (`imagen_sample_in_chunks`, :201-219).
+
+Training (optimisers, schedulers, accelerate, dataloaders: trainer.py:339-380, 543-760, 1099-1128) is outside the sampling hot path:
+the optimizer / scheduler keywords are accepted and ignored, optimizer state in a checkpoint is left alone, `forward` raises.
+"""
+from __future__ import annotations
+
+import os
+from contextlib import contextmanager
+from math import ceil
+
+import numpy as np
+import torch
+from torch import nn
+
+from .elucidated import ElucidatedImagen
+from .imagen import Imagen
+from .unet import NullUnet, Unet
+
+__version__ = "1.20.1"   # version.py of the reference; written into checkpoints so that the reference loads them silently
+
+
+def num_to_groups(num, divisor):
+    groups, remainder = num // divisor, num % divisor
+    return [divisor] * groups + ([remainder] if remainder > 0 else [])
+
+
+def restore_parts(state_dict_target, state_dict_from):
+    """trainer.py:222-233: copy the entries whose name and size match, report the rest."""
+    for name, param in state_dict_from.items():
+        if name not in state_dict_target:
+            continue
+        if param.size() == state_dict_target[name].size():
+            state_dict_target[name].copy_(param)
+        else:
+            print(f"layer {name}({param.size()} different than target: {state_dict_target[name].size()}")
+    return state_dict_target
+
+
+class _EMAHolder(nn.Module):
+    """Stand-in for `ema_pytorch.EMA` (pinned 0.1.4 in requirements.txt:40) with the same state_dict layout:
+    `online_model.*`, `ema_model.*`, `initted`, `step`.  Only `ema_model` matters for sampling."""
+
+    def __init__(self, unet):
+        super().__init__()
+        object.__setattr__(self, "_online", unet)          # not registered: the online weights live in imagen.unets
+        self.ema_model = _clone_unet(unet)
+        self.register_buffer("initted", torch.tensor([False]))
+        self.register_buffer("step", torch.tensor([0]))
+
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        sd = super().state_dict(*args, destination=destination, prefix=prefix, keep_vars=keep_vars)
+        for k, v in self._online.state_dict(keep_vars=keep_vars).items():       # ema_pytorch registers the online model too
+            sd[prefix + "online_model." + k] = v
+        return sd
+
+    def restore_ema_model_device(self):
+        pass
+
+
+def _clone_unet(unet):
+    if isinstance(unet, NullUnet):
+        return NullUnet()
+    new = unet.__class__(**unet._locals)
+    new.load_state_dict(unet.state_dict())
+    new.compute_dtype, new.conv_impl = unet.compute_dtype, unet.conv_impl
+    dev = next(unet.parameters()).device
+    return new.to(dev).eval()
+
+
+class ImagenTrainer(nn.Module):
+    """Drop-in for the sampling / checkpoint surface of `trainer.ImagenTrainer`."""
+
+    def __init__(self, configs=None, imagen=None, imagen_checkpoint_path=None, use_ema=True, lr=1e-4, eps=1e-8, beta1=0.9, beta2=0.99,
+                 max_grad_norm=None, group_wd_params=True, warmup_steps=None, cosine_decay_max_steps=None, only_train_unet_number=None,
+                 fp16=False, precision=None, split_batches=True,
+                 dl_tuple_output_keywords_names=('images', 'lowres_img', 'text_embeds', 'text_masks', 'cond_images'), verbose=True,
+                 split_valid_fraction=0.025, split_valid_from_train=False, split_random_seed=42, checkpoint_path=None, checkpoint_every=None,
+                 checkpoint_fs=None, fs_kwargs=None, max_checkpoints_keep=20, gradient_accumulation_steps=4, **kwargs):
+        super().__init__()
+        assert (imagen is not None) ^ (imagen_checkpoint_path is not None), \
+            'either imagen instance is passed into the trainer, or a checkpoint path that contains the imagen config'
+        if imagen is None:
+            raise NotImplementedError("building Imagen from a checkpoint's stored config (imagen_checkpoint_path) is a CLI feature outside the sampling path")
+        assert isinstance(imagen, (Imagen, ElucidatedImagen))
+        self.configs = configs
+        self.is_elucidated = isinstance(imagen, ElucidatedImagen)
+        self.imagen = imagen
+        self.num_unets = len(self.imagen.unets)
+        self.use_ema = bool(use_ema)
+        self.ema_unets = nn.ModuleList([_EMAHolder(u) for u in self.imagen.unets] if self.use_ema else [])
+        self.register_buffer('steps', torch.tensor([0] * self.num_unets))
+        self.verbose = verbose
+        self.only_train_unet_number = only_train_unet_number
+        self.checkpoint_path, self.checkpoint_every, self.max_checkpoints_keep = checkpoint_path, checkpoint_every, max_checkpoints_keep
+        self.to(self.device)
+
+    # ------------------------------------------------------------------ accelerator-shaped properties (single process)
+    @property
+    def device(self):
+        return self.imagen.device
+
+    is_distributed = False
+    is_main = True
+    is_local_main = True
+    can_checkpoint = True
+
+    def print(self, msg):
+        if self.verbose:
+            print(msg)
+
+    @property
+    def unets(self):
+        return nn.ModuleList([ema.ema_model for ema in self.ema_unets])
+
+    def num_steps_taken(self, unet_number=None):
+        if self.num_unets == 1:
+            unet_number = 1 if unet_number is None else unet_number
+        return int(self.steps[unet_number - 1].item())
+
+    def print_untrained_unets(self):
+        pass
+
+    # ------------------------------------------------------------------ checkpoints (trainer.py:816-945)
+    def save(self, path, overwrite=True, without_optim_and_sched=True, **kwargs):
+        path = str(path)
+        assert overwrite or not os.path.exists(path)
+        os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+        save_obj = dict(model=self.imagen.state_dict(), version=__version__, steps=self.steps.cpu(), **kwargs)
+        if self.use_ema:
+            save_obj['ema'] = self.ema_unets.state_dict()
+        torch.save(save_obj, path)
+        self.print(f'checkpoint saved to {path}')
+
+    def load(self, path, only_model=False, strict=True, noop_if_not_exist=False):
+        path = str(path)
+        if noop_if_not_exist and not os.path.exists(path):
+            self.print(f'trainer checkpoint not found at {path}')
+            return
+        assert os.path.exists(path), f'{path} does not exist'
+        loaded_obj = torch.load(path, map_location='cpu', weights_only=False)
+        if loaded_obj.get('version') != __version__:
+            self.print(f'loading saved imagen at version {loaded_obj.get("version")}, but current package version is {__version__}')
+        try:
+            self.imagen.load_state_dict(loaded_obj['model'], strict=strict)
+        except RuntimeError:
+            print("Failed loading state dict. Trying partial load")
+            self.imagen.load_state_dict(restore_parts(self.imagen.state_dict(), loaded_obj['model']))
+        if only_model:
+            return loaded_obj
+        if 'steps' in loaded_obj:
+            self.steps.copy_(loaded_obj['steps'])
+        if self.use_ema:
+            assert 'ema' in loaded_obj
+            # ema_pytorch keys: '<i>.ema_model.<param>', '<i>.online_model.<param>', '<i>.initted', '<i>.step'
+            for i, holder in enumerate(self.ema_unets):
+                prefix = f'{i}.ema_model.'
+                sd = {k[len(prefix):]: v for k, v in loaded_obj['ema'].items() if k.startswith(prefix)}
+                try:
+                    holder.ema_model.load_state_dict(sd, strict=strict)
+                except RuntimeError:
+                    print("Failed loading state dict. Trying partial load")
+                    holder.ema_model.load_state_dict(restore_parts(holder.ema_model.state_dict(), sd))
+                for name in ('initted', 'step'):
+                    if f'{i}.{name}' in loaded_obj['ema']:
+                        getattr(holder, name).copy_(loaded_obj['ema'][f'{i}.{name}'].reshape(getattr(holder, name).shape))
+            self.ema_unets.to(self.device)
+        self.print(f'checkpoint loaded from {path}')
+        return loaded_obj
+
+    # ------------------------------------------------------------------ sampling (trainer.py:982-1005, 1083-1097)
+    @contextmanager
+    def use_ema_unets(self):
+        if not self.use_ema:
+            yield
+            return
+        trainable = self.imagen.unets
+        self.imagen.unets = self.unets                 # swap in the exponential-moving-average weights
+        try:
+            yield
+        finally:
+            self.imagen.unets = trainable
+
+    @torch.no_grad()
+    def sample(self, *args, max_batch_size=None, use_non_ema=False, _device=None, _cast_device=True, **kwargs):
+        """`imagen.sample(*args, device=self.device, **kwargs)` with the EMA weights (unless use_non_ema), numpy / CPU tensors cast to
+        the device and the batch processed in chunks of `max_batch_size`.  Deviation: the reference's chunking only splits the
+        `batch_size` keyword for this (unconditional) model and would hand every chunk the full `start_image_or_video`; here the
+        batched tensor arguments are split along with it."""
+        device = _device if _device is not None else self.device
+
+        def cast(t):
+            if isinstance(t, np.ndarray):
+                t = torch.from_numpy(t)
+            if _cast_device and isinstance(t, torch.Tensor):
+                t = t.to(device)
+            return t
+
+        args = tuple(cast(a) for a in args)
+        kwargs = {k: cast(v) for k, v in kwargs.items()}
+        kwargs['use_tqdm'] = False
+        chunks = [kwargs]
+        batch_size = kwargs.get('batch_size', 1)
+        if max_batch_size is not None and batch_size > max_batch_size:
+            chunks, start = [], 0
+            for sub in num_to_groups(batch_size, max_batch_size):
+                kw = dict(kwargs, batch_size=sub)
+                for name in ('start_image_or_video', 'cond_images', 'init_images', 'video_frames'):
+                    v = kwargs.get(name)
+                    if isinstance(v, torch.Tensor) and v.shape[0] == batch_size:
+                        kw[name] = v[start:start + sub]
+                chunks.append(kw)
+                start += sub
+        context = self.use_ema_unets if not use_non_ema else _null
+        outputs = []
+        with context():
+            for kw in chunks:
+                outputs.append(self.imagen.sample(*args, device=device, **kw))
+        if len(outputs) == 1:
+            return outputs[0]
+        # (img, list_noisy, list_x0) per chunk: concatenate the images, join the host trajectories step by step
+        imgs = torch.cat([o[0] for o in outputs], dim=0)
+        trajs = []
+        for idx in (1, 2):
+            lists = [o[idx] for o in outputs]
+            trajs.append([np.concatenate(step, axis=0) for step in zip(*lists)] if all(len(l) == len(lists[0]) for l in lists) else lists)
+        return imgs, trajs[0], trajs[1]
+
+    def forward(self, *args, **kwargs):
+        raise NotImplementedError("training (ImagenTrainer.forward / update, trainer.py:1099-1128) is outside the sampling hot path this package implements")
+
+
+@contextmanager
+def _null():
+    yield
