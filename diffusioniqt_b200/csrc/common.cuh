@@ -39,6 +39,26 @@ bool pdl_enabled();  // DIQT_DISABLE_PDL=1 switches the attribute off (A/B measu
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Build-time variants for A/B measurements (tools/gpu_ab.sh):
+//   DIQT_PDL_LATE_TRIGGER=1  let the dependents launch only AFTER this kernel's own wait: at most two kernels of the chain are
+//                            resident at once (K+1 becomes resident when K-1 has completed), instead of an unbounded chain.
+//   DIQT_LOAD_NC=1           Vec<T>::load through the non-coherent path (LDG.CONSTANT) instead of ld.global.cg.
+#ifndef DIQT_PDL_LATE_TRIGGER
+#define DIQT_PDL_LATE_TRIGGER 0
+#endif
+#ifndef DIQT_LOAD_NC
+#define DIQT_LOAD_NC 0
+#endif
+__device__ __forceinline__ void pdl_sync() {
+#if DIQT_PDL_LATE_TRIGGER
+  pdl_wait();
+  pdl_launch_dependents();
+#else
+  pdl_launch_dependents();
+  pdl_wait();
+#endif
+}
+
 // `allow` = false launches the same kernel without the attribute (full stream serialisation): used for the first and last
 // kernels of a sampler step, which sit next to launches this library does not control (graph boundaries, torch kernels).
 template <bool kAllow = true, typename... KArgs, typename... Args>
@@ -85,11 +105,17 @@ struct Vec;
 template <>
 struct Vec<float> {
   static constexpr int N = 4;
+  using Raw = float4;
   float v[4];
-  __device__ __forceinline__ void load(const float* p) {
-    float4 t = __ldcg(reinterpret_cast<const float4*>(p));
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  static __device__ __forceinline__ Raw load_raw(const float* p) {
+#if DIQT_LOAD_NC
+    return __ldg(reinterpret_cast<const float4*>(p));
+#else
+    return __ldcg(reinterpret_cast<const float4*>(p));
+#endif
   }
+  __device__ __forceinline__ void unpack(const Raw& t) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  __device__ __forceinline__ void load(const float* p) { unpack(load_raw(p)); }
   __device__ __forceinline__ void store(float* p) const {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
@@ -98,9 +124,16 @@ struct Vec<float> {
 template <>
 struct Vec<__nv_bfloat16> {
   static constexpr int N = 8;
+  using Raw = uint4;
   float v[8];
-  __device__ __forceinline__ void load(const __nv_bfloat16* p) {
-    uint4 t = __ldcg(reinterpret_cast<const uint4*>(p));
+  static __device__ __forceinline__ Raw load_raw(const __nv_bfloat16* p) {
+#if DIQT_LOAD_NC
+    return __ldg(reinterpret_cast<const uint4*>(p));
+#else
+    return __ldcg(reinterpret_cast<const uint4*>(p));
+#endif
+  }
+  __device__ __forceinline__ void unpack(const Raw& t) {
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -108,6 +141,7 @@ struct Vec<__nv_bfloat16> {
       v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
     }
   }
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { unpack(load_raw(p)); }
   __device__ __forceinline__ void store(__nv_bfloat16* p) const {
     uint32_t w[4];
 #pragma unroll
@@ -204,42 +238,102 @@ __device__ __forceinline__ void stats_group_total(const float* __restrict__ grou
   }
 }
 
+// Per-channel totals of volume nv from the group rows, by all `nthreads` threads of a CTA: `slices` threads per channel each sum a
+// contiguous run of group rows (independent loads, one L2 round trip), then one thread per channel adds the slices.  Fixed order at
+// both levels.  part: [slices][c][2] doubles with slices = max(1, nthreads / c); tot: [c][2] doubles.  Ends with a barrier.
+__device__ __forceinline__ void group_channel_totals(const float* __restrict__ group, int ngroups, int c, int nv, int tid, int nthreads,
+                                                     double* part, double* tot) {
+  const int slices = max(1, nthreads / c);
+  const int per = (ngroups + slices - 1) / slices;
+  const float* base = group + (size_t)nv * ngroups * c * 2;
+  for (int item = tid; item < slices * c; item += nthreads) {
+    const int ch = item % c, sl = item / c;
+    const int g0 = sl * per, g1 = min(ngroups, g0 + per);
+    double s = 0.0, q = 0.0;
+    for (int g = g0; g < g1; g += 4) {
+      float2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = (g + u < g1) ? __ldcg(reinterpret_cast<const float2*>(base + ((size_t)(g + u) * c + ch) * 2)) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { s += (double)v[u].x; q += (double)v[u].y; }
+    }
+    part[(sl * c + ch) * 2] = s;
+    part[(sl * c + ch) * 2 + 1] = q;
+  }
+  __syncthreads();
+  for (int ch = tid; ch < c; ch += nthreads) {
+    double s = 0.0, q = 0.0;
+    for (int sl = 0; sl < slices; ++sl) { s += part[(sl * c + ch) * 2]; q += part[(sl * c + ch) * 2 + 1]; }
+    tot[2 * ch] = s;
+    tot[2 * ch + 1] = q;
+  }
+  __syncthreads();
+}
+
 // GroupNorm(+FiLM) folded into y = a*x + b for every channel of volume nv, from grouped statistics, into shared a_s[c], b_s[c].
-// All `nthreads` threads of the CTA call this; scratch: 2*c doubles + 2*groups doubles.   (imagen_pytorch3D.py:546, :559-561)
+// All `nthreads` threads of the CTA call both halves.   (imagen_pytorch3D.py:546, :559-561)
 struct GnParams {
   const float* group; int ngroups; long long voxels; int c, groups; float eps;
   const float* gamma; const float* beta; const float* film; int film_ld; const int* film_row; int film_row_stride_n;
 };
-__device__ __forceinline__ void gn_affine_from_groups(const GnParams& gp, int nv, int tid, int nthreads, double* scratch, float* a_s, float* b_s) {
-  double* tot = scratch;
-  double* gstat = scratch + 2 * gp.c;
-  for (int ch = tid; ch < gp.c; ch += nthreads) stats_group_total(gp.group, gp.ngroups, gp.c, nv, ch, tot[2 * ch], tot[2 * ch + 1]);
-  __syncthreads();
-  const int cpg = gp.c / gp.groups;
-  for (int g = tid; g < gp.groups; g += nthreads) {
-    double s = 0.0, q = 0.0;
-    for (int i = 0; i < cpg; ++i) { s += tot[(g * cpg + i) * 2]; q += tot[(g * cpg + i) * 2 + 1]; }
-    const double cnt = (double)gp.voxels * cpg, mean = s / cnt;
-    double var = q / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    gstat[2 * g] = mean;
-    gstat[2 * g + 1] = 1.0 / sqrt(var + (double)gp.eps);
-  }
-  __syncthreads();
+// doubles: part[slices*c*2] + tot[c*2] + gstat[groups*2]; floats: a_s[c], b_s[c], cst[4c]
+__host__ __device__ inline size_t gn_scratch_bytes(int c, int groups, int nthreads) {
+  const int slices = nthreads / c > 0 ? nthreads / c : 1;
+  return ((size_t)slices * c * 2 + (size_t)c * 2 + (size_t)groups * 2) * sizeof(double) + (size_t)6 * c * sizeof(float);
+}
+struct GnScratch {
+  double *part, *tot, *gstat;
+  float *a_s, *b_s, *cst;
+};
+__device__ __forceinline__ GnScratch gn_scratch_layout(void* smem, int c, int groups, int nthreads) {
+  const int slices = max(1, nthreads / c);
+  GnScratch g;
+  g.part = reinterpret_cast<double*>(smem);
+  g.tot = g.part + (size_t)slices * c * 2;
+  g.gstat = g.tot + (size_t)c * 2;
+  g.a_s = reinterpret_cast<float*>(g.gstat + (size_t)groups * 2);
+  g.b_s = g.a_s + c;
+  g.cst = g.b_s + c;
+  return g;
+}
+// Half 1, BEFORE pdl_wait(): the constants (gamma, beta, FiLM row of this sampler step) go to shared memory while the producer kernel
+// is still draining.  Legal ahead of the wait: they were written before the first kernel of this forward, which is never launched with
+// the PDL attribute (engine: init_conv / edm_prepare), so it started only after they were complete.
+__device__ __forceinline__ void gn_prefetch_constants(const GnParams& gp, int nv, int tid, int nthreads, const GnScratch& sc) {
   const float* fr = nullptr;
   if (gp.film) fr = gp.film + (long long)((gp.film_row ? __ldcg(gp.film_row) : 0) + nv * gp.film_row_stride_n) * gp.film_ld;
   for (int ch = tid; ch < gp.c; ch += nthreads) {
+    sc.cst[ch] = gp.gamma[ch];
+    sc.cst[gp.c + ch] = gp.beta[ch];
+    sc.cst[2 * gp.c + ch] = fr ? fr[ch] + 1.f : 1.f;  // x * (scale + 1) + shift
+    sc.cst[3 * gp.c + ch] = fr ? fr[gp.c + ch] : 0.f;
+  }
+}
+// Half 2, after pdl_wait(): one L2 round trip for the group rows, then shared-memory arithmetic.
+__device__ __forceinline__ void gn_affine_from_groups(const GnParams& gp, int nv, int tid, int nthreads, const GnScratch& sc) {
+  group_channel_totals(gp.group, gp.ngroups, gp.c, nv, tid, nthreads, sc.part, sc.tot);
+  const int cpg = gp.c / gp.groups;
+  for (int g = tid; g < gp.groups; g += nthreads) {
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < cpg; ++i) { s += sc.tot[(g * cpg + i) * 2]; q += sc.tot[(g * cpg + i) * 2 + 1]; }
+    const double cnt = (double)gp.voxels * cpg, mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    sc.gstat[2 * g] = mean;
+    sc.gstat[2 * g + 1] = 1.0 / sqrt(var + (double)gp.eps);
+  }
+  __syncthreads();
+  for (int ch = tid; ch < gp.c; ch += nthreads) {
     const int g = ch / cpg;
-    const float mean = (float)gstat[2 * g], rstd = (float)gstat[2 * g + 1];
-    float a = rstd * gp.gamma[ch];
-    float b = gp.beta[ch] - mean * a;
-    if (fr) {  // x * (scale + 1) + shift
-      const float sc = fr[ch] + 1.f, sh = fr[gp.c + ch];
-      a *= sc;
-      b = fmaf(b, sc, sh);
-    }
-    a_s[ch] = a;
-    b_s[ch] = b;
+    const float mean = (float)sc.gstat[2 * g], rstd = (float)sc.gstat[2 * g + 1];
+    float a = rstd * sc.cst[ch];
+    float b = sc.cst[gp.c + ch] - mean * a;
+    const float fs = sc.cst[2 * gp.c + ch], fh = sc.cst[3 * gp.c + ch];
+    a *= fs;
+    b = fmaf(b, fs, fh);
+    sc.a_s[ch] = a;
+    sc.b_s[ch] = b;
   }
   __syncthreads();
 }

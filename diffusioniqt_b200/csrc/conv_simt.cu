@@ -37,8 +37,7 @@ __device__ __forceinline__ void tap_offset(int mode, int t, int& dz, int& dy, in
 
 template <typename T>
 __global__ void __launch_bounds__(256) conv_simt_kernel(SimtConvParams p) {
-  pdl_launch_dependents();
-  pdl_wait();
+  pdl_sync();
   __shared__ float As[2][BK][AS_LD];
   __shared__ float Bs[2][BK][BN];
   const int tid = threadIdx.x;

@@ -97,8 +97,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_launch_dependents();
-  pdl_wait();  // prologue above is private to this CTA; the previous kernel's activations are read only below
+  pdl_sync();  // prologue above is private to this CTA; the previous kernel's activations are read only below
 
   auto decode_tile = [&](int work, int& n_tile, int& x0, int& y0, int& z0, int& b0) {
     n_tile = work % p.n_tiles;

@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+#if !DIQT_PDL_LATE_TRIGGER
   pdl_launch_dependents();
+#endif
   // Everything above is private to this CTA.  Only the roles that touch activations / statistics of earlier kernels block in
   // pdl_wait(): the plane producer (reads the input) and the epilogue (writes the output and the statistics rows).  The weight
   // producer streams constant weights and runs ahead, so the first weight stages are already in flight when the predecessor
@@ -138,6 +140,9 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
     // ===================== input plane producer =====================
     if (lane == 0) {
       pdl_wait();
+#if DIQT_PDL_LATE_TRIGGER
+      pdl_launch_dependents();
+#endif
       int ring[2] = {0, 0};
       uint32_t phase[2] = {0, 0};
       for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {

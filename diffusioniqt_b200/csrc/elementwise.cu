@@ -16,6 +16,7 @@ struct SeParams {
   int ngroups, hidden;
   const float* w1;
   const float* w2;
+  int stage_w;  // 1: W1 / W2 are staged in shared memory ahead of the PDL wait (they fit), 0: read from global
 };
 
 // thread mapping shared by every kernel in this file:
@@ -67,8 +68,7 @@ __global__ void channel_stats_kernel(const T* __restrict__ x, int64_t voxels, in
   const int blk = blockIdx.x, n = blockIdx.y, nblk = gridDim.x;
   const int64_t v0 = (int64_t)blk * vpb;
   const int64_t v1 = min(voxels, v0 + vpb);
-  pdl_launch_dependents();
-  pdl_wait();
+  pdl_sync();
   const T* base = x + col * VEC;
   float s[VEC], q[VEC];
 #pragma unroll
@@ -109,8 +109,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblk, 
                                    const float* __restrict__ film, int film_ld, const int32_t* __restrict__ film_row,
                                    int film_row_stride_n, float* __restrict__ a_out, float* __restrict__ b_out) {
   extern __shared__ double sm[];  // acc[parts][c][2], tot[c][2], gstat[groups][2]
-  pdl_launch_dependents();
-  pdl_wait();
+  pdl_sync();
   const int n = blockIdx.x;
   const int parts = max(1, (int)blockDim.x / c);
   double* acc = sm;
@@ -186,28 +185,29 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nblk, 
 
 // ---- y = mish(a * x + b) -----------------------------------------------------------------------
 template <typename T, bool kFast>
-__global__ void affine_mish_kernel(const T* __restrict__ x, int ld_x, T* __restrict__ y, int ld_y, int64_t voxels,
-                                   int c, int nvec, int lanes, int64_t vpb, const float* __restrict__ a,
-                                   const float* __restrict__ b, SubGeom sg, GnParams gp) {
+__global__ void __launch_bounds__(256, 4) affine_mish_kernel(const T* __restrict__ x, int ld_x, T* __restrict__ y, int ld_y, int64_t voxels,
+                                                             int c, int nvec, int lanes, int64_t vpb, const float* __restrict__ a,
+                                                             const float* __restrict__ b, SubGeom sg, GnParams gp) {
   constexpr int VEC = Vec<T>::N;
-  extern __shared__ double gn_scratch[];  // grouped mode: 2c + 2 groups doubles, then a_s[c], b_s[c] floats
+  using Raw = typename Vec<T>::Raw;
+  extern __shared__ double gn_scratch[];  // grouped mode: gn_scratch_bytes()
   const int col = threadIdx.x % nvec, lane = threadIdx.x / nvec;
   const int n = blockIdx.y;
   const int64_t v0 = (int64_t)blockIdx.x * vpb;
   const int64_t v1 = min(voxels, v0 + vpb);
-  pdl_launch_dependents();
-  pdl_wait();
   float av[VEC], bv[VEC];
   if (gp.group) {  // GroupNorm (+FiLM) finalised here from the producer's grouped statistics: no separate finalize kernel
-    float* a_s = reinterpret_cast<float*>(gn_scratch + 2 * c + 2 * gp.groups);
-    float* b_s = a_s + c;
-    gn_affine_from_groups(gp, n, threadIdx.x, blockDim.x, gn_scratch, a_s, b_s);
+    const GnScratch sc = gn_scratch_layout(gn_scratch, c, gp.groups, blockDim.x);
+    gn_prefetch_constants(gp, n, threadIdx.x, blockDim.x, sc);  // overlaps the tail of the producer kernel
+    pdl_sync();
+    gn_affine_from_groups(gp, n, threadIdx.x, blockDim.x, sc);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      av[i] = a_s[col * VEC + i];
-      bv[i] = b_s[col * VEC + i];
+      av[i] = sc.a_s[col * VEC + i];
+      bv[i] = sc.b_s[col * VEC + i];
     }
   } else {
+    pdl_sync();
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
       av[i] = __ldcg(a + (int64_t)n * c + col * VEC + i);  // written by the previous kernel (gn_finalize): L2 only, see Vec<T>::load
@@ -217,23 +217,31 @@ __global__ void affine_mish_kernel(const T* __restrict__ x, int ld_x, T* __restr
   const T* xb = x + col * VEC;
   T* yb = y + col * VEC;
   int64_t v = v0 + lane;
+  // four 16-byte loads in flight per thread, kept packed until they are used (register budget: 4 CTAs of 256 threads per SM)
   for (; v + 3 * (int64_t)lanes < v1; v += 4 * (int64_t)lanes) {
-    Vec<T> r[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) r[u].load(xb + sub_row(sg, voxels, n, v + (int64_t)u * lanes) * ld_x);
+    Raw raw[4];
+    int64_t row[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
+      row[u] = sub_row(sg, voxels, n, v + (int64_t)u * lanes);
+      raw[u] = Vec<T>::load_raw(xb + row[u] * ld_x);
+    }
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) r[u].v[i] = mish<kFast>(fmaf(av[i], r[u].v[i], bv[i]));
-      r[u].store(yb + sub_row(sg, voxels, n, v + (int64_t)u * lanes) * ld_y);
+    for (int u = 0; u < 4; ++u) {
+      Vec<T> r;
+      r.unpack(raw[u]);
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) r.v[i] = mish<kFast>(fmaf(av[i], r.v[i], bv[i]));
+      r.store(yb + row[u] * ld_y);
     }
   }
   for (; v < v1; v += lanes) {
     Vec<T> r;
-    r.load(xb + sub_row(sg, voxels, n, v) * ld_x);
+    const int64_t row = sub_row(sg, voxels, n, v);
+    r.load(xb + row * ld_x);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) r.v[i] = mish<kFast>(fmaf(av[i], r.v[i], bv[i]));
-    r.store(yb + sub_row(sg, voxels, n, v) * ld_y);
+    r.store(yb + row * ld_y);
   }
 }
 
@@ -241,8 +249,7 @@ __global__ void affine_mish_kernel(const T* __restrict__ x, int ld_x, T* __restr
 __global__ void se_gate_kernel(const float* __restrict__ partial, int nblk, int64_t voxels, int c, int hidden,
                                const float* __restrict__ w1, const float* __restrict__ w2, float* __restrict__ gate) {
   extern __shared__ double sd[];  // acc[parts][c] doubles, then mean[c] + hid[hidden] floats
-  pdl_launch_dependents();
-  pdl_wait();
+  pdl_sync();
   const int n = blockIdx.x;
   const int parts = max(1, (int)blockDim.x / c);
   double* acc = sd;
@@ -296,24 +303,37 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
   const int blk = blockIdx.x, n = blockIdx.y, nblk = gridDim.x;
   const int64_t v0 = (int64_t)blk * vpb;
   const int64_t v1 = min(voxels, v0 + vpb);
-  pdl_launch_dependents();
-  pdl_wait();
+  using Raw = typename Vec<T>::Raw;
   float g[VEC], s[VEC], q[VEC];
   if (se.group) {
-    // squeeze-excitation gate (imagen_pytorch3D.py:617-632) from the grouped statistics of conv2's output, recomputed by every CTA
-    float* mean = smem;          // [c]
-    float* hid = smem + c;       // [hidden]
-    float* gs = hid + se.hidden; // [c]
-    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-      double sm, sq;
-      stats_group_total(se.group, se.ngroups, c, n, ch, sm, sq);
-      mean[ch] = (float)(sm / (double)voxels);
+    // squeeze-excitation gate (imagen_pytorch3D.py:617-632) from the grouped statistics of conv2's output, recomputed by every CTA.
+    // Shared layout (se_scratch_bytes): doubles part[slices*c*2], tot[c*2]; floats mean[c], hid[hidden], gs[c], w1[hidden*c], w2[c*hidden]
+    const int slices = max(1, (int)blockDim.x / c);
+    double* part = reinterpret_cast<double*>(smem);
+    double* tot = part + (size_t)slices * c * 2;
+    float* mean = reinterpret_cast<float*>(tot + (size_t)c * 2);
+    float* hid = mean + c;
+    float* gs = hid + se.hidden;
+    const float* w1s = se.w1;
+    const float* w2s = se.w2;
+    if (se.stage_w) {  // constant weights: staged ahead of the wait
+      float* s1 = gs + c;
+      float* s2 = s1 + (size_t)se.hidden * c;
+      for (int idx = threadIdx.x; idx < se.hidden * c; idx += blockDim.x) {
+        s1[idx] = se.w1[idx];
+        s2[idx] = se.w2[idx];
+      }
+      w1s = s1;
+      w2s = s2;
     }
+    pdl_sync();
+    group_channel_totals(se.group, se.ngroups, c, n, threadIdx.x, blockDim.x, part, tot);
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) mean[ch] = (float)(tot[2 * ch] / (double)voxels);
     __syncthreads();
     const int warp = threadIdx.x / 32, wl = threadIdx.x % 32, nwarps = blockDim.x / 32;
     for (int j = warp; j < se.hidden; j += nwarps) {
       float acc = 0.f;
-      for (int k = wl; k < c; k += 32) acc = fmaf(se.w1[(int64_t)j * c + k], mean[k], acc);
+      for (int k = wl; k < c; k += 32) acc = fmaf(w1s[(int64_t)j * c + k], mean[k], acc);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       if (wl == 0) hid[j] = fmaxf(acc, 0.f);
@@ -321,7 +341,7 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
     __syncthreads();
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
       float acc = 0.f;
-      for (int j = 0; j < se.hidden; ++j) acc = fmaf(se.w2[(int64_t)ch * se.hidden + j], hid[j], acc);
+      for (int j = 0; j < se.hidden; ++j) acc = fmaf(w2s[(int64_t)ch * se.hidden + j], hid[j], acc);
       gs[ch] = 1.f / (1.f + expf(-acc));
     }
     __syncthreads();
@@ -329,6 +349,7 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
     for (int i = 0; i < VEC; ++i) g[i] = gs[col * VEC + i];
     __syncthreads();  // smem is reused by the block reduction below
   } else {
+    pdl_sync();
 #pragma unroll
     for (int i = 0; i < VEC; ++i) g[i] = gate ? __ldcg(gate + (int64_t)n * c + col * VEC + i) : 1.f;
   }
@@ -337,41 +358,15 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
   const T* hb = h + col * VEC;
   const T* rb = res + col * VEC;
   T* ob = out + col * VEC;
-  int64_t v = v0 + lane;
-  for (; v + (int64_t)lanes < v1; v += 2 * (int64_t)lanes) {
-    Vec<T> a[2], r[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int64_t row = sub_row(sg, voxels, n, v + (int64_t)u * lanes);
-      a[u].load(hb + row * ld_h);
-      r[u].load(rb + row * ld_res);
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      Vec<T> o;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) o.v[i] = fmaf(a[u].v[i], g[i], r[u].v[i]);
-      o.store(ob + sub_row(sg, voxels, n, v + (int64_t)u * lanes) * ld_out);
-      if (partial) {
-        // statistics of what the next GroupNorm will actually read (the stored, rounded value)
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          const float w = to_float(from_float<T>(o.v[i]));
-          s[i] += w;
-          q[i] = fmaf(w, w, q[i]);
-        }
-      }
-    }
-  }
-  for (; v < v1; v += lanes) {
+  auto emit = [&](const Raw& ra, const Raw& rr, int64_t row) {
     Vec<T> a, r, o;
-    const int64_t row = sub_row(sg, voxels, n, v);
-    a.load(hb + row * ld_h);
-    r.load(rb + row * ld_res);
+    a.unpack(ra);
+    r.unpack(rr);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) o.v[i] = fmaf(a.v[i], g[i], r.v[i]);
     o.store(ob + row * ld_out);
     if (partial) {
+      // statistics of what the next GroupNorm will actually read (the stored, rounded value)
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
         const float w = to_float(from_float<T>(o.v[i]));
@@ -379,6 +374,25 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
         q[i] = fmaf(w, w, q[i]);
       }
     }
+  };
+  int64_t v = v0 + lane;
+  // eight 16-byte loads in flight per thread (4 voxels x 2 streams), kept packed until used; voxel order per thread is unchanged
+  for (; v + 3 * (int64_t)lanes < v1; v += 4 * (int64_t)lanes) {
+    Raw ra[4], rr[4];
+    int64_t row[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      row[u] = sub_row(sg, voxels, n, v + (int64_t)u * lanes);
+      ra[u] = Vec<T>::load_raw(hb + row[u] * ld_h);
+      rr[u] = Vec<T>::load_raw(rb + row[u] * ld_res);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(ra[u], rr[u], row[u]);
+  }
+  for (; v < v1; v += lanes) {
+    const int64_t row = sub_row(sg, voxels, n, v);
+    const Raw ra = Vec<T>::load_raw(hb + row * ld_h), rr = Vec<T>::load_raw(rb + row * ld_res);
+    emit(ra, rr, row);
   }
   if (partial) {
     block_channel_reduce<VEC>(s, q, col, lane, lanes, c, partial + ((int64_t)n * nblk + blk) * c * 2, smem);
@@ -394,8 +408,7 @@ template <typename T>
 __global__ void scale_copy_kernel(const T* __restrict__ src, int ld_src, T* __restrict__ dst, int ld_dst, int64_t rows,
                                   int nvec, float scale) {
   const int64_t total = rows * nvec;
-  pdl_launch_dependents();
-  pdl_wait();
+  pdl_sync();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / nvec;
     const int col = (int)(i - r * nvec);
@@ -486,9 +499,16 @@ static int affine_mish_impl(const void* x, int ld_x, void* y, int ld_y, int dtyp
   if (sub_f > 1) DIQT_REQUIRE(n == sub_f * sub_f * sub_f && voxels == (int64_t)sub_h * sub_h * sub_h, "affine_mish: sub-volume geometry mismatch");
   const int vec = dtype == DIQT_BF16 ? 8 : 4;
   DIQT_REQUIRE(x && y && ((a && b) || gp.group) && nblk > 0, "affine_mish: bad arguments");
-  const size_t gsh = gp.group ? (size_t)(2 * c + 2 * gp.groups) * sizeof(double) + (size_t)2 * c * sizeof(float) : 0;
-  DIQT_REQUIRE(c % vec == 0 && ld_x % vec == 0 && ld_y % vec == 0 && c / vec <= 256, "affine_mish: c=%d not a multiple of %d", c, vec);
   RowMap m = make_rowmap(c, vec, 256);
+  const size_t gsh = gp.group ? gn_scratch_bytes(c, gp.groups, m.threads) : 0;
+  DIQT_REQUIRE(c % vec == 0 && ld_x % vec == 0 && ld_y % vec == 0 && c / vec <= 256, "affine_mish: c=%d not a multiple of %d", c, vec);
+  DIQT_REQUIRE(gsh <= 160 * 1024, "affine_mish: c=%d needs %zu bytes of shared memory", c, gsh);
+  static bool big_smem = false;
+  if (gsh > 48 * 1024 && !big_smem) {  // very wide levels only (c >= 1024)
+    DIQT_CUDA(cudaFuncSetAttribute(affine_mish_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DIQT_CUDA(cudaFuncSetAttribute(affine_mish_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    big_smem = true;
+  }
   dim3 grid(nblk, n);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)
@@ -540,15 +560,23 @@ static int scale_residual_impl(const void* h, int ld_h, const void* res, int ld_
   RowMap m = make_rowmap(c, vec, 512);
   dim3 grid(nblk, n);
   size_t sh = partial ? (size_t)2 * m.lanes * c * sizeof(float) : 0;
-  if (se.group) sh = std::max(sh, (size_t)(2 * c + se.hidden) * sizeof(float));
+  SeParams sev = se;
+  if (se.group) {
+    const int slices = m.threads / c > 0 ? m.threads / c : 1;
+    const size_t base = ((size_t)slices * c * 2 + (size_t)c * 2) * sizeof(double) + ((size_t)2 * c + se.hidden) * sizeof(float);
+    const size_t wbytes = (size_t)2 * se.hidden * c * sizeof(float);
+    sev.stage_w = base + wbytes <= 40 * 1024 ? 1 : 0;
+    sh = std::max(sh, base + (sev.stage_w ? wbytes : 0));
+  }
+  DIQT_REQUIRE(sh <= 48 * 1024, "scale_residual: c=%d hidden=%d needs %zu bytes of shared memory", c, se.hidden, sh);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)
     launch_pdl(scale_residual_kernel<__nv_bfloat16>, grid, m.threads, sh, st, 
         (const __nv_bfloat16*)h, ld_h, (const __nv_bfloat16*)res, ld_res, (__nv_bfloat16*)out, ld_out, voxels, c, m.nvec,
-        m.lanes, vox_per_block(voxels, nblk), gate, partial, sg, se, og);
+        m.lanes, vox_per_block(voxels, nblk), gate, partial, sg, sev, og);
   else
     launch_pdl(scale_residual_kernel<float>, grid, m.threads, sh, st, (const float*)h, ld_h, (const float*)res, ld_res, (float*)out,
-               ld_out, voxels, c, m.nvec, m.lanes, vox_per_block(voxels, nblk), gate, partial, sg, se, og);
+               ld_out, voxels, c, m.nvec, m.lanes, vox_per_block(voxels, nblk), gate, partial, sg, sev, og);
   return check_launch("scale_residual");
 }
 
@@ -563,7 +591,7 @@ extern "C" int diqt_scale_residual(const void* h, int ld_h, const void* res, int
 extern "C" int diqt_scale_residual_g(const void* h, int ld_h, const void* res, int ld_res, void* out, int ld_out, int dtype, int n,
                                      int64_t voxels, int c, const float* se_group, int se_ngroups, int hidden, const float* w1,
                                      const float* w2, int nblk, float* partial, float* group_out, uint32_t* tickets, void* stream) {
-  SeParams se = {se_group, se_ngroups, hidden, w1, w2};
+  SeParams se = {se_group, se_ngroups, hidden, w1, w2, 0};
   if (se_group) DIQT_REQUIRE(se_ngroups > 0 && hidden > 0 && w1 && w2, "scale_residual_g: incomplete SE description");
   return scale_residual_impl(h, ld_h, res, ld_res, out, ld_out, dtype, n, voxels, c, nullptr, nblk, partial, 0, 0, se, group_out, tickets,
                              stream);

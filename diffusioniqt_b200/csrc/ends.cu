@@ -236,8 +236,7 @@ __device__ __forceinline__ void edm_heun_point(const EdmConsts& e, float net, fl
 // x_hat = x + sqrt(sigma_hat^2 - sigma^2) * (S_noise * eps);  x_in = c_in(sigma_hat) * x_hat     (:476-481, :349)
 __global__ void edm_prepare_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ table,
                                    const int32_t* __restrict__ step, float* __restrict__ x_hat, float* __restrict__ x_in, int64_t count) {
-  pdl_launch_dependents();
-  pdl_wait();
+  pdl_sync();
   const EdmConsts e = load_edm(table, step);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
     const float xh = __fadd_rn(x[i], __fmul_rn(e.noise_k, __fmul_rn(e.s_noise, eps[i])));
@@ -262,8 +261,7 @@ __global__ void final_conv_kernel(const T* __restrict__ x, int ld, int64_t voxel
   for (int co = 0; co < MAXCO; ++co)
 #pragma unroll
     for (int i = 0; i < VEC; ++i) wv[co][i] = co < c_out ? w[co * c + col * VEC + i] : 0.f;
-  pdl_launch_dependents();
-  pdl_wait();
+  pdl_sync();
   // step_mode: 0 store the prediction, 1 DDPM update, 2 Elucidated Euler pass, 3 Elucidated Heun pass.  In the Elucidated modes
   // `noise` carries x_hat and `pred` the slope buffer d (written by 2, read by 3); aux_out receives the next network input.
   StepConsts sc;
@@ -342,8 +340,7 @@ __global__ void ddpm_update_kernel(const float* __restrict__ pred, const float* 
                                    const int32_t* __restrict__ step, const float* __restrict__ x_t,
                                    const float* __restrict__ noise, float* __restrict__ x_next, float* __restrict__ x0,
                                    int64_t count) {
-  pdl_launch_dependents();
-  pdl_wait();
+  pdl_sync();
   StepConsts sc = load_step(sched, step);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
     float xn, xs;
@@ -395,8 +392,7 @@ __global__ void linear_kernel(const float* __restrict__ x, int ldx, int k, const
 }
 
 __global__ void advance_step_kernel(int32_t* step) {
-  pdl_launch_dependents();
-  pdl_wait();
+  pdl_sync();
   *step += 1;
 }
 
@@ -529,8 +525,7 @@ extern "C" int diqt_edm_prepare(const float* x, const float* eps, const float* t
 __global__ void edm_update_kernel(const float* __restrict__ denoised, int pass, const float* __restrict__ table, const int32_t* __restrict__ step,
                                   const float* __restrict__ x_hat, float* __restrict__ slope, float* __restrict__ state,
                                   float* __restrict__ next_input, int64_t count) {
-  pdl_launch_dependents();
-  pdl_wait();
+  pdl_sync();
   const EdmConsts e = load_edm(table, step);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
     const float x0 = denoised[i];

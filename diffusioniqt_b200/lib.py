@@ -11,7 +11,7 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdiqt_b200.so")
+LIB_PATH = os.environ.get("DIQT_LIB_PATH") or os.path.join(_HERE, "libdiqt_b200.so")   # the variable selects an A/B build variant
 
 F32, BF16 = 0, 1
 CONV_K3, CONV_K1, CONV_DOWN, CONV_UP = 0, 1, 2, 3
