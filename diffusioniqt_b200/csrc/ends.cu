@@ -268,68 +268,75 @@ __global__ void final_conv_kernel(const T* __restrict__ x, int ld, int64_t voxel
   EdmConsts ec;
   if (step_mode == 1) sc = load_step(sched, step);
   if (step_mode >= 2) ec = load_edm(sched, step);
-  // block-uniform trip count so the full-mask shuffles below are always converged; UNR rows in flight per thread group
-  constexpr int UNR = 4;
-  for (int64_t base = (int64_t)blockIdx.x * rows_per_block * UNR; base < total_rows; base += (int64_t)gridDim.x * rows_per_block * UNR) {
-    Vec<T> r[UNR];
-    bool valid[UNR];
+  // A group of nvec threads owns UNR CONSECUTIVE voxel rows: the row loads are coalesced 16-byte chunks, the dot products are
+  // reduced with butterfly shuffles (every lane ends up with every sum), and lane u of the group finishes row u - so the fp32
+  // sampler state (x_t, noise, x_next, x0) is read and written as contiguous runs instead of one float per 8 lanes.
+  // Block-uniform trip count so the full-mask shuffles are always converged.
+  constexpr int UNR = 8;
+  using Raw = typename Vec<T>::Raw;
+  const int R = min(UNR, nvec);  // rows per group: one finishing lane per row
+  const int grp = threadIdx.x / nvec;
+  for (int64_t base = (int64_t)blockIdx.x * rows_per_block * R; base < total_rows; base += (int64_t)gridDim.x * rows_per_block * R) {
+    const int64_t row0 = base + (int64_t)grp * R;
+    Raw raw[UNR];
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const int64_t row = base + (int64_t)u * rows_per_block + threadIdx.x / nvec;
-      valid[u] = row < total_rows;
-      if (valid[u]) r[u].load(x + row * ld + col * VEC);
-      else {
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) r[u].v[i] = 0.f;
-      }
+      raw[u] = Raw();
+      if (u < R && row0 + u < total_rows) raw[u] = Vec<T>::load_raw(x + (row0 + u) * ld + col * VEC);
     }
+    float mine[MAXCO];
+#pragma unroll
+    for (int co = 0; co < MAXCO; ++co) mine[co] = 0.f;
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
-      const int64_t row = base + (int64_t)u * rows_per_block + threadIdx.x / nvec;
-      float acc[MAXCO];
+      if (u >= R) break;  // block-uniform
+      Vec<T> r;
+      r.unpack(raw[u]);
 #pragma unroll
       for (int co = 0; co < MAXCO; ++co) {
-        acc[co] = 0.f;
         if (co < c_out) {
+          float acc = 0.f;
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) acc[co] = fmaf(r[u].v[i], wv[co][i], acc[co]);
-          for (int o = nvec >> 1; o > 0; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+          for (int i = 0; i < VEC; ++i) acc = fmaf(r.v[i], wv[co][i], acc);
+          for (int o = nvec >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+          if (col == u) mine[co] = acc;
         }
       }
-      if (valid[u] && col == 0) {
-        int64_t b = row / voxels, v = row - b * voxels, ovox = voxels;
-        if (sg.f > 1) {  // merged row -> (sub-volume, local voxel); the fp32 state tensors stay in sub-volume layout
-          const int h = sg.h, fh = sg.f * sg.h;
-          const int xx = (int)(row % fh), yy = (int)((row / fh) % fh), zz = (int)(row / ((int64_t)fh * fh));
-          b = zz / h + sg.f * (yy / h) + sg.f * sg.f * (xx / h);
-          v = ((int64_t)(zz % h) * h + yy % h) * h + xx % h;
-          ovox = (int64_t)h * h * h;
-        }
+    }
+    const int64_t row = row0 + col;
+    if (col < R && row < total_rows) {
+      int64_t b = row / voxels, v = row - b * voxels, ovox = voxels;
+      if (sg.f > 1) {  // merged row -> (sub-volume, local voxel); the fp32 state tensors stay in sub-volume layout
+        const int h = sg.h, fh = sg.f * sg.h;
+        const int xx = (int)(row % fh), yy = (int)((row / fh) % fh), zz = (int)(row / ((int64_t)fh * fh));
+        b = zz / h + sg.f * (yy / h) + sg.f * sg.f * (xx / h);
+        v = ((int64_t)(zz % h) * h + yy % h) * h + xx % h;
+        ovox = (int64_t)h * h * h;
+      }
 #pragma unroll
-        for (int co = 0; co < MAXCO; ++co) {
-          if (co >= c_out) break;
-          const float p = acc[co] + bias[co];
-          const int64_t o = (b * c_out + co) * ovox + v;  // NCDHW fp32
-          if (!step_mode) {
-            pred[o] = p;
-          } else if (step_mode == 1) {
-            float xn, xs;
-            ddpm_point(sc, p, x_t[o], noise[o], xn, xs);
-            x_next[o] = xn;
-            x0[o] = xs;
-          } else if (step_mode == 2) {
-            float d, xe, xs;
-            edm_euler_point(ec, p, noise[o], d, xe, xs);
-            pred[o] = d;
-            x_next[o] = xe;
-            aux_out[o] = __fmul_rn(ec.c_in_next, xe);
-            x0[o] = xs;
-          } else {
-            float xn, xs;
-            edm_heun_point(ec, p, noise[o], x_t[o], pred[o], xn, xs);
-            x_next[o] = xn;
-            x0[o] = xs;
-          }
+      for (int co = 0; co < MAXCO; ++co) {
+        if (co >= c_out) break;
+        const float p = mine[co] + bias[co];
+        const int64_t o = (b * c_out + co) * ovox + v;  // NCDHW fp32
+        if (!step_mode) {
+          pred[o] = p;
+        } else if (step_mode == 1) {
+          float xn, xs;
+          ddpm_point(sc, p, x_t[o], noise[o], xn, xs);
+          x_next[o] = xn;
+          x0[o] = xs;
+        } else if (step_mode == 2) {
+          float d, xe, xs;
+          edm_euler_point(ec, p, noise[o], d, xe, xs);
+          pred[o] = d;
+          x_next[o] = xe;
+          aux_out[o] = __fmul_rn(ec.c_in_next, xe);
+          x0[o] = xs;
+        } else {
+          float xn, xs;
+          edm_heun_point(ec, p, noise[o], x_t[o], pred[o], xn, xs);
+          x_next[o] = xn;
+          x0[o] = xs;
         }
       }
     }
@@ -401,6 +408,51 @@ __global__ void clamp_kernel(float* __restrict__ x, int64_t count, float lo, flo
     x[i] = fminf(fmaxf(x[i], lo), hi);
 }
 
+
+// ---- init conv on the tensor cores: im2col of the fp32 planes into K = 64 bf16 columns --------------------------------------------
+// init_conv (:1291) has K = 27 * c_in = 54 and is compute bound on CUDA cores (0.9 GMAC at 64^3: 108 us).  For 27 * c_in <= 64 the
+// engine instead writes col[row][k = tap * c_in + ci] = plane_ci[voxel + tap] (zero outside the volume = the conv's zero padding,
+// zero for k >= 27 * c_in) and runs a 1x1x1 tcgen05 convolution over it with the weights laid out to match.  One thread = one
+// 16-byte chunk (8 columns) of one row; this is the first kernel of a step, launched without the PDL attribute.
+__global__ void __launch_bounds__(256) init_im2col_kernel(InitPlanes planes, int c_in, __nv_bfloat16* __restrict__ col, int n, int d0, int d1, int d2) {
+  const int64_t vol = (int64_t)d0 * d1 * d2;
+  const int64_t total = (int64_t)n * vol * 8;
+  const int kmax = 27 * c_in;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i >> 3;
+    const int chunk = (int)(i & 7);
+    const int b = (int)(row / vol);
+    int64_t r = row - (int64_t)b * vol;
+    const int z = (int)(r / ((int64_t)d1 * d2));
+    r -= (int64_t)z * d1 * d2;
+    const int y = (int)(r / d2), x = (int)(r - (int64_t)y * d2);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = chunk * 8 + j;
+      v[j] = 0.f;
+      if (k < kmax) {
+        const int tap = k / c_in, ci = k - tap * c_in;
+        const int zz = z + tap / 9 - 1, yy = y + (tap / 3) % 3 - 1, xx = x + tap % 3 - 1;
+        if (zz >= 0 && zz < d0 && yy >= 0 && yy < d1 && xx >= 0 && xx < d2) {
+          const float* pl = planes.p[0];
+          long long ps = planes.stride[0];
+#pragma unroll
+          for (int q = 1; q < kInitMaxCin; ++q)  // select chain: no dynamic indexing of the parameter struct (would go through local memory)
+            if (ci == q) { pl = planes.p[q]; ps = planes.stride[q]; }
+          v[j] = __ldg(pl + (int64_t)b * ps + ((int64_t)zz * d1 + yy) * d2 + xx);
+        }
+      }
+    }
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      w[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(col + row * 64 + chunk * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
 }  // namespace diqt
 
 using namespace diqt;
@@ -408,6 +460,22 @@ using namespace diqt;
 extern "C" int diqt_abi_version(void) { return DIQT_ABI_VERSION; }
 extern "C" const char* diqt_last_error(void) { return g_err; }
 extern "C" uint64_t diqt_launch_count(void) { return g_launches.load(); }
+
+extern "C" int diqt_init_im2col(const float* const* planes, const int64_t* plane_stride, int c_in, void* col, int n, int d0, int d1, int d2,
+                                void* stream) {
+  DIQT_REQUIRE(planes && plane_stride && col && n > 0 && d0 > 0 && d1 > 0 && d2 > 0, "init_im2col: bad arguments");
+  DIQT_REQUIRE(c_in > 0 && c_in <= kInitMaxCin && 27 * c_in <= 64, "init_im2col: 27 * c_in = %d columns do not fit K = 64", 27 * c_in);
+  InitPlanes ip;
+  for (int i = 0; i < kInitMaxCin; ++i) {
+    ip.p[i] = i < c_in ? planes[i] : nullptr;
+    ip.stride[i] = i < c_in ? plane_stride[i] : 0;
+  }
+  const int64_t total = (int64_t)n * d0 * d1 * d2 * 8;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  init_im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ip, c_in, (__nv_bfloat16*)col, n, d0, d1, d2);
+  return check_launch("init_im2col");
+}
 
 extern "C" int diqt_init_conv_pack(const float* w, int c_out, int c_in, float* packed, void* stream) {
   DIQT_REQUIRE(w && packed && c_in > 0 && c_in <= kInitMaxCin, "init_conv_pack: c_in=%d (max %d)", c_in, kInitMaxCin);
@@ -485,7 +553,8 @@ static int final_conv_impl(const void* x, int ld, int dtype, int n, int64_t voxe
   const int64_t rows = (int64_t)n * voxels;
   const int threads = 256;
   const int64_t rpb = threads / nvec;
-  int64_t blocks = (rows + rpb * 4 - 1) / (rpb * 4);
+  const int64_t rgrp = nvec < 8 ? nvec : 8;  // rows per thread group (final_conv_kernel: R)
+  int64_t blocks = (rows + rpb * rgrp - 1) / (rpb * rgrp);
   if (blocks > 148 * 8) blocks = 148 * 8;
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == DIQT_BF16)

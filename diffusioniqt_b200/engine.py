@@ -347,16 +347,33 @@ class UnetEngine:
 
         # ---- init conv
         x = next_out(0, dims[0])
-        self.w_init = torch.empty(27 * u.init_channels * dims[0], dtype=torch.float32, device=self.device)
-        wi = self._f32(u.init_conv.weight)
-        self.b_init = self._f32(u.init_conv.bias)
-        L.check(lib.diqt_init_conv_pack(wi.data_ptr(), dims[0], u.init_channels, self.w_init.data_ptr(), L.current_stream()), "init_conv_pack")
         d0, d1, d2 = self.conv_dims[0]
         xp, xl, c0, nin, cn = x.ptr, x.ld, dims[0], u.init_channels, self.conv_n
-        wip, bip = self.w_init.data_ptr(), self.b_init.data_ptr()
         planes_ref, strides_ref = self._planes, self._pstrides
         sf0, sh0 = self.level_sub[0]
-        ops.append(lambda st: L.check(lib.diqt_init_conv(planes_ref, strides_ref, nin, wip, bip, xp, xl, dd, cn, d0, d1, d2, c0, sf0, sh0, st), "init_conv"))
+        self.init_conv_tc = (self.dtype == "bf16" and self.sub_f <= 1 and 27 * nin <= 64 and c0 % 64 == 0 and self.impl != L.IMPL_SIMT
+                             and os.environ.get("DIQT_DISABLE_INIT_TC", "0") != "1")
+        if self.init_conv_tc:
+            # K = 27 * c_in = 54 is not a tensor-core shape as a 3x3x3 conv, but it is as a 1x1x1 conv over an im2col'ed K = 64 tensor:
+            # one gather kernel + the tcgen05 per-tap kernel (which also emits the GroupNorm statistics of its output)
+            self.im2col = self._empty(n * vox0, 64, dtype=torch.bfloat16)
+            w = u.init_conv.weight.detach().to(self.device, torch.float32)                   # (c0, nin, 3, 3, 3)
+            w2 = torch.zeros(c0, 64, device=self.device, dtype=torch.float32)
+            w2[:, :27 * nin] = w.permute(0, 2, 3, 4, 1).reshape(c0, 27 * nin)                   # k = tap * nin + ci
+            colp = self.im2col.data_ptr()
+            ops.append(lambda st: L.check(lib.diqt_init_im2col(planes_ref, strides_ref, nin, colp, cn, d0, d1, d2, st), "init_im2col"))
+            ops.append(self._conv_site("init_conv", L.CONV_K1, 0, 64, 64, c0, xl, w2.reshape(c0, 64, 1, 1, 1), u.init_conv.bias, colp, xp,
+                                       stats=self._pp))
+            if self._last_conv_stats:
+                x.stats = self._last_conv_stats
+                self._pp ^= 1
+        else:
+            self.w_init = torch.empty(27 * u.init_channels * dims[0], dtype=torch.float32, device=self.device)
+            wi = self._f32(u.init_conv.weight)
+            self.b_init = self._f32(u.init_conv.bias)
+            L.check(lib.diqt_init_conv_pack(wi.data_ptr(), dims[0], u.init_channels, self.w_init.data_ptr(), L.current_stream()), "init_conv_pack")
+            wip, bip = self.w_init.data_ptr(), self.b_init.data_ptr()
+            ops.append(lambda st: L.check(lib.diqt_init_conv(planes_ref, strides_ref, nin, wip, bip, xp, xl, dd, cn, d0, d1, d2, c0, sf0, sh0, st), "init_conv"))
 
         # ---- down path
         skip_scale = u.skip_connect_scale

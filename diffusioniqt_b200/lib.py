@@ -61,6 +61,7 @@ _SIGNATURES = {
     "diqt_linear_attention": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _f, _i, _vp, _vp, _vp],
     "diqt_softmax_attention": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _i, _vp],
     "diqt_init_conv_pack": [_vp, _i, _i, _vp, _vp],
+    "diqt_init_im2col": [C.POINTER(_vp), C.POINTER(_i64), _i, _vp, _i, _i, _i, _i, _vp],
     "diqt_init_conv": [C.POINTER(_vp), C.POINTER(_i64), _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "diqt_final_conv": [_vp, _i, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "diqt_ddpm_update": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp],

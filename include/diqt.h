@@ -215,6 +215,11 @@ int diqt_init_conv(const float* const* planes, const int64_t* plane_stride, int 
                    const float* bias, void* out, int ld_out, int dtype, int n, int d0, int d1, int d2, int c_out,
                    int sub_f, int sub_h, void* stream);
 int diqt_init_conv_pack(const float* w, int c_out, int c_in, float* packed, void* stream);
+/* The same init_conv on the tensor cores (bf16 mode, 27 * c_in <= 64, plain volumes): col[row][k = tap * c_in + ci] = plane_ci at the
+ * tap-shifted voxel (tap = (kz*3+ky)*3+kx, zero outside the volume and for k >= 27 * c_in), bf16 [n*d0*d1*d2][64]; followed by a
+ * DIQT_CONV_K1 convolution 64 -> c_out whose weight is W[co][ci][tap] re-ordered to [co][tap * c_in + ci] and zero-padded to 64. */
+int diqt_init_im2col(const float* const* planes, const int64_t* plane_stride, int c_in, void* col, int n, int d0, int d1, int d2,
+                     void* stream);
 
 /* final_conv (:1477, 1x1x1, c -> c_out<=4) producing the fp32 NCDHW prediction, optionally fused
  * with the DDPM update of Imagen.p_mean_variance / p_sample / q_posterior (:1976-2056, :290-309):

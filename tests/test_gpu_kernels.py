@@ -245,3 +245,32 @@ def test_channel_stats_is_deterministic():
     a, b = ops.channel_stats(x, 13), ops.channel_stats(x, 13)
     torch.cuda.synchronize()
     assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n,dims,c_in,c_out", [(1, (8, 8, 8), 2, 64), (2, (4, 6, 10), 1, 64), (1, (16, 16, 16), 2, 128)])
+def test_init_conv_im2col_tensor_core_path(n, dims, c_in, c_out):
+    """init_conv (:1291) as im2col (K = 27 * c_in -> 64 bf16 columns) + 1x1x1 tcgen05 conv against F.conv3d on the bf16-rounded input."""
+    import ctypes as C
+    from diffusioniqt_b200 import lib as L, ops
+    lib = L.load()
+    x = _rand(n, c_in, *dims, seed=11)
+    w, b = _rand(c_out, c_in, 3, 3, 3, seed=12, scale=(27 * c_in) ** -0.5), _rand(c_out, seed=13, scale=0.1)
+    want = F.conv3d(x.bfloat16().float(), w.bfloat16().float(), b, padding=1)
+    xc = x.cuda().contiguous()
+    vox = dims[0] * dims[1] * dims[2]
+    planes = (C.c_void_p * c_in)(*[xc.data_ptr() + ci * vox * 4 for ci in range(c_in)])
+    strides = (C.c_int64 * c_in)(*[c_in * vox] * c_in)
+    col = torch.empty(n, *dims, 64, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.diqt_init_im2col(planes, strides, c_in, col.data_ptr(), n, *dims, L.current_stream()), "init_im2col")
+    # the im2col tensor itself: column k = tap * c_in + ci holds the tap-shifted, zero-padded plane
+    xp = F.pad(x.bfloat16().float(), (1, 1, 1, 1, 1, 1))
+    ref = torch.zeros(n, *dims, 64)
+    for tap in range(27):
+        kz, ky, kx = tap // 9, (tap // 3) % 3, tap % 3
+        for ci in range(c_in):
+            ref[..., tap * c_in + ci] = xp[:, ci, kz:kz + dims[0], ky:ky + dims[1], kx:kx + dims[2]]
+    assert torch.equal(col.float().cpu(), ref)
+    w2 = torch.zeros(c_out, 64)
+    w2[:, :27 * c_in] = w.permute(0, 2, 3, 4, 1).reshape(c_out, 27 * c_in)
+    got = ops.conv3d(col, w2.reshape(c_out, 64, 1, 1, 1), b, mode="k1", impl="tc")
+    assert max_rel(ops.from_channels_last(got).cpu(), want) < BF16_TOL

@@ -48,7 +48,7 @@ def test_driver_config_uses_tcgen05_kernels():
     unet(x.cuda(), None, time.cuda(), lowres_cond_img=lr.cuda())
     eng = next(iter(unet._engines.values()))
     tc = [k for k, v in eng.conv_impls.items() if v in (lib.IMPL_TC, lib.IMPL_ZM)]
-    assert len(tc) == len(eng.conv_impls) == 47 - 2   # every conv except init_conv / final_conv (39 + 8)
+    assert len(tc) == len(eng.conv_impls) == 47 - 1   # every conv except final_conv (39 + 8); init_conv runs as im2col + 1x1x1
     # the 3x3x3 convs whose volume fits the 16 x 8 plane tile (here: the 16^3 level) run the z-march kernel, 1x1x1 / up / down the per-tap one
     zm = [k for k, v in eng.conv_impls.items() if v == lib.IMPL_ZM]
     assert len(zm) == 20 and all(k.endswith(".project") for k in zm)
