@@ -47,6 +47,20 @@ def read_peaks():
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback")
 
 
+def read_traffic(kernel_label):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        for k, v in t.items():
+            if k.split()[0] in kernel_label and "64^3" in kernel_label:
+                return v["bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
 
@@ -320,7 +334,11 @@ def main():
         step_tflops = value / world * flops_per_patch / 1e12
         dom = time_dominant_kernel(S, B)
         roofline = dict(bound="tensor", kernel="%s 3x3x3 64->64 @%d^3 (batch %d)" % (dom["kernel"], S, B), achieved=dom["tflops"], peak=peaks["burst"],
-                        unit="TFLOP/s", frac=dom["tflops"] / peaks["burst"], traffic=None, ms_per_launch=dom["ms"], flops_per_launch=dom["flops"],
+                        unit="TFLOP/s", frac=dom["tflops"] / peaks["burst"],
+                        traffic=read_traffic("%s 64^3" % dom["kernel"]) if (S == 64 and B == 1) else None,
+                        traffic_note="dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/ncu_traffic.json (ncu --set full); algorithmic "
+                                     "traffic is 67.1 MB (32 MiB in + 32 MiB out), the output of a launch stays in the 126 MB L2",
+                        ms_per_launch=dom["ms"], flops_per_launch=dom["flops"],
                         peak_source=peaks["source"] + " (burst: kernel timed alone)",
                         whole_step=dict(achieved=step_tflops, peak=peaks["sustained"], frac=step_tflops / peaks["sustained"], unit="TFLOP/s",
                                         note="all FLOPs of the U-Net / wall time of the sampler, per GPU, vs sustained bf16 peak"))

@@ -414,45 +414,60 @@ __global__ void clamp_kernel(float* __restrict__ x, int64_t count, float lo, flo
 // engine instead writes col[row][k = tap * c_in + ci] = plane_ci[voxel + tap] (zero outside the volume = the conv's zero padding,
 // zero for k >= 27 * c_in) and runs a 1x1x1 tcgen05 convolution over it with the weights laid out to match.  One thread = one
 // 16-byte chunk (8 columns) of one row; this is the first kernel of a step, launched without the PDL attribute.
+// grid (ceil(d1 / 8), d0, n): a CTA stages the haloed input rows of an 8 (y) x d2 (x) tile of one z-plane in shared memory
+// (c_in x 3 x 10 x (d2 + 2) floats, zero outside the volume = the conv's zero padding) and writes the 8 * d2 rows of 64 bf16 columns.
 __global__ void __launch_bounds__(256) init_im2col_kernel(InitPlanes planes, int c_in, __nv_bfloat16* __restrict__ col, int n, int d0, int d1, int d2) {
-  const int64_t vol = (int64_t)d0 * d1 * d2;
-  const int64_t total = (int64_t)n * vol * 8;
-  const int kmax = 27 * c_in;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = i >> 3;
-    const int chunk = (int)(i & 7);
-    const int b = (int)(row / vol);
-    int64_t r = row - (int64_t)b * vol;
-    const int z = (int)(r / ((int64_t)d1 * d2));
-    r -= (int64_t)z * d1 * d2;
-    const int y = (int)(r / d2), x = (int)(r - (int64_t)y * d2);
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = chunk * 8 + j;
-      v[j] = 0.f;
-      if (k < kmax) {
-        const int tap = k / c_in, ci = k - tap * c_in;
-        const int zz = z + tap / 9 - 1, yy = y + (tap / 3) % 3 - 1, xx = x + tap % 3 - 1;
-        if (zz >= 0 && zz < d0 && yy >= 0 && yy < d1 && xx >= 0 && xx < d2) {
-          const float* pl = planes.p[0];
-          long long ps = planes.stride[0];
-#pragma unroll
-          for (int q = 1; q < kInitMaxCin; ++q)  // select chain: no dynamic indexing of the parameter struct (would go through local memory)
-            if (ci == q) { pl = planes.p[q]; ps = planes.stride[q]; }
-          v[j] = __ldg(pl + (int64_t)b * ps + ((int64_t)zz * d1 + yy) * d2 + xx);
-        }
-      }
+  extern __shared__ float tile[];  // [c_in][3][10][d2 + 2], then int koff[64]
+  const int W = d2 + 2, plane = 3 * 10 * W;
+  int* koff = reinterpret_cast<int*>(tile + (size_t)c_in * plane);
+  const int y0 = blockIdx.x * 8, z = blockIdx.y, b = blockIdx.z;
+  if (threadIdx.x < 64) {
+    const int k = threadIdx.x;
+    int o = -1;
+    if (k < 27 * c_in) {
+      const int tap = k / c_in, ci = k - tap * c_in;
+      o = ci * plane + ((tap / 9) * 10 + (tap / 3) % 3) * W + tap % 3;
     }
+    koff[k] = o;
+  }
+  for (int idx = threadIdx.x; idx < c_in * plane; idx += blockDim.x) {
+    const int ci = idx / plane;
+    int r = idx - ci * plane;
+    const int dz = r / (10 * W);
+    r -= dz * 10 * W;
+    const int yy = r / W, xx = r - yy * W;
+    const int zz = z + dz - 1, y = y0 + yy - 1, x = xx - 1;
+    float v = 0.f;
+    if (zz >= 0 && zz < d0 && y >= 0 && y < d1 && x >= 0 && x < d2) {
+      const float* pl = planes.p[0];
+      long long ps = planes.stride[0];
+#pragma unroll
+      for (int q = 1; q < kInitMaxCin; ++q)  // select chain: no dynamic indexing of the parameter struct (would go through local memory)
+        if (ci == q) { pl = planes.p[q]; ps = planes.stride[q]; }
+      v = __ldg(pl + (int64_t)b * ps + ((int64_t)zz * d1 + y) * d2 + x);
+    }
+    tile[idx] = v;
+  }
+  __syncthreads();
+  const int tasks = 8 * d2 * 8;
+  for (int t = threadIdx.x; t < tasks; t += blockDim.x) {
+    const int chunk = t & 7, vox = t >> 3;
+    const int yl = vox / d2, x = vox - yl * d2;
+    if (y0 + yl >= d1) break;  // later tasks of this thread have an even larger yl
+    const int base = yl * W + x;
     uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-      w[j] = *reinterpret_cast<uint32_t*>(&h);
+    for (int jj = 0; jj < 4; ++jj) {
+      const int o0 = koff[chunk * 8 + 2 * jj], o1 = koff[chunk * 8 + 2 * jj + 1];
+      const float v0 = o0 >= 0 ? tile[o0 + base] : 0.f, v1 = o1 >= 0 ? tile[o1 + base] : 0.f;
+      __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+      w[jj] = *reinterpret_cast<uint32_t*>(&h);
     }
+    const int64_t row = (((int64_t)b * d0 + z) * d1 + (y0 + yl)) * d2 + x;
     *reinterpret_cast<uint4*>(col + row * 64 + chunk * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
+
 }  // namespace diqt
 
 using namespace diqt;
@@ -470,10 +485,10 @@ extern "C" int diqt_init_im2col(const float* const* planes, const int64_t* plane
     ip.p[i] = i < c_in ? planes[i] : nullptr;
     ip.stride[i] = i < c_in ? plane_stride[i] : 0;
   }
-  const int64_t total = (int64_t)n * d0 * d1 * d2 * 8;
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  init_im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ip, c_in, (__nv_bfloat16*)col, n, d0, d1, d2);
+  const size_t sh = (size_t)c_in * 3 * 10 * (d2 + 2) * sizeof(float) + 64 * sizeof(int);
+  DIQT_REQUIRE(sh <= 48 * 1024 && d0 <= 65535 && n <= 65535, "init_im2col: d2=%d too wide for the shared-memory tile", d2);
+  const dim3 grid((d1 + 7) / 8, d0, n);
+  init_im2col_kernel<<<grid, 256, sh, (cudaStream_t)stream>>>(ip, c_in, (__nv_bfloat16*)col, n, d0, d1, d2);
   return check_launch("init_im2col");
 }
 
