@@ -261,6 +261,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # "NCCL version ..." goes to stdout and would precede the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
