@@ -129,6 +129,6 @@ def test_evaluate_crops_like_the_reference_script():
     ca, cb = a[24:-24, 24:-24, 24:-24], b[24:-24, 24:-24, 24:-24]
     assert p == pytest.approx(mo.psnr(ca, cb), rel=1e-9)
     norm = lambda v: (v - v.min()) / (v.max() - v.min())
-    assert s == pytest.approx(M.ms_ssim3d(norm(ca), norm(cb), kernel_size=3), rel=1e-12)
+    assert s == pytest.approx(M.ms_ssim3d(norm(ca), norm(cb), kernel_size=3), rel=1e-8)
     small = synthetic_field((60, 60, 60), 8)
     assert M.evaluate(small, small, kernel_size=3)[0] == pytest.approx(1.0)      # other sizes: no crop
