@@ -72,6 +72,8 @@ _SIGNATURES = {
     "diqt_fourier_features": [_vp, _i, _vp, _i, _vp, _vp],
     "diqt_linear": [_vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _i, _i, _vp],
     "diqt_advance_step": [_vp, _vp],
+    "diqt_gather_patches": [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp],
+    "diqt_stitch_patches": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _f, _vp],
 }
 _RESTYPES = {"diqt_last_error": C.c_char_p, "diqt_launch_count": C.c_uint64, "diqt_conv_plan_destroy": None}
 

@@ -83,41 +83,91 @@ class VolumeResult:
     patches_per_rank: int
 
 
+def split_sub_volumes(patches: torch.Tensor, f: int) -> torch.Tensor:
+    """(B, P, P, P) -> (B * f^3, P/f, P/f, P/f) in the order of convertVolume2subVolume (utils_mine.py:25-42): sub-volume
+    b = b0 + f*b1 + f*f*b2 is block (b0, b1, b2) along the three spatial dims."""
+    B, P = patches.shape[0], patches.shape[-1]
+    h = P // f
+    v = patches.reshape(B, f, h, f, h, f, h)              # B, b0, x, b1, y, b2, z
+    return v.permute(0, 5, 3, 1, 2, 4, 6).reshape(B * f ** 3, h, h, h)
+
+
+def merge_sub_volumes(sub: torch.Tensor, f: int) -> torch.Tensor:
+    """Inverse of `split_sub_volumes` (merge_sub_volumes, utils_mine.py:44-67): (B * f^3, h, h, h) -> (B, f*h, f*h, f*h)."""
+    h = sub.shape[-1]
+    B = sub.shape[0] // f ** 3
+    v = sub.reshape(B, f, f, f, h, h, h)                  # B, b2, b1, b0, x, y, z
+    return v.permute(0, 3, 4, 2, 5, 1, 6).reshape(B, f * h, f * h, f * h)
+
+
 def infer_volume(sample_fn: Callable[[torch.Tensor], torch.Tensor], lowres_norm: torch.Tensor, *, patch: int, overlap: int,
                  raw_lowres: Optional[torch.Tensor] = None, batch_size: int = 1, fill_value: float = 0.0,
-                 rank: int = 0, world: int = 1, group=None, batch_sample: bool = False) -> VolumeResult:
+                 rank: int = 0, world: int = 1, group=None, batch_sample: bool = False, sub_f: int = 0) -> VolumeResult:
     """Denoise a whole (normalised) low-field volume patch by patch and stitch the result.
 
     sample_fn: (B, 1, P, P, P) low-field patches on the compute device -> (B, 1, P, P, P) denoised patches
                (e.g. `lambda lr: imagen.sample(batch_size=lr.shape[0], start_image_or_video=lr, start_at_unet_number=2)[0]`).
+               With sub_f = f > 1 (`Train.batch_sample`, data.py:147-150, test_all.py:230-231, 267-268) every P^3 patch is handed over as
+               its f^3 sub-volumes, (B * f^3, 1, P/f, P/f, P/f), and comes back the same way.
     lowres_norm: (X, Y, Z) normalised volume on the compute device.  raw_lowres: the un-normalised volume used by the
     5 % skip rule (defaults to `lowres_norm`).  fill_value: initial value of the output, `(0 - mean) / std` in the
     reference (test_all.py:211-212).
     With world > 1 every rank must call this with the same arguments; each denoises its block of the patch list and the
     patches are exchanged with ONE all_gather (torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+    On a CUDA device the patches are cut and stitched by two kernels of libdiqt_b200 (`diqt_gather_patches`, `diqt_stitch_patches`);
+    CPU tensors (the multi-process host-logic tests, with a stand-in `sample_fn`) take the equivalent torch slicing below.
     """
     dev = lowres_norm.device
     raw = raw_lowres if raw_lowres is not None else lowres_norm
+    f = int(sub_f) if sub_f and sub_f > 1 else 1
+    if patch % f:
+        raise ValueError(f"patch {patch} is not a multiple of the sub-volume factor {f}")
     grid = patch_grid(lowres_norm.shape, patch, overlap)
     kept = [o for o in grid if keep_patch(raw, o, patch)]
     start, stop, per = shard_range(len(kept), rank, world)
     mine = kept[start:stop]
-    local = torch.zeros((per, patch, patch, patch), dtype=torch.float32, device=dev)
+    on_gpu = dev.type == "cuda"
+    vol32 = lowres_norm.float().contiguous()
+    local = torch.zeros((per, patch ** 3), dtype=torch.float32, device=dev)
+    if on_gpu:
+        from . import lib as L
+        lib = L.load()
+        d0, d1, d2 = (int(v) for v in vol32.shape)
+        origins = torch.tensor(mine if mine else [[0, 0, 0]], dtype=torch.int32, device=dev)
     for b0 in range(0, len(mine), batch_size):
         chunk = mine[b0:b0 + batch_size]
-        lr = torch.stack([lowres_norm[i:i + patch, j:j + patch, k:k + patch] for (i, j, k) in chunk])[:, None].float().contiguous()
+        nb = len(chunk)
+        if on_gpu:
+            lr = torch.empty((nb * f ** 3, 1) + (patch // f,) * 3, dtype=torch.float32, device=dev)
+            L.check(lib.diqt_gather_patches(vol32.data_ptr(), d0, d1, d2, origins[b0:b0 + nb].data_ptr(), nb, patch, f, lr.data_ptr(),
+                                            L.current_stream()), "gather_patches")
+        else:
+            lr = torch.stack([vol32[i:i + patch, j:j + patch, k:k + patch] for (i, j, k) in chunk])
+            lr = (split_sub_volumes(lr, f) if f > 1 else lr)[:, None].contiguous()
         out = sample_fn(lr)
-        local[b0:b0 + len(chunk)] = out[:, 0].to(dev, torch.float32)
+        local[b0:b0 + nb] = out.to(dev, torch.float32).reshape(nb, patch ** 3)     # same (sub-volume) layout as `lr`
     if world > 1:
         import torch.distributed as dist
-        gathered = torch.empty((world * per, patch, patch, patch), dtype=torch.float32, device=dev)
+        gathered = torch.empty((world * per, patch ** 3), dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(gathered, local, group=group)       # the only collective on the path
     else:
         gathered = local
     pred = torch.full(tuple(lowres_norm.shape), float(fill_value), dtype=torch.float32, device=dev)
+    lo = vol32.min()
+    if on_gpu and kept:
+        g = [len(range(0, int(s) - patch + 1, overlap)) for s in vol32.shape]
+        slot = torch.full((g[0] * g[1] * g[2],), -1, dtype=torch.int32)
+        index = {o: n for n, o in enumerate(grid)}
+        for n, o in enumerate(kept):                                    # rank r holds kept[r*per : (r+1)*per] -> row n of `gathered`
+            slot[index[o]] = n
+        slot = slot.to(dev)
+        L.check(lib.diqt_stitch_patches(gathered.data_ptr(), slot.data_ptr(), g[0], g[1], g[2], overlap, patch, overlap, 1 if batch_sample else 0, f,
+                                        pred.data_ptr(), d0, d1, d2, vol32.data_ptr(), float(lo), L.current_stream()), "stitch_patches")
+        return VolumeResult(pred, len(kept), len(grid) - len(kept), per)
     for n, origin in enumerate(kept):                                   # index order: later patches overwrite earlier ones
-        r, slot = divmod(n, per)
-        stitch_patch_(pred, gathered[r * per + slot], origin, patch, overlap, batch_sample)
-    lo = lowres_norm.min()
-    pred[lowres_norm == lo] = lo                                        # background mask (test_all.py:300)
+        p3 = gathered[n].reshape((f ** 3,) + (patch // f,) * 3) if f > 1 else gathered[n].reshape(patch, patch, patch)
+        if f > 1:
+            p3 = merge_sub_volumes(p3, f)[0]
+        stitch_patch_(pred, p3, origin, patch, overlap, batch_sample)
+    pred[vol32 == lo] = lo                                              # background mask (test_all.py:300)
     return VolumeResult(pred, len(kept), len(grid) - len(kept), per)

@@ -271,6 +271,22 @@ int diqt_linear(const float* x, int ldx, int rows, int k, const float* w, const 
 /* increments a device step counter (last node of the captured step graph) */
 int diqt_advance_step(int32_t* step, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Whole-volume inference around the sampler (data.py:139-202, utils_mine.py:25-67, test_all.py:239-300), fp32 volumes (d0, d1, d2).
+ * ------------------------------------------------------------------------------------------ */
+/* out[b] = volume[o0:o0+P, o1:o1+P, o2:o2+P] for the n_patches origins (DEVICE int32 [n][3]).  sub_f <= 1: out is (n, 1, P, P, P).
+ * sub_f = f > 1: every patch is written as f^3 sub-volumes of side P/f in the order of convertVolume2subVolume (utils_mine.py:25-42):
+ * out is (n * f^3, 1, P/f, P/f, P/f), which is what a batch_sample U-Net takes. */
+int diqt_gather_patches(const float* volume, int d0, int d1, int d2, const int32_t* origins, int n_patches, int patch, int sub_f,
+                        float* out, void* stream);
+/* The stitch loop of test_all.py:239-298 for the whole volume at once.  patches: (kept, P^3) in the layout diqt_gather_patches writes;
+ * slot_of_grid: DEVICE int32 [g0*g1*g2], the index of grid patch (i, j, k) in `patches` or -1 for a skipped patch (data.py:192-196).
+ * Every voxel takes the value of the LAST patch in grid order whose centre crop covers it (margin overlap/2, none at volume faces;
+ * `batch_sample` selects the :270-293 face rule; overlap >= patch: no crop), voxels no crop covers keep pred's value.  lowres != NULL:
+ * voxels with lowres == min_val are set to min_val (:300). */
+int diqt_stitch_patches(const float* patches, const int32_t* slot_of_grid, int g0, int g1, int g2, int stride, int patch, int overlap,
+                        int batch_sample, int sub_f, float* pred, int d0, int d1, int d2, const float* lowres, float min_val, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

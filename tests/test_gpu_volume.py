@@ -126,3 +126,33 @@ def test_engine_and_graph_survive_repeated_sample_calls():
         junk.pop()
     assert list(imagen.unets[1]._engines.values()) == [eng]
     assert next(iter(eng.sampler_cache.values())) is st and st.graph is graph
+
+
+def test_file_to_file_inference(tmp_path):
+    """NIfTI in -> z-score -> device patch grid -> Imagen.sample -> device stitch -> NIfTI out + metrics (test_all.py:182-316)."""
+    from diffusioniqt_b200 import Imagen, ImagenTrainer, NullUnet, Unet
+    from diffusioniqt_b200.infer import infer_nifti
+    from diffusioniqt_b200.nifti import load_nifti, save_nifti
+    P, T, N = 16, 3, 48
+    unet = Unet(**KW, img_size=P)
+    unet.load_state_dict(synthetic_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, seed=61))
+    configs = {"Data": {"norm": "z-score", "mean": 271.648, "std": 377.117}, "Train": {"batch_sample": False, "patch_size_sub": P},
+               "Eval": {"overlap": 8, "batch_size": 4}}
+    imagen = Imagen(unets=(NullUnet(), unet), configs=configs, image_sizes=(P, P), channels=1, min_bound=MIN_BOUND, timesteps=T,
+                    pred_objectives="x_start", dynamic_thresholding=False, cond_drop_prob=0.0).cuda()
+    trainer = ImagenTrainer(configs, imagen=imagen, use_ema=True)
+    raw = (synthetic_field((N, N, N), 90) * 300 + 400).clamp(min=0).numpy().astype(np.float32)
+    raw[:10, :20] = 0.0
+    affine = np.diag([1.5, 1.5, 1.5, 1.0])
+    save_nifti(raw, affine, tmp_path / "lr.nii.gz")
+    save_nifti(raw * 1.1, affine, tmp_path / "hr.nii.gz")
+    torch.manual_seed(7)
+    res = infer_nifti(trainer, configs, tmp_path / "lr.nii.gz", tmp_path / "pred.nii.gz", tmp_path / "hr.nii.gz", evaluate_kernel_size=3)
+    data, aff, _ = load_nifti(tmp_path / "pred.nii.gz")
+    assert data.shape == (N, N, N) and np.allclose(aff, affine)
+    assert np.array_equal(data.astype(np.float32), res.prediction.numpy())
+    assert res.n_patches > 0 and res.n_skipped > 0 and np.isfinite(res.prediction.numpy()).all()
+    low = (torch.from_numpy(raw) - 271.648) / 377.117
+    assert torch.equal(res.prediction[low == low.min()], torch.full_like(res.prediction[low == low.min()], float(low.min())))
+    assert float(res.prediction.min()) >= min(MIN_BOUND, float(low.min())) - 1e-6      # sampler clamp (:2157) / background / fill value
+    assert res.psnr is not None and 0.0 < res.ms_ssim <= 1.0

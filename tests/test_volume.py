@@ -99,3 +99,37 @@ def test_infer_volume_two_ranks_gloo():
         vol, n, per = ret[r]
         assert n == nkept and per == (nkept + 1) // 2
         assert np.allclose(vol, want, atol=1e-6)
+
+
+def test_sub_volume_retiling_matches_the_pinned_oracle():
+    """volume.split_sub_volumes / merge_sub_volumes against the oracle helpers (which are pinned on utils_mine.py)."""
+    from oracle import unet_oracle as uo
+    x = torch.randn(2, 12, 12, 12)
+    for f in (2, 3):
+        sub = V.split_sub_volumes(x, f)
+        for b in range(2):
+            want = uo.split_sub_volumes(x[b][None, None], f)[:, 0]
+            assert torch.equal(sub[b * f ** 3:(b + 1) * f ** 3], want)
+        assert torch.equal(V.merge_sub_volumes(sub, f), x)
+
+
+def test_infer_volume_batch_sample_layout_cpu():
+    """sub_f = 3: every 12^3 patch travels as 27 sub-volumes of 4^3 (data.py:147-150, test_all.py:230-231, 267-268) and is stitched with
+    the batch_sample face rule."""
+    import numpy as np
+    from oracle import stitch_oracle as so
+    N, P, stride, f = 28, 12, 8, 3
+    low = torch.randn(N, N, N)
+    low[:5] = low.min()
+    seen = []
+
+    def fake(lr):
+        assert lr.shape[1:] == (1, 4, 4, 4) and lr.shape[0] % 27 == 0
+        seen.append(lr.shape[0])
+        return lr * 2 + 1
+
+    res = V.infer_volume(fake, low, patch=P, overlap=stride, raw_lowres=low - low.min(), fill_value=-3.0, batch_sample=True, sub_f=f)
+    idxs = [i for i in so.patch_index_list(low.shape, P, stride) if not so.is_skipped((low - low.min()).numpy(), i, P)]
+    outs = [(low[i:i + P, j:j + P, k:k + P] * 2 + 1).numpy() for i, j, k in idxs]
+    want = so.background_mask(so.stitch(np.full((N, N, N), -3.0, np.float32), outs, idxs, P, stride, True), low.numpy())
+    assert torch.equal(res.volume, torch.from_numpy(want)) and seen and all(s == 27 for s in seen)
