@@ -14,7 +14,7 @@ def _volume(shape, seed, holes=True):
     g = torch.Generator().manual_seed(seed)
     v = torch.randn(*shape, generator=g)
     if holes:
-        v[: shape[0] // 3, : shape[1] // 2] = v.min()          # background: some patches fall under the 5 % rule
+        v[: shape[0] // 2 + 1] = v.min()                       # a background slab: the patches inside it fall under the 5 % rule
     return v
 
 
