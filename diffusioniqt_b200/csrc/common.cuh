@@ -39,12 +39,15 @@ bool pdl_enabled();  // DIQT_DISABLE_PDL=1 switches the attribute off (A/B measu
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Build-time variants for A/B measurements (tools/gpu_ab.sh):
-//   DIQT_PDL_LATE_TRIGGER=1  let the dependents launch only AFTER this kernel's own wait: at most two kernels of the chain are
-//                            resident at once (K+1 becomes resident when K-1 has completed), instead of an unbounded chain.
-//   DIQT_LOAD_NC=1           Vec<T>::load through the non-coherent path (LDG.CONSTANT) instead of ld.global.cg.
+// Build-time variants for A/B measurements (tools/gpu_ab.sh, profiles/r1m_summary.md):
+//   DIQT_PDL_LATE_TRIGGER=1  (default) let the dependents launch only AFTER this kernel's own wait: at most two kernels of the chain
+//                            are resident at once (K+1 becomes resident when K-1 has completed).  0: trigger at kernel entry, an
+//                            unbounded chain of blocked kernels may pile up on the SMs; measured 0.5-0.7 % slower.
+//   DIQT_LOAD_NC=1           Vec<T>::load through the non-coherent path (LDG.CONSTANT) instead of ld.global.cg; measured ~1 % faster,
+//                            not the default because its lines are only guaranteed fresh for data that is read-only over the whole
+//                            lifetime of the grid (see Vec<T>::load).
 #ifndef DIQT_PDL_LATE_TRIGGER
-#define DIQT_PDL_LATE_TRIGGER 0
+#define DIQT_PDL_LATE_TRIGGER 1
 #endif
 #ifndef DIQT_LOAD_NC
 #define DIQT_LOAD_NC 0

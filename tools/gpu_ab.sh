@@ -1,7 +1,7 @@
 #!/bin/bash
 # A/B of the build variants on one GPU box: short bench (200 iterations) + the back-to-back reproducibility tests per variant.
 OUT=gpurun_out; mkdir -p $OUT; : > $OUT/ab.log
-for v in default ${VARIANTS:-cg_late nc_early nc_late}; do
+for v in default ${VARIANTS:-cg_early nc_early nc_late}; do
   if [ $v = default ]; then unset DIQT_LIB_PATH; else export DIQT_LIB_PATH=$PWD/build/variants/$v.so; fi
   for rep in 1 2; do
     timeout 200 python bench.py --timesteps 200 --steps 2 --warmup 1 --no-cpu-baseline > $OUT/ab_$v.json 2> $OUT/ab_$v.err
