@@ -63,3 +63,27 @@ def test_forward_is_repeatable_and_fresh():
     assert a.data_ptr() != b.data_ptr() and torch.equal(a, b)
     c = unet(x * 0.5, None, time, lowres_cond_img=lr)
     assert not torch.equal(a, c)
+
+
+def test_full_size_patch_bf16_against_fp32_mode():
+    """BASELINE config 2 shape (driver U-Net, one 64^3 patch), too large for the CPU oracle in a test: the tensor-core path is compared
+    with the library's own fp32 exact mode (CUDA-core convs, itself tied to the oracle at 1e-5 per kernel on the small cases above),
+    plus the size-independent properties: repeatable bit for bit, and a batch of two equal patches gives two equal results."""
+    from diffusioniqt_b200 import Unet
+    from diffusioniqt_b200.synth import synthetic_field, synthetic_state_dict
+    kw = dict(FORWARD_CASES["driver_dim64_s16"]["unet"], img_size=64)
+    unet = Unet(**kw)
+    unet.load_state_dict(synthetic_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, seed=11))
+    unet = unet.cuda()
+    x, lr = synthetic_field((1, 1, 64, 64, 64), 3).cuda(), synthetic_field((1, 1, 64, 64, 64), 4).cuda()
+    t = torch.tensor([1.3], device="cuda")
+    unet.set_compute_dtype("bf16")
+    a = unet(x, None, t, lowres_cond_img=lr)
+    b = unet(x, None, t, lowres_cond_img=lr)
+    assert torch.equal(a, b) and torch.isfinite(a).all()
+    two = unet(torch.cat([x, x]), None, torch.cat([t, t]), lowres_cond_img=torch.cat([lr, lr]))
+    assert torch.equal(two[0], two[1])
+    assert rel_err(two[0].cpu(), a[0].cpu()) < 1e-2          # batch 2 takes the un-grouped statistics path: same values up to summation order
+    unet.set_compute_dtype("fp32")
+    ref = unet(x, None, t, lowres_cond_img=lr)
+    assert rel_err(a.cpu(), ref.cpu()) < 3e-2
