@@ -9,8 +9,8 @@
 // kernels at the edge of a block (patchify on the way in, the last ChanLayerNorm on the way out) translate rows with SubGeom.
 // Token tensors ([tokens][channels], token = (tz*g + ty)*g + tx over the merged volume) always use the merged order.
 //
-// Status: the token-side products of the N x N softmax attention run on CUDA cores in fp32 (flash-style, no N x N tensor in
-// memory); they are 0.4 % of a forward at the shipped geometry (1728 tokens).  A tcgen05 version is the next step for 13 824 tokens.
+// The N x N softmax attention has two kernels: the tcgen05 one in attn_tc.cu (bf16, head dim 64) and the fp32 CUDA-core one below
+// (flash-style, no N x N tensor in memory) for the other head dims and the fp32 exact mode.
 #include "common.cuh"
 
 namespace diqt {

@@ -1,0 +1,368 @@
+// Softmax attention on the 5th-gen tensor cores (SoftMaxAttention.forward imagen_pytorch3D.py:1087-1100, MultiHeadAttention.forward
+// :826-836): out = act( softmax_k(q k^T * scale) v ) per head, dim_head = 64, bf16 operands, fp32 accumulation in TMEM, nothing N x N in
+// memory.
+//
+// One CTA = 128 queries of one head.  Two passes over the key tiles (128 keys each), so the output accumulator never has to be rescaled:
+//   pass 1:  S = Q K_j^T (tcgen05.mma M128 N128 K64 -> TMEM) ; the softmax warps only take the row maximum m (no exponentials)
+//   pass 2:  S = Q K_j^T again ; P = exp(scale (s - m)) as bf16 into a 128B-swizzled shared tile, l += P ; O += P V_j (M128 N64 K128
+//            -> TMEM) ; the epilogue scales O by 1 / l
+// Q K^T is computed twice (tensor time is cheap) in exchange for no tcgen05.ld / st round trips of O between tiles.  Two CTAs fit an SM
+// (100 KB of shared memory, 256 TMEM columns each), so one CTA's softmax overlaps the other's MMA / TMA latency.
+// Operands are all K-major SWIZZLE_128B tiles written by TMA: Q and K straight from the [tokens][channels] q | k | v buffer, V from a
+// transposed copy V^T [channels][tokens] (written by attn_transpose_kernel; its padding columns must be zero).
+// Warp roles (192 threads): 0 TMA producer, 1 MMA issuer (owns TMEM), 2-5 softmax / epilogue (one query row per thread).
+#include <string.h>
+
+#include <new>
+
+#include "tc_common.cuh"
+
+namespace diqt {
+
+constexpr int AT_Q = 128, AT_K = 128, AT_D = 64;        // queries per CTA, keys per tile, head dim
+constexpr int AT_TILE = AT_Q * 128;                     // one [128 rows][64 bf16] tile: 16 KB
+constexpr int AT_VCHUNK = 64 * 128;                     // one [64 d rows][64 keys] tile of V^T: 8 KB
+constexpr int AT_THREADS = 192;
+
+struct AttnTcParams {
+  CUtensorMap q_map, k_map, vt_map;
+  __nv_bfloat16* out;
+  int ld_out, ntok, heads, q_col0, k_col0, act;
+  float c;  // scale * log2(e)
+  uint32_t idesc_s, idesc_o;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {  // arguments are <= 0 here
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tma_load_2d_as5(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int row0) {
+  tma_load_5d(dst, map, bar, c0, row0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 2) softmax_attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_s = smem;                       // 16 KB
+  uint8_t* k_s = q_s + AT_TILE;              // 2 stages x 16 KB
+  uint8_t* v_s = k_s + 2 * AT_TILE;          // 2 key chunks x 8 KB (one stage: V_j is only needed once P_j exists)
+  uint8_t* p_s = v_s + 2 * AT_VCHUNK;        // 2 key chunks x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(p_s + 2 * AT_TILE);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // 2
+  uint64_t* k_empty = bars + 3;       // 2
+  uint64_t* v_full = bars + 5;        // 2
+  uint64_t* v_empty = bars + 7;       // 2
+  uint64_t* s_full = bars + 9;        // 1
+  uint64_t* s_free = bars + 10;       // 1 (4 arrivals)
+  uint64_t* p_full = bars + 11;       // 1 (4 arrivals)
+  uint64_t* p_free = bars + 12;       // 1
+  uint64_t* o_full = bars + 13;       // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qtile = blockIdx.x, head = blockIdx.y;
+  const int nkt = (p.ntok + AT_K - 1) / AT_K;
+
+  if (warp == 0 && lane == 0) {
+    mbar_init(smem_u32(q_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&k_full[s]), 1);
+      mbar_init(smem_u32(&k_empty[s]), 1);
+      mbar_init(smem_u32(&v_full[s]), 1);
+      mbar_init(smem_u32(&v_empty[s]), 1);
+    }
+    mbar_init(smem_u32(s_full), 1);
+    mbar_init(smem_u32(s_free), 4);
+    mbar_init(smem_u32(p_full), 4);
+    mbar_init(smem_u32(p_free), 1);
+    mbar_init(smem_u32(o_full), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;          // columns [0, 128): S
+  const uint32_t tmem_o = tmem_base + 128;    // columns [128, 192): O
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(q_full), AT_TILE);
+      tma_load_2d_as5(smem_u32(q_s), &p.q_map, smem_u32(q_full), p.q_col0 + head * AT_D, qtile * AT_Q);
+      int ks = 0;
+      const int vs = 0;
+      uint32_t kph = 0, vph = 0;
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int j = 0; j < nkt; ++j) {
+          mbar_wait(smem_u32(&k_empty[ks]), kph ^ 1);
+          mbar_expect_tx(smem_u32(&k_full[ks]), AT_TILE);
+          tma_load_2d_as5(smem_u32(k_s + ks * AT_TILE), &p.k_map, smem_u32(&k_full[ks]), p.k_col0 + head * AT_D, j * AT_K);
+          if (++ks == 2) { ks = 0; kph ^= 1; }
+          if (pass == 1) {
+            mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1);
+            mbar_expect_tx(smem_u32(&v_full[vs]), 2 * AT_VCHUNK);
+            uint8_t* dst = v_s + vs * 2 * AT_VCHUNK;
+            tma_load_2d_as5(smem_u32(dst), &p.vt_map, smem_u32(&v_full[vs]), j * AT_K, head * AT_D);
+            tma_load_2d_as5(smem_u32(dst + AT_VCHUNK), &p.vt_map, smem_u32(&v_full[vs]), j * AT_K + 64, head * AT_D);
+            vph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform; the issuing lane is elected inside umma_bf16 / umma_commit) =====================
+    mbar_wait(smem_u32(q_full), 0);
+    tc_fence_after();
+    const uint64_t qdesc = make_sw128_desc(smem_u32(q_s));
+    int ks = 0, it = 0, pit = 0;
+    const int vs = 0;
+    uint32_t kph = 0, vph = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int j = 0; j < nkt; ++j) {
+        mbar_wait(smem_u32(&k_full[ks]), kph);
+        mbar_wait(smem_u32(s_free), (uint32_t)((it & 1) ^ 1));  // the softmax warps have read the previous S
+        tc_fence_after();
+        {
+          const uint64_t kdesc = make_sw128_desc(smem_u32(k_s + ks * AT_TILE));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem_s, qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), p.idesc_s, k != 0);
+          umma_commit(smem_u32(&k_empty[ks]));
+          umma_commit(smem_u32(s_full));
+        }
+        if (++ks == 2) { ks = 0; kph ^= 1; }
+        ++it;
+        if (pass == 1) {
+          mbar_wait(smem_u32(&v_full[vs]), vph);
+          mbar_wait(smem_u32(p_full), (uint32_t)(pit & 1));
+          tc_fence_after();
+          {
+            const uint32_t vb = smem_u32(v_s + vs * 2 * AT_VCHUNK);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const uint64_t pdesc = make_sw128_desc(smem_u32(p_s + c * AT_TILE));
+              const uint64_t vdesc = make_sw128_desc(vb + c * AT_VCHUNK);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_o, pdesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), p.idesc_o, (j | c | k) != 0);
+            }
+            umma_commit(smem_u32(&v_empty[vs]));
+            umma_commit(smem_u32(p_free));
+          }
+          vph ^= 1;
+          ++pit;
+        }
+      }
+    }
+    umma_commit(smem_u32(o_full));
+  } else {
+    // ===================== softmax / epilogue (warps 2..5): thread = one query row =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    float m = -INFINITY, l = 0.f;  // row maximum of the raw scores, sum of exp(scale (s - m))
+    int it = 0;
+    // ---- pass 1: row maximum
+    for (int j = 0; j < nkt; ++j, ++it) {
+      mbar_wait(smem_u32(s_full), (uint32_t)(it & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int c32 = 0; c32 < 4; ++c32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_s + lane_addr + (uint32_t)(c32 * 32), r);
+        tmem_ld_wait();
+        const int key0 = j * AT_K + c32 * 32;
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (key0 + i < p.ntok) m = fmaxf(m, __uint_as_float(r[i]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(s_free));
+    }
+    const float mc = m * p.c;  // key 0 always exists: m is finite
+    // ---- pass 2: probabilities -> shared memory (A operand of P V)
+    int pit = 0;
+    for (int j = 0; j < nkt; ++j, ++it, ++pit) {
+      mbar_wait(smem_u32(s_full), (uint32_t)(it & 1));
+      mbar_wait(smem_u32(p_free), (uint32_t)((pit & 1) ^ 1));  // the previous P V has finished reading the P tile
+      tc_fence_after();
+#pragma unroll 1
+      for (int c32 = 0; c32 < 4; ++c32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_s + lane_addr + (uint32_t)(c32 * 32), r);
+        tmem_ld_wait();
+        const int key0 = j * AT_K + c32 * 32;
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = key0 + 2 * i < p.ntok ? ex2_approx(fmaf(__uint_as_float(r[2 * i]), p.c, -mc)) : 0.f;
+          const float p1 = key0 + 2 * i + 1 < p.ntok ? ex2_approx(fmaf(__uint_as_float(r[2 * i + 1]), p.c, -mc)) : 0.f;
+          l += p0 + p1;
+          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+          packed[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        // 32 keys = 64 B of this row: four 16-byte units of the 128-byte swizzled row of key chunk (c32 >> 1)
+        uint8_t* rowp = p_s + (size_t)(c32 >> 1) * AT_TILE + (size_t)row * 128;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int unit = ((c32 & 1) * 4 + u) ^ (row & 7);
+          *reinterpret_cast<uint4*>(rowp + unit * 16) = make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();  // generic-proxy writes of P become visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(s_free));
+        mbar_arrive(smem_u32(p_full));
+      }
+    }
+    // ---- epilogue: O / l -> activation -> bf16 rows
+    const float inv_l = 1.f / l;
+    mbar_wait(smem_u32(o_full), 0);
+    tc_fence_after();
+    const int q = qtile * AT_Q + row;
+#pragma unroll 1
+    for (int c32 = 0; c32 < 2; ++c32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_o + lane_addr + (uint32_t)(c32 * 32), r);
+      tmem_ld_wait();
+      if (q < p.ntok) {
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float v0 = __uint_as_float(r[2 * i]) * inv_l, v1 = __uint_as_float(r[2 * i + 1]) * inv_l;
+          if (p.act == 1) { v0 = mish<false>(v0); v1 = mish<false>(v1); }
+          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+          packed[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)q * p.ld_out + head * AT_D + c32 * 32);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dst[u] = make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// vt[ch][tok] = v[tok][ch] for ch < channels, tok < ntok (32 x 32 tiles through shared memory)
+__global__ void __launch_bounds__(256) attn_transpose_kernel(const __nv_bfloat16* __restrict__ v, int ld, int ntok, int channels,
+                                                             __nv_bfloat16* __restrict__ vt, int ldt) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int tok = t0 + r, ch = c0 + tx;
+    tile[r][tx] = (tok < ntok && ch < channels) ? v[(size_t)tok * ld + ch] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int ch = c0 + r, tok = t0 + tx;
+    if (ch < channels && tok < ntok) vt[(size_t)ch * ldt + tok] = tile[tx][r];
+  }
+}
+
+struct AttnTcPlan {
+  AttnTcParams p;
+  const __nv_bfloat16* v;
+  __nv_bfloat16* vt;
+  int ld_v, npad, inner;
+  dim3 grid;
+  size_t smem;
+};
+
+}  // namespace diqt
+
+using namespace diqt;
+
+struct diqt_attn_plan {
+  AttnTcPlan a;
+};
+
+extern "C" int diqt_attn_tc_supported(int dtype, int dim_head, int ld_q, int ld_k, int ld_v, int ld_out) {
+  return dtype == DIQT_BF16 && dim_head == AT_D && ld_q % 8 == 0 && ld_k % 8 == 0 && ld_v % 8 == 0 && ld_out % 8 == 0;
+}
+
+extern "C" int diqt_attn_tc_workspace_bytes(int tokens, int heads, size_t* bytes) {
+  DIQT_REQUIRE(bytes && tokens > 0 && heads > 0, "attn_tc_workspace_bytes: bad arguments");
+  const size_t npad = ((size_t)tokens + 127) / 128 * 128;
+  *bytes = (size_t)heads * AT_D * npad * 2;
+  return DIQT_OK;
+}
+
+extern "C" int diqt_attn_tc_plan_create(const void* q, const void* k, const void* v, int ld_q, int ld_k, int ld_v, void* out, int ld_out, int tokens,
+                                        int heads, float scale, int act, void* workspace, diqt_attn_plan** plan) {
+  DIQT_REQUIRE(q && k && v && out && workspace && plan && tokens > 0 && heads > 0, "attn_tc_plan_create: bad arguments");
+  DIQT_REQUIRE(diqt_attn_tc_supported(DIQT_BF16, AT_D, ld_q, ld_k, ld_v, ld_out), "attn_tc_plan_create: pitches must be multiples of 8");
+  DIQT_REQUIRE(act == 0 || act == 1, "attn_tc_plan_create: act %d (0 none, 1 Mish)", act);
+  DIQT_REQUIRE(((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out | (uintptr_t)workspace) % 16 == 0, "attn_tc_plan_create: pointers must be 16-byte aligned");
+  diqt_attn_plan* pl = new (std::nothrow) diqt_attn_plan();
+  DIQT_REQUIRE(pl, "attn_tc_plan_create: out of host memory");
+  AttnTcPlan& a = pl->a;
+  memset(&a.p, 0, sizeof(a.p));
+  const int inner = heads * AT_D;
+  a.inner = inner;
+  a.npad = (tokens + 127) / 128 * 128;
+  a.v = (const __nv_bfloat16*)v;
+  a.vt = (__nv_bfloat16*)workspace;
+  a.ld_v = ld_v;
+  AttnTcParams& p = a.p;
+  p.out = (__nv_bfloat16*)out;
+  p.ld_out = ld_out; p.ntok = tokens; p.heads = heads; p.q_col0 = 0; p.k_col0 = 0; p.act = act;
+  p.c = scale * 1.4426950408889634f;
+  p.idesc_s = make_idesc_bf16(AT_Q, AT_K);
+  p.idesc_o = make_idesc_bf16(AT_Q, AT_D);
+  // q / k: [tokens][ld] rows, the head's 64 channels are one 128-byte box row; v^T: [inner][npad]
+  int rc = encode_volume_map(&p.q_map, q, inner, tokens, 1, 1, 1, ld_q, (int64_t)tokens * ld_q, (int64_t)tokens * ld_q, (int64_t)tokens * ld_q, AT_Q, 1, 1, 1);
+  if (rc == DIQT_OK)
+    rc = encode_volume_map(&p.k_map, k, inner, tokens, 1, 1, 1, ld_k, (int64_t)tokens * ld_k, (int64_t)tokens * ld_k, (int64_t)tokens * ld_k, AT_K, 1, 1, 1);
+  if (rc == DIQT_OK)
+    rc = encode_volume_map(&p.vt_map, workspace, a.npad, inner, 1, 1, 1, a.npad, (int64_t)inner * a.npad, (int64_t)inner * a.npad,
+                           (int64_t)inner * a.npad, AT_D, 1, 1, 1);
+  if (rc != DIQT_OK) {
+    delete pl;
+    return rc;
+  }
+  a.grid = dim3((tokens + AT_Q - 1) / AT_Q, heads);
+  a.smem = (size_t)AT_TILE * 6 + 256 + 1024;  // Q + 2 K + 2 V^T chunks (= 1 tile) + 2 P, barriers, alignment slack: two CTAs per SM
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(softmax_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) {
+      set_error("attn_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      delete pl;
+      return DIQT_ECUDA;
+    }
+    attr_done = true;
+  }
+  *plan = pl;
+  return DIQT_OK;
+}
+
+extern "C" void diqt_attn_tc_plan_destroy(diqt_attn_plan* plan) { delete plan; }
+
+extern "C" int diqt_attn_tc_run(const diqt_attn_plan* plan, void* stream) {
+  DIQT_REQUIRE(plan, "attn_tc_run: null plan");
+  const AttnTcPlan& a = plan->a;
+  cudaStream_t st = (cudaStream_t)stream;
+  const dim3 tgrid((a.p.ntok + 31) / 32, (a.inner + 31) / 32);
+  attn_transpose_kernel<<<tgrid, 256, 0, st>>>(a.v, a.ld_v, a.p.ntok, a.inner, a.vt, a.npad);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  softmax_attn_tc_kernel<<<a.grid, AT_THREADS, a.smem, st>>>(a.p);
+  return check_launch("softmax_attention_tc");
+}

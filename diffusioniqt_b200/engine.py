@@ -88,6 +88,8 @@ class UnetEngine:
         self.conv_impls = {}                  # site name -> resolved impl (for tests / reporting)
         # sampler states (schedule tables, captured step graphs) that bake this engine's buffer addresses live and die with it
         self.sampler_cache = {}
+        self._attn_plans: List[int] = []
+        self.attn_impls = {}                  # attention site -> "tc" | "simt"
         self._build()
 
     # ------------------------------------------------------------------ helpers
@@ -528,6 +530,27 @@ class UnetEngine:
             sp, sl, dp, dl = src.ptr, src.ld, dst.ptr, dst.ld
             ops.append(lambda st: L.check(lib.diqt_upsample_trilinear(sp, sl, dp, dl, dd, g, p, cdim, st), f"{name}.{what}"))
 
+        def softmax_attn(dst: Act, act: int, what: str):
+            """softmax_k(q k^T * scale) v per head into dst: the tcgen05 kernel when the shape allows (bf16, dim_head 64), else CUDA cores."""
+            dp, dl = dst.ptr, dst.ld
+            if (self.dtype == "bf16" and os.environ.get("DIQT_DISABLE_ATTN_TC", "0") != "1"
+                    and lib.diqt_attn_tc_supported(dd, dh, ldq, ldq, ldq, dl)):
+                nbytes = C.c_size_t(0)
+                L.check(lib.diqt_attn_tc_workspace_bytes(N, heads, C.byref(nbytes)), "attn_tc_workspace_bytes")
+                ws = torch.zeros(nbytes.value, dtype=torch.uint8, device=self.device)      # V^T, padding columns stay zero
+                self._keep.append(ws)
+                plan = C.c_void_p(0)
+                L.check(lib.diqt_attn_tc_plan_create(q_ptr, k_ptr, v_ptr, ldq, ldq, ldq, dp, dl, N, heads, scale, act, ws.data_ptr(), C.byref(plan)),
+                        f"{name}.{what}.plan")
+                self._attn_plans.append(plan.value)
+                pv = plan.value
+                self.attn_impls[f"{name}.{what}"] = "tc"
+                ops.append(lambda st: L.check(lib.diqt_attn_tc_run(pv, st), f"{name}.{what}"))
+            else:
+                self.attn_impls[f"{name}.{what}"] = "simt"
+                ops.append(lambda st: L.check(lib.diqt_softmax_attention(q_ptr, k_ptr, v_ptr, ldq, ldq, ldq, dp, dl, dd, N, heads, dh, scale, act, st),
+                                              f"{name}.{what}"))
+
         esz = 2 if self.dtype == "bf16" else 4
         F0, F1, F2 = buf(rows, cdim), buf(rows, cdim), buf(rows, cdim)
         T0, T1, T2, T3 = buf(N, cdim), buf(N, cdim), buf(N, cdim), buf(N, cdim)
@@ -555,9 +578,7 @@ class UnetEngine:
                 wq = mha.qkv.weight.detach().reshape(heads, dh, 3, cdim).permute(2, 0, 1, 3).reshape(3 * inner, cdim)
                 bq = mha.qkv.bias.detach().reshape(heads, dh, 3).permute(2, 0, 1).reshape(3 * inner)
                 conv1(T2, QKV, wq, bq, f"layers.{i}.qkv", vol=tok_vol, c_out=3 * inner)
-                op_, ol = O.ptr, O.ld
-                ops.append(lambda st, op_=op_, ol=ol, i=i: L.check(lib.diqt_softmax_attention(q_ptr, k_ptr, v_ptr, ldq, ldq, ldq, op_, ol, dd, N, heads, dh, scale, 0, st),
-                                                                   f"{name}.layers.{i}.mha"))
+                softmax_attn(O, 0, f"layers.{i}.mha")
                 conv1(O, T3, mha.projection.weight, mha.projection.bias, f"layers.{i}.projection", vol=tok_vol)
                 tok2 = buf(N, cdim)
                 combine(T3, tok2, N, b=tok, what=f"layers.{i}.res1")
@@ -617,8 +638,7 @@ class UnetEngine:
                 ops.append(lambda st, lname=lname: L.check(lib.diqt_linear_attention(q_ptr, k_ptr, v_ptr, ldq, op_, ol, dd, N, heads, dh, scale, 1, csp, cpp, st),
                                               f"{name}.{lname}.linear_attention"))
             else:
-                ops.append(lambda st, lname=lname: L.check(lib.diqt_softmax_attention(q_ptr, k_ptr, v_ptr, ldq, ldq, ldq, op_, ol, dd, N, heads, dh, scale, 1, st),
-                                              f"{name}.{lname}.softmax_attention"))
+                softmax_attn(O, 1, f"{lname}.softmax_attention")
             conv1(O, T3, attn.to_out[0].weight, None, f"{lname}.to_out.0", vol=tok_vol)
             ln(T3, T0, N, attn.to_out[1].g, what=f"{lname}.to_out.1")
             # reconstruct :952-959, then "+ x" :1148
@@ -698,6 +718,9 @@ class UnetEngine:
         for p in self._plans:
             self.lib.diqt_conv_plan_destroy(p)
         self._plans = []
+        for p in getattr(self, "_attn_plans", []):
+            self.lib.diqt_attn_tc_plan_destroy(p)
+        self._attn_plans = []
         self._ops = []
         self.sampler_cache = {}
 

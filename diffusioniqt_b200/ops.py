@@ -260,13 +260,29 @@ def linear_attention(qkv, heads, dim_head, act=1):
     return out
 
 
-def softmax_attention(qkv, heads, dim_head, act=1):
-    """qkv: (tokens, 3*heads*dim_head) holding q | k | v blocks -> (tokens, heads*dim_head)   (imagen_pytorch3D.py:1087-1100)."""
+def softmax_attention(qkv, heads, dim_head, act=1, impl="simt"):
+    """qkv: (tokens, 3*heads*dim_head) holding q | k | v blocks -> (tokens, heads*dim_head)   (imagen_pytorch3D.py:1087-1100).
+    impl "tc": the tcgen05 kernel (bf16, dim_head 64); "simt": the fp32 CUDA-core kernel."""
     lib = L.load()
     n, inner = qkv.shape[0], heads * dim_head
     esz = qkv.element_size()
     out = torch.empty(n, inner, dtype=qkv.dtype, device=qkv.device)
     p = qkv.data_ptr()
+    if impl == "tc":
+        if not lib.diqt_attn_tc_supported(_dt(qkv), dim_head, 3 * inner, 3 * inner, 3 * inner, inner):
+            raise L.DiqtError("softmax_attention(tc): needs bf16, dim_head 64")
+        nbytes = C.c_size_t(0)
+        L.check(lib.diqt_attn_tc_workspace_bytes(n, heads, C.byref(nbytes)), "attn_tc_workspace_bytes")
+        ws = torch.zeros(nbytes.value, dtype=torch.uint8, device=qkv.device)
+        plan = C.c_void_p(0)
+        L.check(lib.diqt_attn_tc_plan_create(p, p + inner * esz, p + 2 * inner * esz, 3 * inner, 3 * inner, 3 * inner, out.data_ptr(), inner, n, heads,
+                                             float(dim_head) ** -0.5, act, ws.data_ptr(), C.byref(plan)), "attn_tc_plan_create")
+        try:
+            L.check(lib.diqt_attn_tc_run(plan.value, L.current_stream()), "attn_tc_run")
+            torch.cuda.current_stream().synchronize()
+        finally:
+            lib.diqt_attn_tc_plan_destroy(plan.value)
+        return out
     L.check(lib.diqt_softmax_attention(p, p + inner * esz, p + 2 * inner * esz, 3 * inner, 3 * inner, 3 * inner, out.data_ptr(), inner, _dt(qkv), n, heads,
                                        dim_head, float(dim_head) ** -0.5, act, L.current_stream()), "softmax_attention")
     return out

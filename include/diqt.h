@@ -204,6 +204,19 @@ int diqt_linear_attention(const void* q, const void* k, const void* v, int ld_qk
 int diqt_softmax_attention(const void* q, const void* k, const void* v, int ld_q, int ld_k, int ld_v, void* out, int ld_out,
                            int dtype, int tokens, int heads, int dim_head, float scale, int act, void* stream);
 
+/* The same product on the tensor cores (csrc/attn_tc.cu): tcgen05.mma for Q K^T and P V with fp32 accumulators in TMEM, two passes over
+ * the key tiles (row max / sum, then probabilities), nothing N x N in memory.  bf16, dim_head = 64, pitches multiples of 8, 16-byte aligned
+ * pointers; q / k / v may be column blocks of one [tokens][3 * heads * 64] buffer.  `workspace`: diqt_attn_tc_workspace_bytes() bytes of
+ * device memory, ZERO-initialised once by the caller (it holds V^T padded to a multiple of 128 tokens).  A plan bakes the pointers
+ * (TMA descriptors); create it once outside stream capture. */
+typedef struct diqt_attn_plan diqt_attn_plan;
+int diqt_attn_tc_supported(int dtype, int dim_head, int ld_q, int ld_k, int ld_v, int ld_out);
+int diqt_attn_tc_workspace_bytes(int tokens, int heads, size_t* bytes);
+int diqt_attn_tc_plan_create(const void* q, const void* k, const void* v, int ld_q, int ld_k, int ld_v, void* out, int ld_out, int tokens,
+                             int heads, float scale, int act, void* workspace, diqt_attn_plan** plan);
+void diqt_attn_tc_plan_destroy(diqt_attn_plan* plan);
+int diqt_attn_tc_run(const diqt_attn_plan* plan, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Network ends.
  * ------------------------------------------------------------------------------------------ */

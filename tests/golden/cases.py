@@ -57,6 +57,10 @@ FORWARD_CASES = {
     "attn_linear_dim64_f2_s32": dict(unet=_unet(64, **_attn("linear", batch_sample_factor=2, img_size=64, attn_dim_head=64, attend_at_enc_depth=(1, 1, 1),
                                                             attend_at_enc_heads=(2, 2, 4), attend_at_enc=(True, False, True))),
                                      batch=8, size=32, weight_seed=20, input_seed=30, log_snr=[0.9] * 8, taps=("downs.0.2",)),
+    # softmax attention with head dim 64: the tcgen05 attention kernel (csrc/attn_tc.cu) in bf16 mode
+    "attn_softmax_dim64_f2_s32": dict(unet=_unet(64, **_attn("softmax", batch_sample_factor=2, img_size=64, attn_dim_head=64, attend_at_enc_depth=(1, 1, 1),
+                                                             attend_at_enc_heads=(2, 2, 2), attend_at_enc=(True, True, False), attend_at_middle_heads=4)),
+                                      batch=8, size=32, weight_seed=21, input_seed=31, log_snr=[-0.3] * 8, taps=("mid_attn",)),
 }
 
 # Full-sampler cases (Imagen.sample with injected noise)

@@ -148,3 +148,29 @@ def test_softmax_attention(name, dt, tol, n, heads, dh, act):
     want = F.mish(out) if act else out
     got = ops.softmax_attention(qkv.to(dt).cuda(), heads, dh, act=act)
     assert max_rel(got.float().cpu(), want) < tol
+
+
+@pytest.mark.parametrize("n,heads,act", [(128, 1, 0), (100, 2, 1), (300, 3, 0), (1728, 8, 1), (520, 2, 1)])
+def test_softmax_attention_tensor_core_kernel(n, heads, act):
+    """csrc/attn_tc.cu (tcgen05 Q K^T and P V, two passes) against the fp32 PyTorch product; bf16, dim_head 64; token counts that are
+    not multiples of the 128-key tile exercise the key mask and the query-row guard."""
+    from diffusioniqt_b200 import ops
+    dh, dt, tol = 64, torch.bfloat16, 1e-2
+    qkv = _q(_rand(n, 3 * heads * dh, seed=3), dt)
+    q, k, v = (_split_heads(t, heads) for t in qkv.chunk(3, dim=1))
+    att = (torch.einsum("bqd,bkd->bqk", q, k) * dh ** -0.5).softmax(dim=-1)
+    out = torch.einsum("bnd,bde->bne", att, v).permute(1, 0, 2).reshape(n, heads * dh)
+    want = F.mish(out) if act else out
+    got = ops.softmax_attention(qkv.to(dt).cuda(), heads, dh, act=act, impl="tc")
+    assert torch.isfinite(got).all()
+    assert max_rel(got.float().cpu(), want) < tol
+    # sharper logits (larger scale of q): the row maximum matters
+    qkv2 = qkv.clone()
+    qkv2[:, : heads * dh] *= 6.0
+    qkv2 = _q(qkv2, dt)
+    q, k, v = (_split_heads(t, heads) for t in qkv2.chunk(3, dim=1))
+    att = (torch.einsum("bqd,bkd->bqk", q, k) * dh ** -0.5).softmax(dim=-1)
+    out = torch.einsum("bnd,bde->bne", att, v).permute(1, 0, 2).reshape(n, heads * dh)
+    want = F.mish(out) if act else out
+    got = ops.softmax_attention(qkv2.to(dt).cuda(), heads, dh, act=act, impl="tc")
+    assert max_rel(got.float().cpu(), want) < tol

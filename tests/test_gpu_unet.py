@@ -89,3 +89,15 @@ def test_full_size_patch_bf16_against_fp32_mode():
     unet.set_compute_dtype("fp32")
     ref = unet(x, None, t, lowres_cond_img=lr)
     assert rel_err(a.cpu(), ref.cpu()) < 3e-2
+
+
+def test_softmax_attention_sites_use_the_tensor_core_kernel():
+    case = FORWARD_CASES["attn_softmax_dim64_f2_s32"]
+    unet = _gpu_unet(case, "bf16")
+    x, lr, time = build_inputs(case)
+    unet(x.cuda(), None, time.cuda(), lowres_cond_img=lr.cuda())
+    eng = next(iter(unet._engines.values()))
+    assert eng.attn_impls and set(eng.attn_impls.values()) == {"tc"}
+    unet32 = _gpu_unet(case, "fp32")
+    unet32(x.cuda(), None, time.cuda(), lowres_cond_img=lr.cuda())
+    assert set(next(iter(unet32._engines.values())).attn_impls.values()) == {"simt"}
