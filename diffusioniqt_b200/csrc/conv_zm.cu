@@ -43,6 +43,7 @@ constexpr int ZM_WSTAGES = 4;
 constexpr int ZM_THREADS = 256;
 constexpr int ZM_OUT_BYTES = 128 * 128;
 constexpr int ZM_MAX_COUT = 256;
+constexpr int ZM_MAX_SEG = 64;                          // z-segments per column (boundaries live in the kernel parameters)
 
 struct ZmParams {
   CUtensorMap in_map, out_map;
@@ -52,7 +53,8 @@ struct ZmParams {
   StatsGroups sink;   // optional grouped reduction of the statistics rows (common.cuh)
   int n, D, H, W;
   int KC, NH, c_out;  // c_in / 64, c_out / 64
-  int tiles_x, tiles_y, nseg, L;
+  int tiles_x, tiles_y, nseg;
+  short zs[ZM_MAX_SEG + 1];  // segment s covers output planes [zs[s], zs[s+1])
   int ipn, ipn_pad;   // work items per output-channel group (padded to even so that a slot pair shares its weights)
   int items, pairs;
   uint32_t idesc[3];  // N = 64, 128, 192
@@ -74,7 +76,7 @@ __device__ __forceinline__ ZmItem zm_item(const ZmParams& p, int item) {
   const int ty = t % p.tiles_y;
   it.b = t / p.tiles_y;
   it.x0 = tx * ZM_TX; it.y0 = ty * ZM_TY;
-  it.z0 = seg * p.L; it.z1 = min(p.D, it.z0 + p.L);
+  it.z0 = p.zs[seg]; it.z1 = p.zs[seg + 1];
   it.p_lo = max(it.z0 - 1, 0);
   it.niter = min(it.z1, p.D - 1) - it.p_lo + 1;
   return it;
@@ -477,23 +479,44 @@ int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // pick the z-segment length: minimise  rounds x (tensor cycles of the slot pair + fixed per-CTA cost); ties go to the longer
-  // segment (fewer halo planes streamed from L2)
+  // pick the z-segmentation: minimise  rounds x (tensor cycles of the slowest slot pair + fixed per-CTA cost); ties go to fewer
+  // segments (fewer halo planes streamed from L2).  Segments are balanced by COST, not length: an interior segment of n planes
+  // reads n + 2 input planes, the two at the ends of the volume n + 1, so the end segments get one more output plane
+  // (64 planes in 9 segments = 8,7,7,7,7,7,7,7,7: nine input planes each, 144 CTAs, instead of 8 x 8: ten input planes, 128 CTAs).
   const int64_t cols = (int64_t)d->n * p.tiles_x * p.tiles_y;
+  const int D = d->d0;
+  auto split = [&](int nseg, short* zs) {
+    // lengths: T - 1 at both ends, T - 2 inside, with T the smallest per-segment plane budget that covers D; surplus removed from the back
+    int T = 3;
+    while (true) {
+      const int cap = nseg == 1 ? T : 2 * (T - 1) + (nseg - 2) * (T - 2);
+      if (cap >= D) break;
+      ++T;
+    }
+    int len[ZM_MAX_SEG];
+    int total = 0;
+    for (int i = 0; i < nseg; ++i) { len[i] = (nseg == 1) ? D : ((i == 0 || i == nseg - 1) ? T - 1 : T - 2); total += len[i]; }
+    for (int i = nseg - 1; total > D; i = (i == 0 ? nseg - 1 : i - 1))
+      if (len[i] > 1) { --len[i]; --total; }
+    zs[0] = 0;
+    for (int i = 0; i < nseg; ++i) zs[i + 1] = (short)(zs[i] + len[i]);
+  };
   double best = 1e30;
-  int bestL = d->d0;
-  for (int L = d->d0; L >= 1; --L) {
-    const int nseg = (d->d0 + L - 1) / L;
+  int best_nseg = 1;
+  for (int nseg = 1; nseg <= std::min(D, ZM_MAX_SEG); ++nseg) {
+    short zs[ZM_MAX_SEG + 1];
+    split(nseg, zs);
+    if (zs[nseg] != D) continue;
     const int64_t ipn = cols * nseg, ipn_pad = ipn + (ipn & 1);
     const int64_t pairs = (int64_t)p.NH * ipn_pad / 2;
     const int64_t rounds = (pairs + sms - 1) / sms;
     int worst = 0;
-    for (int sgi = 0; sgi < nseg; ++sgi) worst = std::max(worst, zm_segment_cycles(sgi * L, std::min(d->d0, sgi * L + L), d->d0));
+    for (int sgi = 0; sgi < nseg; ++sgi) worst = std::max(worst, zm_segment_cycles(zs[sgi], zs[sgi + 1], D));
     const double cost = (double)rounds * (2.0 * worst * 36.0 * p.KC + 6000.0);
-    if (cost < best * 0.99) { best = cost; bestL = L; }
+    if (cost < best * 0.99) { best = cost; best_nseg = nseg; }
   }
-  p.L = bestL;
-  p.nseg = (d->d0 + p.L - 1) / p.L;
+  p.nseg = best_nseg;
+  split(p.nseg, p.zs);
   p.ipn = (int)(cols * p.nseg);
   p.ipn_pad = p.ipn + (p.ipn & 1);
   p.items = p.NH * p.ipn_pad;
