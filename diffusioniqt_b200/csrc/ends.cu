@@ -449,17 +449,20 @@ __global__ void __launch_bounds__(256) init_im2col_kernel(InitPlanes planes, int
     tile[idx] = v;
   }
   __syncthreads();
-  const int tasks = 8 * d2 * 8;
-  for (int t = threadIdx.x; t < tasks; t += blockDim.x) {
-    const int chunk = t & 7, vox = t >> 3;
+  // a thread keeps the same 16-byte chunk (8 columns) for all its tasks (blockDim is a multiple of 8): its 8 tile offsets live in registers
+  const int chunk = threadIdx.x & 7;
+  int off[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) off[j] = koff[chunk * 8 + j];
+  const int nvox = 8 * d2;
+  for (int vox = threadIdx.x >> 3; vox < nvox; vox += blockDim.x >> 3) {
     const int yl = vox / d2, x = vox - yl * d2;
     if (y0 + yl >= d1) break;  // later tasks of this thread have an even larger yl
     const int base = yl * W + x;
     uint32_t w[4];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
-      const int o0 = koff[chunk * 8 + 2 * jj], o1 = koff[chunk * 8 + 2 * jj + 1];
-      const float v0 = o0 >= 0 ? tile[o0 + base] : 0.f, v1 = o1 >= 0 ? tile[o1 + base] : 0.f;
+      const float v0 = off[2 * jj] >= 0 ? tile[off[2 * jj] + base] : 0.f, v1 = off[2 * jj + 1] >= 0 ? tile[off[2 * jj + 1] + base] : 0.f;
       __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
       w[jj] = *reinterpret_cast<uint32_t*>(&h);
     }
