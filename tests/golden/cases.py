@@ -76,6 +76,9 @@ SAMPLE_CASES = {
     "boundary_dim32_s8_t4": dict(unet=_unet(32, boundary=True, batch_sample=True), batch=27, size=8, timesteps=4,
                                  weight_seed=35, input_seed=45, noise_seed=55, min_bound=MIN_BOUND, norm="z-score",
                                  boundary=True),
+    # BASELINE.json configs[0] exactly: the reference's own CPU-runnable case (dim 32, one 32^3 patch, 50-step DDPM, fp32)
+    "baseline_cfg1_dim32_s32_t50": dict(unet=_unet(32), batch=1, size=32, timesteps=50, weight_seed=37, input_seed=47,
+                                        noise_seed=57, min_bound=MIN_BOUND, norm="z-score"),
     "skip_dim32_s8_t20_skip4": dict(unet=_unet(32), batch=1, size=8, timesteps=20, skip_steps=4, weight_seed=36,
                                     input_seed=46, noise_seed=56, min_bound=MIN_BOUND, norm="z-score"),
 }

@@ -102,3 +102,19 @@ def test_dynamic_threshold_path():
     img, _, _ = im.sample(batch_size=1, start_image_or_video=lr, start_at_unet_number=2, use_tqdm=False)
     want, _, _ = oracle_sample(case)
     assert max_rel(img.cpu(), want) < 2e-3
+
+
+def test_baseline_config1_bf16_against_the_reference_fixture():
+    """BASELINE.json configs[0] (dim 32, one 32^3 patch, 50-step DDPM) in bf16 against the fixture written by the reference itself
+    (tests/golden/make_golden.py): 50 chained forwards of a randomly initialised net amplify rounding, so the bound is on the rel-L2 of
+    the final patch (the fp32 exact mode is held to 2e-3 by test_sampler_fp32_matches_oracle_and_fixture)."""
+    case = SAMPLE_CASES["baseline_cfg1_dim32_s32_t50"]
+    im = _imagen(case, "bf16")
+    im.noise_override = _noise(case)
+    _, lr, _ = build_inputs(case)
+    img, _, _ = im.sample(batch_size=1, start_image_or_video=lr, start_at_unet_number=2, use_tqdm=False)
+    g = load_golden("sample_baseline_cfg1_dim32_s32_t50")
+    err = rel_err(img.cpu(), g["img"])
+    print(f"baseline cfg1 bf16 rel-L2 vs reference fixture: {err:.3e}")
+    assert err < 6e-2
+    assert float(img.min()) >= case["min_bound"] - 1e-6
