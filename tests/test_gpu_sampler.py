@@ -115,6 +115,6 @@ def test_baseline_config1_bf16_against_the_reference_fixture():
     img, _, _ = im.sample(batch_size=1, start_image_or_video=lr, start_at_unet_number=2, use_tqdm=False)
     g = load_golden("sample_baseline_cfg1_dim32_s32_t50")
     err = rel_err(img.cpu(), g["img"])
-    print(f"baseline cfg1 bf16 rel-L2 vs reference fixture: {err:.3e}")
-    assert err < 6e-2
+    print(f"baseline cfg1 bf16 rel-L2 vs reference fixture: {err:.3e}")      # measured 9.7e-3
+    assert err < 3e-2
     assert float(img.min()) >= case["min_bound"] - 1e-6
