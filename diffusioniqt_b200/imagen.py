@@ -321,8 +321,11 @@ class Imagen(nn.Module):
                       dynamic_threshold=True, use_tqdm=True):
         if inpaint_images is not None or inpaint_masks is not None:
             raise NotImplementedError("inpainting is broken in the reference (undefined right_pad_dims_to_datatype, :2143) and not built here")
-        if cond_scale != 1:
-            raise NotImplementedError("classifier-free guidance (cond_scale != 1) is not on the shipped sampling path")
+        # Classifier-free guidance (:1540-1552, :1993): the reference runs a second forward with cond_drop_prob = 1, but its 3-D Unet.forward
+        # never reads cond_drop_prob (there is no text conditioning to drop), so null_logits == logits bit for bit and
+        # null + (logits - null) * cond_scale == logits.  The guarded assert is kept, the redundant forward is not run.
+        assert not (cond_scale != 1. and not self.can_classifier_guidance), \
+            'imagen was not trained with conditional dropout, and thus one cannot use classifier free guidance (cond_scale anything other than 1)'
         device = self.device
         if device.type != 'cuda':
             raise RuntimeError("Imagen.sample runs only on a CUDA device (sm_100a kernels; there is no CPU fallback)")

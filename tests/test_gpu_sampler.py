@@ -118,3 +118,23 @@ def test_baseline_config1_bf16_against_the_reference_fixture():
     print(f"baseline cfg1 bf16 rel-L2 vs reference fixture: {err:.3e}")      # measured 9.7e-3
     assert err < 3e-2
     assert float(img.min()) >= case["min_bound"] - 1e-6
+
+
+def test_cond_scale_is_accepted_like_the_reference():
+    """cond_scale != 1 needs cond_drop_prob > 0 (:1993) and, for this text-free U-Net, changes nothing (see p_sample_loop)."""
+    from diffusioniqt_b200 import Imagen, NullUnet, Unet
+    case = SAMPLE_CASES["minmax_dim32_s8_t8"]
+    _, lr, _ = build_inputs(case)
+    outs = []
+    for drop, scale in ((0.1, 1.0), (0.1, 3.0)):
+        unet = Unet(**dict(case["unet"], img_size=case["size"]))
+        unet.load_state_dict(weights_for(case))
+        S = case["size"]
+        im = Imagen(unets=(NullUnet(), unet), configs=make_configs(case), image_sizes=(S, S), channels=1, min_bound=case["min_bound"],
+                    timesteps=case["timesteps"], pred_objectives="x_start", dynamic_thresholding=False, cond_drop_prob=drop).cuda()
+        im.noise_override = _noise(case)
+        outs.append(im.sample(batch_size=1, start_image_or_video=lr, start_at_unet_number=2, cond_scale=scale, use_tqdm=False)[0])
+    assert torch.equal(outs[0], outs[1])
+    im = _imagen(case, "bf16")                       # cond_drop_prob = 0
+    with pytest.raises(AssertionError):
+        im.sample(batch_size=1, start_image_or_video=lr, start_at_unet_number=2, cond_scale=2.0, use_tqdm=False)

@@ -74,3 +74,16 @@ def test_flop_count_matches_survey():
     assert abs(uo.count_flops(spec, 1, 64) / 1e9 - 1488.44) < 0.01
     spec32 = uo.UnetSpec(dim=32, init_dim=32, dim_mults=(1, 2, 4), num_resnet_blocks=(2, 2, 2), channels=1, lowres_cond=True, deep_feature=False)
     assert abs(uo.count_flops(spec32, 1, 32) / 1e9 - 46.57) < 0.01
+
+
+def test_reference_cond_scale_is_an_identity_for_the_3d_unet(ref):
+    """The claim behind Imagen.p_sample_loop's handling of cond_scale != 1: the reference's 3-D Unet.forward ignores cond_drop_prob, so
+    its classifier-free-guidance double forward (:1540-1552) returns the plain forward bit for bit."""
+    case = FORWARD_CASES["deep_dim32_s8"]
+    unet = ref.Unet(**unet_kwargs_for_reference(case)).eval()
+    fill_module_(unet, seed=case["weight_seed"])
+    x, lr, time = build_inputs(case)
+    with torch.no_grad():
+        plain = unet(x, None, time, lowres_cond_img=lr)
+        guided = unet.forward_with_cond_scale(x, None, time, lowres_cond_img=lr, cond_scale=3.0)
+    assert torch.equal(plain, guided)
