@@ -6,6 +6,8 @@
 // nn.Mish (:547, 563), SE3D (:617-632), residual add (:612).
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace diqt {
@@ -557,7 +559,7 @@ static int scale_residual_impl(const void* h, int ld_h, const void* res, int ld_
   DIQT_REQUIRE(h && res && out && nblk > 0, "scale_residual: bad arguments");
   DIQT_REQUIRE(c % vec == 0 && ld_h % vec == 0 && ld_res % vec == 0 && ld_out % vec == 0 && c / vec <= 256,
                "scale_residual: c=%d not a multiple of %d", c, vec);
-  RowMap m = make_rowmap(c, vec, 512);
+  RowMap m = make_rowmap(c, vec, 512);  // one 512-thread CTA per SM; 2 x 256 or 4 x 256 threads per SM measured no better (r1s A/B)
   dim3 grid(nblk, n);
   size_t sh = partial ? (size_t)2 * m.lanes * c * sizeof(float) : 0;
   SeParams sev = se;
