@@ -45,3 +45,22 @@ def test_bad_arguments_are_reported_without_a_gpu():
         lib.check(rc, "conv_packed_bytes")
     d.mode, d.impl, d.dtype = lib.CONV_K3, lib.IMPL_TC, lib.F32   # tcgen05 kernel is bf16 only
     assert h.diqt_conv_packed_bytes(ctypes.byref(d), ctypes.byref(nbytes)) == -3
+
+
+def test_missing_library_fails_loudly():
+    """No CPU / PyTorch fallback: without the built kernel library the product path raises instead of computing something else."""
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); os.environ['DIQT_LIB_PATH'] = '/nonexistent/libdiqt_b200.so'\n"
+            "from diffusioniqt_b200 import lib\n"
+            "try:\n    lib.load()\nexcept lib.DiqtError as e:\n    print('RAISED', 'no CPU or PyTorch fallback' in str(e))\n") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert "RAISED True" in out.stdout, out.stdout + out.stderr
+
+
+def test_product_package_does_not_import_the_oracle():
+    """oracle/ is test infrastructure: nothing under diffusioniqt_b200/ may import it."""
+    import glob
+    for path in glob.glob(os.path.join(ROOT, "diffusioniqt_b200", "**", "*.py"), recursive=True):
+        text = open(path).read()
+        assert "import oracle" not in text and "from oracle" not in text, path
