@@ -167,6 +167,44 @@ def time_dominant_kernel(size, batch, reps=20):
     return dict(ms=ms, ms_min=min(times), flops=flops, tflops=flops / (ms * 1e-3) / 1e12, kernel=kernel)
 
 
+def time_elementwise_kernel(size, batch, reps=20):
+    """The bandwidth-bound companion of the dominant kernel: GroupNorm + FiLM + Mish apply (y = mish(a*x + b), 1 read + 1 write) over a
+    64-channel full-resolution tensor, alone, CUDA events, rotating buffers (each 32 MiB at 64^3)."""
+    from diffusioniqt_b200 import lib as L
+    lib = L.load()
+    dev = torch.device("cuda")
+    n, c = batch, 64
+    vox = size ** 3
+    bufs = [(torch.randn(n * vox, c, device=dev).bfloat16(), torch.empty(n * vox, c, device=dev, dtype=torch.bfloat16)) for _ in range(4)]
+    a = torch.rand(n * c, device=dev) + 0.5
+    b = torch.randn(n * c, device=dev) * 0.1
+    nblk = max(1, 592 // n)
+
+    def run(i, st):
+        x, y = bufs[i % len(bufs)]
+        L.check(lib.diqt_affine_mish(x.data_ptr(), c, y.data_ptr(), c, L.BF16, n, vox, c, a.data_ptr(), b.data_ptr(), nblk, 0, 0, st))
+
+    for i in range(4):
+        run(i, L.current_stream())
+    torch.cuda.synchronize()
+    # a ~15 us kernel is shorter than a Python launch: replay `reps` launches as one CUDA graph so the host is out of the measurement
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(reps):
+            run(i, L.current_stream())
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / (3 * reps)
+    nbytes = 2.0 * n * vox * c * 2
+    return dict(ms=ms, bytes=nbytes, gbs=nbytes / (ms * 1e-3) / 1e9)
+
+
 def cpu_baseline(size, timesteps, batch, denoise_steps, threads=None):
     """The CPU oracle port (same algorithm as the reference's CPU sampler) on a bounded sample: `denoise_steps`
     iterations of the sampler at the benchmark shape; patches/s is extrapolated to `timesteps` iterations."""
@@ -344,12 +382,17 @@ def main():
                         peak_source=peaks["source"] + " (burst: kernel timed alone)",
                         whole_step=dict(achieved=step_tflops, peak=peaks["sustained"], frac=step_tflops / peaks["sustained"], unit="TFLOP/s",
                                         note="all FLOPs of the U-Net / wall time of the sampler, per GPU, vs sustained bf16 peak"))
+        ew = time_elementwise_kernel(S, B)
+        roofline_hbm = dict(bound="hbm", kernel="affine_mish_kernel (GroupNorm+FiLM+Mish apply) 64 ch @%d^3 (batch %d)" % (S, B), achieved=ew["gbs"],
+                            peak=peaks["hbm"], unit="GB/s", frac=ew["gbs"] / peaks["hbm"], ms_per_launch=ew["ms"], bytes_per_launch=ew["bytes"],
+                            note="second-largest kernel class of the step (38 launches per iteration); algorithmic bytes = 1 read + 1 write, 20 launches "
+                                 "over rotating buffers replayed as one CUDA graph, CUDA events around the replays")
         line = dict(metric="3D patches/sec (full denoise loop)", value=value, unit="patches/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
                     config=workload_config(args), clocks=clk,
                     e2e=dict(value=patches / (e2e_ms * 1e-3), unit="patches/s", h2d_bytes_per_step=B * S ** 3 * 4, d2h_bytes_per_step=3 * B * S ** 3 * 4),
                     gpu_launches=int(graph_launches + eager_launches), ms_per_denoise_iteration=ms_per_step / args.timesteps,
-                    roofline=roofline)
+                    roofline=roofline, roofline_elementwise=roofline_hbm)
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(S, args.timesteps, B, args.cpu_denoise_steps)
         print(json.dumps(line), flush=True)
