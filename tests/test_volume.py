@@ -133,3 +133,54 @@ def test_infer_volume_batch_sample_layout_cpu():
     outs = [(low[i:i + P, j:j + P, k:k + P] * 2 + 1).numpy() for i, j, k in idxs]
     want = so.background_mask(so.stitch(np.full((N, N, N), -3.0, np.float32), outs, idxs, P, stride, True), low.numpy())
     assert torch.equal(res.volume, torch.from_numpy(want)) and seen and all(s == 27 for s in seen)
+
+
+class _FakeSampler:
+    """Stands in for ImagenTrainer / Imagen on the CPU: same `.sample(...)` keywords as test_all.py:234, output = 2 * lr + 1."""
+
+    def __init__(self):
+        self.calls = []
+
+    def sample(self, batch_size=1, skip_steps=None, return_all_outputs=False, return_pil_images=False, start_image_or_video=None,
+               start_at_unet_number=1, **kw):
+        assert start_at_unet_number == 2 and batch_size == start_image_or_video.shape[0]
+        self.calls.append(tuple(start_image_or_video.shape))
+        return start_image_or_video * 2 + 1, [], []
+
+
+@pytest.mark.parametrize("batch_sample", [False, True])
+def test_infer_nifti_file_to_file_on_cpu(tmp_path, batch_sample):
+    """The host side of test_all.py:182-316 (NIfTI in, z-score, patch grid / skip rule, stitch, mask, NIfTI out, metrics) with a stand-in
+    sampler, against the loop-by-loop oracle; `batch_sample` routes every 24^3 patch through 27 sub-volumes of 8^3."""
+    import numpy as np
+    from diffusioniqt_b200.infer import infer_nifti
+    from diffusioniqt_b200.nifti import load_nifti, save_nifti
+    from oracle import stitch_oracle as so
+    N, sub, stride = 48, (8 if batch_sample else 16), 8      # 48: the smallest side with five MS-SSIM scales of a 3-wide window
+    P = sub * 3 if batch_sample else sub
+    mean, std = 271.648, 377.117
+    cfg = {"Data": {"norm": "z-score", "mean": mean, "std": std},
+           "Train": {"batch_sample": batch_sample, "batch_sample_factor": 3, "patch_size_sub": sub}, "Eval": {"overlap": stride, "batch_size": 5}}
+    rs = np.random.RandomState(3)
+    raw = np.abs(rs.standard_normal((N, N, N)).astype(np.float32)) * 300
+    raw[:P + 2] = 0.0                                            # air: skipped patches
+    affine = np.diag([2.0, 2.0, 2.0, 1.0])
+    save_nifti(raw, affine, tmp_path / "lr.nii.gz")
+    save_nifti(raw * 1.05 + 3, affine, tmp_path / "hr.nii")
+    fake = _FakeSampler()
+    res = infer_nifti(fake, cfg, tmp_path / "lr.nii.gz", tmp_path / "out.nii.gz", tmp_path / "hr.nii", device="cpu", evaluate_kernel_size=3)
+    low = (raw - mean) / std
+    idxs = [i for i in so.patch_index_list(raw.shape, P, stride) if not so.is_skipped(raw, i, P)]
+    outs = [low[i:i + P, j:j + P, k:k + P] * 2 + 1 for i, j, k in idxs]
+    want = so.background_mask(so.stitch(np.full(raw.shape, (0 - mean) / std, np.float32), outs, idxs, P, stride, batch_sample), low)
+    assert res.n_patches == len(idxs) and res.n_skipped > 0
+    assert np.allclose(res.prediction.numpy(), want, atol=1e-6)
+    data, aff, _ = load_nifti(tmp_path / "out.nii.gz")
+    assert np.array_equal(data.astype(np.float32), res.prediction.numpy()) and np.allclose(aff, affine)
+    assert res.psnr is not None and res.ms_ssim is not None
+    side = sub
+    assert all(c[1:] == (1, side, side, side) for c in fake.calls)
+    if batch_sample:
+        assert all(c[0] == 27 for c in fake.calls)               # one 24^3 patch = 27 sub-volumes per call (test_all.py:184-185)
+    else:
+        assert max(c[0] for c in fake.calls) == 5                # Eval.batch_size patches per call
