@@ -184,3 +184,29 @@ def test_infer_nifti_file_to_file_on_cpu(tmp_path, batch_sample):
         assert all(c[0] == 27 for c in fake.calls)               # one 24^3 patch = 27 sub-volumes per call (test_all.py:184-185)
     else:
         assert max(c[0] for c in fake.calls) == 5                # Eval.batch_size patches per call
+
+
+def test_infer_volume_edge_cases_cpu():
+    """Empty and ragged inputs: every patch skipped (an all-air volume), a volume that holds exactly one patch, a ragged last batch."""
+    P, stride = 8, 4
+    calls = []
+
+    def fake(lr):
+        calls.append(lr.shape[0])
+        return lr + 1
+
+    air = torch.zeros(16, 16, 16)
+    res = V.infer_volume(fake, (air - 1.0), patch=P, overlap=stride, raw_lowres=air, fill_value=-9.0)
+    assert res.n_patches == 0 and res.n_skipped == 27 and not calls
+    assert torch.equal(res.volume, torch.full((16, 16, 16), -1.0))          # background mask: every voxel equals the minimum
+    one = torch.rand(P, P, P) + 0.5
+    res = V.infer_volume(fake, one, patch=P, overlap=stride, fill_value=0.0)
+    assert res.n_patches == 1 and calls == [1]
+    want = one + 1
+    want[one == one.min()] = one.min()
+    assert torch.equal(res.volume, want)
+    calls.clear()
+    vol = torch.rand(16, 16, 16) + 0.5
+    res = V.infer_volume(fake, vol, patch=P, overlap=stride, batch_size=4)
+    assert res.n_patches == 27 and calls == [4] * 6 + [3]
+    assert V.shard_range(0, 1, 4) == (0, 0, 0) and V.shard_range(5, 3, 4) == (5, 5, 2)
