@@ -471,6 +471,72 @@ __global__ void __launch_bounds__(256) init_im2col_kernel(InitPlanes planes, int
   }
 }
 
+
+// ---- CrossEmbedLayer as init conv (imagen_pytorch3D.py:661-686, :1289-1291; the constructor default, init_cross_embed=True): several
+// Conv3d(c_in, dim_scale, k, stride 1, padding (k-1)/2) with k in e.g. (3, 7, 15) over the same input, concatenated along channels.
+// One launch per kernel size: one thread = one voxel x 16 output channels; the weights of one dz-slab ([k*k][c_in][16] floats) are
+// staged in shared memory per step, every input value is read once per slab (L1-cached fp32 planes) and feeds 16 FMAs.
+// 15^3 x 2 x 16 MACs per voxel is CUDA-core work by construction (K = 2 input channels); it is what the reference computes.
+template <typename T>
+__global__ void __launch_bounds__(128) init_conv_k_kernel(InitPlanes planes, int c_in, int k, const float* __restrict__ w /*[k^3][c_in][nco]*/,
+                                                         const float* __restrict__ bias, T* __restrict__ out, int ld_out, int co_off, int nco,
+                                                         int n, int d0, int d1, int d2) {
+  extern __shared__ float sw[];  // [k*k][c_in][16]
+  const int64_t vol = (int64_t)d0 * d1 * d2, total = (int64_t)n * vol;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = idx < total;
+  const int pad = (k - 1) / 2, kk = k * k;
+  int b = 0, z = 0, y = 0, x = 0;
+  if (live) {
+    b = (int)(idx / vol);
+    int64_t r = idx - (int64_t)b * vol;
+    z = (int)(r / ((int64_t)d1 * d2));
+    r -= (int64_t)z * d1 * d2;
+    y = (int)(r / d2);
+    x = (int)(r - (int64_t)y * d2);
+  }
+  for (int co0 = 0; co0 < nco; co0 += 16) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = (co0 + j < nco) ? bias[co0 + j] : 0.f;
+    for (int dz = 0; dz < k; ++dz) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < kk * c_in * 16; i += blockDim.x) {
+        const int j = i & 15, tc = i >> 4;  // tc = tap_in_slab * c_in + ci
+        sw[i] = (co0 + j < nco) ? w[((size_t)dz * kk * c_in + tc) * nco + co0 + j] : 0.f;
+      }
+      __syncthreads();
+      const int zz = z + dz - pad;
+      if (!live || zz < 0 || zz >= d0) continue;
+      for (int dy = 0; dy < k; ++dy) {
+        const int yy = y + dy - pad;
+        if (yy < 0 || yy >= d1) continue;
+        for (int dx = 0; dx < k; ++dx) {
+          const int xx = x + dx - pad;
+          if (xx < 0 || xx >= d2) continue;
+          const int64_t off = ((int64_t)zz * d1 + yy) * d2 + xx;
+          const float* wt = sw + (size_t)(dy * k + dx) * c_in * 16;
+          for (int ci = 0; ci < c_in; ++ci) {
+            const float* pl = planes.p[0];
+            long long ps = planes.stride[0];
+#pragma unroll
+            for (int q = 1; q < kInitMaxCin; ++q)
+              if (ci == q) { pl = planes.p[q]; ps = planes.stride[q]; }
+            const float v = __ldg(pl + (int64_t)b * ps + off);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[j] = fmaf(v, wt[ci * 16 + j], acc[j]);
+          }
+        }
+      }
+    }
+    if (live) {
+      T* orow = out + idx * ld_out + co_off + co0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (co0 + j < nco) orow[j] = from_float<T>(acc[j]);
+    }
+  }
+}
 }  // namespace diqt
 
 using namespace diqt;
@@ -478,6 +544,35 @@ using namespace diqt;
 extern "C" int diqt_abi_version(void) { return DIQT_ABI_VERSION; }
 extern "C" const char* diqt_last_error(void) { return g_err; }
 extern "C" uint64_t diqt_launch_count(void) { return g_launches.load(); }
+
+extern "C" int diqt_init_conv_k(const float* const* planes, const int64_t* plane_stride, int c_in, int k, const float* w, const float* bias, void* out,
+                                int ld_out, int co_off, int nco, int dtype, int n, int d0, int d1, int d2, void* stream) {
+  DIQT_REQUIRE(planes && plane_stride && w && bias && out && n > 0 && d0 > 0 && d1 > 0 && d2 > 0, "init_conv_k: bad arguments");
+  DIQT_REQUIRE(c_in > 0 && c_in <= kInitMaxCin, "init_conv_k: c_in=%d (max %d)", c_in, kInitMaxCin);
+  DIQT_REQUIRE(k >= 1 && k % 2 == 1 && k <= 31, "init_conv_k: kernel size %d (odd, <= 31)", k);
+  DIQT_REQUIRE(nco > 0 && co_off >= 0 && co_off + nco <= ld_out, "init_conv_k: channel slice [%d, %d) does not fit pitch %d", co_off, co_off + nco, ld_out);
+  DIQT_REQUIRE(dtype == DIQT_F32 || dtype == DIQT_BF16, "init_conv_k: bad dtype %d", dtype);
+  InitPlanes ip;
+  for (int i = 0; i < kInitMaxCin; ++i) {
+    ip.p[i] = i < c_in ? planes[i] : nullptr;
+    ip.stride[i] = i < c_in ? plane_stride[i] : 0;
+  }
+  const size_t sh = (size_t)k * k * c_in * 16 * sizeof(float);
+  DIQT_REQUIRE(sh <= 160 * 1024, "init_conv_k: weight slab of %zu bytes does not fit shared memory", sh);
+  const int64_t total = (int64_t)n * d0 * d1 * d2;
+  const unsigned blocks = (unsigned)((total + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DIQT_BF16) {
+    auto kern = init_conv_k_kernel<__nv_bfloat16>;
+    if (sh > 48 * 1024) DIQT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    kern<<<blocks, 128, sh, st>>>(ip, c_in, k, w, bias, (__nv_bfloat16*)out, ld_out, co_off, nco, n, d0, d1, d2);
+  } else {
+    auto kern = init_conv_k_kernel<float>;
+    if (sh > 48 * 1024) DIQT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+    kern<<<blocks, 128, sh, st>>>(ip, c_in, k, w, bias, (float*)out, ld_out, co_off, nco, n, d0, d1, d2);
+  }
+  return check_launch("init_conv_k");
+}
 
 extern "C" int diqt_init_im2col(const float* const* planes, const int64_t* plane_stride, int c_in, void* col, int n, int d0, int d1, int d2,
                                 void* stream) {

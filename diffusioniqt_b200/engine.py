@@ -353,7 +353,8 @@ class UnetEngine:
         xp, xl, c0, nin, cn = x.ptr, x.ld, dims[0], u.init_channels, self.conv_n
         planes_ref, strides_ref = self._planes, self._pstrides
         sf0, sh0 = self.level_sub[0]
-        self.init_conv_tc = (self.dtype == "bf16" and self.sub_f <= 1 and 27 * nin <= 64 and c0 % 64 == 0 and self.impl != L.IMPL_SIMT
+        cross_embed = hasattr(u.init_conv, "convs")
+        self.init_conv_tc = (not cross_embed and self.dtype == "bf16" and self.sub_f <= 1 and 27 * nin <= 64 and c0 % 64 == 0 and self.impl != L.IMPL_SIMT
                              and os.environ.get("DIQT_DISABLE_INIT_TC", "0") != "1")
         if self.init_conv_tc:
             # K = 27 * c_in = 54 is not a tensor-core shape as a 3x3x3 conv, but it is as a 1x1x1 conv over an im2col'ed K = 64 tensor:
@@ -369,6 +370,19 @@ class UnetEngine:
             if self._last_conv_stats:
                 x.stats = self._last_conv_stats
                 self._pp ^= 1
+        elif cross_embed:
+            # CrossEmbedLayer (:661-686): one direct conv per kernel size into its channel slice of x
+            co_off = 0
+            for conv in u.init_conv.convs:
+                k, nco = int(conv.kernel_size[0]), int(conv.out_channels)
+                w = conv.weight.detach().to(self.device, torch.float32)                       # (nco, nin, k, k, k)
+                wk = self._f32(w.permute(2, 3, 4, 1, 0).reshape(k ** 3, nin, nco).contiguous())   # [tap][ci][co]
+                bk = self._f32(conv.bias)
+                wp, bp = wk.data_ptr(), bk.data_ptr()
+                ops.append(lambda st, k=k, nco=nco, wp=wp, bp=bp, co_off=co_off: L.check(
+                    lib.diqt_init_conv_k(planes_ref, strides_ref, nin, k, wp, bp, xp, xl, co_off, nco, dd, cn, d0, d1, d2, st), f"init_conv.convs(k={k})"))
+                co_off += nco
+            assert co_off == c0, (co_off, c0)
         else:
             self.w_init = torch.empty(27 * u.init_channels * dims[0], dtype=torch.float32, device=self.device)
             wi = self._f32(u.init_conv.weight)

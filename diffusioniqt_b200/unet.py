@@ -103,6 +103,21 @@ class PixelShuffleUpsample(_NoForward):
         nn.init.zeros_(conv.bias.data)
 
 
+class CrossEmbedLayer(_NoForward):
+    """imagen_pytorch3D.py:661-686: parallel convs of several kernel sizes over the same input, concatenated along channels."""
+
+    def __init__(self, dim_in, kernel_sizes, dim_out=None, stride=2):
+        super().__init__()
+        assert all((t % 2) == (stride % 2) for t in kernel_sizes)
+        dim_out = dim_out if dim_out is not None else dim_in
+        kernel_sizes = sorted(kernel_sizes)
+        num_scales = len(kernel_sizes)
+        dim_scales = [int(dim_out / (2 ** i)) for i in range(1, num_scales)]
+        dim_scales = [*dim_scales, dim_out - sum(dim_scales)]
+        self.kernel_sizes, self.dim_scales, self.stride = kernel_sizes, dim_scales, stride
+        self.convs = nn.ModuleList([nn.Conv3d(dim_in, ds, k, stride=stride, padding=(k - stride) // 2) for k, ds in zip(kernel_sizes, dim_scales)])
+
+
 def Downsample(dim, dim_out=None):
     """pixel-unshuffle (parameter-free, index 0) + 1x1x1 conv (index 1)  (imagen_pytorch3D.py:489-496)."""
     dim_out = dim_out if dim_out is not None else dim
@@ -177,8 +192,8 @@ class Unet(nn.Module):
         attend_at_enc = tuple(attend_at_enc)[:num_layers] if isinstance(attend_at_enc, (list, tuple)) else (attend_at_enc,) * num_layers
         # -------- options of the reference this build does not take
         unsupported = []
-        if init_cross_embed:
-            unsupported.append("init_cross_embed=True (CrossEmbedLayer init conv; the drivers pass False, train.py:91)")
+        if init_cross_embed and boundary:
+            unsupported.append("init_cross_embed=True with boundary=True (boundary_pad followed by padded convs changes the volume size in the reference, :1587-1589)")
         if cross_embed_downsample:
             unsupported.append("cross_embed_downsample=True")
         if memory_efficient:
@@ -220,7 +235,10 @@ class Unet(nn.Module):
         # NB: the reference does not widen init_conv for self_cond (imagen_pytorch3D.py:1273-1286)
         init_dim = init_dim if init_dim is not None else dim
         self.init_channels = init_channels
-        self.init_conv = nn.Conv3d(init_channels, init_dim, 3) if boundary else nn.Conv3d(init_channels, init_dim, 3, padding=1)
+        if init_cross_embed:    # the constructor default (:1222-1223, 1289-1291); the shipped drivers pass False (train.py:91)
+            self.init_conv = CrossEmbedLayer(init_channels, init_cross_embed_kernel_sizes, dim_out=init_dim, stride=1)
+        else:
+            self.init_conv = nn.Conv3d(init_channels, init_dim, 3) if boundary else nn.Conv3d(init_channels, init_dim, 3, padding=1)
 
         dims = [init_dim, *[dim * m for m in dim_mults]]
         in_out = list(zip(dims[:-1], dims[1:]))

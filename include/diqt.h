@@ -231,6 +231,11 @@ int diqt_init_conv_pack(const float* w, int c_out, int c_in, float* packed, void
 /* The same init_conv on the tensor cores (bf16 mode, 27 * c_in <= 64, plain volumes): col[row][k = tap * c_in + ci] = plane_ci at the
  * tap-shifted voxel (tap = (kz*3+ky)*3+kx, zero outside the volume and for k >= 27 * c_in), bf16 [n*d0*d1*d2][64]; followed by a
  * DIQT_CONV_K1 convolution 64 -> c_out whose weight is W[co][ci][tap] re-ordered to [co][tap * c_in + ci] and zero-padded to 64. */
+/* CrossEmbedLayer as init conv (:661-686, init_cross_embed=True, the constructor default): one call per kernel size k (odd), writing
+ * the channel slice [co_off, co_off + nco) of the channels-last output.  w: fp32 [k^3][c_in][nco] (tap = (kz*k+ky)*k+kx), zero padding
+ * (k-1)/2.  Plain volumes (the reference's boundary mode cannot run with a cross-embed init conv: boundary_pad + padded convs). */
+int diqt_init_conv_k(const float* const* planes, const int64_t* plane_stride, int c_in, int k, const float* w, const float* bias, void* out,
+                     int ld_out, int co_off, int nco, int dtype, int n, int d0, int d1, int d2, void* stream);
 int diqt_init_im2col(const float* const* planes, const int64_t* plane_stride, int c_in, void* col, int n, int d0, int d1, int d2,
                      void* stream);
 

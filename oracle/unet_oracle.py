@@ -240,7 +240,15 @@ def unet_forward(sd: Dict[str, Tensor], spec: UnetSpec, x: Tensor, time: Tensor,
         x = torch.cat((cond_images, x), dim=1)                               # :1584
 
     k = spec.init_conv_kernel_size
-    if spec.boundary:                                                        # :1587-1589
+    if "init_conv.convs.0.weight" in sd:                                     # CrossEmbedLayer (:661-686, init_cross_embed=True)
+        assert not spec.boundary
+        maps, i = [], 0
+        while f"init_conv.convs.{i}.weight" in sd:
+            w = sd[f"init_conv.convs.{i}.weight"]
+            maps.append(F.conv3d(x, w, sd[f"init_conv.convs.{i}.bias"], padding=(w.shape[-1] - 1) // 2))
+            i += 1
+        x = torch.cat(maps, dim=1)
+    elif spec.boundary:                                                        # :1587-1589
         x = F.conv3d(boundary_pad(x, spec.batch_sample_factor), sd["init_conv.weight"], sd["init_conv.bias"])
     else:
         x = F.conv3d(x, sd["init_conv.weight"], sd["init_conv.bias"], padding=k // 2)

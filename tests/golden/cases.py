@@ -43,6 +43,9 @@ FORWARD_CASES = {
     # different depth / width pattern and skip scaling
     "alt_dim32_s16": dict(unet=_unet(32, dim_mults=(1, 2), num_resnet_blocks=(1, 2), scale_skip_connection=True, init_dim=64),
                           batch=1, size=16, weight_seed=15, input_seed=25, log_snr=[-1.0], taps=()),
+    # the constructor-default init conv: CrossEmbedLayer with kernel sizes (3, 7, 15) (imagen_pytorch3D.py:661-686, 1222-1223)
+    "crossembed_dim32_s16": dict(unet=_unet(32, init_cross_embed=True, init_cross_embed_kernel_sizes=(3, 7, 15)), batch=1, size=16, weight_seed=22,
+                                 input_seed=32, log_snr=[0.4], taps=("init_conv",)),
     # ---- attention blocks (off in the shipped configs).  27 sub-volumes of 8^3 = one merged 24^3 volume; patch sizes
     # 8 / 4 / 2 / 2 give 27 tokens at every level.  `img_size` is the merged side (it only sizes the ViT position table).
     "attn_linear_dim32_s8": dict(unet=_unet(32, **_attn("linear")), batch=27, size=8, weight_seed=16, input_seed=26,

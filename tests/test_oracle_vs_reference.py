@@ -17,7 +17,7 @@ def ref():
 
 
 @pytest.mark.parametrize("name", ["cfg1_dim32_s16_b2", "deep_dim32_s8", "boundary_dim32_s8", "alt_dim32_s16", "attn_linear_dim32_s8",
-                                  "attn_softmax_boundary_dim32_s8", "attn_vit_dim32_s8", "attn_vitlocal_dim32_s8"])
+                                  "attn_softmax_boundary_dim32_s8", "attn_vit_dim32_s8", "attn_vitlocal_dim32_s8", "crossembed_dim32_s16"])
 def test_unet_forward_bit_exact(ref, name):
     case = FORWARD_CASES[name]
     unet = ref.Unet(**unet_kwargs_for_reference(case)).eval()
