@@ -188,13 +188,16 @@ __device__ __forceinline__ StepConsts load_step(const float* __restrict__ sched,
   return s;
 }
 
+// torch.clamp propagates NaN (fminf / fmaxf drop it): a diverged prediction must stay visible in x0 and in the stitched volume
+__device__ __forceinline__ float clamp_nan(float x, float lo, float hi) { return x != x ? x : fminf(fmaxf(x, lo), hi); }
+
 // x_start from the network output (imagen_pytorch3D.py:1996-2004), static clamp (:2022-2026), posterior mean
 // (:301-302) and the sampling line (:2055), in the reference's operation order.
 __device__ __forceinline__ void ddpm_point(const StepConsts& s, float pred, float xt, float eps, float& x_next, float& x0) {
   float xs = pred;
   if (s.objective == 1) xs = (xt - s.sigma * pred) / fmaxf(s.alpha, 1e-8f);
   else if (s.objective == 2) xs = s.alpha * xt - s.sigma * pred;
-  xs = fminf(fmaxf(xs, s.lo), s.hi);
+  xs = clamp_nan(xs, s.lo, s.hi);
   const float mean = s.alpha_next * (xt * (1.f - s.c) / s.alpha + s.c * xs);
   x_next = mean + s.noise_scale * eps;
   x0 = xs;
@@ -218,7 +221,7 @@ __device__ __forceinline__ EdmConsts load_edm(const float* __restrict__ table, c
 // model_output = clamp(c_skip * x + c_out * net)   (:352-358; products and sum rounded separately like the reference's tensor ops)
 __device__ __forceinline__ float edm_denoised(const EdmConsts& e, float x, float net) {
   const float out = __fadd_rn(__fmul_rn(e.c_skip, x), __fmul_rn(e.c_out, net));
-  return fminf(fmaxf(out, e.lo), e.hi);
+  return clamp_nan(out, e.lo, e.hi);
 }
 // Euler pass (:488-498): x_hat -> (d = (x_hat - D(x_hat)) / sigma_hat, x_euler = x_hat + (sigma_next - sigma_hat) d)
 __device__ __forceinline__ void edm_euler_point(const EdmConsts& e, float net, float x_hat, float& d, float& x_euler, float& x0) {
@@ -249,8 +252,8 @@ template <typename T, int MAXCO>
 __global__ void final_conv_kernel(const T* __restrict__ x, int ld, int64_t voxels, int c, int c_out, int nvec,
                                   const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ pred,
                                   int step_mode, const float* __restrict__ sched, const int32_t* __restrict__ step,
-                                  const float* __restrict__ x_t, const float* __restrict__ noise,
-                                  float* __restrict__ x_next, float* __restrict__ x0, float* __restrict__ aux_out,
+                                  const float* x_t /* may alias x_next (in-place update) */, const float* __restrict__ noise,
+                                  float* x_next, float* __restrict__ x0, float* __restrict__ aux_out,
                                   int64_t total_rows, SubGeom sg) {
   constexpr int VEC = Vec<T>::N;
   // nvec (power of two <= 32) consecutive threads share one voxel row
@@ -322,19 +325,19 @@ __global__ void final_conv_kernel(const T* __restrict__ x, int ld, int64_t voxel
           pred[o] = p;
         } else if (step_mode == 1) {
           float xn, xs;
-          ddpm_point(sc, p, x_t[o], noise[o], xn, xs);
+          ddpm_point(sc, p, __ldcg(x_t + o), __ldcg(noise + o), xn, xs);
           x_next[o] = xn;
           x0[o] = xs;
         } else if (step_mode == 2) {
           float d, xe, xs;
-          edm_euler_point(ec, p, noise[o], d, xe, xs);
+          edm_euler_point(ec, p, __ldcg(noise + o), d, xe, xs);
           pred[o] = d;
           x_next[o] = xe;
           aux_out[o] = __fmul_rn(ec.c_in_next, xe);
           x0[o] = xs;
         } else {
           float xn, xs;
-          edm_heun_point(ec, p, noise[o], x_t[o], pred[o], xn, xs);
+          edm_heun_point(ec, p, __ldcg(noise + o), __ldcg(x_t + o), __ldcg(pred + o), xn, xs);
           x_next[o] = xn;
           x0[o] = xs;
         }
@@ -343,15 +346,14 @@ __global__ void final_conv_kernel(const T* __restrict__ x, int ld, int64_t voxel
   }
 }
 
-__global__ void ddpm_update_kernel(const float* __restrict__ pred, const float* __restrict__ sched,
-                                   const int32_t* __restrict__ step, const float* __restrict__ x_t,
-                                   const float* __restrict__ noise, float* __restrict__ x_next, float* __restrict__ x0,
-                                   int64_t count) {
+__global__ void ddpm_update_kernel(const float* pred /* may alias x0 */, const float* __restrict__ sched,
+                                   const int32_t* __restrict__ step, const float* x_t /* may alias x_next */,
+                                   const float* __restrict__ noise, float* x_next, float* x0, int64_t count) {
   pdl_sync();
   StepConsts sc = load_step(sched, step);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
     float xn, xs;
-    ddpm_point(sc, pred[i], x_t[i], noise[i], xn, xs);
+    ddpm_point(sc, __ldcg(pred + i), __ldcg(x_t + i), __ldcg(noise + i), xn, xs);
     x_next[i] = xn;
     if (x0) x0[i] = xs;
   }
@@ -405,7 +407,7 @@ __global__ void advance_step_kernel(int32_t* step) {
 
 __global__ void clamp_kernel(float* __restrict__ x, int64_t count, float lo, float hi) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
-    x[i] = fminf(fmaxf(x[i], lo), hi);
+    x[i] = clamp_nan(x[i], lo, hi);
 }
 
 

@@ -257,6 +257,8 @@ class ElucidatedImagen(nn.Module):
             st.x += init_images                                                     # :436-437
         eng.load_inputs(None, lowres_cond_img, cond_images)
         eng.set_condition(st.c_noise)                                               # time MLPs of every forward at once
+        if getattr(st, "film_gen", None) != eng.film_gen:                           # the FiLM table moved: captured graphs read the old one
+            st.graphs, st.film_gen = None, eng.film_gen
         eng.film_row_ptr, eng.film_stride_n = st.fwd.data_ptr(), 0
         st.fwd.zero_()
         count = st.x.numel()

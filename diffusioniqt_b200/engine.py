@@ -29,12 +29,12 @@ from . import lib as L
 class Act:
     """A channels-last activation view: n volumes x voxels rows of `c` channels, row pitch `ld`."""
 
-    __slots__ = ("buf", "ptr", "c", "ld", "stats")
+    __slots__ = ("buf", "ptr", "c", "ld", "off", "stats")
 
     def __init__(self, buf: torch.Tensor, c: int, ld: int, offset: int = 0):
         self.buf = buf
         self.ptr = buf.data_ptr() + offset * buf.element_size()
-        self.c, self.ld = c, ld
+        self.c, self.ld, self.off = c, ld, offset
         self.stats = None  # (partial tensor, nblk) when a producer already reduced this tensor
 
 
@@ -45,8 +45,12 @@ def _nblk(n: int, voxels: int, per_device: int = 148) -> int:
 
 
 class UnetEngine:
-    def __init__(self, unet, batch: int, dims, dtype: str = "bf16", device=None, conv_impl: str = "auto"):
+    def __init__(self, unet, batch: int, dims, dtype: str = "bf16", device=None, conv_impl: str = "auto", taps=()):
         self.lib = L.load()
+        # names of ResnetBlocks (the oracle's tap names, e.g. "downs.0.1") whose output is copied aside during the forward: parity tests
+        # compare intermediate activations at full size without a second code path
+        self.tap_names = tuple(taps)
+        self.taps = {}
         if not torch.cuda.is_available():
             raise L.DiqtError("UnetEngine needs a CUDA device (sm_100a); there is no CPU fallback")
         self.device = torch.device(device if device is not None else "cuda")
@@ -88,6 +92,7 @@ class UnetEngine:
         self.conv_impls = {}                  # site name -> resolved impl (for tests / reporting)
         # sampler states (schedule tables, captured step graphs) that bake this engine's buffer addresses live and die with it
         self.sampler_cache = {}
+        self.film_gen = 0
         self._attn_plans: List[int] = []
         self.attn_impls = {}                  # attention site -> "tc" | "simt"
         self._build()
@@ -345,6 +350,8 @@ class UnetEngine:
             else:
                 ops.append(lambda st: L.check(sres(hp, hl, rp, rl, op_, ol, dd, n, vox, cout, gate_ptr, nbk, opp, sf, sh, st), name + ".residual"))
                 out.stats = (opart, nbk, None, 0)
+            if name in self.tap_names:
+                self._add_tap(name, out, level)
             return out
 
         # ---- init conv
@@ -470,6 +477,20 @@ class UnetEngine:
         self.film_b = self._f32(torch.cat([b.to(self.device) for b in self._film_b], dim=0))
         self.film = None
         torch.cuda.current_stream().synchronize()
+
+    def _add_tap(self, name, act: Act, level: int):
+        rows = self.n * self.level_vox[level]
+        src = torch.as_strided(act.buf.view(-1), (rows, act.c), (act.ld, 1), act.off)
+        dst = self._empty(rows, act.c)
+        self.taps[name] = (dst, level)
+        self._ops.append(lambda st: dst.copy_(src))
+
+    def tap(self, name) -> torch.Tensor:
+        """Tapped activation as the reference's (B, C, D, H, W) fp32 tensor (plain layout only)."""
+        assert self.sub_f <= 1, "taps are recorded in the plain (non-boundary) layout"
+        t, level = self.taps[name]
+        d = self.level_dims[level]
+        return t.view(self.n, *d, t.shape[1]).permute(0, 4, 1, 2, 3).float().contiguous()
 
     # ------------------------------------------------------------------ attention blocks (SURVEY 8 a17)
     def _add_attention(self, mod, x: Act, level: int, out: Act, name: str, outer_residual: bool) -> Act:
@@ -681,6 +702,9 @@ class UnetEngine:
         t = log_snr.detach().to(device=self.device, dtype=torch.float32).contiguous()
         half = self.w_four.shape[0]
         if self.film is None or self._film_rows < rows:
+            # captured step graphs bake self.film.data_ptr(): a larger table means new buffers, so the generation counter tells every
+            # cached sampler state to drop its graph and capture again on next use (imagen.py / elucidated.py compare it)
+            self.film_gen += 1
             self._film_rows = rows
             self.four = torch.empty(rows, 1 + 2 * half, dtype=torch.float32, device=self.device)
             self.thid = torch.empty(rows, self.tdim, dtype=torch.float32, device=self.device)

@@ -364,6 +364,8 @@ class Imagen(nn.Module):
             img += init_images                                                   # :2084-2085
         eng.load_inputs(img, lowres_cond_img, cond_images)
         eng.set_condition(st.log_snr)                                            # time MLPs for every step at once
+        if getattr(st, "film_gen", None) != eng.film_gen:                        # the FiLM table moved: the captured graph reads the old one
+            st.graph, st.film_gen = None, eng.film_gen
         eng.film_row_ptr, eng.film_stride_n = st.step.data_ptr(), 0
         st.step.zero_()
         x_t = eng.x_in                                                           # sampler state lives in the engine's input buffer

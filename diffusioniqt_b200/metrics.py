@@ -60,8 +60,8 @@ def _ssim_and_cs(p: torch.Tensor, t: torch.Tensor, kernel_size: int, sigma: floa
     return ssim.mean(), cs.mean()
 
 
-def ssim3d(pred, target, kernel_size: int = 11, sigma: float = 1.5, data_range: Optional[float] = None) -> float:
-    """metrics.py:23-30.  data_range=None: min-max normalise both volumes first (as the reference does) and use range 1."""
+def ssim3d(pred, target, kernel_size: int = 3, sigma: float = 1.5, data_range: Optional[float] = None) -> float:
+    """metrics.py:23-30 (the reference's SSIM() defaults to a 3-wide window).  data_range=None: min-max normalise both volumes first (as the reference does) and use range 1."""
     p, t = _as5d(pred), _as5d(target)
     if data_range is None:
         p, t, data_range = _minmax(p), _minmax(t), 1.0

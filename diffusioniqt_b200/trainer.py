@@ -25,19 +25,28 @@ __version__ = "1.20.1"   # version.py of the reference; written into checkpoints
 
 
 def num_to_groups(num, divisor):
-    groups, remainder = num // divisor, num % divisor
-    return [divisor] * groups + ([remainder] if remainder > 0 else [])
+    """Sizes of the chunks a batch of `num` is split into when at most `divisor` go through at once (trainer.py:217-220)."""
+    full, rest = divmod(int(num), int(divisor))
+    sizes = [divisor for _ in range(full)]
+    if rest:
+        sizes.append(rest)
+    return sizes
 
 
 def restore_parts(state_dict_target, state_dict_from):
-    """trainer.py:222-233: copy the entries whose name and size match, report the rest."""
-    for name, param in state_dict_from.items():
-        if name not in state_dict_target:
+    """Partial restore (the behaviour of trainer.py:222-233): every tensor of `state_dict_from` whose key exists in the target with
+    the same shape is copied in place; shape mismatches are reported and skipped; unknown keys are ignored."""
+    mismatched = []
+    for key, src in state_dict_from.items():
+        dst = state_dict_target.get(key)
+        if dst is None:
             continue
-        if param.size() == state_dict_target[name].size():
-            state_dict_target[name].copy_(param)
-        else:
-            print(f"layer {name}({param.size()} different than target: {state_dict_target[name].size()}")
+        if tuple(dst.shape) != tuple(src.shape):
+            mismatched.append((key, tuple(src.shape), tuple(dst.shape)))
+            continue
+        dst.copy_(src)
+    for key, got, want in mismatched:
+        print(f"restore_parts: skipped {key}: checkpoint shape {got}, model shape {want}")
     return state_dict_target
 
 

@@ -197,7 +197,8 @@ class Unet(nn.Module):
         if cross_embed_downsample:
             unsupported.append("cross_embed_downsample=True")
         if memory_efficient:
-            unsupported.append("memory_efficient=True (broken in the reference: changes the output size)")
+            unsupported.append("memory_efficient=True (broken in the reference: changes the output size; note that SRUnet256 / SRUnet1024 keep the "
+                               "reference's default memory_efficient=True, so pass memory_efficient=False explicitly, as train.py:100 and test_all.py do)")
         if not pixel_shuffle_upsample:
             unsupported.append("pixel_shuffle_upsample=False (ConvTranspose3d upsampling)")
         if init_conv_to_final_conv_residual:
@@ -362,6 +363,8 @@ class Unet(nn.Module):
             e.close()
         self._engines = {}
 
+    refresh_weights = invalidate_engines   # explicit name for "I changed parameters behind autograd's back (p.data[...] = ...)"
+
     def load_state_dict(self, *args, **kwargs):
         self.invalidate_engines()  # packed weight copies would be stale
         return super().load_state_dict(*args, **kwargs)
@@ -381,10 +384,18 @@ class Unet(nn.Module):
 
     def engine_for(self, batch, dims, device):
         from .engine import UnetEngine
-        key = (int(batch), tuple(int(d) for d in dims), self.compute_dtype, self.conv_impl, str(device))
+        taps = tuple(getattr(self, "debug_taps", ()) or ())
+        key = (int(batch), tuple(int(d) for d in dims), self.compute_dtype, self.conv_impl, str(device), taps)
+        # engines hold packed copies of the weights: an in-place parameter update (optimizer / EMA step, p.copy_()) bumps `_version`,
+        # a re-assigned `.data` changes `data_ptr`; either drops every engine (and its captured graphs).  Writes through `.data` that
+        # keep the storage are invisible to both: call invalidate_engines() / refresh_weights() after those.
+        sig = self._param_signature()
+        if self._engines and sig != getattr(self, "_engine_sig", None):
+            self.invalidate_engines()
+        self._engine_sig = sig
         eng = self._engines.get(key)
         if eng is None:
-            eng = UnetEngine(self, key[0], key[1], dtype=self.compute_dtype, device=device, conv_impl=self.conv_impl)
+            eng = UnetEngine(self, key[0], key[1], dtype=self.compute_dtype, device=device, conv_impl=self.conv_impl, taps=taps)
             self._engines[key] = eng
         return eng
 

@@ -102,7 +102,8 @@ def merge_sub_volumes(sub: torch.Tensor, f: int) -> torch.Tensor:
 
 def infer_volume(sample_fn: Callable[[torch.Tensor], torch.Tensor], lowres_norm: torch.Tensor, *, patch: int, overlap: int,
                  raw_lowres: Optional[torch.Tensor] = None, batch_size: int = 1, fill_value: float = 0.0,
-                 rank: int = 0, world: int = 1, group=None, batch_sample: bool = False, sub_f: int = 0) -> VolumeResult:
+                 rank: int = 0, world: int = 1, group=None, batch_sample: bool = False, sub_f: int = 0,
+                 gather_fn: Optional[Callable[[torch.Tensor], Optional[torch.Tensor]]] = None) -> Optional[VolumeResult]:
     """Denoise a whole (normalised) low-field volume patch by patch and stitch the result.
 
     sample_fn: (B, 1, P, P, P) low-field patches on the compute device -> (B, 1, P, P, P) denoised patches
@@ -114,6 +115,9 @@ def infer_volume(sample_fn: Callable[[torch.Tensor], torch.Tensor], lowres_norm:
     reference (test_all.py:211-212).
     With world > 1 every rank must call this with the same arguments; each denoises its block of the patch list and the
     patches are exchanged with ONE all_gather (torch.distributed; NCCL on GPUs, gloo in the CPU tests).
+    gather_fn replaces the collective: it receives this rank's padded shard (per, P^3) and returns all shards concatenated in rank order
+    (world * per, P^3), or None to stop before the stitch (callers that exchange the shards themselves; the single-process tests of the
+    multi-rank path).
     On a CUDA device the patches are cut and stitched by two kernels of libdiqt_b200 (`diqt_gather_patches`, `diqt_stitch_patches`);
     CPU tensors (the multi-process host-logic tests, with a stand-in `sample_fn`) take the equivalent torch slicing below.
     """
@@ -146,7 +150,12 @@ def infer_volume(sample_fn: Callable[[torch.Tensor], torch.Tensor], lowres_norm:
             lr = (split_sub_volumes(lr, f) if f > 1 else lr)[:, None].contiguous()
         out = sample_fn(lr)
         local[b0:b0 + nb] = out.to(dev, torch.float32).reshape(nb, patch ** 3)     # same (sub-volume) layout as `lr`
-    if world > 1:
+    if gather_fn is not None:
+        gathered = gather_fn(local)
+        if gathered is None:
+            return None
+        assert tuple(gathered.shape) == (world * per, patch ** 3), (tuple(gathered.shape), world, per)
+    elif world > 1:
         import torch.distributed as dist
         gathered = torch.empty((world * per, patch ** 3), dtype=torch.float32, device=dev)
         dist.all_gather_into_tensor(gathered, local, group=group)       # the only collective on the path

@@ -25,7 +25,7 @@ def psnr(pred: torch.Tensor, target: torch.Tensor, rng=None) -> float:
     return float(10.0 * torch.log10(1.0 / mse))
 
 
-def ssim3d(pred: torch.Tensor, target: torch.Tensor, kernel_size: int = 11, sigma: float = 1.5, normalise: bool = True, rng=None) -> float:
+def ssim3d(pred: torch.Tensor, target: torch.Tensor, kernel_size: int = 3, sigma: float = 1.5, normalise: bool = True, rng=None) -> float:
     p, t = pred.double(), target.double()
     if normalise:
         p, t = _minmax(p, rng), _minmax(t, rng)

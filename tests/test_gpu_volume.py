@@ -20,14 +20,14 @@ KW = dict(dim=32, init_dim=32, dim_mults=(1, 2, 4), num_resnet_blocks=(2, 2, 2),
           boundary=False, batch_sample=False)
 
 
-@pytest.mark.parametrize("dtype,psnr_tol,ssim_tol", [("fp32", 0.05, 1e-3), ("bf16", 0.05, 1e-3)])
-def test_stitched_volume_psnr_ssim(dtype, psnr_tol, ssim_tol):
+@pytest.mark.parametrize("dtype,norm,psnr_tol,ssim_tol", [("fp32", "z-score", 0.05, 1e-3), ("bf16", "z-score", 0.05, 1e-3), ("bf16", "min-max", 0.05, 1e-3)])
+def test_stitched_volume_psnr_ssim(dtype, norm, psnr_tol, ssim_tol):
     from diffusioniqt_b200 import Imagen, NullUnet, Unet
     P, stride, T, N = 16, 8, 6, 32
     unet = Unet(**KW, img_size=P)
     sd = synthetic_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, seed=61)
     unet.load_state_dict(sd)
-    imagen = Imagen(unets=(NullUnet(), unet), configs={"Data": {"norm": "z-score"}, "Train": {"batch_sample": False}}, image_sizes=(P, P),
+    imagen = Imagen(unets=(NullUnet(), unet), configs={"Data": {"norm": norm}, "Train": {"batch_sample": False}}, image_sizes=(P, P),
                     channels=1, min_bound=MIN_BOUND, timesteps=T, pred_objectives="x_start", dynamic_thresholding=False,
                     cond_drop_prob=0.0).cuda()
     imagen.unets[1].set_compute_dtype(dtype)
@@ -54,7 +54,7 @@ def test_stitched_volume_psnr_ssim(dtype, psnr_tol, ssim_tol):
         lr = lowres[g[0]:g[0] + P, g[1]:g[1] + P, g[2]:g[2] + P][None, None]
         with torch.no_grad():
             img, _, _ = ddpm_sample(lambda x, ls: unet_forward(sd, spec, x, ls, lowres_cond_img=lr), (1, 1, P, P, P), noise[g], timesteps=T,
-                                    min_bound=MIN_BOUND)
+                                    min_bound=MIN_BOUND, norm=norm)
         outs.append(img[0, 0].numpy())
         kept.append(list(g))
     want = np.full((N, N, N), MIN_BOUND, np.float32)
@@ -66,7 +66,7 @@ def test_stitched_volume_psnr_ssim(dtype, psnr_tol, ssim_tol):
     # of a real IQT model; against an unrelated random truth, ~13 dB, the statistic mostly measures chance correlations).
     lo, hi = float(want.min()), float(want.max())
     truth = (want + synthetic_field((N, N, N), 63) * ((hi - lo) * 10 ** (-25 / 20))).clamp(lo, hi)
-    assert 22.0 < mo.psnr(want, truth) < 26.0
+    assert 20.0 < mo.psnr(want, truth) < 28.0
     # North-star acceptance: PSNR within 0.05 dB and SSIM within 1e-3 of the reference pipeline.  The reference's metric scales every
     # volume by its OWN min / max (metrics.py:18-19); with random weights the maximum is a single outlier voxel (8.1 against an rms of
     # 1.8), so in bf16 a 1 % change of that ONE voxel rescales the whole volume and moves the literal metric by tenths of a dB.  The
@@ -74,9 +74,16 @@ def test_stitched_volume_psnr_ssim(dtype, psnr_tol, ssim_tol):
     rng = (truth.min(), truth.max())
     assert abs(mo.psnr(got, truth, rng) - mo.psnr(want, truth, rng)) < psnr_tol
     assert abs(mo.ssim3d(got, truth, rng=rng) - mo.ssim3d(want, truth, rng=rng)) < ssim_tol
-    literal = (1.0, 1e-2) if dtype == "bf16" else (psnr_tol, ssim_tol)
-    assert abs(mo.psnr(got, truth) - mo.psnr(want, truth)) < literal[0]
-    assert abs(mo.ssim3d(got, truth) - mo.ssim3d(want, truth)) < literal[1]
+    # In min-max mode (Data.norm = "min-max": x0 and the final patch are clamped to [-1, 1], :2024, :2154) the extremes of both volumes are
+    # the clamp bounds themselves, as they are for a trained model whose output range is set by the data: there the LITERAL metric is held
+    # to the north-star tolerance in bf16 too.  In z-score mode with random weights the measured bf16 deviation is printed and recorded in
+    # DESIGN.md section 4.
+    d_psnr, d_ssim = abs(mo.psnr(got, truth) - mo.psnr(want, truth)), abs(mo.ssim3d(got, truth) - mo.ssim3d(want, truth))
+    print(f"literal metric deviation [{dtype}, {norm}]: dPSNR = {d_psnr:.4f} dB, dSSIM = {d_ssim:.2e}; "
+          f"range-pinned: dPSNR = {abs(mo.psnr(got, truth, rng) - mo.psnr(want, truth, rng)):.4f} dB")
+    literal = (1.0, 1e-2) if (dtype == "bf16" and norm == "z-score") else (psnr_tol, ssim_tol)
+    assert d_psnr < literal[0]
+    assert d_ssim < literal[1]
     assert mo.psnr(got, want) > (60.0 if dtype == "fp32" else 30.0)
 
 
