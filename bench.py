@@ -47,18 +47,32 @@ def read_peaks():
     return dict(burst=1590.0, sustained=1400.0, hbm=6650.0, source="fallback")
 
 
+def kernel_source_sha():
+    """Hash of the sources the dominant kernel is built from: ties a committed ncu capture to the code it profiled."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in ("conv_zm.cu", "tc_common.cuh", "common.cuh"):
+        with open(os.path.join(ROOT, "diffusioniqt_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def read_traffic(kernel_label):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json), or None."""
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json, written by
+    tools/update_traffic.py from an `ncu --set full` CSV).  None when there is no capture or when the kernel's sources changed since
+    it was taken (a stale figure is worse than none)."""
     path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
         with open(path) as f:
             t = json.load(f)
         for k, v in t.items():
             if k.split()[0] in kernel_label and "64^3" in kernel_label:
-                return v["bytes_per_launch"]
+                if v.get("source_sha") != kernel_source_sha():
+                    return None, "capture %s is older than the kernel sources (sha %s != %s): not reported" % (v.get("source", "?"), v.get("source_sha"), kernel_source_sha())
+                return v["bytes_per_launch"], "dram__bytes_read.sum + dram__bytes_write.sum per launch, %s" % v.get("source", "?")
     except (OSError, ValueError, KeyError):
         pass
-    return None
+    return None, "no ncu capture committed"
 
 
 class ClockSampler:
@@ -205,7 +219,7 @@ def time_elementwise_kernel(size, batch, reps=20):
     return dict(ms=ms, bytes=nbytes, gbs=nbytes / (ms * 1e-3) / 1e9)
 
 
-def cpu_baseline(size, timesteps, batch, denoise_steps, threads=None):
+def cpu_baseline(size, timesteps, batch, denoise_steps, threads=None, warm=True):
     """The CPU oracle port (same algorithm as the reference's CPU sampler) on a bounded sample: `denoise_steps`
     iterations of the sampler at the benchmark shape; patches/s is extrapolated to `timesteps` iterations."""
     from diffusioniqt_b200 import SRUnet256
@@ -229,29 +243,140 @@ def cpu_baseline(size, timesteps, batch, denoise_steps, threads=None):
             mean, _, log_var = q_posterior(x0, x, t, tn)
             x = mean + (0.5 * log_var).exp() * torch.randn_like(x)
 
-    one(0)  # warm-up (oneDNN primitive creation)
-    t0 = time.perf_counter()
+    if warm:
+        one(0)  # warm-up (oneDNN primitive creation)
+    per = []
     for i in range(denoise_steps):
+        t0 = time.perf_counter()
         one(1 + i)
-    dt = (time.perf_counter() - t0) / denoise_steps
+        per.append(time.perf_counter() - t0)
+    dt = statistics.median(per)
     return dict(value=batch / (dt * timesteps), unit="patches/s", cores=threads, kind="port", ms_per_denoise_step=dt * 1e3,
+                ms_per_denoise_step_min=min(per) * 1e3, ms_per_denoise_step_max=max(per) * 1e3,
                 sample=f"{denoise_steps} of {timesteps} denoising iterations of one {size}^3 patch (batch {batch}), oracle/ CPU port of the reference "
-                       f"sampler, torch {torch.__version__} fp32, extrapolated linearly to {timesteps} iterations")
+                       f"sampler, torch {torch.__version__} fp32, median iteration extrapolated linearly to {timesteps} iterations")
+
+
+def torch_gpu_baseline(size, batch, reps=5):
+    """The kernel to beat on the same box: the reference's own op list (oracle.unet_forward = the ATen / cuDNN
+    calls of imagen_pytorch3D.py:1554-1684) run eagerly on THIS GPU, one forward = one denoising iteration at the benchmark shape:
+    fp32 with TF32 off (the parity-grade reference), fp32 with TF32 on (what the reference does on a GPU by default) and bf16 autocast
+    over channels_last_3d tensors.  A reported baseline like cpu_baseline: the oracle is timed, never shipped."""
+    from diffusioniqt_b200 import SRUnet256
+    from diffusioniqt_b200.synth import synthetic_field, synthetic_state_dict
+    from oracle.unet_oracle import UnetSpec, unet_forward
+    dev = torch.device("cuda")
+    shapes = {k: tuple(v.shape) for k, v in SRUnet256(**DRIVER_UNET, img_size=size).state_dict().items()}
+    sd = {k: v.to(dev) for k, v in synthetic_state_dict(shapes, seed=0).items()}
+    spec = UnetSpec(dim=64, init_dim=64, dim_mults=(1, 2, 4), num_resnet_blocks=(2, 2, 2), channels=1, lowres_cond=True, deep_feature=False)
+    x = synthetic_field((batch, 1, size, size, size), 2).to(dev)
+    lr = synthetic_field((batch, 1, size, size, size), 1).to(dev)
+    t = torch.full((batch,), 1.3, device=dev)
+    out = {}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.benchmark = True
+
+    def run(mode):
+        with torch.no_grad():
+            if mode == "bf16_autocast_channels_last_3d":
+                sd_ = {k: (v.contiguous(memory_format=torch.channels_last_3d) if v.dim() == 5 else v) for k, v in sd.items()}
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    return unet_forward(sd_, spec, x.contiguous(memory_format=torch.channels_last_3d), t,
+                                        lowres_cond_img=lr.contiguous(memory_format=torch.channels_last_3d)).float()
+            return unet_forward(sd, spec, x, t, lowres_cond_img=lr)
+
+    try:
+        for mode, tf32 in (("fp32_tf32_off", False), ("fp32_tf32_on", True), ("bf16_autocast_channels_last_3d", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            try:
+                for _ in range(2):
+                    run(mode)
+                torch.cuda.synchronize()
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+                ev[0].record()
+                for i in range(reps):
+                    run(mode)
+                    ev[i + 1].record()
+                torch.cuda.synchronize()
+                ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+                out[mode] = dict(ms_per_denoise_iteration=ms[len(ms) // 2], ms_min=ms[0], ms_max=ms[-1])
+            except Exception as e:  # a cuDNN configuration that does not run is a fact worth reporting, not a bench failure
+                out[mode] = dict(error=f"{type(e).__name__}: {e}"[:200])
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    out["note"] = ("eager PyTorch %s / cuDNN %s forward of the reference op list on this GPU, batch %d, %d^3, median of %d; sampler update excluded"
+                   % (torch.__version__, torch.backends.cudnn.version(), batch, size, reps))
+    del sd
+    torch.cuda.empty_cache()
+    return out
+
+
+def volume_record(dev, rank, world, dist, side=256, timesteps=20, batch=7):
+    """BASELINE config 3 through the same process group: one synthetic `side`^3 low-field volume cut into overlapping 64^3 patches
+    (stride 32: 7^3 = 343 for 256^3, data.py:159-162), 5 % skip rule, contiguous shards over the ranks (343 = 8 * 43 - 1: the last rank
+    is one patch short and padded), T denoising iterations per patch (eval_config.yaml:21), ONE all-gather, device-side stitch and
+    background mask (test_all.py:182-300).  Strong scaling: the volume is fixed, ranks split it."""
+    from diffusioniqt_b200 import volume as V
+    from diffusioniqt_b200.synth import synthetic_field
+    imagen = build_model(timesteps, dev, "bf16")
+    imagen.return_host_lists = False
+    low = synthetic_field((side, side, side), 11)
+    low[: side // 8] = low.min()                                  # air: some patches fall under the 5 % rule
+    low = low.to(dev)
+    raw = low - low.min()
+
+    def sample_fn(lr):
+        return imagen.sample(batch_size=lr.shape[0], start_image_or_video=lr, start_at_unet_number=2, use_tqdm=False)[0]
+
+    def run(vol, rawv):
+        return V.infer_volume(sample_fn, vol, patch=64, overlap=32, raw_lowres=rawv, batch_size=batch, fill_value=MIN_BOUND, rank=rank, world=world)
+
+    # warm-up: engine build + graph capture for every batch size the shards will use (full chunks and the ragged tail)
+    grid = V.patch_grid(low.shape, 64, 32)
+    kept = [o for o in grid if V.keep_patch(raw, o, 64)]
+    start, stop, per = V.shard_range(len(kept), rank, world)
+    sizes = {min(batch, stop - start - b0) for b0 in range(0, stop - start, batch)}
+    lr0 = torch.zeros((1, 1, 64, 64, 64), device=dev)
+    for bsz in sorted(sizes):
+        sample_fn(lr0.expand(bsz, -1, -1, -1, -1).contiguous())
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = run(low, raw)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    if dist is not None:
+        t = torch.tensor([sec], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t)
+    vol = res.volume
+    ok = bool(torch.isfinite(vol).all()) and float(vol.min()) >= min(MIN_BOUND, float(low.min())) - 1e-5
+    del imagen
+    torch.cuda.empty_cache()
+    return dict(workload=f"BASELINE config 3: {side}^3 volume, 64^3 patches, stride 32, T = {timesteps}, {batch} patches per sampler call, bf16",
+                seconds=sec, patches=res.n_patches, skipped=res.n_skipped, patches_per_rank=res.patches_per_rank, patches_per_s=res.n_patches / sec,
+                n_gpus=world, scaling="strong", finite_and_bounded=ok, gather_bytes=world * res.patches_per_rank * 64 ** 3 * 4,
+                timing="CUDA events on rank-local stream around gather -> sample -> all_gather -> stitch, max over ranks")
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    per_step = max(1, args.ref_denoise_steps)
-    vals, ms = [], []
+    per_step = max(5, args.ref_denoise_steps)         # >= 5 timed denoising iterations per bench step; the spread is reported
+    vals, its = [], []
     for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        r = cpu_baseline(args.size, args.timesteps, args.batch, per_step)
+        r = cpu_baseline(args.size, args.timesteps, args.batch, per_step, warm=(i == 0))
         if i >= args.warmup:
             vals.append(r["value"])
-            ms.append((time.perf_counter() - t0) * 1e3)
+            its += [r["ms_per_denoise_step_min"], r["ms_per_denoise_step"], r["ms_per_denoise_step_max"]]
     v = statistics.median(vals)
     r["value"] = v
+    r["spread"] = dict(value_min=min(vals), value_max=max(vals), ms_per_denoise_step_min=min(its), ms_per_denoise_step_max=max(its),
+                       bench_steps=len(vals), iterations_per_bench_step=per_step)
     line = dict(impl="reference", metric="3D patches/sec (full denoise loop)", value=v, unit="patches/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 / v * args.batch, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
                 data="synthetic", config=workload_config(args), cpu_baseline=r,
@@ -278,8 +403,12 @@ def main():
     ap.add_argument("--timesteps", type=int, default=1000)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-denoise-steps", type=int, default=3, help="bounded CPU-baseline sample (denoising iterations)")
-    ap.add_argument("--ref-denoise-steps", type=int, default=2)
+    ap.add_argument("--ref-denoise-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-gpu-baseline", action="store_true")
+    ap.add_argument("--no-volume", action="store_true", help="skip the BASELINE config 3 sub-record (whole 256^3 volume, T = 20)")
+    ap.add_argument("--volume-side", type=int, default=256)
+    ap.add_argument("--volume-timesteps", type=int, default=20)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -365,6 +494,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms, e2e_ms = t.tolist()
 
+    volume = None
+    if not args.no_volume:
+        volume = volume_record(dev, rank, world, dist, side=args.volume_side, timesteps=args.volume_timesteps)
+
     if rank == 0:
         peaks = read_peaks()
         patches = world * B * args.steps
@@ -373,11 +506,10 @@ def main():
         flops_per_patch = FLOPS_PER_FWD_64 * (S / 64.0) ** 3 * args.timesteps
         step_tflops = value / world * flops_per_patch / 1e12
         dom = time_dominant_kernel(S, B)
+        traffic, traffic_note = read_traffic("%s 64^3" % dom["kernel"]) if (S == 64 and B == 1) else (None, "only captured for the 64^3 batch-1 shape")
         roofline = dict(bound="tensor", kernel="%s 3x3x3 64->64 @%d^3 (batch %d)" % (dom["kernel"], S, B), achieved=dom["tflops"], peak=peaks["burst"],
-                        unit="TFLOP/s", frac=dom["tflops"] / peaks["burst"],
-                        traffic=read_traffic("%s 64^3" % dom["kernel"]) if (S == 64 and B == 1) else None,
-                        traffic_note="dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/ncu_traffic.json (ncu --set full); algorithmic "
-                                     "traffic is 67.1 MB (32 MiB in + 32 MiB out), the output of a launch stays in the 126 MB L2",
+                        unit="TFLOP/s", frac=dom["tflops"] / peaks["burst"], traffic=traffic,
+                        traffic_note=traffic_note + "; algorithmic traffic is 67.1 MB (32 MiB in + 32 MiB out), the output of a launch stays in the 126 MB L2",
                         ms_per_launch=dom["ms"], flops_per_launch=dom["flops"],
                         peak_source=peaks["source"] + " (burst: kernel timed alone)",
                         whole_step=dict(achieved=step_tflops, peak=peaks["sustained"], frac=step_tflops / peaks["sustained"], unit="TFLOP/s",
@@ -393,6 +525,14 @@ def main():
                     e2e=dict(value=patches / (e2e_ms * 1e-3), unit="patches/s", h2d_bytes_per_step=B * S ** 3 * 4, d2h_bytes_per_step=3 * B * S ** 3 * 4),
                     gpu_launches=int(graph_launches + eager_launches), ms_per_denoise_iteration=ms_per_step / args.timesteps,
                     roofline=roofline, roofline_elementwise=roofline_hbm)
+        if volume is not None:
+            line["volume"] = volume
+        if not args.no_torch_gpu_baseline:
+            line["torch_gpu_baseline"] = torch_gpu_baseline(S, B)
+            ours = ms_per_step / args.timesteps
+            for k, v in line["torch_gpu_baseline"].items():
+                if isinstance(v, dict) and "ms_per_denoise_iteration" in v:
+                    v["speedup_of_this_library"] = v["ms_per_denoise_iteration"] / ours
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(S, args.timesteps, B, args.cpu_denoise_steps)
         print(json.dumps(line), flush=True)

@@ -42,7 +42,7 @@ constexpr int ZM_WSTAGE = 3 * ZM_WBLOCK;
 constexpr int ZM_WSTAGES = 4;
 constexpr int ZM_THREADS = 256;
 constexpr int ZM_OUT_BYTES = 128 * 128;
-constexpr int ZM_MAX_COUT = 256;
+constexpr int ZM_MAX_COUT = 512;                        // BASELINE config 5 sweeps up to 512 channels
 constexpr int ZM_MAX_SEG = 64;                          // z-segments per column (boundaries live in the kernel parameters)
 
 struct ZmParams {

@@ -116,6 +116,8 @@ ZM_SHAPES = [
     (2, (3, 16, 8), 64, 192),       # odd item count per channel group: one slot of the last pair idles
     (1, (8, 16, 16), 256, 256),     # mid_block width (deep_feature)
     (5, (2, 16, 8), 64, 128),       # several volumes per CTA slot: per-(volume, group) statistics flushes
+    (1, (8, 16, 16), 512, 512),     # BASELINE config 5's widest layer: eight K chunks, eight output-channel groups
+    (1, (4, 16, 8), 320, 448),      # widths that are multiples of 64 but not powers of two
 ]
 
 
