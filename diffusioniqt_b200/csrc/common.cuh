@@ -244,8 +244,13 @@ __device__ __forceinline__ void stats_group_total(const float* __restrict__ grou
 // Per-channel totals of volume nv from the group rows, by all `nthreads` threads of a CTA: `slices` threads per channel each sum a
 // contiguous run of group rows (independent loads, one L2 round trip), then one thread per channel adds the slices.  Fixed order at
 // both levels.  part: [slices][c][2] doubles with slices = max(1, nthreads / c); tot: [c][2] doubles.  Ends with a barrier.
+struct SyncThreads {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+// `sync` must be a barrier over exactly the `nthreads` calling threads (default: the whole CTA)
+template <typename Sync = SyncThreads>
 __device__ __forceinline__ void group_channel_totals(const float* __restrict__ group, int ngroups, int c, int nv, int tid, int nthreads,
-                                                     double* part, double* tot) {
+                                                     double* part, double* tot, Sync sync = Sync()) {
   const int slices = max(1, nthreads / c);
   const int per = (ngroups + slices - 1) / slices;
   const float* base = group + (size_t)nv * ngroups * c * 2;
@@ -264,14 +269,14 @@ __device__ __forceinline__ void group_channel_totals(const float* __restrict__ g
     part[(sl * c + ch) * 2] = s;
     part[(sl * c + ch) * 2 + 1] = q;
   }
-  __syncthreads();
+  sync();
   for (int ch = tid; ch < c; ch += nthreads) {
     double s = 0.0, q = 0.0;
     for (int sl = 0; sl < slices; ++sl) { s += part[(sl * c + ch) * 2]; q += part[(sl * c + ch) * 2 + 1]; }
     tot[2 * ch] = s;
     tot[2 * ch + 1] = q;
   }
-  __syncthreads();
+  sync();
 }
 
 // GroupNorm(+FiLM) folded into y = a*x + b for every channel of volume nv, from grouped statistics, into shared a_s[c], b_s[c].
@@ -314,8 +319,9 @@ __device__ __forceinline__ void gn_prefetch_constants(const GnParams& gp, int nv
   }
 }
 // Half 2, after pdl_wait(): one L2 round trip for the group rows, then shared-memory arithmetic.
-__device__ __forceinline__ void gn_affine_from_groups(const GnParams& gp, int nv, int tid, int nthreads, const GnScratch& sc) {
-  group_channel_totals(gp.group, gp.ngroups, gp.c, nv, tid, nthreads, sc.part, sc.tot);
+template <typename Sync = SyncThreads>
+__device__ __forceinline__ void gn_affine_from_groups(const GnParams& gp, int nv, int tid, int nthreads, const GnScratch& sc, Sync sync = Sync()) {
+  group_channel_totals(gp.group, gp.ngroups, gp.c, nv, tid, nthreads, sc.part, sc.tot, sync);
   const int cpg = gp.c / gp.groups;
   for (int g = tid; g < gp.groups; g += nthreads) {
     double s = 0.0, q = 0.0;
@@ -326,7 +332,7 @@ __device__ __forceinline__ void gn_affine_from_groups(const GnParams& gp, int nv
     sc.gstat[2 * g] = mean;
     sc.gstat[2 * g + 1] = 1.0 / sqrt(var + (double)gp.eps);
   }
-  __syncthreads();
+  sync();
   for (int ch = tid; ch < gp.c; ch += nthreads) {
     const int g = ch / cpg;
     const float mean = (float)sc.gstat[2 * g], rstd = (float)sc.gstat[2 * g + 1];
@@ -338,7 +344,7 @@ __device__ __forceinline__ void gn_affine_from_groups(const GnParams& gp, int nv
     sc.a_s[ch] = a;
     sc.b_s[ch] = b;
   }
-  __syncthreads();
+  sync();
 }
 
 // Mish(x) = x * tanh(softplus(x)) = x * n / (n + 2),  n = e^x (e^x + 2)       (nn.Mish)

@@ -25,6 +25,16 @@
 //
 // Warp roles (256 threads): 0 plane TMA producer, 1 weight producer, 2-3 MMA issuers (slot 0 / 1; warp 2 owns TMEM),
 // 4-7 epilogue.
+//
+// Fused GroupNorm + FiLM + Mish (kGN = true, 512 threads): Block.forward is GroupNorm -> FiLM -> Mish -> conv
+// (imagen_pytorch3D.py:555-565) and the normalisation needs the statistics of the whole tensor, so it cannot ride on the PRODUCER's
+// epilogue; it rides on the CONSUMER's load path instead.  The TMA lands the raw plane, warps 8-15 (four per slot) rewrite it in
+// place as mish(a_c * x + b_c) (zero padding rows stay zero), fence it towards the async proxy and only then hand it to the MMA
+// issuer.  Per plane and slot that is 11 520 elements = 2 MUFU + ~12 issue slots each against 9 x 4 x 96 = 3456 tensor-pipe cycles,
+// i.e. ~40 % of the MUFU and ~30 % of the issue budget of the SM, and it removes one full read + write of the activation tensor and
+// one kernel launch per convolution (38 per U-Net forward at the driver config).  The per-channel (a, b) come from the producer's
+// grouped statistics and are finalised in this kernel's prologue exactly like affine_mish_kernel does (common.cuh), so the values
+// entering the tensor cores are bit-identical to the two-kernel path.
 #include <string.h>
 
 #include <algorithm>
@@ -41,6 +51,9 @@ constexpr int ZM_WBLOCK = 64 * 128;                     // one (dz,dy,dx) weight
 constexpr int ZM_WSTAGE = 3 * ZM_WBLOCK;
 constexpr int ZM_WSTAGES = 4;
 constexpr int ZM_THREADS = 256;
+constexpr int ZM_THREADS_GN = 512;                      // + 8 warps that apply GroupNorm + FiLM + Mish to the landed planes
+constexpr int ZM_GN_MAX_CIN = 256, ZM_GN_MAX_N = 2;      // (a, b) of every (volume, channel) live in shared memory
+constexpr int ZM_PLANE_ROWS = (ZM_TY + 2) * (ZM_TX + 2);
 constexpr int ZM_OUT_BYTES = 128 * 128;
 constexpr int ZM_MAX_COUT = 512;                        // BASELINE config 5 sweeps up to 512 channels
 constexpr int ZM_MAX_SEG = 64;                          // z-segments per column (boundaries live in the kernel parameters)
@@ -51,6 +64,7 @@ struct ZmParams {
   const float* bias;  // [c_out]
   float* stats;       // NULL or [n][2*gridDim.x][c_out][2]
   StatsGroups sink;   // optional grouped reduction of the statistics rows (common.cuh)
+  GnParams gn;        // kGN: GroupNorm (+FiLM) of the INPUT, from the grouped statistics of its producer (gn.group != NULL)
   int n, D, H, W;
   int KC, NH, c_out;  // c_in / 64, c_out / 64
   int tiles_x, tiles_y, nseg;
@@ -88,7 +102,8 @@ __device__ __forceinline__ void zm_jrange(int pl, int z0, int z1, int& jlo, int&
   jhi = min(2, (z1 - 1) - (pl - 1));
 }
 
-__global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_constant__ ZmParams p) {
+template <bool kGN>
+__global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_kernel(const __grid_constant__ ZmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* planes = smem;                                               // [2 slots][ZM_RING][ZM_PLANE_STRIDE]
@@ -103,13 +118,15 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
   uint64_t* w_empty = w_full + ZM_WSTAGES;        // [ZM_WSTAGES]  (one arrival per issuing warp)
   uint64_t* acc_full = w_empty + ZM_WSTAGES;      // [2][2]
   uint64_t* acc_free = acc_full + 4;              // [2][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_free + 4);
+  uint64_t* pl_ready = acc_free + 4;              // [2][ZM_RING]  kGN: plane normalised (one arrival per transform warp of the slot)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pl_ready + 2 * ZM_RING);
+  float* aff = reinterpret_cast<float*>(bars + 64);  // kGN: a[n][c_in] then b[n][c_in], n <= ZM_GN_MAX_N, c_in <= ZM_GN_MAX_CIN
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  for (int i = threadIdx.x; i < p.c_out; i += ZM_THREADS) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.c_out; i += blockDim.x) s_bias[i] = p.bias[i];
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < 2 * ZM_RING; ++i) { mbar_init(smem_u32(&pl_full[i]), 1); mbar_init(smem_u32(&pl_empty[i]), 1); }
+    for (int i = 0; i < 2 * ZM_RING; ++i) { mbar_init(smem_u32(&pl_full[i]), 1); mbar_init(smem_u32(&pl_empty[i]), 1); mbar_init(smem_u32(&pl_ready[i]), 4); }
     for (int i = 0; i < ZM_WSTAGES; ++i) { mbar_init(smem_u32(&w_full[i]), 1); mbar_init(smem_u32(&w_empty[i]), 2); }
     for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_free[i]), 4); }
     fence_barrier_init();
@@ -122,7 +139,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  if (warp >= 4) {  // all accumulator blocks start at zero: every MMA accumulates
+  if (warp >= 4 && warp < 8) {  // all accumulator blocks start at zero: every MMA accumulates
     const uint32_t q = (uint32_t)(warp & 3) * 32;
     for (int c = 0; c < 16; ++c) tmem_st32_zero(tmem_base + (q << 16) + (uint32_t)c * 32);
     tmem_st_wait();
@@ -237,7 +254,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
         for (int kc = 0; kc < p.KC; ++kc) {
           uint32_t a_base = 0;
           if (act) {
-            mbar_wait(smem_u32(&pl_full[s * ZM_RING + ring]), rphase);
+            mbar_wait(smem_u32(kGN ? &pl_ready[s * ZM_RING + ring] : &pl_full[s * ZM_RING + ring]), rphase);
             a_base = smem_u32(planes + (size_t)(s * ZM_RING + ring) * ZM_PLANE_STRIDE);
           }
           tc_fence_after();
@@ -276,7 +293,7 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
         }
       }
     }
-  } else {
+  } else if (warp < 8) {
     // ===================== epilogue (warps 4..7) =====================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;  // GEMM row = y * 8 + x inside the tile
@@ -402,6 +419,82 @@ __global__ void __launch_bounds__(ZM_THREADS, 1) conv_zm_kernel(const __grid_con
                        [] { asm volatile("bar.sync 1, 128;" ::: "memory"); });
     }
     if (et == 0) bulk_wait0();
+  } else if (kGN) {
+    // ===================== GroupNorm + FiLM + Mish of the landed input planes (warps 8..15, four per slot) =====================
+    const int tt = threadIdx.x - 256;  // 0..255
+    const int c_in = p.KC * 64;
+    auto sync256 = [] { asm volatile("bar.sync 2, 256;" ::: "memory"); };
+    {
+      // (a, b) per (volume, channel) from the producer's grouped statistics.  The scratch aliases the output staging tile, which the
+      // epilogue cannot touch before the first accumulator is complete, i.e. not before these warps have released a plane.
+      const GnScratch sc = gn_scratch_layout(out_stage, c_in, p.gn.groups, 256);
+      gn_prefetch_constants(p.gn, 0, tt, 256, sc);  // constants of volume 0 while the producer kernel is still draining
+      pdl_wait();
+      for (int nv = 0; nv < p.n; ++nv) {
+        if (nv > 0) gn_prefetch_constants(p.gn, nv, tt, 256, sc);
+        sync256();
+        gn_affine_from_groups(p.gn, nv, tt, 256, sc, sync256);
+        for (int ch = tt; ch < c_in; ch += 256) {
+          aff[nv * c_in + ch] = sc.a_s[ch];
+          aff[(p.n + nv) * c_in + ch] = sc.b_s[ch];
+        }
+        sync256();
+      }
+    }
+    const int s = tt >> 7, tg = tt & 127;
+    // thread -> (physical 16-byte chunk pc, rows rbase + 16 k): the swizzled chunk holds logical chunk pc ^ (row & 7), and
+    // (rbase + 16 k) & 7 == rbase & 7, so one thread always works on the same eight channels of a 64-channel chunk
+    const int pc = tg & 7, rbase = tg >> 3;
+    const int ch0 = (pc ^ (rbase & 7)) << 3;
+    int ring = 0;
+    uint32_t phase = 0;
+    for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
+      const ZmItem it = zm_item(p, 2 * pair + s);
+      if (it.niter == 0) continue;
+      uint32_t vmask = 0;  // rows of this thread that lie inside the volume (the others are the zero padding: left untouched)
+#pragma unroll
+      for (int k = 0; k < 12; ++k) {
+        const int r = rbase + 16 * k;
+        const int ry = r / (ZM_TX + 2), rx = r - ry * (ZM_TX + 2);
+        const int y = it.y0 - 1 + ry, x = it.x0 - 1 + rx;
+        if (r < ZM_PLANE_ROWS && (unsigned)y < (unsigned)p.H && (unsigned)x < (unsigned)p.W) vmask |= 1u << k;
+      }
+      for (int i = 0; i < it.niter; ++i) {
+        for (int kc = 0; kc < p.KC; ++kc) {
+          float av[8], bv[8];
+          {
+            const float4* ap = reinterpret_cast<const float4*>(aff + it.b * c_in + kc * 64 + ch0);
+            const float4* bp = reinterpret_cast<const float4*>(aff + (p.n + it.b) * c_in + kc * 64 + ch0);
+            const float4 a0 = ap[0], a1 = ap[1], b0 = bp[0], b1 = bp[1];
+            av[0] = a0.x; av[1] = a0.y; av[2] = a0.z; av[3] = a0.w; av[4] = a1.x; av[5] = a1.y; av[6] = a1.z; av[7] = a1.w;
+            bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+          }
+          const int b = s * ZM_RING + ring;
+          mbar_wait(smem_u32(&pl_full[b]), phase);
+          uint8_t* base = planes + (size_t)b * ZM_PLANE_STRIDE + rbase * 128 + pc * 16;
+#pragma unroll
+          for (int k0 = 0; k0 < 12; k0 += 4) {
+            uint4 raw[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if ((vmask >> (k0 + u)) & 1u) raw[u] = *reinterpret_cast<const uint4*>(base + (k0 + u) * 16 * 128);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (!((vmask >> (k0 + u)) & 1u)) continue;
+              Vec<__nv_bfloat16> r;
+              r.unpack(raw[u]);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) r.v[e] = mish<true>(fmaf(av[e], r.v[e], bv[e]));
+              r.store(reinterpret_cast<__nv_bfloat16*>(base + (k0 + u) * 16 * 128));
+            }
+          }
+          fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&pl_ready[b]));
+          if (++ring == ZM_RING) { ring = 0; phase ^= 1; }
+        }
+      }
+    }
   }
 
   tc_fence_before();
@@ -533,10 +626,12 @@ int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
     return rc;
   }
   plan->grid = p.pairs < sms ? p.pairs : sms;
-  plan->smem = (size_t)2 * ZM_RING * ZM_PLANE_STRIDE + (size_t)ZM_WSTAGES * ZM_WSTAGE + ZM_OUT_BYTES + ZM_MAX_COUT * 4 + 4 * 64 * 2 * 4 + 512 + 1024;
+  plan->smem = (size_t)2 * ZM_RING * ZM_PLANE_STRIDE + (size_t)ZM_WSTAGES * ZM_WSTAGE + ZM_OUT_BYTES + ZM_MAX_COUT * 4 + 4 * 64 * 2 * 4 + 512 + 1024 +
+               (size_t)2 * ZM_GN_MAX_N * ZM_GN_MAX_CIN * 4;
   static bool attr_done = false;
   if (!attr_done) {
-    DIQT_CUDA(cudaFuncSetAttribute(conv_zm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DIQT_CUDA(cudaFuncSetAttribute(conv_zm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DIQT_CUDA(cudaFuncSetAttribute(conv_zm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
   *out_plan = plan;
@@ -544,8 +639,35 @@ int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
 }
 
 int conv_zm_run(const ZmPlan* plan, cudaStream_t st) {
-  launch_pdl(conv_zm_kernel, plan->grid, ZM_THREADS, plan->smem, st, plan->p);
+  if (plan->p.gn.group)
+    launch_pdl(conv_zm_kernel<true>, plan->grid, ZM_THREADS_GN, plan->smem, st, plan->p);
+  else
+    launch_pdl(conv_zm_kernel<false>, plan->grid, ZM_THREADS, plan->smem, st, plan->p);
   return check_launch("conv_zm");
+}
+
+// GroupNorm (+FiLM) + Mish of the input folded into the plane path.  The statistics must be the grouped kind (<= 16 rows).
+bool conv_zm_gn_supported(const diqt_conv_desc* d) {
+  return conv_zm_supported(d) && d->c_in <= ZM_GN_MAX_CIN && d->n <= ZM_GN_MAX_N;
+}
+
+int conv_zm_set_gn(ZmPlan* plan, const GnParams& gn) {
+  const int c_in = plan->p.KC * 64;
+  DIQT_REQUIRE(c_in <= ZM_GN_MAX_CIN && plan->p.n <= ZM_GN_MAX_N, "conv(zm) fused GroupNorm: c_in=%d (<= %d), n=%d (<= %d)", c_in, ZM_GN_MAX_CIN,
+               plan->p.n, ZM_GN_MAX_N);
+  DIQT_REQUIRE(gn.group && gn.ngroups > 0 && gn.gamma && gn.beta && gn.groups > 0 && c_in % gn.groups == 0 && gn.c == c_in,
+               "conv(zm) fused GroupNorm: bad description (c=%d, c_in=%d, groups=%d)", gn.c, c_in, gn.groups);
+  DIQT_REQUIRE(gn_scratch_bytes(c_in, gn.groups, 256) <= (size_t)ZM_OUT_BYTES, "conv(zm) fused GroupNorm: finalisation scratch of %zu bytes does not fit",
+               gn_scratch_bytes(c_in, gn.groups, 256));
+  plan->p.gn = gn;
+  return DIQT_OK;
+}
+
+void conv_zm_set_film(ZmPlan* plan, const float* film, int film_ld, const int* film_row, int film_row_stride_n) {
+  plan->p.gn.film = film;
+  plan->p.gn.film_ld = film_ld;
+  plan->p.gn.film_row = film_row;
+  plan->p.gn.film_row_stride_n = film_row_stride_n;
 }
 
 int conv_zm_set_stats(ZmPlan* plan, float* partial, float* group, unsigned int* tickets, int* ngroups) {
