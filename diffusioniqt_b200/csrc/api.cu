@@ -25,6 +25,9 @@ int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
 int conv_zm_run(const ZmPlan* plan, cudaStream_t st);
 int conv_zm_set_stats(ZmPlan* plan, float* partial, float* group, unsigned int* tickets, int* ngroups);
 void conv_zm_destroy(ZmPlan* plan);
+bool conv_zm_gn_supported(const diqt_conv_desc* d);
+int conv_zm_set_gn(ZmPlan* plan, const GnParams& gn);
+void conv_zm_set_film(ZmPlan* plan, const float* film, int film_ld, const int* film_row, int film_row_stride_n);
 }  // namespace diqt
 
 using namespace diqt;
@@ -166,5 +169,26 @@ extern "C" int diqt_conv_plan_set_stats_g(diqt_conv_plan* plan, float* partial, 
           : plan->impl == DIQT_IMPL_TC ? conv_tc_set_stats(plan->tc, partial, group, tickets, ngroups)
                                        : 0;
   if (*nblk == 0) *ngroups = 0;
+  return DIQT_OK;
+}
+
+// ---- GroupNorm (+FiLM) + Mish of the conv INPUT, fused into the conv's load path (z-march family) ------------------------------
+extern "C" int diqt_conv_gn_fusable(const diqt_conv_desc* d) {
+  int impl = 0;
+  if (check_desc(d) || resolve_impl(d, &impl)) return 0;
+  return impl == DIQT_IMPL_ZM && conv_zm_gn_supported(d) ? 1 : 0;
+}
+
+extern "C" int diqt_conv_plan_set_gn(diqt_conv_plan* plan, const float* group, int ngroups, int64_t voxels, int groups, float eps,
+                                     const float* gamma, const float* beta) {
+  DIQT_REQUIRE(plan && group && gamma && beta, "conv_plan_set_gn: null pointer");
+  DIQT_REQUIRE(plan->impl == DIQT_IMPL_ZM && plan->zm, "conv_plan_set_gn: only the z-march family fuses the input GroupNorm (ask diqt_conv_gn_fusable first)");
+  GnParams gn = {group, ngroups, (long long)voxels, plan->d.c_in, groups, eps, gamma, beta, nullptr, 0, nullptr, 0};
+  return conv_zm_set_gn(plan->zm, gn);
+}
+
+extern "C" int diqt_conv_plan_set_film(diqt_conv_plan* plan, const float* film, int film_ld, const int32_t* film_row, int film_row_stride_n) {
+  DIQT_REQUIRE(plan && plan->impl == DIQT_IMPL_ZM && plan->zm, "conv_plan_set_film: plan has no fused GroupNorm");
+  conv_zm_set_film(plan->zm, film, film_ld, film_row, film_row_stride_n);
   return DIQT_OK;
 }

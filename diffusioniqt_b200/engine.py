@@ -90,6 +90,7 @@ class UnetEngine:
         self.film_row_ptr = 0                 # device int32* (sampler step) or NULL
         self.film_stride_n = 1
         self.conv_impls = {}                  # site name -> resolved impl (for tests / reporting)
+        self.fused_gn = []                    # conv sites that apply GroupNorm + FiLM + Mish on their own load path
         # sampler states (schedule tables, captured step graphs) that bake this engine's buffer addresses live and die with it
         self.sampler_cache = {}
         self.film_gen = 0
@@ -106,10 +107,17 @@ class UnetEngine:
         self._keep.append(t)
         return t
 
-    def _conv_site(self, name, mode, level_in, c_in, ld_in, c_out, ld_out, weight, bias, src_ptr, dst_ptr, stats=None, vol=None, impl=None):
+    def _conv_desc(self, mode, level_in, c_in, ld_in, c_out, ld_out, vol=None, impl=None):
+        cn, (d0, d1, d2) = (self.conv_n, self.conv_dims[level_in]) if vol is None else (vol[0], vol[1:])
+        return L.ConvDesc(mode=mode, dtype=self.ddtype, impl=self.impl if impl is None else impl, n=cn, d0=d0, d1=d1, d2=d2,
+                          c_in=c_in, ld_in=ld_in, c_out=c_out, ld_out=ld_out, flags=0)
+
+    def _conv_site(self, name, mode, level_in, c_in, ld_in, c_out, ld_out, weight, bias, src_ptr, dst_ptr, stats=None, vol=None, impl=None, gn=None):
         """Pack weights, create the plan, return the launch closure.  With `stats` (index of a statistics scratch set) the conv
         is asked to emit the channel statistics of its output; if it cannot, a separate stats pass is appended by the caller.
-        `vol` = (n, d0, d1, d2) overrides the level geometry (token volumes of the attention blocks)."""
+        `vol` = (n, d0, d1, d2) overrides the level geometry (token volumes of the attention blocks).
+        `gn` = (grouped stats record of the input, nn.GroupNorm holder, FiLM column offset or None): the conv reads the RAW input and
+        applies GroupNorm + FiLM + Mish on its own load path (include/diqt.h: diqt_conv_plan_set_gn)."""
         cn, (d0, d1, d2) = (self.conv_n, self.conv_dims[level_in]) if vol is None else (vol[0], vol[1:])
         if self.sub_f > 1:
             stats = None   # fused conv statistics are per conv volume; boundary mode needs them per sub-volume
@@ -136,6 +144,13 @@ class UnetEngine:
                 f"plan {name}")
         self._plans.append(plan.value)
         run, pv = self.lib.diqt_conv_run, plan.value
+        film_off = None
+        if gn is not None:
+            (gpart, gnb, ggrp, gng), gmod, film_off = gn
+            gamma, beta = self._f32(gmod.weight), self._f32(gmod.bias)
+            L.check(self.lib.diqt_conv_plan_set_gn(pv, ggrp.data_ptr(), gng, self.level_vox[level_in], gmod.num_groups, float(gmod.eps),
+                                                   gamma.data_ptr(), beta.data_ptr()), f"set_gn {name}")
+            self.fused_gn.append(name)
         self._last_conv_stats = None          # (partial, nblk, group, ngroups) when the conv emits the statistics of its output
         if stats is not None:
             nb, ng = C.c_int(0), C.c_int(0)
@@ -147,6 +162,13 @@ class UnetEngine:
                 L.check(self.lib.diqt_conv_plan_set_stats(pv, part.data_ptr(), C.byref(nb)), f"set_stats {name}")
             if nb.value:
                 self._last_conv_stats = (part, nb.value, self.grp[stats] if ng.value else None, ng.value)
+        if film_off is not None:
+            eng, set_film = self, self.lib.diqt_conv_plan_set_film
+
+            def op(st):          # the FiLM table may move between calls (set_condition): bind its address at launch / capture time
+                L.check(set_film(pv, eng.film.data_ptr() + film_off * 4, eng._film_cols, eng.film_row_ptr, eng.film_stride_n), name)
+                L.check(run(pv, st), name)
+            return op
         return lambda st: L.check(run(pv, st), name)
 
     # ------------------------------------------------------------------ build
@@ -191,12 +213,15 @@ class UnetEngine:
         self.nblk = [_nblk(n, v) for v in self.level_vox]
         self.nblk_stream = [_nblk(n, v, 592) for v in self.level_vox]
         pmax = 304 * n * cmax * 2     # up to two partials (z-march slots) per SM and volume
-        self.part = [torch.zeros(pmax, dtype=torch.float32, device=self.device) for _ in range(3)]
+        # statistics scratch sets: 0 / 1 ping-pong between block outputs, 2 = conv1 output, 3 = conv2 output (a conv with the fused
+        # input GroupNorm READS its input's set in its prologue and WRITES its output's set at its end: they must not be the same set)
+        self.part = [torch.zeros(pmax, dtype=torch.float32, device=self.device) for _ in range(4)]
         # grouped statistics (include/diqt.h): producers also reduce their partial rows in <= 16 groups and the consumers finalise
         # GroupNorm / SE in their own prologue, which removes ~57 single-CTA finalize launches per forward.  Plain small batches only.
         self.grouped = self.sub_f <= 1 and n <= 2 and os.environ.get("DIQT_DISABLE_GROUPED", "0") != "1"   # variable: A/B and diagnostics
-        self.grp = [torch.zeros(16 * n * cmax * 2, dtype=torch.float32, device=self.device) for _ in range(3)]
-        self.tick = [torch.zeros(16 * n, dtype=torch.int32, device=self.device) for _ in range(3)]
+        self.grp = [torch.zeros(16 * n * cmax * 2, dtype=torch.float32, device=self.device) for _ in range(4)]
+        self.tick = [torch.zeros(16 * n, dtype=torch.int32, device=self.device) for _ in range(4)]
+        self.fuse_gn = self.grouped and self.dtype == "bf16" and os.environ.get("DIQT_DISABLE_GN_FUSION", "0") != "1"   # variable: A/B
         self.aff_a = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
         self.aff_b = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
         self.gate = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
@@ -303,17 +328,31 @@ class UnetEngine:
                 x.stats = add_stats(x, level, self._pp)
                 self._pp ^= 1
             film_off = film_slot(blk)
-            a1 = add_norm_act(x, level, blk.block1.groupnorm, None, sc["A"], name + ".block1")
+
+            def norm_conv(cname, src: Act, gmod, f_off, ci, dst: Act, weight, bias, si):
+                """mish(FiLM(GroupNorm(src))) -> 3x3x3 conv -> dst; the normalisation rides on the conv's load path when the plan can."""
+                desc = self._conv_desc(L.CONV_K3, level, ci, src.ld, cout, dst.ld)
+                if self.fuse_gn and src.stats[2] is not None and lib.diqt_conv_gn_fusable(C.byref(desc)):
+                    ops.append(self._conv_site(cname, L.CONV_K3, level, ci, src.ld, cout, dst.ld, weight, bias, src.ptr, dst.ptr, stats=si,
+                                               gn=(src.stats, gmod, f_off)))
+                    return True
+                a = add_norm_act(src, level, gmod, f_off, sc["A"], cname.rsplit(".", 1)[0])
+                ops.append(self._conv_site(cname, L.CONV_K3, level, ci, a.ld, cout, dst.ld, weight, bias, a.ptr, dst.ptr, stats=si))
+                return False
+
             h = Act(sc["H"], cout, cout)
-            ops.append(self._conv_site(name + ".block1.project", L.CONV_K3, level, cin, a1.ld, cout, h.ld, blk.block1.project.weight,
-                                       blk.block1.project.bias, a1.ptr, h.ptr, stats=2))
+            norm_conv(name + ".block1.project", x, blk.block1.groupnorm, None, cin, h, blk.block1.project.weight, blk.block1.project.bias, 2)
             h.stats = self._last_conv_stats or add_stats(h, level, 2)
-            a2 = add_norm_act(h, level, blk.block2.groupnorm, film_off, sc["A"], name + ".block2")
-            ops.append(self._conv_site(name + ".block2.project", L.CONV_K3, level, cout, a2.ld, cout, h.ld, blk.block2.project.weight,
-                                       blk.block2.project.bias, a2.ptr, h.ptr, stats=2 if blk.has_se else None))
+            # conv2 cannot run in place: with the fused normalisation it reads h itself, so its output goes to the (otherwise unused) A buffer
+            fusable2 = (self.fuse_gn and h.stats[2] is not None
+                        and lib.diqt_conv_gn_fusable(C.byref(self._conv_desc(L.CONV_K3, level, cout, h.ld, cout, cout))))
+            h2 = Act(sc["A"], cout, cout) if fusable2 else h
+            norm_conv(name + ".block2.project", h, blk.block2.groupnorm, film_off, cout, h2, blk.block2.project.weight, blk.block2.project.bias,
+                      3 if blk.has_se else None)
+            h = h2
             gate_ptr, se = 0, None
             if blk.has_se:
-                part, nb, grp, ng = self._last_conv_stats or add_stats(h, level, 2)
+                part, nb, grp, ng = self._last_conv_stats or add_stats(h, level, 3)
                 w1, w2 = self._f32(blk.se.fc[0].weight), self._f32(blk.se.fc[2].weight)
                 hidden = w1.shape[0]
                 if hidden < 1:

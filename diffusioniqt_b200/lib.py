@@ -49,6 +49,9 @@ _SIGNATURES = {
     "diqt_stats_groups": [_i, _i, C.POINTER(C.c_int)],
     "diqt_conv_plan_set_stats_g": [_vp, _vp, _vp, _vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "diqt_channel_stats_g": [_vp, _i, _i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "diqt_conv_gn_fusable": [C.POINTER(ConvDesc)],
+    "diqt_conv_plan_set_gn": [_vp, _vp, _i, _i64, _i, _f, _vp, _vp],
+    "diqt_conv_plan_set_film": [_vp, _vp, _i, _vp, _i],
     "diqt_gn_mish_g": [_vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _i, _i, _f, _vp, _vp, _vp, _i, _vp, _i, _i, _vp],
     "diqt_scale_residual_g": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp],
     "diqt_scale_copy": [_vp, _i, _vp, _i, _i, _i64, _i, _f, _vp],

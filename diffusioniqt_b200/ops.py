@@ -35,8 +35,10 @@ def from_channels_last(x: torch.Tensor) -> torch.Tensor:
 
 
 def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], mode: str = "k3", impl: str = "auto", with_stats: bool = False,
-           grouped: bool = False):
+           grouped: bool = False, gn: Optional[dict] = None):
     """x: (n, d0, d1, d2, c_in) bf16/fp32 on CUDA; weight/bias exactly as in the reference state_dict (fp32).
+    gn = dict(groups, gamma, beta, scale_shift=None, eps=1e-5, nblk=8): the conv computes conv(mish(FiLM(GroupNorm(x)))) with the
+    normalisation fused into its load path (z-march family only; raises if the plan cannot).
     with_stats=True also returns the fused per-block channel statistics (n, nblk, c_out, 2) or None if the kernel cannot fuse them;
     with grouped=True the statistics are (partial rows, group sums (n, ngroups, c_out, 2)) through the grouped sink."""
     lib = L.load()
@@ -70,6 +72,18 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
     L.check(lib.diqt_conv_plan_create(C.byref(desc), x.data_ptr(), out.data_ptr(), packed.data_ptr(), pbias.data_ptr(), C.byref(plan)), "conv_plan")
     stats = None
     try:
+        if gn is not None:
+            if not lib.diqt_conv_gn_fusable(C.byref(desc)):
+                raise L.DiqtError("conv3d(gn=...): this shape / family cannot fuse the input GroupNorm")
+            _, ggrp = channel_stats_grouped(x, gn.get("nblk", 8))
+            gamma = gn["gamma"].detach().float().contiguous().to(x.device)
+            beta = gn["beta"].detach().float().contiguous().to(x.device)
+            L.check(lib.diqt_conv_plan_set_gn(plan.value, ggrp.data_ptr(), ggrp.shape[1], d0 * d1 * d2, gn["groups"], gn.get("eps", 1e-5),
+                                              gamma.data_ptr(), beta.data_ptr()), "conv_plan_set_gn")
+            film = gn.get("scale_shift")
+            if film is not None:
+                film = film.detach().float().contiguous().to(x.device)
+                L.check(lib.diqt_conv_plan_set_film(plan.value, film.data_ptr(), 2 * c_in, 0, 1), "conv_plan_set_film")
         if with_stats:
             buf = torch.full((n * 320 * c_out * 2,), float("nan"), dtype=torch.float32, device=x.device)
             nb = C.c_int(0)

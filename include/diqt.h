@@ -151,6 +151,16 @@ int diqt_stats_groups(int nblk, int rows_per_cta, int* ngroups);
 int diqt_conv_plan_set_stats_g(diqt_conv_plan* plan, float* partial, float* group, uint32_t* tickets, int* nblk, int* ngroups);
 int diqt_channel_stats_g(const void* x, int dtype, int n, int64_t voxels, int c, int ld, int nblk, float* partial,
                          float* group, uint32_t* tickets, void* stream);
+/* Block.forward is GroupNorm -> FiLM -> Mish -> Conv3d (imagen_pytorch3D.py:555-565).  For plans of the z-march family
+ * (diqt_conv_gn_fusable(desc) != 0: 3x3x3 bf16, c_in <= 256, n <= 2) the first three steps can ride on the conv's load path: the conv then
+ * reads the RAW tensor x (not mish(GN(x))) and normalises every input plane in shared memory between the TMA and the tensor core, with
+ * the statistics of x taken from `group` exactly as diqt_gn_mish_g does (bit-identical operands, one tensor read + write and one launch
+ * less).  diqt_conv_plan_set_film adds / updates the FiLM rows (arguments as in diqt_gn_finalize); call it before diqt_conv_run
+ * whenever the table pointer or the row selector changes. */
+int diqt_conv_gn_fusable(const diqt_conv_desc* desc);
+int diqt_conv_plan_set_gn(diqt_conv_plan* plan, const float* group, int ngroups, int64_t voxels, int groups, float eps,
+                          const float* gamma, const float* beta);
+int diqt_conv_plan_set_film(diqt_conv_plan* plan, const float* film, int film_ld, const int32_t* film_row, int film_row_stride_n);
 /* y = mish(GroupNorm(groups, eps, gamma, beta)(x) [* (scale + 1) + shift]) with the statistics of x taken from `group`
  * (nn.GroupNorm :546, FiLM :559-561, nn.Mish :547); film arguments as in diqt_gn_finalize */
 int diqt_gn_mish_g(const void* x, int ld_x, void* y, int ld_y, int dtype, int n, int64_t voxels, int c, const float* group,

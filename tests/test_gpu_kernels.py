@@ -137,6 +137,41 @@ def test_conv_zmarch_bf16(n, dims, c_in, c_out):
     assert max_rel(s[..., 1], (stored ** 2).sum(dim=(2, 3, 4))) < 2e-4
 
 
+GN_FUSED_SHAPES = [
+    # n, dims, c_in, c_out, film
+    (1, (16, 16, 16), 64, 64, True),
+    (1, (5, 16, 8), 64, 64, False),      # one column, odd depth
+    (2, (8, 32, 16), 64, 128, True),     # two volumes: per-volume statistics and FiLM rows, two output-channel groups
+    (1, (32, 32, 32), 192, 128, True),   # ups.0.1.block1: concat input, GroupNorm groups of 24 channels straddling the 64-channel chunks
+    (1, (16, 16, 16), 128, 128, False),
+    (1, (8, 16, 16), 256, 64, True),     # widest fusable input
+    (1, (64, 64, 64), 64, 64, True),     # BASELINE config 2 shape
+]
+
+
+@pytest.mark.parametrize("n,dims,c_in,c_out,film", GN_FUSED_SHAPES)
+def test_conv_zmarch_fused_groupnorm_film_mish(n, dims, c_in, c_out, film):
+    """Block.forward (GroupNorm -> FiLM -> Mish -> conv, imagen_pytorch3D.py:555-565) as ONE conv launch: the normalisation rides on the
+    conv's load path.  Checked against fp32 PyTorch on the CPU, and bit for bit against the two-kernel path of this library (the
+    transform produces the same bf16 operands the separate apply kernel would have stored)."""
+    from diffusioniqt_b200 import ops
+    x = (_rand(n, c_in, *dims, seed=31) * 1.7 + 0.3).bfloat16().float()
+    w, b = _conv_weight("k3", c_in, c_out, 32)
+    gamma, beta = _rand(c_in, seed=33) * 0.2 + 1.0, _rand(c_in, seed=34) * 0.1
+    ss = _rand(n, 2 * c_in, seed=35) * 0.3 if film else None
+    y = F.group_norm(x, 8, gamma, beta, 1e-5)
+    if film:
+        y = y * (ss[:, :c_in, None, None, None] + 1) + ss[:, c_in:, None, None, None]
+    want = F.conv3d(F.mish(y), w.bfloat16().float(), b, padding=1)
+    xg = ops.to_channels_last(x.cuda(), torch.bfloat16)
+    got, stats = ops.conv3d(xg, w, b, mode="k3", impl="zm", with_stats=True, gn=dict(groups=8, gamma=gamma, beta=beta, scale_shift=ss, nblk=16))
+    assert max_rel(ops.from_channels_last(got).cpu(), want) < BF16_TOL
+    a = ops.group_norm_film_mish(xg, 8, gamma, beta, ss, nblk=16, grouped=True)
+    two, stats2 = ops.conv3d(a, w, b, mode="k3", impl="zm", with_stats=True)
+    assert torch.equal(got, two)
+    assert torch.equal(stats, stats2)
+
+
 @pytest.mark.parametrize("mode,n,dims,c_in,c_out", [("k3", 1, (16, 16, 16), 64, 64), ("k3", 2, (8, 8, 8), 128, 128), ("down", 1, (16, 16, 16), 64, 128),
                                                      ("k1", 2, (8, 8, 8), 128, 256), ("k3", 1, (12, 12, 12), 64, 64)])
 def test_conv_tcgen05_fused_stats(mode, n, dims, c_in, c_out):

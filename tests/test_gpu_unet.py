@@ -54,6 +54,27 @@ def test_driver_config_uses_tcgen05_kernels():
     assert len(zm) == 20 and all(k.endswith(".project") for k in zm)
 
 
+def test_fused_input_groupnorm_equals_the_two_kernel_path(monkeypatch):
+    """Every Block.project the z-march family takes applies GroupNorm + FiLM + Mish on its own load path (no separate apply kernel, no
+    normalised copy of the tensor); the forward must not change by a single bit against the two-kernel path."""
+    case = FORWARD_CASES["driver_dim64_s16"]
+    x, lr, time = (t.cuda() for t in build_inputs(case))
+    outs, launches = [], []
+    for disable in ("1", "0"):
+        monkeypatch.setenv("DIQT_DISABLE_GN_FUSION", disable)
+        unet = _gpu_unet(case, "bf16")
+        outs.append(unet(x, None, time, lowres_cond_img=lr))
+        eng = next(iter(unet._engines.values()))
+        launches.append(len(eng._ops))
+        if disable == "1":
+            assert eng.fused_gn == []
+        else:
+            # the twelve + eight 3x3x3 convs of the 16^3 level (the only level whose planes fit the 16 x 8 tile at this test size)
+            assert len(eng.fused_gn) == 20 and all(k.endswith(".project") for k in eng.fused_gn)
+    assert torch.equal(outs[0], outs[1])
+    assert launches[1] == launches[0] - 20          # one launch less per fused conv
+
+
 def test_forward_is_repeatable_and_fresh():
     case = FORWARD_CASES["cfg1_dim32_s16_b2"]
     unet = _gpu_unet(case, "bf16")
