@@ -27,6 +27,7 @@ int conv_zm_set_stats(ZmPlan* plan, float* partial, float* group, unsigned int* 
 void conv_zm_destroy(ZmPlan* plan);
 bool conv_zm_gn_supported(const diqt_conv_desc* d);
 int conv_zm_set_gn(ZmPlan* plan, const GnParams& gn);
+int conv_zm_set_gn_affine(ZmPlan* plan, const float* a, const float* b);
 void conv_zm_set_film(ZmPlan* plan, const float* film, int film_ld, const int* film_row, int film_row_stride_n);
 }  // namespace diqt
 
@@ -187,8 +188,14 @@ extern "C" int diqt_conv_plan_set_gn(diqt_conv_plan* plan, const float* group, i
   return conv_zm_set_gn(plan->zm, gn);
 }
 
+extern "C" int diqt_conv_plan_set_gn_affine(diqt_conv_plan* plan, const float* a, const float* b) {
+  DIQT_REQUIRE(plan && plan->impl == DIQT_IMPL_ZM && plan->zm, "conv_plan_set_gn_affine: only the z-march family fuses the input GroupNorm");
+  return conv_zm_set_gn_affine(plan->zm, a, b);
+}
+
 extern "C" int diqt_conv_plan_set_film(diqt_conv_plan* plan, const float* film, int film_ld, const int32_t* film_row, int film_row_stride_n) {
   DIQT_REQUIRE(plan && plan->impl == DIQT_IMPL_ZM && plan->zm, "conv_plan_set_film: plan has no fused GroupNorm");
+  // (with diqt_conv_plan_set_gn_affine the FiLM rows are already folded into a, b by diqt_gn_finalize)
   conv_zm_set_film(plan->zm, film, film_ld, film_row, film_row_stride_n);
   return DIQT_OK;
 }

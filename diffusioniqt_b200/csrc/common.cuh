@@ -350,8 +350,22 @@ __device__ __forceinline__ void gn_affine_from_groups(const GnParams& gp, int nv
 // Mish(x) = x * tanh(softplus(x)) = x * n / (n + 2),  n = e^x (e^x + 2)       (nn.Mish)
 // Branch-free: the exponent is clamped at 20 (the softplus threshold of the reference op), where n/(n+2) == 1 in fp32.
 // kFast uses the approximate SFU ops with flush-to-zero (2 MUFU + 7 FP32 ops per element, no range fix-up code).
+//   DIQT_MISH_V2=1   kFast: x - 2x / (u^2 + 2u + 2), u = e^x: two instructions less per element and no clamp (u = inf gives 1/inf = 0,
+//                    i.e. mish = x); loses RELATIVE accuracy in the far negative tail (|mish| < 1e-4), which bf16 storage cannot see.
+#ifndef DIQT_MISH_V2
+#define DIQT_MISH_V2 0
+#endif
 template <bool kFast>
 __device__ __forceinline__ float mish(float x) {
+#if DIQT_MISH_V2
+  if (kFast) {
+    float u, w;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(x * 1.4426950408889634f));
+    const float d = fmaf(u, u + 2.f, 2.f);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(d));
+    return fmaf(x * w, -2.f, x);
+  }
+#endif
   if (kFast) {
     float t = fminf(x * 1.4426950408889634f, 28.853900817779268f), u, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(t));

@@ -307,6 +307,26 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
   const int64_t v1 = min(voxels, v0 + vpb);
   using Raw = typename Vec<T>::Raw;
   float g[VEC], s[VEC], q[VEC];
+  const T* hb = h + col * VEC;
+  const T* rb = res + col * VEC;
+  T* ob = out + col * VEC;
+  // The first batch of streaming loads (8 x 16 bytes per thread) is issued right after the grid dependency resolves and BEFORE the gate
+  // is worked out: the gate needs an L2 round trip and five barriers, during which the memory system would otherwise sit idle.
+  Raw ra0[4], rr0[4];
+  int64_t row0[4];
+  int64_t v = v0 + lane;
+  bool pre = false;
+  auto preload = [&] {
+    pre = v + 3 * (int64_t)lanes < v1;
+    if (pre) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        row0[u] = sub_row(sg, voxels, n, v + (int64_t)u * lanes);
+        ra0[u] = Vec<T>::load_raw(hb + row0[u] * ld_h);
+        rr0[u] = Vec<T>::load_raw(rb + row0[u] * ld_res);
+      }
+    }
+  };
   if (se.group) {
     // squeeze-excitation gate (imagen_pytorch3D.py:617-632) from the grouped statistics of conv2's output, recomputed by every CTA.
     // Shared layout (se_scratch_bytes): doubles part[slices*c*2], tot[c*2]; floats mean[c], hid[hidden], gs[c], w1[hidden*c], w2[c*hidden]
@@ -329,6 +349,7 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
       w2s = s2;
     }
     pdl_sync();
+    preload();
     group_channel_totals(se.group, se.ngroups, c, n, threadIdx.x, blockDim.x, part, tot);
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) mean[ch] = (float)(tot[2 * ch] / (double)voxels);
     __syncthreads();
@@ -352,14 +373,12 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
     __syncthreads();  // smem is reused by the block reduction below
   } else {
     pdl_sync();
+    preload();
 #pragma unroll
     for (int i = 0; i < VEC; ++i) g[i] = gate ? __ldcg(gate + (int64_t)n * c + col * VEC + i) : 1.f;
   }
 #pragma unroll
   for (int i = 0; i < VEC; ++i) s[i] = q[i] = 0.f;
-  const T* hb = h + col * VEC;
-  const T* rb = res + col * VEC;
-  T* ob = out + col * VEC;
   auto emit = [&](const Raw& ra, const Raw& rr, int64_t row) {
     Vec<T> a, r, o;
     a.unpack(ra);
@@ -377,7 +396,11 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
       }
     }
   };
-  int64_t v = v0 + lane;
+  if (pre) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(ra0[u], rr0[u], row0[u]);
+    v += 4 * (int64_t)lanes;
+  }
   // eight 16-byte loads in flight per thread (4 voxels x 2 streams), kept packed until used; voxel order per thread is unchanged
   for (; v + 3 * (int64_t)lanes < v1; v += 4 * (int64_t)lanes) {
     Raw ra[4], rr[4];

@@ -112,12 +112,17 @@ class UnetEngine:
         return L.ConvDesc(mode=mode, dtype=self.ddtype, impl=self.impl if impl is None else impl, n=cn, d0=d0, d1=d1, d2=d2,
                           c_in=c_in, ld_in=ld_in, c_out=c_out, ld_out=ld_out, flags=0)
 
+    def _resolves_to_zm(self, desc) -> bool:
+        impl = C.c_int(0)
+        return self.lib.diqt_conv_resolved_impl(C.byref(desc), C.byref(impl)) == 0 and impl.value == L.IMPL_ZM
+
     def _conv_site(self, name, mode, level_in, c_in, ld_in, c_out, ld_out, weight, bias, src_ptr, dst_ptr, stats=None, vol=None, impl=None, gn=None):
         """Pack weights, create the plan, return the launch closure.  With `stats` (index of a statistics scratch set) the conv
         is asked to emit the channel statistics of its output; if it cannot, a separate stats pass is appended by the caller.
         `vol` = (n, d0, d1, d2) overrides the level geometry (token volumes of the attention blocks).
         `gn` = (grouped stats record of the input, nn.GroupNorm holder, FiLM column offset or None): the conv reads the RAW input and
-        applies GroupNorm + FiLM + Mish on its own load path (include/diqt.h: diqt_conv_plan_set_gn)."""
+        applies GroupNorm + FiLM + Mish on its own load path (include/diqt.h: diqt_conv_plan_set_gn); `gn` = "affine": the same with
+        the per-(volume, channel) affine that diqt_gn_finalize leaves in self.aff_a / self.aff_b (diqt_conv_plan_set_gn_affine)."""
         cn, (d0, d1, d2) = (self.conv_n, self.conv_dims[level_in]) if vol is None else (vol[0], vol[1:])
         if self.sub_f > 1:
             stats = None   # fused conv statistics are per conv volume; boundary mode needs them per sub-volume
@@ -145,7 +150,10 @@ class UnetEngine:
         self._plans.append(plan.value)
         run, pv = self.lib.diqt_conv_run, plan.value
         film_off = None
-        if gn is not None:
+        if gn == "affine":
+            L.check(self.lib.diqt_conv_plan_set_gn_affine(pv, self.aff_a.data_ptr(), self.aff_b.data_ptr()), f"set_gn_affine {name}")
+            self.fused_gn.append(name)
+        elif gn is not None:
             (gpart, gnb, ggrp, gng), gmod, film_off = gn
             gamma, beta = self._f32(gmod.weight), self._f32(gmod.bias)
             L.check(self.lib.diqt_conv_plan_set_gn(pv, ggrp.data_ptr(), gng, self.level_vox[level_in], gmod.num_groups, float(gmod.eps),
@@ -222,6 +230,8 @@ class UnetEngine:
         self.grp = [torch.zeros(16 * n * cmax * 2, dtype=torch.float32, device=self.device) for _ in range(4)]
         self.tick = [torch.zeros(16 * n, dtype=torch.int32, device=self.device) for _ in range(4)]
         self.fuse_gn = self.grouped and self.dtype == "bf16" and os.environ.get("DIQT_DISABLE_GN_FUSION", "0") != "1"   # variable: A/B
+        # larger batches: statistics are finalised by diqt_gn_finalize into (aff_a, aff_b) and the conv applies that affine + Mish
+        self.fuse_gn_affine = (not self.grouped and self.sub_f <= 1 and self.dtype == "bf16" and os.environ.get("DIQT_DISABLE_GN_FUSION", "0") != "1")
         self.aff_a = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
         self.aff_b = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
         self.gate = torch.zeros(n * cmax, dtype=torch.float32, device=self.device)
@@ -295,8 +305,9 @@ class UnetEngine:
             gamma, beta = self._f32(gn.weight), self._f32(gn.bias)
             groups, eps = gn.num_groups, float(gn.eps)
             gp, bp, c = gamma.data_ptr(), beta.data_ptr(), x.c
-            dst = Act(dst_buf, x.c, x.c)
-            xp, xl, dp, dl, nbk = x.ptr, x.ld, dst.ptr, dst.ld, self.nblk_stream[level]
+            dst = Act(dst_buf, x.c, x.c) if dst_buf is not None else None      # None: finalize only (the consumer applies the affine itself)
+            xp, xl, nbk = x.ptr, x.ld, self.nblk_stream[level]
+            dp, dl = (dst.ptr, dst.ld) if dst is not None else (0, 0)
             if grp is not None:
                 # one kernel: GroupNorm finalisation in the prologue, then the affine + Mish pass
                 gptr = grp.data_ptr()
@@ -315,6 +326,8 @@ class UnetEngine:
                     fptr = eng.film.data_ptr() + film_off * 4
                     L.check(gnf(pp, n, nb, vox, c, groups, eps, gp, bp, fptr, eng._film_cols, eng.film_row_ptr, eng.film_stride_n, pa, pb, st), name + ".gn")
                 ops.append(op)
+            if dst is None:
+                return None
             sf, sh = self.level_sub[level]
             ops.append(lambda st: L.check(aff(xp, xl, dp, dl, dd, n, vox, c, pa, pb, nbk, sf, sh, st), name + ".mish"))
             return dst
@@ -336,6 +349,10 @@ class UnetEngine:
                     ops.append(self._conv_site(cname, L.CONV_K3, level, ci, src.ld, cout, dst.ld, weight, bias, src.ptr, dst.ptr, stats=si,
                                                gn=(src.stats, gmod, f_off)))
                     return True
+                if self.fuse_gn_affine and src.stats[2] is None and self._resolves_to_zm(desc):
+                    add_norm_act(src, level, gmod, f_off, None, cname.rsplit(".", 1)[0])       # finalize only: (a, b) -> self.aff_a / aff_b
+                    ops.append(self._conv_site(cname, L.CONV_K3, level, ci, src.ld, cout, dst.ld, weight, bias, src.ptr, dst.ptr, stats=si, gn="affine"))
+                    return True
                 a = add_norm_act(src, level, gmod, f_off, sc["A"], cname.rsplit(".", 1)[0])
                 ops.append(self._conv_site(cname, L.CONV_K3, level, ci, a.ld, cout, dst.ld, weight, bias, a.ptr, dst.ptr, stats=si))
                 return False
@@ -344,8 +361,9 @@ class UnetEngine:
             norm_conv(name + ".block1.project", x, blk.block1.groupnorm, None, cin, h, blk.block1.project.weight, blk.block1.project.bias, 2)
             h.stats = self._last_conv_stats or add_stats(h, level, 2)
             # conv2 cannot run in place: with the fused normalisation it reads h itself, so its output goes to the (otherwise unused) A buffer
-            fusable2 = (self.fuse_gn and h.stats[2] is not None
-                        and lib.diqt_conv_gn_fusable(C.byref(self._conv_desc(L.CONV_K3, level, cout, h.ld, cout, cout))))
+            d2_ = self._conv_desc(L.CONV_K3, level, cout, h.ld, cout, cout)
+            fusable2 = ((self.fuse_gn and h.stats[2] is not None and lib.diqt_conv_gn_fusable(C.byref(d2_)))
+                        or (self.fuse_gn_affine and h.stats[2] is None and self._resolves_to_zm(d2_)))
             h2 = Act(sc["A"], cout, cout) if fusable2 else h
             norm_conv(name + ".block2.project", h, blk.block2.groupnorm, film_off, cout, h2, blk.block2.project.weight, blk.block2.project.bias,
                       3 if blk.has_se else None)

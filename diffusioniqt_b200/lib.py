@@ -52,6 +52,7 @@ _SIGNATURES = {
     "diqt_conv_gn_fusable": [C.POINTER(ConvDesc)],
     "diqt_conv_plan_set_gn": [_vp, _vp, _i, _i64, _i, _f, _vp, _vp],
     "diqt_conv_plan_set_film": [_vp, _vp, _i, _vp, _i],
+    "diqt_conv_plan_set_gn_affine": [_vp, _vp, _vp],
     "diqt_gn_mish_g": [_vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _i, _i, _f, _vp, _vp, _vp, _i, _vp, _i, _i, _vp],
     "diqt_scale_residual_g": [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp],
     "diqt_scale_copy": [_vp, _i, _vp, _i, _i, _i64, _i, _f, _vp],

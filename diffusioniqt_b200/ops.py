@@ -72,7 +72,21 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
     L.check(lib.diqt_conv_plan_create(C.byref(desc), x.data_ptr(), out.data_ptr(), packed.data_ptr(), pbias.data_ptr(), C.byref(plan)), "conv_plan")
     stats = None
     try:
-        if gn is not None:
+        if gn is not None and gn.get("affine"):
+            # any batch / width: statistics -> diqt_gn_finalize -> (a, b) in global memory -> the conv applies mish(a * x + b)
+            nblk = gn.get("nblk", 8)
+            part = channel_stats(x, nblk)
+            vox = d0 * d1 * d2
+            ga = gn["gamma"].detach().float().contiguous().to(x.device)
+            be = gn["beta"].detach().float().contiguous().to(x.device)
+            film = gn.get("scale_shift")
+            film = film.detach().float().contiguous().to(x.device) if film is not None else None
+            aa = torch.empty(n, c_in, dtype=torch.float32, device=x.device)
+            ab = torch.empty_like(aa)
+            L.check(lib.diqt_gn_finalize(part.data_ptr(), n, nblk, vox, c_in, gn["groups"], gn.get("eps", 1e-5), ga.data_ptr(), be.data_ptr(), L.ptr(film),
+                                         2 * c_in, 0, 1, aa.data_ptr(), ab.data_ptr(), st), "gn_finalize")
+            L.check(lib.diqt_conv_plan_set_gn_affine(plan.value, aa.data_ptr(), ab.data_ptr()), "conv_plan_set_gn_affine")
+        elif gn is not None:
             if not lib.diqt_conv_gn_fusable(C.byref(desc)):
                 raise L.DiqtError("conv3d(gn=...): this shape / family cannot fuse the input GroupNorm")
             _, ggrp = channel_stats_grouped(x, gn.get("nblk", 8))

@@ -161,6 +161,9 @@ int diqt_conv_gn_fusable(const diqt_conv_desc* desc);
 int diqt_conv_plan_set_gn(diqt_conv_plan* plan, const float* group, int ngroups, int64_t voxels, int groups, float eps,
                           const float* gamma, const float* beta);
 int diqt_conv_plan_set_film(diqt_conv_plan* plan, const float* film, int film_ld, const int32_t* film_row, int film_row_stride_n);
+/* Same fusion for any batch size / any z-march width: the conv applies y = mish(a * x + b) with the per-(volume, channel) affine
+ * a, b ([n][c_in] fp32) that diqt_gn_finalize wrote in the launch before it (GroupNorm and FiLM already folded in). */
+int diqt_conv_plan_set_gn_affine(diqt_conv_plan* plan, const float* a, const float* b);
 /* y = mish(GroupNorm(groups, eps, gamma, beta)(x) [* (scale + 1) + shift]) with the statistics of x taken from `group`
  * (nn.GroupNorm :546, FiLM :559-561, nn.Mish :547); film arguments as in diqt_gn_finalize */
 int diqt_gn_mish_g(const void* x, int ld_x, void* y, int ld_y, int dtype, int n, int64_t voxels, int c, const float* group,

@@ -172,6 +172,26 @@ def test_conv_zmarch_fused_groupnorm_film_mish(n, dims, c_in, c_out, film):
     assert torch.equal(stats, stats2)
 
 
+@pytest.mark.parametrize("n,dims,c_in,c_out,film", [(4, (8, 16, 16), 64, 64, True), (3, (4, 16, 8), 320, 128, False), (5, (2, 16, 8), 128, 64, True)])
+def test_conv_zmarch_fused_affine_mish_any_batch(n, dims, c_in, c_out, film):
+    """Larger batches (BASELINE config 4) / wider layers: the statistics are finalised by diqt_gn_finalize and the conv applies the
+    per-(volume, channel) affine + Mish on its load path; same bits as the separate apply kernel."""
+    from diffusioniqt_b200 import ops
+    x = (_rand(n, c_in, *dims, seed=41) * 1.3 - 0.2).bfloat16().float()
+    w, b = _conv_weight("k3", c_in, c_out, 42)
+    gamma, beta = _rand(c_in, seed=43) * 0.2 + 1.0, _rand(c_in, seed=44) * 0.1
+    ss = _rand(n, 2 * c_in, seed=45) * 0.3 if film else None
+    y = F.group_norm(x, 8, gamma, beta, 1e-5)
+    if film:
+        y = y * (ss[:, :c_in, None, None, None] + 1) + ss[:, c_in:, None, None, None]
+    want = F.conv3d(F.mish(y), w.bfloat16().float(), b, padding=1)
+    xg = ops.to_channels_last(x.cuda(), torch.bfloat16)
+    got = ops.conv3d(xg, w, b, mode="k3", impl="zm", gn=dict(groups=8, gamma=gamma, beta=beta, scale_shift=ss, nblk=8, affine=True))
+    assert max_rel(ops.from_channels_last(got).cpu(), want) < BF16_TOL
+    a = ops.group_norm_film_mish(xg, 8, gamma, beta, ss, nblk=8, grouped=False)
+    assert torch.equal(got, ops.conv3d(a, w, b, mode="k3", impl="zm"))
+
+
 @pytest.mark.parametrize("mode,n,dims,c_in,c_out", [("k3", 1, (16, 16, 16), 64, 64), ("k3", 2, (8, 8, 8), 128, 128), ("down", 1, (16, 16, 16), 64, 128),
                                                      ("k1", 2, (8, 8, 8), 128, 256), ("k3", 1, (12, 12, 12), 64, 64)])
 def test_conv_tcgen05_fused_stats(mode, n, dims, c_in, c_out):

@@ -14,14 +14,14 @@ timeout 300 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo 
 fi
 if [ -z "${SKIP_NCU:-}" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 1200 --csv --log-file $OUT/launches_$TAG.csv \
-  python bench.py --timesteps 3 --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_launch_$TAG.log 2>&1; echo "ncu launches rc=$?"
+  python bench.py --timesteps 3 --steps 1 --warmup 1 --no-cpu-baseline --no-volume --no-torch-gpu-baseline > $OUT/ncu_launch_$TAG.log 2>&1; echo "ncu launches rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_zm_kernel -s 40 -c 3 -f -o $OUT/prof_zm_$TAG \
-  python bench.py --timesteps 2 --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_zm_$TAG.log 2>&1; echo "ncu zm rc=$?"
+  python bench.py --timesteps 2 --steps 1 --warmup 1 --no-cpu-baseline --no-volume --no-torch-gpu-baseline > $OUT/ncu_zm_$TAG.log 2>&1; echo "ncu zm rc=$?"
 ncu -i $OUT/prof_zm_$TAG.ncu-rep --page raw --csv > $OUT/prof_zm_${TAG}_raw.csv 2>/dev/null
 ncu -i $OUT/prof_zm_$TAG.ncu-rep --page source --csv --print-source sass > $OUT/prof_zm_${TAG}_source.csv 2>/dev/null
 if [ -n "${NCU_TC:-}" ]; then
 timeout 600 ncu --set full --clock-control none -k regex:"${NCU_TC}" -c ${NCU_TC_COUNT:-6} -f -o $OUT/prof_x_$TAG \
-  python bench.py --timesteps 2 --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_x_$TAG.log 2>&1; echo "ncu x rc=$?"
+  python bench.py --timesteps 2 --steps 1 --warmup 1 --no-cpu-baseline --no-volume --no-torch-gpu-baseline > $OUT/ncu_x_$TAG.log 2>&1; echo "ncu x rc=$?"
 ncu -i $OUT/prof_x_$TAG.ncu-rep --page raw --csv > $OUT/prof_x_${TAG}_raw.csv 2>/dev/null
 fi
 rm -f $OUT/*.ncu-rep

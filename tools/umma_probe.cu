@@ -154,6 +154,66 @@ __global__ void __launch_bounds__(128, 1) probe_rate(int n, int iters, int a_shi
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// ---------------------------------------------------------------- E4: does LSU traffic to shared memory slow the tensor pipe's operand fetch?
+// Thread 0 issues the E1 loop (M=128, N=n); `hammer` further warps stream ld.shared.v4 (conflict-free, 512 B per warp instruction) over a
+// separate 16 KB region until thread 0 is done.  Reports MMA cycles and the LSU bytes per cycle the hammer warps achieved.
+__global__ void __launch_bounds__(256, 1) probe_contend(int n, int iters, int hammer, int do_store, long long* cycles, unsigned long long* lsu_bytes) {
+  extern __shared__ __align__(1024) uint8_t raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* A = smem;
+  uint8_t* B = smem + 64 * 1024;
+  uint64_t* bar = (uint64_t*)(smem + 64 * 1024 + 256 * 128);
+  uint32_t* slot = (uint32_t*)(bar + 1);
+  volatile int* done = (volatile int*)(bar + 2);
+  uint8_t* H = smem + 100 * 1024;      // hammer region, 16 KB
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < (116 * 1024) / 4; i += 256) ((uint32_t*)smem)[i] = 0;
+  if (tid == 0) { mbar_init(smem_u32(bar), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); *done = 0; }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *slot;
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc(128, n);
+    const uint64_t bd = make_desc(smem_u32(B), 1024, 0);
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t aa = smem_u32(A) + (uint32_t)(it % 3) * 16384;
+      const uint64_t ad = make_desc(aa, 1024, 0);
+      const uint32_t d = tmem + (uint32_t)(((it / 27) & 1) * n);
+      for (int k = 0; k < 4; ++k) umma(d, ad + 2 * k, bd + 2 * k, idesc, 1);
+    }
+    commit(smem_u32(bar));
+    mbar_wait(smem_u32(bar), 0);
+    long long t1 = clock64();
+    cycles[blockIdx.x] = t1 - t0;
+    *done = 1;
+  } else if (warp >= 1 && warp <= hammer) {
+    unsigned long long moved = 0;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    const uint32_t base = smem_u32(H) + lane * 16;
+    while (!*done) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base + (uint32_t)((u & 15) * 512 + (warp & 1) * 8192)));
+        acc.x ^= v.x; acc.y += v.y; acc.z ^= v.z; acc.w += v.w;
+        if (do_store) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(((u + 7) & 15) * 512 + (warp & 1) * 8192)), "r"(acc.x), "r"(acc.y), "r"(acc.z), "r"(acc.w));
+      }
+      moved += 16ull * 512ull * (do_store ? 2 : 1);
+    }
+    if (lane == 0) atomicAdd(&lsu_bytes[blockIdx.x], moved + (acc.x == 0x12345678u));
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
 // ---------------------------------------------------------------- E3 (cta_group::2, M=256)
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe_rate2(int n, int iters, long long* cycles) {
   extern __shared__ __align__(1024) uint8_t raw[];
@@ -252,6 +312,29 @@ int main(int argc, char** argv) {
       double macs = 256.0 * n * 16 / per_mma / 2;
       printf("E3 cta_group::2 M=256 N=%3d: %.1f cycles per K=16 MMA -> %.0f MAC/cyc/SM (%.1f%% of 4096)\n", n, per_mma, macs, macs / 40.96);
     }
+  }
+  if (which == 0 || which == 4) {
+    long long* cyc; unsigned long long* lb;
+    CK(cudaMalloc(&cyc, 148 * sizeof(long long))); CK(cudaMalloc(&lb, 148 * sizeof(unsigned long long)));
+    CK(cudaFuncSetAttribute(probe_contend, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    const int iters = 27 * 64;
+    for (int n : {128, 192, 256})
+      for (int st = 0; st < 2; ++st)
+        for (int hammer : {0, 1, 2, 4, 7}) {
+          if (st && !hammer) continue;
+          for (int rep = 0; rep < 2; ++rep) {
+            CK(cudaMemset(lb, 0, 148 * sizeof(unsigned long long)));
+            probe_contend<<<148, 256, 120 * 1024>>>(n, iters, hammer, st, cyc, lb);
+            CK(cudaDeviceSynchronize());
+          }
+          long long h[148]; unsigned long long hb[148];
+          CK(cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost)); CK(cudaMemcpy(hb, lb, sizeof(hb), cudaMemcpyDeviceToHost));
+          double avg = 0, bytes = 0; for (int i = 0; i < 148; ++i) { avg += h[i]; bytes += hb[i]; } avg /= 148; bytes /= 148;
+          double per_mma = avg / (iters * 4.0);
+          double mma_bpc = (128.0 * 32 + n * 32.0) / per_mma;
+          printf("E4 N=%3d hammer warps=%d (%s): %.1f cycles per K=16 MMA (%.1f%% of the N/2-cycle floor), operand fetch %.1f B/clk, LSU %.1f B/clk, sum %.1f B/clk\n",
+                 n, hammer, st ? "ld+st" : "ld   ", per_mma, 100.0 * (n / 2.0 > 64 ? n / 2.0 : 64.0) / per_mma, mma_bpc, bytes / avg, mma_bpc + bytes / avg);
+        }
   }
   return 0;
 }
