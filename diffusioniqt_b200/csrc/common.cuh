@@ -353,7 +353,7 @@ __device__ __forceinline__ void gn_affine_from_groups(const GnParams& gp, int nv
 //   DIQT_MISH_V2=1   kFast: x - 2x / (u^2 + 2u + 2), u = e^x: two instructions less per element and no clamp (u = inf gives 1/inf = 0,
 //                    i.e. mish = x); loses RELATIVE accuracy in the far negative tail (|mish| < 1e-4), which bf16 storage cannot see.
 #ifndef DIQT_MISH_V2
-#define DIQT_MISH_V2 0
+#define DIQT_MISH_V2 1
 #endif
 template <bool kFast>
 __device__ __forceinline__ float mish(float x) {

@@ -478,7 +478,9 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
       }
       for (int i = 0; i < niter; ++i) {
         for (int kc = 0; kc < p.KC; ++kc) {
-#pragma unroll
+          // (runtime loops, small unrolled bodies: the five roles of this kernel share the SM's instruction cache; the first version of
+          // this loop, fully unrolled over slots and rows, spent a fifth of its samples waiting for instructions)
+#pragma unroll 1
           for (int s = 0; s < 2; ++s) {
             const ZmItem& it = s ? it1 : it0;
             if (i >= it.niter) continue;
@@ -498,26 +500,30 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
               bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
             }
             const int b = s * ZM_RING + ring[s];
-            const uint32_t vm = vmask[s];
-            mbar_wait(smem_u32(&pl_full[b]), phase[s]);
+            const uint32_t vm = s ? vmask[1] : vmask[0];
+            mbar_wait(smem_u32(&pl_full[b]), s ? phase[1] : phase[0]);
             uint8_t* base = planes + (size_t)b * ZM_PLANE_STRIDE + rbase * 128 + pc * 16;
-            uint4 raw[XF_ROWS];
+#pragma unroll 1
+            for (int k0 = 0; k0 < XF_ROWS; k0 += 3) {
+              uint4 raw[3];
 #pragma unroll
-            for (int k = 0; k < XF_ROWS; ++k)
-              if ((vm >> k) & 1u) raw[k] = *reinterpret_cast<const uint4*>(base + k * 32 * 128);
+              for (int u = 0; u < 3; ++u)
+                if ((vm >> (k0 + u)) & 1u) raw[u] = *reinterpret_cast<const uint4*>(base + (k0 + u) * 32 * 128);
 #pragma unroll
-            for (int k = 0; k < XF_ROWS; ++k) {
-              if (!((vm >> k) & 1u)) continue;
-              Vec<__nv_bfloat16> r;
-              r.unpack(raw[k]);
+              for (int u = 0; u < 3; ++u) {
+                if (!((vm >> (k0 + u)) & 1u)) continue;
+                Vec<__nv_bfloat16> r;
+                r.unpack(raw[u]);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) r.v[e] = mish<true>(fmaf(av[e], r.v[e], bv[e]));
-              r.store(reinterpret_cast<__nv_bfloat16*>(base + k * 32 * 128));
+                for (int e = 0; e < 8; ++e) r.v[e] = mish<true>(fmaf(av[e], r.v[e], bv[e]));
+                r.store(reinterpret_cast<__nv_bfloat16*>(base + (k0 + u) * 32 * 128));
+              }
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&pl_ready[b]));
-            if (++ring[s] == ZM_RING) { ring[s] = 0; phase[s] ^= 1; }
+            if (s) { if (++ring[1] == ZM_RING) { ring[1] = 0; phase[1] ^= 1; } }
+            else   { if (++ring[0] == ZM_RING) { ring[0] = 0; phase[0] ^= 1; } }
           }
         }
       }

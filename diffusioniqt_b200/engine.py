@@ -229,6 +229,7 @@ class UnetEngine:
         self.grouped = self.sub_f <= 1 and n <= 2 and os.environ.get("DIQT_DISABLE_GROUPED", "0") != "1"   # variable: A/B and diagnostics
         self.grp = [torch.zeros(16 * n * cmax * 2, dtype=torch.float32, device=self.device) for _ in range(4)]
         self.tick = [torch.zeros(16 * n, dtype=torch.int32, device=self.device) for _ in range(4)]
+        self.gn_fusion_min = int(os.environ.get("DIQT_GN_FUSION_MIN", str(1 << 22)))   # voxels x input channels; variable: A/B, tests
         self.fuse_gn = self.grouped and self.dtype == "bf16" and os.environ.get("DIQT_DISABLE_GN_FUSION", "0") != "1"   # variable: A/B
         # larger batches: statistics are finalised by diqt_gn_finalize into (aff_a, aff_b) and the conv applies that affine + Mish
         self.fuse_gn_affine = (not self.grouped and self.sub_f <= 1 and self.dtype == "bf16" and os.environ.get("DIQT_DISABLE_GN_FUSION", "0") != "1")
@@ -342,14 +343,22 @@ class UnetEngine:
                 self._pp ^= 1
             film_off = film_slot(blk)
 
+            def worth_fusing(ci):
+                # measured (profiles/conv_gn_r2c.jsonl): the fused conv beats apply + conv from 32^3 x 128 channels up (64^3 x 64: 52.7 vs
+                # 62.7 us); on smaller tensors the normalisation latency in front of the first MMA of every short z-segment costs more than
+                # the 5-8 us apply kernel it replaces
+                return self.n * vox * ci >= self.gn_fusion_min
+
             def norm_conv(cname, src: Act, gmod, f_off, ci, dst: Act, weight, bias, si):
                 """mish(FiLM(GroupNorm(src))) -> 3x3x3 conv -> dst; the normalisation rides on the conv's load path when the plan can."""
                 desc = self._conv_desc(L.CONV_K3, level, ci, src.ld, cout, dst.ld)
-                if self.fuse_gn and src.stats[2] is not None and lib.diqt_conv_gn_fusable(C.byref(desc)):
+                if not worth_fusing(ci):
+                    pass
+                elif self.fuse_gn and src.stats[2] is not None and lib.diqt_conv_gn_fusable(C.byref(desc)):
                     ops.append(self._conv_site(cname, L.CONV_K3, level, ci, src.ld, cout, dst.ld, weight, bias, src.ptr, dst.ptr, stats=si,
                                                gn=(src.stats, gmod, f_off)))
                     return True
-                if self.fuse_gn_affine and src.stats[2] is None and self._resolves_to_zm(desc):
+                elif self.fuse_gn_affine and src.stats[2] is None and self._resolves_to_zm(desc):
                     add_norm_act(src, level, gmod, f_off, None, cname.rsplit(".", 1)[0])       # finalize only: (a, b) -> self.aff_a / aff_b
                     ops.append(self._conv_site(cname, L.CONV_K3, level, ci, src.ld, cout, dst.ld, weight, bias, src.ptr, dst.ptr, stats=si, gn="affine"))
                     return True
@@ -362,8 +371,8 @@ class UnetEngine:
             h.stats = self._last_conv_stats or add_stats(h, level, 2)
             # conv2 cannot run in place: with the fused normalisation it reads h itself, so its output goes to the (otherwise unused) A buffer
             d2_ = self._conv_desc(L.CONV_K3, level, cout, h.ld, cout, cout)
-            fusable2 = ((self.fuse_gn and h.stats[2] is not None and lib.diqt_conv_gn_fusable(C.byref(d2_)))
-                        or (self.fuse_gn_affine and h.stats[2] is None and self._resolves_to_zm(d2_)))
+            fusable2 = worth_fusing(cout) and ((self.fuse_gn and h.stats[2] is not None and lib.diqt_conv_gn_fusable(C.byref(d2_)))
+                                               or (self.fuse_gn_affine and h.stats[2] is None and self._resolves_to_zm(d2_)))
             h2 = Act(sc["A"], cout, cout) if fusable2 else h
             norm_conv(name + ".block2.project", h, blk.block2.groupnorm, film_off, cout, h2, blk.block2.project.weight, blk.block2.project.bias,
                       3 if blk.has_se else None)

@@ -62,6 +62,7 @@ def test_fused_input_groupnorm_equals_the_two_kernel_path(monkeypatch):
     outs, launches = [], []
     for disable in ("1", "0"):
         monkeypatch.setenv("DIQT_DISABLE_GN_FUSION", disable)
+        monkeypatch.setenv("DIQT_GN_FUSION_MIN", "0")       # the engine only fuses from 32^3 x 128 channels up by default (where it pays)
         unet = _gpu_unet(case, "bf16")
         outs.append(unet(x, None, time, lowres_cond_img=lr))
         eng = next(iter(unet._engines.values()))
