@@ -35,6 +35,7 @@
 // one kernel launch per convolution (38 per U-Net forward at the driver config).  The per-channel (a, b) come from the producer's
 // grouped statistics and are finalised in this kernel's prologue exactly like affine_mish_kernel does (common.cuh), so the values
 // entering the tensor cores are bit-identical to the two-kernel path.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -73,22 +74,35 @@ struct ZmParams {
   short zs[ZM_MAX_SEG + 1];  // segment s covers output planes [zs[s], zs[s+1])
   int ipn, ipn_pad;   // work items per output-channel group (padded to even so that a slot pair shares its weights)
   int items, pairs;
-  uint32_t idesc[3];  // N = 64, 128, 192
+  uint32_t idesc[3];  // N = 64, 128, 192 (M = 128, or M = 256 for the CTA-pair kernel)
+  // k2 (CTA pair, tcgen05.mma.cta_group::2): a work item is a PAIR of x-adjacent columns (one per CTA of the pair) over one z-segment
+  int ncp, ncp_pad;   // column pairs (n * tiles_y * tiles_x / 2), padded to even so that both slots always share their z-segment
+  CUtensorMap w_map;  // the packed weights as rows of 64 channels (128 bytes), box = 32 rows, no TMA swizzle (they are pre-swizzled)
 };
 
 struct ZmItem {
   int valid, b, nh, x0, y0, z0, z1, p_lo, niter;
 };
 
-__device__ __forceinline__ ZmItem zm_item(const ZmParams& p, int item) {
+template <bool k2 = false>
+__device__ __forceinline__ ZmItem zm_item(const ZmParams& p, int item, int rank = 0) {
   ZmItem it;
   it.nh = item / p.ipn_pad;
   const int r = item - it.nh * p.ipn_pad;
-  it.valid = item < p.items && r < p.ipn;
+  int seg, t;
+  if (k2) {  // column pair fastest: the two slots of a CTA pair (items 2q, 2q + 1) always share their z-segment
+    seg = r / p.ncp_pad;
+    t = r - seg * p.ncp_pad;
+    it.valid = item < p.items && t < p.ncp;
+  } else {
+    seg = r % p.nseg;
+    t = r / p.nseg;
+    it.valid = item < p.items && r < p.ipn;
+  }
   if (!it.valid) { it.b = it.x0 = it.y0 = it.z0 = it.z1 = it.p_lo = 0; it.niter = 0; return it; }
-  const int seg = r % p.nseg;
-  int t = r / p.nseg;
-  const int tx = t % p.tiles_x; t /= p.tiles_x;
+  const int ntx = k2 ? p.tiles_x / 2 : p.tiles_x;
+  int tx = t % ntx; t /= ntx;
+  if (k2) tx = 2 * tx + rank;
   const int ty = t % p.tiles_y;
   it.b = t / p.tiles_y;
   it.x0 = tx * ZM_TX; it.y0 = ty * ZM_TY;
@@ -104,7 +118,78 @@ __device__ __forceinline__ void zm_jrange(int pl, int z0, int z1, int& jlo, int&
   jhi = min(2, (z1 - 1) - (pl - 1));
 }
 
-template <bool kGN>
+// ---- CTA-pair helpers (k2) --------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope: the arrivals come from the peer CTA too
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      ".reg .b16 m;\n\t"
+      "mov.b16 m, 3;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t"
+      "}" ::"r"(bar)
+      : "memory");
+}
+// TMA loads of the pair: data lands in THIS CTA's shared memory, the bytes are counted on a barrier of the leader CTA
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// k2: two CTAs on the SMs of one TPC run ONE tcgen05.mma.cta_group::2 per step (M = 256: 128 voxel rows from each CTA's own plane, N
+// split between the CTAs' weight halves).  Shared memory serves ~135 B/clk per SM and the tensor pipe's operand fetch has priority
+// (tools/umma_probe.cu E4, profiles/umma_probe_e4_r2c.log): at M = 128, N = 192 the MMAs alone fetch 107 B/clk, leaving a quarter of
+// what the plane / weight TMA writes, the plane transform and the epilogue need at full tensor rate -- the single-CTA kernel is bound by
+// shared-memory bandwidth at ~70-80 % tensor utilisation.  In the pair each CTA fetches its 128 A rows but only HALF of B (73 B/clk) and
+// lands half of every weight stage.  Barriers that gate the single issuing CTA (weights landed, planes ready, accumulators drained) live
+// in the LEADER (cluster rank 0) and are signalled from both CTAs; barriers that gate per-CTA roles (stage / plane / accumulator
+// consumed by the MMAs) exist in both CTAs and are signalled by the leader's multicast tcgen05.commit.
+template <bool kGN, bool k2>
 __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_kernel(const __grid_constant__ ZmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -125,6 +210,10 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
   float* aff = reinterpret_cast<float*>(bars + 64);  // kGN: a[n][c_in] then b[n][c_in], n <= ZM_GN_MAX_N, c_in <= ZM_GN_MAX_CIN
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = k2 ? (int)cluster_ctarank() : 0;                      // leader = 0
+  const int unit0 = k2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // work units (slot pairs) are dealt to CTAs / CTA pairs round robin
+  const int unit_stride = k2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto to_leader = [&](uint64_t* bar) -> uint32_t { return k2 ? map_to_cta(smem_u32(bar), 0) : smem_u32(bar); };
   // Warp roles.  The SM's warp scheduler prefers the HIGHEST warp id among the eligible warps of a sub-partition (measured,
   // B300_MICROARCH "arbiter priority"), so the latency-critical single-thread roles get the highest ids: the two MMA issuers, then the
   // two TMA producers, then the epilogue (its four warps must cover the four TMEM lane quarters: warp & 3), and the throughput-bound
@@ -135,17 +224,27 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
 
   for (int i = threadIdx.x; i < p.c_out; i += blockDim.x) s_bias[i] = p.bias[i];
   if (warp == W_PLANE && lane == 0) {
-    for (int i = 0; i < 2 * ZM_RING; ++i) { mbar_init(smem_u32(&pl_full[i]), 1); mbar_init(smem_u32(&pl_empty[i]), 1); mbar_init(smem_u32(&pl_ready[i]), 8); }
+    for (int i = 0; i < 2 * ZM_RING; ++i) {
+      mbar_init(smem_u32(&pl_full[i]), 1);
+      mbar_init(smem_u32(&pl_empty[i]), 1);
+      mbar_init(smem_u32(&pl_ready[i]), k2 ? 16 : 8);   // one arrival per transform warp (of both CTAs)
+    }
     for (int i = 0; i < ZM_WSTAGES; ++i) { mbar_init(smem_u32(&w_full[i]), 1); mbar_init(smem_u32(&w_empty[i]), 2); }
-    for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_free[i]), 4); }
+    for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&acc_full[i]), 1); mbar_init(smem_u32(&acc_free[i]), k2 ? 8 : 4); }   // one per epilogue warp
     fence_barrier_init();
   }
+  if (k2) cluster_sync_all();  // both CTAs' barriers exist before anyone signals across the pair
   if (warp == W_ISSUE) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (k2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (k2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp >= W_EPI && warp < W_EPI + 4) {  // all accumulator blocks start at zero: every MMA accumulates
@@ -154,7 +253,7 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
     tmem_st_wait();
   }
   tc_fence_before();
-  __syncthreads();
+  if (k2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
 #if !DIQT_PDL_LATE_TRIGGER
   pdl_launch_dependents();
@@ -173,8 +272,8 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
 #endif
       int ring[2] = {0, 0};
       uint32_t phase[2] = {0, 0};
-      for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
-        const ZmItem it0 = zm_item(p, 2 * pair), it1 = zm_item(p, 2 * pair + 1);
+      for (int pair = unit0; pair < p.pairs; pair += unit_stride) {
+        const ZmItem it0 = zm_item<k2>(p, 2 * pair, rank), it1 = zm_item<k2>(p, 2 * pair + 1, rank);
         const int niter = max(it0.niter, it1.niter);
         for (int i = 0; i < niter; ++i) {
           // chunk-major, slot-minor: both issuers consume the weight stages of chunk kc in lockstep, so the producer must never
@@ -186,9 +285,17 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
               if (i >= it.niter) continue;
               const int b = s * ZM_RING + ring[s];
               mbar_wait(smem_u32(&pl_empty[b]), phase[s] ^ 1);
-              const uint32_t bar = smem_u32(&pl_full[b]);
-              mbar_expect_tx(bar, ZM_PLANE_BYTES);
-              tma_load_5d(smem_u32(planes + (size_t)b * ZM_PLANE_STRIDE), &p.in_map, bar, kc * 64, it.x0 - 1, it.y0 - 1, it.p_lo + i, it.b);
+              if (k2 && !kGN) {
+                // the issuer (leader CTA) waits for BOTH CTAs' planes on its own barrier; with kGN the transform warps of each CTA wait
+                // on their local barrier instead and report to the leader's pl_ready
+                if (rank == 0) mbar_expect_tx(smem_u32(&pl_full[b]), 2 * ZM_PLANE_BYTES);
+                tma_load_5d_pair(smem_u32(planes + (size_t)b * ZM_PLANE_STRIDE), &p.in_map, to_leader(&pl_full[b]), kc * 64, it.x0 - 1, it.y0 - 1,
+                                 it.p_lo + i, it.b);
+              } else {
+                const uint32_t bar = smem_u32(&pl_full[b]);
+                mbar_expect_tx(bar, ZM_PLANE_BYTES);
+                tma_load_5d(smem_u32(planes + (size_t)b * ZM_PLANE_STRIDE), &p.in_map, bar, kc * 64, it.x0 - 1, it.y0 - 1, it.p_lo + i, it.b);
+              }
               if (++ring[s] == ZM_RING) { ring[s] = 0; phase[s] ^= 1; }
             }
           }
@@ -200,8 +307,8 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
-        const ZmItem it0 = zm_item(p, 2 * pair), it1 = zm_item(p, 2 * pair + 1);
+      for (int pair = unit0; pair < p.pairs; pair += unit_stride) {
+        const ZmItem it0 = zm_item<k2>(p, 2 * pair, rank), it1 = zm_item<k2>(p, 2 * pair + 1, rank);
         const int niter = max(it0.niter, it1.niter);
         const uint8_t* wnh = p.w + (size_t)it0.nh * p.KC * 27 * ZM_WBLOCK;
         for (int i = 0; i < niter; ++i) {
@@ -215,11 +322,32 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
             jlo = min(jlo, a); jhi = max(jhi, b);
           }
           const uint32_t bytes = (uint32_t)(jhi - jlo + 1) * ZM_WBLOCK;
+          // k2: an MMA over weight rows [a, a + N) takes rows [a, a + N/2) from the leader's shared memory and rows [a + N/2, a + N) from
+          // the peer's, both AT THE POSITION of row a (one descriptor serves both CTAs).  So each CTA lands its half of every run at the
+          // run's natural position: two runs at most (the accumulator window may wrap around the 4-block TMEM ring, see the issuer).
+          int ra[2] = {0, 0}, rn[2] = {0, 0};
+          if (k2) {
+            const int nb = jhi - jlo + 1, blk = (it0.p_lo + i - 1 + jlo - it0.z0) & 3;
+            const int len0 = min(nb, 4 - blk);
+            ra[0] = jlo * 64; rn[0] = len0 * 64;
+            ra[1] = (jlo + len0) * 64; rn[1] = (nb - len0) * 64;
+          }
           for (int kk = 0; kk < 9 * p.KC; ++kk) {  // kk = kc * 9 + kb
             mbar_wait(smem_u32(&w_empty[stage]), phase ^ 1);
-            const uint32_t bar = smem_u32(&w_full[stage]);
-            mbar_expect_tx(bar, bytes);
-            bulk_load(smem_u32(wst + (size_t)stage * ZM_WSTAGE + (size_t)jlo * ZM_WBLOCK), wnh + ((size_t)kk * 3 + jlo) * ZM_WBLOCK, bytes, bar);
+            if (k2) {
+              if (rank == 0) mbar_expect_tx(smem_u32(&w_full[stage]), bytes);  // both halves count on the leader's barrier
+              const uint32_t bar = to_leader(&w_full[stage]);
+              const int row0 = ((it0.nh * p.KC * 9 + kk) * 3) * 64;            // first row of this (chunk, tap) in the packed weights
+#pragma unroll
+              for (int r = 0; r < 2; ++r)
+                for (int q = 0; q < rn[r] / 2; q += 32)
+                  tma_load_2d_pair(smem_u32(wst + (size_t)stage * ZM_WSTAGE + (size_t)(ra[r] + q) * 128), &p.w_map, bar, 0,
+                                   row0 + ra[r] + rank * (rn[r] / 2) + q);
+            } else {
+              const uint32_t bar = smem_u32(&w_full[stage]);
+              mbar_expect_tx(bar, bytes);
+              bulk_load(smem_u32(wst + (size_t)stage * ZM_WSTAGE + (size_t)jlo * ZM_WBLOCK), wnh + ((size_t)kk * 3 + jlo) * ZM_WBLOCK, bytes, bar);
+            }
             if (++stage == ZM_WSTAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -228,13 +356,16 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
   } else if (warp >= W_ISSUE) {
     // ===================== MMA issuer of slot s =====================
     const int s = warp - W_ISSUE;
+    auto mma = [](uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) { if (k2) umma_bf16_2cta(d, a, b, idesc, acc); else umma_bf16(d, a, b, idesc, acc); };
+    auto commit = [](uint32_t bar) { if (k2) umma_commit_pair(bar); else umma_commit(bar); };
+    auto mbar_wait_any = [](uint32_t bar, uint32_t parity) { if (k2) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity); };
     int stage = 0;
     uint32_t wphase = 0;
     int ring = 0;
     uint32_t rphase = 0;
     int kcount = 0;  // plane iterations issued so far for this slot (pairs up with the epilogue's counter)
-    for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
-      const ZmItem it = zm_item(p, 2 * pair + s), ot = zm_item(p, 2 * pair + 1 - s);
+    for (int pair = unit0; pair < p.pairs && rank == 0; pair += unit_stride) {  // k2: only the leader CTA issues (for both)
+      const ZmItem it = zm_item<k2>(p, 2 * pair + s, 0), ot = zm_item<k2>(p, 2 * pair + 1 - s, 0);
       const int niter = max(it.niter, ot.niter);
       for (int i = 0; i < niter; ++i) {
         const bool act = i < it.niter;
@@ -257,18 +388,18 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
           const int k = kcount;
           // the block written for the first time in this iteration was drained two iterations ago; a new item needs
           // every block of the slot drained
-          if (k >= 2) mbar_wait(smem_u32(&acc_free[s * 2 + (k & 1)]), (uint32_t)(((k - 2) >> 1) & 1));
-          if (i == 0 && k >= 1) mbar_wait(smem_u32(&acc_free[s * 2 + ((k - 1) & 1)]), (uint32_t)(((k - 1) >> 1) & 1));
+          if (k >= 2) mbar_wait_any(smem_u32(&acc_free[s * 2 + (k & 1)]), (uint32_t)(((k - 2) >> 1) & 1));
+          if (i == 0 && k >= 1) mbar_wait_any(smem_u32(&acc_free[s * 2 + ((k - 1) & 1)]), (uint32_t)(((k - 1) >> 1) & 1));
         }
         for (int kc = 0; kc < p.KC; ++kc) {
           uint32_t a_base = 0;
           if (act) {
-            mbar_wait(smem_u32(kGN ? &pl_ready[s * ZM_RING + ring] : &pl_full[s * ZM_RING + ring]), rphase);
+            mbar_wait_any(smem_u32(kGN ? &pl_ready[s * ZM_RING + ring] : &pl_full[s * ZM_RING + ring]), rphase);
             a_base = smem_u32(planes + (size_t)(s * ZM_RING + ring) * ZM_PLANE_STRIDE);
           }
           tc_fence_after();
           for (int kb = 0; kb < 9; ++kb) {
-            mbar_wait(smem_u32(&w_full[stage]), wphase);
+            mbar_wait_any(smem_u32(&w_full[stage]), wphase);
             tc_fence_after();
             if (act) {  // warp-uniform issue code; the single issuing lane is elected inside umma_bf16 / umma_commit
               const uint32_t w_addr = smem_u32(wst + (size_t)stage * ZM_WSTAGE);
@@ -276,28 +407,31 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
               {
                 const uint64_t bdesc = make_sw128_desc(w_addr + b_off0);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(d0, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc0, 1u);
+                for (int k = 0; k < 4; ++k) mma(d0, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc0, 1u);
               }
               if (run1) {
                 const uint64_t bdesc = make_sw128_desc(w_addr + b_off1);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(d1, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, 1u);
+                for (int k = 0; k < 4; ++k) mma(d1, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc1, 1u);
               }
-              umma_commit(smem_u32(&w_empty[stage]));
+              commit(smem_u32(&w_empty[stage]));
             } else {
-              // idle slot (odd item count / shorter z-segment): stay in lockstep with the weight ring
-              if (lane == 0) mbar_arrive(smem_u32(&w_empty[stage]));
+              // idle slot (odd item count / shorter z-segment): stay in lockstep with the weight ring (of both CTAs)
+              if (lane == 0) {
+                mbar_arrive(smem_u32(&w_empty[stage]));
+                if (k2) mbar_arrive_cluster(map_to_cta(smem_u32(&w_empty[stage]), 1));
+              }
               __syncwarp();
             }
             if (++stage == ZM_WSTAGES) { stage = 0; wphase ^= 1; }
           }
           if (act) {
-            umma_commit(smem_u32(&pl_empty[s * ZM_RING + ring]));
+            commit(smem_u32(&pl_empty[s * ZM_RING + ring]));
             if (++ring == ZM_RING) { ring = 0; rphase ^= 1; }
           }
         }
         if (act) {
-          umma_commit(smem_u32(&acc_full[s * 2 + (kcount & 1)]));
+          commit(smem_u32(&acc_full[s * 2 + (kcount & 1)]));
           ++kcount;
         }
       }
@@ -344,8 +478,8 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
       asm volatile("bar.sync 1, 128;" ::: "memory");
     };
 
-    for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
-      const ZmItem it0 = zm_item(p, 2 * pair), it1 = zm_item(p, 2 * pair + 1);
+    for (int pair = unit0; pair < p.pairs; pair += unit_stride) {
+      const ZmItem it0 = zm_item<k2>(p, 2 * pair, rank), it1 = zm_item<k2>(p, 2 * pair + 1, rank);
       const int niter = max(it0.niter, it1.niter);
       if (p.stats) {
 #pragma unroll
@@ -415,7 +549,10 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&acc_free[s * 2 + (k & 1)]));
+          if (lane == 0) {
+            if (k2) mbar_arrive_cluster(to_leader(&acc_free[s * 2 + (k & 1)]));
+            else mbar_arrive(smem_u32(&acc_free[s * 2 + (k & 1)]));
+          }
           ++kcount[s];
         }
       }
@@ -461,8 +598,8 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
     constexpr int XF_ROWS = (ZM_PLANE_ROWS + 31) / 32;  // 6 row groups of 32
     int ring[2] = {0, 0};
     uint32_t phase[2] = {0, 0};
-    for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
-      const ZmItem it0 = zm_item(p, 2 * pair), it1 = zm_item(p, 2 * pair + 1);
+    for (int pair = unit0; pair < p.pairs; pair += unit_stride) {
+      const ZmItem it0 = zm_item<k2>(p, 2 * pair, rank), it1 = zm_item<k2>(p, 2 * pair + 1, rank);
       const int niter = max(it0.niter, it1.niter);
       uint32_t vmask[2] = {0, 0};  // rows of this thread that lie inside the volume (the others are the zero padding: left untouched)
 #pragma unroll
@@ -521,7 +658,10 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&pl_ready[b]));
+            if (lane == 0) {
+              if (k2) mbar_arrive_cluster(to_leader(&pl_ready[b]));
+              else mbar_arrive(smem_u32(&pl_ready[b]));
+            }
             if (s) { if (++ring[1] == ZM_RING) { ring[1] = 0; phase[1] ^= 1; } }
             else   { if (++ring[0] == ZM_RING) { ring[0] = 0; phase[0] ^= 1; } }
           }
@@ -531,10 +671,11 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (k2) cluster_sync_all(); else __syncthreads();  // k2: neither CTA may leave while the other can still signal its barriers
   if (warp == W_ISSUE) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (k2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -556,7 +697,20 @@ struct ZmPlan {
   ZmParams p;
   int grid;
   size_t smem;
+  bool pair;   // CTA-pair kernel (k2)
 };
+
+// The z-march kernel as a CTA pair: needs an even number of x tiles (the two CTAs of a pair take x-adjacent columns) and at least two
+// column pairs per launch so that both slots of the pair have work.  DIQT_ZM_2CTA=0 switches it off (A/B measurements).
+static bool zm_use_pair(const diqt_conv_desc* d) {
+  static int env = -1;
+  if (env < 0) {
+    const char* e = getenv("DIQT_ZM_2CTA");
+    env = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int tiles_x = d->d2 / ZM_TX, tiles_y = d->d1 / ZM_TY;
+  return env == 1 && !(d->flags & DIQT_CONV_FLAG_NO_CTA_PAIR) && tiles_x % 2 == 0 && (int64_t)d->n * tiles_y * (tiles_x / 2) >= 2;
+}
 
 bool conv_zm_supported(const diqt_conv_desc* d) {
   if (d->mode != DIQT_CONV_K3 || d->dtype != DIQT_BF16) return false;
@@ -609,7 +763,13 @@ int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
   // segments (fewer halo planes streamed from L2).  Segments are balanced by COST, not length: an interior segment of n planes
   // reads n + 2 input planes, the two at the ends of the volume n + 1, so the end segments get one more output plane
   // (64 planes in 9 segments = 8,7,7,7,7,7,7,7,7: nine input planes each, 144 CTAs, instead of 8 x 8: ten input planes, 128 CTAs).
-  const int64_t cols = (int64_t)d->n * p.tiles_x * p.tiles_y;
+  plan->pair = zm_use_pair(d);
+  const bool k2 = plan->pair;
+  // units of the column dimension: columns, or x-adjacent column pairs (padded to even) for the CTA-pair kernel
+  p.ncp = (int)((int64_t)d->n * p.tiles_y * (p.tiles_x / 2));
+  p.ncp_pad = p.ncp + (p.ncp & 1);
+  const int64_t cols = k2 ? p.ncp_pad : (int64_t)d->n * p.tiles_x * p.tiles_y;
+  const int workers = k2 ? sms / 2 : sms;   // CTAs or CTA pairs
   const int D = d->d0;
   auto split = [&](int nseg, short* zs) {
     // lengths: T - 1 at both ends, T - 2 inside, with T the smallest per-segment plane budget that covers D; surplus removed from the back
@@ -635,7 +795,7 @@ int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
     if (zs[nseg] != D) continue;
     const int64_t ipn = cols * nseg, ipn_pad = ipn + (ipn & 1);
     const int64_t pairs = (int64_t)p.NH * ipn_pad / 2;
-    const int64_t rounds = (pairs + sms - 1) / sms;
+    const int64_t rounds = (pairs + workers - 1) / workers;
     int worst = 0;
     for (int sgi = 0; sgi < nseg; ++sgi) worst = std::max(worst, zm_segment_cycles(zs[sgi], zs[sgi + 1], D));
     const double cost = (double)rounds * (2.0 * worst * 36.0 * p.KC + 6000.0);
@@ -647,7 +807,7 @@ int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
   p.ipn_pad = p.ipn + (p.ipn & 1);
   p.items = p.NH * p.ipn_pad;
   p.pairs = p.items / 2;
-  for (int i = 0; i < 3; ++i) p.idesc[i] = make_idesc_bf16(128, 64 * (i + 1));
+  for (int i = 0; i < 3; ++i) p.idesc[i] = make_idesc_bf16(k2 ? 256 : 128, 64 * (i + 1));
   const int64_t ld = d->ld_in, lo = d->ld_out;
   int rc = encode_volume_map(&p.in_map, in, d->c_in, d->d2, d->d1, d->d0, d->n, ld, (int64_t)d->d2 * ld, (int64_t)d->d1 * d->d2 * ld,
                              (int64_t)d->d0 * d->d1 * d->d2 * ld, ZM_TX + 2, ZM_TY + 2, 1, 1);
@@ -658,24 +818,68 @@ int conv_zm_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
     delete plan;
     return rc;
   }
-  plan->grid = p.pairs < sms ? p.pairs : sms;
+  if (k2 && rc == DIQT_OK) {
+    // packed weights as a 2-D tensor of 128-byte rows; 32-row boxes; the rows are already XOR-swizzled in global memory
+    const cuuint64_t gdim[2] = {64, (cuuint64_t)27 * d->c_in * d->c_out / 64};
+    const cuuint64_t gstr[1] = {128};
+    const cuuint32_t box[2] = {64, 32}, estr[2] = {1, 1};
+    const CUresult cr = get_encode_tiled()(&p.w_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(packed), gdim, gstr, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("conv(zm): cuTensorMapEncodeTiled(weights) failed (%d)", (int)cr);
+      rc = DIQT_ECUDA;
+    }
+  }
+  if (rc != DIQT_OK) {
+    delete plan;
+    return rc;
+  }
+  plan->grid = k2 ? 2 * (p.pairs < workers ? p.pairs : workers) : (p.pairs < sms ? p.pairs : sms);
   plan->smem = (size_t)2 * ZM_RING * ZM_PLANE_STRIDE + (size_t)ZM_WSTAGES * ZM_WSTAGE + ZM_OUT_BYTES + ZM_MAX_COUT * 4 + 4 * 64 * 2 * 4 + 512 + 1024 +
                (size_t)2 * ZM_GN_MAX_N * ZM_GN_MAX_CIN * 4;
   static bool attr_done = false;
   if (!attr_done) {
-    DIQT_CUDA(cudaFuncSetAttribute(conv_zm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DIQT_CUDA(cudaFuncSetAttribute(conv_zm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DIQT_CUDA(cudaFuncSetAttribute(conv_zm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DIQT_CUDA(cudaFuncSetAttribute(conv_zm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DIQT_CUDA(cudaFuncSetAttribute(conv_zm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DIQT_CUDA(cudaFuncSetAttribute(conv_zm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
   *out_plan = plan;
   return DIQT_OK;
 }
 
+// PDL launch of a kernel whose CTAs come in pairs (thread-block cluster of two: the unit tcgen05.mma.cta_group::2 works on)
+template <typename K>
+static void launch_pair(K kernel, int grid, int threads, size_t smem, cudaStream_t st, const ZmParams& p) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, p);  // errors surface in check_launch()
+}
+
 int conv_zm_run(const ZmPlan* plan, cudaStream_t st) {
-  if (plan->p.gn.group || plan->p.aff_a)
-    launch_pdl(conv_zm_kernel<true>, plan->grid, ZM_THREADS_GN, plan->smem, st, plan->p);
-  else
-    launch_pdl(conv_zm_kernel<false>, plan->grid, ZM_THREADS, plan->smem, st, plan->p);
+  const bool gn = plan->p.gn.group || plan->p.aff_a;
+  if (plan->pair) {
+    if (gn) launch_pair(conv_zm_kernel<true, true>, plan->grid, ZM_THREADS_GN, plan->smem, st, plan->p);
+    else launch_pair(conv_zm_kernel<false, true>, plan->grid, ZM_THREADS, plan->smem, st, plan->p);
+  } else if (gn) {
+    launch_pdl(conv_zm_kernel<true, false>, plan->grid, ZM_THREADS_GN, plan->smem, st, plan->p);
+  } else {
+    launch_pdl(conv_zm_kernel<false, false>, plan->grid, ZM_THREADS, plan->smem, st, plan->p);
+  }
   return check_launch("conv_zm");
 }
 

@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("DIQT_LIB_PATH") or os.path.join(_HERE, "libdiqt_b200.
 F32, BF16 = 0, 1
 CONV_K3, CONV_K1, CONV_DOWN, CONV_UP = 0, 1, 2, 3
 IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_ZM = 0, 1, 2, 3
+CONV_FLAG_NO_CTA_PAIR = 1   # include/diqt.h DIQT_CONV_FLAG_NO_CTA_PAIR
 ABI_VERSION = 1
 
 

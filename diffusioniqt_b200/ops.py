@@ -35,10 +35,11 @@ def from_channels_last(x: torch.Tensor) -> torch.Tensor:
 
 
 def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], mode: str = "k3", impl: str = "auto", with_stats: bool = False,
-           grouped: bool = False, gn: Optional[dict] = None):
+           grouped: bool = False, gn: Optional[dict] = None, pair: bool = True):
     """x: (n, d0, d1, d2, c_in) bf16/fp32 on CUDA; weight/bias exactly as in the reference state_dict (fp32).
     gn = dict(groups, gamma, beta, scale_shift=None, eps=1e-5, nblk=8): the conv computes conv(mish(FiLM(GroupNorm(x)))) with the
     normalisation fused into its load path (z-march family only; raises if the plan cannot).
+    pair=False keeps the z-march kernel on single CTAs where it would otherwise run as CTA pairs (tcgen05.mma.cta_group::2).
     with_stats=True also returns the fused per-block channel statistics (n, nblk, c_out, 2) or None if the kernel cannot fuse them;
     with grouped=True the statistics are (partial rows, group sums (n, ngroups, c_out, 2)) through the grouped sink."""
     lib = L.load()
@@ -56,7 +57,7 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
         out = torch.empty(n, d0, d1, d2, c_out, dtype=x.dtype, device=x.device)
         ld_out = c_out
     desc = L.ConvDesc(mode=_MODES[mode], dtype=_dt(x), impl=_IMPLS[impl], n=n, d0=d0, d1=d1, d2=d2, c_in=c_in, ld_in=c_in,
-                      c_out=c_out, ld_out=ld_out, flags=0)
+                      c_out=c_out, ld_out=ld_out, flags=0 if pair else L.CONV_FLAG_NO_CTA_PAIR)
     nbytes = C.c_size_t(0)
     L.check(lib.diqt_conv_packed_bytes(C.byref(desc), C.byref(nbytes)), "conv_packed_bytes")
     packed = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)

@@ -71,6 +71,9 @@ uint64_t diqt_launch_count(void);
  * Weights are repacked once by diqt_conv_pack_weights from the reference's
  * (C_out, C_in, k, k, k) fp32 tensor into the layout the chosen kernel family wants.
  * ------------------------------------------------------------------------------------------ */
+/* keep the z-march conv on single CTAs even where the CTA-pair kernel (tcgen05.mma.cta_group::2) applies: parity tests, A/B */
+#define DIQT_CONV_FLAG_NO_CTA_PAIR 1
+
 typedef struct diqt_conv_desc {
   int32_t mode;          /* DIQT_CONV_*                                                     */
   int32_t dtype;         /* DIQT_F32 / DIQT_BF16 (activations in and out)                   */
@@ -79,7 +82,7 @@ typedef struct diqt_conv_desc {
   int32_t d0, d1, d2;    /* INPUT spatial dims                                              */
   int32_t c_in, ld_in;   /* input channels / row pitch                                      */
   int32_t c_out, ld_out; /* GEMM N (for DIQT_CONV_UP: 8x the channels stored) / out pitch   */
-  int32_t flags;         /* reserved, 0                                                     */
+  int32_t flags;         /* DIQT_CONV_FLAG_* (0 = defaults)                                 */
 } diqt_conv_desc;
 
 /* which kernel family DIQT_IMPL_AUTO resolves to for this shape (DIQT_IMPL_SIMT or DIQT_IMPL_TC) */

@@ -137,6 +137,42 @@ def test_conv_zmarch_bf16(n, dims, c_in, c_out):
     assert max_rel(s[..., 1], (stored ** 2).sum(dim=(2, 3, 4))) < 2e-4
 
 
+PAIR_SHAPES = [
+    # n, dims, c_in, c_out: shapes the z-march kernel runs as CTA pairs (even number of 8-wide x tiles, >= 2 column pairs)
+    (2, (8, 32, 16), 64, 64),
+    (1, (32, 32, 32), 64, 64),
+    (1, (32, 32, 32), 192, 128),
+    (1, (5, 16, 48), 64, 128),      # three column pairs: the second slot of the last pair idles; odd depth
+    (3, (4, 32, 16), 128, 64),      # several volumes, two K chunks
+    (1, (64, 64, 64), 64, 64),      # BASELINE config 2 shape
+]
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("n,dims,c_in,c_out", PAIR_SHAPES)
+def test_conv_zmarch_cta_pair_equals_single_cta(n, dims, c_in, c_out, fused):
+    """tcgen05.mma.cta_group::2 version of the z-march kernel (two CTAs share every weight stage, M = 256 per MMA) against the single-CTA
+    version: same products, same accumulation order per output element -> the same bits, statistics included; and against fp32 PyTorch."""
+    from diffusioniqt_b200 import ops
+    x = (_rand(n, c_in, *dims, seed=51) * 1.2 + 0.1).bfloat16().float()
+    w, b = _conv_weight("k3", c_in, c_out, 52)
+    gamma, beta = _rand(c_in, seed=53) * 0.2 + 1.0, _rand(c_in, seed=54) * 0.1
+    ss = _rand(n, 2 * c_in, seed=55) * 0.3
+    gn = dict(groups=8, gamma=gamma, beta=beta, scale_shift=ss, nblk=16, affine=n > 2) if fused else None
+    xg = ops.to_channels_last(x.cuda(), torch.bfloat16)
+    one, st1 = ops.conv3d(xg, w, b, mode="k3", impl="zm", with_stats=True, gn=gn, pair=False)
+    two, st2 = ops.conv3d(xg, w, b, mode="k3", impl="zm", with_stats=True, gn=gn, pair=True)
+    assert torch.equal(one, two)
+    # the statistics rows are laid out per CTA slot; their totals must agree exactly up to fp32 summation order
+    assert max_rel(st2.sum(dim=1), st1.sum(dim=1)) < 1e-5
+    y = x
+    if fused:
+        y = F.group_norm(x, 8, gamma, beta, 1e-5) * (ss[:, :c_in, None, None, None] + 1) + ss[:, c_in:, None, None, None]
+        y = F.mish(y)
+    want = F.conv3d(y, w.bfloat16().float(), b, padding=1)
+    assert max_rel(ops.from_channels_last(two).cpu(), want) < BF16_TOL
+
+
 GN_FUSED_SHAPES = [
     # n, dims, c_in, c_out, film
     (1, (16, 16, 16), 64, 64, True),
