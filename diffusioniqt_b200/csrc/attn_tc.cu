@@ -11,6 +11,7 @@
 // Operands are all K-major SWIZZLE_128B tiles written by TMA: Q and K straight from the [tokens][channels] q | k | v buffer, V from a
 // transposed copy V^T [channels][tokens] (written by attn_transpose_kernel; its padding columns must be zero).
 // Warp roles (192 threads): 0 TMA producer, 1 MMA issuer (owns TMEM), 2-5 softmax / epilogue (one query row per thread).
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -260,6 +261,247 @@ __global__ void __launch_bounds__(AT_THREADS, 2) softmax_attn_tc_kernel(const __
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Version 2: ONE pass over the keys (online softmax), NQ query tiles of 128 rows per CTA in ping-pong, probabilities handed to the
+// tensor core through TENSOR MEMORY (tcgen05.mma with the A operand in TMEM), never through shared memory.
+//
+// Why (profiles/r1s_ncu_softmax_attn_tc.csv, profiles/sweep_r2a.jsonl): the two-pass kernel above ran the chain Q K^T -> tcgen05.ld ->
+// exp -> st.shared -> P V serially per CTA (tensor pipe 14 % active) and computed Q K^T twice; cuDNN's fused attention on the same GPU
+// was 1.9x (1728 tokens) and 2.7x (13 824 tokens) faster.  Per (query tile, key tile) the tensor pipe needs 256 (Q K^T, N = 128) + 512
+// (P V: N = 64 runs at the 64-cycle-per-instruction floor) cycles, the 128 x 128 exponentials need 1024 MUFU cycles: the kernel is bound
+// by the SFU, so everything else has to overlap with it:
+//   * two query tiles per CTA, each with its own softmax warpgroup (thread = one query row, no shuffles), S / P / O of both in TMEM
+//     (2 x 128 + 2 x 64 + 2 x 64 = 512 columns): while one warpgroup exponentiates, the tensor pipe fills the other's S;
+//   * the issuer queues Q_i K_{j+1}^T as soon as warpgroup i has READ S_i(j) into registers (s_free), then P_i(j) V_j when P_i(j) exists;
+//   * online softmax with LAZY rescaling: the running reference maximum only moves when a row's new maximum exceeds it by more than
+//     2^8 (probabilities up to 256 are harmless in bf16 / fp32), so O is rescaled in TMEM (tcgen05.ld / st by the warpgroup that owns
+//     the rows) a handful of times per row instead of once per key tile; the final O / l is exact either way.
+// Warp roles (128 NQ + 64 threads): warps 0 .. 4 NQ - 1 softmax / epilogue, then the TMA producer, then the MMA issuer (TMEM owner);
+// the single-thread roles have the highest warp ids (scheduler priority, see conv_zm.cu).
+constexpr int AT2_KSTAGES = 3, AT2_VSTAGES = 2;
+constexpr float AT2_TAU = 8.f;  // log2 units
+
+template <int NQ>
+__global__ void __launch_bounds__(128 * NQ + 64, 1) softmax_attn_tc2_kernel(const __grid_constant__ AttnTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_s = smem;                                   // NQ x 16 KB
+  uint8_t* k_s = q_s + NQ * AT_TILE;                     // AT2_KSTAGES x 16 KB
+  uint8_t* v_s = k_s + AT2_KSTAGES * AT_TILE;            // AT2_VSTAGES x (2 key chunks x 8 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_s + AT2_VSTAGES * 2 * AT_VCHUNK);
+  uint64_t* q_full = bars;                               // 1
+  uint64_t* k_full = q_full + 1;                         // [AT2_KSTAGES]
+  uint64_t* k_empty = k_full + AT2_KSTAGES;
+  uint64_t* v_full = k_empty + AT2_KSTAGES;              // [AT2_VSTAGES]
+  uint64_t* v_empty = v_full + AT2_VSTAGES;
+  uint64_t* s_full = v_empty + AT2_VSTAGES;              // [NQ]  Q_i K_j^T complete
+  uint64_t* s_free = s_full + 2;                         // [NQ]  S_i read into registers (4 warp arrivals)
+  uint64_t* p_full = s_free + 2;                         // [NQ]  P_i(j) stored in TMEM, O_i rescaled if needed (4 warp arrivals)
+  uint64_t* pv_done = p_full + 2;                        // [NQ]  P_i(j) V_j complete: P_i may be overwritten, O_i is up to date
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int W_TMA = 4 * NQ, W_MMA = 4 * NQ + 1;
+  const int head = blockIdx.y;
+  const int q0 = blockIdx.x * (AT_Q * NQ);
+  const int nkt = (p.ntok + AT_K - 1) / AT_K;
+
+  if (warp == W_TMA && lane == 0) {
+    mbar_init(smem_u32(q_full), 1);
+    for (int s = 0; s < AT2_KSTAGES; ++s) { mbar_init(smem_u32(&k_full[s]), 1); mbar_init(smem_u32(&k_empty[s]), 1); }
+    for (int s = 0; s < AT2_VSTAGES; ++s) { mbar_init(smem_u32(&v_full[s]), 1); mbar_init(smem_u32(&v_empty[s]), 1); }
+    for (int i = 0; i < NQ; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&s_free[i]), 4);
+      mbar_init(smem_u32(&p_full[i]), 4);
+      mbar_init(smem_u32(&pv_done[i]), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == W_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // columns: S_i at 128 i, O_i at 256 + 64 i, P_i at 384 + 64 i
+  if (warp == W_TMA) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(smem_u32(q_full), NQ * AT_TILE);
+      for (int i = 0; i < NQ; ++i) tma_load_2d_as5(smem_u32(q_s + i * AT_TILE), &p.q_map, smem_u32(q_full), p.q_col0 + head * AT_D, q0 + i * AT_Q);
+      int ks = 0, vs = 0;
+      uint32_t kph = 0, vph = 0;
+      for (int j = 0; j < nkt; ++j) {
+        mbar_wait(smem_u32(&k_empty[ks]), kph ^ 1);
+        mbar_expect_tx(smem_u32(&k_full[ks]), AT_TILE);
+        tma_load_2d_as5(smem_u32(k_s + ks * AT_TILE), &p.k_map, smem_u32(&k_full[ks]), p.k_col0 + head * AT_D, j * AT_K);
+        if (++ks == AT2_KSTAGES) { ks = 0; kph ^= 1; }
+        mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1);
+        mbar_expect_tx(smem_u32(&v_full[vs]), 2 * AT_VCHUNK);
+        uint8_t* dst = v_s + vs * 2 * AT_VCHUNK;
+        tma_load_2d_as5(smem_u32(dst), &p.vt_map, smem_u32(&v_full[vs]), j * AT_K, head * AT_D);
+        tma_load_2d_as5(smem_u32(dst + AT_VCHUNK), &p.vt_map, smem_u32(&v_full[vs]), j * AT_K + 64, head * AT_D);
+        if (++vs == AT2_VSTAGES) { vs = 0; vph ^= 1; }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ===================== MMA issuer (warp-uniform code; the issuing lane is elected inside the wrappers) =====================
+    mbar_wait(smem_u32(q_full), 0);
+    tc_fence_after();
+    int ks = 0, vs = 0;
+    uint32_t kph = 0, vph = 0;
+    auto issue_qk = [&](int i, int kstage) {
+      const uint64_t qdesc = make_sw128_desc(smem_u32(q_s + i * AT_TILE));
+      const uint64_t kdesc = make_sw128_desc(smem_u32(k_s + kstage * AT_TILE));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem_base + (uint32_t)(i * 128), qdesc + (uint64_t)(2 * k), kdesc + (uint64_t)(2 * k), p.idesc_s, k != 0);
+      umma_commit(smem_u32(&s_full[i]));
+    };
+    // S_i(0)
+    mbar_wait(smem_u32(&k_full[0]), 0);
+    tc_fence_after();
+    for (int i = 0; i < NQ; ++i) issue_qk(i, 0);
+    umma_commit(smem_u32(&k_empty[0]));
+    ks = 1 % AT2_KSTAGES;
+    if (ks == 0) kph ^= 1;
+    for (int j = 0; j < nkt; ++j) {
+      const uint32_t ph = (uint32_t)(j & 1);
+      if (j + 1 < nkt) {  // S_i(j + 1) as soon as warpgroup i holds S_i(j) in registers
+        mbar_wait(smem_u32(&k_full[ks]), kph);
+        for (int i = 0; i < NQ; ++i) {
+          mbar_wait(smem_u32(&s_free[i]), ph);
+          tc_fence_after();
+          issue_qk(i, ks);
+        }
+        umma_commit(smem_u32(&k_empty[ks]));
+        if (++ks == AT2_KSTAGES) { ks = 0; kph ^= 1; }
+      }
+      mbar_wait(smem_u32(&v_full[vs]), vph);
+      const uint32_t vb = smem_u32(v_s + vs * 2 * AT_VCHUNK);
+      for (int i = 0; i < NQ; ++i) {
+        mbar_wait(smem_u32(&p_full[i]), ph);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // K = 16 keys per instruction: 8 TMEM columns of P, 32 bytes along the V^T rows
+          const uint64_t vdesc = make_sw128_desc(vb + (kk >> 2) * AT_VCHUNK) + (uint64_t)(2 * (kk & 3));
+          umma_bf16_ts(tmem_base + (uint32_t)(256 + i * 64), tmem_base + (uint32_t)(384 + i * 64 + kk * 8), vdesc, p.idesc_o, (j | kk) != 0);
+        }
+        umma_commit(smem_u32(&pv_done[i]));
+      }
+      umma_commit(smem_u32(&v_empty[vs]));
+      if (++vs == AT2_VSTAGES) { vs = 0; vph ^= 1; }
+    }
+  } else {
+    // ===================== softmax / epilogue: warpgroup i = query tile i, thread = one query row =====================
+    const int i = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_addr + (uint32_t)(i * 128);
+    const uint32_t t_o = tmem_base + lane_addr + (uint32_t)(256 + i * 64);
+    const uint32_t t_p = tmem_base + lane_addr + (uint32_t)(384 + i * 64);
+    float m_used = -INFINITY, l = 0.f;  // reference maximum (log2 units, already scaled) and sum of 2^(s c - m_used)
+    for (int j = 0; j < nkt; ++j) {
+      const uint32_t ph = (uint32_t)(j & 1);
+      mbar_wait(smem_u32(&s_full[i]), ph);
+      tc_fence_after();
+      uint32_t s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(t_s + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(s + 32 * c));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_free[i]));
+      const int nvalid = p.ntok - j * AT_K;  // keys of this tile that exist (the TMA zero-fills the rest)
+      float mx = -INFINITY;
+      if (nvalid >= AT_K) {
+#pragma unroll
+        for (int k = 0; k < 128; ++k) mx = fmaxf(mx, __uint_as_float(s[k]));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 128; ++k) {
+          if (k >= nvalid) s[k] = 0xff800000u;  // -inf
+          mx = fmaxf(mx, __uint_as_float(s[k]));
+        }
+      }
+      const float mnew = mx * p.c;
+      float alpha = 1.f;
+      const bool grow = mnew > m_used + AT2_TAU;  // key 0 of tile 0 always exists: the first tile always sets the reference
+      if (grow) {
+        alpha = ex2_approx(m_used - mnew);  // 0 on the first tile (m_used = -inf)
+        m_used = mnew;
+        l *= alpha;
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 64; ++k) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * k]), p.c, -m_used));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * k + 1]), p.c, -m_used));
+        sum += p0 + p1;
+        __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+        s[k] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      l += sum;
+      if (j > 0) {
+        mbar_wait(smem_u32(&pv_done[i]), ph ^ 1);  // P_i(j - 1) V_{j-1} complete: P_i free, O_i consistent
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {  // rescale this warp's 32 rows of O_i (alpha = 1 for the rows that did not move)
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(t_o + (uint32_t)(c * 32), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+            tmem_st32(t_o + (uint32_t)(c * 32), o);
+          }
+        }
+      }
+      tmem_st32(t_p, *reinterpret_cast<uint32_t(*)[32]>(s));
+      tmem_st32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(s + 32));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_full[i]));
+    }
+    // ---- epilogue: O / l -> activation -> bf16 rows
+    const float inv_l = 1.f / l;
+    mbar_wait(smem_u32(&pv_done[i]), (uint32_t)((nkt - 1) & 1));
+    tc_fence_after();
+    const int q = q0 + i * AT_Q + row;
+#pragma unroll 1
+    for (int c32 = 0; c32 < 2; ++c32) {
+      uint32_t r[32];
+      tmem_ld32(t_o + (uint32_t)(c32 * 32), r);
+      tmem_ld_wait();
+      if (q < p.ntok) {
+        uint32_t packed[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          float v0 = __uint_as_float(r[2 * k]) * inv_l, v1 = __uint_as_float(r[2 * k + 1]) * inv_l;
+          if (p.act == 1) { v0 = mish<false>(v0); v1 = mish<false>(v1); }
+          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+          packed[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)q * p.ld_out + head * AT_D + c32 * 32);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dst[u] = make_uint4(packed[4 * u], packed[4 * u + 1], packed[4 * u + 2], packed[4 * u + 3]);
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // vt[ch][tok] = v[tok][ch] for ch < channels, tok < ntok (32 x 32 tiles through shared memory)
 __global__ void __launch_bounds__(256) attn_transpose_kernel(const __nv_bfloat16* __restrict__ v, int ld, int ntok, int channels,
                                                              __nv_bfloat16* __restrict__ vt, int ldt) {
@@ -284,6 +526,7 @@ struct AttnTcPlan {
   int ld_v, npad, inner;
   dim3 grid;
   size_t smem;
+  int version, nq;   // 1: two-pass kernel; 2: single-pass kernel with nq query tiles per CTA
 };
 
 }  // namespace diqt
@@ -338,11 +581,26 @@ extern "C" int diqt_attn_tc_plan_create(const void* q, const void* k, const void
     delete pl;
     return rc;
   }
-  a.grid = dim3((tokens + AT_Q - 1) / AT_Q, heads);
-  a.smem = (size_t)AT_TILE * 6 + 256 + 1024;  // Q + 2 K + 2 V^T chunks (= 1 tile) + 2 P, barriers, alignment slack: two CTAs per SM
+  const char* ev = getenv("DIQT_ATTN_TC_VERSION");   // variable: A/B against the two-pass kernel
+  a.version = (ev && ev[0] == '1') ? 1 : 2;
+  if (a.version == 1) {
+    a.nq = 1;
+    a.grid = dim3((tokens + AT_Q - 1) / AT_Q, heads);
+    a.smem = (size_t)AT_TILE * 6 + 256 + 1024;  // Q + 2 K + 2 V^T chunks (= 1 tile) + 2 P, barriers, alignment slack: two CTAs per SM
+  } else {
+    // two query tiles per CTA (ping-pong) when that still leaves at least one CTA per SM, else one
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    a.nq = ((tokens + 2 * AT_Q - 1) / (2 * AT_Q)) * heads >= sms ? 2 : 1;
+    a.grid = dim3((tokens + a.nq * AT_Q - 1) / (a.nq * AT_Q), heads);
+    a.smem = (size_t)AT_TILE * (a.nq + AT2_KSTAGES + AT2_VSTAGES) + 256 + 1024;
+  }
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(softmax_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(softmax_attn_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(softmax_attn_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
     if (e != cudaSuccess) {
       set_error("attn_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       delete pl;
@@ -363,6 +621,8 @@ extern "C" int diqt_attn_tc_run(const diqt_attn_plan* plan, void* stream) {
   const dim3 tgrid((a.p.ntok + 31) / 32, (a.inner + 31) / 32);
   attn_transpose_kernel<<<tgrid, 256, 0, st>>>(a.v, a.ld_v, a.p.ntok, a.inner, a.vt, a.npad);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  softmax_attn_tc_kernel<<<a.grid, AT_THREADS, a.smem, st>>>(a.p);
+  if (a.version == 1) softmax_attn_tc_kernel<<<a.grid, AT_THREADS, a.smem, st>>>(a.p);
+  else if (a.nq == 2) softmax_attn_tc2_kernel<2><<<a.grid, 128 * 2 + 64, a.smem, st>>>(a.p);
+  else softmax_attn_tc2_kernel<1><<<a.grid, 128 + 64, a.smem, st>>>(a.p);
   return check_launch("softmax_attention_tc");
 }

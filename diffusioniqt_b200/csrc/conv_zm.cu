@@ -44,6 +44,12 @@
 
 namespace diqt {
 
+// DIQT_XF_MODE (build-time, timing experiments only; results are wrong unless 0): 1 = the transform warps only hand the plane on,
+// 2 = affine without Mish.  Separates the cost of the extra pipeline stage from the cost of its arithmetic (profiles/r2f_xf_modes.md).
+#ifndef DIQT_XF_MODE
+#define DIQT_XF_MODE 0
+#endif
+
 constexpr int ZM_TX = 8, ZM_TY = 16;                    // output tile of one plane: 16 (y) x 8 (x) = 128 GEMM rows
 constexpr int ZM_PLANE_BYTES = (ZM_TY + 2) * (ZM_TX + 2) * 128;  // 180 haloed rows x 64 bf16 = 23040
 constexpr int ZM_PLANE_STRIDE = 23552;                  // next multiple of 1024
@@ -125,16 +131,20 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// Remote arrive with the DEFAULT semantics (.release at CTA scope), as production 2-SM GEMMs do: what the arrival publishes is consumed
+// by tcgen05 instructions (already ordered by fence.proxy.async / tcgen05.fence in the signalling thread), not by ld/st of the peer.  The
+// first version used .release.cluster, which ptxas turns into a full ERRBAR fence per arrival: 16 % of the kernel's stall samples
+// (profiles/r2d_pair_stalls.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // acquire at cluster scope: the arrivals come from the peer CTA too
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // (arrivals come from the peer CTA too; default semantics, see above)
   uint32_t done;
   do {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
         : "=r"(done)
@@ -640,6 +650,9 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
             const uint32_t vm = s ? vmask[1] : vmask[0];
             mbar_wait(smem_u32(&pl_full[b]), s ? phase[1] : phase[0]);
             uint8_t* base = planes + (size_t)b * ZM_PLANE_STRIDE + rbase * 128 + pc * 16;
+#if DIQT_XF_MODE == 1   // timing experiment: handshake only, the plane is handed on untouched
+            if (false)
+#endif
 #pragma unroll 1
             for (int k0 = 0; k0 < XF_ROWS; k0 += 3) {
               uint4 raw[3];
@@ -651,8 +664,13 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
                 if (!((vm >> (k0 + u)) & 1u)) continue;
                 Vec<__nv_bfloat16> r;
                 r.unpack(raw[u]);
+#if DIQT_XF_MODE == 2   // timing experiment: affine only (no MUFU)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) r.v[e] = fmaf(av[e], r.v[e], bv[e]);
+#else
 #pragma unroll
                 for (int e = 0; e < 8; ++e) r.v[e] = mish<true>(fmaf(av[e], r.v[e], bv[e]));
+#endif
                 r.store(reinterpret_cast<__nv_bfloat16*>(base + (k0 + u) * 32 * 128));
               }
             }
@@ -709,7 +727,11 @@ static bool zm_use_pair(const diqt_conv_desc* d) {
     env = (e && e[0] == '0') ? 0 : 1;
   }
   const int tiles_x = d->d2 / ZM_TX, tiles_y = d->d1 / ZM_TY;
-  return env == 1 && !(d->flags & DIQT_CONV_FLAG_NO_CTA_PAIR) && tiles_x % 2 == 0 && (int64_t)d->n * tiles_y * (tiles_x / 2) >= 2;
+  // measured (profiles/sweep_conv_r2e.jsonl): the pair wins from 64^3 up (41.3 vs 42.9 us at 64 channels, 2.36 vs 2.44 ms at 512) and
+  // loses a few percent on 32^3 volumes, where its two cluster barriers and cross-CTA signalling are a larger share of a 15-30 us kernel
+  const char* mp = getenv("DIQT_ZM_2CTA_MIN_PAIRS");   // read per plan: the parity tests lower it to exercise the pair kernel on small volumes
+  const int min_pairs = mp ? atoi(mp) : 16;
+  return env == 1 && !(d->flags & DIQT_CONV_FLAG_NO_CTA_PAIR) && tiles_x % 2 == 0 && (int64_t)d->n * tiles_y * (tiles_x / 2) >= min_pairs;
 }
 
 bool conv_zm_supported(const diqt_conv_desc* d) {

@@ -150,11 +150,14 @@ def test_softmax_attention(name, dt, tol, n, heads, dh, act):
     assert max_rel(got.float().cpu(), want) < tol
 
 
-@pytest.mark.parametrize("n,heads,act", [(128, 1, 0), (100, 2, 1), (300, 3, 0), (1728, 8, 1), (520, 2, 1)])
-def test_softmax_attention_tensor_core_kernel(n, heads, act):
-    """csrc/attn_tc.cu (tcgen05 Q K^T and P V, two passes) against the fp32 PyTorch product; bf16, dim_head 64; token counts that are
-    not multiples of the 128-key tile exercise the key mask and the query-row guard."""
+@pytest.mark.parametrize("version", ["2", "1"])
+@pytest.mark.parametrize("n,heads,act", [(128, 1, 0), (100, 2, 1), (300, 3, 0), (1728, 8, 1), (520, 2, 1), (4736, 8, 0), (5000, 5, 1)])
+def test_softmax_attention_tensor_core_kernel(n, heads, act, version, monkeypatch):
+    """csrc/attn_tc.cu (tcgen05 Q K^T and P V) against the fp32 PyTorch product; bf16, dim_head 64; token counts that are not multiples
+    of the 128-key tile exercise the key mask and the query-row guard.  Version 2 = single pass, online softmax with lazy rescaling,
+    P through tensor memory (one or two query tiles per CTA: 4736 x 8 and 5000 x 5 take the two-tile path); version 1 = two passes."""
     from diffusioniqt_b200 import ops
+    monkeypatch.setenv("DIQT_ATTN_TC_VERSION", version)
     dh, dt, tol = 64, torch.bfloat16, 1e-2
     qkv = _q(_rand(n, 3 * heads * dh, seed=3), dt)
     q, k, v = (_split_heads(t, heads) for t in qkv.chunk(3, dim=1))
@@ -174,3 +177,26 @@ def test_softmax_attention_tensor_core_kernel(n, heads, act):
     want = F.mish(out) if act else out
     got = ops.softmax_attention(qkv2.to(dt).cuda(), heads, dh, act=act, impl="tc")
     assert max_rel(got.float().cpu(), want) < tol
+
+
+def test_softmax_attention_tensor_core_13824_tokens():
+    """BASELINE config 5's long sequence (192^3 / 8^3 tokens): two heads against fp32 PyTorch on the CPU, plus rows whose maximum keeps
+    growing from key tile to key tile (every lazy rescale of O in tensor memory is exercised) and rows with one dominant late key."""
+    from diffusioniqt_b200 import ops
+    n, heads, dh, dt = 13824, 2, 64, torch.bfloat16
+    qkv = _q(_rand(n, 3 * heads * dh, seed=9), dt)
+    # keys whose norm grows with their index: the running maximum of every query row rises across the 108 key tiles
+    ramp = torch.linspace(0.2, 3.0, n)[:, None]
+    qkv[:, heads * dh: 2 * heads * dh] *= ramp
+    qkv[:, : heads * dh] *= 3.0
+    qkv = _q(qkv, dt)
+    q, k, v = (_split_heads(t, heads) for t in qkv.chunk(3, dim=1))
+    want = torch.empty(heads, n, dh)
+    for h in range(heads):
+        for r0 in range(0, n, 1728):
+            att = (q[h, r0:r0 + 1728] @ k[h].t() * dh ** -0.5).softmax(dim=-1)
+            want[h, r0:r0 + 1728] = att @ v[h]
+    want = want.permute(1, 0, 2).reshape(n, heads * dh)
+    got = ops.softmax_attention(qkv.to(dt).cuda(), heads, dh, act=0, impl="tc")
+    assert torch.isfinite(got).all()
+    assert max_rel(got.float().cpu(), want) < 1e-2

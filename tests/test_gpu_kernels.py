@@ -150,7 +150,12 @@ PAIR_SHAPES = [
 
 @pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("n,dims,c_in,c_out", PAIR_SHAPES)
-def test_conv_zmarch_cta_pair_equals_single_cta(n, dims, c_in, c_out, fused):
+def test_conv_zmarch_cta_pair_equals_single_cta(n, dims, c_in, c_out, fused, monkeypatch):
+    monkeypatch.setenv("DIQT_ZM_2CTA_MIN_PAIRS", "2")     # by default only volumes from 64^3 up run as CTA pairs (where it pays)
+    _pair_vs_single(n, dims, c_in, c_out, fused)
+
+
+def _pair_vs_single(n, dims, c_in, c_out, fused):
     """tcgen05.mma.cta_group::2 version of the z-march kernel (two CTAs share every weight stage, M = 256 per MMA) against the single-CTA
     version: same products, same accumulation order per output element -> the same bits, statistics included; and against fp32 PyTorch."""
     from diffusioniqt_b200 import ops

@@ -83,26 +83,36 @@ def sweep_conv():
             # ---- ours
             xs = [torch.randn(1, S, S, S, Cc, device=dev).bfloat16() for _ in range(nb)]
             ys = [torch.empty(1, S, S, S, Cc, device=dev, dtype=torch.bfloat16) for _ in range(nb)]
-            desc = L.ConvDesc(mode=L.CONV_K3, dtype=L.BF16, impl=L.IMPL_AUTO, n=1, d0=S, d1=S, d2=S, c_in=Cc, ld_in=Cc, c_out=Cc, ld_out=Cc, flags=0)
-            impl = C.c_int(0)
-            L.check(lib.diqt_conv_resolved_impl(C.byref(desc), C.byref(impl)))
-            nbytes = C.c_size_t(0)
-            L.check(lib.diqt_conv_packed_bytes(C.byref(desc), C.byref(nbytes)))
-            packed = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
-            pb = torch.empty(Cc, dtype=torch.float32, device=dev)
+            def ours(impl_id, flags=0):
+                desc = L.ConvDesc(mode=L.CONV_K3, dtype=L.BF16, impl=impl_id, n=1, d0=S, d1=S, d2=S, c_in=Cc, ld_in=Cc, c_out=Cc, ld_out=Cc, flags=flags)
+                impl = C.c_int(0)
+                L.check(lib.diqt_conv_resolved_impl(C.byref(desc), C.byref(impl)))
+                nbytes = C.c_size_t(0)
+                L.check(lib.diqt_conv_packed_bytes(C.byref(desc), C.byref(nbytes)))
+                packed = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+                pb = torch.empty(Cc, dtype=torch.float32, device=dev)
+                L.check(lib.diqt_conv_pack(C.byref(desc), wb.data_ptr(), b.data_ptr(), packed.data_ptr(), pb.data_ptr(), L.current_stream()))
+                plans = []
+                for x, y in zip(xs, ys):
+                    p = C.c_void_p(0)
+                    L.check(lib.diqt_conv_plan_create(C.byref(desc), x.data_ptr(), y.data_ptr(), packed.data_ptr(), pb.data_ptr(), C.byref(p)))
+                    plans.append(p.value)
+                t, _ = timed([(lambda p=p: L.check(lib.diqt_conv_run(p, L.current_stream()))) for p in plans], reps)
+                torch.cuda.synchronize()
+                for p in plans:
+                    lib.diqt_conv_plan_destroy(p)
+                return t, impl.value
+
             wb = w.bfloat16().float().contiguous()
-            L.check(lib.diqt_conv_pack(C.byref(desc), wb.data_ptr(), b.data_ptr(), packed.data_ptr(), pb.data_ptr(), L.current_stream()))
-            plans = []
-            for x, y in zip(xs, ys):
-                p = C.c_void_p(0)
-                L.check(lib.diqt_conv_plan_create(C.byref(desc), x.data_ptr(), y.data_ptr(), packed.data_ptr(), pb.data_ptr(), C.byref(p)))
-                plans.append(p.value)
-            ours, _ = timed([(lambda p=p: L.check(lib.diqt_conv_run(p, L.current_stream()))) for p in plans], reps)
+            alt = {}
+            alt["conv_tc_kernel (per tap)"], _ = ours(L.IMPL_TC)
+            alt["conv_zm_kernel single CTA"], _ = ours(L.IMPL_ZM, L.CONV_FLAG_NO_CTA_PAIR)
+            ours_ms, impl_v = ours(L.IMPL_AUTO)          # last: ys[0] holds the product path's output for the cross-check below
+            impl = C.c_int(impl_v)
+            ours = ours_ms
             # numerical cross-check against cuDNN on the first buffer (bf16 in, fp32 accumulate on both sides)
             ref = F.conv3d(xs[0].permute(0, 4, 1, 2, 3).float(), wb, b, padding=1)
             err = ((ys[0].permute(0, 4, 1, 2, 3).float() - ref).abs().max() / ref.abs().max()).item()
-            for p in plans:
-                lib.diqt_conv_plan_destroy(p)
             del ref
             # ---- torch
             t = {}
@@ -122,7 +132,7 @@ def sweep_conv():
                 del x32
             best = min(t.values())
             kernel = {L.IMPL_SIMT: "conv_simt_kernel", L.IMPL_TC: "conv_tc_kernel", L.IMPL_ZM: "conv_zm_kernel"}[impl.value]
-            print(json.dumps(dict(op="conv3x3x3", side=S, channels=Cc, gflop=flops / 1e9, ours_ms=ours, ours_kernel=kernel,
+            print(json.dumps(dict(op="conv3x3x3", side=S, channels=Cc, gflop=flops / 1e9, ours_ms=ours, ours_kernel=kernel, ours_other_kernels_ms=alt,
                                   ours_tflops=flops / ours / 1e9, ours_frac_burst=flops / ours / 1e9 / peaks["burst"], torch_ms=t,
                                   torch_best_tflops=flops / best / 1e9, speedup=best / ours, max_rel_vs_cudnn=err, torch_timing=how)), flush=True)
             del xs, ys, xcl
