@@ -139,16 +139,25 @@ def build_model(timesteps, device, dtype):
 
 
 def time_dominant_kernel(size, batch, reps=20):
-    """The 3x3x3 conv 64->64 at full resolution (82 % of all FLOPs), alone, CUDA events."""
+    """The 3x3x3 conv 64->64 at full resolution (82 % of all FLOPs), alone, exactly as the engine launches
+    it in the step: conv_zm_kernel with GroupNorm + FiLM + Mish of its input fused into the load path and the output statistics in its
+    epilogue (`fused`), and the same conv without the fused normalisation (`plain`: the kernel the r1 roofline line described).
+    `reps` launches over 4 rotating buffer sets (4 x 2 x 32 MiB at 64^3: consecutive launches never hit the same L2 lines) captured as
+    ONE CUDA graph -- back to back on the stream with programmatic dependent launch, as inside a sampler iteration -- and CUDA events on
+    that stream around 3 replays."""
     import ctypes as C
     from diffusioniqt_b200 import lib as L
     lib = L.load()
     dev = torch.device("cuda")
     n, c = batch, 64
-    # two input/output pairs, alternated, so consecutive launches do not hit the same lines in L2 (each tensor 32 MiB at 64^3)
-    bufs = [(torch.randn(n, size, size, size, c, device=dev).bfloat16(), torch.empty(n, size, size, size, c, device=dev, dtype=torch.bfloat16)) for _ in range(4)]
-    w = torch.randn(c, c, 3, 3, 3, device=dev) * 0.02
+    vox = size ** 3
+    nb = 4
+    xs = [torch.randn(n * vox, c, device=dev).bfloat16() for _ in range(nb)]
+    ys = [torch.empty(n * vox, c, device=dev, dtype=torch.bfloat16) for _ in range(nb)]
+    w = (torch.randn(c, c, 3, 3, 3, device=dev) * 0.02).bfloat16().float().contiguous()
     b = torch.zeros(c, device=dev)
+    gamma, beta = torch.rand(c, device=dev) + 0.5, torch.randn(c, device=dev) * 0.1
+    film = (torch.randn(n, 2 * c, device=dev) * 0.2).contiguous()
     desc = L.ConvDesc(mode=L.CONV_K3, dtype=L.BF16, impl=L.IMPL_AUTO, n=n, d0=size, d1=size, d2=size, c_in=c, ld_in=c, c_out=c, ld_out=c, flags=0)
     impl = C.c_int(0)
     L.check(lib.diqt_conv_resolved_impl(C.byref(desc), C.byref(impl)))
@@ -158,27 +167,60 @@ def time_dominant_kernel(size, batch, reps=20):
     pb = torch.empty(c, dtype=torch.float32, device=dev)
     st = L.current_stream()
     L.check(lib.diqt_conv_pack(C.byref(desc), w.data_ptr(), b.data_ptr(), packed.data_ptr(), pb.data_ptr(), st))
-    plans = []
-    for xi, yo in bufs:
-        p = C.c_void_p(0)
-        L.check(lib.diqt_conv_plan_create(C.byref(desc), xi.data_ptr(), yo.data_ptr(), packed.data_ptr(), pb.data_ptr(), C.byref(p)))
-        plans.append(p.value)
-    for p in plans:
-        L.check(lib.diqt_conv_run(p, st))
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
-    ev[0].record()
-    for i in range(reps):
-        L.check(lib.diqt_conv_run(plans[i % len(plans)], st))
-        ev[i + 1].record()
-    torch.cuda.synchronize()
-    times = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
-    for p in plans:
-        lib.diqt_conv_plan_destroy(p)
-    flops = 2.0 * c * c * 27 * n * size ** 3
-    ms = sum(times) / len(times)
-    kernel = {L.IMPL_SIMT: "conv_simt_kernel", L.IMPL_TC: "conv_tc_kernel", L.IMPL_ZM: "conv_zm_kernel"}[impl.value]
-    return dict(ms=ms, ms_min=min(times), flops=flops, tflops=flops / (ms * 1e-3) / 1e12, kernel=kernel)
+    fusable = n <= 2 and bool(lib.diqt_conv_gn_fusable(C.byref(desc)))
+    # statistics of the inputs (what the producer of x would have left behind) and sinks for the conv's own output statistics
+    nblk = max(1, min(vox // 128, 148 // n))
+    ng = C.c_int(0)
+    L.check(lib.diqt_stats_groups(nblk, 1, C.byref(ng)))
+    part = torch.zeros(n * nblk * c * 2, device=dev)
+    grp = torch.zeros(16 * n * c * 2, device=dev)
+    tick = torch.zeros(16 * n, dtype=torch.int32, device=dev)
+    L.check(lib.diqt_channel_stats_g(xs[0].data_ptr(), L.BF16, n, vox, c, c, nblk, part.data_ptr(), grp.data_ptr(), tick.data_ptr(), st))
+    opart, ogrp, otick = torch.zeros(n * 320 * c * 2, device=dev), torch.zeros(16 * n * c * 2, device=dev), torch.zeros(16 * n, dtype=torch.int32, device=dev)
+    plans = {"fused": [], "plain": []}
+    for x, y in zip(xs, ys):
+        for kind in ("fused", "plain"):
+            if kind == "fused" and not fusable:
+                continue
+            p = C.c_void_p(0)
+            L.check(lib.diqt_conv_plan_create(C.byref(desc), x.data_ptr(), y.data_ptr(), packed.data_ptr(), pb.data_ptr(), C.byref(p)))
+            nbk, ngo = C.c_int(0), C.c_int(0)
+            L.check(lib.diqt_conv_plan_set_stats_g(p.value, opart.data_ptr(), ogrp.data_ptr(), otick.data_ptr(), C.byref(nbk), C.byref(ngo)))
+            if kind == "fused":
+                L.check(lib.diqt_conv_plan_set_gn(p.value, grp.data_ptr(), ng.value, vox, 8, 1e-5, gamma.data_ptr(), beta.data_ptr()))
+                L.check(lib.diqt_conv_plan_set_film(p.value, film.data_ptr(), 2 * c, 0, 1))
+            plans[kind].append(p.value)
+
+    def graph_ms(pl):
+        for p in pl:
+            L.check(lib.diqt_conv_run(p, L.current_stream()))
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(reps):
+                L.check(lib.diqt_conv_run(pl[i % len(pl)], L.current_stream()))
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (3 * reps)
+
+    flops = 2.0 * c * c * 27 * n * vox
+    out = dict(flops=flops, kernel={L.IMPL_SIMT: "conv_simt_kernel", L.IMPL_TC: "conv_tc_kernel", L.IMPL_ZM: "conv_zm_kernel"}[impl.value])
+    for kind, pl in plans.items():
+        if pl:
+            ms = graph_ms(pl)
+            out[kind] = dict(ms=ms, tflops=flops / (ms * 1e-3) / 1e12)
+    for pl in plans.values():
+        for p in pl:
+            lib.diqt_conv_plan_destroy(p)
+    main = out.get("fused") or out["plain"]
+    out.update(ms=main["ms"], tflops=main["tflops"], as_launched="fused GroupNorm+FiLM+Mish input path" if "fused" in out else "plain")
+    return out
 
 
 def time_elementwise_kernel(size, batch, reps=20):
@@ -507,8 +549,13 @@ def main():
         step_tflops = value / world * flops_per_patch / 1e12
         dom = time_dominant_kernel(S, B)
         traffic, traffic_note = read_traffic("%s 64^3" % dom["kernel"]) if (S == 64 and B == 1) else (None, "only captured for the 64^3 batch-1 shape")
-        roofline = dict(bound="tensor", kernel="%s 3x3x3 64->64 @%d^3 (batch %d)" % (dom["kernel"], S, B), achieved=dom["tflops"], peak=peaks["burst"],
-                        unit="TFLOP/s", frac=dom["tflops"] / peaks["burst"], traffic=traffic,
+        roofline = dict(bound="tensor", kernel="%s 3x3x3 64->64 @%d^3 (batch %d), %s" % (dom["kernel"], S, B, dom["as_launched"]), achieved=dom["tflops"],
+                        peak=peaks["burst"], unit="TFLOP/s", frac=dom["tflops"] / peaks["burst"], traffic=traffic,
+                        plain_conv=dict(achieved=dom["plain"]["tflops"], frac=dom["plain"]["tflops"] / peaks["burst"], ms_per_launch=dom["plain"]["ms"],
+                                        note="the same conv launched without the fused input normalisation (what the r1 line measured); in the step "
+                                             "that variant needs a separate GroupNorm-apply kernel in front of it"),
+                        timing="20 launches over 4 rotating buffer sets captured as one CUDA graph (back to back with programmatic dependent launch, "
+                               "as inside a sampler iteration), CUDA events around 3 replays",
                         traffic_note=traffic_note + "; algorithmic traffic is 67.1 MB (32 MiB in + 32 MiB out), the output of a launch stays in the 126 MB L2",
                         ms_per_launch=dom["ms"], flops_per_launch=dom["flops"],
                         peak_source=peaks["source"] + " (burst: kernel timed alone)",

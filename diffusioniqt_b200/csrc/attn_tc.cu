@@ -283,7 +283,7 @@ constexpr int AT2_KSTAGES = 3, AT2_VSTAGES = 2;
 constexpr float AT2_TAU = 8.f;  // log2 units
 
 template <int NQ>
-__global__ void __launch_bounds__(128 * NQ + 64, 1) softmax_attn_tc2_kernel(const __grid_constant__ AttnTcParams p) {
+__global__ void __maxnreg__(200) softmax_attn_tc2_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* q_s = smem;                                   // NQ x 16 KB
@@ -416,17 +416,21 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) softmax_attn_tc2_kernel(cons
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_free[i]));
       const int nvalid = p.ntok - j * AT_K;  // keys of this tile that exist (the TMA zero-fills the rest)
-      float mx = -INFINITY;
-      if (nvalid >= AT_K) {
+      if (nvalid < AT_K) {
 #pragma unroll
-        for (int k = 0; k < 128; ++k) mx = fmaxf(mx, __uint_as_float(s[k]));
-      } else {
-#pragma unroll
-        for (int k = 0; k < 128; ++k) {
+        for (int k = 0; k < 128; ++k)
           if (k >= nvalid) s[k] = 0xff800000u;  // -inf
-          mx = fmaxf(mx, __uint_as_float(s[k]));
-        }
       }
+      // eight independent chains (a single running maximum is a 128-deep dependent chain: ~500 cycles of pure latency per tile with
+      // only two warps per scheduler to hide it)
+      float mx8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) mx8[u] = __uint_as_float(s[u]);
+#pragma unroll
+      for (int k = 8; k < 128; k += 8)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) mx8[u] = fmaxf(mx8[u], __uint_as_float(s[k + u]));
+      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])), fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
       const float mnew = mx * p.c;
       float alpha = 1.f;
       const bool grow = mnew > m_used + AT2_TAU;  // key 0 of tile 0 always exists: the first tile always sets the reference
@@ -435,16 +439,16 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) softmax_attn_tc2_kernel(cons
         m_used = mnew;
         l *= alpha;
       }
-      float sum = 0.f;
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int k = 0; k < 64; ++k) {
         const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * k]), p.c, -m_used));
         const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * k + 1]), p.c, -m_used));
-        sum += p0 + p1;
+        sum4[k & 3] += p0 + p1;
         __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
         s[k] = *reinterpret_cast<uint32_t*>(&h);
       }
-      l += sum;
+      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
       if (j > 0) {
         mbar_wait(smem_u32(&pv_done[i]), ph ^ 1);  // P_i(j - 1) V_{j-1} complete: P_i free, O_i consistent
         tc_fence_after();

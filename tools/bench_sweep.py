@@ -223,8 +223,45 @@ def sweep_attn():
                               speedup=t["sdpa_bf16"] / ours, max_rel_vs_sdpa_fp32=err, torch_timing=how)), flush=True)
 
 
+def sweep_linear_attn():
+    """LinearAttention core (imagen_pytorch3D.py:1001-1011): softmax over d of q (scaled), softmax over tokens of k, ctx = k^T v (64 x 64 per
+    head), out = mish(q ctx).  4 N d^2 FLOP per head against 4 N d bf16 values of traffic: bandwidth / latency work, not tensor work."""
+    heads, dh = 8, 64
+    inner = heads * dh
+    for n in (1728, 13824):
+        qkvs = [torch.randn(n, 3 * inner, device=dev).bfloat16() for _ in range(3)]
+        outs = [torch.empty(n, inner, dtype=torch.bfloat16, device=dev) for _ in range(3)]
+        chunks = C.c_int(0)
+        L.check(lib.diqt_linear_attention_chunks(n, C.byref(chunks)))
+        stat = torch.empty(inner * 2, dtype=torch.float32, device=dev)
+        part = torch.empty(chunks.value * heads * dh * dh, dtype=torch.float32, device=dev)
+
+        def run(qkv, out):
+            p = qkv.data_ptr()
+            L.check(lib.diqt_linear_attention(p, p + inner * 2, p + 2 * inner * 2, 3 * inner, out.data_ptr(), inner, L.BF16, n, heads, dh, dh ** -0.5, 1,
+                                              stat.data_ptr(), part.data_ptr(), L.current_stream()))
+
+        ours, _ = timed([(lambda q=q, o=o: run(q, o)) for q, o in zip(qkvs, outs)], 20)
+
+        def ref(qkv):
+            q, k, v = (t.view(n, heads, dh).permute(1, 0, 2) for t in qkv.chunk(3, dim=1))
+            q = q.softmax(dim=-1) * dh ** -0.5
+            k = k.softmax(dim=-2)
+            ctx = torch.einsum("hnd,hne->hde", k, v)
+            return F.mish(torch.einsum("hnd,hde->hne", q, ctx)).permute(1, 0, 2).reshape(n, inner)
+
+        t, how = timed([(lambda q=q: ref(q)) for q in qkvs], 20)
+        want = ref(qkvs[0].float())
+        run(qkvs[0], outs[0]); torch.cuda.synchronize()
+        err = ((outs[0].float() - want).abs().max() / want.abs().max()).item()
+        nbytes = 4.0 * n * inner * 2
+        print(json.dumps(dict(op="linear_attention", tokens=n, heads=heads, dim_head=dh, ours_ms=ours, ours_gbs=nbytes / ours / 1e6,
+                              ours_frac_hbm=nbytes / ours / 1e6 / peaks["hbm"], torch_ms={"bf16_eager": t}, speedup=t / ours, max_rel_vs_torch_fp32=err,
+                              torch_timing=how)), flush=True)
+
+
 if __name__ == "__main__":
-    which = set(sys.argv[1:]) or {"conv", "norm", "attn"}
+    which = set(sys.argv[1:]) or {"conv", "norm", "attn", "linattn"}
     print(json.dumps(dict(info="cfg5 sweep", gpu=torch.cuda.get_device_name(0), torch=torch.__version__, cudnn=torch.backends.cudnn.version(),
                           peaks=peaks)), flush=True)
     if "conv" in which:
@@ -233,3 +270,5 @@ if __name__ == "__main__":
         sweep_norm()
     if "attn" in which:
         sweep_attn()
+    if "linattn" in which:
+        sweep_linear_attn()
