@@ -479,9 +479,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    B, S = args.batch, args.size
+    # the isolated-kernel timings run FIRST, on a GPU that has not yet been under minutes of full load: the burst peak they are divided by
+    # (MEASURED_PEAKS.json: best of 10 cuBLAS calls) was taken in the same condition
+    dom = time_dominant_kernel(S, B) if rank == 0 else None
+    ew = time_elementwise_kernel(S, B) if rank == 0 else None
+    barrier()
     imagen = build_model(args.timesteps, dev, args.dtype)
     unet, sched = imagen.unets[1], imagen.noise_schedulers[1]
-    B, S = args.batch, args.size
     shape = (B, 1, S, S, S)
     lr_host = synthetic_field(shape, 100 + rank).pin_memory()
     lr_dev = lr_host.to(dev)
@@ -547,7 +552,6 @@ def main():
         ms_per_step = elapsed_ms / args.steps
         flops_per_patch = FLOPS_PER_FWD_64 * (S / 64.0) ** 3 * args.timesteps
         step_tflops = value / world * flops_per_patch / 1e12
-        dom = time_dominant_kernel(S, B)
         traffic, traffic_note = read_traffic("%s 64^3" % dom["kernel"]) if (S == 64 and B == 1) else (None, "only captured for the 64^3 batch-1 shape")
         roofline = dict(bound="tensor", kernel="%s 3x3x3 64->64 @%d^3 (batch %d), %s" % (dom["kernel"], S, B, dom["as_launched"]), achieved=dom["tflops"],
                         peak=peaks["burst"], unit="TFLOP/s", frac=dom["tflops"] / peaks["burst"], traffic=traffic,
@@ -561,7 +565,6 @@ def main():
                         peak_source=peaks["source"] + " (burst: kernel timed alone)",
                         whole_step=dict(achieved=step_tflops, peak=peaks["sustained"], frac=step_tflops / peaks["sustained"], unit="TFLOP/s",
                                         note="all FLOPs of the U-Net / wall time of the sampler, per GPU, vs sustained bf16 peak"))
-        ew = time_elementwise_kernel(S, B)
         roofline_hbm = dict(bound="hbm", kernel="affine_mish_kernel (GroupNorm+FiLM+Mish apply) 64 ch @%d^3 (batch %d)" % (S, B), achieved=ew["gbs"],
                             peak=peaks["hbm"], unit="GB/s", frac=ew["gbs"] / peaks["hbm"], ms_per_launch=ew["ms"], bytes_per_launch=ew["bytes"],
                             note="second-largest kernel class of the step (38 launches per iteration); algorithmic bytes = 1 read + 1 write, 20 launches "

@@ -283,7 +283,7 @@ constexpr int AT2_KSTAGES = 3, AT2_VSTAGES = 2;
 constexpr float AT2_TAU = 8.f;  // log2 units
 
 template <int NQ>
-__global__ void __maxnreg__(200) softmax_attn_tc2_kernel(const __grid_constant__ AttnTcParams p) {
+__global__ void __launch_bounds__(128 * NQ + 64, 1) softmax_attn_tc2_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* q_s = smem;                                   // NQ x 16 KB

@@ -53,10 +53,16 @@ namespace diqt {
 constexpr int ZM_TX = 8, ZM_TY = 16;                    // output tile of one plane: 16 (y) x 8 (x) = 128 GEMM rows
 constexpr int ZM_PLANE_BYTES = (ZM_TY + 2) * (ZM_TX + 2) * 128;  // 180 haloed rows x 64 bf16 = 23040
 constexpr int ZM_PLANE_STRIDE = 23552;                  // next multiple of 1024
-constexpr int ZM_RING = 2;                              // plane buffers per slot
+#ifndef DIQT_ZM_RING
+#define DIQT_ZM_RING 2
+#endif
+#ifndef DIQT_ZM_WSTAGES
+#define DIQT_ZM_WSTAGES 4
+#endif
+constexpr int ZM_RING = DIQT_ZM_RING;                   // plane buffers per slot
 constexpr int ZM_WBLOCK = 64 * 128;                     // one (dz,dy,dx) weight block: 64 c_out rows x 64 c_in
 constexpr int ZM_WSTAGE = 3 * ZM_WBLOCK;
-constexpr int ZM_WSTAGES = 4;
+constexpr int ZM_WSTAGES = DIQT_ZM_WSTAGES;
 constexpr int ZM_THREADS = 256;
 constexpr int ZM_THREADS_GN = 512;                      // + 8 warps that apply GroupNorm + FiLM + Mish to the landed planes
 constexpr int ZM_GN_MAX_CIN = 256, ZM_GN_MAX_N = 2;      // (a, b) of every (volume, channel) live in shared memory
@@ -582,6 +588,13 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
     const int tt = threadIdx.x - W_XF * 32;  // 0..255
     const int c_in = p.KC * 64;
     auto sync256 = [] { asm volatile("bar.sync 2, 256;" ::: "memory"); };
+#if DIQT_XF_MODE == 3   // timing experiment: no finalisation prologue (identity affine)
+    if (true) {
+      pdl_wait();
+      for (int ch = tt; ch < c_in * p.n; ch += 256) { aff[ch] = 1.f; aff[p.n * c_in + ch] = 0.f; }
+      sync256();
+    } else
+#endif
     if (!p.gn.group) {
       pdl_wait();  // (a, b) were written by the finalize kernel in front of this one
     } else {
