@@ -279,6 +279,9 @@ __global__ void __launch_bounds__(AT_THREADS, 2) softmax_attn_tc_kernel(const __
 //     the rows) a handful of times per row instead of once per key tile; the final O / l is exact either way.
 // Warp roles (128 NQ + 64 threads): warps 0 .. 4 NQ - 1 softmax / epilogue, then the TMA producer, then the MMA issuer (TMEM owner);
 // the single-thread roles have the highest warp ids (scheduler priority, see conv_zm.cu).
+#ifndef DIQT_ATTN_LOADS
+#define DIQT_ATTN_LOADS 2   // 1: all 128 scores of a row in registers (one TMEM read); 2: two reads, half the registers (see the kernel)
+#endif
 constexpr int AT2_KSTAGES = 3, AT2_VSTAGES = 2;
 constexpr float AT2_TAU = 8.f;  // log2 units
 
@@ -408,6 +411,77 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) softmax_attn_tc2_kernel(cons
       const uint32_t ph = (uint32_t)(j & 1);
       mbar_wait(smem_u32(&s_full[i]), ph);
       tc_fence_after();
+      const int nvalid = p.ntok - j * AT_K;  // keys of this tile that exist (the TMA zero-fills the rest)
+#if DIQT_ATTN_LOADS == 2
+      // Two reads of S from tensor memory (64 columns at a time): the first for the row maximum, the second to exponentiate.  A 320-thread
+      // block is allocated registers for 12 warps (168 per thread); holding all 128 scores of a row plus the packed probabilities does
+      // not fit without spills, while TMEM reads are cheap (16 KB per warp and pass at 64 B/clk, hidden behind the other warpgroup's MUFU).
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[64];
+        tmem_ld32(t_s + (uint32_t)(half * 64), *reinterpret_cast<uint32_t(*)[32]>(r));
+        tmem_ld32(t_s + (uint32_t)(half * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(r + 32));
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+          const float v = (half * 64 + k < nvalid) ? __uint_as_float(r[k]) : -INFINITY;
+          mx4[k & 3] = fmaxf(mx4[k & 3], v);
+        }
+      }
+      const float mnew = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.c;
+      float alpha = 1.f;
+      const bool grow = mnew > m_used + AT2_TAU;  // key 0 of tile 0 always exists: the first tile always sets the reference
+      if (grow) {
+        alpha = ex2_approx(m_used - mnew);  // 0 on the first tile (m_used = -inf)
+        m_used = mnew;
+        l *= alpha;
+      }
+      if (j > 0) {
+        mbar_wait(smem_u32(&pv_done[i]), ph ^ 1);  // P_i(j - 1) V_{j-1} complete: P_i free, O_i consistent
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {  // rescale this warp's 32 rows of O_i (alpha = 1 for the rows that did not move)
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(t_o + (uint32_t)(c * 32), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+            tmem_st32(t_o + (uint32_t)(c * 32), o);
+          }
+        }
+      }
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[64];
+        tmem_ld32(t_s + (uint32_t)(half * 64), *reinterpret_cast<uint32_t(*)[32]>(r));
+        tmem_ld32(t_s + (uint32_t)(half * 64 + 32), *reinterpret_cast<uint32_t(*)[32]>(r + 32));
+        tmem_ld_wait();
+        if (half == 1) {  // S_i is in registers for the last time: the issuer may overwrite it with Q_i K_{j+1}^T
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&s_free[i]));
+        }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const int k0 = half * 64 + 2 * k;
+          const float p0 = k0 < nvalid ? ex2_approx(fmaf(__uint_as_float(r[2 * k]), p.c, -m_used)) : 0.f;
+          const float p1 = k0 + 1 < nvalid ? ex2_approx(fmaf(__uint_as_float(r[2 * k + 1]), p.c, -m_used)) : 0.f;
+          sum4[k & 3] += p0 + p1;
+          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+          r[k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        tmem_st32(t_p + (uint32_t)(half * 32), *reinterpret_cast<uint32_t(*)[32]>(r));
+      }
+      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_full[i]));
+    }
+#else
       uint32_t s[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld32(t_s + (uint32_t)(c * 32), *reinterpret_cast<uint32_t(*)[32]>(s + 32 * c));
@@ -415,7 +489,6 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) softmax_attn_tc2_kernel(cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_free[i]));
-      const int nvalid = p.ntok - j * AT_K;  // keys of this tile that exist (the TMA zero-fills the rest)
       if (nvalid < AT_K) {
 #pragma unroll
         for (int k = 0; k < 128; ++k)
@@ -471,6 +544,7 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) softmax_attn_tc2_kernel(cons
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&p_full[i]));
     }
+#endif
     // ---- epilogue: O / l -> activation -> bf16 rows
     const float inv_l = 1.f / l;
     mbar_wait(smem_u32(&pv_done[i]), (uint32_t)((nkt - 1) & 1));

@@ -429,9 +429,36 @@ class UnetEngine:
         cross_embed = hasattr(u.init_conv, "convs")
         self.init_conv_tc = (not cross_embed and self.dtype == "bf16" and self.sub_f <= 1 and 27 * nin <= 64 and c0 % 64 == 0 and self.impl != L.IMPL_SIMT
                              and os.environ.get("DIQT_DISABLE_INIT_TC", "0") != "1")
-        if self.init_conv_tc:
-            # K = 27 * c_in = 54 is not a tensor-core shape as a 3x3x3 conv, but it is as a 1x1x1 conv over an im2col'ed K = 64 tensor:
-            # one gather kernel + the tcgen05 per-tap kernel (which also emits the GroupNorm statistics of its output)
+        self.init_conv_fused = (self.init_conv_tc and os.environ.get("DIQT_DISABLE_INIT_FUSED", "0") != "1"
+                                and bool(lib.diqt_init_conv_tc_supported(nin, c0, d1, d2)))
+        if self.init_conv_fused:
+            # K = 27 * c_in = 54 is not a tensor-core shape as a 3x3x3 conv, but it is as a GEMM over im2col rows of K = 64: ONE persistent
+            # kernel builds the rows in shared memory, multiplies them on the tensor cores and emits the first GroupNorm's statistics
+            w = u.init_conv.weight.detach().to(self.device, torch.float32)                   # (c0, nin, 3, 3, 3)
+            w2 = torch.zeros(c0, 64, device=self.device, dtype=torch.float32)
+            w2[:, :27 * nin] = w.permute(0, 2, 3, 4, 1).reshape(c0, 27 * nin)                   # k = tap * nin + ci
+            rows = torch.arange(c0, device=self.device)[:, None]
+            chunks = torch.arange(8, device=self.device)[None, :]
+            src = (chunks ^ (rows & 7))                                                      # position c holds logical chunk c ^ (row & 7)
+            wsw = torch.gather(w2.to(torch.bfloat16).view(c0, 8, 8), 1, src[:, :, None].expand(c0, 8, 8)).contiguous()
+            self._keep.append(wsw)
+            bi = self._f32(u.init_conv.bias)
+            nb_i = C.c_int(0)
+            L.check(lib.diqt_init_conv_tc_blocks(cn, d0, d1, C.byref(nb_i)), "init_conv_tc_blocks")
+            si = self._pp
+            self._pp ^= 1
+            part = self.part[si]
+            assert part.numel() >= n * nb_i.value * c0 * 2
+            ng_i = C.c_int(0)
+            if self.grouped:
+                L.check(lib.diqt_stats_groups(nb_i.value, 1, C.byref(ng_i)), "stats_groups")
+            gp_, tp_ = (self.grp[si].data_ptr(), self.tick[si].data_ptr()) if self.grouped else (0, 0)
+            wp, bp, pp = wsw.data_ptr(), bi.data_ptr(), part.data_ptr()
+            ops.append(lambda st: L.check(lib.diqt_init_conv_tc(planes_ref, strides_ref, nin, wp, bp, xp, xl, cn, d0, d1, d2, c0, pp, gp_, tp_, st), "init_conv_tc"))
+            x.stats = (part, nb_i.value, self.grp[si] if self.grouped else None, ng_i.value)
+            self.conv_impls["init_conv"] = L.IMPL_TC
+        elif self.init_conv_tc:
+            # round-1 path (kept for shapes the fused kernel does not take): im2col rows in global memory + the 1x1x1 tcgen05 conv
             self.im2col = self._empty(n * vox0, 64, dtype=torch.bfloat16)
             w = u.init_conv.weight.detach().to(self.device, torch.float32)                   # (c0, nin, 3, 3, 3)
             w2 = torch.zeros(c0, 64, device=self.device, dtype=torch.float32)

@@ -72,6 +72,9 @@ _SIGNATURES = {
     "diqt_attn_tc_run": [_vp, _vp],
     "diqt_init_conv_pack": [_vp, _i, _i, _vp, _vp],
     "diqt_init_conv_k": [C.POINTER(_vp), C.POINTER(_i64), _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "diqt_init_conv_tc_supported": [_i, _i, _i, _i],
+    "diqt_init_conv_tc_blocks": [_i, _i, _i, C.POINTER(C.c_int)],
+    "diqt_init_conv_tc": [C.POINTER(_vp), C.POINTER(_i64), _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "diqt_init_im2col": [C.POINTER(_vp), C.POINTER(_i64), _i, _vp, _i, _i, _i, _i, _vp],
     "diqt_init_conv": [C.POINTER(_vp), C.POINTER(_i64), _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "diqt_final_conv": [_vp, _i, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],

@@ -372,3 +372,53 @@ def test_init_conv_im2col_tensor_core_path(n, dims, c_in, c_out):
     w2[:, :27 * c_in] = w.permute(0, 2, 3, 4, 1).reshape(c_out, 27 * c_in)
     got = ops.conv3d(col, w2.reshape(c_out, 64, 1, 1, 1), b, mode="k1", impl="tc")
     assert max_rel(ops.from_channels_last(got).cpu(), want) < BF16_TOL
+
+
+@pytest.mark.parametrize("grouped", [False, True])
+@pytest.mark.parametrize("n,dims,c_in,c_out", [(1, (8, 8, 16), 2, 64), (2, (3, 12, 32), 1, 64), (1, (16, 16, 16), 2, 128), (1, (5, 20, 64), 2, 64),
+                                               (1, (64, 64, 64), 2, 64)])
+def test_init_conv_fused_tensor_core_kernel(n, dims, c_in, c_out, grouped):
+    """init_conv (:1291) as ONE kernel: im2col rows built in shared memory, tcgen05 GEMM, bias, bf16 store and the channel statistics the first
+    GroupNorm needs -- against F.conv3d on the bf16-rounded input, bit for bit against the round-1 two-kernel path, statistics against
+    the stored output.  d1 = 12 and 20 are not multiples of the 8-row work item: the last item of a plane is partly outside the volume."""
+    import ctypes as C
+    from diffusioniqt_b200 import lib as L, ops
+    lib = L.load()
+    assert lib.diqt_init_conv_tc_supported(c_in, c_out, dims[1], dims[2])
+    x = _rand(n, c_in, *dims, seed=61)
+    w, b = _rand(c_out, c_in, 3, 3, 3, seed=62, scale=(27 * c_in) ** -0.5), _rand(c_out, seed=63, scale=0.1)
+    want = F.conv3d(x.bfloat16().float(), w.bfloat16().float(), b, padding=1)
+    xc = x.cuda().contiguous()
+    vox = dims[0] * dims[1] * dims[2]
+    planes = (C.c_void_p * c_in)(*[xc.data_ptr() + ci * vox * 4 for ci in range(c_in)])
+    strides = (C.c_int64 * c_in)(*[c_in * vox] * c_in)
+    w2 = torch.zeros(c_out, 64)
+    w2[:, :27 * c_in] = w.permute(0, 2, 3, 4, 1).reshape(c_out, 27 * c_in)
+    rows, chunks = torch.arange(c_out)[:, None], torch.arange(8)[None, :]
+    wsw = torch.gather(w2.bfloat16().view(c_out, 8, 8), 1, (chunks ^ (rows & 7))[:, :, None].expand(c_out, 8, 8)).contiguous().cuda()
+    bias = b.cuda()
+    nb = C.c_int(0)
+    L.check(lib.diqt_init_conv_tc_blocks(n, dims[0], dims[1], C.byref(nb)))
+    out = torch.full((n, *dims, c_out), float("nan"), dtype=torch.bfloat16, device="cuda")
+    part = torch.full((n, nb.value, c_out, 2), float("nan"), device="cuda")
+    ng = C.c_int(0)
+    L.check(lib.diqt_stats_groups(nb.value, 1, C.byref(ng)))
+    grp = torch.full((n, ng.value, c_out, 2), float("nan"), device="cuda")
+    tick = torch.zeros(16 * n, dtype=torch.int32, device="cuda")
+    L.check(lib.diqt_init_conv_tc(planes, strides, c_in, wsw.data_ptr(), bias.data_ptr(), out.data_ptr(), c_out, n, *dims, c_out, part.data_ptr(),
+                                  grp.data_ptr() if grouped else 0, tick.data_ptr() if grouped else 0, L.current_stream()), "init_conv_tc")
+    torch.cuda.synchronize()
+    stored = ops.from_channels_last(out).cpu()
+    assert max_rel(stored, want) < BF16_TOL
+    assert not torch.isnan(part).any()
+    s = part.sum(dim=1).cpu()
+    assert max_rel(s[..., 0], stored.sum(dim=(2, 3, 4))) < 2e-4
+    assert max_rel(s[..., 1], (stored ** 2).sum(dim=(2, 3, 4))) < 2e-4
+    if grouped:
+        assert int(tick.abs().sum()) == 0
+        assert max_rel(grp.sum(dim=1).cpu(), s) < 1e-5
+    # the round-1 path: im2col rows in global memory + the 1x1x1 tcgen05 conv (same products, same accumulation order)
+    col = torch.empty(n, *dims, 64, dtype=torch.bfloat16, device="cuda")
+    L.check(lib.diqt_init_im2col(planes, strides, c_in, col.data_ptr(), n, *dims, L.current_stream()), "init_im2col")
+    two = ops.conv3d(col, w2.reshape(c_out, 64, 1, 1, 1), b, mode="k1", impl="tc")
+    assert torch.equal(two, out)
