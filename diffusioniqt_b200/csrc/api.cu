@@ -16,6 +16,9 @@ int conv_tc_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
 int conv_tc_run(const TcPlan* plan, cudaStream_t st);
 void conv_tc_destroy(TcPlan* plan);
 int conv_tc_set_stats(TcPlan* plan, float* partial, float* group, unsigned int* tickets, int* ngroups);
+bool conv_tc_prefers_small(const diqt_conv_desc* d);
+size_t conv_tc_workspace_bytes(const TcPlan* plan);
+int conv_tc_set_workspace(TcPlan* plan, void* ws, size_t bytes);
 struct ZmPlan;
 bool conv_zm_supported(const diqt_conv_desc* d);
 bool conv_zm_profitable(const diqt_conv_desc* d);
@@ -61,7 +64,9 @@ static int check_desc(const diqt_conv_desc* d) {
 static int resolve_impl(const diqt_conv_desc* d, int* impl) {
   int want = d->impl;
   if (want == DIQT_IMPL_AUTO)
-    want = (conv_zm_supported(d) && conv_zm_profitable(d)) ? DIQT_IMPL_ZM : conv_tc_supported(d) ? DIQT_IMPL_TC : DIQT_IMPL_SIMT;
+    want = (conv_zm_supported(d) && conv_zm_profitable(d) && !conv_tc_prefers_small(d)) ? DIQT_IMPL_ZM
+           : conv_tc_supported(d)                                                          ? DIQT_IMPL_TC
+                                                                                           : DIQT_IMPL_SIMT;
   if (want == DIQT_IMPL_ZM && !conv_zm_supported(d)) {
     set_error("conv: z-march kernel needs 3x3x3 bf16, c_in %% 64 == 0, c_out %% 64 == 0 (<= 256), d2 %% 8 == 0, d1 %% 16 == 0 (got c_in=%d c_out=%d dims %d,%d,%d)", d->c_in,
               d->c_out, d->d0, d->d1, d->d2);
@@ -198,4 +203,16 @@ extern "C" int diqt_conv_plan_set_film(diqt_conv_plan* plan, const float* film, 
   // (with diqt_conv_plan_set_gn_affine the FiLM rows are already folded into a, b by diqt_gn_finalize)
   conv_zm_set_film(plan->zm, film, film_ld, film_row, film_row_stride_n);
   return DIQT_OK;
+}
+
+// ---- split-K workspace of the per-tap family (small volumes) --------------------------------------------------------------------
+extern "C" int diqt_conv_plan_workspace_bytes(const diqt_conv_plan* plan, size_t* bytes) {
+  DIQT_REQUIRE(plan && bytes, "conv_plan_workspace_bytes: null pointer");
+  *bytes = (plan->impl == DIQT_IMPL_TC && plan->tc) ? conv_tc_workspace_bytes(plan->tc) : 0;
+  return DIQT_OK;
+}
+
+extern "C" int diqt_conv_plan_set_workspace(diqt_conv_plan* plan, void* workspace, size_t bytes) {
+  DIQT_REQUIRE(plan && plan->impl == DIQT_IMPL_TC && plan->tc, "conv_plan_set_workspace: this plan takes no workspace");
+  return conv_tc_set_workspace(plan->tc, workspace, bytes);
 }

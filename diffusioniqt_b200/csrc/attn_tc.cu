@@ -39,6 +39,22 @@ __device__ __forceinline__ float ex2_approx(float x) {  // arguments are <= 0 he
   return y;
 }
 
+// 2^x on the FMA / ALU pipes (Cody-Waite split + cubic): the softmax is bound by the 16 / clk / SM special-function unit, so a share of
+// the exponentials is computed here instead (the trick FlashAttention-4 uses on this architecture).  x <= ~8; relative error < 7e-4,
+// far below the bf16 rounding of P; x = -inf (masked keys) gives 2^-126 instead of 0, which no sum notices.
+__device__ __forceinline__ float ex2_poly(float x) {
+  const float xr = fmaxf(x, -126.f);
+  const float t = xr + 12582912.f;           // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = xr - (t - 12582912.f);     // [-0.5, 0.5]
+  float p = fmaf(f, 0.0555041f, 0.2402265f);
+  p = fmaf(p, f, 0.6931472f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+#ifndef DIQT_ATTN_POLY
+#define DIQT_ATTN_POLY 1   // 1: every fourth exponential of the single-pass kernel goes through ex2_poly; 0: all through MUFU
+#endif
+
 __device__ __forceinline__ void tma_load_2d_as5(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int row0) {
   tma_load_5d(dst, map, bar, c0, row0, 0, 0, 0);
 }
@@ -280,7 +296,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) softmax_attn_tc_kernel(const __
 // Warp roles (128 NQ + 64 threads): warps 0 .. 4 NQ - 1 softmax / epilogue, then the TMA producer, then the MMA issuer (TMEM owner);
 // the single-thread roles have the highest warp ids (scheduler priority, see conv_zm.cu).
 #ifndef DIQT_ATTN_LOADS
-#define DIQT_ATTN_LOADS 2   // 1: all 128 scores of a row in registers (one TMEM read); 2: two reads, half the registers (see the kernel)
+#define DIQT_ATTN_LOADS 3   // 1: whole row in registers, then maximum, then exponentials; 2: two TMEM reads (measured 1.6x slower); 3: speculative maximum
 #endif
 constexpr int AT2_KSTAGES = 3, AT2_VSTAGES = 2;
 constexpr float AT2_TAU = 8.f;  // log2 units
@@ -412,7 +428,94 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) softmax_attn_tc2_kernel(cons
       mbar_wait(smem_u32(&s_full[i]), ph);
       tc_fence_after();
       const int nvalid = p.ntok - j * AT_K;  // keys of this tile that exist (the TMA zero-fills the rest)
-#if DIQT_ATTN_LOADS == 2
+#if DIQT_ATTN_LOADS == 3
+      // Speculative reference maximum: tensor memory delivers S at ~64 B/clk per SM (measured: a second read of S costs as much as all
+      // the exponentials), so the loads must overlap the MUFU work of the SAME warp, which the row maximum normally forbids (it needs the
+      // whole row first).  With lazy rescaling the reference maximum of a row rarely moves: exponentiate chunk c against the CURRENT
+      // reference while chunk c + 1 is in flight, track the row maximum on the side, and only if some row of the warp outgrew its
+      // reference by more than 2^8 redo the tile for the warp (first tile always; afterwards a handful of tiles per row at most).
+      uint32_t pk[64];
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      auto exp_chunk = [&](const uint32_t (&r)[32], int c, const bool mask) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int k0 = c * 32 + 2 * k;
+          const float v0 = (!mask || k0 < nvalid) ? __uint_as_float(r[2 * k]) : -INFINITY;
+          const float v1 = (!mask || k0 + 1 < nvalid) ? __uint_as_float(r[2 * k + 1]) : -INFINITY;
+          mx4[k & 3] = fmaxf(mx4[k & 3], fmaxf(v0, v1));
+          const float p0 = ex2_approx(fmaf(v0, p.c, -m_used));
+          const float p1 = (DIQT_ATTN_POLY && (k & 1)) ? ex2_poly(fmaf(v1, p.c, -m_used)) : ex2_approx(fmaf(v1, p.c, -m_used));
+          sum4[k & 3] += p0 + p1;
+          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+          pk[c * 16 + k] = *reinterpret_cast<uint32_t*>(&h);
+        }
+      };
+      auto max_chunk = [&](const uint32_t (&r)[32], int c) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) mx4[k & 3] = fmaxf(mx4[k & 3], c * 32 + k < nvalid ? __uint_as_float(r[k]) : -INFINITY);
+      };
+      auto exp_tile = [&](const bool mask) {  // four chunks, the load of chunk c + 1 in flight under the exponentials of chunk c
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_s, ra);
+        tmem_ld_wait();
+        tmem_ld32(t_s + 32, rb); exp_chunk(ra, 0, mask); tmem_ld_wait();
+        tmem_ld32(t_s + 64, ra); exp_chunk(rb, 1, mask); tmem_ld_wait();
+        tmem_ld32(t_s + 96, rb); exp_chunk(ra, 2, mask); tmem_ld_wait();
+        exp_chunk(rb, 3, mask);
+      };
+      const bool full = nvalid >= AT_K;  // every tile but possibly the last
+      if (j > 0) {
+        if (full) exp_tile(false); else exp_tile(true);
+      } else {  // no reference yet: only the maximum
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_s, ra);
+        tmem_ld_wait();
+        tmem_ld32(t_s + 32, rb); max_chunk(ra, 0); tmem_ld_wait();
+        tmem_ld32(t_s + 64, ra); max_chunk(rb, 1); tmem_ld_wait();
+        tmem_ld32(t_s + 96, rb); max_chunk(ra, 2); tmem_ld_wait();
+        max_chunk(rb, 3);
+      }
+      const float mnew = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.c;
+      float alpha = 1.f;
+      const bool grow = mnew > m_used + AT2_TAU;
+      const bool redo = __any_sync(0xffffffffu, grow);
+      if (redo) {
+        if (grow) {
+          alpha = ex2_approx(m_used - mnew);  // 0 on the first tile (m_used = -inf)
+          m_used = mnew;
+          l *= alpha;
+        }
+        sum4[0] = sum4[1] = sum4[2] = sum4[3] = 0.f;
+        exp_tile(true);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_free[i]));
+      l += (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      if (j > 0) {
+        mbar_wait(smem_u32(&pv_done[i]), ph ^ 1);  // P_i(j - 1) V_{j-1} complete: P_i free, O_i consistent
+        tc_fence_after();
+        if (redo) {  // rescale this warp's 32 rows of O_i (alpha = 1 for the rows that did not move)
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld32(t_o + (uint32_t)(c * 32), o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 32; ++k) o[k] = __float_as_uint(__uint_as_float(o[k]) * alpha);
+            tmem_st32(t_o + (uint32_t)(c * 32), o);
+          }
+        }
+      }
+      tmem_st32(t_p, *reinterpret_cast<uint32_t(*)[32]>(pk));
+      tmem_st32(t_p + 32, *reinterpret_cast<uint32_t(*)[32]>(pk + 32));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_full[i]));
+    }
+#elif DIQT_ATTN_LOADS == 2
       // Two reads of S from tensor memory (64 columns at a time): the first for the row maximum, the second to exponentiate.  A 320-thread
       // block is allocated registers for 12 warps (168 per thread); holding all 128 scores of a row plus the packed probabilities does
       // not fit without spills, while TMEM reads are cheap (16 KB per warp and pass at 64 B/clk, hidden behind the other warpgroup's MUFU).

@@ -53,6 +53,12 @@ struct TcParams {
   int n_batch;           // volumes
   int ox, oy, oz;        // output voxel grid (to mask rows of edge tiles)
   int edge_tiles;        // 1 if some tile sticks out of the volume
+  // split-K (small volumes: fewer output tiles than SMs): the K-blocks of a tile are dealt to `ksplit` CTAs, each leaves its fp32
+  // partial tile in `ws`; the LAST of them to finish (ticket) sums all partials in split order -- not arrival order: results stay
+  // bitwise reproducible -- and runs the normal epilogue.  ksplit = 1: off.
+  int ksplit, kbper;
+  float* ws;                 // [tile][ksplit][128 rows][block_n] fp32
+  unsigned int* tickets;     // [tile], zero before first use, self-resetting
 };
 
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = p.taps * p.kchunks;
-  const int total_work = p.m_tiles * p.n_tiles;
+  const int total_work = p.m_tiles * p.n_tiles * p.ksplit;
 
   for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += blockDim.x) s_bias[i] = p.bias[i];
   if (warp == 0 && lane == 0) {
@@ -100,6 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   pdl_sync();  // prologue above is private to this CTA; the previous kernel's activations are read only below
 
   auto decode_tile = [&](int work, int& n_tile, int& x0, int& y0, int& z0, int& b0) {
+    work /= p.ksplit;  // the splits of one tile are neighbouring work units: they run at the same time on different CTAs
     n_tile = work % p.n_tiles;
     int m = work / p.n_tiles;
     const int tx = m % p.tiles_x; m /= p.tiles_x;
@@ -117,7 +124,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         int n_tile, x0, y0, z0, b0;
         decode_tile(work, n_tile, x0, y0, z0, b0);
         const uint8_t* wsrc = p.w + (size_t)n_tile * kblocks * b_bytes;
-        for (int kb = 0; kb < kblocks; ++kb) {
+        const int kb0 = (work % p.ksplit) * p.kbper, kb1 = min(kblocks, kb0 + p.kbper);
+        for (int kb = kb0; kb < kb1; ++kb) {
           const int t = kb / p.kchunks, q = kb - t * p.kchunks;
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t bar = smem_u32(&full_bar[stage]);
@@ -142,7 +150,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
-      for (int kb = 0; kb < kblocks; ++kb) {
+      const int kb0 = (work % p.ksplit) * p.kbper, kb1 = min(kblocks, kb0 + p.kbper);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
         {  // warp-uniform issue code; the issuing lane is elected inside umma_bf16 / umma_commit
@@ -151,9 +160,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint64_t bdesc = make_sw128_desc(a_addr + kABytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // +32 B (16 bf16) along K inside the swizzle atom = +2 in the address field
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (kb | k) != 0);
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, ((kb - kb0) | k) != 0);
           umma_commit(smem_u32(&empty_bar[stage]));
-          if (kb == kblocks - 1) umma_commit(smem_u32(&tfull_bar[acc]));
+          if (kb == kb1 - 1) umma_commit(smem_u32(&tfull_bar[acc]));
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
@@ -202,20 +211,69 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
       int n_tile, x0, y0, z0, b0;
       decode_tile(work, n_tile, x0, y0, z0, b0);
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      tc_fence_after();
+      const float* wtile = nullptr;  // split-K: this tile's partials [ksplit][128][block_n]
+      if (p.ksplit > 1) {
+        const int tile = work / p.ksplit, ks = work % p.ksplit;
+        float* mine = p.ws + ((size_t)tile * p.ksplit + ks) * kTileM * p.block_n + (size_t)row * p.block_n;
+        for (int c32 = 0; c32 < p.block_n / 32; ++c32) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.block_n + c32 * 32), r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            __stcg(reinterpret_cast<uint4*>(mine + c32 * 32) + j, make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));  // the accumulator is free: the next unit's MMAs may start
+        __threadfence();  // the partial is visible device-wide before the ticket is taken
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        int* s_flag = reinterpret_cast<int*>(s_red);
+        if (et == 0) {
+          const unsigned t = atomicAdd(&p.tickets[tile], 1u);
+          *s_flag = (t == (unsigned)p.ksplit - 1u);
+          if (t == (unsigned)p.ksplit - 1u) p.tickets[tile] = 0u;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const bool last = *s_flag != 0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // s_red is reused by the statistics flush
+        if (!last) {
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
+        __threadfence();
+        wtile = p.ws + (size_t)tile * p.ksplit * kTileM * p.block_n + (size_t)row * p.block_n;
+      }
       if (p.stats) {
         if (st_n >= 0 && b0 != st_n) flush_stats(st_n);
         if (st_first < 0) st_first = b0;
         st_n = b0;
       }
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
-      tc_fence_after();
       if (et == 0) bulk_wait_read0();  // previous tile's TMA stores have finished reading the staging tile
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const float* bias = s_bias + n_tile * p.block_n;
       for (int c32 = 0; c32 < p.block_n / 32; ++c32) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.block_n + c32 * 32), r);
-        tmem_ld_wait();
+        if (wtile) {  // sum of the partials in split order
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+          for (int ks = 0; ks < p.ksplit; ++ks) {
+            const uint4* src = reinterpret_cast<const uint4*>(wtile + (size_t)ks * kTileM * p.block_n + c32 * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 v = __ldcg(src + j);
+              r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + __uint_as_float(v.x));
+              r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + __uint_as_float(v.y));
+              r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + __uint_as_float(v.z));
+              r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + __uint_as_float(v.w));
+            }
+          }
+        } else {
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.block_n + c32 * 32), r);
+          tmem_ld_wait();
+        }
         uint32_t packed[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -235,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (lane == 0 && !wtile) mbar_arrive(smem_u32(&tempty_bar[acc]));  // (split-K released it before the ticket)
       fence_proxy_async();
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (et == 0) {
@@ -430,6 +488,8 @@ int conv_tc_plan(const diqt_conv_desc* d, const void* in, void* out, const void*
   p.ox = od2; p.oy = od1; p.oz = od0;
   p.edge_tiles = (od2 % p.bx || od1 % p.by || od0 % p.bz) ? 1 : 0;
   p.tmem_cols = 2 * p.block_n < 32 ? 32 : 2 * p.block_n;  // 128 / 256 / 512: powers of two
+  p.ksplit = 1;
+  p.kbper = p.taps * p.kchunks;
 
   const __nv_bfloat16* inb = (const __nv_bfloat16*)in;
   __nv_bfloat16* outb = (__nv_bfloat16*)out;
@@ -498,6 +558,52 @@ int conv_tc_run(const TcPlan* plan, cudaStream_t st) {
 }
 
 void conv_tc_destroy(TcPlan* plan) { delete plan; }
+
+// ---- split-K for small volumes ---------------------------------------------------------------------------------------------
+static int tc_sms() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+// splits that bring the number of CTAs close to the SM count (0 / 1: not worth it)
+static int tc_ksplit_for(const TcParams& p, int* kbper_out) {
+  const int kblocks = p.taps * p.kchunks, tiles = p.m_tiles * p.n_tiles, sms = tc_sms();
+  if (p.mode != DIQT_CONV_K3 || tiles * 2 > sms || kblocks < 8) return 1;
+  int want = sms / tiles;
+  if (want > 8) want = 8;
+  const int kbper = (kblocks + want - 1) / want;
+  if (kbper_out) *kbper_out = kbper;
+  return (kblocks + kbper - 1) / kbper;
+}
+bool conv_tc_prefers_small(const diqt_conv_desc* d) {  // fewer output tiles than half the SMs: the per-tap kernel with split-K wins over the z-march
+  if (d->mode != DIQT_CONV_K3 || !conv_tc_supported(d)) return false;
+  const int64_t rows = (int64_t)d->n * d->d0 * d->d1 * d->d2;
+  const int64_t tiles = (rows + kTileM - 1) / kTileM * (d->c_out / tc_block_n(d));
+  return tiles * 2 <= tc_sms();
+}
+size_t conv_tc_workspace_bytes(const TcPlan* plan) {
+  int kbper = 0;
+  const int ks = tc_ksplit_for(plan->p, &kbper);
+  if (ks <= 1) return 0;
+  const size_t tiles = (size_t)plan->p.m_tiles * plan->p.n_tiles;
+  return ((tiles * 4 + 255) / 256) * 256 + tiles * ks * kTileM * plan->p.block_n * sizeof(float);
+}
+// workspace: [tickets (zeroed by the caller once; self-resetting)] [partials]; must be called before conv_tc_set_stats (the grid changes)
+int conv_tc_set_workspace(TcPlan* plan, void* ws, size_t bytes) {
+  const size_t need = conv_tc_workspace_bytes(plan);
+  DIQT_REQUIRE(need > 0, "conv(tc): this plan does not use a split-K workspace");
+  DIQT_REQUIRE(ws && bytes >= need && (uintptr_t)ws % 256 == 0, "conv(tc): split-K workspace of %zu bytes (256-byte aligned) needed, got %zu", need, bytes);
+  DIQT_REQUIRE(!plan->p.stats, "conv(tc): set the workspace before the statistics sink");
+  TcParams& p = plan->p;
+  p.ksplit = tc_ksplit_for(p, &p.kbper);
+  const size_t tiles = (size_t)p.m_tiles * p.n_tiles;
+  p.tickets = (unsigned int*)ws;
+  p.ws = (float*)((uint8_t*)ws + ((tiles * 4 + 255) / 256) * 256);
+  const int total = (int)tiles * p.ksplit, sms = tc_sms();
+  plan->grid = total < sms ? total : sms;
+  return DIQT_OK;
+}
 
 // Fused output statistics are available when one CTA tile never mixes volumes and N fits one tile.
 int conv_tc_set_stats(TcPlan* plan, float* partial, float* group, unsigned int* tickets, int* ngroups) {

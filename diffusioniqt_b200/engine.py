@@ -91,6 +91,7 @@ class UnetEngine:
         self.film_stride_n = 1
         self.conv_impls = {}                  # site name -> resolved impl (for tests / reporting)
         self.fused_gn = []                    # conv sites that apply GroupNorm + FiLM + Mish on their own load path
+        self.split_k = []                     # conv sites of the per-tap family that run with split-K (small volumes)
         # sampler states (schedule tables, captured step graphs) that bake this engine's buffer addresses live and die with it
         self.sampler_cache = {}
         self.film_gen = 0
@@ -149,6 +150,14 @@ class UnetEngine:
                 f"plan {name}")
         self._plans.append(plan.value)
         run, pv = self.lib.diqt_conv_run, plan.value
+        # small volumes: the per-tap family splits K over several CTAs and wants a scratch buffer for the fp32 partial tiles
+        wsb = C.c_size_t(0)
+        L.check(self.lib.diqt_conv_plan_workspace_bytes(pv, C.byref(wsb)), f"workspace_bytes {name}")
+        if wsb.value and os.environ.get("DIQT_DISABLE_SPLITK", "0") != "1":
+            ws = torch.zeros(wsb.value, dtype=torch.uint8, device=self.device)
+            self._keep.append(ws)
+            L.check(self.lib.diqt_conv_plan_set_workspace(pv, ws.data_ptr(), wsb.value), f"set_workspace {name}")
+            self.split_k.append(name)
         film_off = None
         if gn == "affine":
             L.check(self.lib.diqt_conv_plan_set_gn_affine(pv, self.aff_a.data_ptr(), self.aff_b.data_ptr()), f"set_gn_affine {name}")

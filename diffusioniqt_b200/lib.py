@@ -40,6 +40,8 @@ _SIGNATURES = {
     "diqt_conv_pack": [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp],
     "diqt_conv_plan_create": [C.POINTER(ConvDesc), _vp, _vp, _vp, _vp, C.POINTER(_vp)],
     "diqt_conv_plan_set_stats": [_vp, _vp, C.POINTER(C.c_int)],
+    "diqt_conv_plan_workspace_bytes": [_vp, C.POINTER(C.c_size_t)],
+    "diqt_conv_plan_set_workspace": [_vp, _vp, C.c_size_t],
     "diqt_conv_plan_destroy": [_vp],
     "diqt_conv_run": [_vp, _vp],
     "diqt_channel_stats": [_vp, _i, _i, _i64, _i, _i, _i, _vp, _i, _i, _vp],

@@ -35,11 +35,12 @@ def from_channels_last(x: torch.Tensor) -> torch.Tensor:
 
 
 def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], mode: str = "k3", impl: str = "auto", with_stats: bool = False,
-           grouped: bool = False, gn: Optional[dict] = None, pair: bool = True):
+           grouped: bool = False, gn: Optional[dict] = None, pair: bool = True, split_k: bool = True):
     """x: (n, d0, d1, d2, c_in) bf16/fp32 on CUDA; weight/bias exactly as in the reference state_dict (fp32).
     gn = dict(groups, gamma, beta, scale_shift=None, eps=1e-5, nblk=8): the conv computes conv(mish(FiLM(GroupNorm(x)))) with the
     normalisation fused into its load path (z-march family only; raises if the plan cannot).
     pair=False keeps the z-march kernel on single CTAs where it would otherwise run as CTA pairs (tcgen05.mma.cta_group::2).
+    split_k=False keeps the per-tap kernel unsplit on small volumes (it otherwise deals a tile's K-blocks to several CTAs).
     with_stats=True also returns the fused per-block channel statistics (n, nblk, c_out, 2) or None if the kernel cannot fuse them;
     with grouped=True the statistics are (partial rows, group sums (n, ngroups, c_out, 2)) through the grouped sink."""
     lib = L.load()
@@ -73,6 +74,11 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
     L.check(lib.diqt_conv_plan_create(C.byref(desc), x.data_ptr(), out.data_ptr(), packed.data_ptr(), pbias.data_ptr(), C.byref(plan)), "conv_plan")
     stats = None
     try:
+        wsb = C.c_size_t(0)
+        L.check(lib.diqt_conv_plan_workspace_bytes(plan.value, C.byref(wsb)), "conv_plan_workspace_bytes")
+        if wsb.value and split_k:
+            ws = torch.zeros(wsb.value, dtype=torch.uint8, device=x.device)
+            L.check(lib.diqt_conv_plan_set_workspace(plan.value, ws.data_ptr(), wsb.value), "conv_plan_set_workspace")
         if gn is not None and gn.get("affine"):
             # any batch / width: statistics -> diqt_gn_finalize -> (a, b) in global memory -> the conv applies mish(a * x + b)
             nblk = gn.get("nblk", 8)

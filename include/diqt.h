@@ -103,6 +103,11 @@ int diqt_conv_plan_create(const diqt_conv_desc* d, const void* in, void* out, co
  * layout of diqt_channel_stats: partial[n][*nblk][c_out][2].  *nblk = 0 means this plan cannot fuse them
  * (SIMT family, DIQT_CONV_UP, tiny volumes): run diqt_channel_stats on the output instead. */
 int diqt_conv_plan_set_stats(diqt_conv_plan* plan, float* partial, int* nblk);
+/* Small volumes (fewer 128-voxel output tiles than half the SMs) run the per-tap family with split-K: *bytes > 0 says the plan wants a
+ * workspace of that size (256-byte aligned, its first bytes zero before the first run, shareable between plans that never run
+ * concurrently); hand it over BEFORE diqt_conv_plan_set_stats*.  Without a workspace the plan runs unsplit (same results, slower). */
+int diqt_conv_plan_workspace_bytes(const diqt_conv_plan* plan, size_t* bytes);
+int diqt_conv_plan_set_workspace(diqt_conv_plan* plan, void* workspace, size_t bytes);
 void diqt_conv_plan_destroy(diqt_conv_plan* plan);
 int diqt_conv_run(const diqt_conv_plan* plan, void* stream);
 

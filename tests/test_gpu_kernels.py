@@ -422,3 +422,31 @@ def test_init_conv_fused_tensor_core_kernel(n, dims, c_in, c_out, grouped):
     L.check(lib.diqt_init_im2col(planes, strides, c_in, col.data_ptr(), n, *dims, L.current_stream()), "init_im2col")
     two = ops.conv3d(col, w2.reshape(c_out, 64, 1, 1, 1), b, mode="k1", impl="tc")
     assert torch.equal(two, out)
+
+
+@pytest.mark.parametrize("n,dims,c_in,c_out", [(1, (16, 16, 16), 128, 128), (1, (16, 16, 16), 64, 64), (2, (8, 8, 8), 128, 128), (1, (8, 8, 8), 256, 256),
+                                               (1, (16, 16, 16), 512, 512), (1, (4, 6, 10), 64, 128), (1, (16, 16, 16), 192, 128)])
+def test_conv_tcgen05_split_k_small_volumes(n, dims, c_in, c_out):
+    """Small volumes (fewer 128-voxel tiles than half the SMs) run the per-tap kernel with the K-blocks of a tile dealt to several CTAs; the last
+    CTA to finish sums the fp32 partials in split order.  Against fp32 PyTorch, against the unsplit kernel (same products, another
+    summation tree: equal up to bf16 rounding of a few elements), repeatable bit for bit, statistics consistent with the stored output."""
+    from diffusioniqt_b200 import ops
+    x = _rand(n, c_in, *dims, seed=71).bfloat16().float()
+    w, b = _conv_weight("k3", c_in, c_out, 72)
+    want = _conv_reference(x, w.bfloat16().float(), b, "k3")
+    xg = ops.to_channels_last(x.cuda(), torch.bfloat16)
+    got, stats = ops.conv3d(xg, w, b, mode="k3", impl="tc", with_stats=True)
+    again, _ = ops.conv3d(xg, w, b, mode="k3", impl="tc", with_stats=True)
+    plain = ops.conv3d(xg, w, b, mode="k3", impl="tc", split_k=False)
+    stored = ops.from_channels_last(got).cpu()
+    assert max_rel(stored, want) < BF16_TOL
+    assert torch.equal(got, again)
+    assert max_rel(got.float().cpu(), plain.float().cpu()) < 8e-3
+    if stats is not None:
+        assert not torch.isnan(stats).any()
+        s = stats.sum(dim=1).cpu()
+        assert max_rel(s[..., 0], stored.sum(dim=(2, 3, 4))) < 2e-4
+        assert max_rel(s[..., 1], (stored ** 2).sum(dim=(2, 3, 4))) < 2e-4
+    # auto dispatch takes this path for such shapes
+    auto = ops.conv3d(xg, w, b, mode="k3", impl="auto")
+    assert torch.equal(auto, got)

@@ -83,7 +83,7 @@ def sweep_conv():
             # ---- ours
             xs = [torch.randn(1, S, S, S, Cc, device=dev).bfloat16() for _ in range(nb)]
             ys = [torch.empty(1, S, S, S, Cc, device=dev, dtype=torch.bfloat16) for _ in range(nb)]
-            def ours(impl_id, flags=0):
+            def ours(impl_id, flags=0, split_k=True):
                 desc = L.ConvDesc(mode=L.CONV_K3, dtype=L.BF16, impl=impl_id, n=1, d0=S, d1=S, d2=S, c_in=Cc, ld_in=Cc, c_out=Cc, ld_out=Cc, flags=flags)
                 impl = C.c_int(0)
                 L.check(lib.diqt_conv_resolved_impl(C.byref(desc), C.byref(impl)))
@@ -92,10 +92,16 @@ def sweep_conv():
                 packed = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
                 pb = torch.empty(Cc, dtype=torch.float32, device=dev)
                 L.check(lib.diqt_conv_pack(C.byref(desc), wb.data_ptr(), b.data_ptr(), packed.data_ptr(), pb.data_ptr(), L.current_stream()))
-                plans = []
+                plans, keep = [], []
                 for x, y in zip(xs, ys):
                     p = C.c_void_p(0)
                     L.check(lib.diqt_conv_plan_create(C.byref(desc), x.data_ptr(), y.data_ptr(), packed.data_ptr(), pb.data_ptr(), C.byref(p)))
+                    wsb = C.c_size_t(0)
+                    L.check(lib.diqt_conv_plan_workspace_bytes(p.value, C.byref(wsb)))
+                    if wsb.value and split_k:
+                        ws = torch.zeros(wsb.value, dtype=torch.uint8, device=dev)
+                        keep.append(ws)
+                        L.check(lib.diqt_conv_plan_set_workspace(p.value, ws.data_ptr(), wsb.value))
                     plans.append(p.value)
                 t, _ = timed([(lambda p=p: L.check(lib.diqt_conv_run(p, L.current_stream()))) for p in plans], reps)
                 torch.cuda.synchronize()
@@ -105,7 +111,7 @@ def sweep_conv():
 
             wb = w.bfloat16().float().contiguous()
             alt = {}
-            alt["conv_tc_kernel (per tap)"], _ = ours(L.IMPL_TC)
+            alt["conv_tc_kernel (per tap, no split-K)"], _ = ours(L.IMPL_TC, split_k=False)
             alt["conv_zm_kernel single CTA"], _ = ours(L.IMPL_ZM, L.CONV_FLAG_NO_CTA_PAIR)
             ours_ms, impl_v = ours(L.IMPL_AUTO)          # last: ys[0] holds the product path's output for the cross-check below
             impl = C.c_int(impl_v)
