@@ -52,7 +52,8 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 #ifndef DIQT_ATTN_POLY
-#define DIQT_ATTN_POLY 1   // 1: every fourth exponential of the single-pass kernel goes through ex2_poly; 0: all through MUFU
+#define DIQT_ATTN_POLY 0   // 1: every fourth exponential of the single-pass kernel goes through ex2_poly; 0: all through MUFU (measured: 0.580 ms
+                           // against 0.594 with the polynomial share at 13 824 tokens: the kernel is not MUFU-saturated, the extra issue slots cost more)
 #endif
 
 __device__ __forceinline__ void tma_load_2d_as5(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int row0) {

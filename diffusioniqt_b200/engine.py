@@ -238,7 +238,7 @@ class UnetEngine:
         self.grouped = self.sub_f <= 1 and n <= 2 and os.environ.get("DIQT_DISABLE_GROUPED", "0") != "1"   # variable: A/B and diagnostics
         self.grp = [torch.zeros(16 * n * cmax * 2, dtype=torch.float32, device=self.device) for _ in range(4)]
         self.tick = [torch.zeros(16 * n, dtype=torch.int32, device=self.device) for _ in range(4)]
-        self.gn_fusion_min = int(os.environ.get("DIQT_GN_FUSION_MIN", str(1 << 22)))   # voxels x input channels; variable: A/B, tests
+        self.gn_fusion_min = int(os.environ.get("DIQT_GN_FUSION_MIN", str(1 << 21)))   # voxels x input channels; variable: A/B, tests
         self.fuse_gn = self.grouped and self.dtype == "bf16" and os.environ.get("DIQT_DISABLE_GN_FUSION", "0") != "1"   # variable: A/B
         # larger batches: statistics are finalised by diqt_gn_finalize into (aff_a, aff_b) and the conv applies that affine + Mish
         self.fuse_gn_affine = (not self.grouped and self.sub_f <= 1 and self.dtype == "bf16" and os.environ.get("DIQT_DISABLE_GN_FUSION", "0") != "1")
@@ -353,9 +353,9 @@ class UnetEngine:
             film_off = film_slot(blk)
 
             def worth_fusing(ci):
-                # measured (profiles/conv_gn_r2c.jsonl): the fused conv beats apply + conv from 32^3 x 128 channels up (64^3 x 64: 52.7 vs
-                # 62.7 us); on smaller tensors the normalisation latency in front of the first MMA of every short z-segment costs more than
-                # the 5-8 us apply kernel it replaces
+                # measured (profiles/conv_gn_r2c.jsonl, r2q A/B): the fused conv beats apply + conv clearly from 32^3 x 128 channels up
+                # (64^3 x 64: 51 vs 62 us), is level at 32^3 x 64 (whole step 2.214 vs 2.221 ms with those fused too) and loses on smaller
+                # tensors, where the normalisation latency in front of the first MMA of every short z-segment exceeds the 5-8 us apply kernel
                 return self.n * vox * ci >= self.gn_fusion_min
 
             def norm_conv(cname, src: Act, gmod, f_off, ci, dst: Act, weight, bias, si):

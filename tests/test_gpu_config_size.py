@@ -47,11 +47,13 @@ def test_config2_forward_bf16_against_the_oracle_with_taps():
     t = torch.tensor([1.3])
     got = unet(x.cuda(), None, t.cuda(), lowres_cond_img=lr.cuda()).cpu()
     eng = next(iter(unet._engines.values()))
-    # every Block.project of the forward (38 of the 39 3x3x3 convs; the 39th is init_conv) runs the z-march kernel at this size, everything else with C % 64 == 0 the per-tap kernel
+    # the Block.project convs of the 64^3 and 32^3 levels (32 of the 38) run the z-march kernel, those of the 16^3 level the per-tap kernel
+    # with split-K, everything else with C % 64 == 0 the per-tap kernel, init_conv its own fused tcgen05 kernel
     zm = [k for k, v in eng.conv_impls.items() if v == lib.IMPL_ZM]
-    assert len(zm) == 38 and all(k.endswith(".project") for k in zm)
-    # GroupNorm + FiLM + Mish ride on the conv's load path at the full-resolution level and on the 128-channel convs of the 32^3 level
-    assert len(eng.fused_gn) == 20 + 6, len(eng.fused_gn)
+    assert len(zm) == 32 and all(k.endswith(".project") for k in zm)
+    assert len(eng.split_k) == 6 and eng.init_conv_fused
+    # GroupNorm + FiLM + Mish ride on the conv's load path at the 64^3 and 32^3 levels
+    assert len(eng.fused_gn) == 20 + 12, len(eng.fused_gn)
     taps = {}
     with torch.no_grad():
         want = unet_forward(sd, spec_from_kwargs(DRIVER), x, t, lowres_cond_img=lr, taps=taps)

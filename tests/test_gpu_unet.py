@@ -48,29 +48,36 @@ def test_driver_config_uses_tcgen05_kernels():
     unet(x.cuda(), None, time.cuda(), lowres_cond_img=lr.cuda())
     eng = next(iter(unet._engines.values()))
     tc = [k for k, v in eng.conv_impls.items() if v in (lib.IMPL_TC, lib.IMPL_ZM)]
-    assert len(tc) == len(eng.conv_impls) == 47 - 1   # every conv except final_conv (39 + 8); init_conv runs as im2col + 1x1x1
-    # the 3x3x3 convs whose volume fits the 16 x 8 plane tile (here: the 16^3 level) run the z-march kernel, 1x1x1 / up / down the per-tap one
-    zm = [k for k, v in eng.conv_impls.items() if v == lib.IMPL_ZM]
-    assert len(zm) == 20 and all(k.endswith(".project") for k in zm)
+    assert len(tc) == len(eng.conv_impls) == 47 - 1   # every conv except final_conv (39 + 8); init_conv is one fused tcgen05 kernel
+    # at this test size every level has fewer 128-voxel tiles than half the SMs: all 38 3x3x3 convs run the per-tap kernel with split-K
+    # (the z-march kernel takes over from 32^3 up, tests/test_gpu_config_size.py)
+    assert sorted(eng.split_k) == sorted(k for k in eng.conv_impls if k.endswith(".project"))
+    assert len(eng.split_k) == 38
 
 
 def test_fused_input_groupnorm_equals_the_two_kernel_path(monkeypatch):
     """Every Block.project the z-march family takes applies GroupNorm + FiLM + Mish on its own load path (no separate apply kernel, no
-    normalised copy of the tensor); the forward must not change by a single bit against the two-kernel path."""
-    case = FORWARD_CASES["driver_dim64_s16"]
-    x, lr, time = (t.cuda() for t in build_inputs(case))
+    normalised copy of the tensor); the forward must not change by a single bit against the two-kernel path.  Driver U-Net on a 32^3
+    patch: the twenty 3x3x3 convs of the full-resolution level run the z-march kernel."""
+    from diffusioniqt_b200 import Unet
+    from diffusioniqt_b200.synth import synthetic_field, synthetic_state_dict
+    kw = dict(FORWARD_CASES["driver_dim64_s16"]["unet"], img_size=32)
+    sd = synthetic_state_dict({k: tuple(v.shape) for k, v in Unet(**kw).state_dict().items()}, seed=17)
+    x, lr = synthetic_field((1, 1, 32, 32, 32), 5).cuda(), synthetic_field((1, 1, 32, 32, 32), 6).cuda()
+    time = torch.tensor([0.7], device="cuda")
     outs, launches = [], []
     for disable in ("1", "0"):
         monkeypatch.setenv("DIQT_DISABLE_GN_FUSION", disable)
         monkeypatch.setenv("DIQT_GN_FUSION_MIN", "0")       # the engine only fuses from 32^3 x 128 channels up by default (where it pays)
-        unet = _gpu_unet(case, "bf16")
+        unet = Unet(**kw)
+        unet.load_state_dict(sd)
+        unet = unet.cuda().set_compute_dtype("bf16")
         outs.append(unet(x, None, time, lowres_cond_img=lr))
         eng = next(iter(unet._engines.values()))
         launches.append(len(eng._ops))
         if disable == "1":
             assert eng.fused_gn == []
         else:
-            # the twelve + eight 3x3x3 convs of the 16^3 level (the only level whose planes fit the 16 x 8 tile at this test size)
             assert len(eng.fused_gn) == 20 and all(k.endswith(".project") for k in eng.fused_gn)
     assert torch.equal(outs[0], outs[1])
     assert launches[1] == launches[0] - 20          # one launch less per fused conv
