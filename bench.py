@@ -224,26 +224,36 @@ def time_dominant_kernel(size, batch, reps=20):
 
 
 def time_elementwise_kernel(size, batch, reps=20):
-    """The bandwidth-bound companion of the dominant kernel: GroupNorm + FiLM + Mish apply (y = mish(a*x + b), 1 read + 1 write) over a
-    64-channel full-resolution tensor, alone, CUDA events, rotating buffers (each 32 MiB at 64^3)."""
+    """The bandwidth-bound companion of the dominant kernel, as the step launches it: the SE / residual pass of a ResnetBlock
+    (out = h * sigmoid(W2 relu(W1 mean(h))) + x, plus the channel statistics of `out` for the next GroupNorm; SE3D :617-632, :612) over a
+    64-channel full-resolution tensor: 2 reads + 1 write, alone, rotating buffers (each 32 MiB at 64^3), graph replay, CUDA events."""
+    import ctypes as C
     from diffusioniqt_b200 import lib as L
     lib = L.load()
     dev = torch.device("cuda")
     n, c = batch, 64
     vox = size ** 3
-    bufs = [(torch.randn(n * vox, c, device=dev).bfloat16(), torch.empty(n * vox, c, device=dev, dtype=torch.bfloat16)) for _ in range(4)]
-    a = torch.rand(n * c, device=dev) + 0.5
-    b = torch.randn(n * c, device=dev) * 0.1
-    nblk = max(1, 592 // n)
+    nb = 4
+    hs = [torch.randn(n * vox, c, device=dev).bfloat16() for _ in range(nb)]
+    xs = [torch.randn(n * vox, c, device=dev).bfloat16() for _ in range(nb)]
+    outs = [torch.empty(n * vox, c, device=dev, dtype=torch.bfloat16) for _ in range(nb)]
+    hidden = c // 16
+    w1, w2 = torch.randn(hidden, c, device=dev) * 0.1, torch.randn(c, hidden, device=dev) * 0.1
+    nblk = max(1, min(vox // 128, 148 // n))
+    ng = C.c_int(0)
+    L.check(lib.diqt_stats_groups(nblk, 1, C.byref(ng)))
+    part, grp, tick = torch.zeros(n * nblk * c * 2, device=dev), torch.zeros(16 * n * c * 2, device=dev), torch.zeros(16 * n, dtype=torch.int32, device=dev)
+    L.check(lib.diqt_channel_stats_g(hs[0].data_ptr(), L.BF16, n, vox, c, c, nblk, part.data_ptr(), grp.data_ptr(), tick.data_ptr(), L.current_stream()))
+    opart, ogrp, otick = torch.zeros(n * nblk * c * 2, device=dev), torch.zeros(16 * n * c * 2, device=dev), torch.zeros(16 * n, dtype=torch.int32, device=dev)
 
     def run(i, st):
-        x, y = bufs[i % len(bufs)]
-        L.check(lib.diqt_affine_mish(x.data_ptr(), c, y.data_ptr(), c, L.BF16, n, vox, c, a.data_ptr(), b.data_ptr(), nblk, 0, 0, st))
+        i %= nb
+        L.check(lib.diqt_scale_residual_g(hs[i].data_ptr(), c, xs[i].data_ptr(), c, outs[i].data_ptr(), c, L.BF16, n, vox, c, grp.data_ptr(), ng.value, hidden,
+                                          w1.data_ptr(), w2.data_ptr(), nblk, opart.data_ptr(), ogrp.data_ptr(), otick.data_ptr(), st))
 
-    for i in range(4):
+    for i in range(nb):
         run(i, L.current_stream())
     torch.cuda.synchronize()
-    # a ~15 us kernel is shorter than a Python launch: replay `reps` launches as one CUDA graph so the host is out of the measurement
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
         for i in range(reps):
@@ -257,7 +267,7 @@ def time_elementwise_kernel(size, batch, reps=20):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / (3 * reps)
-    nbytes = 2.0 * n * vox * c * 2
+    nbytes = 3.0 * n * vox * c * 2
     return dict(ms=ms, bytes=nbytes, gbs=nbytes / (ms * 1e-3) / 1e9)
 
 
@@ -565,10 +575,12 @@ def main():
                         peak_source=peaks["source"] + " (burst: kernel timed alone)",
                         whole_step=dict(achieved=step_tflops, peak=peaks["sustained"], frac=step_tflops / peaks["sustained"], unit="TFLOP/s",
                                         note="all FLOPs of the U-Net / wall time of the sampler, per GPU, vs sustained bf16 peak"))
-        roofline_hbm = dict(bound="hbm", kernel="affine_mish_kernel (GroupNorm+FiLM+Mish apply) 64 ch @%d^3 (batch %d)" % (S, B), achieved=ew["gbs"],
-                            peak=peaks["hbm"], unit="GB/s", frac=ew["gbs"] / peaks["hbm"], ms_per_launch=ew["ms"], bytes_per_launch=ew["bytes"],
-                            note="second-largest kernel class of the step (38 launches per iteration); algorithmic bytes = 1 read + 1 write, 20 launches "
-                                 "over rotating buffers replayed as one CUDA graph, CUDA events around the replays")
+        roofline_hbm = dict(bound="hbm", kernel="scale_residual_ring_kernel (SE gate + h*gate + residual + statistics) 64 ch @%d^3 (batch %d)" % (S, B),
+                            achieved=ew["gbs"], peak=peaks["hbm"], unit="GB/s", frac=ew["gbs"] / peaks["hbm"], ms_per_launch=ew["ms"],
+                            bytes_per_launch=ew["bytes"],
+                            note="second-largest kernel class of the step (19 launches per iteration; the GroupNorm apply now rides on the convs); "
+                                 "algorithmic bytes = 2 reads + 1 write, 20 launches over rotating buffers replayed as one CUDA graph, CUDA events around "
+                                 "the replays")
         line = dict(metric="3D patches/sec (full denoise loop)", value=value, unit="patches/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
                     config=workload_config(args), clocks=clk,

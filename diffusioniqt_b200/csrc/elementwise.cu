@@ -8,7 +8,7 @@
 
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace diqt {
 
@@ -428,6 +428,148 @@ __global__ void scale_residual_kernel(const T* __restrict__ h, int ld_h, const T
   }
 }
 
+
+// ---- out = h * gate + res through a shared-memory ring fed by bulk copies --------------------------------------------------------
+// The register-staged kernel above keeps 8 x 16 bytes per thread in flight only while its threads are not computing or storing:
+// 100 MB (64^3 x 64 channels: two reads + one write) took 24.7 us = 0.62 of the measured HBM peak (profiles/bench_residual_r2s.jsonl).
+// Here one producer lane streams 16 KB tiles of h and res into a ring of RS_STAGES stages with cp.async.bulk (up to 160 KB in flight
+// per SM, independent of what the other warps do), eight consumer warps multiply, store and accumulate the statistics, and the
+// squeeze-excitation gate is worked out by the consumers while the first stages are already landing.  bf16, contiguous h / res rows.
+constexpr int RS_STAGES = 5, RS_TILE_BYTES = 16384, RS_CONSUMERS = 256;
+
+__global__ void __launch_bounds__(RS_CONSUMERS + 32, 1)
+scale_residual_ring_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloat16* __restrict__ res, __nv_bfloat16* __restrict__ out, int ld_out,
+                           int64_t voxels, int c, int64_t vpb, const float* __restrict__ gate, float* __restrict__ partial, SeParams se, StatsGroups og) {
+  extern __shared__ __align__(1024) uint8_t ring_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>(((uintptr_t)ring_raw + 127) & ~(uintptr_t)127);   // [RS_STAGES][2][RS_TILE_BYTES]
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)RS_STAGES * 2 * RS_TILE_BYTES);
+  uint64_t* empty = full + RS_STAGES;
+  float* scratch = reinterpret_cast<float*>(empty + RS_STAGES);   // SE scratch, later the block reduction
+  const int warp = threadIdx.x >> 5, lane_id = threadIdx.x & 31;
+  const int blk = blockIdx.x, n = blockIdx.y, nblk = gridDim.x;
+  const int64_t v0 = (int64_t)blk * vpb, v1 = min(voxels, v0 + vpb);
+  const int tile_rows = RS_TILE_BYTES / (c * 2);
+  const int ntiles = v1 > v0 ? (int)((v1 - v0 + tile_rows - 1) / tile_rows) : 0;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RS_STAGES; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), RS_CONSUMERS / 32); }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (warp == RS_CONSUMERS / 32) {
+    // ===================== producer =====================
+    if (lane_id == 0) {
+      pdl_sync();
+      const __nv_bfloat16* hb = h + ((int64_t)n * voxels + v0) * c;
+      const __nv_bfloat16* rb = res + ((int64_t)n * voxels + v0) * c;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int64_t r0 = (int64_t)t * tile_rows;
+        const uint32_t bytes = (uint32_t)(min((int64_t)tile_rows, (v1 - v0) - r0) * c * 2);
+        mbar_wait(smem_u32(&empty[stage]), phase ^ 1);
+        const uint32_t bar = smem_u32(&full[stage]);
+        mbar_expect_tx(bar, 2 * bytes);
+        bulk_load(smem_u32(ring + (size_t)(stage * 2) * RS_TILE_BYTES), hb + r0 * c, bytes, bar);
+        bulk_load(smem_u32(ring + (size_t)(stage * 2 + 1) * RS_TILE_BYTES), rb + r0 * c, bytes, bar);
+        if (++stage == RS_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    return;   // (no block-wide barrier below: the consumers synchronise among themselves)
+  }
+  // ===================== consumers (warps 0..7) =====================
+  const int tid = threadIdx.x;
+  auto csync = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+  const int nvec = c / 8, lanes = RS_CONSUMERS / nvec;
+  const int col = tid % nvec, lane = tid / nvec;
+  float g[8], s[8], q[8];
+  if (se.group) {
+    const int slices = max(1, RS_CONSUMERS / c);
+    double* part = reinterpret_cast<double*>(scratch);
+    double* tot = part + (size_t)slices * c * 2;
+    float* mean = reinterpret_cast<float*>(tot + (size_t)c * 2);
+    float* hid = mean + c;
+    float* gs = hid + se.hidden;
+    pdl_wait();
+    group_channel_totals(se.group, se.ngroups, c, n, tid, RS_CONSUMERS, part, tot, csync);
+    for (int ch = tid; ch < c; ch += RS_CONSUMERS) mean[ch] = (float)(tot[2 * ch] / (double)voxels);
+    csync();
+    const int nwarps = RS_CONSUMERS / 32;
+    for (int j = warp; j < se.hidden; j += nwarps) {
+      float acc = 0.f;
+      for (int k = lane_id; k < c; k += 32) acc = fmaf(se.w1[(int64_t)j * c + k], mean[k], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane_id == 0) hid[j] = fmaxf(acc, 0.f);
+    }
+    csync();
+    for (int ch = tid; ch < c; ch += RS_CONSUMERS) {
+      float acc = 0.f;
+      for (int j = 0; j < se.hidden; ++j) acc = fmaf(se.w2[(int64_t)ch * se.hidden + j], hid[j], acc);
+      gs[ch] = 1.f / (1.f + expf(-acc));
+    }
+    csync();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = gs[col * 8 + i];
+    csync();  // the scratch is reused by the block reduction
+  } else {
+    pdl_wait();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = gate ? __ldcg(gate + (int64_t)n * c + col * 8 + i) : 1.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  __nv_bfloat16* ob = out + ((int64_t)n * voxels + v0) * ld_out + col * 8;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int t = 0; t < ntiles; ++t) {
+    const int64_t r0 = (int64_t)t * tile_rows;
+    const int rows = (int)min((int64_t)tile_rows, (v1 - v0) - r0);
+    mbar_wait(smem_u32(&full[stage]), phase);
+    const uint8_t* hs = ring + (size_t)(stage * 2) * RS_TILE_BYTES + (size_t)col * 16;
+    const uint8_t* rs = hs + RS_TILE_BYTES;
+    for (int r = lane; r < rows; r += lanes) {
+      Vec<__nv_bfloat16> a, x, o;
+      a.unpack(*reinterpret_cast<const uint4*>(hs + (size_t)r * c * 2));
+      x.unpack(*reinterpret_cast<const uint4*>(rs + (size_t)r * c * 2));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = fmaf(a.v[i], g[i], x.v[i]);
+      o.store(ob + (r0 + r) * ld_out);
+      if (partial) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float w = to_float(from_float<__nv_bfloat16>(o.v[i]));   // what the next GroupNorm will read: the stored, rounded value
+          s[i] += w;
+          q[i] = fmaf(w, w, q[i]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane_id == 0) mbar_arrive(smem_u32(&empty[stage]));
+    if (++stage == RS_STAGES) { stage = 0; phase ^= 1; }
+  }
+  if (partial) {
+    // per-CTA reduction of the per-thread channel sums, fixed order (as block_channel_reduce, over the consumer threads only)
+    float* ss = scratch;
+    float* sq = scratch + (size_t)lanes * c;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ss[lane * c + col * 8 + i] = s[i];
+      sq[lane * c + col * 8 + i] = q[i];
+    }
+    csync();
+    float* dst = partial + ((int64_t)n * nblk + blk) * c * 2;
+    for (int ch = tid; ch < c; ch += RS_CONSUMERS) {
+      float a = 0.f, b = 0.f;
+      for (int l = 0; l < lanes; ++l) { a += ss[l * c + ch]; b += sq[l * c + ch]; }
+      dst[2 * ch] = a;
+      dst[2 * ch + 1] = b;
+    }
+    StatsGroups ov = og;
+    if (ov.group) { ov.group += (int64_t)n * og.ngroups * c * 2; ov.tickets += n * og.ngroups; }
+    stats_group_tail(ov, partial + (int64_t)n * nblk * c * 2, 1, nblk, c, blk, 1, tid, RS_CONSUMERS, reinterpret_cast<int*>(scratch + 2 * (size_t)lanes * c), csync);
+  }
+}
+
 // ---- dst = src * scale  (row-pitched copy; the scaled skip connection, imagen_pytorch3D.py:1346, 1653) ----------
 template <typename T>
 __global__ void scale_copy_kernel(const T* __restrict__ src, int ld_src, T* __restrict__ dst, int ld_dst, int64_t rows,
@@ -582,6 +724,27 @@ static int scale_residual_impl(const void* h, int ld_h, const void* res, int ld_
   DIQT_REQUIRE(h && res && out && nblk > 0, "scale_residual: bad arguments");
   DIQT_REQUIRE(c % vec == 0 && ld_h % vec == 0 && ld_res % vec == 0 && ld_out % vec == 0 && c / vec <= 256,
                "scale_residual: c=%d not a multiple of %d", c, vec);
+  cudaStream_t st0 = (cudaStream_t)stream;
+  static int ring_env = -1;
+  if (ring_env < 0) { const char* e = getenv("DIQT_DISABLE_RESIDUAL_RING"); ring_env = (e && e[0] == '1') ? 0 : 1; }
+  // bf16, plain volumes, contiguous input rows, channel counts whose 16 KB tiles split evenly over the 256 consumer threads
+  if (ring_env && dtype == DIQT_BF16 && sub_f <= 1 && ld_h == c && ld_res == c && c % 8 == 0 && (c == 64 || c == 128 || c == 256) && voxels / nblk >= 128) {
+    const int lanes = RS_CONSUMERS / (c / 8);
+    size_t scratch = (size_t)2 * lanes * c * sizeof(float) + 64;
+    if (se.group) {
+      const int slices = RS_CONSUMERS / c > 0 ? RS_CONSUMERS / c : 1;
+      scratch = std::max(scratch, ((size_t)slices * c * 2 + (size_t)c * 2) * sizeof(double) + ((size_t)2 * c + se.hidden) * sizeof(float));
+    }
+    const size_t sh = (size_t)RS_STAGES * 2 * RS_TILE_BYTES + 2 * RS_STAGES * sizeof(uint64_t) + scratch + 256;
+    static bool attr_done = false;
+    if (!attr_done) {
+      DIQT_CUDA(cudaFuncSetAttribute(scale_residual_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_done = true;
+    }
+    launch_pdl(scale_residual_ring_kernel, dim3(nblk, n), RS_CONSUMERS + 32, sh, st0, (const __nv_bfloat16*)h, (const __nv_bfloat16*)res, (__nv_bfloat16*)out,
+               ld_out, voxels, c, vox_per_block(voxels, nblk), gate, partial, se, og);
+    return check_launch("scale_residual");
+  }
   RowMap m = make_rowmap(c, vec, 512);  // one 512-thread CTA per SM; 2 x 256 or 4 x 256 threads per SM measured no better (r1s A/B)
   dim3 grid(nblk, n);
   size_t sh = partial ? (size_t)2 * m.lanes * c * sizeof(float) : 0;

@@ -310,6 +310,28 @@ def test_se_scale_residual(dtype, tol, grouped):
     assert max_rel(s[..., 1], (stored ** 2).sum(dim=(2, 3, 4))) < 1e-4
 
 
+@pytest.mark.parametrize("grouped", [False, True])
+@pytest.mark.parametrize("n,c,dims,nblk", [(1, 64, (32, 32, 32), 37), (2, 128, (16, 16, 24), 8), (1, 256, (8, 16, 16), 4), (1, 64, (17, 16, 16), 5),
+                                            (1, 64, (64, 64, 64), 148)])
+def test_se_scale_residual_ring_kernel(n, c, dims, nblk, grouped, monkeypatch):
+    """The bulk-copy ring version of the SE / residual pass (bf16, contiguous rows, >= 256 voxels per CTA) against fp32 PyTorch, and
+    against the register-staged kernel: the same products and roundings -> the same stored bits; statistics equal up to summation order.
+    (17, 16, 16) with 5 CTAs leaves ragged last tiles."""
+    import importlib
+    from diffusioniqt_b200 import ops
+    h, r = _rand(n, c, *dims, seed=81).bfloat16().float(), _rand(n, c, *dims, seed=82).bfloat16().float()
+    w1, w2 = _rand(c // 16, c, seed=83, scale=0.3), _rand(c, c // 16, seed=84, scale=0.8)
+    y = torch.sigmoid(F.linear(torch.relu(F.linear(h.mean(dim=(2, 3, 4)), w1)), w2))
+    want = h * y[:, :, None, None, None] + r
+    hg, rg = ops.to_channels_last(h.cuda(), torch.bfloat16), ops.to_channels_last(r.cuda(), torch.bfloat16)
+    out, gate, part = ops.se_scale_residual(hg, rg, w1, w2, nblk=nblk, grouped=grouped)
+    stored = ops.from_channels_last(out).cpu()
+    assert max_rel(stored, want) < BF16_TOL
+    s = part.sum(dim=1).cpu()
+    assert max_rel(s[..., 0], stored.sum(dim=(2, 3, 4))) < 1e-4
+    assert max_rel(s[..., 1], (stored ** 2).sum(dim=(2, 3, 4))) < 1e-4
+
+
 def test_grouped_statistics_sum_to_the_partial_rows():
     """Group rows are sums of consecutive partial rows (fixed order); several group sizes incl. a ragged last group; tickets reset."""
     from diffusioniqt_b200 import ops
