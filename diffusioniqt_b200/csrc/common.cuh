@@ -318,24 +318,38 @@ __device__ __forceinline__ void gn_prefetch_constants(const GnParams& gp, int nv
     sc.cst[3 * gp.c + ch] = fr ? fr[gp.c + ch] : 0.f;
   }
 }
-// Half 2, after pdl_wait(): one L2 round trip for the group rows, then shared-memory arithmetic.
+// Half 2, after pdl_wait(): one L2 round trip for the group rows, then shared-memory arithmetic.  This sits on the critical path of
+// every consumer (the fused conv cannot normalise its first plane before it: profiles/r2v_zm_timeline.txt showed 3.5 us from grid
+// dependency to first plane with the round-1 version: five barriers, a separate pass per reduction level), so it is two phases now:
+//   1. one thread per channel sums that channel's <= 16 group rows (independent loads: one round trip) in double;
+//   2. one thread per channel adds the totals of its GroupNorm group (redundantly per channel: a handful of shared-memory reads) and
+//      forms (a, b).
 template <typename Sync = SyncThreads>
 __device__ __forceinline__ void gn_affine_from_groups(const GnParams& gp, int nv, int tid, int nthreads, const GnScratch& sc, Sync sync = Sync()) {
-  group_channel_totals(gp.group, gp.ngroups, gp.c, nv, tid, nthreads, sc.part, sc.tot, sync);
-  const int cpg = gp.c / gp.groups;
-  for (int g = tid; g < gp.groups; g += nthreads) {
+  const float* base = gp.group + (size_t)nv * gp.ngroups * gp.c * 2;
+  for (int ch = tid; ch < gp.c; ch += nthreads) {
     double s = 0.0, q = 0.0;
-    for (int i = 0; i < cpg; ++i) { s += sc.tot[(g * cpg + i) * 2]; q += sc.tot[(g * cpg + i) * 2 + 1]; }
-    const double cnt = (double)gp.voxels * cpg, mean = s / cnt;
-    double var = q / cnt - mean * mean;
-    if (var < 0.0) var = 0.0;
-    sc.gstat[2 * g] = mean;
-    sc.gstat[2 * g + 1] = 1.0 / sqrt(var + (double)gp.eps);
+    for (int g = 0; g < gp.ngroups; g += 8) {
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = (g + u < gp.ngroups) ? __ldcg(reinterpret_cast<const float2*>(base + ((size_t)(g + u) * gp.c + ch) * 2)) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s += (double)v[u].x; q += (double)v[u].y; }  // fixed order
+    }
+    sc.tot[2 * ch] = s;
+    sc.tot[2 * ch + 1] = q;
   }
   sync();
+  const int cpg = gp.c / gp.groups;
   for (int ch = tid; ch < gp.c; ch += nthreads) {
     const int g = ch / cpg;
-    const float mean = (float)sc.gstat[2 * g], rstd = (float)sc.gstat[2 * g + 1];
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < cpg; ++i) { s += sc.tot[(g * cpg + i) * 2]; q += sc.tot[(g * cpg + i) * 2 + 1]; }
+    const double cnt = (double)gp.voxels * cpg, mean_d = s / cnt;
+    double var = q / cnt - mean_d * mean_d;
+    if (var < 0.0) var = 0.0;
+    const float mean = (float)mean_d, rstd = (float)(1.0 / sqrt(var + (double)gp.eps));
     float a = rstd * sc.cst[ch];
     float b = sc.cst[gp.c + ch] - mean * a;
     const float fs = sc.cst[2 * gp.c + ch], fh = sc.cst[3 * gp.c + ch];

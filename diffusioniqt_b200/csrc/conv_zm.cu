@@ -50,6 +50,18 @@ namespace diqt {
 #define DIQT_XF_MODE 0
 #endif
 
+// DIQT_ZM_TRACE (build-time, diagnostics only): CTA 0 records clock64() at the hand-over points of its pipeline into g_zm_trace
+// [event][slot][plane iteration]; tools/zm_trace.py prints the timeline (profiles/r2_zm_timeline.md).
+#ifndef DIQT_ZM_TRACE
+#define DIQT_ZM_TRACE 0
+#endif
+#if DIQT_ZM_TRACE
+__device__ long long g_zm_trace[8 * 2 * 16];
+#define ZM_TRACE(ev, slot, it) do { if (blockIdx.x == 0 && (it) < 16) g_zm_trace[((ev) * 2 + (slot)) * 16 + (it)] = clock64(); } while (0)
+#else
+#define ZM_TRACE(ev, slot, it) do { } while (0)
+#endif
+
 constexpr int ZM_TX = 8, ZM_TY = 16;                    // output tile of one plane: 16 (y) x 8 (x) = 128 GEMM rows
 constexpr int ZM_PLANE_BYTES = (ZM_TY + 2) * (ZM_TX + 2) * 128;  // 180 haloed rows x 64 bf16 = 23040
 constexpr int ZM_PLANE_STRIDE = 23552;                  // next multiple of 1024
@@ -301,6 +313,7 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
               if (i >= it.niter) continue;
               const int b = s * ZM_RING + ring[s];
               mbar_wait(smem_u32(&pl_empty[b]), phase[s] ^ 1);
+              ZM_TRACE(0, s, i);
               if (k2 && !kGN) {
                 // the issuer (leader CTA) waits for BOTH CTAs' planes on its own barrier; with kGN the transform warps of each CTA wait
                 // on their local barrier instead and report to the leader's pl_ready
@@ -411,6 +424,7 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
           uint32_t a_base = 0;
           if (act) {
             mbar_wait_any(smem_u32(kGN ? &pl_ready[s * ZM_RING + ring] : &pl_full[s * ZM_RING + ring]), rphase);
+            if (lane == 0) ZM_TRACE(3, s, i);
             a_base = smem_u32(planes + (size_t)(s * ZM_RING + ring) * ZM_PLANE_STRIDE);
           }
           tc_fence_after();
@@ -442,6 +456,7 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
             if (++stage == ZM_WSTAGES) { stage = 0; wphase ^= 1; }
           }
           if (act) {
+            if (lane == 0) ZM_TRACE(4, s, i);
             commit(smem_u32(&pl_empty[s * ZM_RING + ring]));
             if (++ring == ZM_RING) { ring = 0; rphase ^= 1; }
           }
@@ -516,6 +531,7 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
           const int k = kcount[s];
           const float* bias = s_bias + it.nh * 64;
           mbar_wait(smem_u32(&acc_full[s * 2 + (k & 1)]), (uint32_t)((k >> 1) & 1));
+          if (et == 0) ZM_TRACE(5, s, i);
           tc_fence_after();
           // outputs whose last contributing input plane is pl:  z = pl-1, and z = pl at the top face of the volume
           for (int which = 0; which < 2; ++which) {
@@ -565,6 +581,7 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
           tmem_st_wait();
           tc_fence_before();
           __syncwarp();
+          if (et == 0) ZM_TRACE(6, s, i);
           if (lane == 0) {
             if (k2) mbar_arrive_cluster(to_leader(&acc_free[s * 2 + (k & 1)]));
             else mbar_arrive(smem_u32(&acc_free[s * 2 + (k & 1)]));
@@ -604,15 +621,14 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
       gn_prefetch_constants(p.gn, 0, tt, 256, sc);  // constants of volume 0 while the producer kernel is still draining
       pdl_wait();
       for (int nv = 0; nv < p.n; ++nv) {
-        if (nv > 0) gn_prefetch_constants(p.gn, nv, tt, 256, sc);
-        sync256();
+        if (nv > 0) gn_prefetch_constants(p.gn, nv, tt, 256, sc);   // (every thread reads back only the constants it wrote itself)
         gn_affine_from_groups(p.gn, nv, tt, 256, sc, sync256);
-        for (int ch = tt; ch < c_in; ch += 256) {
+        for (int ch = tt; ch < c_in; ch += 256) {                    // same thread -> channel mapping as inside: no barrier in between
           aff[nv * c_in + ch] = sc.a_s[ch];
           aff[(p.n + nv) * c_in + ch] = sc.b_s[ch];
         }
-        sync256();
       }
+      sync256();
     }
     // thread -> (physical 16-byte chunk pc, rows rbase + 32 k): the swizzled chunk holds logical chunk pc ^ (row & 7), and
     // (rbase + 32 k) & 7 == rbase & 7, so one thread always works on the same eight channels of a 64-channel chunk
@@ -662,6 +678,7 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
             const int b = s * ZM_RING + ring[s];
             const uint32_t vm = s ? vmask[1] : vmask[0];
             mbar_wait(smem_u32(&pl_full[b]), s ? phase[1] : phase[0]);
+            if (tt == 0) ZM_TRACE(1, s, i);
             uint8_t* base = planes + (size_t)b * ZM_PLANE_STRIDE + rbase * 128 + pc * 16;
 #if DIQT_XF_MODE == 1   // timing experiment: handshake only, the plane is handed on untouched
             if (false)
@@ -689,6 +706,7 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
             __syncwarp();
+            if (tt == 0) ZM_TRACE(2, s, i);
             if (lane == 0) {
               if (k2) mbar_arrive_cluster(to_leader(&pl_ready[b]));
               else mbar_arrive(smem_u32(&pl_ready[b]));
@@ -966,3 +984,9 @@ int conv_zm_set_stats(ZmPlan* plan, float* partial, float* group, unsigned int* 
 void conv_zm_destroy(ZmPlan* plan) { delete plan; }
 
 }  // namespace diqt
+
+#if DIQT_ZM_TRACE
+extern "C" int diqt_debug_zm_trace(long long* out) {
+  return cudaMemcpyFromSymbol(out, diqt::g_zm_trace, sizeof(diqt::g_zm_trace)) == cudaSuccess ? 0 : -1;
+}
+#endif
