@@ -26,11 +26,11 @@ constexpr int AT_VCHUNK = 64 * 128;                     // one [64 d rows][64 ke
 constexpr int AT_THREADS = 192;
 
 struct AttnTcParams {
-  CUtensorMap q_map, k_map, vt_map;
+  CUtensorMap q_map, k_map, vt_map, v_map;   // vt_map: transposed copy (two-pass kernel); v_map: V as it lies (single-pass kernel)
   __nv_bfloat16* out;
   int ld_out, ntok, heads, q_col0, k_col0, act;
   float c;  // scale * log2(e)
-  uint32_t idesc_s, idesc_o;
+  uint32_t idesc_s, idesc_o, idesc_o_mn;   // idesc_o_mn: B operand MN-major
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {  // arguments are <= 0 here
@@ -362,9 +362,9 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) softmax_attn_tc2_kernel(cons
         if (++ks == AT2_KSTAGES) { ks = 0; kph ^= 1; }
         mbar_wait(smem_u32(&v_empty[vs]), vph ^ 1);
         mbar_expect_tx(smem_u32(&v_full[vs]), 2 * AT_VCHUNK);
-        uint8_t* dst = v_s + vs * 2 * AT_VCHUNK;
-        tma_load_2d_as5(smem_u32(dst), &p.vt_map, smem_u32(&v_full[vs]), j * AT_K, head * AT_D);
-        tma_load_2d_as5(smem_u32(dst + AT_VCHUNK), &p.vt_map, smem_u32(&v_full[vs]), j * AT_K + 64, head * AT_D);
+        // V_j as it lies in memory: a [128 keys][64 d] box IS the MN-major SWIZZLE_128B B operand (N = d contiguous, eight-key groups
+        // 1024 B apart; see linattn_tc.cu), so the single-pass kernel needs no transposed copy; keys past the end arrive as zeros
+        tma_load_2d_as5(smem_u32(v_s + vs * 2 * AT_VCHUNK), &p.v_map, smem_u32(&v_full[vs]), head * AT_D, j * AT_K);
         if (++vs == AT2_VSTAGES) { vs = 0; vph ^= 1; }
       }
     }
@@ -407,8 +407,8 @@ __global__ void __launch_bounds__(128 * NQ + 64, 1) softmax_attn_tc2_kernel(cons
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {  // K = 16 keys per instruction: 8 TMEM columns of P, 32 bytes along the V^T rows
-          const uint64_t vdesc = make_sw128_desc(vb + (kk >> 2) * AT_VCHUNK) + (uint64_t)(2 * (kk & 3));
-          umma_bf16_ts(tmem_base + (uint32_t)(256 + i * 64), tmem_base + (uint32_t)(384 + i * 64 + kk * 8), vdesc, p.idesc_o, (j | kk) != 0);
+          const uint64_t vdesc = make_sw128_desc_sbo(vb + kk * 2048, 1024);   // 16 keys = two 8-key groups 1024 B apart
+          umma_bf16_ts(tmem_base + (uint32_t)(256 + i * 64), tmem_base + (uint32_t)(384 + i * 64 + kk * 8), vdesc, p.idesc_o_mn, (j | kk) != 0);
         }
         umma_commit(smem_u32(&pv_done[i]));
       }
@@ -752,6 +752,7 @@ extern "C" int diqt_attn_tc_plan_create(const void* q, const void* k, const void
   p.c = scale * 1.4426950408889634f;
   p.idesc_s = make_idesc_bf16(AT_Q, AT_K);
   p.idesc_o = make_idesc_bf16(AT_Q, AT_D);
+  p.idesc_o_mn = p.idesc_o | (1u << 16);
   // q / k: [tokens][ld] rows, the head's 64 channels are one 128-byte box row; v^T: [inner][npad]
   int rc = encode_volume_map(&p.q_map, q, inner, tokens, 1, 1, 1, ld_q, (int64_t)tokens * ld_q, (int64_t)tokens * ld_q, (int64_t)tokens * ld_q, AT_Q, 1, 1, 1);
   if (rc == DIQT_OK)
@@ -759,6 +760,8 @@ extern "C" int diqt_attn_tc_plan_create(const void* q, const void* k, const void
   if (rc == DIQT_OK)
     rc = encode_volume_map(&p.vt_map, workspace, a.npad, inner, 1, 1, 1, a.npad, (int64_t)inner * a.npad, (int64_t)inner * a.npad,
                            (int64_t)inner * a.npad, AT_D, 1, 1, 1);
+  if (rc == DIQT_OK)
+    rc = encode_volume_map(&p.v_map, v, inner, tokens, 1, 1, 1, ld_v, (int64_t)tokens * ld_v, (int64_t)tokens * ld_v, (int64_t)tokens * ld_v, AT_K, 1, 1, 1);
   if (rc != DIQT_OK) {
     delete pl;
     return rc;
@@ -801,8 +804,10 @@ extern "C" int diqt_attn_tc_run(const diqt_attn_plan* plan, void* stream) {
   const AttnTcPlan& a = plan->a;
   cudaStream_t st = (cudaStream_t)stream;
   const dim3 tgrid((a.p.ntok + 31) / 32, (a.inner + 31) / 32);
-  attn_transpose_kernel<<<tgrid, 256, 0, st>>>(a.v, a.ld_v, a.p.ntok, a.inner, a.vt, a.npad);
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (a.version == 1) {   // only the two-pass kernel reads the transposed copy
+    attn_transpose_kernel<<<tgrid, 256, 0, st>>>(a.v, a.ld_v, a.p.ntok, a.inner, a.vt, a.npad);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   if (a.version == 1) softmax_attn_tc_kernel<<<a.grid, AT_THREADS, a.smem, st>>>(a.p);
   else if (a.nq == 2) softmax_attn_tc2_kernel<2><<<a.grid, 128 * 2 + 64, a.smem, st>>>(a.p);
   else softmax_attn_tc2_kernel<1><<<a.grid, 128 + 64, a.smem, st>>>(a.p);

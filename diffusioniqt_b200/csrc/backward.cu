@@ -1,0 +1,374 @@
+// Backward kernels of the training step (Imagen.p_losses -> loss.backward() -> optimizer step; imagen_pytorch3D.py:2277-2387 and the
+// autograd graph PyTorch builds for Unet.forward :1554-1684).  Channels-last activations [n][voxels][c] with row pitch ld, fp32 or bf16
+// storage, fp32 math, every reduction in a fixed order (bitwise reproducible gradients).
+//
+// The reverse of one `Block` (GroupNorm -> FiLM -> Mish -> conv, :546-565) and of the SE gate / residual join (:612-632) needs exactly
+// two shapes of pass over an activation tensor:
+//   reduce : per (n, channel)   S1 = sum_v t ,  S2 = sum_v t * x       t = dz * mish'(a_c x + b_c)   (GroupNorm / FiLM / Mish)
+//                                                                      t = dz                        (SE gate: x = the gated tensor)
+//   apply  : out = c1 * t + c2 * x + c3 (+ acc)      with per-(n, channel) coefficients: the GroupNorm input gradient
+//            r (1+s) gamma dw - r m1 - r^2 m2 (x - mu), or  gate * dz + dmean / V  for the SE join; `acc` adds the residual branch.
+// The coefficients are a few (n, c) vectors derived from S1 / S2 on the host side of the C ABI (diffusioniqt_b200/train.py).
+// Weight gradients: conv_wgrad_simt (any shape, fp32 accumulation, per-chunk partials summed in a fixed order); the tcgen05 version for
+// channel counts that are multiples of 64 lives in wgrad_tc.cu.  Data gradients of the convolutions are convolutions with the flipped,
+// transposed weights and run through the forward kernels.
+#include "common.cuh"
+
+namespace diqt {
+
+namespace {
+
+struct BwMap {
+  int nvec, lanes, threads;
+};
+inline BwMap bw_map(int c, int vec, int max_threads) {
+  BwMap m;
+  m.nvec = c / vec;
+  m.lanes = max_threads / m.nvec;
+  if (m.lanes < 1) m.lanes = 1;
+  m.threads = m.nvec * m.lanes;
+  return m;
+}
+inline int64_t bw_vpb(int64_t voxels, int nblk) { return (voxels + nblk - 1) / nblk; }
+
+// d/dw [ w tanh(softplus(w)) ] = T + w sigma(w) (1 - T^2),  T = n / (n + 2),  n = u (u + 2),  u = e^w ;  1 - T^2 = 4 (n + 1) / (n + 2)^2
+__device__ __forceinline__ float mish_grad(float w) {
+  const float u = expf(fminf(w, 20.f));      // w > 20: T = 1 and the second term vanishes in fp32
+  const float n = u * (u + 2.f);
+  const float d = 1.f / (n + 2.f);
+  const float T = n * d;
+  const float sig = u / (1.f + u);
+  return fmaf(w * sig, 4.f * (n + 1.f) * d * d, T);
+}
+
+}  // namespace
+
+// ---- reduce: partial[n][blk][c][2] = (sum t, sum t * x) over the block's voxels ------------------------------------------------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* x, int ld_x, const T* dz, int ld_dz, int64_t voxels, int c, int nvec, int lanes,
+                                                         int64_t vpb, const float* a, const float* b, float* partial) {
+  constexpr int VEC = Vec<T>::N;
+  extern __shared__ float bw_smem[];
+  const int col = threadIdx.x % nvec, lane = threadIdx.x / nvec;
+  const int blk = blockIdx.x, n = blockIdx.y, nblk = gridDim.x;
+  const int64_t v0 = (int64_t)blk * vpb, v1 = min(voxels, v0 + vpb);
+  pdl_sync();
+  float av[VEC], bv[VEC], s1[VEC], s2[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    av[i] = MODE ? __ldcg(a + (int64_t)n * c + col * VEC + i) : 1.f;
+    bv[i] = MODE ? __ldcg(b + (int64_t)n * c + col * VEC + i) : 0.f;
+    s1[i] = s2[i] = 0.f;
+  }
+  const T* xb = x + (int64_t)n * voxels * ld_x + col * VEC;
+  const T* gb = dz + (int64_t)n * voxels * ld_dz + col * VEC;
+  for (int64_t v = v0 + lane; v < v1; v += 2 * (int64_t)lanes) {
+    Vec<T> xr[2], gr[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t vv = v + (int64_t)u * lanes;
+      if (vv < v1) {
+        xr[u].load(xb + vv * ld_x);
+        gr[u].load(gb + vv * ld_dz);
+      } else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) xr[u].v[i] = gr[u].v[i] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float t = MODE ? gr[u].v[i] * mish_grad(fmaf(av[i], xr[u].v[i], bv[i])) : gr[u].v[i];
+        s1[i] += t;
+        s2[i] = fmaf(t, xr[u].v[i], s2[i]);
+      }
+  }
+  float* ss = bw_smem;
+  float* sq = bw_smem + (size_t)lanes * c;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    ss[lane * c + col * VEC + i] = s1[i];
+    sq[lane * c + col * VEC + i] = s2[i];
+  }
+  __syncthreads();
+  float* out = partial + ((int64_t)n * nblk + blk) * c * 2;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float p = 0.f, q = 0.f;
+    for (int l = 0; l < lanes; ++l) {  // fixed order
+      p += ss[l * c + ch];
+      q += sq[l * c + ch];
+    }
+    out[2 * ch] = p;
+    out[2 * ch + 1] = q;
+  }
+}
+
+// ---- apply: out = c1 * t + c2 * x + c3 (+ acc) ------------------------------------------------------------------------------------
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) bwd_apply_kernel(const T* x, int ld_x, const T* dz, int ld_dz, const T* acc, int ld_acc, T* out, int ld_out,
+                                                        int64_t voxels, int c, int nvec, int lanes, int64_t vpb, const float* a, const float* b,
+                                                        const float* c1, const float* c2, const float* c3) {
+  constexpr int VEC = Vec<T>::N;
+  const int col = threadIdx.x % nvec, lane = threadIdx.x / nvec;
+  const int n = blockIdx.y;
+  const int64_t v0 = (int64_t)blockIdx.x * vpb, v1 = min(voxels, v0 + vpb);
+  pdl_sync();
+  float av[VEC], bv[VEC], k1[VEC], k2[VEC], k3[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const int64_t o = (int64_t)n * c + col * VEC + i;
+    av[i] = MODE ? __ldcg(a + o) : 1.f;
+    bv[i] = MODE ? __ldcg(b + o) : 0.f;
+    k1[i] = __ldcg(c1 + o);
+    k2[i] = c2 ? __ldcg(c2 + o) : 0.f;
+    k3[i] = c3 ? __ldcg(c3 + o) : 0.f;
+  }
+  const int64_t base = (int64_t)n * voxels;
+  for (int64_t v = v0 + lane; v < v1; v += lanes) {
+    Vec<T> xr, gr, ar, o;
+    gr.load(dz + (base + v) * ld_dz + col * VEC);
+    if (MODE || c2) xr.load(x + (base + v) * ld_x + col * VEC);
+    else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) xr.v[i] = 0.f;
+    }
+    if (acc) ar.load(acc + (base + v) * ld_acc + col * VEC);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float t = MODE ? gr.v[i] * mish_grad(fmaf(av[i], xr.v[i], bv[i])) : gr.v[i];
+      float r = fmaf(k1[i], t, fmaf(k2[i], xr.v[i], k3[i]));
+      if (acc) r += ar.v[i];
+      o.v[i] = r;
+    }
+    o.store(out + (base + v) * ld_out + col * VEC);
+  }
+}
+
+// ---- weight gradient, CUDA cores: partial[chunk][tap][c_out][c_in] over the chunk's voxels ---------------------------------------
+constexpr int WG_VT = 32;   // voxels per shared-memory tile
+template <typename T>
+__global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const T* x, int ld_x, const T* dy, int ld_dy, int n, int d0, int d1, int d2, int c_in,
+                                                              int c_out, int taps, int ci_tiles, int64_t vox_per_chunk, float* partial) {
+  __shared__ float dys[WG_VT][65], xs[WG_VT][65];
+  const int chunk = blockIdx.x, tap = blockIdx.y;
+  const int co0 = (blockIdx.z / ci_tiles) * 64, ci0 = (blockIdx.z % ci_tiles) * 64;
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+  const int oz = taps == 27 ? tap / 9 - 1 : 0, oy = taps == 27 ? (tap / 3) % 3 - 1 : 0, ox = taps == 27 ? tap % 3 - 1 : 0;
+  const int64_t vol = (int64_t)d0 * d1 * d2, total = vol * n;
+  const int64_t r0 = (int64_t)chunk * vox_per_chunk, r1 = min(total, r0 + vox_per_chunk);
+  pdl_sync();
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int64_t base = r0; base < r1; base += WG_VT) {
+    for (int idx = threadIdx.x; idx < WG_VT * 64; idx += 256) {
+      const int r = idx >> 6, ch = idx & 63;
+      const int64_t row = base + r;
+      float gv = 0.f, xv = 0.f;
+      if (row < r1) {
+        if (co0 + ch < c_out) gv = to_float(dy[row * ld_dy + co0 + ch]);
+        if (ci0 + ch < c_in) {
+          const int64_t vv = row % vol;
+          const int z = (int)(vv / ((int64_t)d1 * d2)), y = (int)((vv / d2) % d1), xx = (int)(vv % d2);
+          const int zz = z + oz, yy = y + oy, xq = xx + ox;
+          if ((unsigned)zz < (unsigned)d0 && (unsigned)yy < (unsigned)d1 && (unsigned)xq < (unsigned)d2)
+            xv = to_float(x[(row + ((int64_t)oz * d1 + oy) * d2 + ox) * ld_x + ci0 + ch]);
+        }
+      }
+      dys[r][ch] = gv;
+      xs[r][ch] = xv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < WG_VT; ++r) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        av[i] = dys[r][ty * 4 + i];
+        bv[i] = xs[r][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* dst = partial + ((int64_t)chunk * taps + tap) * c_out * c_in;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + ty * 4 + i, ci = ci0 + tx * 4 + j;
+      if (co < c_out && ci < c_in) dst[(int64_t)co * c_in + ci] = acc[i][j];
+    }
+}
+
+// dw[c_out][c_in][taps] = sum_chunks partial[chunk][tap][c_out][c_in]  (fixed order; the layout of nn.Conv3d.weight)
+__global__ void __launch_bounds__(256) conv_wgrad_reduce_kernel(const float* partial, int nchunks, int taps, int c_out, int c_in, float* dw) {
+  pdl_sync();
+  const int64_t per = (int64_t)c_out * c_in, count = per * taps;
+  for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < count; idx += (int64_t)gridDim.x * 256) {
+    const int tap = (int)(idx / per);
+    const int64_t cc = idx - (int64_t)tap * per;
+    float s = 0.f;
+    for (int ch = 0; ch < nchunks; ++ch) s += __ldcg(partial + ((int64_t)ch * taps + tap) * per + cc);
+    dw[cc * taps + tap] = s;
+  }
+}
+
+// ---- loss and its gradient (p_losses :2355-2365): per-sample mean of l1 / l2 / smooth-l1, x_start objective clamps pred from below ----
+__global__ void __launch_bounds__(256) loss_grad_kernel(const float* pred, const float* target, int64_t count, int kind, int clamp_lo, float lo,
+                                                        const float* sample_weight, float* dpred, float* loss_partial) {
+  __shared__ float red[256];
+  const int n = blockIdx.y, nblk = gridDim.x;
+  const int64_t per = (count + nblk - 1) / nblk, i0 = (int64_t)blockIdx.x * per, i1 = min(count, i0 + per);
+  const float w = sample_weight[n];   // loss weight of the sample / (batch * count)
+  float s = 0.f;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += 256) {
+    const float p = pred[(int64_t)n * count + i], t = target[(int64_t)n * count + i];
+    const bool clamped = clamp_lo && p < lo;
+    const float d = (clamped ? lo : p) - t;
+    float l, g;
+    if (kind == 0) { l = fabsf(d); g = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
+    else if (kind == 1) { l = d * d; g = 2.f * d; }
+    else { const float ad = fabsf(d); l = ad < 1.f ? 0.5f * d * d : ad - 0.5f; g = ad < 1.f ? d : (d > 0.f ? 1.f : -1.f); }
+    s += l;
+    dpred[(int64_t)n * count + i] = clamped ? 0.f : g * w;
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss_partial[n * nblk + blockIdx.x] = red[0];
+}
+
+// ---- Adam (torch.optim.Adam, no amsgrad; trainer.py's optimizer) + optional EMA of the parameter -----------------------------------
+__global__ void __launch_bounds__(256) adam_step_kernel(float* p, const float* g, float* m, float* v, int64_t count, float lr, float b1, float b2,
+                                                        float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, float* ema, float ema_decay) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < count; i += (int64_t)gridDim.x * 256) {
+    float gi = g[i] * grad_scale;
+    float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    const float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * (mi / denom);
+    p[i] = pi;
+    if (ema) ema[i] = fmaf(ema_decay, ema[i] - pi, pi);   // ema * decay + p * (1 - decay)
+  }
+}
+
+}  // namespace diqt
+
+using namespace diqt;
+
+extern "C" int diqt_bwd_reduce(const void* x, int ld_x, const void* dz, int ld_dz, int dtype, int n, int64_t voxels, int c, const float* a, const float* b,
+                               int mode, int nblk, float* partial, void* stream) {
+  DIQT_REQUIRE(x && dz && partial && n > 0 && voxels > 0 && nblk > 0, "bwd_reduce: bad arguments");
+  DIQT_REQUIRE(dtype == DIQT_F32 || dtype == DIQT_BF16, "bwd_reduce: bad dtype %d", dtype);
+  DIQT_REQUIRE(mode == 0 || (mode == 1 && a && b), "bwd_reduce: mode %d (0 plain, 1 through mish(a x + b))", mode);
+  const int vec = dtype == DIQT_BF16 ? 8 : 4;
+  DIQT_REQUIRE(c % vec == 0 && ld_x % vec == 0 && ld_dz % vec == 0 && c / vec <= 256, "bwd_reduce: c=%d not a multiple of %d", c, vec);
+  const BwMap m = bw_map(c, vec, 256);
+  const size_t sh = (size_t)2 * m.lanes * c * sizeof(float);
+  DIQT_REQUIRE(sh <= 48 * 1024, "bwd_reduce: c=%d too wide", c);
+  const dim3 grid(nblk, n);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t vpb = bw_vpb(voxels, nblk);
+#define DIQT_BW_REDUCE(T, M) \
+  launch_pdl(bwd_reduce_kernel<T, M>, grid, m.threads, sh, st, (const T*)x, ld_x, (const T*)dz, ld_dz, voxels, c, m.nvec, m.lanes, vpb, a, b, partial)
+  if (dtype == DIQT_BF16) { if (mode) DIQT_BW_REDUCE(__nv_bfloat16, 1); else DIQT_BW_REDUCE(__nv_bfloat16, 0); }
+  else { if (mode) DIQT_BW_REDUCE(float, 1); else DIQT_BW_REDUCE(float, 0); }
+#undef DIQT_BW_REDUCE
+  return check_launch("bwd_reduce");
+}
+
+extern "C" int diqt_bwd_apply(const void* x, int ld_x, const void* dz, int ld_dz, const void* acc, int ld_acc, void* out, int ld_out, int dtype, int n,
+                              int64_t voxels, int c, const float* a, const float* b, const float* c1, const float* c2, const float* c3, int mode,
+                              int nblk, void* stream) {
+  DIQT_REQUIRE(dz && out && c1 && n > 0 && voxels > 0 && nblk > 0, "bwd_apply: bad arguments");
+  DIQT_REQUIRE(dtype == DIQT_F32 || dtype == DIQT_BF16, "bwd_apply: bad dtype %d", dtype);
+  DIQT_REQUIRE(mode == 0 || (mode == 1 && a && b && x), "bwd_apply: mode %d (0 plain, 1 through mish(a x + b))", mode);
+  DIQT_REQUIRE(x || !c2, "bwd_apply: c2 needs x");
+  const int vec = dtype == DIQT_BF16 ? 8 : 4;
+  DIQT_REQUIRE(c % vec == 0 && ld_x % vec == 0 && ld_dz % vec == 0 && ld_acc % vec == 0 && ld_out % vec == 0 && c / vec <= 256,
+               "bwd_apply: c=%d not a multiple of %d", c, vec);
+  const BwMap m = bw_map(c, vec, 256);
+  const dim3 grid(nblk, n);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t vpb = bw_vpb(voxels, nblk);
+#define DIQT_BW_APPLY(T, M)                                                                                                                        \
+  launch_pdl(bwd_apply_kernel<T, M>, grid, m.threads, 0, st, (const T*)x, ld_x, (const T*)dz, ld_dz, (const T*)acc, ld_acc, (T*)out, ld_out, voxels, c, \
+             m.nvec, m.lanes, vpb, a, b, c1, c2, c3)
+  if (dtype == DIQT_BF16) { if (mode) DIQT_BW_APPLY(__nv_bfloat16, 1); else DIQT_BW_APPLY(__nv_bfloat16, 0); }
+  else { if (mode) DIQT_BW_APPLY(float, 1); else DIQT_BW_APPLY(float, 0); }
+#undef DIQT_BW_APPLY
+  return check_launch("bwd_apply");
+}
+
+static int wgrad_chunks(int64_t total_vox, int taps, int tiles) {
+  int64_t ch = 1184 / ((int64_t)taps * tiles);
+  if (ch > 64) ch = 64;
+  const int64_t max_ch = (total_vox + WG_VT - 1) / WG_VT;
+  if (ch > max_ch) ch = max_ch;
+  if (ch < 1) ch = 1;
+  return (int)ch;
+}
+
+extern "C" int diqt_conv_wgrad_workspace_bytes(int n, int d0, int d1, int d2, int c_in, int c_out, int taps, size_t* bytes) {
+  DIQT_REQUIRE(bytes && n > 0 && d0 > 0 && d1 > 0 && d2 > 0 && c_in > 0 && c_out > 0 && (taps == 1 || taps == 27), "conv_wgrad_workspace_bytes: bad arguments");
+  const int tiles = ((c_out + 63) / 64) * ((c_in + 63) / 64);
+  *bytes = (size_t)wgrad_chunks((int64_t)n * d0 * d1 * d2, taps, tiles) * taps * c_out * c_in * sizeof(float);
+  return DIQT_OK;
+}
+
+extern "C" int diqt_conv_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, int dtype, int n, int d0, int d1, int d2, int c_in, int c_out, int taps,
+                               float* dw, float* workspace, void* stream) {
+  DIQT_REQUIRE(x && dy && dw && workspace && n > 0 && d0 > 0 && d1 > 0 && d2 > 0 && c_in > 0 && c_out > 0, "conv_wgrad: bad arguments");
+  DIQT_REQUIRE(taps == 1 || taps == 27, "conv_wgrad: taps %d (1: 1x1x1, 27: 3x3x3 with padding 1)", taps);
+  DIQT_REQUIRE(dtype == DIQT_F32 || dtype == DIQT_BF16, "conv_wgrad: bad dtype %d", dtype);
+  const int ci_tiles = (c_in + 63) / 64, tiles = ((c_out + 63) / 64) * ci_tiles;
+  const int64_t total = (int64_t)n * d0 * d1 * d2;
+  const int nchunks = wgrad_chunks(total, taps, tiles);
+  int64_t vpc = (total + nchunks - 1) / nchunks;
+  vpc = (vpc + WG_VT - 1) / WG_VT * WG_VT;
+  const dim3 grid(nchunks, taps, tiles);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DIQT_BF16)
+    launch_pdl(conv_wgrad_simt_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)x, ld_x, (const __nv_bfloat16*)dy, ld_dy, n, d0, d1, d2, c_in,
+               c_out, taps, ci_tiles, vpc, workspace);
+  else
+    launch_pdl(conv_wgrad_simt_kernel<float>, grid, 256, 0, st, (const float*)x, ld_x, (const float*)dy, ld_dy, n, d0, d1, d2, c_in, c_out, taps, ci_tiles,
+               vpc, workspace);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const int64_t count = (int64_t)c_out * c_in * taps;
+  launch_pdl(conv_wgrad_reduce_kernel, dim3((unsigned)((count + 255) / 256 > 1184 ? 1184 : (count + 255) / 256)), 256, 0, st, (const float*)workspace,
+             nchunks, taps, c_out, c_in, dw);
+  return check_launch("conv_wgrad");
+}
+
+extern "C" int diqt_loss_grad(const float* pred, const float* target, int n, int64_t count, int kind, int clamp_lo, float lo, const float* sample_weight,
+                              float* dpred, float* loss_partial, int nblk, void* stream) {
+  DIQT_REQUIRE(pred && target && sample_weight && dpred && loss_partial && n > 0 && count > 0 && nblk > 0, "loss_grad: bad arguments");
+  DIQT_REQUIRE(kind >= 0 && kind <= 2, "loss_grad: kind %d (0 l1, 1 l2, 2 huber)", kind);
+  loss_grad_kernel<<<dim3(nblk, n), 256, 0, (cudaStream_t)stream>>>(pred, target, count, kind, clamp_lo, lo, sample_weight, dpred, loss_partial);
+  return check_launch("loss_grad");
+}
+
+extern "C" int diqt_adam_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, int step, float grad_scale, float* ema, float ema_decay, void* stream) {
+  DIQT_REQUIRE(p && g && m && v && count > 0 && step > 0, "adam_step: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  const int64_t blocks = (count + 255) / 256;
+  adam_step_kernel<<<(unsigned)(blocks > 1184 ? 1184 : blocks), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, count, lr, beta1, beta2, eps, weight_decay, bc1,
+                                                                                                 sqrtf(bc2), grad_scale, ema, ema_decay);
+  return check_launch("adam_step");
+}

@@ -96,6 +96,7 @@ class UnetEngine:
         self.sampler_cache = {}
         self.film_gen = 0
         self._attn_plans: List[int] = []
+        self._linattn_plans: List[int] = []
         self.attn_impls = {}                  # attention site -> "tc" | "simt"
         self._build()
 
@@ -744,7 +745,14 @@ class UnetEngine:
             return out
 
         # ---- {Linear,SoftMax}AttentionTransformerBlock.forward :1146-1150 / :1181-1186
-        if mod.kind == "linear":
+        lin_tc = (mod.kind == "linear" and self.dtype == "bf16" and os.environ.get("DIQT_DISABLE_ATTN_TC", "0") != "1"
+                  and bool(lib.diqt_linattn_tc_supported(dd, dh, heads, 3 * inner, inner)))
+        if mod.kind == "linear" and lin_tc:
+            nbytes = C.c_size_t(0)
+            L.check(lib.diqt_linattn_tc_workspace_bytes(N, heads, C.byref(nbytes)), "linattn_tc_workspace_bytes")
+            lin_ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=self.device)
+            self._keep.append(lin_ws)
+        elif mod.kind == "linear":
             nch = C.c_int(0)
             L.check(lib.diqt_linear_attention_chunks(N, C.byref(nch)), "linear_attention_chunks")
             col_stat = torch.zeros(inner * 2, dtype=torch.float32, device=self.device)
@@ -770,7 +778,15 @@ class UnetEngine:
             wp, s0, s0l, d0p, d0l = wdw.data_ptr(), QKV0.ptr, QKV0.ld, QKV.ptr, QKV.ld
             ops.append(lambda st, wp=wp, lname=lname: L.check(lib.diqt_dw_conv3(s0, s0l, d0p, d0l, dd, g, g, g, 3 * inner, wp, 0, st), f"{name}.{lname}.to_qkv.2"))
             op_, ol = O.ptr, O.ld
-            if mod.kind == "linear":
+            if mod.kind == "linear" and lin_tc:
+                plan = C.c_void_p(0)     # the layers of a block run one after the other: they share the workspace
+                L.check(lib.diqt_linattn_tc_plan_create(q_ptr, k_ptr, v_ptr, ldq, op_, ol, N, heads, scale, 1, (lin_ws.data_ptr() + 255) // 256 * 256,
+                                                        C.byref(plan)), f"{name}.{lname}.linear_attention.plan")
+                self._linattn_plans.append(plan.value)
+                self.attn_impls[f"{name}.{lname}.linear_attention"] = "tc"
+                ops.append(lambda st, pv=plan.value, lname=lname: L.check(lib.diqt_linattn_tc_run(pv, st), f"{name}.{lname}.linear_attention"))
+            elif mod.kind == "linear":
+                self.attn_impls[f"{name}.{lname}.linear_attention"] = "simt"
                 csp, cpp = col_stat.data_ptr(), ctx_part.data_ptr()
                 ops.append(lambda st, lname=lname: L.check(lib.diqt_linear_attention(q_ptr, k_ptr, v_ptr, ldq, op_, ol, dd, N, heads, dh, scale, 1, csp, cpp, st),
                                               f"{name}.{lname}.linear_attention"))
@@ -861,6 +877,9 @@ class UnetEngine:
         for p in getattr(self, "_attn_plans", []):
             self.lib.diqt_attn_tc_plan_destroy(p)
         self._attn_plans = []
+        for p in getattr(self, "_linattn_plans", []):
+            self.lib.diqt_linattn_tc_plan_destroy(p)
+        self._linattn_plans = []
         self._ops = []
         self.sampler_cache = {}
 

@@ -72,6 +72,11 @@ _SIGNATURES = {
     "diqt_attn_tc_plan_create": [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _f, _i, _vp, C.POINTER(_vp)],
     "diqt_attn_tc_plan_destroy": [_vp],
     "diqt_attn_tc_run": [_vp, _vp],
+    "diqt_linattn_tc_supported": [_i, _i, _i, _i, _i],
+    "diqt_linattn_tc_workspace_bytes": [_i, _i, C.POINTER(C.c_size_t)],
+    "diqt_linattn_tc_plan_create": [_vp, _vp, _vp, _i, _vp, _i, _i, _i, _f, _i, _vp, C.POINTER(_vp)],
+    "diqt_linattn_tc_plan_destroy": [_vp],
+    "diqt_linattn_tc_run": [_vp, _vp],
     "diqt_init_conv_pack": [_vp, _i, _i, _vp, _vp],
     "diqt_init_conv_k": [C.POINTER(_vp), C.POINTER(_i64), _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "diqt_init_conv_tc_supported": [_i, _i, _i, _i],
@@ -91,7 +96,8 @@ _SIGNATURES = {
     "diqt_gather_patches": [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp],
     "diqt_stitch_patches": [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _f, _vp],
 }
-_RESTYPES = {"diqt_last_error": C.c_char_p, "diqt_launch_count": C.c_uint64, "diqt_conv_plan_destroy": None, "diqt_attn_tc_plan_destroy": None}
+_RESTYPES = {"diqt_last_error": C.c_char_p, "diqt_launch_count": C.c_uint64, "diqt_conv_plan_destroy": None, "diqt_attn_tc_plan_destroy": None,
+             "diqt_linattn_tc_plan_destroy": None}
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

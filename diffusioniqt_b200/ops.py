@@ -279,17 +279,35 @@ def upsample_trilinear(tokens, grid_dim, factor):
     return out
 
 
-def linear_attention(qkv, heads, dim_head, act=1):
-    """qkv: (tokens, 3*heads*dim_head) holding q | k | v blocks -> (tokens, heads*dim_head)   (imagen_pytorch3D.py:1001-1011)."""
+def linear_attention(qkv, heads, dim_head, act=1, impl="auto"):
+    """qkv: (tokens, 3*heads*dim_head) holding q | k | v blocks -> (tokens, heads*dim_head)   (imagen_pytorch3D.py:1001-1011).
+    impl "tc": the tcgen05 kernels (bf16, dim_head 64, even number of heads); "simt": the CUDA-core kernels; "auto": tc when supported."""
     lib = L.load()
     n, inner = qkv.shape[0], heads * dim_head
     esz = qkv.element_size()
     out = torch.empty(n, inner, dtype=qkv.dtype, device=qkv.device)
+    p = qkv.data_ptr()
+    tc_ok = bool(lib.diqt_linattn_tc_supported(_dt(qkv), dim_head, heads, 3 * inner, inner))
+    if impl == "tc" and not tc_ok:
+        raise L.DiqtError("linear_attention(tc): needs bf16, dim_head 64 and an even number of heads")
+    if impl == "tc" or (impl == "auto" and tc_ok):
+        nbytes = C.c_size_t(0)
+        L.check(lib.diqt_linattn_tc_workspace_bytes(n, heads, C.byref(nbytes)), "linattn_tc_workspace_bytes")
+        ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=qkv.device)
+        wp = (ws.data_ptr() + 255) // 256 * 256
+        plan = C.c_void_p(0)
+        L.check(lib.diqt_linattn_tc_plan_create(p, p + inner * esz, p + 2 * inner * esz, 3 * inner, out.data_ptr(), inner, n, heads,
+                                                float(dim_head) ** -0.5, act, wp, C.byref(plan)), "linattn_tc_plan_create")
+        try:
+            L.check(lib.diqt_linattn_tc_run(plan.value, L.current_stream()), "linattn_tc_run")
+            torch.cuda.current_stream().synchronize()
+        finally:
+            lib.diqt_linattn_tc_plan_destroy(plan.value)
+        return out
     chunks = C.c_int(0)
     L.check(lib.diqt_linear_attention_chunks(n, C.byref(chunks)), "linear_attention_chunks")
     stat = torch.empty(inner * 2, dtype=torch.float32, device=qkv.device)
     part = torch.empty(chunks.value * heads * dim_head * dim_head, dtype=torch.float32, device=qkv.device)
-    p = qkv.data_ptr()
     L.check(lib.diqt_linear_attention(p, p + inner * esz, p + 2 * inner * esz, 3 * inner, out.data_ptr(), inner, _dt(qkv), n, heads, dim_head,
                                       float(dim_head) ** -0.5, act, stat.data_ptr(), part.data_ptr(), L.current_stream()), "linear_attention")
     return out

@@ -228,7 +228,8 @@ int diqt_softmax_attention(const void* q, const void* k, const void* v, int ld_q
 /* The same product on the tensor cores (csrc/attn_tc.cu): tcgen05.mma for Q K^T and P V with fp32 accumulators in TMEM, two passes over
  * the key tiles (row max / sum, then probabilities), nothing N x N in memory.  bf16, dim_head = 64, pitches multiples of 8, 16-byte aligned
  * pointers; q / k / v may be column blocks of one [tokens][3 * heads * 64] buffer.  `workspace`: diqt_attn_tc_workspace_bytes() bytes of
- * device memory, ZERO-initialised once by the caller (it holds V^T padded to a multiple of 128 tokens).  A plan bakes the pointers
+ * device memory, ZERO-initialised once by the caller (V^T padded to a multiple of 128 tokens: read by the two-pass kernel only; the
+ * single-pass kernel takes V as an MN-major operand where it lies).  A plan bakes the pointers
  * (TMA descriptors); create it once outside stream capture. */
 typedef struct diqt_attn_plan diqt_attn_plan;
 int diqt_attn_tc_supported(int dtype, int dim_head, int ld_q, int ld_k, int ld_v, int ld_out);
@@ -237,6 +238,19 @@ int diqt_attn_tc_plan_create(const void* q, const void* k, const void* v, int ld
                              int heads, float scale, int act, void* workspace, diqt_attn_plan** plan);
 void diqt_attn_tc_plan_destroy(diqt_attn_plan* plan);
 int diqt_attn_tc_run(const diqt_attn_plan* plan, void* stream);
+
+/* LinearAttention core (:1001-1011) on the tensor cores (csrc/linattn_tc.cu): k^T v and q ctx as tcgen05.mma (the k / v boxes are used
+ * as MN-major operands exactly as TMA lands them: no transposed copies), q, k, v read once, partial contexts of the token chunks summed
+ * in a fixed order.  bf16, dim_head = 64, an even number of heads (<= 32), pitches multiples of 8, 16-byte aligned pointers; q / k / v are
+ * column blocks of [tokens][ld_qkv] buffers.  `workspace`: diqt_linattn_tc_workspace_bytes() bytes, 256-byte aligned, no initialisation
+ * needed.  A plan bakes the pointers (TMA descriptors); create it once outside stream capture.  act: 0 none, 1 Mish (:1011). */
+typedef struct diqt_linattn_plan diqt_linattn_plan;
+int diqt_linattn_tc_supported(int dtype, int dim_head, int heads, int ld_qkv, int ld_out);
+int diqt_linattn_tc_workspace_bytes(int tokens, int heads, size_t* bytes);
+int diqt_linattn_tc_plan_create(const void* q, const void* k, const void* v, int ld_qkv, void* out, int ld_out, int tokens, int heads,
+                                float scale, int act, void* workspace, diqt_linattn_plan** plan);
+void diqt_linattn_tc_plan_destroy(diqt_linattn_plan* plan);
+int diqt_linattn_tc_run(const diqt_linattn_plan* plan, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Network ends.

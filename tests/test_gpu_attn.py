@@ -133,8 +133,53 @@ def test_linear_attention(name, dt, tol, n, heads, dh):
     k = k.softmax(dim=-2)
     out = torch.einsum("bnd,bde->bne", q, torch.einsum("bnd,bne->bde", k, v))
     want = F.mish(out.permute(1, 0, 2).reshape(n, heads * dh))
-    got = ops.linear_attention(qkv.to(dt).cuda(), heads, dh)
+    got = ops.linear_attention(qkv.to(dt).cuda(), heads, dh, impl="simt")
     assert max_rel(got.float().cpu(), want) < tol
+
+
+def _linear_attention_want(qkv, heads, dh, act):
+    n = qkv.shape[0]
+    q, k, v = (_split_heads(t, heads) for t in qkv.chunk(3, dim=1))
+    q = q.softmax(dim=-1) * dh ** -0.5
+    k = k.softmax(dim=-2)
+    out = torch.einsum("bnd,bde->bne", q, torch.einsum("bnd,bne->bde", k, v)).permute(1, 0, 2).reshape(n, heads * dh)
+    return F.mish(out) if act else out
+
+
+@pytest.mark.parametrize("n,heads,act", [(128, 2, 0), (100, 2, 1), (27, 4, 1), (1728, 8, 1), (520, 6, 0), (5000, 4, 1), (13824, 8, 1)])
+def test_linear_attention_tensor_core_kernel(n, heads, act):
+    """csrc/linattn_tc.cu (tcgen05 k^T v with MN-major operands, tcgen05 q ctx) against the fp32 PyTorch product (imagen_pytorch3D.py:1001-1011);
+    bf16, dim_head 64.  Token counts that are not multiples of the 128-token tile exercise the row mask (rows past the end must not enter the
+    column sums); 13 824 x 8 is BASELINE config 5's long sequence (37 chunks x 4 head pairs); a second pass uses keys with a large
+    dynamic range and a trend along the sequence, so the column maximum comes from far-away chunks."""
+    from diffusioniqt_b200 import ops
+    dh, dt, tol = 64, torch.bfloat16, 1e-2
+    qkv = _q(_rand(n, 3 * heads * dh, seed=4, scale=1.5), dt)
+    want = _linear_attention_want(qkv, heads, dh, act)
+    got = ops.linear_attention(qkv.to(dt).cuda(), heads, dh, act=act, impl="tc")
+    assert torch.isfinite(got).all()
+    assert max_rel(got.float().cpu(), want) < tol
+    assert torch.equal(got, ops.linear_attention(qkv.to(dt).cuda(), heads, dh, act=act, impl="tc"))      # fixed summation order
+    simt = ops.linear_attention(qkv.to(dt).cuda(), heads, dh, act=act, impl="simt")
+    assert max_rel(got.float().cpu(), simt.float().cpu()) < tol
+    inner = heads * dh
+    qkv2 = qkv.clone()
+    qkv2[:, inner: 2 * inner] *= torch.linspace(0.3, 6.0, n)[:, None]     # k: the largest entries sit at the end of the sequence
+    qkv2[:, :inner] *= 4.0                                                # q: sharp softmax over the head dimension
+    qkv2 = _q(qkv2, dt)
+    want = _linear_attention_want(qkv2, heads, dh, act)
+    got = ops.linear_attention(qkv2.to(dt).cuda(), heads, dh, act=act, impl="tc")
+    assert torch.isfinite(got).all()
+    assert max_rel(got.float().cpu(), want) < tol
+
+
+def test_linear_attention_tensor_core_rejects_unsupported_shapes():
+    from diffusioniqt_b200 import lib as L, ops
+    qkv = torch.zeros(64, 3 * 3 * 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(L.DiqtError):
+        ops.linear_attention(qkv, 3, 64, impl="tc")           # odd number of heads
+    with pytest.raises(L.DiqtError):
+        ops.linear_attention(qkv.float(), 3, 64, impl="tc")   # fp32 exact mode stays on the CUDA cores
 
 
 @pytest.mark.parametrize("name,dt,tol", DTYPES)

@@ -130,3 +130,17 @@ def test_softmax_attention_sites_use_the_tensor_core_kernel():
     unet32 = _gpu_unet(case, "fp32")
     unet32(x.cuda(), None, time.cuda(), lowres_cond_img=lr.cuda())
     assert set(next(iter(unet32._engines.values())).attn_impls.values()) == {"simt"}
+
+
+def test_linear_attention_sites_use_the_tensor_core_kernel():
+    """bf16, head dim 64, even head counts: every LinearAttention core of the engine runs csrc/linattn_tc.cu, and the forward still
+    matches the fp32 oracle fixture; fp32 exact mode stays on the CUDA cores."""
+    case = FORWARD_CASES["attn_linear_dim64_f2_s32"]
+    unet = _gpu_unet(case, "bf16")
+    x, lr, time = build_inputs(case)
+    unet(x.cuda(), None, time.cuda(), lowres_cond_img=lr.cuda())
+    eng = next(iter(unet._engines.values()))
+    assert eng.attn_impls and set(eng.attn_impls.values()) == {"tc"}
+    unet32 = _gpu_unet(case, "fp32")
+    unet32(x.cuda(), None, time.cuda(), lowres_cond_img=lr.cuda())
+    assert set(next(iter(unet32._engines.values())).attn_impls.values()) == {"simt"}
