@@ -147,6 +147,7 @@ class Imagen(nn.Module):
         super().__init__()
         self.configs = configs
         self.boundary = boundary
+        self.use_lpips = bool(lpips or medlpips)   # the perceptual term (:2366-2381) needs a pretrained VGG: sampling ignores it, training refuses
         if loss_type not in ('l1', 'l2', 'huber'):
             raise NotImplementedError()
         self.loss_type = loss_type
@@ -477,5 +478,42 @@ class Imagen(nn.Module):
         finally:
             self.train(was_training)
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError("training (Imagen.forward / p_losses, imagen_pytorch3D.py:2277-2442) is outside the sampling hot path this package implements")
+    def p_losses(self, unet, x_start, times, *, noise_scheduler, lowres_cond_img=None, cond_images=None, noise=None, pred_objective='noise',
+                 p2_loss_weight_gamma=0., **kwargs):
+        """imagen_pytorch3D.py:2277-2387 on the kernels (diffusioniqt_b200/train.py): returns (loss, pred, x_noisy, lowres_cond_img);
+        `loss.backward()` runs the hand-written reverse pass and accumulates `.grad` on the U-Net's parameters."""
+        from .train import p_losses
+        if cond_images is not None:
+            raise NotImplementedError("the training step does not implement cond_images")
+        if getattr(self, 'use_lpips', False):
+            raise NotImplementedError("the training step does not implement the LPIPS term (:2366-2381): it needs a pretrained network")
+        return p_losses(self, unet, x_start, times, noise_scheduler=noise_scheduler, lowres_cond_img=lowres_cond_img, noise=noise,
+                        pred_objective=pred_objective, p2_loss_weight_gamma=p2_loss_weight_gamma)
+
+    def forward(self, images, lowres_img=None, unet=None, text_embeds=None, text_masks=None, unet_number=None, cond_images=None, **kwargs):
+        """imagen_pytorch3D.py:2389-2442: one training evaluation of U-Net `unet_number` on a batch of high-field patches."""
+        assert images.shape[-1] == images.shape[-2], f'the images you pass in must be a square, but received dimensions of {images.shape[2]}, {images.shape[-1]}'
+        assert not (len(self.unets) > 1 and unet_number is None), \
+            f'you must specify which unet you want trained, from a range of 1 to {len(self.unets)}, if you are training cascading DDPM (multiple unets)'
+        unet_number = unet_number if unet_number is not None else 1
+        assert self.only_train_unet_number is None or self.only_train_unet_number == unet_number, \
+            f'you can only train on unet #{self.only_train_unet_number}'
+        assert images.dtype == torch.float, f'images tensor needs to be floats but {images.dtype} dtype found instead'
+        unet_index = unet_number - 1
+        unet = unet if unet is not None else self.get_unet(unet_number)
+        assert not isinstance(unet, NullUnet), 'null unet cannot and should not be trained'
+        noise_scheduler = self.noise_schedulers[unet_index]
+        p2_loss_weight_gamma = self.p2_loss_weight_gamma[unet_index]
+        pred_objective = self.pred_objectives[unet_index]
+        target_image_size = self.image_sizes[unet_index]
+        b, c = images.shape[:2]
+        assert c == self.channels and images.dim() == 5
+        assert images.shape[-2] >= target_image_size and images.shape[-3] >= target_image_size
+        if self.configs['Train']['batch_sample']:
+            times = noise_scheduler.sample_random_times(1, device=images.device).repeat(b)
+        else:
+            times = noise_scheduler.sample_random_times(b, device=images.device)
+        assert lowres_img is not None, 'lowres image must be provided'
+        self.lowres_cond_img = lowres_img
+        return self.p_losses(unet, images, times, cond_images=cond_images, noise_scheduler=noise_scheduler, lowres_cond_img=lowres_img,
+                             pred_objective=pred_objective, p2_loss_weight_gamma=p2_loss_weight_gamma, **kwargs)

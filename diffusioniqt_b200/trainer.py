@@ -106,6 +106,12 @@ class ImagenTrainer(nn.Module):
         self.verbose = verbose
         self.only_train_unet_number = only_train_unet_number
         self.checkpoint_path, self.checkpoint_every, self.max_checkpoints_keep = checkpoint_path, checkpoint_every, max_checkpoints_keep
+        cast = lambda v: tuple(v) if isinstance(v, (list, tuple)) else (v,) * self.num_unets
+        self._optim_args = dict(lr=cast(lr), eps=cast(eps), beta1=beta1, beta2=beta2)
+        self._optims = {}
+        self._micro = [0] * self.num_unets
+        self.max_grad_norm = max_grad_norm
+        self.gradient_accumulation_steps = gradient_accumulation_steps
         self.to(self.device)
 
     # ------------------------------------------------------------------ accelerator-shaped properties (single process)
@@ -239,8 +245,105 @@ class ImagenTrainer(nn.Module):
             trajs.append([np.concatenate(step, axis=0) for step in zip(*lists)] if all(len(l) == len(lists[0]) for l in lists) else lists)
         return imgs, trajs[0], trajs[1]
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError("training (ImagenTrainer.forward / update, trainer.py:1099-1128) is outside the sampling hot path this package implements")
+    # ------------------------------------------------------------------ training (trainer.py:1038-1130)
+    # ema_pytorch (pinned 0.1.4, requirements.txt:40) is absent from the reference tree; its published update rule, with the defaults the
+    # reference constructs it with (`EMA(unet)`): every `update_every` = 10th call, copy the online weights while step <= 100, afterwards
+    # ema = decay * ema + (1 - decay) * online with decay = clamp(1 - (1 + (step - 101) / inv_gamma) ** -power, 0, beta),
+    # beta = 0.9999, inv_gamma = 1, power = 2 / 3.
+    EMA_BETA, EMA_UPDATE_AFTER, EMA_UPDATE_EVERY, EMA_INV_GAMMA, EMA_POWER = 0.9999, 100, 10, 1.0, 2.0 / 3.0
+
+    def _optimizer(self, index):
+        from .train import AdamState
+        if index not in self._optims:
+            o = self._optim_args
+            self._optims[index] = AdamState(self.imagen.unets[index].parameters(), lr=o["lr"][index], betas=(o["beta1"], o["beta2"]), eps=o["eps"][index])
+        return self._optims[index]
+
+    def get_lr(self, unet_number):
+        return self._optimizer(unet_number - 1).lr
+
+    def validate_unet_number(self, unet_number=None):
+        if self.num_unets == 1:
+            unet_number = 1 if unet_number is None else unet_number
+        assert unet_number is not None and 0 < unet_number <= self.num_unets, f'unet number should be in between 1 and {self.num_unets}'
+        return unet_number
+
+    def _ema_decay(self, step):
+        epoch = max(step - self.EMA_UPDATE_AFTER - 1, 0)
+        value = 1 - (1 + epoch / self.EMA_INV_GAMMA) ** -self.EMA_POWER
+        return 0. if epoch <= 0 else min(max(value, 0.), self.EMA_BETA)
+
+    @torch.no_grad()
+    def update(self, unet_number=None):
+        """optimizer.step(), optimizer.zero_grad(), ema_unet.update(), steps += 1 (trainer.py:1038-1070).  With gradient accumulation the
+        call is a no-op except on every `gradient_accumulation_steps`-th micro-batch, as under `accelerator.accumulate`."""
+        unet_number = self.validate_unet_number(unet_number)
+        index = unet_number - 1
+        self._micro[index] += 1
+        if self._micro[index] % self.gradient_accumulation_steps != 0:
+            return
+        unet = self.imagen.unets[index]
+        opt = self._optimizer(index)
+        if self.max_grad_norm is not None:
+            torch.nn.utils.clip_grad_norm_(unet.parameters(), self.max_grad_norm)
+        ema_params, decay = None, 0.
+        if self.use_ema:
+            holder = self.ema_unets[index]
+            holder.step += 1
+            step = int(holder.step.item())
+            if step % self.EMA_UPDATE_EVERY == 0:
+                if step <= self.EMA_UPDATE_AFTER or not bool(holder.initted.item()):
+                    copy_after = True
+                    if step > self.EMA_UPDATE_AFTER:
+                        holder.initted.fill_(True)
+                else:
+                    copy_after = False
+                    ema_params, decay = [p for p in holder.ema_model.parameters()], self._ema_decay(step)
+            else:
+                copy_after = None
+        opt.step(ema_params=ema_params, ema_decay=decay)
+        opt.zero_grad()
+        if self.use_ema and copy_after:
+            for pe, po in zip(holder.ema_model.parameters(), unet.parameters()):
+                pe.copy_(po)
+        if self.use_ema and copy_after is not None:
+            for be, bo in zip(holder.ema_model.buffers(), unet.buffers()):
+                be.copy_(bo)
+            holder.ema_model.invalidate_engines()
+        unet.invalidate_engines()          # packed weight copies of the sampling engines are stale now
+        self.steps[index] += 1
+
+    def forward(self, *args, unet_number=None, max_batch_size=None, **kwargs):
+        """One training call (trainer.py:1099-1130): the batch in chunks of `max_batch_size`, per chunk `imagen(...)`, loss scaled by the
+        chunk's share (and by 1 / gradient_accumulation_steps, as `accelerator.backward` does), `loss.backward()`, `update()`."""
+        unet_number = self.validate_unet_number(unet_number)
+        assert self.only_train_unet_number is None or self.only_train_unet_number == unet_number, f'you can only train unet #{self.only_train_unet_number}'
+        unet = self.imagen.unets[unet_number - 1]
+
+        def cast(t):
+            if isinstance(t, np.ndarray):
+                t = torch.from_numpy(t)
+            return t.to(self.device) if isinstance(t, torch.Tensor) else t
+
+        args = tuple(cast(a) for a in args)
+        kwargs = {k: cast(v) for k, v in kwargs.items()}
+        tensors = [a for a in (*args, *kwargs.values()) if isinstance(a, torch.Tensor)]
+        batch = tensors[0].shape[0]
+        sizes = num_to_groups(batch, max_batch_size) if max_batch_size is not None else [batch]
+        total_loss, start = 0., 0
+        out = None
+        for sz in sizes:
+            def cut(t):
+                return t[start:start + sz] if isinstance(t, torch.Tensor) and t.shape[0] == batch else t
+            loss, pred, x_noisy, lowres = self.imagen(*(cut(a) for a in args), unet=unet, unet_number=unet_number, **{k: cut(v) for k, v in kwargs.items()})
+            loss = loss * (sz / batch)
+            if self.training:
+                (loss / self.gradient_accumulation_steps).backward()
+                self.update(unet_number=unet_number)
+            total_loss += loss.item()
+            out = (pred, x_noisy, lowres)
+            start += sz
+        return (total_loss, *out)
 
 
 @contextmanager

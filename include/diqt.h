@@ -253,6 +253,37 @@ void diqt_linattn_tc_plan_destroy(diqt_linattn_plan* plan);
 int diqt_linattn_tc_run(const diqt_linattn_plan* plan, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training step (csrc/backward.cu): the reverse pass of Unet.forward for loss.backward() in
+ * Imagen.forward / p_losses (imagen_pytorch3D.py:2277-2387) and the optimizer update of
+ * ImagenTrainer.update (trainer.py).  Data gradients of convolutions run through diqt_conv_*
+ * with the flipped, transposed weights.
+ * ------------------------------------------------------------------------------------------ */
+/* partial[n][blk][c][2] = (sum_v t, sum_v t * x) with t = dz * mish'(a[n][c] x + b[n][c]) (mode 1: reverse of GroupNorm -> FiLM -> Mish,
+ * :546-563) or t = dz (mode 0: reverse of the SE gate x * gate, :630).  a, b: the forward pass's folded affine (diqt_gn_finalize). */
+int diqt_bwd_reduce(const void* x, int ld_x, const void* dz, int ld_dz, int dtype, int n, int64_t voxels, int c, const float* a,
+                    const float* b, int mode, int nblk, float* partial, void* stream);
+/* out = c1[n][c] * t + c2[n][c] * x + c3[n][c] (+ acc): the input gradient of GroupNorm -> FiLM -> Mish (mode 1) or of the SE join
+ * (mode 0); acc adds the gradient arriving over the residual branch (:612).  c2, c3, acc, x (mode 0 without c2) may be NULL. */
+int diqt_bwd_apply(const void* x, int ld_x, const void* dz, int ld_dz, const void* acc, int ld_acc, void* out, int ld_out, int dtype,
+                   int n, int64_t voxels, int c, const float* a, const float* b, const float* c1, const float* c2, const float* c3,
+                   int mode, int nblk, void* stream);
+/* dw[c_out][c_in][taps] (the layout of nn.Conv3d.weight, fp32) = sum over voxels of dy[v][c_out] * x[v + tap][c_in]; taps 27: 3x3x3 with
+ * padding 1 (:550), taps 1: 1x1x1 (:597, :1388, :1477, and the pixel (un)shuffle convs on rearranged tensors).  Any channel counts,
+ * fp32 accumulation, per-chunk partials summed in a fixed order.  workspace: diqt_conv_wgrad_workspace_bytes(). */
+int diqt_conv_wgrad_workspace_bytes(int n, int d0, int d1, int d2, int c_in, int c_out, int taps, size_t* bytes);
+int diqt_conv_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, int dtype, int n, int d0, int d1, int d2, int c_in, int c_out,
+                    int taps, float* dw, float* workspace, void* stream);
+/* losses = reduce(loss_fn(pred, target, 'none'), 'b ... -> b', 'mean') (:2355-2357) and d loss / d pred in one pass.  kind 0 l1, 1 l2,
+ * 2 smooth-l1; clamp_lo: pred.clamp_(min = lo) first (x_start objective, :2353); sample_weight[n] = p2 weight / (batch * count);
+ * loss_partial[n][nblk]: unweighted partial sums. */
+int diqt_loss_grad(const float* pred, const float* target, int n, int64_t count, int kind, int clamp_lo, float lo,
+                   const float* sample_weight, float* dpred, float* loss_partial, int nblk, void* stream);
+/* torch.optim.Adam step (no amsgrad) on one fp32 parameter tensor, gradient pre-multiplied by grad_scale; ema != NULL also updates
+ * the exponential moving average ema = ema * ema_decay + p * (1 - ema_decay) (ImagenTrainer.update). */
+int diqt_adam_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, float grad_scale, float* ema, float ema_decay, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Network ends.
  * ------------------------------------------------------------------------------------------ */
 /* init_conv (:1291, :1576): 3x3x3 conv over up to 8 single-channel fp32 planes (the channel

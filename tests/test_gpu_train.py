@@ -1,0 +1,219 @@
+"""Training step on the GPU (csrc/backward.cu + diffusioniqt_b200/train.py through the C ABI) against PyTorch autograd of the CPU oracle
+(oracle/unet_oracle.py is plain functional torch, so `loss.backward()` on it IS the reference's reverse pass, imagen_pytorch3D.py:2277-2387).
+Tolerances: fp32 mode 1e-3 relative L2 per parameter gradient (~40 convolutions deep, fp32 accumulation order differs); bf16 mode 6e-2."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from cases import FORWARD_CASES, build_inputs, make_configs, unet_kwargs_for_reference
+from helpers import max_rel, rel_err, spec_from_kwargs, weights_for
+from oracle.unet_oracle import unet_forward
+
+pytestmark = pytest.mark.gpu
+
+DT = [("fp32", torch.float32, 2e-4), ("bf16", torch.bfloat16, 2e-2)]
+
+
+def _cl(t, dt):
+    return t.permute(0, 2, 3, 4, 1).contiguous().to(dt).cuda()
+
+
+def _q(t, dt):
+    return t.to(dt).float()
+
+
+@pytest.mark.parametrize("name,dt,tol", DT)
+@pytest.mark.parametrize("c_in,c_out,dims,taps,n", [(16, 32, (8, 8, 8), 27, 2), (64, 64, (4, 16, 8), 27, 1), (2, 8, (6, 5, 7), 27, 1), (24, 1, (8, 8, 8), 1, 2),
+                                                     (128, 64, (8, 8, 8), 1, 1), (64, 192, (8, 8, 8), 27, 1)])
+def test_conv_wgrad(name, dt, tol, c_in, c_out, dims, taps, n):
+    from diffusioniqt_b200 import lib as L
+    if dt == torch.bfloat16 and (c_in % 8 or c_out % 8):
+        pytest.skip("bf16 rows are addressed in 16-byte vectors elsewhere; odd channel counts are exercised in fp32")
+    lib = L.load()
+    torch.manual_seed(c_in + c_out)
+    k = 3 if taps == 27 else 1
+    x = _q(torch.randn(n, c_in, *dims), dt)
+    dy = _q(torch.randn(n, c_out, *dims), dt)
+    w = torch.zeros(c_out, c_in, k, k, k, requires_grad=True)
+    F.conv3d(x, w, None, padding=k // 2).backward(dy)
+    xc, dyc = _cl(x, dt), _cl(dy, dt)
+    nb = C.c_size_t(0)
+    L.check(lib.diqt_conv_wgrad_workspace_bytes(n, *dims, c_in, c_out, taps, C.byref(nb)), "ws")
+    ws = torch.empty(nb.value // 4, dtype=torch.float32, device="cuda")
+    dw = torch.empty(c_out, c_in, taps, dtype=torch.float32, device="cuda")
+    L.check(lib.diqt_conv_wgrad(xc.data_ptr(), c_in, dyc.data_ptr(), c_out, L.BF16 if dt == torch.bfloat16 else L.F32, n, *dims, c_in, c_out, taps,
+                                dw.data_ptr(), ws.data_ptr(), L.current_stream()), "wgrad")
+    torch.cuda.synchronize()
+    assert max_rel(dw.cpu().reshape(w.shape), w.grad) < 2e-5     # inputs are exactly representable: only the summation order differs
+    dw2 = torch.empty_like(dw)
+    L.check(lib.diqt_conv_wgrad(xc.data_ptr(), c_in, dyc.data_ptr(), c_out, L.BF16 if dt == torch.bfloat16 else L.F32, n, *dims, c_in, c_out, taps,
+                                dw2.data_ptr(), ws.data_ptr(), L.current_stream()), "wgrad")
+    torch.cuda.synchronize()
+    assert torch.equal(dw, dw2)                                   # fixed summation order
+
+
+@pytest.mark.parametrize("name,dt,tol", DT)
+@pytest.mark.parametrize("film", [False, True])
+def test_groupnorm_film_mish_backward_kernels(name, dt, tol, film):
+    """diqt_bwd_reduce / diqt_bwd_apply around the host algebra against autograd of GroupNorm -> FiLM -> Mish (:546-563)."""
+    from diffusioniqt_b200 import Unet
+    from diffusioniqt_b200.train import UnetBackprop
+    torch.manual_seed(5)
+    n, c, G, S = 2, 64, 8, 8
+    gn = torch.nn.GroupNorm(G, c).cuda()
+    with torch.no_grad():
+        gn.weight.copy_(torch.randn(c) * 0.5 + 1)
+        gn.bias.copy_(torch.randn(c) * 0.3)
+    x = _q(torch.randn(n, c, S, S, S) * 1.5 + 0.3, dt)
+    dy = _q(torch.randn(n, c, S, S, S), dt)
+    acc = _q(torch.randn(n, c, S, S, S), dt)
+    fl = (torch.randn(n, 2 * c) * 0.4) if film else None
+    xr = x.clone().requires_grad_(True)
+    g2, b2 = gn.weight.detach().cpu().clone().requires_grad_(True), gn.bias.detach().cpu().clone().requires_grad_(True)
+    flr = fl.clone().requires_grad_(True) if film else None
+    y = F.group_norm(xr, G, g2, b2, eps=gn.eps)
+    if film:
+        y = y * (flr[:, :c, None, None, None] + 1) + flr[:, c:, None, None, None]
+    F.mish(y).backward(dy)
+    bp = UnetBackprop.__new__(UnetBackprop)
+    from diffusioniqt_b200 import lib as L
+    bp.lib = L.load()
+    z, saved = bp._gn_forward(_cl(x, dt), gn, fl.cuda().contiguous() if film else None)
+    assert max_rel(z.float().cpu().permute(0, 4, 1, 2, 3), F.mish(y).detach()) < tol
+    dx, dfilm = bp._gn_backward(saved, _cl(dy, dt), acc=_cl(acc, dt))
+    assert max_rel(dx.float().cpu().permute(0, 4, 1, 2, 3), xr.grad + acc) < tol
+    assert max_rel(gn.weight.grad.cpu(), g2.grad) < tol and max_rel(gn.bias.grad.cpu(), b2.grad) < tol
+    if film:
+        assert max_rel(dfilm.cpu(), flr.grad) < tol
+    else:
+        assert dfilm is None
+
+
+def _oracle_grads(case, target):
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in weights_for(case).items()}
+    x, lr, time = build_inputs(case)
+    out = unet_forward(sd, spec_from_kwargs(case["unet"]), x, time, lowres_cond_img=lr)
+    loss = F.mse_loss(out, target)
+    loss.backward()
+    return out.detach(), loss.item(), {k: v.grad for k, v in sd.items() if v.requires_grad and v.grad is not None}
+
+
+@pytest.mark.parametrize("name,mode,tol_out,tol_grad", [("cfg1_dim32_s16_b2", "fp32", 5e-4, 2e-3), ("deep_dim32_s8", "fp32", 5e-4, 2e-3),
+                                                        ("alt_dim32_s16", "fp32", 5e-4, 2e-3), ("driver_dim64_s16", "fp32", 5e-4, 2e-3),
+                                                        ("driver_dim64_s16", "bf16", 3e-2, 8e-2), ("cfg1_dim32_s16_b2", "bf16", 3e-2, 8e-2)])
+def test_unet_parameter_gradients_match_autograd_of_the_oracle(name, mode, tol_out, tol_grad):
+    from diffusioniqt_b200 import Unet
+    from diffusioniqt_b200.train import UnetBackprop
+    case = FORWARD_CASES[name]
+    x, lr, time = build_inputs(case)
+    torch.manual_seed(3)
+    target = torch.randn_like(x)
+    want_out, _, want = _oracle_grads(case, target)
+    unet = Unet(**unet_kwargs_for_reference(case))
+    unet.load_state_dict(weights_for(case))
+    unet = unet.cuda().set_compute_dtype(mode)
+    bp = UnetBackprop(unet)
+    pred = bp.forward(x.cuda(), time.cuda(), lowres_cond_img=lr.cuda())
+    assert rel_err(pred.cpu(), want_out) < tol_out
+    dpred = 2 * (pred - target.cuda()) / pred.numel()
+    bp.backward(dpred)
+    params = dict(unet.named_parameters())
+    worst = {}
+    for k, g in want.items():
+        assert params[k].grad is not None, f"no gradient for {k}"
+        if g.norm() < 1e-7 * max(1.0, float(params[k].detach().norm())):
+            continue
+        worst[k] = rel_err(params[k].grad.cpu(), g)
+    bad = {k: v for k, v in worst.items() if v > tol_grad}
+    assert not bad, f"{len(bad)} of {len(worst)} gradients off: " + ", ".join(f"{k}={v:.2e}" for k, v in sorted(bad.items(), key=lambda kv: -kv[1])[:8])
+    unused = [k for k, p in params.items() if p.grad is not None and k not in want]
+    assert not unused, f"gradients on parameters autograd leaves untouched: {unused[:5]}"
+
+
+@pytest.mark.parametrize("objective,loss_type,gamma", [("x_start", "l2", 0.5), ("noise", "l1", 0.0), ("v", "huber", 0.5)])
+def test_p_losses_matches_the_reference_formula(objective, loss_type, gamma):
+    """Imagen.p_losses (:2277-2373): q_sample, objective target, clamp, per-sample mean, p2 reweighting; loss and the gradient it starts."""
+    from diffusioniqt_b200 import Imagen, NullUnet, Unet
+    case = FORWARD_CASES["cfg1_dim32_s16_b2"]
+    unet = Unet(**unet_kwargs_for_reference(case))
+    unet.load_state_dict(weights_for(case))
+    min_bound = -0.3
+    imagen = Imagen(unets=(NullUnet(), unet), configs=make_configs(case), image_sizes=(16, 16), channels=1, timesteps=10, pred_objectives=objective,
+                    loss_type=loss_type, p2_loss_weight_gamma=gamma, min_bound=min_bound, cond_drop_prob=0.0, auto_normalize_img=False).cuda()
+    unet = imagen.unets[1].set_compute_dtype("fp32")
+    x, lr, _ = build_inputs(case)
+    torch.manual_seed(7)
+    noise = torch.randn_like(x)
+    times = torch.tensor([0.3, 0.8])
+    sched = imagen.noise_schedulers[1]
+    loss, pred, x_noisy, _ = imagen.p_losses(unet, x.cuda(), times.cuda(), noise_scheduler=sched, lowres_cond_img=lr.cuda(), noise=noise.cuda(),
+                                             pred_objective=objective, p2_loss_weight_gamma=gamma)
+    loss.backward()
+    # the same arithmetic on the CPU oracle with autograd
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in weights_for(case).items()}
+    xn, log_snr, alpha, sigma = (t.cpu() if torch.is_tensor(t) else t for t in sched.cpu().q_sample(x_start=x, t=times, noise=noise))
+    out = unet_forward(sd, spec_from_kwargs(case["unet"]), xn, sched.log_snr(times), lowres_cond_img=lr)
+    target = {"noise": noise, "x_start": x, "v": alpha * noise - sigma * x}[objective]
+    if objective == "x_start":
+        out = out.clamp(min=min_bound)
+    fn = {"l1": F.l1_loss, "l2": F.mse_loss, "huber": F.smooth_l1_loss}[loss_type]
+    losses = fn(out, target, reduction="none").mean(dim=(1, 2, 3, 4))
+    if gamma > 0:
+        losses = losses * (1 + log_snr.exp()) ** -gamma
+    want = losses.mean()
+    want.backward()
+    assert abs(loss.item() - want.item()) < 1e-4 * abs(want.item()) + 1e-7
+    assert rel_err(x_noisy.cpu(), xn) < 1e-6 and rel_err(pred.cpu(), out.detach()) < 5e-4
+    params = dict(imagen.unets[1].named_parameters())
+    for k in ("final_conv.weight", "init_conv.weight", "downs.0.1.block2.project.weight", "ups.0.1.block1.groupnorm.weight", "to_time_cond.0.weight",
+              "downs.1.3.0.time_mlp.1.weight", "downs.0.3.1.se.fc.0.weight"):
+        assert rel_err(params[k].grad.cpu(), sd[k].grad) < 3e-3, k
+
+
+def test_adam_kernel_matches_torch_adam_and_ema():
+    from diffusioniqt_b200.train import AdamState
+    torch.manual_seed(0)
+    p = torch.nn.Parameter(torch.randn(1000, 33, device="cuda"))
+    q = torch.nn.Parameter(p.detach().clone())
+    ema = p.detach().clone()
+    ema_ref = ema.clone()
+    ours, ref = AdamState([p], lr=3e-3, betas=(0.9, 0.99), eps=1e-8), torch.optim.Adam([q], lr=3e-3, betas=(0.9, 0.99), eps=1e-8)
+    for step in range(4):
+        g = torch.randn_like(p)
+        p.grad, q.grad = g.clone(), g.clone()
+        ours.step(ema_params=[ema], ema_decay=0.9)
+        ref.step()
+        ema_ref = ema_ref * 0.9 + q.detach() * 0.1
+        assert max_rel(p.detach().cpu(), q.detach().cpu()) < 1e-6
+        assert max_rel(ema.cpu(), ema_ref.cpu()) < 1e-6
+
+
+def test_trainer_steps_reduce_the_loss_and_refresh_the_sampler():
+    """ImagenTrainer.forward / update (trainer.py:1038-1130): a few optimizer steps on one fixed batch reduce the loss, the EMA copy follows
+    the schedule, and the sampling engines are rebuilt from the updated weights."""
+    from diffusioniqt_b200 import Imagen, ImagenTrainer, NullUnet, Unet
+    case = FORWARD_CASES["cfg1_dim32_s16_b2"]
+    unet = Unet(**unet_kwargs_for_reference(case))
+    unet.load_state_dict(weights_for(case))
+    imagen = Imagen(unets=(NullUnet(), unet), configs=make_configs(case), image_sizes=(16, 16), channels=1, timesteps=4, pred_objectives="x_start",
+                    loss_type="l2", p2_loss_weight_gamma=0.5, min_bound=-10.0, cond_drop_prob=0.0, auto_normalize_img=False).cuda()
+    imagen.unets[1].set_compute_dtype("fp32")
+    trainer = ImagenTrainer(configs=make_configs(case), imagen=imagen, lr=1e-4, use_ema=True, gradient_accumulation_steps=1, verbose=False)
+    trainer.train()
+    x, lr, _ = build_inputs(case)
+    before = {k: v.detach().clone() for k, v in imagen.unets[1].named_parameters()}
+    torch.manual_seed(11)
+    losses = []
+    for _ in range(8):
+        torch.manual_seed(11)       # the same times and noise every step: the loss must go down
+        total, pred, x_noisy, lowres = trainer(x, lr, unet_number=2)
+        losses.append(total)
+    assert losses[-1] < losses[0] and min(losses[1:]) < 0.98 * losses[0], losses
+    assert trainer.num_steps_taken(2) == 8
+    changed = sum(int(not torch.equal(before[k], v.detach())) for k, v in imagen.unets[1].named_parameters())
+    assert changed > 100
+    assert all(p.grad is None for p in imagen.unets[1].parameters())
+    out, _, _ = trainer.sample(batch_size=2, start_image_or_video=lr, start_at_unet_number=2, use_non_ema=True)
+    assert torch.isfinite(out).all()

@@ -1,0 +1,90 @@
+"""Host-side logic of the training step (diffusioniqt_b200/train.py) against PyTorch autograd on the CPU: the GroupNorm / FiLM / Mish
+coefficient algebra between the reduce and the apply kernel (the two kernels are emulated in torch here), the channels-last pixel
+(un)shuffles, the flipped-weight data gradient and the EMA schedule."""
+import torch
+import torch.nn.functional as F
+
+from diffusioniqt_b200.train import _flip_t, _shuffle_cl, _unshuffle_cl, gn_backward_coefficients
+from oracle.unet_oracle import pixel_shuffle3d, pixel_unshuffle3d
+
+
+def _mish_grad(w):
+    sp = F.softplus(w)
+    t = torch.tanh(sp)
+    return t + w * torch.sigmoid(w) * (1 - t * t)
+
+
+def test_groupnorm_film_mish_backward_algebra_matches_autograd():
+    torch.manual_seed(0)
+    n, c, G, S = 2, 16, 4, 6
+    x = (torch.randn(n, c, S, S, S, dtype=torch.float64) * 1.7 + 0.4).requires_grad_(True)
+    gamma = torch.randn(c, dtype=torch.float64).requires_grad_(True)
+    beta = torch.randn(c, dtype=torch.float64).requires_grad_(True)
+    film = (torch.randn(n, 2 * c, dtype=torch.float64) * 0.5).requires_grad_(True)
+    dy = torch.randn(n, c, S, S, S, dtype=torch.float64)
+    scale, shift = film[:, :c, None, None, None], film[:, c:, None, None, None]
+    y = F.mish(F.group_norm(x, G, gamma, beta, eps=1e-5) * (scale + 1) + shift)
+    y.backward(dy)
+    # what the forward kernels leave behind: group mean / rstd and the folded affine w = a x + b
+    xd = x.detach()
+    xg = xd.reshape(n, G, -1)
+    mean, var = xg.mean(dim=2), xg.var(dim=2, unbiased=False)
+    rstd = 1 / torch.sqrt(var + 1e-5)
+    cpg = c // G
+    mu_c, r_c = mean.repeat_interleave(cpg, 1), rstd.repeat_interleave(cpg, 1)
+    k = 1 + film.detach()[:, :c]
+    a = r_c * gamma.detach() * k
+    b = (beta.detach() - mu_c * r_c * gamma.detach()) * k + film.detach()[:, c:]
+    # diqt_bwd_reduce (mode 1)
+    w = a[:, :, None, None, None] * xd + b[:, :, None, None, None]
+    dw = dy * _mish_grad(w)
+    S1, S2x = dw.sum(dim=(2, 3, 4)), (dw * xd).sum(dim=(2, 3, 4))
+    c1, c2, c3, dgamma, dbeta, dfilm = gn_backward_coefficients(S1, S2x, mean, rstd, gamma.detach(), beta.detach(), film.detach(), S ** 3, G)
+    # diqt_bwd_apply (mode 1)
+    dx = c1.double()[:, :, None, None, None] * dw + c2.double()[:, :, None, None, None] * xd + c3.double()[:, :, None, None, None]
+    assert torch.allclose(dx, x.grad, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(dgamma, gamma.grad, rtol=1e-9, atol=1e-9)
+    assert torch.allclose(dbeta, beta.grad, rtol=1e-9, atol=1e-9)
+    assert torch.allclose(dfilm.double(), film.grad, rtol=1e-5, atol=1e-5)
+    # without FiLM
+    x2 = xd.clone().requires_grad_(True)
+    y2 = F.mish(F.group_norm(x2, G, gamma.detach(), beta.detach(), eps=1e-5))
+    y2.backward(dy)
+    a2, b2 = r_c * gamma.detach(), beta.detach() - mu_c * r_c * gamma.detach()
+    dw2 = dy * _mish_grad(a2[:, :, None, None, None] * xd + b2[:, :, None, None, None])
+    c1, c2, c3, _, _, none = gn_backward_coefficients(dw2.sum(dim=(2, 3, 4)), (dw2 * xd).sum(dim=(2, 3, 4)), mean, rstd, gamma.detach(), beta.detach(),
+                                                     None, S ** 3, G)
+    dx2 = c1.double()[:, :, None, None, None] * dw2 + c2.double()[:, :, None, None, None] * xd + c3.double()[:, :, None, None, None]
+    assert none is None and torch.allclose(dx2, x2.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_channels_last_pixel_shuffles_match_the_oracle():
+    torch.manual_seed(1)
+    x = torch.randn(2, 3, 4, 6, 8)
+    cl = lambda t: t.permute(0, 2, 3, 4, 1).contiguous()
+    assert torch.equal(_unshuffle_cl(cl(x)), cl(pixel_unshuffle3d(x)))
+    y = torch.randn(2, 16, 2, 3, 4)
+    assert torch.equal(_shuffle_cl(cl(y)), cl(pixel_shuffle3d(y)))
+    assert torch.equal(_shuffle_cl(_unshuffle_cl(cl(x))), cl(x))
+
+
+def test_data_gradient_is_a_convolution_with_flipped_transposed_weights():
+    torch.manual_seed(2)
+    x = torch.randn(1, 5, 6, 7, 8, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(4, 5, 3, 3, 3, dtype=torch.float64)
+    dy = torch.randn(1, 4, 6, 7, 8, dtype=torch.float64)
+    F.conv3d(x, w, None, padding=1).backward(dy)
+    assert torch.allclose(F.conv3d(dy, _flip_t(w), None, padding=1), x.grad, atol=1e-10)
+    w1 = torch.randn(4, 5, 1, 1, 1, dtype=torch.float64)
+    x.grad = None
+    F.conv3d(x, w1).backward(dy)
+    assert torch.allclose(F.conv3d(dy, _flip_t(w1)), x.grad, atol=1e-10)
+
+
+def test_ema_schedule_of_the_trainer():
+    from diffusioniqt_b200.trainer import ImagenTrainer
+    d = ImagenTrainer._ema_decay
+    class T: EMA_BETA, EMA_UPDATE_AFTER, EMA_UPDATE_EVERY, EMA_INV_GAMMA, EMA_POWER = 0.9999, 100, 10, 1.0, 2.0 / 3.0
+    assert d(T, 100) == 0. and d(T, 101) == 0.
+    assert abs(d(T, 110) - (1 - (1 + 9) ** (-2 / 3))) < 1e-12
+    assert d(T, 10 ** 9) == 0.9999
