@@ -12,6 +12,8 @@
 // Weight gradients: conv_wgrad_simt (any shape, fp32 accumulation, per-chunk partials summed in a fixed order); the tcgen05 version for
 // channel counts that are multiples of 64 lives in wgrad_tc.cu.  Data gradients of the convolutions are convolutions with the flipped,
 // transposed weights and run through the forward kernels.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace diqt {
@@ -323,18 +325,42 @@ static int wgrad_chunks(int64_t total_vox, int taps, int tiles) {
   return (int)ch;
 }
 
+namespace diqt {   // wgrad_tc.cu
+bool wgrad_tc_supported(int dtype, int c_in, int c_out, int ld_x, int ld_dy, int taps);
+size_t wgrad_tc_workspace_bytes(int n, int d0, int d1, int d2, int c_in, int c_out, int taps);
+int wgrad_tc_run(const void* x, int ld_x, const void* dy, int ld_dy, int n, int d0, int d1, int d2, int c_in, int c_out, int taps, float* dw,
+                 float* workspace, cudaStream_t st);
+}  // namespace diqt
+
 extern "C" int diqt_conv_wgrad_workspace_bytes(int n, int d0, int d1, int d2, int c_in, int c_out, int taps, size_t* bytes) {
   DIQT_REQUIRE(bytes && n > 0 && d0 > 0 && d1 > 0 && d2 > 0 && c_in > 0 && c_out > 0 && (taps == 1 || taps == 27), "conv_wgrad_workspace_bytes: bad arguments");
   const int tiles = ((c_out + 63) / 64) * ((c_in + 63) / 64);
-  *bytes = (size_t)wgrad_chunks((int64_t)n * d0 * d1 * d2, taps, tiles) * taps * c_out * c_in * sizeof(float);
+  size_t b = (size_t)wgrad_chunks((int64_t)n * d0 * d1 * d2, taps, tiles) * taps * c_out * c_in * sizeof(float);
+  if (wgrad_tc_supported(DIQT_BF16, c_in, c_out, 8, 8, taps)) b = std::max(b, wgrad_tc_workspace_bytes(n, d0, d1, d2, c_in, c_out, taps));
+  *bytes = b;
+  return DIQT_OK;
+}
+
+extern "C" int diqt_conv_wgrad_resolved_impl(int dtype, int c_in, int c_out, int ld_x, int ld_dy, int taps, int impl, int* resolved) {
+  DIQT_REQUIRE(resolved && (impl == DIQT_IMPL_AUTO || impl == DIQT_IMPL_SIMT || impl == DIQT_IMPL_TC), "conv_wgrad_resolved_impl: bad arguments");
+  const bool tc = wgrad_tc_supported(dtype, c_in, c_out, ld_x, ld_dy, taps);
+  if (impl == DIQT_IMPL_TC && !tc) {
+    set_error("conv_wgrad: the tcgen05 kernel needs bf16 and channel counts that are multiples of 64 (got dtype=%d c_in=%d c_out=%d)", dtype, c_in, c_out);
+    return DIQT_EUNSUPPORTED;
+  }
+  *resolved = (impl == DIQT_IMPL_SIMT || !tc) ? DIQT_IMPL_SIMT : DIQT_IMPL_TC;
   return DIQT_OK;
 }
 
 extern "C" int diqt_conv_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, int dtype, int n, int d0, int d1, int d2, int c_in, int c_out, int taps,
-                               float* dw, float* workspace, void* stream) {
+                               int impl, float* dw, float* workspace, void* stream) {
   DIQT_REQUIRE(x && dy && dw && workspace && n > 0 && d0 > 0 && d1 > 0 && d2 > 0 && c_in > 0 && c_out > 0, "conv_wgrad: bad arguments");
   DIQT_REQUIRE(taps == 1 || taps == 27, "conv_wgrad: taps %d (1: 1x1x1, 27: 3x3x3 with padding 1)", taps);
   DIQT_REQUIRE(dtype == DIQT_F32 || dtype == DIQT_BF16, "conv_wgrad: bad dtype %d", dtype);
+  int resolved = 0;
+  const int rc = diqt_conv_wgrad_resolved_impl(dtype, c_in, c_out, ld_x, ld_dy, taps, impl, &resolved);
+  if (rc) return rc;
+  if (resolved == DIQT_IMPL_TC) return wgrad_tc_run(x, ld_x, dy, ld_dy, n, d0, d1, d2, c_in, c_out, taps, dw, workspace, (cudaStream_t)stream);
   const int ci_tiles = (c_in + 63) / 64, tiles = ((c_out + 63) / 64) * ci_tiles;
   const int64_t total = (int64_t)n * d0 * d1 * d2;
   const int nchunks = wgrad_chunks(total, taps, tiles);

@@ -11,7 +11,7 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 mkdir -p "$BUILD"
 OBJS=()
 PIDS=()
-for f in elementwise ends init_tc attn attn_tc linattn_tc backward volume conv_simt conv_tc conv_zm api; do
+for f in elementwise ends init_tc attn attn_tc linattn_tc backward wgrad_tc volume conv_simt conv_tc conv_zm api; do
   o="$BUILD/$f.o"
   if [ ! -f "$o" ] || [ "$HERE/$f.cu" -nt "$o" ] || [ "$HERE/common.cuh" -nt "$o" ] || [ "$HERE/tc_common.cuh" -nt "$o" ] || [ "$HERE/../../include/diqt.h" -nt "$o" ] || [ -n "${DIQT_PTXAS_V:-}" ]; then
     "$NVCC" "${FLAGS[@]}" -c "$HERE/$f.cu" -o "$o" &

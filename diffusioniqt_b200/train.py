@@ -179,8 +179,8 @@ class UnetBackprop:
         L.check(self.lib.diqt_conv_wgrad_workspace_bytes(n, d0, d1, d2, c_in, c_out, taps, C.byref(nbytes)), "conv_wgrad_workspace_bytes")
         ws = torch.empty(nbytes.value // 4, dtype=torch.float32, device=x.device)
         dw = torch.empty(c_out, c_in, taps, dtype=torch.float32, device=x.device)
-        L.check(self.lib.diqt_conv_wgrad(x.data_ptr(), c_in, dy.data_ptr(), c_out, _dt(x), n, d0, d1, d2, c_in, c_out, taps, dw.data_ptr(), ws.data_ptr(),
-                                         L.current_stream()), "conv_wgrad")
+        L.check(self.lib.diqt_conv_wgrad(x.data_ptr(), c_in, dy.data_ptr(), c_out, _dt(x), n, d0, d1, d2, c_in, c_out, taps, L.IMPL_AUTO, dw.data_ptr(),
+                                         ws.data_ptr(), L.current_stream()), "conv_wgrad")
         torch.cuda.current_stream().synchronize()
         return dw
 

@@ -271,8 +271,12 @@ int diqt_bwd_apply(const void* x, int ld_x, const void* dz, int ld_dz, const voi
  * padding 1 (:550), taps 1: 1x1x1 (:597, :1388, :1477, and the pixel (un)shuffle convs on rearranged tensors).  Any channel counts,
  * fp32 accumulation, per-chunk partials summed in a fixed order.  workspace: diqt_conv_wgrad_workspace_bytes(). */
 int diqt_conv_wgrad_workspace_bytes(int n, int d0, int d1, int d2, int c_in, int c_out, int taps, size_t* bytes);
+/* impl: DIQT_IMPL_AUTO / _SIMT / _TC.  TC (csrc/wgrad_tc.cu): bf16, channel counts multiples of 64: tcgen05.mma over the voxels with the
+ * dy box and the tap-shifted x boxes as MN-major operands exactly as TMA lands them (out-of-volume rows = zero padding), fp32
+ * accumulators in TMEM.  AUTO picks it whenever the shape allows. */
+int diqt_conv_wgrad_resolved_impl(int dtype, int c_in, int c_out, int ld_x, int ld_dy, int taps, int impl, int* resolved);
 int diqt_conv_wgrad(const void* x, int ld_x, const void* dy, int ld_dy, int dtype, int n, int d0, int d1, int d2, int c_in, int c_out,
-                    int taps, float* dw, float* workspace, void* stream);
+                    int taps, int impl, float* dw, float* workspace, void* stream);
 /* losses = reduce(loss_fn(pred, target, 'none'), 'b ... -> b', 'mean') (:2355-2357) and d loss / d pred in one pass.  kind 0 l1, 1 l2,
  * 2 smooth-l1; clamp_lo: pred.clamp_(min = lo) first (x_start objective, :2353); sample_weight[n] = p2 weight / (batch * count);
  * loss_partial[n][nblk]: unweighted partial sums. */

@@ -26,7 +26,8 @@ def _q(t, dt):
 
 @pytest.mark.parametrize("name,dt,tol", DT)
 @pytest.mark.parametrize("c_in,c_out,dims,taps,n", [(16, 32, (8, 8, 8), 27, 2), (64, 64, (4, 16, 8), 27, 1), (2, 8, (6, 5, 7), 27, 1), (24, 1, (8, 8, 8), 1, 2),
-                                                     (128, 64, (8, 8, 8), 1, 1), (64, 192, (8, 8, 8), 27, 1)])
+                                                     (128, 64, (8, 8, 8), 1, 1), (64, 192, (8, 8, 8), 27, 1), (128, 128, (16, 16, 16), 27, 1),
+                                                     (64, 64, (6, 10, 12), 27, 3), (256, 128, (4, 4, 4), 27, 1), (512, 64, (8, 8, 8), 1, 2)])
 def test_conv_wgrad(name, dt, tol, c_in, c_out, dims, taps, n):
     from diffusioniqt_b200 import lib as L
     if dt == torch.bfloat16 and (c_in % 8 or c_out % 8):
@@ -42,16 +43,26 @@ def test_conv_wgrad(name, dt, tol, c_in, c_out, dims, taps, n):
     nb = C.c_size_t(0)
     L.check(lib.diqt_conv_wgrad_workspace_bytes(n, *dims, c_in, c_out, taps, C.byref(nb)), "ws")
     ws = torch.empty(nb.value // 4, dtype=torch.float32, device="cuda")
-    dw = torch.empty(c_out, c_in, taps, dtype=torch.float32, device="cuda")
-    L.check(lib.diqt_conv_wgrad(xc.data_ptr(), c_in, dyc.data_ptr(), c_out, L.BF16 if dt == torch.bfloat16 else L.F32, n, *dims, c_in, c_out, taps,
-                                dw.data_ptr(), ws.data_ptr(), L.current_stream()), "wgrad")
-    torch.cuda.synchronize()
-    assert max_rel(dw.cpu().reshape(w.shape), w.grad) < 2e-5     # inputs are exactly representable: only the summation order differs
-    dw2 = torch.empty_like(dw)
-    L.check(lib.diqt_conv_wgrad(xc.data_ptr(), c_in, dyc.data_ptr(), c_out, L.BF16 if dt == torch.bfloat16 else L.F32, n, *dims, c_in, c_out, taps,
-                                dw2.data_ptr(), ws.data_ptr(), L.current_stream()), "wgrad")
-    torch.cuda.synchronize()
-    assert torch.equal(dw, dw2)                                   # fixed summation order
+    code = L.BF16 if dt == torch.bfloat16 else L.F32
+    res = C.c_int(0)
+    L.check(lib.diqt_conv_wgrad_resolved_impl(code, c_in, c_out, c_in, c_out, taps, L.IMPL_AUTO, C.byref(res)), "resolved")
+    tc = dt == torch.bfloat16 and c_in % 64 == 0 and c_out % 64 == 0
+    assert res.value == (L.IMPL_TC if tc else L.IMPL_SIMT)          # the tcgen05 kernel whenever the shape allows
+    for impl in ([L.IMPL_TC, L.IMPL_SIMT] if tc else [L.IMPL_AUTO]):
+        dw = torch.full((c_out, c_in, taps), float("nan"), dtype=torch.float32, device="cuda")
+        L.check(lib.diqt_conv_wgrad(xc.data_ptr(), c_in, dyc.data_ptr(), c_out, code, n, *dims, c_in, c_out, taps, impl, dw.data_ptr(), ws.data_ptr(),
+                                    L.current_stream()), "wgrad")
+        torch.cuda.synchronize()
+        assert max_rel(dw.cpu().reshape(w.shape), w.grad) < 2e-5     # inputs are exactly representable: only the summation order differs
+        dw2 = torch.empty_like(dw)
+        L.check(lib.diqt_conv_wgrad(xc.data_ptr(), c_in, dyc.data_ptr(), c_out, code, n, *dims, c_in, c_out, taps, impl, dw2.data_ptr(), ws.data_ptr(),
+                                    L.current_stream()), "wgrad")
+        torch.cuda.synchronize()
+        assert torch.equal(dw, dw2)                                   # fixed summation order
+    if not tc:
+        with pytest.raises(L.DiqtError):
+            L.check(lib.diqt_conv_wgrad(xc.data_ptr(), c_in, dyc.data_ptr(), c_out, code, n, *dims, c_in, c_out, taps, L.IMPL_TC, dw.data_ptr(), ws.data_ptr(),
+                                        L.current_stream()), "wgrad")
 
 
 @pytest.mark.parametrize("name,dt,tol", DT)
