@@ -34,7 +34,16 @@ inline BwMap bw_map(int c, int vec, int max_threads) {
 inline int64_t bw_vpb(int64_t voxels, int nblk) { return (voxels + nblk - 1) / nblk; }
 
 // d/dw [ w tanh(softplus(w)) ] = T + w sigma(w) (1 - T^2),  T = n / (n + 2),  n = u (u + 2),  u = e^w ;  1 - T^2 = 4 (n + 1) / (n + 2)^2
+template <bool kFast>
 __device__ __forceinline__ float mish_grad(float w) {
+  if (kFast) {   // bf16 storage: ex2.approx + two rcp.approx (relative error ~1e-6, far below the bf16 rounding of the result)
+    float u, d, e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(fminf(w, 20.f) * 1.4426950408889634f));
+    const float n = u * (u + 2.f);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(n + 2.f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(1.f + u));
+    return fmaf(w * u * e, 4.f * (n + 1.f) * d * d, n * d);
+  }
   const float u = expf(fminf(w, 20.f));      // w > 20: T = 1 and the second term vanishes in fp32
   const float n = u * (u + 2.f);
   const float d = 1.f / (n + 2.f);
@@ -42,6 +51,10 @@ __device__ __forceinline__ float mish_grad(float w) {
   const float sig = u / (1.f + u);
   return fmaf(w * sig, 4.f * (n + 1.f) * d * d, T);
 }
+template <typename T>
+struct FastMath { static constexpr bool value = false; };
+template <>
+struct FastMath<__nv_bfloat16> { static constexpr bool value = true; };
 
 }  // namespace
 
@@ -81,7 +94,7 @@ __global__ void __launch_bounds__(256) bwd_reduce_kernel(const T* x, int ld_x, c
     for (int u = 0; u < 2; ++u)
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
-        const float t = MODE ? gr[u].v[i] * mish_grad(fmaf(av[i], xr[u].v[i], bv[i])) : gr[u].v[i];
+        const float t = MODE ? gr[u].v[i] * mish_grad<FastMath<T>::value>(fmaf(av[i], xr[u].v[i], bv[i])) : gr[u].v[i];
         s1[i] += t;
         s2[i] = fmaf(t, xr[u].v[i], s2[i]);
       }
@@ -127,23 +140,127 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* x, int ld_x, co
     k3[i] = c3 ? __ldcg(c3 + o) : 0.f;
   }
   const int64_t base = (int64_t)n * voxels;
-  for (int64_t v = v0 + lane; v < v1; v += lanes) {
-    Vec<T> xr, gr, ar, o;
-    gr.load(dz + (base + v) * ld_dz + col * VEC);
-    if (MODE || c2) xr.load(x + (base + v) * ld_x + col * VEC);
-    else {
+  const bool need_x = MODE || c2;
+  for (int64_t v = v0 + lane; v < v1; v += 2 * (int64_t)lanes) {   // two rows in flight per thread
+    Vec<T> xr[2], gr[2], ar[2];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) xr.v[i] = 0.f;
+    for (int u = 0; u < 2; ++u) {
+      const int64_t vv = v + (int64_t)u * lanes;
+      if (vv < v1) {
+        gr[u].load(dz + (base + vv) * ld_dz + col * VEC);
+        if (need_x) xr[u].load(x + (base + vv) * ld_x + col * VEC);
+        if (acc) ar[u].load(acc + (base + vv) * ld_acc + col * VEC);
+      }
     }
-    if (acc) ar.load(acc + (base + v) * ld_acc + col * VEC);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) {
-      const float t = MODE ? gr.v[i] * mish_grad(fmaf(av[i], xr.v[i], bv[i])) : gr.v[i];
-      float r = fmaf(k1[i], t, fmaf(k2[i], xr.v[i], k3[i]));
-      if (acc) r += ar.v[i];
-      o.v[i] = r;
+    for (int u = 0; u < 2; ++u) {
+      const int64_t vv = v + (int64_t)u * lanes;
+      if (vv >= v1) break;
+      Vec<T> o;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        const float xv = need_x ? xr[u].v[i] : 0.f;
+        const float t = MODE ? gr[u].v[i] * mish_grad<FastMath<T>::value>(fmaf(av[i], xv, bv[i])) : gr[u].v[i];
+        float r = fmaf(k1[i], t, fmaf(k2[i], xv, k3[i]));
+        if (acc) r += ar[u].v[i];
+        o.v[i] = r;
+      }
+      o.store(out + (base + vv) * ld_out + col * VEC);
     }
-    o.store(out + (base + v) * ld_out + col * VEC);
+  }
+}
+
+// ---- the (n, c)-sized algebra between reduce and apply for GroupNorm -> FiLM -> Mish (see gn_backward_coefficients in train.py for the
+// derivation): one CTA, fp64, fixed summation order.  fpart: the forward statistics (sum x, sum x^2), bpart: (sum dw, sum dw x).
+__global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* fpart, int nblk_f, const float* bpart, int nblk_b, int n, int64_t voxels, int c,
+                                                               int groups, float eps, const float* gamma, const float* beta, const float* film,
+                                                               float* c1, float* c2, float* c3, float* dgamma, float* dbeta, float* dfilm) {
+  extern __shared__ double fin_sm[];
+  const int parts = max(1, (int)blockDim.x / c), cpg = c / groups;
+  double* acc = fin_sm;                          // [parts][c][4]
+  double* tot = acc + (size_t)parts * c * 4;     // [c][4]: sum x, sum x^2, S1, S2x   (later [c][2]: kg S1, kg S2)
+  double* gst = tot + (size_t)c * 4;             // [groups][4]: mean, rstd, m1, m2
+  pdl_sync();
+  const double cnt = (double)voxels * cpg;
+  double dg[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};   // thread tid owns channels tid, tid + blockDim, ... (c <= 4096)
+  for (int nv = 0; nv < n; ++nv) {
+    for (int idx = threadIdx.x; idx < parts * c; idx += blockDim.x) {
+      const int ch = idx % c, part = idx / c;
+      double s = 0, q = 0, s1 = 0, s2 = 0;
+      auto sum_rows = [&](const float* p, int nblk, double& o0, double& o1) {   // four loads in flight, summation order unchanged
+        const float2 zero = make_float2(0.f, 0.f);
+        for (int b = part; b < nblk; b += 4 * parts) {
+          float2 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            v[u] = b + u * parts < nblk ? __ldcg(reinterpret_cast<const float2*>(p + (((int64_t)nv * nblk + b + u * parts) * c + ch) * 2)) : zero;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { o0 += v[u].x; o1 += v[u].y; }
+        }
+      };
+      sum_rows(fpart, nblk_f, s, q);
+      sum_rows(bpart, nblk_b, s1, s2);
+      double* a = acc + ((size_t)part * c + ch) * 4;
+      a[0] = s; a[1] = q; a[2] = s1; a[3] = s2;
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      double t[4] = {0, 0, 0, 0};
+      for (int pz = 0; pz < parts; ++pz)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) t[j] += acc[((size_t)pz * c + ch) * 4 + j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tot[ch * 4 + j] = t[j];
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      double s = 0, q = 0;
+      for (int i = 0; i < cpg; ++i) { s += tot[(g * cpg + i) * 4]; q += tot[(g * cpg + i) * 4 + 1]; }
+      const double mean = s / cnt;
+      double var = q / cnt - mean * mean;
+      if (var < 0) var = 0;
+      gst[g * 4] = mean;
+      gst[g * 4 + 1] = 1.0 / sqrt(var + (double)eps);
+    }
+    __syncthreads();
+    int slot = 0;
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x, ++slot) {
+      const int g = ch / cpg;
+      const double mu = gst[g * 4], r = gst[g * 4 + 1];
+      const double S1 = tot[ch * 4 + 2], S2 = r * (tot[ch * 4 + 3] - mu * S1);
+      const double k = film ? 1.0 + (double)film[(int64_t)nv * 2 * c + ch] : 1.0;
+      const double ga = gamma[ch], be = beta[ch];
+      if (slot < 4) { db[slot] += k * S1; dg[slot] += k * S2; }
+      if (dfilm) {
+        dfilm[(int64_t)nv * 2 * c + ch] = (float)(ga * S2 + be * S1);
+        dfilm[(int64_t)nv * 2 * c + c + ch] = (float)S1;
+      }
+      tot[ch * 4] = k * ga * S1;      // (sum x / sum x^2 are consumed: reuse the slots)
+      tot[ch * 4 + 1] = k * ga * S2;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      double a1 = 0, a2 = 0;
+      for (int i = 0; i < cpg; ++i) { a1 += tot[(g * cpg + i) * 4]; a2 += tot[(g * cpg + i) * 4 + 1]; }
+      gst[g * 4 + 2] = a1 / cnt;
+      gst[g * 4 + 3] = a2 / cnt;
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      const int g = ch / cpg;
+      const double mu = gst[g * 4], r = gst[g * 4 + 1], m1 = gst[g * 4 + 2], m2 = gst[g * 4 + 3];
+      const double k = film ? 1.0 + (double)film[(int64_t)nv * 2 * c + ch] : 1.0;
+      const int64_t o = (int64_t)nv * c + ch;
+      c1[o] = (float)(r * k * (double)gamma[ch]);
+      c2[o] = (float)(-r * r * m2);
+      c3[o] = (float)(r * (r * m2 * mu - m1));
+    }
+    __syncthreads();
+  }
+  int slot = 0;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x, ++slot) {
+    dgamma[ch] = (float)dg[slot];
+    dbeta[ch] = (float)db[slot];
   }
 }
 
@@ -207,6 +324,57 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const T* x, int ld
       const int co = co0 + ty * 4 + i, ci = ci0 + tx * 4 + j;
       if (co < c_out && ci < c_in) dst[(int64_t)co * c_in + ci] = acc[i][j];
     }
+}
+
+// Narrow inputs (c_in <= 16: init_conv :1291 sees the 2-channel concat of x_t and the low-field patch): thread = (output channel, voxel
+// lane), the c_in input values of a voxel are a broadcast load, c_in FMAs per dy value; same partial layout as the tiled kernel.
+constexpr int WGS_LANES = 4;
+template <typename T, int CI>
+__global__ void __launch_bounds__(64 * WGS_LANES) conv_wgrad_narrow_kernel(const T* x, int ld_x, const T* dy, int ld_dy, int n, int d0, int d1, int d2, int c_in,
+                                                                           int c_out, int taps, int64_t vox_per_chunk, float* partial) {
+  __shared__ float red[WGS_LANES][64][CI];
+  const int chunk = blockIdx.x, tap = blockIdx.y, co0 = blockIdx.z * 64;
+  const int co = co0 + (threadIdx.x & 63), lane = threadIdx.x >> 6;
+  const int oz = taps == 27 ? tap / 9 - 1 : 0, oy = taps == 27 ? (tap / 3) % 3 - 1 : 0, ox = taps == 27 ? tap % 3 - 1 : 0;
+  const int64_t vol = (int64_t)d0 * d1 * d2, total = vol * n;
+  const int64_t r0 = (int64_t)chunk * vox_per_chunk, r1 = min(total, r0 + vox_per_chunk);
+  const int64_t shift = ((int64_t)oz * d1 + oy) * d2 + ox;
+  pdl_sync();
+  float acc[CI];
+#pragma unroll
+  for (int i = 0; i < CI; ++i) acc[i] = 0.f;
+  // voxel coordinates are advanced incrementally (a 64-bit division per voxel made the first version of this kernel 20x slower)
+  int cz, cy, cx;
+  {
+    const int64_t vv = (r0 + lane) % vol;
+    cz = (int)(vv / ((int64_t)d1 * d2)); cy = (int)((vv / d2) % d1); cx = (int)(vv % d2);
+  }
+  for (int64_t row = r0 + lane; row < r1; row += WGS_LANES) {
+    const int z = cz + oz, y = cy + oy, xx = cx + ox;
+    cx += WGS_LANES;
+    while (cx >= d2) {
+      cx -= d2;
+      if (++cy == d1) { cy = 0; if (++cz == d0) cz = 0; }
+    }
+    if ((unsigned)z >= (unsigned)d0 || (unsigned)y >= (unsigned)d1 || (unsigned)xx >= (unsigned)d2) continue;   // warp-uniform: a warp shares the voxel
+    const float g = co < c_out ? to_float(dy[row * ld_dy + co]) : 0.f;
+    const T* xr = x + (row + shift) * ld_x;
+#pragma unroll
+    for (int i = 0; i < CI; ++i)
+      if (i < c_in) acc[i] = fmaf(g, to_float(xr[i]), acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < CI; ++i) red[lane][threadIdx.x & 63][i] = acc[i];
+  __syncthreads();
+  if (lane == 0 && co < c_out) {
+    float* dst = partial + (((int64_t)chunk * taps + tap) * c_out + co) * c_in;
+    for (int i = 0; i < c_in; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int l = 0; l < WGS_LANES; ++l) s += red[l][threadIdx.x & 63][i];   // fixed order
+      dst[i] = s;
+    }
+  }
 }
 
 // dw[c_out][c_in][taps] = sum_chunks partial[chunk][tap][c_out][c_in]  (fixed order; the layout of nn.Conv3d.weight)
@@ -316,6 +484,25 @@ extern "C" int diqt_bwd_apply(const void* x, int ld_x, const void* dz, int ld_dz
   return check_launch("bwd_apply");
 }
 
+extern "C" int diqt_gn_bwd_finalize(const float* fwd_partial, int nblk_f, const float* bwd_partial, int nblk_b, int n, int64_t voxels, int c, int groups,
+                                    float eps, const float* gamma, const float* beta, const float* film, float* c1, float* c2, float* c3, float* dgamma,
+                                    float* dbeta, float* dfilm, void* stream) {
+  DIQT_REQUIRE(fwd_partial && bwd_partial && gamma && beta && c1 && c2 && c3 && dgamma && dbeta && n > 0 && nblk_f > 0 && nblk_b > 0, "gn_bwd_finalize: bad arguments");
+  DIQT_REQUIRE(groups > 0 && c % groups == 0 && c <= 4096, "gn_bwd_finalize: c=%d groups=%d", c, groups);
+  DIQT_REQUIRE(!dfilm || film, "gn_bwd_finalize: dfilm without film");
+  const int threads = 1024, parts = threads / c > 0 ? threads / c : 1;
+  const size_t sh = ((size_t)parts * c * 4 + (size_t)c * 4 + (size_t)groups * 4) * sizeof(double);
+  DIQT_REQUIRE(sh <= 200 * 1024, "gn_bwd_finalize: c=%d too wide", c);
+  static bool attr_set = false;
+  if (sh > 48 * 1024 && !attr_set) {
+    DIQT_CUDA(cudaFuncSetAttribute(gn_bwd_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  launch_pdl(gn_bwd_finalize_kernel, dim3(1), dim3(threads), sh, (cudaStream_t)stream, fwd_partial, nblk_f, bwd_partial, nblk_b, n, voxels, c, groups, eps, gamma,
+             beta, film, c1, c2, c3, dgamma, dbeta, dfilm);
+  return check_launch("gn_bwd_finalize");
+}
+
 static int wgrad_chunks(int64_t total_vox, int taps, int tiles) {
   int64_t ch = 1184 / ((int64_t)taps * tiles);
   if (ch > 64) ch = 64;
@@ -368,7 +555,20 @@ extern "C" int diqt_conv_wgrad(const void* x, int ld_x, const void* dy, int ld_d
   vpc = (vpc + WG_VT - 1) / WG_VT * WG_VT;
   const dim3 grid(nchunks, taps, tiles);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == DIQT_BF16)
+  if (c_in <= 16) {
+    const dim3 ngrid(nchunks, taps, (c_out + 63) / 64);
+#define DIQT_WG_NARROW(T, CI)                                                                                                                         \
+  launch_pdl(conv_wgrad_narrow_kernel<T, CI>, ngrid, 64 * WGS_LANES, 0, st, (const T*)x, ld_x, (const T*)dy, ld_dy, n, d0, d1, d2, c_in, c_out, taps, vpc, \
+             workspace)
+    if (dtype == DIQT_BF16) {
+      if (c_in <= 2) DIQT_WG_NARROW(__nv_bfloat16, 2); else if (c_in <= 4) DIQT_WG_NARROW(__nv_bfloat16, 4);
+      else if (c_in <= 8) DIQT_WG_NARROW(__nv_bfloat16, 8); else DIQT_WG_NARROW(__nv_bfloat16, 16);
+    } else {
+      if (c_in <= 2) DIQT_WG_NARROW(float, 2); else if (c_in <= 4) DIQT_WG_NARROW(float, 4);
+      else if (c_in <= 8) DIQT_WG_NARROW(float, 8); else DIQT_WG_NARROW(float, 16);
+    }
+#undef DIQT_WG_NARROW
+  } else if (dtype == DIQT_BF16)
     launch_pdl(conv_wgrad_simt_kernel<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)x, ld_x, (const __nv_bfloat16*)dy, ld_dy, n, d0, d1, d2, c_in,
                c_out, taps, ci_tiles, vpc, workspace);
   else

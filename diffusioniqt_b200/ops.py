@@ -16,6 +16,14 @@ _MODES = {"k3": L.CONV_K3, "k1": L.CONV_K1, "down": L.CONV_DOWN, "up": L.CONV_UP
 _IMPLS = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tc": L.IMPL_TC, "zm": L.IMPL_ZM}
 
 
+SYNC = True   # wrappers wait for their kernels (tests read results right away); the training step switches this off and lets the stream run ahead
+
+
+def _sync():
+    if SYNC:
+        torch.cuda.current_stream().synchronize()
+
+
 def _dt(t: torch.Tensor) -> int:
     if t.dtype == torch.bfloat16:
         return L.BF16
@@ -120,7 +128,7 @@ def conv3d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
                 if nb.value > 0:
                     stats = buf[: n * nb.value * c_out * 2].view(n, nb.value, c_out, 2)
         L.check(lib.diqt_conv_run(plan.value, st), "conv_run")
-        torch.cuda.current_stream().synchronize()
+        _sync()
     finally:
         lib.diqt_conv_plan_destroy(plan.value)
     return (out, stats) if with_stats else out
@@ -148,7 +156,7 @@ def channel_stats_grouped(x: torch.Tensor, nblk: int = 8):
     tick = torch.zeros(n * ng.value, dtype=torch.int32, device=x.device)
     L.check(lib.diqt_channel_stats_g(x.data_ptr(), _dt(x), n, vox, c, c, nblk, part.data_ptr(), grp.data_ptr(), tick.data_ptr(),
                                      L.current_stream()), "channel_stats_g")
-    torch.cuda.current_stream().synchronize()
+    _sync()
     assert int(tick.abs().sum()) == 0, "tickets must reset themselves"
     return part, grp
 
@@ -168,7 +176,7 @@ def group_norm_film_mish(x: torch.Tensor, groups: int, gamma, beta, scale_shift:
         y = torch.empty_like(x)
         L.check(lib.diqt_gn_mish_g(x.data_ptr(), c, y.data_ptr(), c, _dt(x), n, vox, c, grp.data_ptr(), grp.shape[1], groups, eps, g.data_ptr(),
                                    be.data_ptr(), L.ptr(film), 2 * c, 0, 1, nblk, L.current_stream()), "gn_mish_g")
-        torch.cuda.current_stream().synchronize()
+        _sync()
         return y
     part = channel_stats(x, nblk)
     a = torch.empty(n, c, dtype=torch.float32, device=x.device)
@@ -181,7 +189,7 @@ def group_norm_film_mish(x: torch.Tensor, groups: int, gamma, beta, scale_shift:
                                  a.data_ptr(), b.data_ptr(), st), "gn_finalize")
     y = torch.empty_like(x)
     L.check(lib.diqt_affine_mish(x.data_ptr(), c, y.data_ptr(), c, _dt(x), n, vox, c, a.data_ptr(), b.data_ptr(), nblk, 0, 0, st), "affine_mish")
-    torch.cuda.current_stream().synchronize()
+    _sync()
     return y
 
 
@@ -203,7 +211,7 @@ def se_scale_residual(h: torch.Tensor, res: torch.Tensor, w1, w2, nblk: int = 8,
         L.check(lib.diqt_scale_residual_g(h.data_ptr(), c, res.data_ptr(), c, out.data_ptr(), c, _dt(h), n, vox, c, grp.data_ptr(), grp.shape[1],
                                           w1.shape[0], w1.data_ptr(), w2.data_ptr(), nblk, opart.data_ptr(), ogrp.data_ptr(), tick.data_ptr(), st),
                 "scale_residual_g")
-        torch.cuda.current_stream().synchronize()
+        _sync()
         return out, None, ogrp
     part = channel_stats(h, nblk)
     gate = torch.empty(n, c, dtype=torch.float32, device=h.device)
@@ -214,7 +222,7 @@ def se_scale_residual(h: torch.Tensor, res: torch.Tensor, w1, w2, nblk: int = 8,
     opart = torch.empty(n, nblk, c, 2, dtype=torch.float32, device=h.device)
     L.check(lib.diqt_scale_residual(h.data_ptr(), c, res.data_ptr(), c, out.data_ptr(), c, _dt(h), n, vox, c, gate.data_ptr(), nblk,
                                     opart.data_ptr(), 0, 0, st), "scale_residual")
-    torch.cuda.current_stream().synchronize()
+    _sync()
     return out, gate, opart
 
 
@@ -300,7 +308,7 @@ def linear_attention(qkv, heads, dim_head, act=1, impl="auto"):
                                                 float(dim_head) ** -0.5, act, wp, C.byref(plan)), "linattn_tc_plan_create")
         try:
             L.check(lib.diqt_linattn_tc_run(plan.value, L.current_stream()), "linattn_tc_run")
-            torch.cuda.current_stream().synchronize()
+            _sync()
         finally:
             lib.diqt_linattn_tc_plan_destroy(plan.value)
         return out
@@ -332,7 +340,7 @@ def softmax_attention(qkv, heads, dim_head, act=1, impl="simt"):
                                              float(dim_head) ** -0.5, act, ws.data_ptr(), C.byref(plan)), "attn_tc_plan_create")
         try:
             L.check(lib.diqt_attn_tc_run(plan.value, L.current_stream()), "attn_tc_run")
-            torch.cuda.current_stream().synchronize()
+            _sync()
         finally:
             lib.diqt_attn_tc_plan_destroy(plan.value)
         return out

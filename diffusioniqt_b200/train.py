@@ -30,7 +30,20 @@ import torch.nn.functional as F
 from . import lib as L
 from . import ops
 
-NBLK = 32   # partial rows per volume for the statistics / reduce kernels
+def _nblk(t):
+    """partial rows per volume for the statistics / reduce / apply kernels: about four CTAs per SM over the whole batch, at least 64 voxels each"""
+    return int(max(1, min(320, 592 // t.shape[0], _vox(t) // 64)))
+
+
+class _stream_ordered:
+    """Inside the training step nothing reads results on the host: the per-call synchronisation of the ops wrappers is switched off, every
+    kernel and every PyTorch op is ordered by the current stream (which also makes the whole step capturable in a CUDA graph)."""
+
+    def __enter__(self):
+        self.prev, ops.SYNC = ops.SYNC, False
+
+    def __exit__(self, *exc):
+        ops.SYNC = self.prev
 
 
 def _dt(t):
@@ -115,12 +128,13 @@ class UnetBackprop:
     # ------------------------------------------------------------------ kernels
     def _stats(self, x):
         """-> per-(n, c) sums (n, c, 2) in fp64 from the partial rows of diqt_channel_stats."""
-        return ops.channel_stats(x, NBLK).double().sum(dim=1)
+        return ops.channel_stats(x, _nblk(x)).double().sum(dim=1)
 
     def _gn_forward(self, x, gn, film):
         """GroupNorm (+FiLM) folded into a per-(n, c) affine, then Mish.  Returns z and what the reverse pass needs."""
         n, c = x.shape[0], x.shape[-1]
         vox, G = _vox(x), gn.num_groups
+        NBLK = _nblk(x)
         part = ops.channel_stats(x, NBLK)
         a = torch.empty(n, c, dtype=torch.float32, device=x.device)
         b = torch.empty_like(a)
@@ -130,12 +144,7 @@ class UnetBackprop:
                                           a.data_ptr(), b.data_ptr(), st), "gn_finalize")
         z = torch.empty_like(x)
         L.check(self.lib.diqt_affine_mish(x.data_ptr(), c, z.data_ptr(), c, _dt(x), n, vox, c, a.data_ptr(), b.data_ptr(), NBLK, 0, 0, st), "affine_mish")
-        tot = part.double().sum(dim=1)                                # (n, c, 2)
-        g = tot.reshape(n, G, c // G, 2).sum(dim=2)                   # (n, G, 2)
-        cnt = float(vox * (c // G))
-        mean = g[..., 0] / cnt
-        rstd = 1.0 / torch.sqrt((g[..., 1] / cnt - mean * mean).clamp_min(0.0) + gn.eps)
-        return z, dict(x=x, a=a, b=b, mean=mean, rstd=rstd, gn=gn, film=film)
+        return z, dict(x=x, a=a, b=b, part=part, gn=gn, film=film)
 
     def _gn_backward(self, s, dz, acc=None):
         """Reverse of `_gn_forward`: returns dx (+ acc) and accumulates d gamma / d beta; FiLM gradients come back as (n, 2c) or None."""
@@ -143,19 +152,25 @@ class UnetBackprop:
         n, c = x.shape[0], x.shape[-1]
         vox, G = _vox(x), gn.num_groups
         cpg = c // G
+        NBLK = _nblk(x)
         part = torch.empty(n, NBLK, c, 2, dtype=torch.float32, device=x.device)
         st = L.current_stream()
         L.check(self.lib.diqt_bwd_reduce(x.data_ptr(), c, dz.data_ptr(), c, _dt(x), n, vox, c, a.data_ptr(), b.data_ptr(), 1, NBLK, part.data_ptr(), st),
                 "bwd_reduce")
-        tot = part.double().sum(dim=1)
-        c1, c2, c3, dgamma, dbeta, dfilm = gn_backward_coefficients(tot[..., 0], tot[..., 1], s["mean"], s["rstd"], gn.weight.detach(), gn.bias.detach(),
-                                                                    s["film"], vox, G)
+        # the (n, c)-sized algebra (gn_backward_coefficients below states it in torch; tests/test_train_host.py checks it against autograd)
+        fpart, film = s["part"], s["film"]
+        c1, c2, c3 = (torch.empty(n, c, dtype=torch.float32, device=x.device) for _ in range(3))
+        dgamma, dbeta = (torch.empty(c, dtype=torch.float32, device=x.device) for _ in range(2))
+        dfilm = torch.empty(n, 2 * c, dtype=torch.float32, device=x.device) if film is not None else None
+        gamma, beta = gn.weight.detach().float().contiguous(), gn.bias.detach().float().contiguous()
+        L.check(self.lib.diqt_gn_bwd_finalize(fpart.data_ptr(), fpart.shape[1], part.data_ptr(), NBLK, n, vox, c, G, gn.eps, gamma.data_ptr(), beta.data_ptr(),
+                                              L.ptr(film), c1.data_ptr(), c2.data_ptr(), c3.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), L.ptr(dfilm), st),
+                "gn_bwd_finalize")
         _accum(gn.bias, dbeta)
         _accum(gn.weight, dgamma)
         dx = torch.empty_like(x)
         L.check(self.lib.diqt_bwd_apply(x.data_ptr(), c, dz.data_ptr(), c, L.ptr(acc), c, dx.data_ptr(), c, _dt(x), n, vox, c, a.data_ptr(), b.data_ptr(),
                                         c1.data_ptr(), c2.data_ptr(), c3.data_ptr(), 1, NBLK, st), "bwd_apply")
-        torch.cuda.current_stream().synchronize()
         return dx, dfilm
 
     def _conv(self, x, conv, mode="k3"):
@@ -172,16 +187,16 @@ class UnetBackprop:
             return None
         return ops.conv3d(dy, _flip_t(conv.weight), None, mode=mode)
 
-    def _wgrad(self, x, dy, taps):
-        n, d0, d1, d2, c_in = x.shape
+    def _wgrad(self, x, dy, taps, c_in=None):
+        n, d0, d1, d2, ld_x = x.shape
+        c_in = ld_x if c_in is None else c_in
         c_out = dy.shape[-1]
         nbytes = C.c_size_t(0)
         L.check(self.lib.diqt_conv_wgrad_workspace_bytes(n, d0, d1, d2, c_in, c_out, taps, C.byref(nbytes)), "conv_wgrad_workspace_bytes")
         ws = torch.empty(nbytes.value // 4, dtype=torch.float32, device=x.device)
         dw = torch.empty(c_out, c_in, taps, dtype=torch.float32, device=x.device)
-        L.check(self.lib.diqt_conv_wgrad(x.data_ptr(), c_in, dy.data_ptr(), c_out, _dt(x), n, d0, d1, d2, c_in, c_out, taps, L.IMPL_AUTO, dw.data_ptr(),
+        L.check(self.lib.diqt_conv_wgrad(x.data_ptr(), ld_x, dy.data_ptr(), c_out, _dt(x), n, d0, d1, d2, c_in, c_out, taps, L.IMPL_AUTO, dw.data_ptr(),
                                          ws.data_ptr(), L.current_stream()), "conv_wgrad")
-        torch.cuda.current_stream().synchronize()
         return dw
 
     def _add(self, a, b):
@@ -200,7 +215,7 @@ class UnetBackprop:
         sv = dict(blk=blk, x=x, z1=z1, z2=z2, h2=h2, s1=s1, s2=s2, te=te)
         if blk.has_se:
             w1, w2 = blk.se.fc[0].weight, blk.se.fc[2].weight
-            out, gate, _ = ops.se_scale_residual(h2, res, w1, w2, NBLK)
+            out, gate, _ = ops.se_scale_residual(h2, res, w1, w2, _nblk(h2))
             sv["gate"] = gate
         else:
             out = self._add(h2, res)
@@ -210,6 +225,7 @@ class UnetBackprop:
         blk, x, h2 = sv["blk"], sv["x"], sv["h2"]
         n, c = h2.shape[0], h2.shape[-1]
         vox = _vox(h2)
+        NBLK = _nblk(h2)
         st = L.current_stream()
         # residual branch
         if blk.has_res_conv:
@@ -231,7 +247,6 @@ class UnetBackprop:
             d_h2 = torch.empty_like(h2)
             L.check(self.lib.diqt_bwd_apply(0, c, d_out.data_ptr(), c, 0, c, d_h2.data_ptr(), c, _dt(h2), n, vox, c, 0, 0, c1.data_ptr(), 0, c3.data_ptr(), 0,
                                             NBLK, st), "bwd_apply")
-            torch.cuda.current_stream().synchronize()
         else:
             d_h2 = d_out
         d_z2 = self._conv_backward(sv["z2"], blk.block2.project, d_h2)
@@ -243,6 +258,15 @@ class UnetBackprop:
 
     # ------------------------------------------------------------------ Unet.forward :1554-1684
     def forward(self, x, time, lowres_cond_img=None):
+        with _stream_ordered():
+            return self._forward(x, time, lowres_cond_img)
+
+    def backward(self, dpred):
+        """dpred: (n, c_out, S, S, S) fp32 gradient of the loss with respect to the prediction."""
+        with _stream_ordered():
+            return self._backward(dpred)
+
+    def _forward(self, x, time, lowres_cond_img=None):
         unet = self.unet
         assert not (unet.lowres_cond and lowres_cond_img is None), 'low resolution conditioning image must be present'
         dev = x.device
@@ -295,9 +319,8 @@ class UnetBackprop:
                 one = torch.ones(n_, c8, dtype=torch.float32, device=dev)
                 zero = torch.zeros_like(one)
                 act = torch.empty_like(pre)
-                L.check(self.lib.diqt_affine_mish(pre.data_ptr(), c8, act.data_ptr(), c8, _dt(pre), n_, _vox(pre), c8, one.data_ptr(), zero.data_ptr(), NBLK, 0, 0,
+                L.check(self.lib.diqt_affine_mish(pre.data_ptr(), c8, act.data_ptr(), c8, _dt(pre), n_, _vox(pre), c8, one.data_ptr(), zero.data_ptr(), _nblk(pre), 0, 0,
                                                   L.current_stream()), "affine_mish")
-                torch.cuda.current_stream().synchronize()
                 h = _shuffle_cl(act)
                 skip = hiddens.pop()
                 if unet.skip_connect_scale != 1.:
@@ -326,8 +349,7 @@ class UnetBackprop:
         self.saved = dict(tape=tape, skip_grads={})
         return pred.permute(0, 4, 1, 2, 3).contiguous()
 
-    def backward(self, dpred):
-        """dpred: (n, c_out, S, S, S) fp32 gradient of the loss with respect to the prediction."""
+    def _backward(self, dpred):
         assert self.saved is not None, "backward() needs a forward() first"
         unet, tape = self.unet, self.saved["tape"]
         dev = dpred.device
@@ -340,7 +362,12 @@ class UnetBackprop:
                 fc = unet.final_conv
                 taps = 27 if k == 3 else 1
                 dy = dpred.permute(0, 2, 3, 4, 1).contiguous().float()                               # (n, S, S, S, co)
-                _accum(fc.weight, self._wgrad(hf, dy, taps))
+                if k == 1 and co <= 16:
+                    # one output channel: the roles swapped (dw[co][ci] = sum_v dy[v][co] hf[v][ci] is the narrow-input gradient of a conv
+                    # that maps dy to hf), so the narrow kernel applies instead of a 64 x 64 tile with one live row
+                    _accum(fc.weight, self._wgrad(dy, hf, 1).transpose(0, 1).contiguous())
+                else:
+                    _accum(fc.weight, self._wgrad(hf, dy, taps))
                 _accum(fc.bias, dy.sum(dim=(0, 1, 2, 3)))
                 dy16 = torch.zeros(*dy.shape[:-1], 16, dtype=torch.float32, device=dev)
                 dy16[..., :co] = dy
@@ -364,8 +391,7 @@ class UnetBackprop:
                 zero = torch.zeros_like(one)
                 d_pre = torch.empty_like(pre)
                 L.check(self.lib.diqt_bwd_apply(pre.data_ptr(), c8, g.data_ptr(), c8, 0, c8, d_pre.data_ptr(), c8, _dt(pre), n_, _vox(pre), c8, one.data_ptr(),
-                                                zero.data_ptr(), one.data_ptr(), 0, 0, 1, NBLK, L.current_stream()), "bwd_apply")
-                torch.cuda.current_stream().synchronize()
+                                                zero.data_ptr(), one.data_ptr(), 0, 0, 1, _nblk(pre), L.current_stream()), "bwd_apply")
                 d = self._conv_backward(h_in, conv, d_pre, "k1")
             elif kind == "k1":
                 _, h_in, conv = rec
@@ -378,8 +404,7 @@ class UnetBackprop:
             elif kind == "init":
                 _, x16, cin = rec
                 conv = unet.init_conv
-                dw = self._wgrad(x16, d, 27).reshape(conv.weight.shape[0], 16, *conv.weight.shape[2:])
-                _accum(conv.weight, dw[:, :cin])
+                _accum(conv.weight, self._wgrad(x16, d, 27, c_in=cin))          # only the real input channels (row pitch 16)
                 _accum(conv.bias, self._stats(d)[..., 0].sum(dim=0).float())
         # FiLM rows -> time MLPs (autograd on (n, 2c) vectors)
         tes = [te for te, g in self._film_grads if g is not None]

@@ -267,6 +267,12 @@ int diqt_bwd_reduce(const void* x, int ld_x, const void* dz, int ld_dz, int dtyp
 int diqt_bwd_apply(const void* x, int ld_x, const void* dz, int ld_dz, const void* acc, int ld_acc, void* out, int ld_out, int dtype,
                    int n, int64_t voxels, int c, const float* a, const float* b, const float* c1, const float* c2, const float* c3,
                    int mode, int nblk, void* stream);
+/* The (n, c)-sized step between the two: from the forward statistics (fwd_partial[n][nblk_f][c][2] of diqt_channel_stats) and
+ * bwd_partial[n][nblk_b][c][2] of diqt_bwd_reduce (mode 1) to the coefficients c1, c2, c3 [n][c] of diqt_bwd_apply, d gamma / d beta [c]
+ * and (film != NULL) d (scale | shift) [n][2c]; fp64 inside, one CTA, fixed summation order. */
+int diqt_gn_bwd_finalize(const float* fwd_partial, int nblk_f, const float* bwd_partial, int nblk_b, int n, int64_t voxels, int c,
+                         int groups, float eps, const float* gamma, const float* beta, const float* film, float* c1, float* c2, float* c3,
+                         float* dgamma, float* dbeta, float* dfilm, void* stream);
 /* dw[c_out][c_in][taps] (the layout of nn.Conv3d.weight, fp32) = sum over voxels of dy[v][c_out] * x[v + tap][c_in]; taps 27: 3x3x3 with
  * padding 1 (:550), taps 1: 1x1x1 (:597, :1388, :1477, and the pixel (un)shuffle convs on rearranged tensors).  Any channel counts,
  * fp32 accumulation, per-chunk partials summed in a fixed order.  workspace: diqt_conv_wgrad_workspace_bytes(). */
