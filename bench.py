@@ -364,6 +364,97 @@ def torch_gpu_baseline(size, batch, reps=5):
     return out
 
 
+def train_step_record(size, batch, reps=5):
+    """SURVEY 8 f-4 next to the headline: one optimizer step (forward with the activations kept, loss gradient, reverse pass, Adam) of the
+    driver U-Net on one patch, bf16, captured once and replayed as ONE CUDA graph (CUDA events around the replays), against PyTorch autograd
+    over the reference's op list (oracle.unet_forward, the ATen / cuDNN calls of imagen_pytorch3D.py:1554-1684) + torch.optim.Adam(fused) on
+    the same GPU.  A baseline leg like torch_gpu_baseline: the oracle is timed, never shipped."""
+    import torch.nn.functional as F
+    from diffusioniqt_b200 import SRUnet256, lib as L
+    from diffusioniqt_b200.synth import synthetic_field, synthetic_state_dict
+    from diffusioniqt_b200.train import AdamState, UnetBackprop
+    from oracle.unet_oracle import UnetSpec, unet_forward
+    dev = torch.device("cuda")
+    unet = SRUnet256(**DRIVER_UNET, img_size=size)
+    sd = synthetic_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, seed=0)
+    unet.load_state_dict(sd)
+    unet = unet.to(dev).set_compute_dtype("bf16")
+    x = synthetic_field((batch, 1, size, size, size), 2).to(dev)
+    lr = synthetic_field((batch, 1, size, size, size), 1).to(dev)
+    t = torch.full((batch,), 1.3, device=dev)
+    target = synthetic_field((batch, 1, size, size, size), 3).to(dev)
+    opt = AdamState(unet.parameters(), lr=1e-6)
+    out = {}
+
+    def step():
+        bp = UnetBackprop(unet)
+        pred = bp.forward(x, t, lowres_cond_img=lr)
+        bp.backward(2 * (pred - target) / pred.numel())
+        opt.step()
+        opt.zero_grad()
+
+    def event_ms(fn):
+        fn()
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+        ev[0].record()
+        for i in range(reps):
+            fn()
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
+        return ms[len(ms) // 2]
+
+    n0 = L.launch_count()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+        launches = L.launch_count() - n0
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    out["ms_launched_from_python"] = event_ms(step)
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        out["ms_graph_replay"] = event_ms(g.replay)
+    except Exception as e:  # noqa: BLE001
+        out["graph_error"] = f"{type(e).__name__}: {e}"[:200]
+        torch.cuda.synchronize()
+    out["kernel_launches_of_this_library"] = int(launches)
+    sdg = {k: v.to(dev).requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    spec = UnetSpec(dim=64, init_dim=64, dim_mults=(1, 2, 4), num_resnet_blocks=(2, 2, 2), channels=1, lowres_cond=True, deep_feature=False)
+    ropt = torch.optim.Adam([v for v in sdg.values() if v.requires_grad], lr=1e-6, fused=True)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for name, amp in (("torch_autograd_fp32_tf32_ms", False), ("torch_autograd_bf16_autocast_ms", True)):
+            def ref():
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                    o = unet_forward(sdg, spec, x, t, lowres_cond_img=lr)
+                F.mse_loss(o.float(), target).backward()
+                ropt.step()
+                ropt.zero_grad(set_to_none=True)
+            try:
+                ref()
+                out[name] = event_ms(ref)
+            except Exception as e:  # noqa: BLE001
+                out[name] = None
+                out[name + "_error"] = f"{type(e).__name__}: {e}"[:200]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    ours = out.get("ms_graph_replay") or out["ms_launched_from_python"]
+    refs = [v for k, v in out.items() if k.startswith("torch_autograd") and isinstance(v, float)]
+    if refs:
+        out["speedup_over_fastest_torch_mode"] = min(refs) / ours
+    out["workload"] = "one optimizer step, driver U-Net (dim 64), %d^3 patch, batch %d, bf16, l2 loss, Adam" % (size, batch)
+    del sdg, unet
+    torch.cuda.empty_cache()
+    return out
+
+
 def volume_record(dev, rank, world, dist, side=256, timesteps=20, batch=7):
     """BASELINE config 3 through the same process group: one synthetic `side`^3 low-field volume cut into overlapping 64^3 patches
     (stride 32: 7^3 = 343 for 256^3, data.py:159-162), 5 % skip rule, contiguous shards over the ranks (343 = 8 * 43 - 1: the last rank
@@ -458,6 +549,7 @@ def main():
     ap.add_argument("--ref-denoise-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-gpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the training-step sub-record (SURVEY 8 f-4)")
     ap.add_argument("--no-volume", action="store_true", help="skip the BASELINE config 3 sub-record (whole 256^3 volume, T = 20)")
     ap.add_argument("--volume-side", type=int, default=256)
     ap.add_argument("--volume-timesteps", type=int, default=20)
@@ -595,6 +687,11 @@ def main():
             for k, v in line["torch_gpu_baseline"].items():
                 if isinstance(v, dict) and "ms_per_denoise_iteration" in v:
                     v["speedup_of_this_library"] = v["ms_per_denoise_iteration"] / ours
+        if not args.no_train_step:
+            try:
+                line["train_step"] = train_step_record(S, B)
+            except Exception as e:  # a failure of the secondary record must not take the headline line with it
+                line["train_step"] = dict(error=f"{type(e).__name__}: {e}"[:300])
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(S, args.timesteps, B, args.cpu_denoise_steps)
         print(json.dumps(line), flush=True)

@@ -202,7 +202,7 @@ static WgTcGeom wgrad_tc_geom(int n, int d0, int d1, int d2, int c_in, int c_out
   (void)cudaGetLastError();
   if (sms <= 0) sms = 148;
   const int per_chunk = ((g.nmb + 1) / 2) * g.ntile_n;
-  int nc = (sms + per_chunk - 1) / per_chunk;
+  int nc = sms / per_chunk;   // one wave: 22 x 7 = 154 CTAs on 148 SMs ran as two waves and took twice as long (profiles/r3j_ncu_wgrad_tc.csv)
   nc = std::max(1, std::min(nc, g.m_tiles));
   nc = std::min(nc, 64);
   g.nchunks = nc;

@@ -44,6 +44,26 @@ def _nblk(n: int, voxels: int, per_device: int = 148) -> int:
     return max(1, min(voxels // 128, max(1, per_device // n)))
 
 
+def deconv_as_conv3_weights(w, b):
+    """nn.ConvTranspose3d(k 3, stride 2, padding 1, output_padding 1) (imagen_pytorch3D.py:445-447) as a 3x3x3 conv (padding 1) to 8 c_out
+    channels followed by a pixel shuffle: output voxel 2 j + p takes, per axis, kernel tap 1 of input j (p = 0), or tap 2 of input j and tap 0
+    of input j + 1 (p = 1).  w: (c_in, c_out, 3, 3, 3) -> (8 c_out, c_in, 3, 3, 3) with channel = c_out_index * 8 + p1 * 4 + p2 * 2 + p3
+    (the order PixelShuffle3D :415-438 reads them in); the unused taps are zero."""
+    ci, co = w.shape[:2]
+    kmap = {(0, 1): 1, (1, 1): 2, (1, 2): 0}                      # (parity, conv tap a = offset + 1) -> transposed-conv tap
+    wc = torch.zeros(co, 2, 2, 2, ci, 3, 3, 3, dtype=w.dtype, device=w.device)
+    for p1 in range(2):
+        for p2 in range(2):
+            for p3 in range(2):
+                for a in range(3):
+                    for b_ in range(3):
+                        for c in range(3):
+                            ks = (kmap.get((p1, a)), kmap.get((p2, b_)), kmap.get((p3, c)))
+                            if None not in ks:
+                                wc[:, p1, p2, p3, :, a, b_, c] = w[:, :, ks[0], ks[1], ks[2]].t()
+    return wc.reshape(co * 8, ci, 3, 3, 3), b.repeat_interleave(8)
+
+
 class UnetEngine:
     def __init__(self, unet, batch: int, dims, dtype: str = "bf16", device=None, conv_impl: str = "auto", taps=()):
         self.lib = L.load()
@@ -558,10 +578,21 @@ class UnetEngine:
                 lo = nl - 2 - ui                      # resolution level of the output
                 c_up = dims[lo + 1]
                 ctot = c_up + dims[lo]
-                conv = upsample.net[0]
                 cat = Act(self.cat[lo], ctot, ctot)
-                # GEMM N = 8*c_up; stored channels c_up at pitch ctot (channel offset 0 of the concat buffer)
-                ops.append(self._conv_site(f"ups.{ui}.0.net.0", L.CONV_UP, lo + 1, x.c, x.ld, 8 * c_up, ctot, conv.weight, conv.bias, x.ptr, cat.ptr))
+                if hasattr(upsample, "deconv"):
+                    # Upsample_deconv (:440-457): ConvTranspose3d(k 3, stride 2) + Mish = a 3x3x3 conv to 8 c_up parity channels (zero taps
+                    # where a parity does not reach), then Mish + pixel shuffle, which the pixel-shuffle conv applies with identity weights
+                    wc, bc = deconv_as_conv3_weights(upsample.deconv[0].weight.detach().to(self.device), upsample.deconv[0].bias.detach().to(self.device))
+                    par = self._empty(n * self.level_vox[lo + 1], 8 * c_up)
+                    self._keep.append(par)
+                    ops.append(self._conv_site(f"ups.{ui}.0.deconv.0", L.CONV_K3, lo + 1, x.c, x.ld, 8 * c_up, 8 * c_up, wc, bc, x.ptr, par.data_ptr()))
+                    eye = torch.eye(8 * c_up, device=self.device).reshape(8 * c_up, 8 * c_up, 1, 1, 1)
+                    ops.append(self._conv_site(f"ups.{ui}.0.deconv.shuffle", L.CONV_UP, lo + 1, 8 * c_up, 8 * c_up, 8 * c_up, ctot, eye, None, par.data_ptr(),
+                                               cat.ptr))
+                else:
+                    conv = upsample.net[0]
+                    # GEMM N = 8*c_up; stored channels c_up at pitch ctot (channel offset 0 of the concat buffer)
+                    ops.append(self._conv_site(f"ups.{ui}.0.net.0", L.CONV_UP, lo + 1, x.c, x.ld, 8 * c_up, ctot, conv.weight, conv.bias, x.ptr, cat.ptr))
                 x, level = cat, lo
             x = add_resblock(init_block, x, level, next_out(level, init_block.dim_out), f"ups.{ui}.1")
             for i, blk in enumerate(blocks):

@@ -113,6 +113,8 @@ class UnetBackprop:
             unsupported.append("attention blocks")
         if unet.boundary:
             unsupported.append("boundary=True")
+        if any(m[0] is not None and hasattr(m[0], "deconv") for m in unet.ups):
+            unsupported.append("pixel_shuffle_upsample=False")
         if not isinstance(unet.init_conv, torch.nn.Conv3d):
             unsupported.append("init_cross_embed=True")
         if unet.has_cond_image or unet.self_cond:

@@ -103,6 +103,14 @@ class PixelShuffleUpsample(_NoForward):
         nn.init.zeros_(conv.bias.data)
 
 
+class Deconv3D(_NoForward):
+    """imagen_pytorch3D.py:440-457 (`Upsample_deconv`): deconv = [ConvTranspose3d(k 3, stride 2, padding 1, output_padding 1), Mish]."""
+
+    def __init__(self, inp_feat, out_feat):
+        super().__init__()
+        self.deconv = nn.Sequential(nn.ConvTranspose3d(inp_feat, out_feat, kernel_size=3, stride=2, padding=1, output_padding=1, bias=True), _Tag())
+
+
 class CrossEmbedLayer(_NoForward):
     """imagen_pytorch3D.py:661-686: parallel convs of several kernel sizes over the same input, concatenated along channels."""
 
@@ -195,12 +203,13 @@ class Unet(nn.Module):
         if init_cross_embed and boundary:
             unsupported.append("init_cross_embed=True with boundary=True (boundary_pad followed by padded convs changes the volume size in the reference, :1587-1589)")
         if cross_embed_downsample:
-            unsupported.append("cross_embed_downsample=True")
+            unsupported.append("cross_embed_downsample=True (cannot be constructed in the reference either: `downsample_klass(current_dim, dim_out)` "
+                               "passes dim_out into CrossEmbedLayer's `kernel_sizes` slot that the partial at :1342 already fills -> TypeError at :1388)")
         if memory_efficient:
             unsupported.append("memory_efficient=True (broken in the reference: changes the output size; note that SRUnet256 / SRUnet1024 keep the "
                                "reference's default memory_efficient=True, so pass memory_efficient=False explicitly, as train.py:100 and test_all.py do)")
-        if not pixel_shuffle_upsample:
-            unsupported.append("pixel_shuffle_upsample=False (ConvTranspose3d upsampling)")
+        if not pixel_shuffle_upsample and boundary:
+            unsupported.append("pixel_shuffle_upsample=False (ConvTranspose3d upsampling) with boundary=True")
         if init_conv_to_final_conv_residual:
             unsupported.append("init_conv_to_final_conv_residual=True (channel mismatch in the reference itself)")
         has_attn = any(attend_at_enc) or (deep_feature and attend_at_middle)
@@ -301,7 +310,7 @@ class Unet(nn.Module):
             if not is_last:
                 skip = skip_dims.pop()
             self.ups.append(nn.ModuleList([
-                PixelShuffleUpsample(dim_in, dim_out) if not is_last else None,
+                (PixelShuffleUpsample(dim_in, dim_out) if pixel_shuffle_upsample else Deconv3D(dim_in, dim_out)) if not is_last else None,
                 ResnetBlock(dim_out + skip, dim_out, groups=grp, use_se=use_se_attn, **rb) if not is_last
                 else ResnetBlock(dim_in, dim_out, groups=grp, use_se=use_se_attn, **rb),
                 nn.ModuleList([ResnetBlock(dim_out, dim_out, groups=grp, use_se=use_se_attn, **rb) for _ in range(nblk)]),

@@ -295,8 +295,11 @@ def unet_forward(sd: Dict[str, Tensor], spec: UnetSpec, x: Tensor, time: Tensor,
     for u in range(nl):                                                      # :1657-1664
         last = u == nl - 1
         if not last:
-            w, b = sd[f"ups.{u}.0.net.0.weight"], sd[f"ups.{u}.0.net.0.bias"]
-            x = pixel_shuffle3d(mish(F.conv3d(x, w, b)))                     # :459-487
+            if f"ups.{u}.0.deconv.0.weight" in sd:                           # Upsample_deconv (:440-457), pixel_shuffle_upsample=False
+                x = mish(F.conv_transpose3d(x, sd[f"ups.{u}.0.deconv.0.weight"], sd[f"ups.{u}.0.deconv.0.bias"], stride=2, padding=1, output_padding=1))
+            else:
+                w, b = sd[f"ups.{u}.0.net.0.weight"], sd[f"ups.{u}.0.net.0.bias"]
+                x = pixel_shuffle3d(mish(F.conv3d(x, w, b)))                 # :459-487
             tap(f"ups.{u}.0", x)
             x = torch.cat((x, hiddens.pop() * skip_scale), dim=1)            # :1653
         x = resnet_block(sd, f"ups.{u}.1.", x, t, rgroups[u], spec)

@@ -43,6 +43,11 @@ FORWARD_CASES = {
     # different depth / width pattern and skip scaling
     "alt_dim32_s16": dict(unet=_unet(32, dim_mults=(1, 2), num_resnet_blocks=(1, 2), scale_skip_connection=True, init_dim=64),
                           batch=1, size=16, weight_seed=15, input_seed=25, log_snr=[-1.0], taps=()),
+    # ConvTranspose3d upsampling (Upsample_deconv :440-457, pixel_shuffle_upsample=False)
+    "deconv_dim32_s16": dict(unet=_unet(32, pixel_shuffle_upsample=False), batch=2, size=16, weight_seed=23, input_seed=33, log_snr=[0.7, -1.2],
+                             taps=("ups.0.0", "ups.1.0")),
+    # the same with channel counts that are multiples of 64 (tcgen05 convs in bf16 mode)
+    "deconv_dim64_s16": dict(unet=_unet(64, pixel_shuffle_upsample=False), batch=1, size=16, weight_seed=24, input_seed=34, log_snr=[0.2], taps=("ups.0.0",)),
     # the constructor-default init conv: CrossEmbedLayer with kernel sizes (3, 7, 15) (imagen_pytorch3D.py:661-686, 1222-1223)
     "crossembed_dim32_s16": dict(unet=_unet(32, init_cross_embed=True, init_cross_embed_kernel_sizes=(3, 7, 15)), batch=1, size=16, weight_seed=22,
                                  input_seed=32, log_snr=[0.4], taps=("init_conv",)),

@@ -35,7 +35,7 @@ def test_unsupported_options_raise():
     from diffusioniqt_b200 import Unet
     base = dict(dim=32, init_dim=32, dim_mults=(1, 2), channels=1, lowres_cond=True, init_cross_embed=False, attend_at_middle=False,
                 attend_at_enc=(False, False), deep_feature=False)
-    for bad in (dict(init_cross_embed=True, boundary=True), dict(memory_efficient=True), dict(pixel_shuffle_upsample=False), dict(attend_at_enc=(True, False), attn_dim_head=48),
+    for bad in (dict(init_cross_embed=True, boundary=True), dict(memory_efficient=True), dict(pixel_shuffle_upsample=False, boundary=True), dict(attend_at_enc=(True, False), attn_dim_head=48),
                 dict(self_cond=True), dict(cross_embed_downsample=True)):
         with pytest.raises(NotImplementedError):
             Unet(**{**base, **bad})

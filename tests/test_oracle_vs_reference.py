@@ -17,7 +17,7 @@ def ref():
 
 
 @pytest.mark.parametrize("name", ["cfg1_dim32_s16_b2", "deep_dim32_s8", "boundary_dim32_s8", "alt_dim32_s16", "attn_linear_dim32_s8",
-                                  "attn_softmax_boundary_dim32_s8", "attn_vit_dim32_s8", "attn_vitlocal_dim32_s8", "crossembed_dim32_s16"])
+                                  "attn_softmax_boundary_dim32_s8", "attn_vit_dim32_s8", "attn_vitlocal_dim32_s8", "crossembed_dim32_s16", "deconv_dim32_s16"])
 def test_unet_forward_bit_exact(ref, name):
     case = FORWARD_CASES[name]
     unet = ref.Unet(**unet_kwargs_for_reference(case)).eval()
@@ -27,6 +27,14 @@ def test_unet_forward_bit_exact(ref, name):
         want = unet(x, None, time, lowres_cond_img=lr)
     got = oracle_forward(case, sd=unet.state_dict())
     assert torch.equal(got, want)
+
+
+def test_cross_embed_downsample_cannot_be_constructed_in_the_reference(ref):
+    """Why diffusioniqt_b200.Unet refuses `cross_embed_downsample=True`: the reference passes dim_out into CrossEmbedLayer's `kernel_sizes`
+    slot, which the partial at imagen_pytorch3D.py:1342 already fills."""
+    kw = unet_kwargs_for_reference(FORWARD_CASES["cfg1_dim32_s16_b2"])
+    with pytest.raises(TypeError, match="kernel_sizes"):
+        ref.Unet(**{**kw, "cross_embed_downsample": True})
 
 
 def test_sub_volume_helpers(ref):
