@@ -482,6 +482,24 @@ def p_losses(imagen, unet, x_start, times, *, noise_scheduler, lowres_cond_img=N
     return loss, pred, x_noisy, lowres_cond_img
 
 
+def allreduce_gradients(params, group=None):
+    """Data-parallel training, one process per GPU (the reference wraps the U-Net in DistributedDataParallel through accelerate,
+    trainer.py:476-499): the gradients of all ranks are averaged with ONE all-reduce over a flat buffer (NCCL over NVLink on the GPU box,
+    gloo in the CPU tests) before the optimizer step.  Parameters without a gradient on this rank contribute zeros."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    params = [p for p in params]
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).float() for p in params])
+    dist.all_reduce(flat, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for p in params:
+        n = p.numel()
+        p.grad = flat[off:off + n].reshape(p.shape).to(p.dtype)
+        off += n
+
+
 class AdamState:
     """torch.optim.Adam's arithmetic (trainer.py: `Adam(unet.parameters(), lr, eps, betas)`) as one kernel per parameter tensor, with the
     exponential moving average of ImagenTrainer.update folded into the same pass."""

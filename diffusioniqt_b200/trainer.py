@@ -284,6 +284,8 @@ class ImagenTrainer(nn.Module):
             return
         unet = self.imagen.unets[index]
         opt = self._optimizer(index)
+        from .train import allreduce_gradients
+        allreduce_gradients(unet.parameters())     # one process per GPU: average the gradients (no-op in a single process)
         if self.max_grad_norm is not None:
             torch.nn.utils.clip_grad_norm_(unet.parameters(), self.max_grad_norm)
         ema_params, decay = None, 0.

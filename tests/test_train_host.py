@@ -88,3 +88,33 @@ def test_ema_schedule_of_the_trainer():
     assert d(T, 100) == 0. and d(T, 101) == 0.
     assert abs(d(T, 110) - (1 - (1 + 9) ** (-2 / 3))) < 1e-12
     assert d(T, 10 ** 9) == 0.9999
+
+
+def _allreduce_worker(rank, world, port, ret):
+    import os
+    import torch.distributed as dist
+    from diffusioniqt_b200.train import allreduce_gradients
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(3, 5)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+    params[0].grad = torch.full((3, 5), float(rank + 1))
+    params[1].grad = torch.arange(7.) * (rank + 1)
+    if rank == 0:
+        params[2].grad = torch.ones(2, 2)          # rank 1 has no gradient for this one
+    allreduce_gradients(params)
+    ret[rank] = [p.grad.clone() for p in params]
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_two_ranks_gloo():
+    """ImagenTrainer.update averages the gradients over the ranks with one flat all-reduce (NCCL on the GPU box, gloo here)."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_allreduce_worker, args=(2, port, ret), nprocs=2, join=True)
+    for r in (0, 1):
+        g = ret[r]
+        assert torch.equal(g[0], torch.full((3, 5), 1.5)) and torch.equal(g[1], torch.arange(7.) * 1.5) and torch.equal(g[2], torch.full((2, 2), 0.5))
