@@ -343,25 +343,35 @@ __global__ void __launch_bounds__(64 * WGS_LANES) conv_wgrad_narrow_kernel(const
   float acc[CI];
 #pragma unroll
   for (int i = 0; i < CI; ++i) acc[i] = 0.f;
-  // voxel coordinates are advanced incrementally (a 64-bit division per voxel made the first version of this kernel 20x slower)
+  // voxel coordinates are advanced incrementally (a 64-bit division per voxel made the first version of this kernel 20x slower), and four
+  // voxels are in flight per thread: the loop is a chain of L2 round trips otherwise
   int cz, cy, cx;
   {
     const int64_t vv = (r0 + lane) % vol;
     cz = (int)(vv / ((int64_t)d1 * d2)); cy = (int)((vv / d2) % d1); cx = (int)(vv % d2);
   }
-  for (int64_t row = r0 + lane; row < r1; row += WGS_LANES) {
-    const int z = cz + oz, y = cy + oy, xx = cx + ox;
-    cx += WGS_LANES;
-    while (cx >= d2) {
-      cx -= d2;
-      if (++cy == d1) { cy = 0; if (++cz == d0) cz = 0; }
-    }
-    if ((unsigned)z >= (unsigned)d0 || (unsigned)y >= (unsigned)d1 || (unsigned)xx >= (unsigned)d2) continue;   // warp-uniform: a warp shares the voxel
-    const float g = co < c_out ? to_float(dy[row * ld_dy + co]) : 0.f;
-    const T* xr = x + (row + shift) * ld_x;
+  constexpr int U = 4;
+  for (int64_t row = r0 + lane; row < r1; row += WGS_LANES * U) {
+    float g[U], xv[U][CI];
 #pragma unroll
-    for (int i = 0; i < CI; ++i)
-      if (i < c_in) acc[i] = fmaf(g, to_float(xr[i]), acc[i]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t rr = row + (int64_t)u * WGS_LANES;
+      const int z = cz + oz, y = cy + oy, xx = cx + ox;
+      cx += WGS_LANES;
+      while (cx >= d2) {
+        cx -= d2;
+        if (++cy == d1) { cy = 0; if (++cz == d0) cz = 0; }
+      }
+      const bool ok = rr < r1 && (unsigned)z < (unsigned)d0 && (unsigned)y < (unsigned)d1 && (unsigned)xx < (unsigned)d2;   // warp-uniform
+      g[u] = (ok && co < c_out) ? to_float(dy[rr * ld_dy + co]) : 0.f;
+      const T* xr = x + (rr + shift) * ld_x;
+#pragma unroll
+      for (int i = 0; i < CI; ++i) xv[u][i] = (ok && i < c_in) ? to_float(xr[i]) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int i = 0; i < CI; ++i) acc[i] = fmaf(g[u], xv[u][i], acc[i]);
   }
 #pragma unroll
   for (int i = 0; i < CI; ++i) red[lane][threadIdx.x & 63][i] = acc[i];

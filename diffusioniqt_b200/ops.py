@@ -193,7 +193,7 @@ def group_norm_film_mish(x: torch.Tensor, groups: int, gamma, beta, scale_shift:
     return y
 
 
-def se_scale_residual(h: torch.Tensor, res: torch.Tensor, w1, w2, nblk: int = 8, grouped: bool = False):
+def se_scale_residual(h: torch.Tensor, res: torch.Tensor, w1, w2, nblk: int = 8, grouped: bool = False, return_stats: bool = False):
     """SE3D gate on h, then h*gate + res.  Returns (out, gate, partial stats of out); grouped=True computes the gate in the
     residual kernel's prologue from grouped statistics and returns (out, None, group sums of out)."""
     lib = L.load()
@@ -223,7 +223,7 @@ def se_scale_residual(h: torch.Tensor, res: torch.Tensor, w1, w2, nblk: int = 8,
     L.check(lib.diqt_scale_residual(h.data_ptr(), c, res.data_ptr(), c, out.data_ptr(), c, _dt(h), n, vox, c, gate.data_ptr(), nblk,
                                     opart.data_ptr(), 0, 0, st), "scale_residual")
     _sync()
-    return out, gate, opart
+    return (out, gate, opart, part) if return_stats else (out, gate, opart)
 
 
 # ------------------------------------------------------------------ attention-block ops (csrc/attn.cu); rows = (rows, c) tensors

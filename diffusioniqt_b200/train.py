@@ -217,8 +217,8 @@ class UnetBackprop:
         sv = dict(blk=blk, x=x, z1=z1, z2=z2, h2=h2, s1=s1, s2=s2, te=te)
         if blk.has_se:
             w1, w2 = blk.se.fc[0].weight, blk.se.fc[2].weight
-            out, gate, _ = ops.se_scale_residual(h2, res, w1, w2, _nblk(h2))
-            sv["gate"] = gate
+            out, gate, _, hpart = ops.se_scale_residual(h2, res, w1, w2, _nblk(h2), return_stats=True)
+            sv["gate"], sv["hpart"] = gate, hpart
         else:
             out = self._add(h2, res)
         return out, sv
@@ -239,7 +239,7 @@ class UnetBackprop:
             part = torch.empty(n, NBLK, c, 2, dtype=torch.float32, device=h2.device)
             L.check(self.lib.diqt_bwd_reduce(h2.data_ptr(), c, d_out.data_ptr(), c, _dt(h2), n, vox, c, 0, 0, 0, NBLK, part.data_ptr(), st), "bwd_reduce")
             dgate = part.double().sum(dim=1)[..., 1].float()                       # sum_v d_out * h2
-            mean = (self._stats(h2)[..., 0] / vox).float().requires_grad_(True)
+            mean = (sv["hpart"].double().sum(dim=1)[..., 0] / vox).float().requires_grad_(True)      # the forward pass's statistics of h2
             w1, w2 = blk.se.fc[0].weight, blk.se.fc[2].weight
             with torch.enable_grad():
                 gate = torch.sigmoid(F.linear(torch.relu(F.linear(mean, w1)), w2))
@@ -279,10 +279,13 @@ class UnetBackprop:
         inp = torch.cat((x, lowres_cond_img), dim=1) if lowres_cond_img is not None else x          # :1576
         n, cin = inp.shape[:2]
         # init_conv :1291: channels zero-padded to 16 so that the general convolution kernels apply
-        x16 = torch.zeros(n, *inp.shape[2:], 16, dtype=self.act, device=dev)
+        # (bf16: padded to 64 so that the conv and its weight gradient run on the tensor cores: 50 + 75 us instead of 460 + 1080 us on the
+        # CUDA-core kernels at 64^3, profiles/launch_summary_train_r3h.txt; fp32 exact mode: 16, the CUDA-core kernels' granularity)
+        cpad = 64 if self.act == torch.bfloat16 and unet.init_conv.weight.shape[0] % 64 == 0 else 16
+        x16 = torch.zeros(n, *inp.shape[2:], cpad, dtype=self.act, device=dev)
         x16[..., :cin] = inp.permute(0, 2, 3, 4, 1).to(self.act)
         w = unet.init_conv.weight
-        w16 = torch.zeros(w.shape[0], 16, *w.shape[2:], dtype=w.dtype, device=dev)
+        w16 = torch.zeros(w.shape[0], cpad, *w.shape[2:], dtype=w.dtype, device=dev)
         w16[:, :cin] = w.detach()
         h = ops.conv3d(x16, w16, unet.init_conv.bias, mode="k3")
         tape.append(("init", x16, cin))
@@ -406,7 +409,10 @@ class UnetBackprop:
             elif kind == "init":
                 _, x16, cin = rec
                 conv = unet.init_conv
-                _accum(conv.weight, self._wgrad(x16, d, 27, c_in=cin))          # only the real input channels (row pitch 16)
+                if x16.shape[-1] == 64:      # tensor-core weight gradient over the padded channels, the real ones kept
+                    _accum(conv.weight, self._wgrad(x16, d, 27).reshape(conv.weight.shape[0], 64, *conv.weight.shape[2:])[:, :cin])
+                else:
+                    _accum(conv.weight, self._wgrad(x16, d, 27, c_in=cin))      # only the real input channels (row pitch 16)
                 _accum(conv.bias, self._stats(d)[..., 0].sum(dim=0).float())
         # FiLM rows -> time MLPs (autograd on (n, 2c) vectors)
         tes = [te for te, g in self._film_grads if g is not None]
