@@ -30,6 +30,11 @@ import torch.nn.functional as F
 from . import lib as L
 from . import ops
 
+def _nblk_apply(t):
+    """CTAs per volume for the apply pass (it leaves no partial rows behind): eight CTAs per SM keep enough loads in flight"""
+    return int(max(1, min(1184 // t.shape[0], _vox(t) // 64)))
+
+
 def _nblk(t):
     """partial rows per volume for the statistics / reduce / apply kernels: about four CTAs per SM over the whole batch, at least 64 voxels each"""
     return int(max(1, min(320, 592 // t.shape[0], _vox(t) // 64)))
@@ -145,7 +150,7 @@ class UnetBackprop:
         L.check(self.lib.diqt_gn_finalize(part.data_ptr(), n, NBLK, vox, c, G, gn.eps, gamma.data_ptr(), beta.data_ptr(), L.ptr(film), 2 * c, 0, 1,
                                           a.data_ptr(), b.data_ptr(), st), "gn_finalize")
         z = torch.empty_like(x)
-        L.check(self.lib.diqt_affine_mish(x.data_ptr(), c, z.data_ptr(), c, _dt(x), n, vox, c, a.data_ptr(), b.data_ptr(), NBLK, 0, 0, st), "affine_mish")
+        L.check(self.lib.diqt_affine_mish(x.data_ptr(), c, z.data_ptr(), c, _dt(x), n, vox, c, a.data_ptr(), b.data_ptr(), _nblk_apply(x), 0, 0, st), "affine_mish")
         return z, dict(x=x, a=a, b=b, part=part, gn=gn, film=film)
 
     def _gn_backward(self, s, dz, acc=None):
@@ -172,7 +177,7 @@ class UnetBackprop:
         _accum(gn.weight, dgamma)
         dx = torch.empty_like(x)
         L.check(self.lib.diqt_bwd_apply(x.data_ptr(), c, dz.data_ptr(), c, L.ptr(acc), c, dx.data_ptr(), c, _dt(x), n, vox, c, a.data_ptr(), b.data_ptr(),
-                                        c1.data_ptr(), c2.data_ptr(), c3.data_ptr(), 1, NBLK, st), "bwd_apply")
+                                        c1.data_ptr(), c2.data_ptr(), c3.data_ptr(), 1, _nblk_apply(x), st), "bwd_apply")
         return dx, dfilm
 
     def _conv(self, x, conv, mode="k3"):
@@ -248,7 +253,7 @@ class UnetBackprop:
             c3 = (mean.grad / vox).float().contiguous()
             d_h2 = torch.empty_like(h2)
             L.check(self.lib.diqt_bwd_apply(0, c, d_out.data_ptr(), c, 0, c, d_h2.data_ptr(), c, _dt(h2), n, vox, c, 0, 0, c1.data_ptr(), 0, c3.data_ptr(), 0,
-                                            NBLK, st), "bwd_apply")
+                                            _nblk_apply(h2), st), "bwd_apply")
         else:
             d_h2 = d_out
         d_z2 = self._conv_backward(sv["z2"], blk.block2.project, d_h2)
@@ -324,7 +329,7 @@ class UnetBackprop:
                 one = torch.ones(n_, c8, dtype=torch.float32, device=dev)
                 zero = torch.zeros_like(one)
                 act = torch.empty_like(pre)
-                L.check(self.lib.diqt_affine_mish(pre.data_ptr(), c8, act.data_ptr(), c8, _dt(pre), n_, _vox(pre), c8, one.data_ptr(), zero.data_ptr(), _nblk(pre), 0, 0,
+                L.check(self.lib.diqt_affine_mish(pre.data_ptr(), c8, act.data_ptr(), c8, _dt(pre), n_, _vox(pre), c8, one.data_ptr(), zero.data_ptr(), _nblk_apply(pre), 0, 0,
                                                   L.current_stream()), "affine_mish")
                 h = _shuffle_cl(act)
                 skip = hiddens.pop()
@@ -396,7 +401,7 @@ class UnetBackprop:
                 zero = torch.zeros_like(one)
                 d_pre = torch.empty_like(pre)
                 L.check(self.lib.diqt_bwd_apply(pre.data_ptr(), c8, g.data_ptr(), c8, 0, c8, d_pre.data_ptr(), c8, _dt(pre), n_, _vox(pre), c8, one.data_ptr(),
-                                                zero.data_ptr(), one.data_ptr(), 0, 0, 1, _nblk(pre), L.current_stream()), "bwd_apply")
+                                                zero.data_ptr(), one.data_ptr(), 0, 0, 1, _nblk_apply(pre), L.current_stream()), "bwd_apply")
                 d = self._conv_backward(h_in, conv, d_pre, "k1")
             elif kind == "k1":
                 _, h_in, conv = rec
