@@ -163,3 +163,79 @@ def test_file_to_file_inference(tmp_path):
     assert torch.equal(res.prediction[low == low.min()], torch.full_like(res.prediction[low == low.min()], float(low.min())))
     assert float(res.prediction.min()) >= min(MIN_BOUND, float(low.min())) - 1e-6      # sampler clamp (:2157) / background / fill value
     assert res.psnr is not None and 0.0 < res.ms_ssim <= 1.0
+
+
+def test_literal_acceptance_metric_with_trained_weights():
+    """The north star's LITERAL criterion (per-volume PSNR / SSIM with every volume scaled by its own min / max, metrics.py:17-30) in bf16 and
+    z-score mode on weights that have been TRAINED, not drawn at random: a short run of this package's own training step (Imagen.forward,
+    the hand-written reverse pass, the Adam kernel) on synthetic high-field / low-field pairs teaches the U-Net to return a smooth field
+    close to its conditioning image, so the extremes of the stitched volume are set by the data, not by a single outlier voxel.
+    The reference pipeline (CPU oracle, fp32) runs on the same trained weights, noise and patches."""
+    import torch.nn.functional as F
+    from diffusioniqt_b200 import Imagen, ImagenTrainer, NullUnet, Unet
+    P, stride, T, N = 16, 8, 6, 32
+    unet = Unet(**KW, img_size=P)
+    unet.load_state_dict(synthetic_state_dict({k: tuple(v.shape) for k, v in unet.state_dict().items()}, seed=61))
+    configs = {"Data": {"norm": "z-score"}, "Train": {"batch_sample": False}}
+    imagen = Imagen(unets=(NullUnet(), unet), configs=configs, image_sizes=(P, P), channels=1, min_bound=MIN_BOUND, timesteps=T, pred_objectives="x_start",
+                    loss_type="l2", p2_loss_weight_gamma=0.5, dynamic_thresholding=False, cond_drop_prob=0.0).cuda()
+    imagen.unets[1].set_compute_dtype("fp32")
+    trainer = ImagenTrainer(configs=configs, imagen=imagen, lr=3e-4, use_ema=False, gradient_accumulation_steps=1, verbose=False)
+    trainer.train()
+    hr_vol = synthetic_field((48, 48, 48), 91, smooth=3).clamp(min=MIN_BOUND)
+
+    def degrade(v):      # low-field stand-in: blurred, noisier
+        b = F.avg_pool3d(v[None, None], 3, stride=1, padding=1)[0, 0]
+        return b + 0.15 * synthetic_field(tuple(v.shape), 92, smooth=0)
+
+    lr_vol = degrade(hr_vol)
+    rs = np.random.RandomState(5)
+    torch.manual_seed(5)
+    losses = []
+    for step in range(160):
+        idx = rs.randint(0, 48 - P + 1, size=(4, 3))
+        hr = torch.stack([hr_vol[i:i + P, j:j + P, k:k + P] for i, j, k in idx])[:, None]
+        lo = torch.stack([lr_vol[i:i + P, j:j + P, k:k + P] for i, j, k in idx])[:, None]
+        losses.append(trainer(hr, lo, unet_number=2)[0])
+    assert np.mean(losses[-20:]) < 0.5 * np.mean(losses[:5]), (losses[:5], losses[-20:])
+    sd = {k: v.detach().cpu().clone() for k, v in imagen.unets[1].state_dict().items()}
+
+    # ---- the volume pipeline on the trained weights: bf16 kernels against the fp32 oracle
+    imagen.eval()
+    imagen.unets[1].set_compute_dtype("bf16")
+    test_hr = synthetic_field((N, N, N), 93, smooth=3).clamp(min=MIN_BOUND)
+    lowres = degrade(test_hr)
+    lowres[:6, :10] = lowres.min()
+    grid = V.patch_grid(lowres.shape, P, stride)
+    noise = {g: synthetic_noise((1, 1, P, P, P), T + 1, 164 + n) for n, g in enumerate(grid)}
+    order = iter(grid)
+
+    def gpu_sampler(lr):
+        imagen.noise_override = noise[next(order)]
+        return imagen.sample(batch_size=1, start_image_or_video=lr, start_at_unet_number=2, use_tqdm=False)[0]
+
+    res = V.infer_volume(gpu_sampler, lowres.cuda(), patch=P, overlap=stride, raw_lowres=(lowres - lowres.min()).cuda(), batch_size=1, fill_value=MIN_BOUND)
+    got = res.volume.cpu()
+    spec = spec_from_kwargs(KW)
+    outs, kept = [], []
+    raw = (lowres - lowres.min()).numpy()
+    for g in grid:
+        if so.is_skipped(raw, list(g), P):
+            continue
+        lr = lowres[g[0]:g[0] + P, g[1]:g[1] + P, g[2]:g[2] + P][None, None]
+        with torch.no_grad():
+            img, _, _ = ddpm_sample(lambda x, ls: unet_forward(sd, spec, x, ls, lowres_cond_img=lr), (1, 1, P, P, P), noise[g], timesteps=T,
+                                    min_bound=MIN_BOUND, norm="z-score")
+        outs.append(img[0, 0].numpy())
+        kept.append(list(g))
+    want = np.full((N, N, N), MIN_BOUND, np.float32)
+    so.stitch(want, outs, kept, P, stride, False)
+    want = torch.from_numpy(so.background_mask(want, lowres.numpy()))
+    truth = torch.from_numpy(so.background_mask(test_hr.numpy().copy(), lowres.numpy()))      # the real high-field volume this time
+    p_ref, p_got = mo.psnr(want, truth), mo.psnr(got, truth)
+    s_ref, s_got = mo.ssim3d(want, truth), mo.ssim3d(got, truth)
+    print(f"trained weights, bf16 z-score: reference pipeline PSNR {p_ref:.3f} dB SSIM {s_ref:.4f}; this library {p_got:.3f} dB {s_got:.4f}; "
+          f"loss {np.mean(losses[:5]):.3f} -> {np.mean(losses[-20:]):.3f}")
+    assert abs(p_got - p_ref) < 0.05          # the north star's literal tolerance
+    assert abs(s_got - s_ref) < 1e-3
+    assert mo.psnr(got, want) > 30.0
