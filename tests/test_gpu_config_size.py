@@ -210,3 +210,34 @@ def test_film_table_reallocation_drops_stale_graphs():
     b2 = go(None, full)
     del filler
     assert torch.equal(a, a2) and torch.equal(b, b2)
+
+
+def test_config2_size_training_gradients_bf16_against_autograd_of_the_oracle():
+    """SURVEY 8 f-4 at the BASELINE config-2 shape: one training evaluation of the driver U-Net on a 64^3 patch in bf16 (tcgen05 forward /
+    data-gradient convs, tcgen05 weight gradients with 144-CTA voxel chunking, the reverse passes over 32 MiB tensors) against PyTorch
+    autograd over the fp32 CPU oracle.  The gradient as one vector over all parameters, and the largest tensors one by one."""
+    import torch.nn.functional as F
+    from diffusioniqt_b200 import lib as L
+    from diffusioniqt_b200.train import UnetBackprop
+    unet, sd = _driver_unet(seed=11)
+    unet = unet.cuda().set_compute_dtype("bf16")
+    x, lr = synthetic_field((1, 1, 64, 64, 64), 3), synthetic_field((1, 1, 64, 64, 64), 4)
+    t = torch.tensor([1.3])
+    target = synthetic_field((1, 1, 64, 64, 64), 5)
+    sdg = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    out = unet_forward(sdg, spec_from_kwargs(DRIVER), x, t, lowres_cond_img=lr)
+    F.mse_loss(out, target).backward()
+    bp = UnetBackprop(unet)
+    n0 = L.launch_count()
+    pred = bp.forward(x.cuda(), t.cuda(), lowres_cond_img=lr.cuda())
+    assert rel_err(pred.cpu(), out.detach()) < 3e-2
+    bp.backward(2 * (pred - target.cuda()) / pred.numel())
+    assert L.launch_count() - n0 > 500                       # the step ran on this library's kernels
+    params = dict(unet.named_parameters())
+    names = [k for k, v in sdg.items() if v.requires_grad and v.grad is not None]
+    got = torch.cat([params[k].grad.cpu().double().reshape(-1) for k in names])
+    want = torch.cat([sdg[k].grad.double().reshape(-1) for k in names])
+    assert rel_err(got, want) < 8e-2
+    big = sorted(names, key=lambda k: -sdg[k].grad.norm().item())[:12]
+    for k in big:
+        assert rel_err(params[k].grad.cpu(), sdg[k].grad) < 8e-2, k
