@@ -138,7 +138,7 @@ def build_model(timesteps, device, dtype):
     return imagen
 
 
-def time_dominant_kernel(size, batch, reps=20):
+def time_dominant_kernel(size, batch, reps=20, kinds=("fused", "plain")):
     """The 3x3x3 conv 64->64 at full resolution (82 % of all FLOPs), alone, exactly as the engine launches
     it in the step: conv_zm_kernel with GroupNorm + FiLM + Mish of its input fused into the load path and the output statistics in its
     epilogue (`fused`), and the same conv without the fused normalisation (`plain`: the kernel the r1 roofline line described).
@@ -179,7 +179,7 @@ def time_dominant_kernel(size, batch, reps=20):
     opart, ogrp, otick = torch.zeros(n * 320 * c * 2, device=dev), torch.zeros(16 * n * c * 2, device=dev), torch.zeros(16 * n, dtype=torch.int32, device=dev)
     plans = {"fused": [], "plain": []}
     for x, y in zip(xs, ys):
-        for kind in ("fused", "plain"):
+        for kind in kinds:
             if kind == "fused" and not fusable:
                 continue
             p = C.c_void_p(0)
