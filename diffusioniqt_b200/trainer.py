@@ -4,8 +4,10 @@ checkpoint dictionary (`{'model', 'ema', 'steps', 'version', optim..}`, trainer.
 default (`use_ema_unets`, trainer.py:982-1005), casts numpy / CPU arguments to the device (`cast_torch_tensor`, :123-147) and chunks
 a batch by `max_batch_size` (`imagen_sample_in_chunks`, :201-219).
 
-Training (optimisers, schedulers, accelerate, dataloaders: trainer.py:339-380, 543-760, 1099-1128) is outside the sampling hot path:
-the optimizer / scheduler keywords are accepted and ignored, optimizer state in a checkpoint is left alone, `forward` raises.
+Training: `forward` / `update` (trainer.py:1038-1130) run the training step of `diffusioniqt_b200/train.py`:
+`imagen(...)`, `loss.backward()` (the hand-written reverse pass), gradient averaging over the ranks, the Adam + EMA kernel.  Learning-rate
+schedulers, warm-up, accelerate's mixed-precision scaler, dataloaders and checkpoint rotation (trainer.py:339-380, 543-812) are not
+mirrored: the scheduler keywords are accepted and ignored, optimizer state in a checkpoint is left alone.
 """
 from __future__ import annotations
 
