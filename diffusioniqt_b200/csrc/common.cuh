@@ -221,10 +221,17 @@ __device__ __forceinline__ void stats_group_tail(const StatsGroups& g, const flo
   for (int idx = tid; idx < n * width; idx += nthreads) {
     const int nv = idx / width, j = idx - nv * width;
     const float* src = partial + ((size_t)nv * nblk + r0) * width + j;
+    // the last CTA of a group finishes after everybody else: its row loop is on the critical path of the whole grid (the in-graph
+    // stamps of profiles/r3t_zm_cta_graph.txt show those CTAs ~2 us behind the median), so eight rows are in flight at once; the order
+    // of the additions stays fixed
     float acc = 0.f;
-    for (int r = r0; r < r1; ++r) {  // fixed order
-      acc += __ldcg(src);
-      src += width;
+    for (int r = r0; r < r1; r += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = r + u < r1 ? __ldcg(src + (size_t)u * width) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+      src += (size_t)8 * width;
     }
     g.group[((size_t)nv * g.ngroups + grp) * width + j] = acc;
   }

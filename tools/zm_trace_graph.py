@@ -19,3 +19,9 @@ for s in range(2):
     for e, nm in enumerate(names):
         row = [buf[(e * 2 + s) * 16 + i] for i in range(10)]
         print(f"  {nm:28s}" + " ".join(f"{(v - t0) / 1965.0:7.2f}" if v > 0 else "      -" for v in row))
+
+# tail events (diagnostic builds that record them): epilogue after its last plane, statistics flushed, group tail done, stores drained; CTA-wide end barrier
+ev7 = [buf[(7 * 2 + 0) * 16 + i] for i in range(4)] + [buf[(7 * 2 + 1) * 16 + i] for i in range(2)]
+if any(ev7):
+    labels = ["epilogue loop done", "statistics flushed", "group tail done", "stores drained", "thread 0 at the end barrier", "end barrier passed"]
+    print("tail events: " + "; ".join(f"{l} {(v - t0) / 1965.0:.2f}" for l, v in zip(labels, ev7) if v > 0))
