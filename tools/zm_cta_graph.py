@@ -25,3 +25,7 @@ for k in range(8):
         line += f" | previous grid's last CTA end -> first release {e2.min() - prev_end:5.2f}, period {e3.max() - prev_end:6.2f}"
     prev_end = e3.max()
     print(line)
+busy = (a[6, 3] - a[6, 2])
+print("CTA busy (us) by block index, launch 6, rows of 16:")
+for r in range(0, 144, 16):
+    print("  " + " ".join(f"{v:5.1f}" for v in busy[r:r + 16]))
