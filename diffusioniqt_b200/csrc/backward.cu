@@ -264,6 +264,80 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* fpar
   }
 }
 
+// ---- reverse of the SE gate MLP (SE3D :617-632: gate = sigmoid(W2 relu(W1 mean_v h))), one CTA, fp32, fixed order.
+// fpart: forward statistics of h ([n][nblk_f][c][2], sum h first); bpart: diqt_bwd_reduce mode 0 ([n][nblk_b][c][2], sum d_out * h second).
+// Outputs: c3[n][c] = d loss / d mean / V (the additive term of diqt_bwd_apply), dw1[hid][c], dw2[c][hid] summed over the batch.
+__global__ void __launch_bounds__(512) se_bwd_kernel(const float* fpart, int nblk_f, const float* bpart, int nblk_b, int n, int64_t voxels, int c, int hid,
+                                                     const float* w1, const float* w2, const float* gate, float* c3, float* dw1, float* dw2) {
+  extern __shared__ float se_sm[];
+  float* mean = se_sm;            // [c]
+  float* dy = mean + c;           // [c]
+  float* z = dy + c;              // [hid]
+  float* dz = z + hid;            // [hid]
+  pdl_sync();
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < hid * c; i += nt) { dw1[i] = 0.f; dw2[i] = 0.f; }
+  __syncthreads();
+  for (int nv = 0; nv < n; ++nv) {
+    // row sums: blockDim / c slices per channel, four loads in flight each, slices added in a fixed order
+    {
+      const int parts = max(1, nt / c);
+      float* ps = dz + hid;          // [parts][c][2]
+      for (int idx = tid; idx < parts * c; idx += nt) {
+        const int ch = idx % c, part = idx / c;
+        float s = 0.f, d = 0.f;
+        for (int b = part; b < nblk_f; b += 4 * parts) {
+          float v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = b + u * parts < nblk_f ? __ldcg(fpart + (((int64_t)nv * nblk_f + b + u * parts) * c + ch) * 2) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) s += v[u];
+        }
+        for (int b = part; b < nblk_b; b += 4 * parts) {
+          float v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = b + u * parts < nblk_b ? __ldcg(bpart + (((int64_t)nv * nblk_b + b + u * parts) * c + ch) * 2 + 1) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) d += v[u];
+        }
+        ps[(part * c + ch) * 2] = s;
+        ps[(part * c + ch) * 2 + 1] = d;
+      }
+      __syncthreads();
+      for (int ch = tid; ch < c; ch += nt) {
+        float s = 0.f, d = 0.f;
+        for (int pz = 0; pz < parts; ++pz) { s += ps[(pz * c + ch) * 2]; d += ps[(pz * c + ch) * 2 + 1]; }
+        const float g = gate[(int64_t)nv * c + ch];
+        mean[ch] = s / (float)voxels;
+        dy[ch] = d * g * (1.f - g);          // through the sigmoid
+      }
+    }
+    __syncthreads();
+    for (int j = tid; j < hid; j += nt) {
+      float a = 0.f, b = 0.f;
+      for (int ch = 0; ch < c; ++ch) {
+        a = fmaf(w1[j * c + ch], mean[ch], a);        // z = W1 mean
+        b = fmaf(w2[ch * hid + j], dy[ch], b);        // d relu-out = W2^T dy
+      }
+      z[j] = a;
+      dz[j] = a > 0.f ? b : 0.f;                      // through the ReLU
+    }
+    __syncthreads();
+    for (int i = tid; i < hid * c; i += nt) {
+      const int j1 = i / c, c1i = i - j1 * c;         // dw1[j][ch] += dz[j] mean[ch]
+      dw1[i] += dz[j1] * mean[c1i];
+      const int c2i = i / hid, j2 = i - c2i * hid;    // dw2[ch][j] += dy[ch] relu(z[j])
+      dw2[i] += dy[c2i] * fmaxf(z[j2], 0.f);
+    }
+    for (int ch = tid; ch < c; ch += nt) {
+      float d = 0.f;
+      for (int j = 0; j < hid; ++j) d = fmaf(w1[j * c + ch], dz[j], d);   // d mean = W1^T dz
+      c3[(int64_t)nv * c + ch] = d / (float)voxels;
+    }
+    __syncthreads();
+  }
+}
+
 // ---- weight gradient, CUDA cores: partial[chunk][tap][c_out][c_in] over the chunk's voxels ---------------------------------------
 constexpr int WG_VT = 32;   // voxels per shared-memory tile
 template <typename T>
@@ -511,6 +585,17 @@ extern "C" int diqt_gn_bwd_finalize(const float* fwd_partial, int nblk_f, const 
   launch_pdl(gn_bwd_finalize_kernel, dim3(1), dim3(threads), sh, (cudaStream_t)stream, fwd_partial, nblk_f, bwd_partial, nblk_b, n, voxels, c, groups, eps, gamma,
              beta, film, c1, c2, c3, dgamma, dbeta, dfilm);
   return check_launch("gn_bwd_finalize");
+}
+
+extern "C" int diqt_se_bwd(const float* fwd_partial, int nblk_f, const float* bwd_partial, int nblk_b, int n, int64_t voxels, int c, int hidden,
+                           const float* w1, const float* w2, const float* gate, float* c3, float* dw1, float* dw2, void* stream) {
+  DIQT_REQUIRE(fwd_partial && bwd_partial && w1 && w2 && gate && c3 && dw1 && dw2 && n > 0 && c > 0 && hidden > 0 && nblk_f > 0 && nblk_b > 0,
+               "se_bwd: bad arguments");
+  const size_t sh = ((size_t)2 * c + 2 * hidden + (size_t)2 * (512 / c > 0 ? 512 / c : 1) * c) * sizeof(float);
+  DIQT_REQUIRE(sh <= 48 * 1024, "se_bwd: c=%d too wide", c);
+  launch_pdl(se_bwd_kernel, dim3(1), dim3(512), sh, (cudaStream_t)stream, fwd_partial, nblk_f, bwd_partial, nblk_b, n, voxels, c, hidden, w1, w2, gate, c3, dw1,
+             dw2);
+  return check_launch("se_bwd");
 }
 
 static int wgrad_chunks(int64_t total_vox, int taps, int tiles) {

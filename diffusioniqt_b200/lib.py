@@ -80,6 +80,7 @@ _SIGNATURES = {
     "diqt_bwd_reduce": [_vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _vp, _i, _i, _vp, _vp],
     "diqt_bwd_apply": [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "diqt_gn_bwd_finalize": [_vp, _i, _vp, _i, _i, _i64, _i, _i, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "diqt_se_bwd": [_vp, _i, _vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "diqt_conv_wgrad_workspace_bytes": [_i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_size_t)],
     "diqt_conv_wgrad_resolved_impl": [_i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_int)],
     "diqt_conv_wgrad": [_vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp],

@@ -243,14 +243,17 @@ class UnetBackprop:
         if blk.has_se:
             part = torch.empty(n, NBLK, c, 2, dtype=torch.float32, device=h2.device)
             L.check(self.lib.diqt_bwd_reduce(h2.data_ptr(), c, d_out.data_ptr(), c, _dt(h2), n, vox, c, 0, 0, 0, NBLK, part.data_ptr(), st), "bwd_reduce")
-            dgate = part.double().sum(dim=1)[..., 1].float()                       # sum_v d_out * h2
-            mean = (sv["hpart"].double().sum(dim=1)[..., 0] / vox).float().requires_grad_(True)      # the forward pass's statistics of h2
-            w1, w2 = blk.se.fc[0].weight, blk.se.fc[2].weight
-            with torch.enable_grad():
-                gate = torch.sigmoid(F.linear(torch.relu(F.linear(mean, w1)), w2))
-                gate.backward(dgate)                                               # -> w1.grad, w2.grad, mean.grad (tiny)
-            c1 = sv["gate"].contiguous()
-            c3 = (mean.grad / vox).float().contiguous()
+            w1 = blk.se.fc[0].weight.detach().float().contiguous()
+            w2 = blk.se.fc[2].weight.detach().float().contiguous()
+            hpart, gate = sv["hpart"], sv["gate"].contiguous()
+            hid = w1.shape[0]
+            c3 = torch.empty(n, c, dtype=torch.float32, device=h2.device)
+            dw1, dw2 = torch.empty_like(w1), torch.empty_like(w2)
+            L.check(self.lib.diqt_se_bwd(hpart.data_ptr(), hpart.shape[1], part.data_ptr(), NBLK, n, vox, c, hid, w1.data_ptr(), w2.data_ptr(), gate.data_ptr(),
+                                         c3.data_ptr(), dw1.data_ptr(), dw2.data_ptr(), st), "se_bwd")
+            _accum(blk.se.fc[0].weight, dw1)
+            _accum(blk.se.fc[2].weight, dw2)
+            c1 = gate
             d_h2 = torch.empty_like(h2)
             L.check(self.lib.diqt_bwd_apply(0, c, d_out.data_ptr(), c, 0, c, d_h2.data_ptr(), c, _dt(h2), n, vox, c, 0, 0, c1.data_ptr(), 0, c3.data_ptr(), 0,
                                             _nblk_apply(h2), st), "bwd_apply")

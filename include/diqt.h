@@ -273,6 +273,10 @@ int diqt_bwd_apply(const void* x, int ld_x, const void* dz, int ld_dz, const voi
 int diqt_gn_bwd_finalize(const float* fwd_partial, int nblk_f, const float* bwd_partial, int nblk_b, int n, int64_t voxels, int c,
                          int groups, float eps, const float* gamma, const float* beta, const float* film, float* c1, float* c2, float* c3,
                          float* dgamma, float* dbeta, float* dfilm, void* stream);
+/* Reverse of the SE gate MLP (:617-632) between the plain-mode reduce and apply: from the forward statistics of h, the reduce's
+ * sum_v d_out * h and the forward gate to c3[n][c] = d mean / V and the weight gradients dw1[hidden][c], dw2[c][hidden] (batch-summed). */
+int diqt_se_bwd(const float* fwd_partial, int nblk_f, const float* bwd_partial, int nblk_b, int n, int64_t voxels, int c, int hidden,
+                const float* w1, const float* w2, const float* gate, float* c3, float* dw1, float* dw2, void* stream);
 /* dw[c_out][c_in][taps] (the layout of nn.Conv3d.weight, fp32) = sum over voxels of dy[v][c_out] * x[v + tap][c_in]; taps 27: 3x3x3 with
  * padding 1 (:550), taps 1: 1x1x1 (:597, :1388, :1477, and the pixel (un)shuffle convs on rearranged tensors).  Any channel counts,
  * fp32 accumulation, per-chunk partials summed in a fixed order.  workspace: diqt_conv_wgrad_workspace_bytes(). */
