@@ -5,14 +5,15 @@ default (`use_ema_unets`, trainer.py:982-1005), casts numpy / CPU arguments to t
 a batch by `max_batch_size` (`imagen_sample_in_chunks`, :201-219).
 
 Training: `forward` / `update` (trainer.py:1038-1130) run the training step of `diffusioniqt_b200/train.py`:
-`imagen(...)`, `loss.backward()` (the hand-written reverse pass), gradient averaging over the ranks, the Adam + EMA kernel.  Learning-rate
-schedulers, warm-up, accelerate's mixed-precision scaler, dataloaders and checkpoint rotation (trainer.py:339-380, 543-812) are not
-mirrored: the scheduler keywords are accepted and ignored, optimizer state in a checkpoint is left alone.
+`imagen(...)`, `loss.backward()` (the hand-written reverse pass), gradient averaging over the ranks, the Adam + EMA kernel.  The cosine
+schedule and the linear warm-up are applied per optimizer step; accelerate's mixed-precision scaler, dataloaders and checkpoint rotation (trainer.py:339-380, 543-812) are not
+mirrored; optimizer state in a checkpoint is left alone.
 """
 from __future__ import annotations
 
 import os
 from contextlib import contextmanager
+import math
 from math import ceil
 
 import numpy as np
@@ -109,7 +110,8 @@ class ImagenTrainer(nn.Module):
         self.only_train_unet_number = only_train_unet_number
         self.checkpoint_path, self.checkpoint_every, self.max_checkpoints_keep = checkpoint_path, checkpoint_every, max_checkpoints_keep
         cast = lambda v: tuple(v) if isinstance(v, (list, tuple)) else (v,) * self.num_unets
-        self._optim_args = dict(lr=cast(lr), eps=cast(eps), beta1=beta1, beta2=beta2)
+        self._optim_args = dict(lr=cast(lr), eps=cast(eps), beta1=beta1, beta2=beta2, warmup_steps=cast(warmup_steps),
+                                cosine_decay_max_steps=cast(cosine_decay_max_steps))
         self._optims = {}
         self._micro = [0] * self.num_unets
         self.max_grad_norm = max_grad_norm
@@ -261,6 +263,21 @@ class ImagenTrainer(nn.Module):
             self._optims[index] = AdamState(self.imagen.unets[index].parameters(), lr=o["lr"][index], betas=(o["beta1"], o["beta2"]), eps=o["eps"][index])
         return self._optims[index]
 
+    def scheduled_lr(self, index, step):
+        """Learning rate of optimizer step `step` (0-based): CosineAnnealingLR(T_max = cosine_decay_max_steps, eta_min = lr[1] * 0.001) in its
+        closed form (trainer.py:368-369), times the linear warm-up of pytorch_warmup's LinearWarmup, min(1, (step + 1) / warmup_steps)
+        (trainer.py:371-372; the package is absent from the reference tree: its published rule)."""
+        o = self._optim_args
+        lr0 = o["lr"][index]
+        tmax, warm = o["cosine_decay_max_steps"][index], o["warmup_steps"][index]
+        lr = lr0
+        if tmax is not None:
+            eta_min = (o["lr"][1] if len(o["lr"]) > 1 else lr0) * 0.001
+            lr = eta_min + (lr0 - eta_min) * (1 + math.cos(math.pi * step / tmax)) / 2
+        if warm is not None:
+            lr *= min(1.0, (step + 1) / warm)
+        return lr
+
     def get_lr(self, unet_number):
         return self._optimizer(unet_number - 1).lr
 
@@ -305,6 +322,7 @@ class ImagenTrainer(nn.Module):
                     ema_params, decay = [p for p in holder.ema_model.parameters()], self._ema_decay(step)
             else:
                 copy_after = None
+        opt.lr = self.scheduled_lr(index, opt.steps)
         opt.step(ema_params=ema_params, ema_decay=decay)
         opt.zero_grad()
         if self.use_ema and copy_after:

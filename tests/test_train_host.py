@@ -118,3 +118,18 @@ def test_gradient_allreduce_two_ranks_gloo():
     for r in (0, 1):
         g = ret[r]
         assert torch.equal(g[0], torch.full((3, 5), 1.5)) and torch.equal(g[1], torch.arange(7.) * 1.5) and torch.equal(g[2], torch.full((2, 2), 0.5))
+
+
+def test_learning_rate_schedule_matches_torch_cosine_annealing_and_linear_warmup():
+    """ImagenTrainer.scheduled_lr against torch.optim.lr_scheduler.CosineAnnealingLR (trainer.py:368-369) and the linear warm-up factor."""
+    from diffusioniqt_b200.trainer import ImagenTrainer
+    class T:
+        _optim_args = dict(lr=(1e-4, 3e-4), warmup_steps=(None, 50), cosine_decay_max_steps=(None, 200))
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.Adam([p], lr=3e-4)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=200, eta_min=3e-4 * 0.001)
+    for step in range(260):
+        want = opt.param_groups[0]["lr"] * min(1.0, (step + 1) / 50)
+        assert abs(ImagenTrainer.scheduled_lr(T, 1, step) - want) < 1e-12 * max(1, step) + 1e-15, step
+        opt.step(); sched.step()
+    assert ImagenTrainer.scheduled_lr(T, 0, 123) == 1e-4
