@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) bwd_apply_kernel(const T* x, int ld_x, co
 }
 
 // ---- the (n, c)-sized algebra between reduce and apply for GroupNorm -> FiLM -> Mish (see gn_backward_coefficients in train.py for the
-// derivation): one CTA, fp64, fixed summation order.  fpart: the forward statistics (sum x, sum x^2), bpart: (sum dw, sum dw x).
+// derivation): one CTA per volume, fp64, fixed summation order; d gamma / d beta leave as per-volume rows [n][c].  fpart: the forward statistics (sum x, sum x^2), bpart: (sum dw, sum dw x).
 __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* fpart, int nblk_f, const float* bpart, int nblk_b, int n, int64_t voxels, int c,
                                                                int groups, float eps, const float* gamma, const float* beta, const float* film,
                                                                float* c1, float* c2, float* c3, float* dgamma, float* dbeta, float* dfilm) {
@@ -182,8 +182,8 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* fpar
   double* gst = tot + (size_t)c * 4;             // [groups][4]: mean, rstd, m1, m2
   pdl_sync();
   const double cnt = (double)voxels * cpg;
-  double dg[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};   // thread tid owns channels tid, tid + blockDim, ... (c <= 4096)
-  for (int nv = 0; nv < n; ++nv) {
+  {
+    const int nv = blockIdx.x;      // one CTA per volume; d gamma / d beta leave as per-volume rows [n][c] (summed over n by the caller)
     for (int idx = threadIdx.x; idx < parts * c; idx += blockDim.x) {
       const int ch = idx % c, part = idx / c;
       double s = 0, q = 0, s1 = 0, s2 = 0;
@@ -223,14 +223,14 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* fpar
       gst[g * 4 + 1] = 1.0 / sqrt(var + (double)eps);
     }
     __syncthreads();
-    int slot = 0;
-    for (int ch = threadIdx.x; ch < c; ch += blockDim.x, ++slot) {
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
       const int g = ch / cpg;
       const double mu = gst[g * 4], r = gst[g * 4 + 1];
       const double S1 = tot[ch * 4 + 2], S2 = r * (tot[ch * 4 + 3] - mu * S1);
       const double k = film ? 1.0 + (double)film[(int64_t)nv * 2 * c + ch] : 1.0;
       const double ga = gamma[ch], be = beta[ch];
-      if (slot < 4) { db[slot] += k * S1; dg[slot] += k * S2; }
+      dbeta[(int64_t)nv * c + ch] = (float)(k * S1);
+      dgamma[(int64_t)nv * c + ch] = (float)(k * S2);
       if (dfilm) {
         dfilm[(int64_t)nv * 2 * c + ch] = (float)(ga * S2 + be * S1);
         dfilm[(int64_t)nv * 2 * c + c + ch] = (float)S1;
@@ -255,18 +255,12 @@ __global__ void __launch_bounds__(1024) gn_bwd_finalize_kernel(const float* fpar
       c2[o] = (float)(-r * r * m2);
       c3[o] = (float)(r * (r * m2 * mu - m1));
     }
-    __syncthreads();
-  }
-  int slot = 0;
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x, ++slot) {
-    dgamma[ch] = (float)dg[slot];
-    dbeta[ch] = (float)db[slot];
   }
 }
 
 // ---- reverse of the SE gate MLP (SE3D :617-632: gate = sigmoid(W2 relu(W1 mean_v h))), one CTA, fp32, fixed order.
 // fpart: forward statistics of h ([n][nblk_f][c][2], sum h first); bpart: diqt_bwd_reduce mode 0 ([n][nblk_b][c][2], sum d_out * h second).
-// Outputs: c3[n][c] = d loss / d mean / V (the additive term of diqt_bwd_apply), dw1[hid][c], dw2[c][hid] summed over the batch.
+// Outputs: c3[n][c] = d loss / d mean / V (the additive term of diqt_bwd_apply) and per-volume dw1[n][hid][c], dw2[n][c][hid]; one CTA per volume.
 __global__ void __launch_bounds__(512) se_bwd_kernel(const float* fpart, int nblk_f, const float* bpart, int nblk_b, int n, int64_t voxels, int c, int hid,
                                                      const float* w1, const float* w2, const float* gate, float* c3, float* dw1, float* dw2) {
   extern __shared__ float se_sm[];
@@ -276,9 +270,10 @@ __global__ void __launch_bounds__(512) se_bwd_kernel(const float* fpart, int nbl
   float* dz = z + hid;            // [hid]
   pdl_sync();
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < hid * c; i += nt) { dw1[i] = 0.f; dw2[i] = 0.f; }
-  __syncthreads();
-  for (int nv = 0; nv < n; ++nv) {
+  {
+    const int nv = blockIdx.x;      // one CTA per volume; dw1 / dw2 leave as per-volume slabs [n][hid * c] (summed over n by the caller)
+    dw1 += (int64_t)nv * hid * c;
+    dw2 += (int64_t)nv * hid * c;
     // row sums: blockDim / c slices per channel, four loads in flight each, slices added in a fixed order
     {
       const int parts = max(1, nt / c);
@@ -325,16 +320,15 @@ __global__ void __launch_bounds__(512) se_bwd_kernel(const float* fpart, int nbl
     __syncthreads();
     for (int i = tid; i < hid * c; i += nt) {
       const int j1 = i / c, c1i = i - j1 * c;         // dw1[j][ch] += dz[j] mean[ch]
-      dw1[i] += dz[j1] * mean[c1i];
-      const int c2i = i / hid, j2 = i - c2i * hid;    // dw2[ch][j] += dy[ch] relu(z[j])
-      dw2[i] += dy[c2i] * fmaxf(z[j2], 0.f);
+      dw1[i] = dz[j1] * mean[c1i];
+      const int c2i = i / hid, j2 = i - c2i * hid;    // dw2[ch][j] = dy[ch] relu(z[j])
+      dw2[i] = dy[c2i] * fmaxf(z[j2], 0.f);
     }
     for (int ch = tid; ch < c; ch += nt) {
       float d = 0.f;
       for (int j = 0; j < hid; ++j) d = fmaf(w1[j * c + ch], dz[j], d);   // d mean = W1^T dz
       c3[(int64_t)nv * c + ch] = d / (float)voxels;
     }
-    __syncthreads();
   }
 }
 
@@ -582,7 +576,7 @@ extern "C" int diqt_gn_bwd_finalize(const float* fwd_partial, int nblk_f, const 
     DIQT_CUDA(cudaFuncSetAttribute(gn_bwd_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  launch_pdl(gn_bwd_finalize_kernel, dim3(1), dim3(threads), sh, (cudaStream_t)stream, fwd_partial, nblk_f, bwd_partial, nblk_b, n, voxels, c, groups, eps, gamma,
+  launch_pdl(gn_bwd_finalize_kernel, dim3(n), dim3(threads), sh, (cudaStream_t)stream, fwd_partial, nblk_f, bwd_partial, nblk_b, n, voxels, c, groups, eps, gamma,
              beta, film, c1, c2, c3, dgamma, dbeta, dfilm);
   return check_launch("gn_bwd_finalize");
 }
@@ -593,7 +587,7 @@ extern "C" int diqt_se_bwd(const float* fwd_partial, int nblk_f, const float* bw
                "se_bwd: bad arguments");
   const size_t sh = ((size_t)2 * c + 2 * hidden + (size_t)2 * (512 / c > 0 ? 512 / c : 1) * c) * sizeof(float);
   DIQT_REQUIRE(sh <= 48 * 1024, "se_bwd: c=%d too wide", c);
-  launch_pdl(se_bwd_kernel, dim3(1), dim3(512), sh, (cudaStream_t)stream, fwd_partial, nblk_f, bwd_partial, nblk_b, n, voxels, c, hidden, w1, w2, gate, c3, dw1,
+  launch_pdl(se_bwd_kernel, dim3(n), dim3(512), sh, (cudaStream_t)stream, fwd_partial, nblk_f, bwd_partial, nblk_b, n, voxels, c, hidden, w1, w2, gate, c3, dw1,
              dw2);
   return check_launch("se_bwd");
 }

@@ -167,14 +167,14 @@ class UnetBackprop:
         # the (n, c)-sized algebra (gn_backward_coefficients below states it in torch; tests/test_train_host.py checks it against autograd)
         fpart, film = s["part"], s["film"]
         c1, c2, c3 = (torch.empty(n, c, dtype=torch.float32, device=x.device) for _ in range(3))
-        dgamma, dbeta = (torch.empty(c, dtype=torch.float32, device=x.device) for _ in range(2))
+        dgamma, dbeta = (torch.empty(n, c, dtype=torch.float32, device=x.device) for _ in range(2))     # per-volume rows
         dfilm = torch.empty(n, 2 * c, dtype=torch.float32, device=x.device) if film is not None else None
         gamma, beta = gn.weight.detach().float().contiguous(), gn.bias.detach().float().contiguous()
         L.check(self.lib.diqt_gn_bwd_finalize(fpart.data_ptr(), fpart.shape[1], part.data_ptr(), NBLK, n, vox, c, G, gn.eps, gamma.data_ptr(), beta.data_ptr(),
                                               L.ptr(film), c1.data_ptr(), c2.data_ptr(), c3.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), L.ptr(dfilm), st),
                 "gn_bwd_finalize")
-        _accum(gn.bias, dbeta)
-        _accum(gn.weight, dgamma)
+        _accum(gn.bias, dbeta.sum(dim=0))
+        _accum(gn.weight, dgamma.sum(dim=0))
         dx = torch.empty_like(x)
         L.check(self.lib.diqt_bwd_apply(x.data_ptr(), c, dz.data_ptr(), c, L.ptr(acc), c, dx.data_ptr(), c, _dt(x), n, vox, c, a.data_ptr(), b.data_ptr(),
                                         c1.data_ptr(), c2.data_ptr(), c3.data_ptr(), 1, _nblk_apply(x), st), "bwd_apply")
@@ -248,11 +248,11 @@ class UnetBackprop:
             hpart, gate = sv["hpart"], sv["gate"].contiguous()
             hid = w1.shape[0]
             c3 = torch.empty(n, c, dtype=torch.float32, device=h2.device)
-            dw1, dw2 = torch.empty_like(w1), torch.empty_like(w2)
+            dw1, dw2 = torch.empty(n, *w1.shape, dtype=torch.float32, device=h2.device), torch.empty(n, *w2.shape, dtype=torch.float32, device=h2.device)
             L.check(self.lib.diqt_se_bwd(hpart.data_ptr(), hpart.shape[1], part.data_ptr(), NBLK, n, vox, c, hid, w1.data_ptr(), w2.data_ptr(), gate.data_ptr(),
                                          c3.data_ptr(), dw1.data_ptr(), dw2.data_ptr(), st), "se_bwd")
-            _accum(blk.se.fc[0].weight, dw1)
-            _accum(blk.se.fc[2].weight, dw2)
+            _accum(blk.se.fc[0].weight, dw1.sum(dim=0))
+            _accum(blk.se.fc[2].weight, dw2.sum(dim=0))
             c1 = gate
             d_h2 = torch.empty_like(h2)
             L.check(self.lib.diqt_bwd_apply(0, c, d_out.data_ptr(), c, 0, c, d_h2.data_ptr(), c, _dt(h2), n, vox, c, 0, 0, c1.data_ptr(), 0, c3.data_ptr(), 0,

@@ -268,13 +268,15 @@ int diqt_bwd_apply(const void* x, int ld_x, const void* dz, int ld_dz, const voi
                    int n, int64_t voxels, int c, const float* a, const float* b, const float* c1, const float* c2, const float* c3,
                    int mode, int nblk, void* stream);
 /* The (n, c)-sized step between the two: from the forward statistics (fwd_partial[n][nblk_f][c][2] of diqt_channel_stats) and
- * bwd_partial[n][nblk_b][c][2] of diqt_bwd_reduce (mode 1) to the coefficients c1, c2, c3 [n][c] of diqt_bwd_apply, d gamma / d beta [c]
- * and (film != NULL) d (scale | shift) [n][2c]; fp64 inside, one CTA, fixed summation order. */
+ * bwd_partial[n][nblk_b][c][2] of diqt_bwd_reduce (mode 1) to the coefficients c1, c2, c3 [n][c] of diqt_bwd_apply, per-volume rows
+ * d gamma / d beta [n][c] (the caller adds them over n) and (film != NULL) d (scale | shift) [n][2c]; fp64 inside, one CTA per volume,
+ * fixed summation order. */
 int diqt_gn_bwd_finalize(const float* fwd_partial, int nblk_f, const float* bwd_partial, int nblk_b, int n, int64_t voxels, int c,
                          int groups, float eps, const float* gamma, const float* beta, const float* film, float* c1, float* c2, float* c3,
                          float* dgamma, float* dbeta, float* dfilm, void* stream);
 /* Reverse of the SE gate MLP (:617-632) between the plain-mode reduce and apply: from the forward statistics of h, the reduce's
- * sum_v d_out * h and the forward gate to c3[n][c] = d mean / V and the weight gradients dw1[hidden][c], dw2[c][hidden] (batch-summed). */
+ * sum_v d_out * h and the forward gate to c3[n][c] = d mean / V and per-volume weight gradients dw1[n][hidden][c], dw2[n][c][hidden]
+ * (the caller adds them over n); one CTA per volume. */
 int diqt_se_bwd(const float* fwd_partial, int nblk_f, const float* bwd_partial, int nblk_b, int n, int64_t voxels, int c, int hidden,
                 const float* w1, const float* w2, const float* gate, float* c3, float* dw1, float* dw2, void* stream);
 /* dw[c_out][c_in][taps] (the layout of nn.Conv3d.weight, fp32) = sum over voxels of dy[v][c_out] * x[v + tap][c_in]; taps 27: 3x3x3 with
