@@ -543,3 +543,33 @@ class AdamState:
     def zero_grad(self):
         for p in self.params:
             p.grad = None
+
+    # ---- the layout of torch.optim.Adam.state_dict() (what trainer.py:858 stores under 'optim{i}'), so that checkpoints written by the
+    # reference resume here and the other way round: state[i] = {step, exp_avg, exp_avg_sq} by parameter index, one param group
+    def state_dict(self):
+        state = {}
+        if self.steps > 0:
+            for i in range(len(self.params)):
+                state[i] = dict(step=torch.tensor(float(self.steps)), exp_avg=self.m[i].detach().clone(), exp_avg_sq=self.v[i].detach().clone())
+        group = dict(lr=self.lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.weight_decay, amsgrad=False, maximize=False, foreach=None,
+                     capturable=False, differentiable=False, fused=None, decoupled_weight_decay=False, params=list(range(len(self.params))))
+        return dict(state=state, param_groups=[group])
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        order = [i for g in groups for i in g["params"]]
+        if len(order) != len(self.params):
+            raise ValueError(f"optimizer state has {len(order)} parameters, this U-Net {len(self.params)}")
+        g0 = groups[0]
+        self.lr, self.betas, self.eps = g0["lr"], tuple(g0["betas"]), g0["eps"]
+        self.weight_decay = g0.get("weight_decay", 0.0)
+        steps = 0
+        for pos, idx in enumerate(order):
+            st = sd["state"].get(idx)
+            if st is None:
+                self.m[pos].zero_(); self.v[pos].zero_()
+                continue
+            self.m[pos].copy_(st["exp_avg"].to(self.m[pos].device, torch.float32))
+            self.v[pos].copy_(st["exp_avg_sq"].to(self.v[pos].device, torch.float32))
+            steps = max(steps, int(float(st["step"])))
+        self.steps = steps

@@ -145,11 +145,14 @@ class ImagenTrainer(nn.Module):
         pass
 
     # ------------------------------------------------------------------ checkpoints (trainer.py:816-945)
-    def save(self, path, overwrite=True, without_optim_and_sched=True, **kwargs):
+    def save(self, path, overwrite=True, without_optim_and_sched=False, **kwargs):
         path = str(path)
         assert overwrite or not os.path.exists(path)
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
         save_obj = dict(model=self.imagen.state_dict(), version=__version__, steps=self.steps.cpu(), **kwargs)
+        if not without_optim_and_sched:      # trainer.py:838-858: 'optim{i}' = torch.optim.Adam.state_dict() of every U-Net that has trained
+            for ind, opt in self._optims.items():
+                save_obj[f'optim{ind}'] = opt.state_dict()
         if self.use_ema:
             save_obj['ema'] = self.ema_unets.state_dict()
         torch.save(save_obj, path)
@@ -173,6 +176,14 @@ class ImagenTrainer(nn.Module):
             return loaded_obj
         if 'steps' in loaded_obj:
             self.steps.copy_(loaded_obj['steps'])
+        for ind, unet in enumerate(self.imagen.unets):          # trainer.py:909-931: resume the optimizers that were saved
+            key = f'optim{ind}'
+            if key in loaded_obj and not isinstance(unet, NullUnet):
+                try:
+                    self._optimizer(ind).load_state_dict(loaded_obj[key])
+                except Exception:   # noqa: BLE001  (the reference resumes with a fresh optimizer in this case, :927-931)
+                    self.print('could not load optimizer and scaler, possibly because you have turned on mixed precision training since the last run. '
+                               'resuming with new optimizer and scalers')
         if self.use_ema:
             assert 'ema' in loaded_obj
             # ema_pytorch keys: '<i>.ema_model.<param>', '<i>.online_model.<param>', '<i>.initted', '<i>.step'

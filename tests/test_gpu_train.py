@@ -235,3 +235,39 @@ def test_trainer_steps_reduce_the_loss_and_refresh_the_sampler():
     assert all(p.grad is None for p in imagen.unets[1].parameters())
     out, _, _ = trainer.sample(batch_size=2, start_image_or_video=lr, start_at_unet_number=2, use_non_ema=True)
     assert torch.isfinite(out).all()
+
+
+def test_checkpoint_resume_continues_bit_for_bit(tmp_path):
+    """ImagenTrainer.save / load (trainer.py:813-945) with the optimizer state in torch.optim.Adam's layout: a trainer restored from a
+    checkpoint takes the same next step, bit for bit, as the trainer that wrote it."""
+    from diffusioniqt_b200 import Imagen, ImagenTrainer, NullUnet, Unet
+    case = FORWARD_CASES["cfg1_dim32_s16_b2"]
+
+    def make():
+        unet = Unet(**unet_kwargs_for_reference(case))
+        unet.load_state_dict(weights_for(case))
+        imagen = Imagen(unets=(NullUnet(), unet), configs=make_configs(case), image_sizes=(16, 16), channels=1, timesteps=4, pred_objectives="x_start",
+                        loss_type="l2", p2_loss_weight_gamma=0.0, min_bound=-10.0, cond_drop_prob=0.0, auto_normalize_img=False).cuda()
+        imagen.unets[1].set_compute_dtype("fp32")
+        t = ImagenTrainer(configs=make_configs(case), imagen=imagen, lr=1e-4, use_ema=True, gradient_accumulation_steps=1, verbose=False,
+                          warmup_steps=(None, 10), cosine_decay_max_steps=(None, 50))
+        return t.train()
+
+    x, lr, _ = build_inputs(case)
+    a = make()
+    for i in range(3):
+        torch.manual_seed(100 + i)
+        a(x, lr, unet_number=2)
+    path = str(tmp_path / "ckpt.pt")
+    a.save(path)
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    assert "optim1" in ck and float(ck["optim1"]["state"][0]["step"]) == 3.0 and "optim0" not in ck
+    b = make()
+    b.load(path)
+    assert b.num_steps_taken(2) == 3 and b._optimizer(1).steps == 3
+    for t in (a, b):
+        torch.manual_seed(200)
+        t(x, lr, unet_number=2)
+    pa, pb = dict(a.imagen.unets[1].named_parameters()), dict(b.imagen.unets[1].named_parameters())
+    assert all(torch.equal(pa[k], pb[k]) for k in pa)
+    assert a._optimizer(1).lr == b._optimizer(1).lr == a.scheduled_lr(1, 3)

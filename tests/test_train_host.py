@@ -133,3 +133,28 @@ def test_learning_rate_schedule_matches_torch_cosine_annealing_and_linear_warmup
         assert abs(ImagenTrainer.scheduled_lr(T, 1, step) - want) < 1e-12 * max(1, step) + 1e-15, step
         opt.step(); sched.step()
     assert ImagenTrainer.scheduled_lr(T, 0, 123) == 1e-4
+
+
+def test_adam_state_round_trips_through_the_torch_optimizer_format():
+    """AdamState.state_dict() is torch.optim.Adam's layout (what the reference stores under 'optim{i}', trainer.py:858): a torch optimizer
+    loads it, and AdamState loads what a torch optimizer wrote."""
+    from diffusioniqt_b200.train import AdamState
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(5))]
+    ours = AdamState(ps, lr=2e-4, betas=(0.9, 0.99), eps=1e-8)
+    ours.steps = 7
+    for m, v in zip(ours.m, ours.v):
+        m.copy_(torch.randn_like(m)); v.copy_(torch.rand_like(v))
+    sd = ours.state_dict()
+    ref = torch.optim.Adam([torch.nn.Parameter(p.detach().clone()) for p in ps], lr=1.0)
+    ref.load_state_dict(sd)
+    got = ref.state_dict()
+    assert got["param_groups"][0]["lr"] == 2e-4 and tuple(got["param_groups"][0]["betas"]) == (0.9, 0.99)
+    for i in range(2):
+        assert torch.equal(got["state"][i]["exp_avg"], ours.m[i]) and torch.equal(got["state"][i]["exp_avg_sq"], ours.v[i])
+        assert float(got["state"][i]["step"]) == 7.0
+    back = AdamState(ps, lr=1.0)
+    back.load_state_dict(got)
+    assert back.steps == 7 and back.lr == 2e-4 and all(torch.equal(a, b) for a, b in zip(back.m, ours.m))
+    fresh = AdamState(ps)
+    assert fresh.state_dict()["state"] == {}
