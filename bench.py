@@ -455,7 +455,7 @@ def train_step_record(size, batch, reps=5):
     return out
 
 
-def volume_record(dev, rank, world, dist, side=256, timesteps=20, batch=7):
+def volume_record(dev, rank, world, dist, side=256, timesteps=20, batch=None):
     """BASELINE config 3 through the same process group: one synthetic `side`^3 low-field volume cut into overlapping 64^3 patches
     (stride 32: 7^3 = 343 for 256^3, data.py:159-162), 5 % skip rule, contiguous shards over the ranks (343 = 8 * 43 - 1: the last rank
     is one patch short and padded), T denoising iterations per patch (eval_config.yaml:21), ONE all-gather, device-side stitch and
@@ -479,6 +479,11 @@ def volume_record(dev, rank, world, dist, side=256, timesteps=20, batch=7):
     grid = V.patch_grid(low.shape, 64, 32)
     kept = [o for o in grid if V.keep_patch(raw, o, 64)]
     start, stop, per = V.shard_range(len(kept), rank, world)
+    if batch is None:
+        # the shard in equal sampler calls of at most 49 patches (343 = 7 x 49 on one GPU, 43 per call from two GPUs up): the step runs at
+        # 0.66 of the sustained peak with 7 patches per call and at 0.72 with 32 (profiles/bench_configs_r2j.jsonl); ~20 GB of activations
+        calls = max(1, -(-per // 49))
+        batch = max(1, -(-per // calls))
     sizes = {min(batch, stop - start - b0) for b0 in range(0, stop - start, batch)}
     lr0 = torch.zeros((1, 1, 64, 64, 64), device=dev)
     for bsz in sorted(sizes):
