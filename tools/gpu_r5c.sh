@@ -1,0 +1,15 @@
+#!/bin/bash
+OUT=gpurun_out; mkdir -p $OUT
+timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "init_conv" --maxfail=10 --tb=short --timeout=100 --timeout-method=thread > $OUT/pytest_r5c.log 2>&1; echo "pytest rc=$?"
+grep -E "^(FAILED|ERROR)|passed|failed" $OUT/pytest_r5c.log | tail -8
+timeout 60 python tools/bench_init.py 64 64 2>&1 | tail -1
+timeout 60 python tools/bench_init.py 64 128 2>&1 | tail -1
+timeout 60 python tools/bench_init.py 32 64 2>&1 | tail -1
+DIQT_INIT_TY=4 timeout 60 python tools/bench_init.py 64 64 2>&1 | tail -1
+timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:init_conv_tc -c 12 python tools/bench_init.py 64 64 2>&1 | grep -E "gpu__time_duration" | tail -3
+for v in default head; do
+  if [ $v = default ]; then unset DIQT_LIB_PATH; else export DIQT_LIB_PATH=$PWD/build/variants/$v.so; fi
+  timeout 200 python bench.py --timesteps 300 --steps 2 --warmup 1 --no-cpu-baseline --no-volume --no-torch-gpu-baseline --no-train-step 2>/dev/null | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$v ms/iter %.4f' % d['ms_per_denoise_iteration'])"
+done
