@@ -19,7 +19,10 @@
 // maps so that PixelShuffle3D is folded into the store coordinates; for DOWN the pixel-unshuffle
 // is folded into per-tap load tensor maps.
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-5 epilogue.
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2-9 epilogue.  One warp issues an instruction
+// every ~5 cycles here, so the epilogue of a wide tile (128 x 256 with Mish: 4 k instructions per thread) on four warps bounded the
+// pixel-shuffle up-conv at 31 us for 40 MB of traffic (profiles/r5_init_conv.md has the same finding for init_conv): eight warps, the two of a
+// lane quarter splitting the columns.
 #include <string.h>
 
 #include <algorithm>
@@ -32,7 +35,9 @@ namespace diqt {
 constexpr int kTileM = 128;
 constexpr int kABytes = kTileM * 128;  // one A stage: 128 rows x 64 bf16
 constexpr int kMaxMaps = 8;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;              // two warps per TMEM lane quarter, each drains half of the accumulator's columns
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
 
 struct TcParams {
   CUtensorMap in_map[kMaxMaps];
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&tfull_bar[a]), 1);
-      mbar_init(smem_u32(&tempty_bar[a]), 4);
+      mbar_init(smem_u32(&tempty_bar[a]), kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -169,15 +174,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int quarter = warp & 3;           // TMEM lane quarter this warp may read
     const int row = quarter * 32 + lane;    // tile row = voxel index inside the box
-    const int et = threadIdx.x - 64;        // 0..127
+    const int et = threadIdx.x - 64;        // 0..255
+    const int half = et >> 7;               // which half of the tile's 32-column chunks this warp drains
+    const int nc32 = p.block_n / 32, c32_lo = half * (nc32 >> 1), c32_hi = c32_lo + (nc32 >> 1);
     int acc = 0;
     uint32_t acc_phase = 0;
     const int ngroups = p.block_n / 64;
     // fused statistics: thread -> (column pair cp of a 64-column group, row quarter rq); sums live in registers
-    const int cp = et & 31, rq = et >> 5;
+    const int cp = et & 31, rq = (et >> 5) & 3;   // statistics: rows rq * 32 .. + 31 of the 64-column groups g with (g & 1) == half
     float st_s[4][2], st_q[4][2];
 #pragma unroll
     for (int g = 0; g < 4; ++g) st_s[g][0] = st_s[g][1] = st_q[g][0] = st_q[g][1] = 0.f;
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       // combine the four row quarters in a fixed order -> one partial per (volume, CTA): deterministic
 #pragma unroll
       for (int g = 0; g < 4; ++g)
-        if (g < ngroups) {
+        if (g < ngroups && (g & 1) == half) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             s_red[(rq * p.block_n + g * 64 + cp * 2 + h) * 2] = st_s[g][h];
@@ -194,9 +201,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             st_s[g][h] = st_q[g][h] = 0.f;
           }
         }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       float* dst = p.stats + ((size_t)nvol * gridDim.x + blockIdx.x) * p.block_n * 2;
-      for (int col = et; col < p.block_n; col += 128) {
+      for (int col = et; col < p.block_n; col += kEpiThreads) {
         float a = 0.f, b = 0.f;
 #pragma unroll
         for (int r4 = 0; r4 < 4; ++r4) {
@@ -206,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         dst[col * 2] = a;
         dst[col * 2 + 1] = b;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
     };
     for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
       int n_tile, x0, y0, z0, b0;
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // partial tile as [16-byte column chunk][row]: the 32 lanes of a warp (consecutive rows) touch consecutive 16-byte words
         // (the row-major layout of the first version made every access 32 separate sectors: 38 us instead of 21 at 16^3 x 128)
         uint4* mine = reinterpret_cast<uint4*>(p.ws + ((size_t)tile * p.ksplit + ks) * kTileM * p.block_n) + row;
-        for (int c32 = 0; c32 < p.block_n / 32; ++c32) {
+        for (int c32 = c32_lo; c32 < c32_hi; ++c32) {
           uint32_t r[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.block_n + c32 * 32), r);
           tmem_ld_wait();
@@ -230,16 +237,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));  // the accumulator is free: the next unit's MMAs may start
         __threadfence();  // the partial is visible device-wide before the ticket is taken
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         int* s_flag = reinterpret_cast<int*>(s_red);
         if (et == 0) {
           const unsigned t = atomicAdd(&p.tickets[tile], 1u);
           *s_flag = (t == (unsigned)p.ksplit - 1u);
           if (t == (unsigned)p.ksplit - 1u) p.tickets[tile] = 0u;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         const bool last = *s_flag != 0;
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // s_red is reused by the statistics flush
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");  // s_red is reused by the statistics flush
         if (!last) {
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
           continue;
@@ -253,9 +260,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         st_n = b0;
       }
       if (et == 0) bulk_wait_read0();  // previous tile's TMA stores have finished reading the staging tile
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       const float* bias = s_bias + n_tile * p.block_n;
-      for (int c32 = 0; c32 < p.block_n / 32; ++c32) {
+      for (int c32 = c32_lo; c32 < c32_hi; ++c32) {
         uint32_t r[32];
         if (wtile) {  // sum of the partials in split order
 #pragma unroll
@@ -296,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       __syncwarp();
       if (lane == 0 && !wtile) mbar_arrive(smem_u32(&tempty_bar[acc]));  // (split-K released it before the ticket)
       fence_proxy_async();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
       if (et == 0) {
         for (int g = 0; g < ngroups; ++g) {
           const int col = n_tile * p.block_n + g * 64;
@@ -313,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // column sums of the staged (bf16-rounded) tile: a warp reads one 128 B row per step -> conflict free
 #pragma unroll
         for (int g = 0; g < 4; ++g)
-          if (g < ngroups) {
+          if (g < ngroups && (g & 1) == half) {
             const uint8_t* gb = out_stage + (size_t)g * kABytes;
 #pragma unroll 4
             for (int r = 0; r < 32; ++r) {
@@ -337,10 +344,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int nv = 0; nv < p.n_batch; ++nv) {
         if (st_first >= 0 && nv >= st_first && nv <= st_n) continue;
         float* dst = p.stats + ((size_t)nv * gridDim.x + blockIdx.x) * p.block_n * 2;
-        for (int col = et; col < p.block_n * 2; col += 128) dst[col] = 0.f;
+        for (int col = et; col < p.block_n * 2; col += kEpiThreads) dst[col] = 0.f;
       }
-      stats_group_tail(p.sink, p.stats, p.n_batch, (int)gridDim.x, p.block_n, (int)blockIdx.x, 1, et, 128, reinterpret_cast<int*>(s_red),
-                       [] { asm volatile("bar.sync 1, 128;" ::: "memory"); });
+      stats_group_tail(p.sink, p.stats, p.n_batch, (int)gridDim.x, p.block_n, (int)blockIdx.x, 1, et, kEpiThreads, reinterpret_cast<int*>(s_red),
+                       [] { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); });
     }
     if (et == 0) bulk_wait0();
   }
