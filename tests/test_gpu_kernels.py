@@ -398,7 +398,10 @@ def test_init_conv_im2col_tensor_core_path(n, dims, c_in, c_out):
 
 @pytest.mark.parametrize("grouped", [False, True])
 @pytest.mark.parametrize("n,dims,c_in,c_out", [(1, (8, 8, 16), 2, 64), (2, (3, 12, 32), 1, 64), (1, (16, 16, 16), 2, 128), (1, (5, 20, 64), 2, 64),
-                                               (1, (64, 64, 64), 2, 64)])
+                                               (1, (64, 64, 64), 2, 64),
+                                               # work items of 4 y rows (d2 = 128; c_out = 128 at d2 = 64: two accumulator sets of 256 columns),
+                                               # three volumes through one CTA's statistics, more items than CTAs with a ragged last y tile
+                                               (1, (4, 8, 128), 2, 64), (1, (6, 12, 64), 2, 128), (3, (2, 8, 32), 2, 64), (1, (40, 36, 64), 1, 64)])
 def test_init_conv_fused_tensor_core_kernel(n, dims, c_in, c_out, grouped):
     """init_conv (:1291) as ONE kernel: im2col rows built in shared memory, tcgen05 GEMM, bias, bf16 store and the channel statistics the first
     GroupNorm needs -- against F.conv3d on the bf16-rounded input, bit for bit against the round-1 two-kernel path, statistics against
