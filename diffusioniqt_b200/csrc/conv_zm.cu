@@ -55,6 +55,10 @@ namespace diqt {
 #ifndef DIQT_ZM_TRACE
 #define DIQT_ZM_TRACE 0
 #endif
+// DIQT_XF_PACKED (build-time, A/B): the transform's affine + Mish on packed fp32 pairs
+#ifndef DIQT_XF_PACKED
+#define DIQT_XF_PACKED 1
+#endif
 #if DIQT_ZM_TRACE
 __device__ long long g_zm_trace[8 * 2 * 16];
 #define ZM_TRACE(ev, slot, it) do { if (blockIdx.x == 0 && (it) < 16) g_zm_trace[((ev) * 2 + (slot)) * 16 + (it)] = clock64(); } while (0)
@@ -697,6 +701,23 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
 #if DIQT_XF_MODE == 2   // timing experiment: affine only (no MUFU)
 #pragma unroll
                 for (int e = 0; e < 8; ++e) r.v[e] = fmaf(av[e], r.v[e], bv[e]);
+#elif DIQT_XF_PACKED
+                // two channels per instruction on the FMA pipe (FFMA2 / FMUL2 / FADD2, sm_100): per lane the same IEEE operations in the same
+                // order as mish<true>(fmaf(a, x, b)), so the values entering the tensor cores stay bit-identical to the two-kernel path
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                  const float2 y = __ffma2_rn(make_float2(av[e], av[e + 1]), make_float2(r.v[e], r.v[e + 1]), make_float2(bv[e], bv[e + 1]));
+                  const float2 t = __fmul2_rn(y, make_float2(1.4426950408889634f, 1.4426950408889634f));
+                  float2 u, w;
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u.x) : "f"(t.x));
+                  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u.y) : "f"(t.y));
+                  const float2 d = __ffma2_rn(u, __fadd2_rn(u, make_float2(2.f, 2.f)), make_float2(2.f, 2.f));
+                  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(w.x) : "f"(d.x));
+                  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(w.y) : "f"(d.y));
+                  const float2 o = __ffma2_rn(__fmul2_rn(y, w), make_float2(-2.f, -2.f), y);
+                  r.v[e] = o.x;
+                  r.v[e + 1] = o.y;
+                }
 #else
 #pragma unroll
                 for (int e = 0; e < 8; ++e) r.v[e] = mish<true>(fmaf(av[e], r.v[e], bv[e]));
