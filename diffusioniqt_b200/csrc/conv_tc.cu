@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
     for (int g = 0; g < 4; ++g) st_s[g][0] = st_s[g][1] = st_q[g][0] = st_q[g][1] = 0.f;
     int st_n = -1, st_first = -1;
+    const uint32_t stage_a = smem_u32(out_stage);
     auto flush_stats = [&](int nvol) {
       // combine the four row quarters in a fixed order -> one partial per (volume, CTA): deterministic
 #pragma unroll
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       if (et == 0) bulk_wait_read0();  // previous tile's TMA stores have finished reading the staging tile
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      const float* bias = s_bias + n_tile * p.block_n;
+      const uint32_t bias_a = smem_u32(s_bias + n_tile * p.block_n);
       for (int c32 = c32_lo; c32 < c32_hi; ++c32) {
         uint32_t r[32];
         if (wtile) {  // sum of the partials in split order
@@ -282,21 +283,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.block_n + c32 * 32), r);
           tmem_ld_wait();
         }
+        // (bias, staging tile and statistics through 32-bit shared-window addresses, the bias in 16-byte loads: the generic pointers cost
+        // 32 scalar loads per chunk and a 64-bit address computation per access)
         uint32_t packed[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v0 = __uint_as_float(r[2 * j]) + bias[c32 * 32 + 2 * j];
-          float v1 = __uint_as_float(r[2 * j + 1]) + bias[c32 * 32 + 2 * j + 1];
-          if (p.mode == DIQT_CONV_UP) { v0 = mish<true>(v0); v1 = mish<true>(v1); }
-          __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-          packed[j] = *reinterpret_cast<uint32_t*>(&h);
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const uint4 bq = lds_128(bias_a + (uint32_t)(c32 * 32 + j4 * 4) * 4);
+          float v0 = __uint_as_float(r[4 * j4]) + __uint_as_float(bq.x), v1 = __uint_as_float(r[4 * j4 + 1]) + __uint_as_float(bq.y);
+          float v2 = __uint_as_float(r[4 * j4 + 2]) + __uint_as_float(bq.z), v3 = __uint_as_float(r[4 * j4 + 3]) + __uint_as_float(bq.w);
+          if (p.mode == DIQT_CONV_UP) { v0 = mish<true>(v0); v1 = mish<true>(v1); v2 = mish<true>(v2); v3 = mish<true>(v3); }
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+          packed[2 * j4] = *reinterpret_cast<uint32_t*>(&h0);
+          packed[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
         }
         // 64 B of this row -> four 16 B chunks of a 128 B swizzled staging row
-        uint8_t* rowp = out_stage + (size_t)(c32 >> 1) * kABytes + (size_t)row * 128;
+        const uint32_t rowp = stage_a + (uint32_t)((c32 >> 1) * kABytes + row * 128);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int chunk = ((c32 & 1) * 4 + j) ^ (row & 7);
-          *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          sts_128(rowp + (uint32_t)(chunk * 16), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
         }
       }
       tc_fence_before();
@@ -321,7 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
         for (int g = 0; g < 4; ++g)
           if (g < ngroups && (g & 1) == half) {
-            const uint8_t* gb = out_stage + (size_t)g * kABytes;
+            const uint32_t gb = stage_a + (uint32_t)(g * kABytes);
 #pragma unroll 4
             for (int r = 0; r < 32; ++r) {
               const int rr = rq * 32 + r;
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 const int lx = rr % p.bx, ly = (rr / p.bx) % p.by, lz = rr / (p.bx * p.by);
                 if (x0 + lx >= p.ox || y0 + ly >= p.oy || z0 + lz >= p.oz) continue;
               }
-              const uint32_t v = *reinterpret_cast<const uint32_t*>(gb + (size_t)rr * 128 + (((cp >> 2) ^ (rr & 7)) << 4) + ((cp & 3) << 2));
+              const uint32_t v = lds_u32(gb + (uint32_t)(rr * 128 + (((cp >> 2) ^ (rr & 7)) << 4) + ((cp & 3) << 2)));
               const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
               st_s[g][0] += lo; st_q[g][0] = fmaf(lo, lo, st_q[g][0]);
               st_s[g][1] += hi; st_q[g][1] = fmaf(hi, hi, st_q[g][1]);

@@ -478,6 +478,7 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
     const int et = threadIdx.x - W_EPI * 32;  // 0..127
     const int cp = et & 31, rq = et >> 5;
     const int nblk = 2 * (int)gridDim.x;
+    const uint32_t stage_a = smem_u32(out_stage);
     pdl_wait();
     int kcount[2] = {0, 0};
     float st_s[2][2], st_q[2][2];
@@ -533,7 +534,7 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
           if (i >= it.niter) continue;
           const int pl = it.p_lo + i;
           const int k = kcount[s];
-          const float* bias = s_bias + it.nh * 64;
+          const uint32_t bias_a = smem_u32(s_bias + it.nh * 64);
           mbar_wait(smem_u32(&acc_full[s * 2 + (k & 1)]), (uint32_t)((k >> 1) & 1));
           if (et == 0) ZM_TRACE(5, s, i);
           tc_fence_after();
@@ -551,18 +552,21 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
               tmem_ld32(tcol + c32 * 32, r);
               tmem_ld_wait();
               tmem_st32_zero(tcol + c32 * 32);  // the block is reused for output plane z+4
+              // (bias, staging tile and statistics through 32-bit shared-window addresses and 16-byte bias loads: the generic pointers
+              // cost 64 scalar bias loads and a 64-bit address computation per access)
               uint32_t packed[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(r[2 * j]) + bias[c32 * 32 + 2 * j],
-                                                          __uint_as_float(r[2 * j + 1]) + bias[c32 * 32 + 2 * j + 1]);
-                packed[j] = *reinterpret_cast<uint32_t*>(&h);
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const uint4 bq = lds_128(bias_a + (uint32_t)(c32 * 32 + j4 * 4) * 4);
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(r[4 * j4]) + __uint_as_float(bq.x), __uint_as_float(r[4 * j4 + 1]) + __uint_as_float(bq.y));
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(r[4 * j4 + 2]) + __uint_as_float(bq.z), __uint_as_float(r[4 * j4 + 3]) + __uint_as_float(bq.w));
+                packed[2 * j4] = *reinterpret_cast<uint32_t*>(&h0);
+                packed[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
               }
-              uint8_t* rowp = out_stage + (size_t)row * 128;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int chunk = (c32 * 4 + j) ^ (row & 7);
-                *reinterpret_cast<uint4*>(rowp + chunk * 16) = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+                sts_128(stage_a + (uint32_t)(row * 128 + chunk * 16), packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
               }
             }
             fence_proxy_async();
@@ -575,7 +579,7 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
 #pragma unroll 4
               for (int r = 0; r < 32; ++r) {
                 const int rr = rq * 32 + r;
-                const uint32_t v = *reinterpret_cast<const uint32_t*>(out_stage + (size_t)rr * 128 + (((cp >> 2) ^ (rr & 7)) << 4) + ((cp & 3) << 2));
+                const uint32_t v = lds_u32(stage_a + (uint32_t)(rr * 128 + (((cp >> 2) ^ (rr & 7)) << 4) + ((cp & 3) << 2)));
                 const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
                 st_s[s][0] += lo; st_q[s][0] = fmaf(lo, lo, st_q[s][0]);
                 st_s[s][1] += hi; st_q[s][1] = fmaf(hi, hi, st_q[s][1]);
@@ -683,7 +687,8 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
             const uint32_t vm = s ? vmask[1] : vmask[0];
             mbar_wait(smem_u32(&pl_full[b]), s ? phase[1] : phase[0]);
             if (tt == 0) ZM_TRACE(1, s, i);
-            uint8_t* base = planes + (size_t)b * ZM_PLANE_STRIDE + rbase * 128 + pc * 16;
+            // (32-bit shared-window addresses: through the generic pointer every access cost a 64-bit address computation)
+            const uint32_t base = smem_u32(planes + (size_t)b * ZM_PLANE_STRIDE + rbase * 128 + pc * 16);
 #if DIQT_XF_MODE == 1   // timing experiment: handshake only, the plane is handed on untouched
             if (false)
 #endif
@@ -692,7 +697,7 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
               uint4 raw[3];
 #pragma unroll
               for (int u = 0; u < 3; ++u)
-                if ((vm >> (k0 + u)) & 1u) raw[u] = *reinterpret_cast<const uint4*>(base + (k0 + u) * 32 * 128);
+                if ((vm >> (k0 + u)) & 1u) raw[u] = lds_128(base + (uint32_t)((k0 + u) * 32 * 128));
 #pragma unroll
               for (int u = 0; u < 3; ++u) {
                 if (!((vm >> (k0 + u)) & 1u)) continue;
@@ -722,7 +727,15 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
 #pragma unroll
                 for (int e = 0; e < 8; ++e) r.v[e] = mish<true>(fmaf(av[e], r.v[e], bv[e]));
 #endif
-                r.store(reinterpret_cast<__nv_bfloat16*>(base + (k0 + u) * 32 * 128));
+                {
+                  uint32_t w[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    __nv_bfloat162 h = __floats2bfloat162_rn(r.v[2 * e], r.v[2 * e + 1]);
+                    w[e] = *reinterpret_cast<uint32_t*>(&h);
+                  }
+                  sts_128(base + (uint32_t)((k0 + u) * 32 * 128), w[0], w[1], w[2], w[3]);
+                }
               }
             }
             fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
