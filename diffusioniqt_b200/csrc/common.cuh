@@ -399,4 +399,21 @@ __device__ __forceinline__ float mish(float x) {
   return x * (n / (n + 2.f));
 }
 
+// mish<true> on two values at once: the non-MUFU arithmetic as packed fp32x2 instructions (FMUL2 / FADD2 / FFMA2, sm_100); per lane the same
+// operations in the same order, so the results are bit-identical to mish<true> (DIQT_MISH_V2 form)
+__device__ __forceinline__ float2 mish2_fast(float2 x) {
+#if DIQT_MISH_V2
+  const float2 t = __fmul2_rn(x, make_float2(1.4426950408889634f, 1.4426950408889634f));
+  float2 u, w;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u.x) : "f"(t.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u.y) : "f"(t.y));
+  const float2 d = __ffma2_rn(u, __fadd2_rn(u, make_float2(2.f, 2.f)), make_float2(2.f, 2.f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(w.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(w.y) : "f"(d.y));
+  return __ffma2_rn(__fmul2_rn(x, w), make_float2(-2.f, -2.f), x);
+#else
+  return make_float2(mish<true>(x.x), mish<true>(x.y));
+#endif
+}
+
 }  // namespace diqt

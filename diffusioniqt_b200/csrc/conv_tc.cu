@@ -289,10 +289,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const uint4 bq = lds_128(bias_a + (uint32_t)(c32 * 32 + j4 * 4) * 4);
-          float v0 = __uint_as_float(r[4 * j4]) + __uint_as_float(bq.x), v1 = __uint_as_float(r[4 * j4 + 1]) + __uint_as_float(bq.y);
-          float v2 = __uint_as_float(r[4 * j4 + 2]) + __uint_as_float(bq.z), v3 = __uint_as_float(r[4 * j4 + 3]) + __uint_as_float(bq.w);
-          if (p.mode == DIQT_CONV_UP) { v0 = mish<true>(v0); v1 = mish<true>(v1); v2 = mish<true>(v2); v3 = mish<true>(v3); }
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
+          // two channels per FADD2 / FFMA2 / FMUL2 (per lane the same IEEE operations as the scalar code and as mish<true>)
+          float2 v01 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), make_float2(__uint_as_float(bq.x), __uint_as_float(bq.y)));
+          float2 v23 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), make_float2(__uint_as_float(bq.z), __uint_as_float(bq.w)));
+          if (p.mode == DIQT_CONV_UP) { v01 = mish2_fast(v01); v23 = mish2_fast(v23); }
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v01.x, v01.y), h1 = __floats2bfloat162_rn(v23.x, v23.y);
           packed[2 * j4] = *reinterpret_cast<uint32_t*>(&h0);
           packed[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
         }
@@ -335,9 +336,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 if (x0 + lx >= p.ox || y0 + ly >= p.oy || z0 + lz >= p.oz) continue;
               }
               const uint32_t v = lds_u32(gb + (uint32_t)(rr * 128 + (((cp >> 2) ^ (rr & 7)) << 4) + ((cp & 3) << 2)));
-              const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
-              st_s[g][0] += lo; st_q[g][0] = fmaf(lo, lo, st_q[g][0]);
-              st_s[g][1] += hi; st_q[g][1] = fmaf(hi, hi, st_q[g][1]);
+              const float2 lh = make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+              const float2 ns = __fadd2_rn(make_float2(st_s[g][0], st_s[g][1]), lh);
+              const float2 nq = __ffma2_rn(lh, lh, make_float2(st_q[g][0], st_q[g][1]));
+              st_s[g][0] = ns.x; st_s[g][1] = ns.y; st_q[g][0] = nq.x; st_q[g][1] = nq.y;
             }
           }
       }

@@ -558,8 +558,11 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const uint4 bq = lds_128(bias_a + (uint32_t)(c32 * 32 + j4 * 4) * 4);
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(r[4 * j4]) + __uint_as_float(bq.x), __uint_as_float(r[4 * j4 + 1]) + __uint_as_float(bq.y));
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(r[4 * j4 + 2]) + __uint_as_float(bq.z), __uint_as_float(r[4 * j4 + 3]) + __uint_as_float(bq.w));
+                // (two channels per FADD2: the same IEEE additions per lane)
+                const float2 v01 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j4]), __uint_as_float(r[4 * j4 + 1])), make_float2(__uint_as_float(bq.x), __uint_as_float(bq.y)));
+                const float2 v23 = __fadd2_rn(make_float2(__uint_as_float(r[4 * j4 + 2]), __uint_as_float(r[4 * j4 + 3])), make_float2(__uint_as_float(bq.z), __uint_as_float(bq.w)));
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(v01.x, v01.y);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(v23.x, v23.y);
                 packed[2 * j4] = *reinterpret_cast<uint32_t*>(&h0);
                 packed[2 * j4 + 1] = *reinterpret_cast<uint32_t*>(&h1);
               }
@@ -580,9 +583,10 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
               for (int r = 0; r < 32; ++r) {
                 const int rr = rq * 32 + r;
                 const uint32_t v = lds_u32(stage_a + (uint32_t)(rr * 128 + (((cp >> 2) ^ (rr & 7)) << 4) + ((cp & 3) << 2)));
-                const float lo = __uint_as_float(v << 16), hi = __uint_as_float(v & 0xffff0000u);
-                st_s[s][0] += lo; st_q[s][0] = fmaf(lo, lo, st_q[s][0]);
-                st_s[s][1] += hi; st_q[s][1] = fmaf(hi, hi, st_q[s][1]);
+                const float2 lh = make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+                const float2 ns = __fadd2_rn(make_float2(st_s[s][0], st_s[s][1]), lh);          // (channel pair per instruction, same sums per lane)
+                const float2 nq = __ffma2_rn(lh, lh, make_float2(st_q[s][0], st_q[s][1]));
+                st_s[s][0] = ns.x; st_s[s][1] = ns.y; st_q[s][0] = nq.x; st_q[s][1] = nq.y;
               }
             }
           }

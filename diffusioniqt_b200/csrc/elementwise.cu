@@ -525,21 +525,30 @@ scale_residual_ring_kernel(const __nv_bfloat16* __restrict__ h, const __nv_bfloa
     const int64_t r0 = (int64_t)t * tile_rows;
     const int rows = (int)min((int64_t)tile_rows, (v1 - v0) - r0);
     mbar_wait(smem_u32(&full[stage]), phase);
-    const uint8_t* hs = ring + (size_t)(stage * 2) * RS_TILE_BYTES + (size_t)col * 16;
-    const uint8_t* rs = hs + RS_TILE_BYTES;
+    // (32-bit shared-window loads and channel pairs per FFMA2 / FADD2: the same IEEE operations per lane with about two thirds of the
+    // instructions; one warp issues an instruction every ~5 cycles, so the instruction count is part of this kernel's time)
+    const uint32_t hs = smem_u32(ring + (size_t)(stage * 2) * RS_TILE_BYTES) + (uint32_t)col * 16;
+    const uint32_t rs = hs + RS_TILE_BYTES;
     for (int r = lane; r < rows; r += lanes) {
-      Vec<__nv_bfloat16> a, x, o;
-      a.unpack(*reinterpret_cast<const uint4*>(hs + (size_t)r * c * 2));
-      x.unpack(*reinterpret_cast<const uint4*>(rs + (size_t)r * c * 2));
+      Vec<__nv_bfloat16> a, x;
+      a.unpack(lds_128(hs + (uint32_t)(r * c * 2)));
+      x.unpack(lds_128(rs + (uint32_t)(r * c * 2)));
+      uint32_t w4[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] = fmaf(a.v[i], g[i], x.v[i]);
-      o.store(ob + (r0 + r) * ld_out);
+      for (int i = 0; i < 4; ++i) {
+        const float2 o = __ffma2_rn(make_float2(a.v[2 * i], a.v[2 * i + 1]), make_float2(g[2 * i], g[2 * i + 1]), make_float2(x.v[2 * i], x.v[2 * i + 1]));
+        __nv_bfloat162 hh = __floats2bfloat162_rn(o.x, o.y);
+        w4[i] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      *reinterpret_cast<uint4*>(ob + (r0 + r) * ld_out) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
       if (partial) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float w = to_float(from_float<__nv_bfloat16>(o.v[i]));   // what the next GroupNorm will read: the stored, rounded value
-          s[i] += w;
-          q[i] = fmaf(w, w, q[i]);
+        for (int i = 0; i < 4; ++i) {
+          // what the next GroupNorm will read: the stored, rounded values
+          const float2 w = make_float2(__uint_as_float(w4[i] << 16), __uint_as_float(w4[i] & 0xffff0000u));
+          const float2 ns = __fadd2_rn(make_float2(s[2 * i], s[2 * i + 1]), w);
+          const float2 nq = __ffma2_rn(w, w, make_float2(q[2 * i], q[2 * i + 1]));
+          s[2 * i] = ns.x; s[2 * i + 1] = ns.y; q[2 * i] = nq.x; q[2 * i + 1] = nq.y;
         }
       }
     }
