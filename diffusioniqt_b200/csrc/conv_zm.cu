@@ -646,6 +646,7 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
     // (rbase + 32 k) & 7 == rbase & 7, so one thread always works on the same eight channels of a 64-channel chunk
     const int pc = tt & 7, rbase = tt >> 3;
     const int ch0 = (pc ^ (rbase & 7)) << 3;
+    const uint32_t aff_a = smem_u32(aff);
     constexpr int XF_ROWS = (ZM_PLANE_ROWS + 31) / 32;  // 6 row groups of 32
     int ring[2] = {0, 0};
     uint32_t phase[2] = {0, 0};
@@ -676,9 +677,12 @@ __global__ void __launch_bounds__(kGN ? ZM_THREADS_GN : ZM_THREADS, 1) conv_zm_k
             {
               float4 a0, a1, b0, b1;
               if (p.gn.group) {
-                const float4* ap = reinterpret_cast<const float4*>(aff + it.b * c_in + kc * 64 + ch0);
-                const float4* bp = reinterpret_cast<const float4*>(aff + (p.n + it.b) * c_in + kc * 64 + ch0);
-                a0 = ap[0]; a1 = ap[1]; b0 = bp[0]; b1 = bp[1];
+                const uint32_t ap = aff_a + (uint32_t)(it.b * c_in + kc * 64 + ch0) * 4, bp = aff_a + (uint32_t)((p.n + it.b) * c_in + kc * 64 + ch0) * 4;
+                const uint4 qa0 = lds_128(ap), qa1 = lds_128(ap + 16), qb0 = lds_128(bp), qb1 = lds_128(bp + 16);
+                a0 = make_float4(__uint_as_float(qa0.x), __uint_as_float(qa0.y), __uint_as_float(qa0.z), __uint_as_float(qa0.w));
+                a1 = make_float4(__uint_as_float(qa1.x), __uint_as_float(qa1.y), __uint_as_float(qa1.z), __uint_as_float(qa1.w));
+                b0 = make_float4(__uint_as_float(qb0.x), __uint_as_float(qb0.y), __uint_as_float(qb0.z), __uint_as_float(qb0.w));
+                b1 = make_float4(__uint_as_float(qb1.x), __uint_as_float(qb1.y), __uint_as_float(qb1.z), __uint_as_float(qb1.w));
               } else {  // L2 round trip, issued before (and hidden behind) the wait for the plane
                 const float4* ap = reinterpret_cast<const float4*>(p.aff_a + (size_t)it.b * c_in + kc * 64 + ch0);
                 const float4* bp = reinterpret_cast<const float4*>(p.aff_b + (size_t)it.b * c_in + kc * 64 + ch0);

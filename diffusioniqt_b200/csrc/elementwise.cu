@@ -233,7 +233,15 @@ __global__ void __launch_bounds__(256, 4) affine_mish_kernel(const T* __restrict
       Vec<T> r;
       r.unpack(raw[u]);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) r.v[i] = mish<kFast>(fmaf(av[i], r.v[i], bv[i]));
+      for (int i = 0; i < VEC; i += 2) {
+        if (kFast) {   // channel pairs per FFMA2 / FMUL2 / FADD2: the same IEEE operations per lane (mish2_fast)
+          const float2 o = mish2_fast(__ffma2_rn(make_float2(av[i], av[i + 1]), make_float2(r.v[i], r.v[i + 1]), make_float2(bv[i], bv[i + 1])));
+          r.v[i] = o.x; r.v[i + 1] = o.y;
+        } else {
+          r.v[i] = mish<kFast>(fmaf(av[i], r.v[i], bv[i]));
+          r.v[i + 1] = mish<kFast>(fmaf(av[i + 1], r.v[i + 1], bv[i + 1]));
+        }
+      }
       r.store(yb + row[u] * ld_y);
     }
   }
@@ -242,7 +250,15 @@ __global__ void __launch_bounds__(256, 4) affine_mish_kernel(const T* __restrict
     const int64_t row = sub_row(sg, voxels, n, v);
     r.load(xb + row * ld_x);
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) r.v[i] = mish<kFast>(fmaf(av[i], r.v[i], bv[i]));
+    for (int i = 0; i < VEC; i += 2) {
+      if (kFast) {
+        const float2 o = mish2_fast(__ffma2_rn(make_float2(av[i], av[i + 1]), make_float2(r.v[i], r.v[i + 1]), make_float2(bv[i], bv[i + 1])));
+        r.v[i] = o.x; r.v[i + 1] = o.y;
+      } else {
+        r.v[i] = mish<kFast>(fmaf(av[i], r.v[i], bv[i]));
+        r.v[i + 1] = mish<kFast>(fmaf(av[i + 1], r.v[i + 1], bv[i + 1]));
+      }
+    }
     r.store(yb + row * ld_y);
   }
 }

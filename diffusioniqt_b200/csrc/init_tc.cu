@@ -345,10 +345,12 @@ __global__ void __launch_bounds__(IT_THREADS, 1) init_conv_tc_kernel(const __gri
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const uint4 b0 = lds_128(bias_a + (uint32_t)(c64 + c32 * 32 + u * 8) * 4), b1 = lds_128(bias_a + (uint32_t)(c64 + c32 * 32 + u * 8 + 4) * 4);
-              uint32_t q0 = pack_bf16x2(__uint_as_float(r[u * 8]) + __uint_as_float(b0.x), __uint_as_float(r[u * 8 + 1]) + __uint_as_float(b0.y));
-              uint32_t q1 = pack_bf16x2(__uint_as_float(r[u * 8 + 2]) + __uint_as_float(b0.z), __uint_as_float(r[u * 8 + 3]) + __uint_as_float(b0.w));
-              uint32_t q2 = pack_bf16x2(__uint_as_float(r[u * 8 + 4]) + __uint_as_float(b1.x), __uint_as_float(r[u * 8 + 5]) + __uint_as_float(b1.y));
-              uint32_t q3 = pack_bf16x2(__uint_as_float(r[u * 8 + 6]) + __uint_as_float(b1.z), __uint_as_float(r[u * 8 + 7]) + __uint_as_float(b1.w));
+              // (channel pairs per FADD2: the same IEEE additions per lane)
+              const float2 s0 = __fadd2_rn(make_float2(__uint_as_float(r[u * 8]), __uint_as_float(r[u * 8 + 1])), make_float2(__uint_as_float(b0.x), __uint_as_float(b0.y)));
+              const float2 s1 = __fadd2_rn(make_float2(__uint_as_float(r[u * 8 + 2]), __uint_as_float(r[u * 8 + 3])), make_float2(__uint_as_float(b0.z), __uint_as_float(b0.w)));
+              const float2 s2 = __fadd2_rn(make_float2(__uint_as_float(r[u * 8 + 4]), __uint_as_float(r[u * 8 + 5])), make_float2(__uint_as_float(b1.x), __uint_as_float(b1.y)));
+              const float2 s3 = __fadd2_rn(make_float2(__uint_as_float(r[u * 8 + 6]), __uint_as_float(r[u * 8 + 7])), make_float2(__uint_as_float(b1.z), __uint_as_float(b1.w)));
+              uint32_t q0 = pack_bf16x2(s0.x, s0.y), q1 = pack_bf16x2(s1.x, s1.y), q2 = pack_bf16x2(s2.x, s2.y), q3 = pack_bf16x2(s3.x, s3.y);
               if (!all_live) {   // warp-uniform; rows outside the volume: zeros, so the statistics may read them
                 if (!live) q0 = q1 = q2 = q3 = 0u;
               }
@@ -368,9 +370,10 @@ __global__ void __launch_bounds__(IT_THREADS, 1) init_conv_tc_kernel(const __gri
               const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int e2 = 0; e2 < 4; ++e2) {
-                const float lo = __uint_as_float(w4[e2] << 16), hi = __uint_as_float(w4[e2] & 0xffff0000u);
-                st_s[g64][2 * e2] += lo; st_q[g64][2 * e2] = fmaf(lo, lo, st_q[g64][2 * e2]);
-                st_s[g64][2 * e2 + 1] += hi; st_q[g64][2 * e2 + 1] = fmaf(hi, hi, st_q[g64][2 * e2 + 1]);
+                const float2 lh = make_float2(__uint_as_float(w4[e2] << 16), __uint_as_float(w4[e2] & 0xffff0000u));
+                const float2 ns = __fadd2_rn(make_float2(st_s[g64][2 * e2], st_s[g64][2 * e2 + 1]), lh);
+                const float2 nq = __ffma2_rn(lh, lh, make_float2(st_q[g64][2 * e2], st_q[g64][2 * e2 + 1]));
+                st_s[g64][2 * e2] = ns.x; st_s[g64][2 * e2 + 1] = ns.y; st_q[g64][2 * e2] = nq.x; st_q[g64][2 * e2 + 1] = nq.y;
               }
             }
           }
