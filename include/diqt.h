@@ -322,7 +322,8 @@ int diqt_init_im2col(const float* const* planes, const int64_t* plane_stride, in
                      void* stream);
 /* init_conv (:1291) as ONE tcgen05 kernel (bf16 output): the im2col rows (K = 27 * c_in <= 64 columns) are built in shared memory, never
  * in global memory; w_packed: bf16 [c_out][64] with column k = tap * c_in + ci, zero padded, 16-byte chunks of every row XOR-swizzled by
- * (row & 7); c_out 64 or 128; d2 a multiple of 16.  partial (may be NULL): channel statistics of the output, one row per CTA,
+ * (row & 7); c_out 64 or 128; d2 a multiple of 16; the input planes 16-byte aligned with strides that are multiples of 4 elements (the
+ * kernel copies them with 16-byte cp.async).  partial (may be NULL): channel statistics of the output, one row per CTA,
  * partial[n][*nblk][c_out][2] with *nblk from diqt_init_conv_tc_blocks; group / tickets: optional grouped sink as in diqt_channel_stats_g. */
 int diqt_init_conv_tc_supported(int c_in, int c_out, int d1, int d2);
 int diqt_init_conv_tc_blocks(int n, int d0, int d1, int* nblk);
