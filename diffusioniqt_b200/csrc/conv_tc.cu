@@ -23,6 +23,7 @@
 // every ~5 cycles here, so the epilogue of a wide tile (128 x 256 with Mish: 4 k instructions per thread) on four warps bounded the
 // pixel-shuffle up-conv at 31 us for 40 MB of traffic (profiles/r5_init_conv.md has the same finding for init_conv): eight warps, the two of a
 // lane quarter splitting the columns.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -592,6 +593,9 @@ static int tc_ksplit_for(const TcParams& p, int* kbper_out) {
   return (kblocks + kbper - 1) / kbper;
 }
 bool conv_tc_prefers_small(const diqt_conv_desc* d) {  // fewer output tiles than half the SMs: the per-tap kernel with split-K wins over the z-march
+  static int env = -1;   // DIQT_TC_SMALL=0: A/B of the z-march kernel (with its fused GroupNorm) on small volumes
+  if (env < 0) { const char* e = getenv("DIQT_TC_SMALL"); env = (e && e[0] == '0') ? 0 : 1; }
+  if (!env) return false;
   if (d->mode != DIQT_CONV_K3 || !conv_tc_supported(d)) return false;
   const int64_t rows = (int64_t)d->n * d->d0 * d->d1 * d->d2;
   const int64_t tiles = (rows + kTileM - 1) / kTileM * (d->c_out / tc_block_n(d));
