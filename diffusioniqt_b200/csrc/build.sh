@@ -20,5 +20,5 @@ for f in elementwise ends init_tc attn attn_tc linattn_tc backward wgrad_tc volu
   OBJS+=("$o")
 done
 for p in "${PIDS[@]:-}"; do [ -n "$p" ] && wait "$p"; done
-"$NVCC" -shared -o "$OUT" "${OBJS[@]}" -lcudart
+"$NVCC" -gencode arch=compute_100a,code=sm_100a -shared -o "$OUT" "${OBJS[@]}" -lcudart   # (the arch on the link line too: no default-arch stub cubin in the library)
 echo "built $OUT"
